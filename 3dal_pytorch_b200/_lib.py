@@ -1,0 +1,59 @@
+"""ctypes binding of libal3d.so (the C ABI declared in include/al3d.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing the import of any model
+module fails with an explicit error telling how to build it (``python -c "import
+__graft_entry__ as g; g.build()"``).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libal3d.so")
+
+_vp, _i, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+
+# name -> argtypes ; every function returns int (0 = ok) unless listed in _RESTYPES
+_SIGNATURES = {
+    "al3d_abi_version": [],
+    "al3d_last_error": [],
+    "al3d_device_supports_tcgen05": [],
+    "al3d_pointwise_first_f32": [_vp, _i64, _i64, _i64, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
+    "al3d_linear_f32": [_vp, _i64, _i64, _i, _vp, _i64, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp],
+    "al3d_mask_compact": [_vp, _vp, _i, _i, _vp, _vp, _vp],
+    "al3d_gather_fg": [_vp, _i64, _i64, _i64, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp],
+    "al3d_parse_heads": [_vp, _i, _vp, _i64] + [_vp] * 8 + [_vp],
+    "al3d_decode_boxes": [_vp] * 6 + [_i64, _i, _vp, _vp, _vp],
+    "al3d_twostage_retransform": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+}
+_RESTYPES = {"al3d_last_error": ctypes.c_char_p}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names include/al3d.h declares (kept in sync by tests/test_abi.py)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libal3d.so is not built (%s missing). Build it with "
+                "`python -c \"import __graft_entry__ as g; g.build()\"`; there is no fallback path." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, args in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        if l.al3d_abi_version() != 1:
+            raise RuntimeError("libal3d.so ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().al3d_last_error()
+        raise RuntimeError("libal3d: %s%s" % (what + ": " if what else "", msg.decode() if msg else "error %d" % rc))

@@ -1,0 +1,76 @@
+"""Drop-in replacement for the reference's dynamic-object model (tools/dynamic_model.py).
+
+DynamicModel keeps the reference's constructor, attributes (``r``, ``s``, ``n_classes``,
+``n_channel``), sub-module / ``state_dict`` layout and ``forward(pts, box, bbox_gt) -> dict``
+contract (tools/dynamic_model.py:109-155): 4-channel segmentation net, foreground gather of
+5*512 points, point embedding, the 101-step box-trajectory encoder and the FC box head.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine, ops, spec
+from .static_model import _AutoLabelBase, _ParamBlock
+
+NUM_HEADING_BIN = spec.NUM_HEADING_BIN
+NUM_SIZE_CLUSTER = spec.NUM_SIZE_CLUSTER
+NUM_OBJECT_POINT = spec.NUM_OBJECT_POINT
+NUM_POINT = spec.NUM_POINT_DYNAMIC
+NUM_FRAME = spec.NUM_FRAME
+MEAN_SIZE_ARR = np.array(spec.MEAN_SIZE_ARR)
+
+
+class PointNetInstanceSeg(_ParamBlock):
+    def __init__(self, n_classes=3, n_channel=4):
+        super().__init__(spec.seg_layers(n_channel), dropout_before="dconv5")
+        self.n_channel = n_channel
+
+
+class PointEmbedding(_ParamBlock):
+    def __init__(self, n_classes=3):
+        super().__init__(spec.point_emb_layers())
+
+
+class BoxEmbedding(_ParamBlock):
+    def __init__(self, n_classes=3):
+        super().__init__(spec.box_emb_layers())
+
+
+class PointNetEstimation(_ParamBlock):
+    def __init__(self, n_classes=3):
+        super().__init__(spec.dynamic_est_layers(n_classes))
+
+
+class DynamicModel(_AutoLabelBase):
+    def __init__(self, n_classes=3, n_channel=4):
+        super().__init__()
+        self.r = 2
+        self.s = 50
+        self.n_classes = n_classes
+        self.n_channel = n_channel
+        self.ins_seg = PointNetInstanceSeg(n_classes=n_classes, n_channel=n_channel)
+        self.point_emb = PointEmbedding(n_classes=n_classes)
+        self.box_emb = BoxEmbedding(n_classes=n_classes)
+        self.box_est = PointNetEstimation(n_classes=n_classes)
+        self._init_common()
+
+    @torch.no_grad()
+    def forward(self, pts, box, bbox_gt=None):
+        self._check_inputs(pts, self.n_channel)
+        if box.dim() != 3 or box.shape[1] != 8:
+            raise ValueError("box must be (bs,8,steps), got %s" % (tuple(box.shape),))
+        logits = self._seg(pts)
+        obj, mask, _ = engine.mask_and_gather(pts[:, :4, :], logits, NUM_FRAME * NUM_OBJECT_POINT, self.gather_policy)
+        fwp, gp = self._trunk("point_emb", self.point_emb, obj)
+        pe = engine.fc_chain(fwp, gp, ("fc1", "fc2"))
+        fwb, gb = self._trunk("box_emb", self.box_emb, box.float())
+        be = engine.fc_chain(fwb, gb, ("fc1", "fc2"))
+        fwe = self._packs.get("box_est_f32", self.box_est, lambda: engine.fold_block(self.box_est, self.box_est._table))
+        box_pred = engine.fc_chain(fwe, torch.cat([pe, be], dim=1), ("fc1", "fc2", "fc3"))
+        out = ops.parse_heads(box_pred)
+        return {
+            "logits": logits, "mask": mask, "center": out["center"], "heading_scores": out["heading_scores"],
+            "heading_residuals_normalized": out["heading_residuals_normalized"],
+            "heading_residuals": out["heading_residuals"], "size_scores": out["size_scores"],
+            "size_residuals_normalized": out["size_residuals_normalized"], "size_residuals": out["size_residuals"],
+        }

@@ -1,0 +1,145 @@
+"""Forward engine behind the drop-in modules: BatchNorm folding / weight packing and the kernel
+sequences of the three model forwards.
+
+Reference forward being replaced: StaticModelOneBoxEst.forward tools/static_model.py:117-146,
+StaticModelTwoBoxEst.forward :158-239, DynamicModel.forward tools/dynamic_model.py:121-155.
+
+Precision modes
+  "fp32"  every MLP layer runs in the fp32 SIMT kernels (al3d_linear_f32): matches the reference
+          to ~1e-6 relative; used for tight parity.
+  "bf16"  the shared point-wise MLPs run on tcgen05 tensor cores (bf16 operands, fp32 accumulation
+          in TMEM); the FC heads, the global-feature GEMV and the last 128->2 segmentation layer
+          stay fp32.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import ops, spec
+
+DEFAULT_PRECISION = os.environ.get("AL3D_PRECISION", "fp32")
+FP32_SCRATCH_BYTES = int(os.environ.get("AL3D_FP32_SCRATCH_BYTES", str(1 << 30)))
+
+
+def fold_block(module, table):
+    """BN-fold every layer of one sub-network: returns {layer: (W' (cout,cin) f32, b' (cout,) f32)}.
+    W' = a*W, b' = a*(b - mean) + beta with a = gamma / sqrt(var + eps) (eval-mode BatchNorm1d)."""
+    out = {}
+    for lname, bn, cin, cout, kind in table:
+        layer = getattr(module, lname)
+        w = layer.weight.detach().reshape(cout, cin).float()
+        b = layer.bias.detach().float()
+        if bn is not None:
+            m = getattr(module, bn)
+            a = m.weight.detach().float() / torch.sqrt(m.running_var.detach().float() + m.eps)
+            w = w * a[:, None]
+            b = a * (b - m.running_mean.detach().float()) + m.bias.detach().float()
+        out[lname] = (w.contiguous(), b.contiguous())
+    return out
+
+
+def params_version(module):
+    """Changes whenever a parameter/buffer is modified in place or replaced (load_state_dict,
+    optimizer.step(), .cuda())."""
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+class PackCache:
+    """Caches folded (and, for bf16, tensor-core-packed) weights per sub-network."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, key, module, builder):
+        ver = params_version(module)
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, builder())
+            self._cache[key] = hit
+        return hit[1]
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32 pipelines
+# ------------------------------------------------------------------------------------------------
+
+def seg_forward_fp32(fw, pts):
+    """fw: folded seg weights; pts (bs,C,n) any strides -> logits (bs,n,2) f32 contiguous."""
+    bs, C, n = pts.shape
+    dev = pts.device
+    logits = torch.empty((bs, n, 2), device=dev, dtype=torch.float32)
+    per_obj = n * (64 + 64 + 64 + 128 + 512 + 256 + 128 + 128) * 4
+    chunk = max(1, min(bs, FP32_SCRATCH_BYTES // max(per_obj, 1)))
+    w_d1 = fw["dconv1"][0]
+    for b0 in range(0, bs, chunk):
+        x = pts[b0:b0 + chunk]
+        cb = x.shape[0]
+        o1 = ops.pointwise_first(x, *fw["conv1"])
+        o2 = ops.linear(o1, *fw["conv2"])
+        o3 = ops.linear(o2, *fw["conv3"])
+        o4 = ops.linear(o3, *fw["conv4"])
+        g = torch.zeros((cb, 1024), device=dev, dtype=torch.float32)
+        ops.linear(o4, *fw["conv5"], rows_per_group=n, max_out=g)
+        del o1, o3, o4
+        # dconv1 on cat[out2, global]: the 1024-wide half is a per-object bias
+        gb = ops.linear(g, w_d1[:, 64:], fw["dconv1"][1], act=ops.ACT_NONE, K=1024)
+        d = ops.linear(o2, w_d1, None, rowbias=gb, rows_per_group=n, K=64)
+        d = ops.linear(d, *fw["dconv2"])
+        d = ops.linear(d, *fw["dconv3"])
+        d = ops.linear(d, *fw["dconv4"])
+        lg = ops.linear(d, *fw["dconv5"], act=ops.ACT_NONE)
+        logits[b0:b0 + cb] = lg.view(cb, n, 2)
+    return logits
+
+
+def trunk_maxpool_fp32(fw, x):
+    """conv1-4 + max over points: x (bs,C,m) -> (bs,512)."""
+    bs, C, m = x.shape
+    o = ops.pointwise_first(x, *fw["conv1"])
+    o = ops.linear(o, *fw["conv2"])
+    o = ops.linear(o, *fw["conv3"])
+    g = torch.zeros((bs, fw["conv4"][0].shape[0]), device=x.device, dtype=torch.float32)
+    ops.linear(o, *fw["conv4"], rows_per_group=m, max_out=g)
+    return g
+
+
+def fc_chain(fw, x, names):
+    """FC layers: ReLU on all but a layer called fc3 (the raw 39-wide head)."""
+    for nme in names:
+        x = ops.linear(x, *fw[nme], act=ops.ACT_NONE if nme == "fc3" else ops.ACT_RELU)
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# mask + gather
+# ------------------------------------------------------------------------------------------------
+
+def choice_table_numpy_legacy(counts_host, n_pts):
+    """Replays the reference's global-RNG calls in batch order (tools/static_model.py:36-45) and
+    returns the (bs,n_pts) int32 table of positions into each object's ascending foreground list."""
+    table = np.zeros((len(counts_host), n_pts), dtype=np.int32)
+    for i, L in enumerate(counts_host):
+        L = int(L)
+        if L <= 0:
+            continue
+        if L >= n_pts:
+            choice = np.random.choice(L, n_pts, replace=False)
+        else:
+            choice = np.concatenate((np.arange(L), np.random.choice(L, n_pts - L, replace=True)))
+        np.random.shuffle(choice)
+        table[i] = choice
+    return table
+
+
+def mask_and_gather(pts, logits, n_pts, policy, want_indices=False):
+    mask, pos, count = ops.mask_compact(logits=logits)
+    choice = None
+    if policy == "numpy_legacy":
+        # the one documented host round-trip: bs counts down, a (bs,n_pts) table up
+        table = choice_table_numpy_legacy(count.cpu().numpy(), n_pts)
+        choice = torch.from_numpy(table).to(pts.device, non_blocking=True)
+    elif policy != "strided":
+        raise ValueError("gather_policy must be 'strided' or 'numpy_legacy'")
+    out = ops.gather_fg(pts, pos, count, n_pts, choice=choice, want_indices=want_indices)
+    return out, mask, count

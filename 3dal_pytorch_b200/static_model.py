@@ -1,0 +1,161 @@
+"""Drop-in replacements for the reference's static auto-label models (tools/static_model.py).
+
+Same class names, constructor arguments, attributes (``name``, ``n_classes``, ``n_channel``),
+sub-module / ``state_dict`` layout and ``forward(pts, init_box, bbox_gt) -> dict`` contract as
+StaticModelOneBoxEst (tools/static_model.py:108-146) and StaticModelTwoBoxEst (:148-239), so the
+reference's static_eval.py / static_train.py can import them unchanged.  The
+forward runs entirely in libal3d.so (sm_100a CUDA); the nn.Conv1d / nn.BatchNorm1d / nn.Linear
+children only hold parameters (identical default initialisation and key names) and are never called.
+
+Extra, non-reference attributes: ``precision`` ("fp32" | "bf16") and ``gather_policy``
+("strided" device rule | "numpy_legacy" reference RNG replay).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine, ops, spec
+
+NUM_HEADING_BIN = spec.NUM_HEADING_BIN
+NUM_SIZE_CLUSTER = spec.NUM_SIZE_CLUSTER
+NUM_OBJECT_POINT = spec.NUM_OBJECT_POINT
+NUM_POINT = spec.NUM_POINT_STATIC
+MEAN_SIZE_ARR = np.array(spec.MEAN_SIZE_ARR)
+
+
+class _ParamBlock(nn.Module):
+    """A sub-network that only owns parameters, created from a spec table in the reference's
+    registration order (so ``torch.manual_seed(s); Model()`` draws the same initial weights)."""
+
+    def __init__(self, table, dropout_before=None):
+        super().__init__()
+        self._table = table
+        for lname, bn, cin, cout, kind in table:
+            if dropout_before == lname:
+                self.dropout = nn.Dropout(p=0.5)
+            setattr(self, lname, nn.Conv1d(cin, cout, 1) if kind == "conv" else nn.Linear(cin, cout))
+        for lname, bn, cin, cout, kind in table:
+            if bn is not None:
+                setattr(self, bn, nn.BatchNorm1d(cout))
+
+    def forward(self, *a, **k):
+        raise RuntimeError("parameter container only; the forward runs in libal3d.so via the parent model")
+
+
+class PointNetInstanceSeg(_ParamBlock):
+    def __init__(self, n_classes=3, n_channel=3):
+        super().__init__(spec.seg_layers(n_channel), dropout_before="dconv5")
+        self.n_channel = n_channel
+
+
+class PointNetEstimation(_ParamBlock):
+    def __init__(self, n_classes=3):
+        super().__init__(spec.static_est_layers())
+
+
+class _AutoLabelBase(nn.Module):
+    precision = engine.DEFAULT_PRECISION
+    gather_policy = "strided"
+
+    def _init_common(self):
+        self._packs = engine.PackCache()
+
+    def _check_inputs(self, pts, C):
+        if self.training:
+            raise NotImplementedError(
+                "training-mode forward (batch-statistics BatchNorm, dropout, backward) is not built yet; "
+                "call .eval() -- see DESIGN.md 'out of scope this round'")
+        if not pts.is_cuda:
+            raise RuntimeError("the B200 build has no CPU path: inputs must be CUDA tensors")
+        if pts.dim() != 3 or pts.shape[1] != C:
+            raise ValueError("pts must be (bs,%d,n), got %s" % (C, tuple(pts.shape)))
+        if pts.dtype != torch.float32:
+            raise TypeError("pts must be float32")
+
+    def _seg(self, pts):
+        fw = self._packs.get("seg_f32", self.ins_seg, lambda: engine.fold_block(self.ins_seg, self.ins_seg._table))
+        if self.precision == "fp32":
+            return engine.seg_forward_fp32(fw, pts)
+        from . import engine_bf16
+        pk = self._packs.get("seg_bf16", self.ins_seg, lambda: engine_bf16.pack_seg(fw, self.ins_seg.n_channel))
+        return engine_bf16.seg_forward(pk, fw, pts)
+
+    def _trunk(self, key, module, x):
+        fw = self._packs.get(key + "_f32", module, lambda: engine.fold_block(module, module._table))
+        if self.precision == "fp32":
+            return fw, engine.trunk_maxpool_fp32(fw, x)
+        from . import engine_bf16
+        pk = self._packs.get(key + "_bf16", module, lambda: engine_bf16.pack_trunk(fw))
+        return fw, engine_bf16.trunk_maxpool(pk, fw, x)
+
+
+class StaticModelOneBoxEst(_AutoLabelBase):
+    def __init__(self, n_classes=3, n_channel=3):
+        super().__init__()
+        self.name = "one_box_est"
+        self.n_classes = n_classes
+        self.n_channel = n_channel
+        self.ins_seg = PointNetInstanceSeg(n_classes=n_classes, n_channel=n_channel)
+        self.box_est = PointNetEstimation(n_classes=n_classes)
+        self._init_common()
+
+    @torch.no_grad()
+    def forward(self, pts, init_box, bbox_gt=None):
+        self._check_inputs(pts, self.n_channel)
+        logits = self._seg(pts)
+        obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, self.gather_policy)
+        fw, g = self._trunk("box_est", self.box_est, obj)
+        box_pred = engine.fc_chain(fw, g, ("fc1", "fc2", "fc3"))
+        out = ops.parse_heads(box_pred, add=init_box.float())
+        return {
+            "logits": logits, "mask": mask, "center_boxnet": out["center_boxnet"],
+            "heading_scores": out["heading_scores"],
+            "heading_residuals_normalized": out["heading_residuals_normalized"],
+            "heading_residuals": out["heading_residuals"], "size_scores": out["size_scores"],
+            "size_residuals_normalized": out["size_residuals_normalized"],
+            "size_residuals": out["size_residuals"], "center": out["center"],
+        }
+
+
+class StaticModelTwoBoxEst(_AutoLabelBase):
+    def __init__(self, n_classes=3, n_channel=3):
+        super().__init__()
+        self.name = "two_box_est"
+        self.n_classes = n_classes
+        self.n_channel = n_channel
+        self.ins_seg = PointNetInstanceSeg(n_classes=n_classes, n_channel=n_channel)
+        self.box_est_one = PointNetEstimation(n_classes=n_classes)
+        self.box_est_two = PointNetEstimation(n_classes=n_classes)
+        self._init_common()
+
+    @torch.no_grad()
+    def forward(self, pts, init_box, bbox_gt):
+        self._check_inputs(pts, self.n_channel)
+        init_box = init_box.float().contiguous()
+        bbox_gt = bbox_gt.float().contiguous()
+        logits = self._seg(pts)
+        obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, self.gather_policy)
+        fw1, g1 = self._trunk("box_est_one", self.box_est_one, obj)
+        one = ops.parse_heads(engine.fc_chain(fw1, g1, ("fc1", "fc2", "fc3")), add=init_box)
+        box_one, _ = ops.decode_boxes(one["center"], one["heading_scores"], one["heading_residuals"],
+                                      one["size_scores"], one["size_residuals"], base_heading=init_box[:, 6])
+        obj2, cls2, res2 = ops.twostage_retransform(obj, init_box, box_one, bbox_gt)
+        fw2, g2 = self._trunk("box_est_two", self.box_est_two, obj2)
+        two = ops.parse_heads(engine.fc_chain(fw2, g2, ("fc1", "fc2", "fc3")), add=one["center"])
+        return {
+            "logits": logits, "mask": mask,
+            "heading_scores_one": one["heading_scores"],
+            "heading_residuals_normalized_one": one["heading_residuals_normalized"],
+            "heading_residuals_one": one["heading_residuals"], "size_scores_one": one["size_scores"],
+            "size_residuals_normalized_one": one["size_residuals_normalized"],
+            "size_residuals_one": one["size_residuals"], "center_one": one["center"], "box_one": box_one,
+            "heading_scores_two": two["heading_scores"],
+            "heading_residuals_normalized_two": two["heading_residuals_normalized"],
+            "heading_residuals_two": two["heading_residuals"], "size_scores_two": two["size_scores"],
+            "size_residuals_normalized_two": two["size_residuals_normalized"],
+            "size_residuals_two": two["size_residuals"], "center_two": two["center"],
+            "heading_class_label_two": cls2, "heading_residuals_label_two": res2,
+            "center": two["center"], "heading_scores": two["heading_scores"],
+            "heading_residuals": two["heading_residuals"], "size_scores": two["size_scores"],
+            "size_residuals": two["size_residuals"],
+        }

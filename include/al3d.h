@@ -1,0 +1,110 @@
+/*
+ * al3d.h -- C ABI of libal3d.so, the B200 (sm_100a) implementation of the 3DAL object-centric
+ * auto-labeling hot path (Frustum-PointNet static / dynamic box refinement + points-in-box crop).
+ *
+ * Conventions:
+ *   - every function returns 0 on success, non-zero on failure; al3d_last_error() returns the text
+ *     of the last failure on the calling thread.  Nothing throws across this boundary.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.  The library allocates
+ *     nothing: inputs, outputs, packed weights and scratch are owned by the caller (PyTorch).
+ *   - everything is stream-ordered on `stream` (a cudaStream_t passed as void*); there are no
+ *     hidden synchronisations and no mutable global state besides the per-thread error string.
+ *   - tensors are dense row-major unless strides are passed (in ELEMENTS).
+ *
+ * Each entry point names the reference code (jacky121298/3DAL_PyTorch, file:line) it replaces.
+ * The reference-side binding (ctypes) is shown in INTEGRATION.md and implemented in
+ * 3dal_pytorch_b200/_lib.py.
+ */
+#ifndef AL3D_H_
+#define AL3D_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AL3D_ABI_VERSION 1
+
+/* activation flags for al3d_linear_f32 */
+#define AL3D_ACT_NONE 0
+#define AL3D_ACT_RELU 1
+
+/* gather index policies (al3d_gather_fg) */
+#define AL3D_GATHER_STRIDED 0   /* device rule: slot j <- pos[(j*L)/n_pts] (L>=n_pts) or pos[j%L]   */
+#define AL3D_GATHER_TABLE   1   /* caller-provided (bs,n_pts) int32 choice table (numpy RNG replay) */
+
+int         al3d_abi_version(void);
+const char *al3d_last_error(void);
+/* 1 if the current device is sm_100 (B200) and the tcgen05 kernels can run, else 0. */
+int         al3d_device_supports_tcgen05(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Shared-MLP building blocks, fp32 SIMT ("exact" precision mode).
+ * Replaces nn.Conv1d(k=1)/nn.Linear + eval BatchNorm1d (folded by the caller) + ReLU
+ * (tools/static_model.py:279-283,289-294,330-338; tools/dynamic_model.py:241-248,278-285,307-311).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* First layer on a strided (bs,C,n) point tensor: y[(b*n+p), o] = act(sum_c x[b,c,p]*w[o,c] + bias[o]).
+ * x strides in elements; C <= 8.  y is (bs*n, cout) row-major. */
+int al3d_pointwise_first_f32(const float *x, int64_t sb, int64_t sc, int64_t sp, int bs, int C, int n,
+                             const float *w, const float *bias, int cout, int act, float *y, void *stream);
+
+/* y[m, o] = act(sum_k a[m*lda + k] * w[o*ldw + k] + bias[o] + rowbias[(m / rows_per_group)*cout + o]).
+ * bias and rowbias may be NULL.  If y_max != NULL the (M,cout) result is NOT stored; instead
+ * y_max[(m / rows_per_group)*cout + o] = max(existing, result) is accumulated with an integer
+ * atomicMax, which requires act == RELU and y_max pre-filled with zeros (max-pool over the points
+ * of an object, tools/static_model.py:284,334). */
+int al3d_linear_f32(const float *a, int64_t lda, int64_t M, int K, const float *w, int64_t ldw,
+                    const float *bias, const float *rowbias, int64_t rows_per_group, int cout, int act,
+                    float *y, int64_t ldy, float *y_max, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Foreground mask, ordered compaction and gather (integer / indexing work, bit-exact).
+ * Replaces point_cloud_masking + gather_object_pts (tools/static_model.py:23-62,
+ * tools/dynamic_model.py:24-63).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* mask[b,p] = logits[b,p,0] < logits[b,p,1] (strict, NaN -> 0) when logits != NULL, otherwise
+ * mask is read as given.  pos[b, 0:count[b]] = ascending indices p with mask set. */
+int al3d_mask_compact(const float *logits, uint8_t *mask, int bs, int n, int32_t *pos, int32_t *count, void *stream);
+
+/* out[b,c,j] = x[b,c,pos[b,sel(j)]] for j < n_pts (zeros when count[b]==0); indices[b,j] likewise
+ * (may be NULL).  policy AL3D_GATHER_STRIDED computes sel on the device, AL3D_GATHER_TABLE reads
+ * choice[b,j].  x strides in elements. */
+int al3d_gather_fg(const float *x, int64_t sb, int64_t sc, int64_t sp, int bs, int C, int n,
+                   const int32_t *pos, const int32_t *count, int policy, const int32_t *choice, int n_pts,
+                   float *out, int64_t *indices, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Head parsing, decode and the two-stage canonical re-transform.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* parse_output_to_tensors (tools/static_model.py:64-96) + the centre residual add (:132,174,211).
+ * box_pred (bs,39).  add (bs, add_stride) may be NULL; centre_out = box_pred[:, :3] + add[:, :3].
+ * Any output pointer may be NULL. */
+int al3d_parse_heads(const float *box_pred, int bs, const float *add, int64_t add_stride,
+                     float *center_boxnet, float *center, float *heading_scores, float *heading_res_norm,
+                     float *heading_res, float *size_scores, float *size_res_norm, float *size_res, void *stream);
+
+/* Box decode shared by the two-box forward (tools/static_model.py:178-190) and the eval loops
+ * (tools/static_eval.py:270-288, tools/dynamic_eval.py:227-242): argmax of the heading / size
+ * scores, class2angle (+wrap) / class2size in float64 (tools/utils.py:69-79), plus base heading.
+ * box_out (bs,7) f32 = [center, size, heading]; cls_out (bs,2) int32 = [heading bin, size cluster]
+ * (may be NULL). */
+int al3d_decode_boxes(const float *center, const float *heading_scores, const float *heading_res,
+                      const float *size_scores, const float *size_res, const float *base_heading,
+                      int64_t base_stride, int bs, float *box_out, int32_t *cls_out, void *stream);
+
+/* Two-stage re-centering (tools/static_model.py:195-205): P <- Rz(-h1) (Rz(h0) P + c0 - c1) on the
+ * gathered (bs,3,m) points, and the head-two heading label angle2class(gt_heading - h1)
+ * (tools/utils.py:53-60 evaluated in f32 like the reference's 0-dim tensors). */
+int al3d_twostage_retransform(const float *obj_pts, int bs, int m, const float *init_box, const float *box_one,
+                              const float *bbox_gt, float *obj_pts_two, int64_t *heading_cls_label,
+                              float *heading_res_label, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AL3D_H_ */
