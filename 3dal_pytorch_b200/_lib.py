@@ -24,6 +24,10 @@ _SIGNATURES = {
     "al3d_parse_heads": [_vp, _i, _vp, _i64] + [_vp] * 8 + [_vp],
     "al3d_decode_boxes": [_vp] * 6 + [_i64, _i, _vp, _vp, _vp],
     "al3d_twostage_retransform": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "al3d_chain_maxpool_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
+    "al3d_seg_pass2_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp],
+    "al3d_umma_selftest": [_vp, _vp, _i, _i, _vp, _i, _vp],
+    "al3d_tc_abort_code": [_vp],
 }
 _RESTYPES = {"al3d_last_error": ctypes.c_char_p}
 

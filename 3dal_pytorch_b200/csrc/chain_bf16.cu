@@ -1,0 +1,698 @@
+// Tensor-core (tcgen05 / TMEM) kernels for the shared point-wise MLPs, bf16 operands, fp32 accumulate.
+//
+//   chain_max_kernel   first layer (tiny K, CUDA cores) -> 2-3 chained MMA layers whose activations
+//                      never leave shared memory -> last layer computed transposed (channels on TMEM
+//                      lanes, points on columns) so the max over points is a per-thread reduction.
+//                      Serves ins_seg conv1-5 + max (tools/static_model.py:279-284), the static box
+//                      head trunk (:330-334), PointEmbedding and BoxEmbedding trunks
+//                      (tools/dynamic_model.py:241-245, 278-282).
+//   seg_pass2_kernel   conv1-2 recomputed, dconv1 (+ per-object global-feature bias) pipelined in
+//                      128-channel chunks into dconv2's accumulation, dconv3, dconv4, and the 128->2
+//                      logits + mask in the last epilogue (tools/static_model.py:286-295, :59).
+//
+// Both are persistent, warp-specialised: warp 0 streams packed weight blocks with cp.async.bulk into a
+// ring, warp 1 (one thread) issues tcgen05.mma, warps 2-5 own the 128 TMEM lanes and run every
+// epilogue.  BatchNorm is folded into the weights by the host; ReLU and bias are applied in the epilogue.
+#include "common.cuh"
+#include "umma.cuh"
+#include "../../include/al3d.h"
+
+namespace al3d {
+using namespace umma;
+
+constexpr int kTile = 128;                 // points per tile == TMEM lanes
+constexpr int kStageBytes = 16384;         // one weight block: 128 rows x 64 K bf16
+constexpr int kPlane = kTile * 16;         // bytes of one activation K-plane (128 rows x 16 B)
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ int epi_row() { return ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31); }
+
+// bias + ReLU + bf16 pack of 32 accumulator columns -> four 16-byte plane rows
+__device__ __forceinline__ void store_act32(uint8_t *buf, int plane0, int row, const uint32_t (&v)[32], const float *bias)
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float a = fmaxf(__uint_as_float(v[j * 8 + 2 * i]) + bias[j * 8 + 2 * i], 0.f);
+            const float b = fmaxf(__uint_as_float(v[j * 8 + 2 * i + 1]) + bias[j * 8 + 2 * i + 1], 0.f);
+            o[i] = pack_bf16x2(a, b);
+        }
+        *reinterpret_cast<uint4 *>(buf + (plane0 + j) * kPlane + row * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// First layer on CUDA cores: x[c] (c < c_in) -> w0 outputs, bf16, into the KP buffer.
+__device__ __forceinline__ void first_layer(uint8_t *buf, int row, const float *xv, int c_in, int w0,
+                                            const float *sw, const float *sb)
+{
+    for (int ch = 0; ch < w0; ch += 8) {
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float a = sb[ch + 2 * i], b = sb[ch + 2 * i + 1];
+            const float *wa = sw + (ch + 2 * i) * 8, *wb = wa + 8;     // weights padded to 8 inputs per row
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                a = fmaf(xv[c], wa[c], a);
+                b = fmaf(xv[c], wb[c], b);
+            }
+            o[i] = pack_bf16x2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+        }
+        *reinterpret_cast<uint4 *>(buf + (ch >> 3) * kPlane + row * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    (void)c_in;
+}
+
+// ================================================================================================
+// UMMA self-test: D(128 x N) = A(128 x K) * B(N x K)^T from KP-packed bf16 operands.
+// ================================================================================================
+__global__ void __launch_bounds__(128)
+umma_selftest_kernel(const uint8_t *__restrict__ a_kp, const uint8_t *__restrict__ b_kp, int N, int K, float *__restrict__ d, int swap)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *sa = smem;
+    uint8_t *sb = smem + (size_t)128 * K * 2;
+    const int a_bytes = 128 * K * 2, b_bytes = N * K * 2;
+    for (int i = threadIdx.x * 16; i < a_bytes; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(sa + i) = *reinterpret_cast<const uint4 *>(a_kp + i);
+    for (int i = threadIdx.x * 16; i < b_bytes; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(sb + i) = *reinterpret_cast<const uint4 *>(b_kp + i);
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc<256>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            const uint64_t da = make_desc(smem_u32(sa) + (k0 / 8) * 128 * 16, 128, swap != 0);
+            const uint64_t db = make_desc(smem_u32(sb) + (k0 / 8) * N * 16, N, swap != 0);
+            mma_bf16(tmem, da, db, idesc, k0 > 0 ? 1u : 0u);
+        }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0, 0xE001);
+    tc_fence_after();
+    const int row = threadIdx.x;       // warps 0..3 <-> lane quarters 0..3
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(row & ~31) << 16) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[row * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<256>(tmem);
+}
+
+// ================================================================================================
+// chain_max_kernel
+// ================================================================================================
+struct ChainParams {
+    const float *x; int64_t sb, sc, sp; int bs, n;       // input (bs, c_in, n), strides in elements
+    int c_in, w0, n_mid, mid[3], last;
+    const float *w0_w, *w0_b, *mid_b, *last_b;           // fp32: (w0, 8) zero-padded rows, (w0), concat(mid), (last)
+    const uint8_t *wstream;                              // packed bf16 blocks, 16 KB slots, consumption order
+    float *out;                                          // (bs, last) fp32, zero-initialised; max-pooled with atomicMax
+    int splits;                                          // work items per object
+    int n_items;
+};
+
+constexpr int kChainStages = 6;
+struct ChainSmem {
+    uint8_t bufA[65536];
+    uint8_t bufB[32768];
+    uint8_t wring[kChainStages][kStageBytes];
+    float w0_w[128 * 8];
+    float w0_b[128];
+    float mid_b[512];
+    uint64_t w_full[kChainStages], w_empty[kChainStages];
+    uint64_t act_ready, acc_ready;
+    uint64_t last_full[2], last_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ int chain_in_width(const ChainParams &p, int l) { return l == 0 ? p.w0 : p.mid[l - 1]; }
+
+__global__ void __launch_bounds__(kThreads, 1)
+chain_max_kernel(const ChainParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    ChainSmem &s = *reinterpret_cast<ChainSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < p.w0 * 8; i += kThreads) s.w0_w[i] = p.w0_w[i];
+    for (int i = threadIdx.x; i < p.w0; i += kThreads) s.w0_b[i] = p.w0_b[i];
+    {
+        int tot = 0;
+        for (int l = 0; l < p.n_mid; ++l) tot += p.mid[l];
+        for (int i = threadIdx.x; i < tot; i += kThreads) s.mid_b[i] = p.mid_b[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kChainStages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+        mbar_init(&s.act_ready, kTile);
+        mbar_init(&s.acc_ready, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.last_full[i], 1); mbar_init(&s.last_empty[i], kTile); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&s.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    const int tiles_per_obj = (p.n + kTile - 1) / kTile;
+    const int n_last_chunks = p.last / 128;
+    const int k_last = p.mid[p.n_mid - 1];
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ weight producer (one thread)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int sp_i = item % p.splits;
+                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+                for (int t = t0; t < t1; ++t) {
+                    int blk = 0;
+                    for (int l = 0; l <= p.n_mid; ++l) {
+                        const int K = (l < p.n_mid) ? chain_in_width(p, l) : k_last;
+                        const int N = (l < p.n_mid) ? p.mid[l] : p.last;
+                        const int rows = N < 128 ? N : 128;
+                        const int nblk = (N / rows) * (K / 64);
+                        for (int i = 0; i < nblk; ++i, ++blk) {
+                            if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0xC100 + stage)) goto done;
+                            const uint32_t bytes = rows * 64 * 2;
+                            mbar_arrive_expect_tx(&s.w_full[stage], bytes);
+                            bulk_g2s(s.wring[stage], p.wstream + (size_t)blk * kStageBytes, bytes, &s.w_full[stage]);
+                            if (++stage == kChainStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            int stage = 0; uint32_t wphase = 0, act_phase = 0, le_phase[2] = {0, 0};
+            const uint32_t aA = smem_u32(s.bufA), aB = smem_u32(s.bufB);
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int sp_i = item % p.splits;
+                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+                for (int t = t0; t < t1; ++t) {
+                    // mid layers: D[points x channels]; input buffer alternates A, B, A, ...
+                    for (int l = 0; l < p.n_mid; ++l) {
+                        const int K = chain_in_width(p, l), N = p.mid[l];
+                        const int rows = N < 128 ? N : 128;
+                        const uint32_t in_addr = (l & 1) ? aB : aA;
+                        if (!mbar_wait(&s.act_ready, act_phase, 0xC200 + l)) goto done;
+                        act_phase ^= 1;
+                        tc_fence_after();
+                        const uint32_t idesc = make_idesc_bf16(128, rows);
+                        for (int nc = 0; nc < N / rows; ++nc)
+                            for (int kb = 0; kb < K / 64; ++kb) {
+                                if (!mbar_wait(&s.w_full[stage], wphase, 0xC300 + stage)) goto done;
+                                tc_fence_after();
+                                mma_block_k64(tmem + nc * 128, in_addr + kb * 8 * kPlane, 128, smem_u32(s.wring[stage]), rows, idesc, kb > 0);
+                                mma_commit(&s.w_empty[stage]);
+                                if (++stage == kChainStages) { stage = 0; wphase ^= 1; }
+                            }
+                        mma_commit(&s.acc_ready);
+                    }
+                    // last layer, transposed: D^T[channels x points], double-buffered in TMEM cols 256..511
+                    {
+                        const uint32_t in_addr = (p.n_mid & 1) ? aB : aA;
+                        if (!mbar_wait(&s.act_ready, act_phase, 0xC2F0)) goto done;
+                        act_phase ^= 1;
+                        tc_fence_after();
+                        const uint32_t idesc = make_idesc_bf16(128, 128);
+                        for (int cc = 0; cc < n_last_chunks; ++cc) {
+                            const int b = cc & 1;
+                            if (!mbar_wait(&s.last_empty[b], le_phase[b] ^ 1, 0xC400 + b)) goto done;
+                            le_phase[b] ^= 1;
+                            tc_fence_after();
+                            for (int kb = 0; kb < k_last / 64; ++kb) {
+                                if (!mbar_wait(&s.w_full[stage], wphase, 0xC500 + stage)) goto done;
+                                tc_fence_after();
+                                mma_block_k64(tmem + 256 + b * 128, smem_u32(s.wring[stage]), 128, in_addr + kb * 8 * kPlane, 128, idesc, kb > 0);
+                                mma_commit(&s.w_empty[stage]);
+                                if (++stage == kChainStages) { stage = 0; wphase ^= 1; }
+                            }
+                            mma_commit(&s.last_full[b]);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (128 threads)
+        const int row = epi_row();
+        const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
+        uint32_t acc_phase = 0, lf_phase[2] = {0, 0};
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int b = item / p.splits, sp_i = item % p.splits;
+            const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+            float rmax[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
+            for (int t = t0; t < t1; ++t) {
+                // ---- first layer (rows past the end of the object replicate its last point: the
+                //      max-pool is idempotent under duplicates)
+                {
+                    int pidx = t * kTile + row;
+                    if (pidx > p.n - 1) pidx = p.n - 1;
+                    const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
+                    float xv[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+                    first_layer(s.bufA, row, xv, p.c_in, p.w0, s.w0_w, s.w0_b);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&s.act_ready);
+                }
+                // ---- mid layers
+                int boff = 0;
+                for (int l = 0; l < p.n_mid; ++l) {
+                    const int N = p.mid[l];
+                    uint8_t *outb = (l & 1) ? s.bufA : s.bufB;
+                    if (!mbar_wait(&s.acc_ready, acc_phase, 0xD100 + l)) goto done;
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                    for (int c0 = 0; c0 < N; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem + lane_addr + c0, v);
+                        tmem_ld_wait();
+                        store_act32(outb, c0 >> 3, row, v, s.mid_b + boff + c0);
+                    }
+                    boff += N;
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    mbar_arrive(&s.act_ready);
+                }
+                // ---- last layer: this thread owns channel (cc*128 + row); columns are the tile's points
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    if (cc < n_last_chunks) {
+                        const int bsel = cc & 1;
+                        if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0xD200 + cc)) goto done;
+                        lf_phase[bsel] ^= 1;
+                        tc_fence_after();
+                        float m = rmax[cc];
+#pragma unroll
+                        for (int c0 = 0; c0 < 128; c0 += 32) {
+                            uint32_t v[32];
+                            tmem_ld32(tmem + lane_addr + 256 + bsel * 128 + c0, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+                        }
+                        rmax[cc] = m;
+                        tc_fence_before();
+                        mbar_arrive(&s.last_empty[bsel]);
+                    }
+                }
+            }
+            // ---- publish: relu(max + bias) >= 0, so integer atomicMax on the bit pattern is exact
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                if (cc < n_last_chunks && t1 > t0) {
+                    const int ch = cc * 128 + row;
+                    const float v = fmaxf(rmax[cc] + __ldg(p.last_b + ch), 0.f);
+                    atomicMax(reinterpret_cast<int *>(p.out + (int64_t)b * p.last + ch), __float_as_int(v));
+                }
+            }
+        }
+    }
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ================================================================================================
+// seg_pass2_kernel
+// ================================================================================================
+struct Pass2Params {
+    const float *x; int64_t sb, sc, sp; int bs, n; int c_in;
+    const float *w1_w, *w1_b;          // conv1 fp32 (64, 8) padded, (64)
+    const float *b2;                   // conv2 bias (64)
+    const float *gbias;                // (bs, 512) per-object dconv1 bias (global-feature half + folded BN bias)
+    const float *bd2, *bd3, *bd4;      // dconv2-4 biases (256),(128),(128)
+    const float *w5, *b5;              // dconv5 fp32 (2,128), (2)
+    const uint8_t *wstream;            // 27 packed blocks
+    float *logits;                     // (bs, n, 2)
+    uint8_t *mask;                     // (bs, n)
+    int tiles_per_obj; int n_items;    // items = bs * tiles_per_obj
+};
+
+constexpr int kP2Stages = 4;
+struct Pass2Smem {
+    uint8_t bufD2[65536];              // dconv2 output (256 ch); first 16 KB doubles as the conv1 output
+    uint8_t ring[2][32768];            // dconv1 128-channel chunks; ring[0] doubles as the dconv3 output
+    uint8_t bufA2[16384];              // conv2 output (64 ch), lives until the last dconv1 chunk
+    uint8_t wring[kP2Stages][kStageBytes];
+    float w1_w[64 * 8], w1_b[64], b2[64], gb[512], bd2[256], bd3[128], bd4[128], w5[256], b5[2];
+    uint64_t w_full[kP2Stages], w_empty[kP2Stages];
+    uint64_t act_ready, acc_ready;
+    uint64_t d1_full[2], d1_act[2], ring_free[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+seg_pass2_kernel(const Pass2Params p)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Pass2Smem &s = *reinterpret_cast<Pass2Smem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < 64 * 8; i += kThreads) s.w1_w[i] = p.w1_w[i];
+    for (int i = threadIdx.x; i < 64; i += kThreads) { s.w1_b[i] = p.w1_b[i]; s.b2[i] = p.b2[i]; }
+    for (int i = threadIdx.x; i < 256; i += kThreads) { s.bd2[i] = p.bd2[i]; s.w5[i] = p.w5[i]; }
+    for (int i = threadIdx.x; i < 128; i += kThreads) { s.bd3[i] = p.bd3[i]; s.bd4[i] = p.bd4[i]; }
+    if (threadIdx.x < 2) s.b5[threadIdx.x] = p.b5[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kP2Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+        mbar_init(&s.act_ready, kTile);
+        mbar_init(&s.acc_ready, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kTile); mbar_init(&s.ring_free[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&s.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    // TMEM columns: [0,256) dconv2 accumulator (conv2 uses [0,64) first); [256,384) / [384,512) dconv1
+    // chunk buffers, reused by dconv3 / dconv4.
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                for (int blk = 0; blk < 27; ++blk) {
+                    if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0xA100 + stage)) goto done;
+                    const uint32_t bytes = (blk == 0) ? 64 * 64 * 2 : kStageBytes;
+                    mbar_arrive_expect_tx(&s.w_full[stage], bytes);
+                    bulk_g2s(s.wring[stage], p.wstream + (size_t)blk * kStageBytes, bytes, &s.w_full[stage]);
+                    if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t wphase = 0, act_phase = 0, d1a_phase[2] = {0, 0};
+            const uint32_t aX = smem_u32(s.bufD2), aA2 = smem_u32(s.bufA2), aD2 = smem_u32(s.bufD2);
+            const uint32_t aRing[2] = {smem_u32(s.ring[0]), smem_u32(s.ring[1])};
+            const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128);
+#define P2_NEXT_W(code)                                                          \
+            if (!mbar_wait(&s.w_full[stage], wphase, code + stage)) goto done;   \
+            tc_fence_after();
+#define P2_REL_W()                                                               \
+            mma_commit(&s.w_empty[stage]);                                       \
+            if (++stage == kP2Stages) { stage = 0; wphase ^= 1; }
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                // conv2 : A = conv1 output (64 ch) in bufD2[0:16K]
+                if (!mbar_wait(&s.act_ready, act_phase, 0xA200)) goto done;
+                act_phase ^= 1; tc_fence_after();
+                P2_NEXT_W(0xA300)
+                mma_block_k64(tmem, aX, 128, smem_u32(s.wring[stage]), 64, id64, false);
+                P2_REL_W()
+                mma_commit(&s.acc_ready);
+                // dconv1 chunks interleaved with dconv2 partial sums
+                if (!mbar_wait(&s.act_ready, act_phase, 0xA201)) goto done;    // conv2 output in bufA2
+                act_phase ^= 1; tc_fence_after();
+                for (int kc = 0; kc < 4; ++kc) {
+                    // dconv1 chunk kc -> TMEM 256 + (kc&1)*128.  The buffer was drained by the epilogue of
+                    // chunk kc-2, which the d1_act wait of partial kc-2 (below) already observed.
+                    P2_NEXT_W(0xA310)
+                    mma_block_k64(tmem + 256 + (kc & 1) * 128, aA2, 128, smem_u32(s.wring[stage]), 128, id128, false);
+                    P2_REL_W()
+                    mma_commit(&s.d1_full[kc & 1]);
+                    if (kc >= 1) {
+                        const int pc = kc - 1, sl = pc & 1;                   // dconv2 partial for chunk kc-1
+                        if (!mbar_wait(&s.d1_act[sl], d1a_phase[sl], 0xA400 + pc)) goto done;
+                        d1a_phase[sl] ^= 1; tc_fence_after();
+                        for (int nc = 0; nc < 2; ++nc)
+                            for (int kb = 0; kb < 2; ++kb) {
+                                P2_NEXT_W(0xA320)
+                                mma_block_k64(tmem + nc * 128, aRing[sl] + kb * 8 * kPlane, 128, smem_u32(s.wring[stage]), 128, id128, pc > 0 || kb > 0);
+                                P2_REL_W()
+                            }
+                        mma_commit(&s.ring_free[sl]);
+                    }
+                }
+                {
+                    const int pc = 3, sl = 1;
+                    if (!mbar_wait(&s.d1_act[sl], d1a_phase[sl], 0xA400 + pc)) goto done;
+                    d1a_phase[sl] ^= 1; tc_fence_after();
+                    for (int nc = 0; nc < 2; ++nc)
+                        for (int kb = 0; kb < 2; ++kb) {
+                            P2_NEXT_W(0xA330)
+                            mma_block_k64(tmem + nc * 128, aRing[sl] + kb * 8 * kPlane, 128, smem_u32(s.wring[stage]), 128, id128, true);
+                            P2_REL_W()
+                        }
+                    mma_commit(&s.ring_free[sl]);
+                    mma_commit(&s.acc_ready);                                  // dconv2 accumulator complete
+                }
+                // dconv3 : A = bufD2 (256 ch) -> TMEM 256..383
+                if (!mbar_wait(&s.act_ready, act_phase, 0xA202)) goto done;
+                act_phase ^= 1; tc_fence_after();
+                for (int kb = 0; kb < 4; ++kb) {
+                    P2_NEXT_W(0xA340)
+                    mma_block_k64(tmem + 256, aD2 + kb * 8 * kPlane, 128, smem_u32(s.wring[stage]), 128, id128, kb > 0);
+                    P2_REL_W()
+                }
+                mma_commit(&s.acc_ready);
+                // dconv4 : A = ring[0] (128 ch) -> TMEM 384..511
+                if (!mbar_wait(&s.act_ready, act_phase, 0xA203)) goto done;
+                act_phase ^= 1; tc_fence_after();
+                for (int kb = 0; kb < 2; ++kb) {
+                    P2_NEXT_W(0xA350)
+                    mma_block_k64(tmem + 384, aRing[0] + kb * 8 * kPlane, 128, smem_u32(s.wring[stage]), 128, id128, kb > 0);
+                    P2_REL_W()
+                }
+                mma_commit(&s.acc_ready);
+            }
+#undef P2_NEXT_W
+#undef P2_REL_W
+        }
+    } else {
+        const int row = epi_row();
+        const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
+        uint32_t acc_phase = 0, d1f_phase[2] = {0, 0}, rf_phase[2] = {0, 0};
+        int cur_obj = -1;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int b = item / p.tiles_per_obj, t = item % p.tiles_per_obj;
+            const int pidx_raw = t * kTile + row;
+            const bool valid = pidx_raw < p.n;
+            const int pidx = valid ? pidx_raw : p.n - 1;
+            // per-object dconv1 bias.  Safe to overwrite here: every reader of s.gb (the dconv1 chunk
+            // epilogues of the previous item) finished before this thread got here, but other epilogue
+            // threads may still be in the previous item's tail, which does not read s.gb.
+            if (b != cur_obj) {
+                // all 128 epilogue threads must be past the previous item's dconv1 epilogues
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = row; i < 512; i += kTile) s.gb[i] = __ldg(p.gbias + (int64_t)b * 512 + i);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cur_obj = b;
+            }
+            // ---- conv1 on CUDA cores -> bufD2[0:16K]
+            {
+                const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
+                float xv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+                first_layer(s.bufD2, row, xv, p.c_in, 64, s.w1_w, s.w1_b);
+                fence_proxy_async_smem();
+                mbar_arrive(&s.act_ready);
+            }
+            // ---- conv2 epilogue -> bufA2
+            if (!mbar_wait(&s.acc_ready, acc_phase, 0xB100)) goto done;
+            acc_phase ^= 1; tc_fence_after();
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + c0, v);
+                tmem_ld_wait();
+                store_act32(s.bufA2, c0 >> 3, row, v, s.b2 + c0);
+            }
+            tc_fence_before(); fence_proxy_async_smem();
+            mbar_arrive(&s.act_ready);
+            // ---- dconv1 chunk epilogues -> ring
+            for (int kc = 0; kc < 4; ++kc) {
+                const int sl = kc & 1;
+                if (!mbar_wait(&s.d1_full[sl], d1f_phase[sl], 0xB200 + kc)) goto done;
+                d1f_phase[sl] ^= 1;
+                // the ring slot is free once dconv2's partial for the chunk that used it last has completed
+                // (first two uses of each item: the previous item's last partials, already waited below)
+                if (kc >= 2) {
+                    if (!mbar_wait(&s.ring_free[sl], rf_phase[sl], 0xB300 + kc)) goto done;
+                    rf_phase[sl] ^= 1;
+                }
+                tc_fence_after();
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + lane_addr + 256 + sl * 128 + c0, v);
+                    tmem_ld_wait();
+                    store_act32(s.ring[sl], c0 >> 3, row, v, s.gb + kc * 128 + c0);
+                }
+                tc_fence_before(); fence_proxy_async_smem();
+                mbar_arrive(&s.d1_act[sl]);
+            }
+            // ---- dconv2 epilogue -> bufD2 (256 ch)
+            if (!mbar_wait(&s.acc_ready, acc_phase, 0xB101)) goto done;
+            acc_phase ^= 1; tc_fence_after();
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + c0, v);
+                tmem_ld_wait();
+                store_act32(s.bufD2, c0 >> 3, row, v, s.bd2 + c0);
+            }
+            tc_fence_before(); fence_proxy_async_smem();
+            mbar_arrive(&s.act_ready);
+            // ---- dconv3 epilogue -> ring[0] (both ring slots are idle: wait out their last partials)
+            for (int sl = 0; sl < 2; ++sl) {
+                if (!mbar_wait(&s.ring_free[sl], rf_phase[sl], 0xB310 + sl)) goto done;
+                rf_phase[sl] ^= 1;
+            }
+            if (!mbar_wait(&s.acc_ready, acc_phase, 0xB102)) goto done;
+            acc_phase ^= 1; tc_fence_after();
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + 256 + c0, v);
+                tmem_ld_wait();
+                store_act32(s.ring[0], c0 >> 3, row, v, s.bd3 + c0);
+            }
+            tc_fence_before(); fence_proxy_async_smem();
+            mbar_arrive(&s.act_ready);
+            // ---- dconv4 epilogue: bias + ReLU in fp32, then the 128 -> 2 layer, logits and mask
+            if (!mbar_wait(&s.acc_ready, acc_phase, 0xB103)) goto done;
+            acc_phase ^= 1; tc_fence_after();
+            float l0 = s.b5[0], l1 = s.b5[1];
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + 384 + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float a = fmaxf(__uint_as_float(v[i]) + s.bd4[c0 + i], 0.f);
+                    l0 = fmaf(a, s.w5[c0 + i], l0);
+                    l1 = fmaf(a, s.w5[128 + c0 + i], l1);
+                }
+            }
+            tc_fence_before();
+            if (valid) {
+                const int64_t o = (int64_t)b * p.n + pidx;
+                *reinterpret_cast<float2 *>(p.logits + o * 2) = make_float2(l0, l1);
+                p.mask[o] = (l0 < l1) ? 1 : 0;
+            }
+        }
+    }
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace al3d
+
+using namespace al3d;
+
+extern "C" int al3d_tc_abort_code(int *code_host)
+{
+    unsigned int v = 0, zero = 0;
+    AL3D_CHECK_CUDA(cudaMemcpyFromSymbol(&v, umma::g_abort, sizeof(v)));
+    if (v != 0) AL3D_CHECK_CUDA(cudaMemcpyToSymbol(umma::g_abort, &zero, sizeof(zero)));
+    if (code_host) *code_host = (int)v;
+    return 0;
+}
+
+extern "C" int al3d_umma_selftest(const void *a_kp, const void *b_kp, int N, int K, float *d_out, int swap_lbo_sbo, void *stream)
+{
+    AL3D_CHECK_ARG(a_kp && b_kp && d_out, "al3d_umma_selftest: null pointer");
+    AL3D_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K % 16 == 0, "al3d_umma_selftest: bad N=%d K=%d", N, K);
+    const size_t smem = (size_t)(128 + N) * K * 2;
+    AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_umma_selftest: tile too large");
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const uint8_t *)a_kp, (const uint8_t *)b_kp, N, K, d_out, swap_lbo_sbo);
+    AL3D_CHECK_LAUNCH("umma_selftest_kernel");
+    return 0;
+}
+
+static int num_sms()
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+extern "C" int al3d_chain_maxpool_bf16(const al3d_chain_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
+                                       int bs, int n, float *out, void *stream)
+{
+    AL3D_CHECK_ARG(w && x && out, "al3d_chain_maxpool_bf16: null pointer");
+    AL3D_CHECK_ARG(w->c_in >= 1 && w->c_in <= 8, "al3d_chain_maxpool_bf16: c_in=%d", w->c_in);
+    AL3D_CHECK_ARG(w->w0 == 64 || w->w0 == 128, "al3d_chain_maxpool_bf16: w0=%d must be 64 or 128", w->w0);
+    AL3D_CHECK_ARG(w->n_mid == 2 || w->n_mid == 3, "al3d_chain_maxpool_bf16: n_mid=%d", w->n_mid);
+    int prev = w->w0, tot = 0;
+    for (int l = 0; l < w->n_mid; ++l) {
+        const int N = w->mid[l];
+        AL3D_CHECK_ARG(N == 64 || N == 128 || N == 256, "al3d_chain_maxpool_bf16: mid width %d", N);
+        AL3D_CHECK_ARG(prev % 64 == 0, "al3d_chain_maxpool_bf16: K=%d", prev);
+        // output buffer capacities: layers 0,2 write bufB (32 KB = 128 ch), layer 1 writes bufA (64 KB = 256 ch)
+        AL3D_CHECK_ARG((l & 1) ? N <= 256 : N <= 128, "al3d_chain_maxpool_bf16: layer %d width %d exceeds its buffer", l, N);
+        prev = N; tot += N;
+    }
+    AL3D_CHECK_ARG(w->w0 <= 128 && tot <= 512, "al3d_chain_maxpool_bf16: widths too large");
+    AL3D_CHECK_ARG(w->last % 256 == 0 && w->last >= 256 && w->last <= 1024, "al3d_chain_maxpool_bf16: last=%d", w->last);
+    AL3D_CHECK_ARG(bs >= 0 && n >= 1, "al3d_chain_maxpool_bf16: bad shape");
+    if (bs == 0) return 0;
+    ChainParams p;
+    p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n;
+    p.c_in = w->c_in; p.w0 = w->w0; p.n_mid = w->n_mid;
+    for (int l = 0; l < 3; ++l) p.mid[l] = w->mid[l];
+    p.last = w->last;
+    p.w0_w = w->w0_w; p.w0_b = w->w0_b; p.mid_b = w->mid_b; p.last_b = w->last_b;
+    p.wstream = (const uint8_t *)w->wstream; p.out = out;
+    const int tiles = (n + kTile - 1) / kTile;
+    const int sms = num_sms();
+    int splits = 1;
+    if (bs < 2 * sms) splits = (int)std::min<int64_t>(tiles, ceil_div(2 * sms, bs));
+    p.splits = splits;
+    p.n_items = bs * splits;
+    const int grid = std::min(p.n_items, sms);
+    const size_t smem = sizeof(ChainSmem) + 128;
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(chain_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chain_max_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    AL3D_CHECK_LAUNCH("chain_max_kernel");
+    return 0;
+}
+
+extern "C" int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
+                                   int bs, int n, const float *gbias, float *logits, uint8_t *mask, void *stream)
+{
+    AL3D_CHECK_ARG(w && x && gbias && logits && mask, "al3d_seg_pass2_bf16: null pointer");
+    AL3D_CHECK_ARG(w->c_in >= 1 && w->c_in <= 8, "al3d_seg_pass2_bf16: c_in=%d", w->c_in);
+    AL3D_CHECK_ARG(bs >= 0 && n >= 1, "al3d_seg_pass2_bf16: bad shape");
+    if (bs == 0) return 0;
+    Pass2Params p;
+    p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n; p.c_in = w->c_in;
+    p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.gbias = gbias;
+    p.bd2 = w->bd2; p.bd3 = w->bd3; p.bd4 = w->bd4; p.w5 = w->w5; p.b5 = w->b5;
+    p.wstream = (const uint8_t *)w->wstream; p.logits = logits; p.mask = mask;
+    p.tiles_per_obj = (n + kTile - 1) / kTile;
+    const int64_t items = (int64_t)bs * p.tiles_per_obj;
+    AL3D_CHECK_ARG(items < (1ll << 31), "al3d_seg_pass2_bf16: too many tiles");
+    p.n_items = (int)items;
+    const int grid = std::min(p.n_items, num_sms());
+    const size_t smem = sizeof(Pass2Smem) + 128;
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(seg_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    seg_pass2_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    AL3D_CHECK_LAUNCH("seg_pass2_kernel");
+    return 0;
+}

@@ -1,0 +1,171 @@
+// sm_100a primitives used by the tensor-core kernels: mbarrier, TMA bulk copy (cp.async.bulk),
+// TMEM allocation, tcgen05.mma / commit / ld, and the shared-memory operand layout.
+//
+// Operand layout ("KP", K-major, no swizzle): a tile of R rows x K columns of bf16 is stored as
+// K/8 planes of R x 16 bytes:   byte(r, k) = (k / 8) * (R * 16) + r * 16 + (k % 8) * 2.
+// One plane row is one 16-byte core-matrix row, 8 consecutive rows are one 8x16B core matrix, so a
+// UMMA shared-memory descriptor (SWIZZLE_NONE, K-major) describes it with
+//     leading-dimension byte offset (between the two K core matrices of one K=16 MMA) = R * 16
+//     stride-dimension  byte offset (between 8-row groups along M/N)                   = 128
+// Packing a (R, K) row-major matrix into this layout is `w.view(R, K/8, 8).permute(1, 0, 2)`.
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace al3d {
+namespace umma {
+
+// A wait that exceeds this many clock64 ticks records a code in g_abort and gives up, so that a
+// protocol bug shows up as a reported error instead of a hung GPU.
+static __device__ unsigned int g_abort = 0;
+constexpr long long kWaitTimeoutCycles = 1ll << 31;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Returns false if the wait was abandoned (timeout or an earlier abort anywhere on the device).
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, uint32_t code)
+{
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023) == 0) {
+            if (*(volatile unsigned int *)&g_abort != 0) return false;
+            if (clock64() - t0 > kWaitTimeoutCycles) {
+                atomicCAS(&g_abort, 0u, code);
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------- proxies / fences
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---------------------------------------------------------------- TMA bulk copy global -> shared
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- TMEM
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem)     // whole warp
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr)       // whole warp
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(kCols) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (warp%4)*32+i.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- descriptors + MMA
+// Shared-memory matrix descriptor for a KP-layout tile of R rows, starting at byte address `saddr`
+// (the first of the two K planes this K=16 MMA reads).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t rows, bool swap_lbo_sbo = false)
+{
+    uint32_t lbo = rows * 16u, sbo = 128u;
+    if (swap_lbo_sbo) { uint32_t t = lbo; lbo = sbo; sbo = t; }
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;                     // descriptor version 1 (sm_100)
+    return d;                                   // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE (0)
+}
+
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N)
+{
+    return (1u << 4)                 // D format fp32
+         | (1u << 7) | (1u << 10)    // A, B format bf16
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread.
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once every tcgen05 op issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One K=64 block: 4 MMAs of K=16.  a_addr / b_addr: smem byte addresses of the first plane of the
+// 64-wide K slice; rows_a / rows_b: row counts of the two KP tiles.
+__device__ __forceinline__ void mma_block_k64(uint32_t tmem_d, uint32_t a_addr, uint32_t rows_a, uint32_t b_addr, uint32_t rows_b,
+                                              uint32_t idesc, bool accumulate_first, bool swap = false)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t da = make_desc(a_addr + k * 2 * rows_a * 16, rows_a, swap);
+        const uint64_t db = make_desc(b_addr + k * 2 * rows_b * 16, rows_b, swap);
+        mma_bf16(tmem_d, da, db, idesc, (accumulate_first || k > 0) ? 1u : 0u);
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+}  // namespace umma
+}  // namespace al3d

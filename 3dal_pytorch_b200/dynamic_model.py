@@ -59,8 +59,8 @@ class DynamicModel(_AutoLabelBase):
         self._check_inputs(pts, self.n_channel)
         if box.dim() != 3 or box.shape[1] != 8:
             raise ValueError("box must be (bs,8,steps), got %s" % (tuple(box.shape),))
-        logits = self._seg(pts)
-        obj, mask, _ = engine.mask_and_gather(pts[:, :4, :], logits, NUM_FRAME * NUM_OBJECT_POINT, self.gather_policy)
+        logits, seg_mask = self._seg(pts)
+        obj, mask, _ = engine.mask_and_gather(pts[:, :4, :], logits, NUM_FRAME * NUM_OBJECT_POINT, self.gather_policy, mask=seg_mask)
         fwp, gp = self._trunk("point_emb", self.point_emb, obj)
         pe = engine.fc_chain(fwp, gp, ("fc1", "fc2"))
         fwb, gb = self._trunk("box_emb", self.box_emb, box.float())

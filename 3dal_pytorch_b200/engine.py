@@ -132,8 +132,13 @@ def choice_table_numpy_legacy(counts_host, n_pts):
     return table
 
 
-def mask_and_gather(pts, logits, n_pts, policy, want_indices=False):
-    mask, pos, count = ops.mask_compact(logits=logits)
+def mask_and_gather(pts, logits, n_pts, policy, want_indices=False, mask=None):
+    """mask: the (bs,n) bool mask already produced by the segmentation epilogue (bf16 mode), or None
+    to derive it from the logits here."""
+    if mask is None:
+        mask, pos, count = ops.mask_compact(logits=logits)
+    else:
+        mask, pos, count = ops.mask_compact(mask=mask)
     choice = None
     if policy == "numpy_legacy":
         # the one documented host round-trip: bs counts down, a (bs,n_pts) table up

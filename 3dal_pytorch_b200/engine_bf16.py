@@ -1,0 +1,173 @@
+"""bf16 tensor-core mode: weight packing for, and launch sequences of, the tcgen05 kernels
+(csrc/chain_bf16.cu).  See engine.py for the fp32 mode and the shared mask / gather / head stages.
+
+Packing: every folded weight matrix W' (N, K) is cut into blocks of (<=128 rows) x (64 K), each
+converted to bf16 and laid out K-plane-major -- ``blk.view(R, 8, 8).permute(1, 0, 2)`` -- which is
+byte-for-byte the shared-memory operand layout the MMA descriptors describe, so the kernel's producer
+warp only issues linear 16 KB bulk copies.  Blocks are stored in consumption order.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _lib, ops
+
+BLOCK_ELEMS = 8192           # 16 KB of bf16
+CHECK_ABORT = os.environ.get("AL3D_TC_CHECK", "0") == "1"
+
+
+class ChainWeightsStruct(ctypes.Structure):
+    _fields_ = [("c_in", ctypes.c_int32), ("w0", ctypes.c_int32), ("n_mid", ctypes.c_int32),
+                ("mid", ctypes.c_int32 * 3), ("last", ctypes.c_int32), ("n_blocks", ctypes.c_int32),
+                ("w0_w", ctypes.c_void_p), ("w0_b", ctypes.c_void_p), ("mid_b", ctypes.c_void_p),
+                ("last_b", ctypes.c_void_p), ("wstream", ctypes.c_void_p)]
+
+
+class Pass2WeightsStruct(ctypes.Structure):
+    _fields_ = [("c_in", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("w1_w", ctypes.c_void_p), ("w1_b", ctypes.c_void_p), ("b2", ctypes.c_void_p),
+                ("bd2", ctypes.c_void_p), ("bd3", ctypes.c_void_p), ("bd4", ctypes.c_void_p),
+                ("w5", ctypes.c_void_p), ("b5", ctypes.c_void_p), ("wstream", ctypes.c_void_p)]
+
+
+def kp_pack(w):
+    """(R, K) float -> bf16 tensor of R*K elements in KP order (K/8 planes of R x 8)."""
+    R, K = w.shape
+    return w.to(torch.bfloat16).view(R, K // 8, 8).permute(1, 0, 2).contiguous().view(-1)
+
+
+def _block(w_blk):
+    flat = kp_pack(w_blk)
+    out = torch.zeros(BLOCK_ELEMS, dtype=torch.bfloat16, device=w_blk.device)
+    out[: flat.numel()] = flat
+    return out
+
+
+def _pad8(w):
+    out = torch.zeros((w.shape[0], 8), dtype=torch.float32, device=w.device)
+    out[:, : w.shape[1]] = w
+    return out.contiguous()
+
+
+def _layer_blocks(w):
+    """Blocks of one layer in (row-chunk, k-block) order."""
+    N, K = w.shape
+    rows = min(N, 128)
+    return [_block(w[r:r + rows, k:k + 64]) for r in range(0, N, rows) for k in range(0, K, 64)]
+
+
+class ChainPack:
+    """Packed weights of a first-layer + mid-layers + max-pooled-last-layer chain."""
+
+    def __init__(self, fw, names):
+        first, mids, last = names[0], names[1:-1], names[-1]
+        w0, b0 = fw[first]
+        self.c_in = w0.shape[1]
+        self.t = {"w0_w": _pad8(w0), "w0_b": b0.contiguous(),
+                  "mid_b": torch.cat([fw[m][1] for m in mids]).contiguous(), "last_b": fw[last][1].contiguous()}
+        blocks = []
+        for m in mids + [last]:
+            blocks += _layer_blocks(fw[m][0])
+        self.t["wstream"] = torch.cat(blocks).contiguous()
+        s = ChainWeightsStruct()
+        s.c_in, s.w0, s.n_mid = self.c_in, w0.shape[0], len(mids)
+        for i in range(3):
+            s.mid[i] = fw[mids[i]][0].shape[0] if i < len(mids) else 0
+        s.last, s.n_blocks = fw[last][0].shape[0], len(blocks)
+        for k in ("w0_w", "w0_b", "mid_b", "last_b", "wstream"):
+            setattr(s, k, self.t[k].data_ptr())
+        self.struct = s
+        self.last = s.last
+
+
+class SegPack:
+    def __init__(self, fw, c_in):
+        self.pass1 = ChainPack(fw, ["conv1", "conv2", "conv3", "conv4", "conv5"])
+        wd1, wd2, wd3, wd4 = (fw[k][0] for k in ("dconv1", "dconv2", "dconv3", "dconv4"))
+        blocks = [_block(fw["conv2"][0])]
+
+        def d1(kc):
+            return [_block(wd1[kc * 128:(kc + 1) * 128, 0:64])]
+
+        def d2(pc):
+            return [_block(wd2[nc * 128:(nc + 1) * 128, pc * 128 + kb * 64: pc * 128 + kb * 64 + 64])
+                    for nc in range(2) for kb in range(2)]
+
+        blocks += d1(0) + d1(1) + d2(0) + d1(2) + d2(1) + d1(3) + d2(2) + d2(3)
+        blocks += [_block(wd3[:, kb * 64:(kb + 1) * 64]) for kb in range(4)]
+        blocks += [_block(wd4[:, kb * 64:(kb + 1) * 64]) for kb in range(2)]
+        assert len(blocks) == 27
+        self.t = {"w1_w": _pad8(fw["conv1"][0]), "w1_b": fw["conv1"][1].contiguous(), "b2": fw["conv2"][1].contiguous(),
+                  "bd2": fw["dconv2"][1].contiguous(), "bd3": fw["dconv3"][1].contiguous(),
+                  "bd4": fw["dconv4"][1].contiguous(), "w5": fw["dconv5"][0].contiguous(),
+                  "b5": fw["dconv5"][1].contiguous(), "wstream": torch.cat(blocks).contiguous()}
+        s = Pass2WeightsStruct()
+        s.c_in = c_in
+        for k, v in self.t.items():
+            setattr(s, k, v.data_ptr())
+        self.struct = s
+        # the 1024-wide half of dconv1 acts on the per-object global feature: kept fp32
+        self.w_glob = wd1[:, 64:]
+        self.b_d1 = fw["dconv1"][1]
+
+
+def pack_seg(fw, c_in):
+    return SegPack(fw, c_in)
+
+
+def pack_trunk(fw):
+    return ChainPack(fw, ["conv1", "conv2", "conv3", "conv4"])
+
+
+def check_abort(what):
+    code = ctypes.c_int(0)
+    _lib.check(_lib.lib().al3d_tc_abort_code(ctypes.byref(code)), "tc_abort_code")
+    if code.value != 0:
+        raise RuntimeError("libal3d: %s gave up on an mbarrier wait (watchdog code 0x%X); outputs are invalid"
+                           % (what, code.value))
+
+
+def chain_maxpool(pack, x):
+    """x (bs,C,n) any strides -> (bs,last) fp32 = relu(max over points of the chain)."""
+    ops._need_cuda(x)
+    bs, C, n = x.shape
+    assert C == pack.c_in, (C, pack.c_in)
+    out = torch.zeros((bs, pack.last), device=x.device, dtype=torch.float32)
+    sb, sc, sp = x.stride()
+    _lib.check(_lib.lib().al3d_chain_maxpool_bf16(ctypes.byref(pack.struct), x.data_ptr(), sb, sc, sp, bs, n,
+                                                  out.data_ptr(), ops._stream()), "chain_maxpool_bf16")
+    if CHECK_ABORT:
+        check_abort("chain_max_kernel")
+    return out
+
+
+def seg_forward(pack, fw, pts):
+    """-> logits (bs,n,2) f32, mask (bs,n) bool."""
+    bs, C, n = pts.shape
+    g = chain_maxpool(pack.pass1, pts)
+    gbias = ops.linear(g, pack.w_glob, pack.b_d1, act=ops.ACT_NONE, K=1024)
+    logits = torch.empty((bs, n, 2), device=pts.device, dtype=torch.float32)
+    mask = torch.empty((bs, n), device=pts.device, dtype=torch.bool)
+    sb, sc, sp = pts.stride()
+    _lib.check(_lib.lib().al3d_seg_pass2_bf16(ctypes.byref(pack.struct), pts.data_ptr(), sb, sc, sp, bs, n,
+                                              gbias.data_ptr(), logits.data_ptr(), mask.data_ptr(), ops._stream()),
+               "seg_pass2_bf16")
+    if CHECK_ABORT:
+        check_abort("seg_pass2_kernel")
+    return logits, mask
+
+
+def trunk_maxpool(pack, fw, x):
+    return chain_maxpool(pack, x)
+
+
+def umma_selftest(a, b, swap=False):
+    """a (128,K), b (N,K) float CUDA tensors -> (128,N) fp32 computed by one tcgen05.mma chain."""
+    N, K = b.shape
+    d = torch.empty((128, N), device=a.device, dtype=torch.float32)
+    ak, bk = kp_pack(a), kp_pack(b)
+    _lib.check(_lib.lib().al3d_umma_selftest(ak.data_ptr(), bk.data_ptr(), N, K, d.data_ptr(), int(swap), ops._stream()),
+               "umma_selftest")
+    check_abort("umma_selftest_kernel")
+    return d

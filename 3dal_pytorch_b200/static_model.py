@@ -75,7 +75,7 @@ class _AutoLabelBase(nn.Module):
     def _seg(self, pts):
         fw = self._packs.get("seg_f32", self.ins_seg, lambda: engine.fold_block(self.ins_seg, self.ins_seg._table))
         if self.precision == "fp32":
-            return engine.seg_forward_fp32(fw, pts)
+            return engine.seg_forward_fp32(fw, pts), None
         from . import engine_bf16
         pk = self._packs.get("seg_bf16", self.ins_seg, lambda: engine_bf16.pack_seg(fw, self.ins_seg.n_channel))
         return engine_bf16.seg_forward(pk, fw, pts)
@@ -102,8 +102,8 @@ class StaticModelOneBoxEst(_AutoLabelBase):
     @torch.no_grad()
     def forward(self, pts, init_box, bbox_gt=None):
         self._check_inputs(pts, self.n_channel)
-        logits = self._seg(pts)
-        obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, self.gather_policy)
+        logits, seg_mask = self._seg(pts)
+        obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, self.gather_policy, mask=seg_mask)
         fw, g = self._trunk("box_est", self.box_est, obj)
         box_pred = engine.fc_chain(fw, g, ("fc1", "fc2", "fc3"))
         out = ops.parse_heads(box_pred, add=init_box.float())
@@ -133,8 +133,8 @@ class StaticModelTwoBoxEst(_AutoLabelBase):
         self._check_inputs(pts, self.n_channel)
         init_box = init_box.float().contiguous()
         bbox_gt = bbox_gt.float().contiguous()
-        logits = self._seg(pts)
-        obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, self.gather_policy)
+        logits, seg_mask = self._seg(pts)
+        obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, self.gather_policy, mask=seg_mask)
         fw1, g1 = self._trunk("box_est_one", self.box_est_one, obj)
         one = ops.parse_heads(engine.fc_chain(fw1, g1, ("fc1", "fc2", "fc3")), add=init_box)
         box_one, _ = ops.decode_boxes(one["center"], one["heading_scores"], one["heading_residuals"],

@@ -104,6 +104,60 @@ int al3d_twostage_retransform(const float *obj_pts, int bs, int m, const float *
                               const float *bbox_gt, float *obj_pts_two, int64_t *heading_cls_label,
                               float *heading_res_label, void *stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05 / TMEM, bf16 operands, fp32 accumulate) shared-MLP kernels.
+ * Weights are BatchNorm-folded and packed by the caller (3dal_pytorch_b200/engine_bf16.py) into
+ * 16 KB blocks of 128 rows x 64 K in the "KP" layout (K/8 planes of rows x 16 bytes), stored in the
+ * order the kernel consumes them.
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct al3d_chain_weights {
+    int32_t c_in;            /* input channels (1..8)                                            */
+    int32_t w0;              /* width of the first layer (CUDA cores): 64 or 128                  */
+    int32_t n_mid;           /* number of chained tensor-core layers: 2 or 3                      */
+    int32_t mid[3];          /* their widths (64 / 128 / 256)                                     */
+    int32_t last;            /* width of the max-pooled last layer (512 / 1024)                   */
+    int32_t n_blocks;        /* number of 16 KB blocks in wstream                                 */
+    const float *w0_w;       /* (w0, 8) fp32, rows zero-padded to 8 inputs                        */
+    const float *w0_b;       /* (w0)                                                              */
+    const float *mid_b;      /* concatenated fp32 biases of the mid layers                        */
+    const float *last_b;     /* (last)                                                            */
+    const void  *wstream;    /* packed bf16 weight blocks                                         */
+} al3d_chain_weights;
+
+/* first layer -> chained MMA layers -> last layer max-pooled over the n points of each object.
+ * out (bs,last) must be zero-filled by the caller; results are relu(max + bias) >= 0.
+ * Replaces ins_seg conv1-5 + torch.max (tools/static_model.py:279-284), the static box-head trunk
+ * (:330-334) and the PointEmbedding / BoxEmbedding trunks (tools/dynamic_model.py:241-245,278-282). */
+int al3d_chain_maxpool_bf16(const al3d_chain_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
+                            int bs, int n, float *out, void *stream);
+
+typedef struct al3d_pass2_weights {
+    int32_t c_in;
+    int32_t reserved;
+    const float *w1_w, *w1_b;      /* ins_seg.conv1 folded fp32: (64,8) zero-padded, (64)          */
+    const float *b2;               /* conv2 bias (64)                                               */
+    const float *bd2, *bd3, *bd4;  /* dconv2-4 biases (256),(128),(128)                             */
+    const float *w5, *b5;          /* dconv5 fp32 (2,128), (2)                                      */
+    const void  *wstream;          /* 27 packed bf16 blocks: conv2, dconv1/dconv2 interleaved, dconv3, dconv4 */
+} al3d_pass2_weights;
+
+/* Second half of PointNetInstanceSeg.forward (tools/static_model.py:286-295) + the mask of
+ * point_cloud_masking (:59).  gbias (bs,512) = W_dconv1[:, 64:] . global_feature + folded bias
+ * (the concat-with-global-feature turned into a per-object bias).  Writes logits (bs,n,2) f32 and
+ * mask (bs,n) u8. */
+int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
+                        int bs, int n, const float *gbias, float *logits, uint8_t *mask, void *stream);
+
+/* D(128,N) fp32 = A(128,K) . B(N,K)^T from KP-packed bf16 operands with one tcgen05.mma chain:
+ * unit test of the descriptor / layout conventions. */
+int al3d_umma_selftest(const void *a_kp, const void *b_kp, int N, int K, float *d_out, int swap_lbo_sbo, void *stream);
+
+/* Reads (and clears) the device-side watchdog code: non-zero means a tensor-core kernel gave up on
+ * an mbarrier wait (protocol bug) and its outputs are invalid.  Synchronises the device. */
+int al3d_tc_abort_code(int *code_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,3 +46,51 @@ def rel_err(a, b):
     a = torch.as_tensor(a).double()
     b = torch.as_tensor(b).double()
     return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def fold_state_dict(sd, block, table):
+    """BN-fold a reference-format state_dict block -> {layer: (W', b')} (fp32, same maths as
+    3dal_pytorch_b200.engine.fold_block, restated here so the tests do not depend on it)."""
+    out = {}
+    for lname, bn, cin, cout, kind in table:
+        w = sd["%s.%s.weight" % (block, lname)].reshape(cout, cin).float()
+        b = sd["%s.%s.bias" % (block, lname)].float()
+        if bn is not None:
+            p = "%s.%s." % (block, bn)
+            a = sd[p + "weight"].float() / torch.sqrt(sd[p + "running_var"].float() + 1e-5)
+            w = w * a[:, None]
+            b = a * (b - sd[p + "running_mean"].float()) + sd[p + "bias"].float()
+        out[lname] = (w.contiguous(), b.contiguous())
+    return out
+
+
+def emulate_chain_bf16(fw, names, x):
+    """Numerics model of chain_max_kernel: fp32 first layer, bf16 activations / weights with fp32
+    accumulation in the MMA layers, max over points, then bias + ReLU.  x (bs,C,n) -> (bs,last)."""
+    h = x.transpose(2, 1).float()                                    # (bs,n,C)
+    w, b = fw[names[0]]
+    h = bf16_round(torch.relu(h @ w.t() + b))
+    for nm in names[1:-1]:
+        w, b = fw[nm]
+        h = bf16_round(torch.relu(h @ bf16_round(w).t() + b))
+    w, b = fw[names[-1]]
+    return torch.relu((h @ bf16_round(w).t()).max(dim=1)[0] + b)
+
+
+def emulate_seg_bf16(fw, x):
+    """Numerics model of the bf16 segmentation path -> logits (bs,n,2)."""
+    g = emulate_chain_bf16(fw, ["conv1", "conv2", "conv3", "conv4", "conv5"], x)
+    h = x.transpose(2, 1).float()
+    h = bf16_round(torch.relu(h @ fw["conv1"][0].t() + fw["conv1"][1]))
+    o2 = bf16_round(torch.relu(h @ bf16_round(fw["conv2"][0]).t() + fw["conv2"][1]))
+    wd1, bd1 = fw["dconv1"]
+    gb = g @ wd1[:, 64:].t() + bd1                                    # fp32 per-object bias
+    d = bf16_round(torch.relu(o2 @ bf16_round(wd1[:, :64]).t() + gb[:, None, :]))
+    d = bf16_round(torch.relu(d @ bf16_round(fw["dconv2"][0]).t() + fw["dconv2"][1]))
+    d = bf16_round(torch.relu(d @ bf16_round(fw["dconv3"][0]).t() + fw["dconv3"][1]))
+    d = torch.relu(d @ bf16_round(fw["dconv4"][0]).t() + fw["dconv4"][1])     # stays fp32
+    return d @ fw["dconv5"][0].t() + fw["dconv5"][1]

@@ -1,0 +1,69 @@
+"""GPU tests of the tcgen05 kernels against a bf16 numerics model (tight) and the fp32 oracle (loose)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+os.environ["AL3D_TC_CHECK"] = "1"
+from helpers import emulate_chain_bf16, emulate_seg_bf16, fold_state_dict, rel_err, spec, synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+eb = importlib.import_module("3dal_pytorch_b200.engine_bf16")
+eb.CHECK_ABORT = True
+
+
+@pytest.mark.parametrize("N,K", [(64, 64), (128, 64), (128, 128), (256, 256), (16, 16), (96, 48)])
+def test_umma_selftest(N, K):
+    torch.manual_seed(N * 1000 + K)
+    a = torch.randn(128, K, device=DEV)
+    b = torch.randn(N, K, device=DEV)
+    ref = a.to(torch.bfloat16).float() @ b.to(torch.bfloat16).float().t()
+    d = eb.umma_selftest(a, b, swap=False)
+    err = rel_err(d.cpu(), ref.cpu())
+    if err >= 1e-5:
+        d2 = eb.umma_selftest(a, b, swap=True)
+        pytest.fail("descriptor convention wrong: err(lbo=R*16,sbo=128)=%g err(swapped)=%g" % (err, rel_err(d2.cpu(), ref.cpu())))
+
+
+def _dev(fw):
+    return {k: (w.to(DEV), b.to(DEV)) for k, (w, b) in fw.items()}
+
+
+@pytest.mark.parametrize("kind,block,table,C,n,bs", [
+    ("static_one", "box_est", "static_est_layers", 3, 512, 5),
+    ("dynamic", "point_emb", "point_emb_layers", 4, 2560, 3),
+    ("dynamic", "box_emb", "box_emb_layers", 8, 101, 7),
+    ("static_one", "box_est", "static_est_layers", 3, 130, 300),     # ragged tile, many objects (no split)
+])
+def test_chain_maxpool_trunks(kind, block, table, C, n, bs):
+    sd = synth.random_state_dict(kind, seed=5)
+    fw = _dev(fold_state_dict(sd, block, getattr(spec, table)()))
+    torch.manual_seed(0)
+    x_pm = torch.randn(bs, n, C, device=DEV)
+    x = x_pm.transpose(2, 1)                                  # strided view
+    pack = eb.pack_trunk(fw)
+    got = eb.chain_maxpool(pack, x)
+    emu = emulate_chain_bf16(fw, ["conv1", "conv2", "conv3", "conv4"], x)
+    assert rel_err(got.cpu(), emu.cpu()) < 2e-3, rel_err(got.cpu(), emu.cpu())
+    got2 = eb.chain_maxpool(pack, x.contiguous())
+    assert torch.equal(got, got2)
+
+
+@pytest.mark.parametrize("C,n,bs", [(3, 4096, 2), (4, 5120, 2), (3, 1000, 3), (3, 77, 40)])
+def test_seg_bf16_against_numerics_model(C, n, bs):
+    kind = "dynamic" if C == 4 else "static_one"
+    sd = synth.random_state_dict(kind, seed=6)
+    fw = _dev(fold_state_dict(sd, "ins_seg", spec.seg_layers(C)))
+    torch.manual_seed(1)
+    x = (torch.randn(bs, n, C, device=DEV) * torch.tensor([2.0, 2.0, 0.7, 0.2][:C], device=DEV)).transpose(2, 1)
+    pack = eb.pack_seg(fw, C)
+    g = eb.chain_maxpool(pack.pass1, x)
+    emu_g = emulate_chain_bf16(fw, ["conv1", "conv2", "conv3", "conv4", "conv5"], x)
+    assert rel_err(g.cpu(), emu_g.cpu()) < 2e-3
+    logits, mask = eb.seg_forward(pack, fw, x)
+    emu = emulate_seg_bf16(fw, x)
+    assert rel_err(logits.cpu(), emu.cpu()) < 5e-3, rel_err(logits.cpu(), emu.cpu())
+    assert torch.equal(mask, logits[..., 0] < logits[..., 1])          # mask is exact w.r.t. our logits

@@ -1,0 +1,72 @@
+"""CPU check of the tensor-core weight packing: decode the packed block stream exactly the way the
+kernels consume it (block order of csrc/chain_bf16.cu, KP plane layout of csrc/umma.cuh) and make
+sure it reproduces the folded weights."""
+import importlib
+
+import torch
+
+from helpers import fold_state_dict, spec, synth
+
+eb = importlib.import_module("3dal_pytorch_b200.engine_bf16")
+
+
+def kp_unpack(flat, R, K):
+    """Inverse of the KP layout: element (r,k) lives at (k//8)*(R*8) + r*8 + k%8."""
+    out = torch.empty(R, K)
+    for k in range(K):
+        for r in range(R):
+            out[r, k] = float(flat[(k // 8) * (R * 8) + r * 8 + (k % 8)])
+    return out
+
+
+def _blocks(stream):
+    return stream.view(-1, eb.BLOCK_ELEMS)
+
+
+def test_kp_pack_is_plane_major():
+    w = (torch.arange(16 * 64) % 251).float().view(16, 64)                 # exactly representable in bf16
+    assert torch.equal(kp_unpack(eb.kp_pack(w).float(), 16, 64), w)
+
+
+def test_chain_stream_order_matches_kernel_loops():
+    sd = synth.random_state_dict("static_one", seed=1)
+    fw = fold_state_dict(sd, "box_est", spec.static_est_layers())
+    pack = eb.pack_trunk(fw)
+    blocks = _blocks(pack.t["wstream"])
+    blk = 0
+    prev = fw["conv1"][0].shape[0]
+    for name in ("conv2", "conv3", "conv4"):          # kernel: for row-chunk: for k-block
+        w = fw[name][0].to(torch.bfloat16).float()
+        N, K = w.shape
+        assert K == prev
+        rows = min(N, 128)
+        for nc in range(N // rows):
+            for kb in range(K // 64):
+                got = kp_unpack(blocks[blk][: rows * 64].float(), rows, 64)
+                assert torch.equal(got, w[nc * rows:(nc + 1) * rows, kb * 64:(kb + 1) * 64]), (name, nc, kb)
+                blk += 1
+        prev = N
+    assert blk == pack.struct.n_blocks == blocks.shape[0]
+    assert (pack.struct.w0, pack.struct.n_mid, list(pack.struct.mid)[:2], pack.struct.last) == (128, 2, [128, 256], 512)
+    assert pack.t["w0_w"].shape == (128, 8) and torch.equal(pack.t["w0_w"][:, :3], fw["conv1"][0])
+
+
+def test_pass2_stream_order_matches_kernel_schedule():
+    sd = synth.random_state_dict("dynamic", seed=2)
+    fw = fold_state_dict(sd, "ins_seg", spec.seg_layers(4))
+    pack = eb.pack_seg(fw, 4)
+    blocks = _blocks(pack.t["wstream"])
+    assert blocks.shape[0] == 27
+    bf = lambda n: fw[n][0].to(torch.bfloat16).float()
+    wd1, wd2, wd3, wd4 = bf("dconv1"), bf("dconv2"), bf("dconv3"), bf("dconv4")
+    expect = [("conv2", bf("conv2"), 64)]
+    d1 = lambda kc: [("d1_%d" % kc, wd1[kc * 128:(kc + 1) * 128, :64], 128)]
+    d2 = lambda pc: [("d2_%d_%d_%d" % (pc, nc, kb), wd2[nc * 128:(nc + 1) * 128, pc * 128 + kb * 64: pc * 128 + kb * 64 + 64], 128)
+                     for nc in range(2) for kb in range(2)]
+    # issue order of the MMA thread in seg_pass2_kernel
+    expect += d1(0) + d1(1) + d2(0) + d1(2) + d2(1) + d1(3) + d2(2) + d2(3)
+    expect += [("d3_%d" % kb, wd3[:, kb * 64:(kb + 1) * 64], 128) for kb in range(4)]
+    expect += [("d4_%d" % kb, wd4[:, kb * 64:(kb + 1) * 64], 128) for kb in range(2)]
+    for i, (name, w, rows) in enumerate(expect):
+        assert torch.equal(kp_unpack(blocks[i][: rows * 64].float(), rows, 64), w), name
+    assert pack.struct.c_in == 4 and pack.w_glob.shape == (512, 1024)
