@@ -57,7 +57,15 @@ def lib():
     return _lib
 
 
+# kernels launched through this binding since import (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+_NO_LAUNCH = ("tc_abort_code",)
+
+
 def check(rc, what=""):
+    global LAUNCHES
+    if rc == 0 and what not in _NO_LAUNCH:
+        LAUNCHES += 1
     if rc != 0:
         msg = lib().al3d_last_error()
         raise RuntimeError("libal3d: %s%s" % (what + ": " if what else "", msg.decode() if msg else "error %d" % rc))

@@ -103,7 +103,7 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_kp, const uint8_t *__restrict
         tmem_ld32(tmem + ((uint32_t)(row & ~31) << 16) + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) d[row * N + c0 + i] = __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) if (c0 + i < N) d[row * N + c0 + i] = __uint_as_float(v[i]);
     }
     tc_fence_before();
     __syncthreads();

@@ -120,6 +120,26 @@ def pack_trunk(fw):
     return ChainPack(fw, ["conv1", "conv2", "conv3", "conv4"])
 
 
+# Optional per-kernel CUDA-event timing (bench.py's roofline leg): {"name": [(start_event, end_event), ...]}
+KERNEL_EVENTS = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KERNEL_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if KERNEL_EVENTS is not None:
+            self.e1.record()
+            KERNEL_EVENTS.setdefault(self.name, []).append((self.e0, self.e1))
+
+
 def check_abort(what):
     code = ctypes.c_int(0)
     _lib.check(_lib.lib().al3d_tc_abort_code(ctypes.byref(code)), "tc_abort_code")
@@ -135,8 +155,9 @@ def chain_maxpool(pack, x):
     assert C == pack.c_in, (C, pack.c_in)
     out = torch.zeros((bs, pack.last), device=x.device, dtype=torch.float32)
     sb, sc, sp = x.stride()
-    _lib.check(_lib.lib().al3d_chain_maxpool_bf16(ctypes.byref(pack.struct), x.data_ptr(), sb, sc, sp, bs, n,
-                                                  out.data_ptr(), ops._stream()), "chain_maxpool_bf16")
+    with _timed("chain_max_kernel[last=%d]" % pack.last):
+        _lib.check(_lib.lib().al3d_chain_maxpool_bf16(ctypes.byref(pack.struct), x.data_ptr(), sb, sc, sp, bs, n,
+                                                      out.data_ptr(), ops._stream()), "chain_maxpool_bf16")
     if CHECK_ABORT:
         check_abort("chain_max_kernel")
     return out
@@ -150,9 +171,10 @@ def seg_forward(pack, fw, pts):
     logits = torch.empty((bs, n, 2), device=pts.device, dtype=torch.float32)
     mask = torch.empty((bs, n), device=pts.device, dtype=torch.bool)
     sb, sc, sp = pts.stride()
-    _lib.check(_lib.lib().al3d_seg_pass2_bf16(ctypes.byref(pack.struct), pts.data_ptr(), sb, sc, sp, bs, n,
-                                              gbias.data_ptr(), logits.data_ptr(), mask.data_ptr(), ops._stream()),
-               "seg_pass2_bf16")
+    with _timed("seg_pass2_kernel"):
+        _lib.check(_lib.lib().al3d_seg_pass2_bf16(ctypes.byref(pack.struct), pts.data_ptr(), sb, sc, sp, bs, n,
+                                                  gbias.data_ptr(), logits.data_ptr(), mask.data_ptr(), ops._stream()),
+                   "seg_pass2_bf16")
     if CHECK_ABORT:
         check_abort("seg_pass2_kernel")
     return logits, mask

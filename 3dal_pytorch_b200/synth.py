@@ -170,3 +170,31 @@ def lidar_frames(n_frames, n_points=180000, n_boxes=200, seed=0):
         pose[:3, 3] = [rng.uniform(-500, 500), rng.uniform(-500, 500), rng.uniform(-5, 5)]
         frames.append({"points": pts, "det_boxes": det, "pose": pose})
     return frames
+
+
+def static_tracks_device(bs, n=spec.NUM_POINT_STATIC, seed=0, device="cuda"):
+    """Device-side twin of ``static_tracks`` for large batches (the host loop is too slow for 8192
+    tracks): same recipe -- anchor-sized box at the origin with a random share of the points inside
+    it, a ground plane and clutter, shuffled -- generated with torch ops.  Returns point-major
+    pts_pm (bs,n,3) f32, init_box (bs,7), bbox_gt (bs,7)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    r = lambda *s: torch.rand(*s, generator=g, device=device)
+    rn = lambda *s: torch.randn(*s, generator=g, device=device)
+    anchors = torch.tensor(spec.MEAN_SIZE_ARR, device=device, dtype=torch.float32)
+    cls = torch.randint(0, 3, (bs,), generator=g, device=device)
+    size = anchors[cls] + 0.1 * rn(bs, 3)
+    n_fg = torch.randint(64, min(3000, n - 1) + 1, (bs, 1), generator=g, device=device)
+    slot = torch.arange(n, device=device)[None, :]
+    kind = torch.where(slot < n_fg, 0, torch.where(r(bs, n) < 1.0 / 3.0, 1, 2))     # 0 fg, 1 ground, 2 clutter
+    u = r(bs, n, 3)
+    fg = (u - 0.5) * size[:, None, :]
+    ground = torch.stack([u[..., 0] * 16 - 8, u[..., 1] * 16 - 8,
+                          -size[:, None, 2].expand(bs, n) / 2 + 0.03 * rn(bs, n)], -1)
+    clutter = (u * 2 - 1) * torch.tensor([8.0, 8.0, 2.0], device=device)
+    pts = torch.where((kind == 0)[..., None], fg, torch.where((kind == 1)[..., None], ground, clutter))
+    perm = torch.argsort(r(bs, n), dim=1)
+    pts = torch.gather(pts, 1, perm[..., None].expand(bs, n, 3)).contiguous()
+    init_box = torch.cat([0.3 * rn(bs, 3), size, 0.1 * rn(bs, 1)], 1)
+    bbox_gt = init_box + 0.05 * rn(bs, 7)
+    return {"pts_pm": pts, "init_box": init_box, "bbox_gt": bbox_gt}

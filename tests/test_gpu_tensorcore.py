@@ -15,7 +15,7 @@ eb = importlib.import_module("3dal_pytorch_b200.engine_bf16")
 eb.CHECK_ABORT = True
 
 
-@pytest.mark.parametrize("N,K", [(64, 64), (128, 64), (128, 128), (256, 256), (16, 16), (96, 48)])
+@pytest.mark.parametrize("N,K", [(64, 64), (128, 64), (128, 128), (256, 256), (16, 16), (96, 48), (32, 512)])
 def test_umma_selftest(N, K):
     torch.manual_seed(N * 1000 + K)
     a = torch.randn(128, K, device=DEV)
