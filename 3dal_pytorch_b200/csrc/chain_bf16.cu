@@ -23,46 +23,92 @@ using namespace umma;
 constexpr int kTile = 128;                 // points per tile == TMEM lanes
 constexpr int kStageBytes = 16384;         // one weight block: 128 rows x 64 K bf16
 constexpr int kPlane = kTile * 16;         // bytes of one activation K-plane (128 rows x 16 B)
-constexpr int kThreads = 192;
+constexpr int kEpiThreads = 256;            // 8 epilogue warps: (lane quarter, column half)
+constexpr int kThreads = 64 + kEpiThreads; // + producer warp + MMA warp
 
+// Epilogue thread geometry: warps 2..9.  A warp may only touch TMEM lanes 32*(warp%4)..+31, so the
+// two warps that share a lane quarter split the accumulator columns between them.
 __device__ __forceinline__ int epi_row() { return ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31); }
+__device__ __forceinline__ int epi_half() { return ((threadIdx.x >> 5) - 2) >> 2; }
+
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi)
+{
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 
 // bias + ReLU + bf16 pack of 32 accumulator columns -> four 16-byte plane rows
 __device__ __forceinline__ void store_act32(uint8_t *buf, int plane0, int row, const uint32_t (&v)[32], const float *bias)
 {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        uint32_t o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float a = fmaxf(__uint_as_float(v[j * 8 + 2 * i]) + bias[j * 8 + 2 * i], 0.f);
-            const float b = fmaxf(__uint_as_float(v[j * 8 + 2 * i + 1]) + bias[j * 8 + 2 * i + 1], 0.f);
-            o[i] = pack_bf16x2(a, b);
-        }
-        *reinterpret_cast<uint4 *>(buf + (plane0 + j) * kPlane + row * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        const float4 b0 = *reinterpret_cast<const float4 *>(bias + j * 8);
+        const float4 b1 = *reinterpret_cast<const float4 *>(bias + j * 8 + 4);
+        uint4 o;
+        o.x = relu_pack_bf16x2(__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y);
+        o.y = relu_pack_bf16x2(__uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w);
+        o.z = relu_pack_bf16x2(__uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y);
+        o.w = relu_pack_bf16x2(__uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w);
+        *reinterpret_cast<uint4 *>(buf + (plane0 + j) * kPlane + row * 16) = o;
     }
 }
 
-// First layer on CUDA cores: x[c] (c < c_in) -> w0 outputs, bf16, into the KP buffer.
-__device__ __forceinline__ void first_layer(uint8_t *buf, int row, const float *xv, int c_in, int w0,
+// Accumulator columns [c0, c0 + NC) of this thread's TMEM lane -> bias + ReLU -> bf16 planes.
+// Two 32-column loads are kept in flight per wait.
+template <int NC>
+__device__ __forceinline__ void epilogue_cols(uint32_t taddr, uint8_t *buf, int c0, int row, const float *bias)
+{
+    static_assert(NC == 32 || NC % 64 == 0, "NC");
+    if constexpr (NC == 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        store_act32(buf, c0 >> 3, row, v, bias + c0);
+    } else {
+#pragma unroll
+        for (int c = 0; c < NC; c += 64) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(taddr + c0 + c, v0);
+            tmem_ld32(taddr + c0 + c + 32, v1);
+            tmem_ld_wait();
+            store_act32(buf, (c0 + c) >> 3, row, v0, bias + c0 + c);
+            store_act32(buf, (c0 + c + 32) >> 3, row, v1, bias + c0 + c + 32);
+        }
+    }
+}
+__device__ __forceinline__ void epilogue_cols_n(int ncols, uint32_t taddr, uint8_t *buf, int c0, int row, const float *bias)
+{
+    if (ncols == 32) epilogue_cols<32>(taddr, buf, c0, row, bias);
+    else if (ncols == 64) epilogue_cols<64>(taddr, buf, c0, row, bias);
+    else epilogue_cols<128>(taddr, buf, c0, row, bias);
+}
+
+// First layer on CUDA cores: x[c] (c < c_in) -> output channels [ch0, ch0 + nch), bf16, into the KP
+// buffer.  Weights are stored transposed in shared memory: sw[c * w0 + ch].
+__device__ __forceinline__ void first_layer(uint8_t *buf, int row, const float *xv, int c_in, int w0, int ch0, int nch,
                                             const float *sw, const float *sb)
 {
-    for (int ch = 0; ch < w0; ch += 8) {
-        uint32_t o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float a = sb[ch + 2 * i], b = sb[ch + 2 * i + 1];
-            const float *wa = sw + (ch + 2 * i) * 8, *wb = wa + 8;     // weights padded to 8 inputs per row
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                a = fmaf(xv[c], wa[c], a);
-                b = fmaf(xv[c], wb[c], b);
-            }
-            o[i] = pack_bf16x2(fmaxf(a, 0.f), fmaxf(b, 0.f));
+    for (int ch = ch0; ch < ch0 + nch; ch += 8) {
+        float4 a0 = *reinterpret_cast<const float4 *>(sb + ch), a1 = *reinterpret_cast<const float4 *>(sb + ch + 4);
+        for (int c = 0; c < c_in; ++c) {
+            const float4 w0v = *reinterpret_cast<const float4 *>(sw + c * w0 + ch);
+            const float4 w1v = *reinterpret_cast<const float4 *>(sw + c * w0 + ch + 4);
+            const float x = xv[c];
+            a0.x = fmaf(x, w0v.x, a0.x); a0.y = fmaf(x, w0v.y, a0.y); a0.z = fmaf(x, w0v.z, a0.z); a0.w = fmaf(x, w0v.w, a0.w);
+            a1.x = fmaf(x, w1v.x, a1.x); a1.y = fmaf(x, w1v.y, a1.y); a1.z = fmaf(x, w1v.z, a1.z); a1.w = fmaf(x, w1v.w, a1.w);
         }
-        *reinterpret_cast<uint4 *>(buf + (ch >> 3) * kPlane + row * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        uint4 o;
+        o.x = relu_pack_bf16x2(a0.x, a0.y); o.y = relu_pack_bf16x2(a0.z, a0.w);
+        o.z = relu_pack_bf16x2(a1.x, a1.y); o.w = relu_pack_bf16x2(a1.z, a1.w);
+        *reinterpret_cast<uint4 *>(buf + (ch >> 3) * kPlane + row * 16) = o;
     }
-    (void)c_in;
 }
 
 // ================================================================================================
@@ -116,7 +162,7 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_kp, const uint8_t *__restrict
 struct ChainParams {
     const float *x; int64_t sb, sc, sp; int bs, n;       // input (bs, c_in, n), strides in elements
     int c_in, w0, n_mid, mid[3], last;
-    const float *w0_w, *w0_b, *mid_b, *last_b;           // fp32: (w0, 8) zero-padded rows, (w0), concat(mid), (last)
+    const float *w0_w, *w0_b, *mid_b, *last_b;           // fp32: (8, w0) transposed + zero-padded, (w0), concat(mid), (last)
     const uint8_t *wstream;                              // packed bf16 blocks, 16 KB slots, consumption order
     float *out;                                          // (bs, last) fp32, zero-initialised; max-pooled with atomicMax
     int splits;                                          // work items per object
@@ -155,9 +201,9 @@ chain_max_kernel(const ChainParams p)
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < kChainStages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
-        mbar_init(&s.act_ready, kTile);
+        mbar_init(&s.act_ready, kEpiThreads);
         mbar_init(&s.acc_ready, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&s.last_full[i], 1); mbar_init(&s.last_empty[i], kTile); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.last_full[i], 1); mbar_init(&s.last_empty[i], kEpiThreads); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<512>(&s.tmem_base);
@@ -248,8 +294,8 @@ chain_max_kernel(const ChainParams p)
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue warps (128 threads)
-        const int row = epi_row();
+        // ------------------------------------------------------------ epilogue warps (256 threads)
+        const int row = epi_row(), half = epi_half();
         const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
         uint32_t acc_phase = 0, lf_phase[2] = {0, 0};
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -260,7 +306,7 @@ chain_max_kernel(const ChainParams p)
             for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
             for (int t = t0; t < t1; ++t) {
                 // ---- first layer (rows past the end of the object replicate its last point: the
-                //      max-pool is idempotent under duplicates)
+                //      max-pool is idempotent under duplicates); each half computes w0/2 channels
                 {
                     int pidx = t * kTile + row;
                     if (pidx > p.n - 1) pidx = p.n - 1;
@@ -268,11 +314,11 @@ chain_max_kernel(const ChainParams p)
                     float xv[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
-                    first_layer(s.bufA, row, xv, p.c_in, p.w0, s.w0_w, s.w0_b);
+                    first_layer(s.bufA, row, xv, p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b);
                     fence_proxy_async_smem();
                     mbar_arrive(&s.act_ready);
                 }
-                // ---- mid layers
+                // ---- mid layers: this thread converts columns [half*N/2, (half+1)*N/2) of its row
                 int boff = 0;
                 for (int l = 0; l < p.n_mid; ++l) {
                     const int N = p.mid[l];
@@ -280,18 +326,13 @@ chain_max_kernel(const ChainParams p)
                     if (!mbar_wait(&s.acc_ready, acc_phase, 0xD100 + l)) goto done;
                     acc_phase ^= 1;
                     tc_fence_after();
-                    for (int c0 = 0; c0 < N; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem + lane_addr + c0, v);
-                        tmem_ld_wait();
-                        store_act32(outb, c0 >> 3, row, v, s.mid_b + boff + c0);
-                    }
+                    epilogue_cols_n(N >> 1, tmem + lane_addr, outb, half * (N >> 1), row, s.mid_b + boff);
                     boff += N;
                     tc_fence_before();
                     fence_proxy_async_smem();
                     mbar_arrive(&s.act_ready);
                 }
-                // ---- last layer: this thread owns channel (cc*128 + row); columns are the tile's points
+                // ---- last layer: this thread owns channel (cc*128 + row) and 64 of the tile's 128 points
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
                     if (cc < n_last_chunks) {
@@ -299,18 +340,26 @@ chain_max_kernel(const ChainParams p)
                         if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0xD200 + cc)) goto done;
                         lf_phase[bsel] ^= 1;
                         tc_fence_after();
-                        float m = rmax[cc];
-#pragma unroll
-                        for (int c0 = 0; c0 < 128; c0 += 32) {
-                            uint32_t v[32];
-                            tmem_ld32(tmem + lane_addr + 256 + bsel * 128 + c0, v);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-                        }
-                        rmax[cc] = m;
+                        uint32_t v0[32], v1[32];
+                        const uint32_t ta = tmem + lane_addr + 256 + bsel * 128 + half * 64;
+                        tmem_ld32(ta, v0);
+                        tmem_ld32(ta + 32, v1);
+                        tmem_ld_wait();
                         tc_fence_before();
-                        mbar_arrive(&s.last_empty[bsel]);
+                        mbar_arrive(&s.last_empty[bsel]);          // the values are in registers: free the buffer early
+                        float m0 = rmax[cc], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            m0 = fmax3(m0, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
+                            m1 = fmax3(m1, __uint_as_float(v0[i + 2]), __uint_as_float(v0[i + 3]));
+                            m2 = fmax3(m2, __uint_as_float(v0[i + 4]), __uint_as_float(v0[i + 5]));
+                            m3 = fmax3(m3, __uint_as_float(v0[i + 6]), __uint_as_float(v0[i + 7]));
+                            m0 = fmax3(m0, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
+                            m1 = fmax3(m1, __uint_as_float(v1[i + 2]), __uint_as_float(v1[i + 3]));
+                            m2 = fmax3(m2, __uint_as_float(v1[i + 4]), __uint_as_float(v1[i + 5]));
+                            m3 = fmax3(m3, __uint_as_float(v1[i + 6]), __uint_as_float(v1[i + 7]));
+                        }
+                        rmax[cc] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                     }
                 }
             }
@@ -354,6 +403,7 @@ struct Pass2Smem {
     uint8_t bufA2[16384];              // conv2 output (64 ch), lives until the last dconv1 chunk
     uint8_t wring[kP2Stages][kStageBytes];
     float w1_w[64 * 8], w1_b[64], b2[64], gb[512], bd2[256], bd3[128], bd4[128], w5[256], b5[2];
+    float lpart[2 * kTile];            // logits partial sums of the upper column half
     uint64_t w_full[kP2Stages], w_empty[kP2Stages];
     uint64_t act_ready, acc_ready;
     uint64_t d1_full[2], d1_act[2], ring_free[2];
@@ -374,9 +424,9 @@ seg_pass2_kernel(const Pass2Params p)
     if (threadIdx.x < 2) s.b5[threadIdx.x] = p.b5[threadIdx.x];
     if (threadIdx.x == 0) {
         for (int i = 0; i < kP2Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
-        mbar_init(&s.act_ready, kTile);
+        mbar_init(&s.act_ready, kEpiThreads);
         mbar_init(&s.acc_ready, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kTile); mbar_init(&s.ring_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kEpiThreads); mbar_init(&s.ring_free[i], 1); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<512>(&s.tmem_base);
@@ -479,8 +529,9 @@ seg_pass2_kernel(const Pass2Params p)
 #undef P2_REL_W
         }
     } else {
-        const int row = epi_row();
+        const int row = epi_row(), half = epi_half();
         const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
+        const int etid = threadIdx.x - 64;                      // 0..255 among the epilogue threads
         uint32_t acc_phase = 0, d1f_phase[2] = {0, 0}, rf_phase[2] = {0, 0};
         int cur_obj = -1;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -488,67 +539,49 @@ seg_pass2_kernel(const Pass2Params p)
             const int pidx_raw = t * kTile + row;
             const bool valid = pidx_raw < p.n;
             const int pidx = valid ? pidx_raw : p.n - 1;
-            // per-object dconv1 bias.  Safe to overwrite here: every reader of s.gb (the dconv1 chunk
-            // epilogues of the previous item) finished before this thread got here, but other epilogue
-            // threads may still be in the previous item's tail, which does not read s.gb.
+            // per-object dconv1 bias: reload when the object changes.  The first barrier makes sure every
+            // epilogue thread is past the previous item's dconv1 epilogues (the only readers of s.gb).
             if (b != cur_obj) {
-                // all 128 epilogue threads must be past the previous item's dconv1 epilogues
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = row; i < 512; i += kTile) s.gb[i] = __ldg(p.gbias + (int64_t)b * 512 + i);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int i = etid; i < 512; i += kEpiThreads) s.gb[i] = __ldg(p.gbias + (int64_t)b * 512 + i);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_obj = b;
             }
-            // ---- conv1 on CUDA cores -> bufD2[0:16K]
+            // ---- conv1 on CUDA cores -> bufD2[0:16K]; each half computes 32 of the 64 channels
             {
                 const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
                 float xv[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
-                first_layer(s.bufD2, row, xv, p.c_in, 64, s.w1_w, s.w1_b);
+                first_layer(s.bufD2, row, xv, p.c_in, 64, half * 32, 32, s.w1_w, s.w1_b);
                 fence_proxy_async_smem();
                 mbar_arrive(&s.act_ready);
             }
-            // ---- conv2 epilogue -> bufA2
+            // ---- conv2 epilogue -> bufA2 (32 columns per thread)
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB100)) goto done;
             acc_phase ^= 1; tc_fence_after();
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_addr + c0, v);
-                tmem_ld_wait();
-                store_act32(s.bufA2, c0 >> 3, row, v, s.b2 + c0);
-            }
+            epilogue_cols<32>(tmem + lane_addr, s.bufA2, half * 32, row, s.b2);
             tc_fence_before(); fence_proxy_async_smem();
             mbar_arrive(&s.act_ready);
-            // ---- dconv1 chunk epilogues -> ring
+            // ---- dconv1 chunk epilogues -> ring (64 columns per thread)
             for (int kc = 0; kc < 4; ++kc) {
                 const int sl = kc & 1;
                 if (!mbar_wait(&s.d1_full[sl], d1f_phase[sl], 0xB200 + kc)) goto done;
                 d1f_phase[sl] ^= 1;
                 // the ring slot is free once dconv2's partial for the chunk that used it last has completed
-                // (first two uses of each item: the previous item's last partials, already waited below)
                 if (kc >= 2) {
                     if (!mbar_wait(&s.ring_free[sl], rf_phase[sl], 0xB300 + kc)) goto done;
                     rf_phase[sl] ^= 1;
                 }
                 tc_fence_after();
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem + lane_addr + 256 + sl * 128 + c0, v);
-                    tmem_ld_wait();
-                    store_act32(s.ring[sl], c0 >> 3, row, v, s.gb + kc * 128 + c0);
-                }
+                epilogue_cols<64>(tmem + lane_addr + 256 + sl * 128, s.ring[sl], half * 64, row, s.gb + kc * 128);
                 tc_fence_before(); fence_proxy_async_smem();
                 mbar_arrive(&s.d1_act[sl]);
             }
-            // ---- dconv2 epilogue -> bufD2 (256 ch)
+            // ---- dconv2 epilogue -> bufD2 (128 columns per thread)
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB101)) goto done;
             acc_phase ^= 1; tc_fence_after();
-            for (int c0 = 0; c0 < 256; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_addr + c0, v);
-                tmem_ld_wait();
-                store_act32(s.bufD2, c0 >> 3, row, v, s.bd2 + c0);
-            }
+            epilogue_cols<128>(tmem + lane_addr, s.bufD2, half * 128, row, s.bd2);
             tc_fence_before(); fence_proxy_async_smem();
             mbar_arrive(&s.act_ready);
             // ---- dconv3 epilogue -> ring[0] (both ring slots are idle: wait out their last partials)
@@ -558,34 +591,51 @@ seg_pass2_kernel(const Pass2Params p)
             }
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB102)) goto done;
             acc_phase ^= 1; tc_fence_after();
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_addr + 256 + c0, v);
-                tmem_ld_wait();
-                store_act32(s.ring[0], c0 >> 3, row, v, s.bd3 + c0);
-            }
+            epilogue_cols<64>(tmem + lane_addr + 256, s.ring[0], half * 64, row, s.bd3);
             tc_fence_before(); fence_proxy_async_smem();
             mbar_arrive(&s.act_ready);
-            // ---- dconv4 epilogue: bias + ReLU in fp32, then the 128 -> 2 layer, logits and mask
+            // ---- dconv4 epilogue: bias + ReLU in fp32, then the 128 -> 2 layer, logits and mask.
+            //      Each half reduces 64 channels; the upper half hands its partial sums over in smem and the
+            //      lower half adds them in a fixed order (deterministic).
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB103)) goto done;
             acc_phase ^= 1; tc_fence_after();
-            float l0 = s.b5[0], l1 = s.b5[1];
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem + lane_addr + 384 + c0, v);
+            {
+                uint32_t v0[32], v1[32];
+                const int c0 = half * 64;
+                tmem_ld32(tmem + lane_addr + 384 + c0, v0);
+                tmem_ld32(tmem + lane_addr + 384 + c0 + 32, v1);
                 tmem_ld_wait();
+                tc_fence_before();
+                float l0a = 0.f, l1a = 0.f, l0b = 0.f, l1b = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float a = fmaxf(__uint_as_float(v[i]) + s.bd4[c0 + i], 0.f);
-                    l0 = fmaf(a, s.w5[c0 + i], l0);
-                    l1 = fmaf(a, s.w5[128 + c0 + i], l1);
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 bb0 = *reinterpret_cast<const float4 *>(s.bd4 + c0 + i);
+                    const float4 bb1 = *reinterpret_cast<const float4 *>(s.bd4 + c0 + 32 + i);
+                    const float4 wa0 = *reinterpret_cast<const float4 *>(s.w5 + c0 + i);
+                    const float4 wb0 = *reinterpret_cast<const float4 *>(s.w5 + 128 + c0 + i);
+                    const float4 wa1 = *reinterpret_cast<const float4 *>(s.w5 + c0 + 32 + i);
+                    const float4 wb1 = *reinterpret_cast<const float4 *>(s.w5 + 128 + c0 + 32 + i);
+                    float a;
+                    a = fmaxf(__uint_as_float(v0[i + 0]) + bb0.x, 0.f); l0a = fmaf(a, wa0.x, l0a); l1a = fmaf(a, wb0.x, l1a);
+                    a = fmaxf(__uint_as_float(v0[i + 1]) + bb0.y, 0.f); l0a = fmaf(a, wa0.y, l0a); l1a = fmaf(a, wb0.y, l1a);
+                    a = fmaxf(__uint_as_float(v0[i + 2]) + bb0.z, 0.f); l0a = fmaf(a, wa0.z, l0a); l1a = fmaf(a, wb0.z, l1a);
+                    a = fmaxf(__uint_as_float(v0[i + 3]) + bb0.w, 0.f); l0a = fmaf(a, wa0.w, l0a); l1a = fmaf(a, wb0.w, l1a);
+                    a = fmaxf(__uint_as_float(v1[i + 0]) + bb1.x, 0.f); l0b = fmaf(a, wa1.x, l0b); l1b = fmaf(a, wb1.x, l1b);
+                    a = fmaxf(__uint_as_float(v1[i + 1]) + bb1.y, 0.f); l0b = fmaf(a, wa1.y, l0b); l1b = fmaf(a, wb1.y, l1b);
+                    a = fmaxf(__uint_as_float(v1[i + 2]) + bb1.z, 0.f); l0b = fmaf(a, wa1.z, l0b); l1b = fmaf(a, wb1.z, l1b);
+                    a = fmaxf(__uint_as_float(v1[i + 3]) + bb1.w, 0.f); l0b = fmaf(a, wa1.w, l0b); l1b = fmaf(a, wb1.w, l1b);
                 }
-            }
-            tc_fence_before();
-            if (valid) {
-                const int64_t o = (int64_t)b * p.n + pidx;
-                *reinterpret_cast<float2 *>(p.logits + o * 2) = make_float2(l0, l1);
-                p.mask[o] = (l0 < l1) ? 1 : 0;
+                const float l0 = l0a + l0b, l1 = l1a + l1b;
+                if (half == 1) { s.lpart[row] = l0; s.lpart[kTile + row] = l1; }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (half == 0 && valid) {
+                    const float f0 = (s.b5[0] + l0) + s.lpart[row];
+                    const float f1 = (s.b5[1] + l1) + s.lpart[kTile + row];
+                    const int64_t o = (int64_t)b * p.n + pidx;
+                    *reinterpret_cast<float2 *>(p.logits + o * 2) = make_float2(f0, f1);
+                    p.mask[o] = (f0 < f1) ? 1 : 0;
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");     // lpart may be rewritten by the next item
             }
         }
     }

@@ -45,8 +45,9 @@ def _block(w_blk):
 
 
 def _pad8(w):
-    out = torch.zeros((w.shape[0], 8), dtype=torch.float32, device=w.device)
-    out[:, : w.shape[1]] = w
+    """(w0, c_in) first-layer weights -> (8, w0) transposed, zero rows for c >= c_in."""
+    out = torch.zeros((8, w.shape[0]), dtype=torch.float32, device=w.device)
+    out[: w.shape[1], :] = w.t()
     return out.contiguous()
 
 

@@ -119,7 +119,7 @@ typedef struct al3d_chain_weights {
     int32_t mid[3];          /* their widths (64 / 128 / 256)                                     */
     int32_t last;            /* width of the max-pooled last layer (512 / 1024)                   */
     int32_t n_blocks;        /* number of 16 KB blocks in wstream                                 */
-    const float *w0_w;       /* (w0, 8) fp32, rows zero-padded to 8 inputs                        */
+    const float *w0_w;       /* (8, w0) fp32, transposed, zero rows for c >= c_in                */
     const float *w0_b;       /* (w0)                                                              */
     const float *mid_b;      /* concatenated fp32 biases of the mid layers                        */
     const float *last_b;     /* (last)                                                            */
@@ -136,7 +136,7 @@ int al3d_chain_maxpool_bf16(const al3d_chain_weights *w, const float *x, int64_t
 typedef struct al3d_pass2_weights {
     int32_t c_in;
     int32_t reserved;
-    const float *w1_w, *w1_b;      /* ins_seg.conv1 folded fp32: (64,8) zero-padded, (64)          */
+    const float *w1_w, *w1_b;      /* ins_seg.conv1 folded fp32: (8,64) transposed + padded, (64)  */
     const float *b2;               /* conv2 bias (64)                                               */
     const float *bd2, *bd3, *bd4;  /* dconv2-4 biases (256),(128),(128)                             */
     const float *w5, *b5;          /* dconv5 fp32 (2,128), (2)                                      */

@@ -48,7 +48,7 @@ def test_chain_stream_order_matches_kernel_loops():
         prev = N
     assert blk == pack.struct.n_blocks == blocks.shape[0]
     assert (pack.struct.w0, pack.struct.n_mid, list(pack.struct.mid)[:2], pack.struct.last) == (128, 2, [128, 256], 512)
-    assert pack.t["w0_w"].shape == (128, 8) and torch.equal(pack.t["w0_w"][:, :3], fw["conv1"][0])
+    assert pack.t["w0_w"].shape == (8, 128) and torch.equal(pack.t["w0_w"][:3, :], fw["conv1"][0].t())
 
 
 def test_pass2_stream_order_matches_kernel_schedule():
