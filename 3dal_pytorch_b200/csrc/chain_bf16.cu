@@ -97,7 +97,9 @@ __device__ __forceinline__ void first_layer(uint8_t *buf, int row, const float *
 {
     for (int ch = ch0; ch < ch0 + nch; ch += 8) {
         float4 a0 = *reinterpret_cast<const float4 *>(sb + ch), a1 = *reinterpret_cast<const float4 *>(sb + ch + 4);
-        for (int c = 0; c < c_in; ++c) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= c_in) break;
             const float4 w0v = *reinterpret_cast<const float4 *>(sw + c * w0 + ch);
             const float4 w1v = *reinterpret_cast<const float4 *>(sw + c * w0 + ch + 4);
             const float x = xv[c];
