@@ -28,6 +28,7 @@ _SIGNATURES = {
     "al3d_seg_pass2_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp],
     "al3d_umma_selftest": [_vp, _vp, _i, _i, _vp, _i, _vp],
     "al3d_tc_abort_code": [_vp],
+    "al3d_set_debug_buffer": [_vp],
 }
 _RESTYPES = {"al3d_last_error": ctypes.c_char_p}
 
@@ -59,7 +60,7 @@ def lib():
 
 # kernels launched through this binding since import (bench.py reports it as gpu_launches)
 LAUNCHES = 0
-_NO_LAUNCH = ("tc_abort_code",)
+_NO_LAUNCH = ("tc_abort_code", "set_debug_buffer")
 
 
 def check(rc, what=""):

@@ -169,20 +169,23 @@ struct ChainParams {
     float *out;                                          // (bs, last) fp32, zero-initialised; max-pooled with atomicMax
     int splits;                                          // work items per object
     int n_items;
+    int bufA_bytes, bufB_bytes, n_stages;                // shared-memory carve-up chosen by the launcher
 };
 
-constexpr int kChainStages = 6;
-struct ChainSmem {
-    uint8_t bufA[65536];
-    uint8_t bufB[32768];
-    uint8_t wring[kChainStages][kStageBytes];
+constexpr int kChainMaxStages = 12;
+// Dynamic shared memory: [bufA | bufB | weight ring (n_stages x 16 KB) | ChainSmemTail]
+struct ChainSmemTail {
     float w0_w[128 * 8];
     float w0_b[128];
     float mid_b[512];
-    uint64_t w_full[kChainStages], w_empty[kChainStages];
+    uint64_t w_full[kChainMaxStages], w_empty[kChainMaxStages];
     uint64_t act_ready, acc_ready;
     uint64_t last_full[2], last_empty[2];
     uint32_t tmem_base;
+};
+struct ChainSmemView {
+    uint8_t *bufA, *bufB, *wring;
+    ChainSmemTail *t;
 };
 
 __device__ __forceinline__ int chain_in_width(const ChainParams &p, int l) { return l == 0 ? p.w0 : p.mid[l - 1]; }
@@ -191,7 +194,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 chain_max_kernel(const ChainParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    ChainSmem &s = *reinterpret_cast<ChainSmem *>(smem_raw);
+    uint8_t *const s_bufA = smem_raw;
+    uint8_t *const s_bufB = smem_raw + p.bufA_bytes;
+    uint8_t *const s_wring = s_bufB + p.bufB_bytes;
+    ChainSmemTail &s = *reinterpret_cast<ChainSmemTail *>(s_wring + (size_t)p.n_stages * kStageBytes);
+    const int kChainStages = p.n_stages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < p.w0 * 8; i += kThreads) s.w0_w[i] = p.w0_w[i];
@@ -235,7 +242,7 @@ chain_max_kernel(const ChainParams p)
                             if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0xC100 + stage)) goto done;
                             const uint32_t bytes = rows * 64 * 2;
                             mbar_arrive_expect_tx(&s.w_full[stage], bytes);
-                            bulk_g2s(s.wring[stage], p.wstream + (size_t)blk * kStageBytes, bytes, &s.w_full[stage]);
+                            bulk_g2s((s_wring + (size_t)stage * kStageBytes), p.wstream + (size_t)blk * kStageBytes, bytes, &s.w_full[stage]);
                             if (++stage == kChainStages) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -246,7 +253,7 @@ chain_max_kernel(const ChainParams p)
         // ------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
             int stage = 0; uint32_t wphase = 0, act_phase = 0, le_phase[2] = {0, 0};
-            const uint32_t aA = smem_u32(s.bufA), aB = smem_u32(s.bufB);
+            const uint32_t aA = smem_u32(s_bufA), aB = smem_u32(s_bufB);
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int sp_i = item % p.splits;
                 const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
@@ -264,7 +271,7 @@ chain_max_kernel(const ChainParams p)
                             for (int kb = 0; kb < K / 64; ++kb) {
                                 if (!mbar_wait(&s.w_full[stage], wphase, 0xC300 + stage)) goto done;
                                 tc_fence_after();
-                                mma_block_k64(tmem + nc * 128, in_addr + kb * 8 * kPlane, 128, smem_u32(s.wring[stage]), rows, idesc, kb > 0);
+                                mma_block_k64(tmem + nc * 128, in_addr + kb * 8 * kPlane, 128, smem_u32((s_wring + (size_t)stage * kStageBytes)), rows, idesc, kb > 0);
                                 mma_commit(&s.w_empty[stage]);
                                 if (++stage == kChainStages) { stage = 0; wphase ^= 1; }
                             }
@@ -285,7 +292,7 @@ chain_max_kernel(const ChainParams p)
                             for (int kb = 0; kb < k_last / 64; ++kb) {
                                 if (!mbar_wait(&s.w_full[stage], wphase, 0xC500 + stage)) goto done;
                                 tc_fence_after();
-                                mma_block_k64(tmem + 256 + b * 128, smem_u32(s.wring[stage]), 128, in_addr + kb * 8 * kPlane, 128, idesc, kb > 0);
+                                mma_block_k64(tmem + 256 + b * 128, smem_u32((s_wring + (size_t)stage * kStageBytes)), 128, in_addr + kb * 8 * kPlane, 128, idesc, kb > 0);
                                 mma_commit(&s.w_empty[stage]);
                                 if (++stage == kChainStages) { stage = 0; wphase ^= 1; }
                             }
@@ -316,7 +323,7 @@ chain_max_kernel(const ChainParams p)
                     float xv[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
-                    first_layer(s.bufA, row, xv, p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b);
+                    first_layer(s_bufA, row, xv, p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b);
                     fence_proxy_async_smem();
                     mbar_arrive(&s.act_ready);
                 }
@@ -324,7 +331,7 @@ chain_max_kernel(const ChainParams p)
                 int boff = 0;
                 for (int l = 0; l < p.n_mid; ++l) {
                     const int N = p.mid[l];
-                    uint8_t *outb = (l & 1) ? s.bufA : s.bufB;
+                    uint8_t *outb = (l & 1) ? s_bufA : s_bufB;
                     if (!mbar_wait(&s.acc_ready, acc_phase, 0xD100 + l)) goto done;
                     acc_phase ^= 1;
                     tc_fence_after();
@@ -396,7 +403,13 @@ struct Pass2Params {
     float *logits;                     // (bs, n, 2)
     uint8_t *mask;                     // (bs, n)
     int tiles_per_obj; int n_items;    // items = bs * tiles_per_obj
+    long long *dbg;                    // optional clock64 timeline of CTA 0 (al3d_set_debug_buffer), else NULL
 };
+
+// timeline stamps: role 0 = MMA thread, 1 = epilogue thread 0, 2 = producer; 64 stamps x 4 items each
+#define AL3D_TS(role)                                                                         \
+    do { if (p.dbg && blockIdx.x == 0 && it_local < 4 && ts_i < 64)                            \
+             p.dbg[((role) * 4 + it_local) * 64 + ts_i++] = clock64(); } while (0)
 
 constexpr int kP2Stages = 4;
 struct Pass2Smem {
@@ -442,9 +455,12 @@ seg_pass2_kernel(const Pass2Params p)
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int it_local = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+                int ts_i = 0;
                 for (int blk = 0; blk < 27; ++blk) {
                     if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0xA100 + stage)) goto done;
+                    AL3D_TS(2);
                     const uint32_t bytes = (blk == 0) ? 64 * 64 * 2 : kStageBytes;
                     mbar_arrive_expect_tx(&s.w_full[stage], bytes);
                     bulk_g2s(s.wring[stage], p.wstream + (size_t)blk * kStageBytes, bytes, &s.w_full[stage]);
@@ -460,13 +476,18 @@ seg_pass2_kernel(const Pass2Params p)
             const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128);
 #define P2_NEXT_W(code)                                                          \
             if (!mbar_wait(&s.w_full[stage], wphase, code + stage)) goto done;   \
+            AL3D_TS(0);                                                          \
             tc_fence_after();
 #define P2_REL_W()                                                               \
             mma_commit(&s.w_empty[stage]);                                       \
             if (++stage == kP2Stages) { stage = 0; wphase ^= 1; }
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int it_local = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+                int ts_i = 0;
+                AL3D_TS(0);
                 // conv2 : A = conv1 output (64 ch) in bufD2[0:16K]
                 if (!mbar_wait(&s.act_ready, act_phase, 0xA200)) goto done;
+                AL3D_TS(0);
                 act_phase ^= 1; tc_fence_after();
                 P2_NEXT_W(0xA300)
                 mma_block_k64(tmem, aX, 128, smem_u32(s.wring[stage]), 64, id64, false);
@@ -474,6 +495,7 @@ seg_pass2_kernel(const Pass2Params p)
                 mma_commit(&s.acc_ready);
                 // dconv1 chunks interleaved with dconv2 partial sums
                 if (!mbar_wait(&s.act_ready, act_phase, 0xA201)) goto done;    // conv2 output in bufA2
+                AL3D_TS(0);
                 act_phase ^= 1; tc_fence_after();
                 for (int kc = 0; kc < 4; ++kc) {
                     // dconv1 chunk kc -> TMEM 256 + (kc&1)*128.  The buffer was drained by the epilogue of
@@ -485,6 +507,7 @@ seg_pass2_kernel(const Pass2Params p)
                     if (kc >= 1) {
                         const int pc = kc - 1, sl = pc & 1;                   // dconv2 partial for chunk kc-1
                         if (!mbar_wait(&s.d1_act[sl], d1a_phase[sl], 0xA400 + pc)) goto done;
+                        AL3D_TS(0);
                         d1a_phase[sl] ^= 1; tc_fence_after();
                         for (int nc = 0; nc < 2; ++nc)
                             for (int kb = 0; kb < 2; ++kb) {
@@ -498,6 +521,7 @@ seg_pass2_kernel(const Pass2Params p)
                 {
                     const int pc = 3, sl = 1;
                     if (!mbar_wait(&s.d1_act[sl], d1a_phase[sl], 0xA400 + pc)) goto done;
+                    AL3D_TS(0);
                     d1a_phase[sl] ^= 1; tc_fence_after();
                     for (int nc = 0; nc < 2; ++nc)
                         for (int kb = 0; kb < 2; ++kb) {
@@ -510,6 +534,7 @@ seg_pass2_kernel(const Pass2Params p)
                 }
                 // dconv3 : A = bufD2 (256 ch) -> TMEM 256..383
                 if (!mbar_wait(&s.act_ready, act_phase, 0xA202)) goto done;
+                AL3D_TS(0);
                 act_phase ^= 1; tc_fence_after();
                 for (int kb = 0; kb < 4; ++kb) {
                     P2_NEXT_W(0xA340)
@@ -519,6 +544,7 @@ seg_pass2_kernel(const Pass2Params p)
                 mma_commit(&s.acc_ready);
                 // dconv4 : A = ring[0] (128 ch) -> TMEM 384..511
                 if (!mbar_wait(&s.act_ready, act_phase, 0xA203)) goto done;
+                AL3D_TS(0);
                 act_phase ^= 1; tc_fence_after();
                 for (int kb = 0; kb < 2; ++kb) {
                     P2_NEXT_W(0xA350)
@@ -536,7 +562,12 @@ seg_pass2_kernel(const Pass2Params p)
         const int etid = threadIdx.x - 64;                      // 0..255 among the epilogue threads
         uint32_t acc_phase = 0, d1f_phase[2] = {0, 0}, rf_phase[2] = {0, 0};
         int cur_obj = -1;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int it_local = 0;
+        const bool ts_on = (threadIdx.x == 64);
+#define AL3D_TSE() do { if (ts_on) AL3D_TS(1); } while (0)
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+            int ts_i = 0;
+            AL3D_TSE();
             const int b = item / p.tiles_per_obj, t = item % p.tiles_per_obj;
             const int pidx_raw = t * kTile + row;
             const bool valid = pidx_raw < p.n;
@@ -555,16 +586,20 @@ seg_pass2_kernel(const Pass2Params p)
                 float xv[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+                AL3D_TSE();
                 first_layer(s.bufD2, row, xv, p.c_in, 64, half * 32, 32, s.w1_w, s.w1_b);
                 fence_proxy_async_smem();
                 mbar_arrive(&s.act_ready);
+                AL3D_TSE();
             }
             // ---- conv2 epilogue -> bufA2 (32 columns per thread)
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB100)) goto done;
+            AL3D_TSE();
             acc_phase ^= 1; tc_fence_after();
             epilogue_cols<32>(tmem + lane_addr, s.bufA2, half * 32, row, s.b2);
             tc_fence_before(); fence_proxy_async_smem();
             mbar_arrive(&s.act_ready);
+            AL3D_TSE();
             // ---- dconv1 chunk epilogues -> ring (64 columns per thread)
             for (int kc = 0; kc < 4; ++kc) {
                 const int sl = kc & 1;
@@ -575,31 +610,49 @@ seg_pass2_kernel(const Pass2Params p)
                     if (!mbar_wait(&s.ring_free[sl], rf_phase[sl], 0xB300 + kc)) goto done;
                     rf_phase[sl] ^= 1;
                 }
+                AL3D_TSE();
                 tc_fence_after();
-                epilogue_cols<64>(tmem + lane_addr + 256 + sl * 128, s.ring[sl], half * 64, row, s.gb + kc * 128);
+                {
+                    uint32_t v0[32], v1[32];
+                    const uint32_t ta = tmem + lane_addr + 256 + sl * 128 + half * 64;
+                    tmem_ld32(ta, v0);
+                    tmem_ld32(ta + 32, v1);
+                    tmem_ld_wait();
+                    AL3D_TSE();
+                    store_act32(s.ring[sl], (half * 64) >> 3, row, v0, s.gb + kc * 128 + half * 64);
+                    store_act32(s.ring[sl], (half * 64 + 32) >> 3, row, v1, s.gb + kc * 128 + half * 64 + 32);
+                    AL3D_TSE();
+                }
                 tc_fence_before(); fence_proxy_async_smem();
+                AL3D_TSE();
                 mbar_arrive(&s.d1_act[sl]);
+                AL3D_TSE();
             }
             // ---- dconv2 epilogue -> bufD2 (128 columns per thread)
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB101)) goto done;
+            AL3D_TSE();
             acc_phase ^= 1; tc_fence_after();
             epilogue_cols<128>(tmem + lane_addr, s.bufD2, half * 128, row, s.bd2);
             tc_fence_before(); fence_proxy_async_smem();
             mbar_arrive(&s.act_ready);
+            AL3D_TSE();
             // ---- dconv3 epilogue -> ring[0] (both ring slots are idle: wait out their last partials)
             for (int sl = 0; sl < 2; ++sl) {
                 if (!mbar_wait(&s.ring_free[sl], rf_phase[sl], 0xB310 + sl)) goto done;
                 rf_phase[sl] ^= 1;
             }
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB102)) goto done;
+            AL3D_TSE();
             acc_phase ^= 1; tc_fence_after();
             epilogue_cols<64>(tmem + lane_addr + 256, s.ring[0], half * 64, row, s.bd3);
             tc_fence_before(); fence_proxy_async_smem();
             mbar_arrive(&s.act_ready);
+            AL3D_TSE();
             // ---- dconv4 epilogue: bias + ReLU in fp32, then the 128 -> 2 layer, logits and mask.
             //      Each half reduces 64 channels; the upper half hands its partial sums over in smem and the
             //      lower half adds them in a fixed order (deterministic).
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB103)) goto done;
+            AL3D_TSE();
             acc_phase ^= 1; tc_fence_after();
             {
                 uint32_t v0[32], v1[32];
@@ -638,6 +691,7 @@ seg_pass2_kernel(const Pass2Params p)
                     p.mask[o] = (f0 < f1) ? 1 : 0;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");     // lpart may be rewritten by the next item
+                AL3D_TSE();
             }
         }
     }
@@ -650,6 +704,9 @@ done:
 }  // namespace al3d
 
 using namespace al3d;
+
+static long long *g_debug_buffer = nullptr;
+extern "C" int al3d_set_debug_buffer(void *dev_ptr) { g_debug_buffer = (long long *)dev_ptr; return 0; }
 
 extern "C" int al3d_tc_abort_code(int *code_host)
 {
@@ -718,7 +775,19 @@ extern "C" int al3d_chain_maxpool_bf16(const al3d_chain_weights *w, const float 
     p.splits = splits;
     p.n_items = bs * splits;
     const int grid = std::min(p.n_items, sms);
-    const size_t smem = sizeof(ChainSmem) + 128;
+    // activation buffers sized for this chain (layer 0 and odd mid layers write A, even mid layers write B);
+    // whatever shared memory is left becomes weight-ring stages: the deeper the ring, the better the
+    // L2 -> smem latency of the weight stream is hidden.
+    int wA = w->w0, wB = 0;
+    for (int l = 0; l < w->n_mid; ++l) { if (l & 1) wA = std::max(wA, w->mid[l]); else wB = std::max(wB, w->mid[l]); }
+    p.bufA_bytes = wA * kTile * 2;
+    p.bufB_bytes = wB * kTile * 2;
+    const int budget = 232448 - 1024;            // 227 KB opt-in limit minus static smem / alignment slack
+    int stages = (budget - p.bufA_bytes - p.bufB_bytes - (int)sizeof(ChainSmemTail)) / kStageBytes;
+    stages = std::min(stages, kChainMaxStages);
+    AL3D_CHECK_ARG(stages >= 2, "al3d_chain_maxpool_bf16: no room for the weight ring");
+    p.n_stages = stages;
+    const size_t smem = (size_t)p.bufA_bytes + p.bufB_bytes + (size_t)stages * kStageBytes + sizeof(ChainSmemTail);
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(chain_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     chain_max_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
     AL3D_CHECK_LAUNCH("chain_max_kernel");
@@ -736,7 +805,7 @@ extern "C" int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, 
     p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n; p.c_in = w->c_in;
     p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.gbias = gbias;
     p.bd2 = w->bd2; p.bd3 = w->bd3; p.bd4 = w->bd4; p.w5 = w->w5; p.b5 = w->b5;
-    p.wstream = (const uint8_t *)w->wstream; p.logits = logits; p.mask = mask;
+    p.wstream = (const uint8_t *)w->wstream; p.logits = logits; p.mask = mask; p.dbg = g_debug_buffer;
     p.tiles_per_obj = (n + kTile - 1) / kTile;
     const int64_t items = (int64_t)bs * p.tiles_per_obj;
     AL3D_CHECK_ARG(items < (1ll << 31), "al3d_seg_pass2_bf16: too many tiles");
