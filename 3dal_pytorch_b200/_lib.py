@@ -24,6 +24,12 @@ _SIGNATURES = {
     "al3d_parse_heads": [_vp, _i, _vp, _i64] + [_vp] * 8 + [_vp],
     "al3d_decode_boxes": [_vp] * 6 + [_i64, _i, _vp, _vp, _vp],
     "al3d_twostage_retransform": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "al3d_crop_chunk_points": [],
+    "al3d_crop_build_grid": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
+    "al3d_crop_hits": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp],
+    "al3d_crop_scan": [_vp, _vp, _i, _i64, _vp, _i, _vp, _vp, _vp],
+    "al3d_crop_fill": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "al3d_crop_dense_mask": [_vp, _vp, _i, _vp, _vp],
     "al3d_chain_maxpool_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
     "al3d_seg_pass2_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp],
     "al3d_umma_selftest": [_vp, _vp, _i, _i, _vp, _i, _vp],
@@ -60,7 +66,7 @@ def lib():
 
 # kernels launched through this binding since import (bench.py reports it as gpu_launches)
 LAUNCHES = 0
-_NO_LAUNCH = ("tc_abort_code", "set_debug_buffer")
+_NO_LAUNCH = ("tc_abort_code", "set_debug_buffer", "crop_chunk_points")
 
 
 def check(rc, what=""):

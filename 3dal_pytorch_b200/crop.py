@@ -1,0 +1,161 @@
+"""Points-in-rotated-box crop on the GPU (host side of csrc/crop.cu).
+
+Drop-in for ``box_np_ops.points_in_rbbox`` (det3d/core/bbox/box_np_ops.py:641-647) and for the per-box
+crop loop of ``_create_pd_detection`` (det3d/datasets/waymo/waymo_common.py:167-171), batched over
+frames.  The box -> corner -> plane arithmetic is done here on the host with numpy float32 element-wise
+operations in the reference's own order (corners_nd / rotation_3d_in_axis / center_to_corner_box3d
+box_np_ops.py:55-85,146-179,241-262; corner_to_surfaces_3d :650-670; surface_equ_3d_jitv2
+geometry.py:351-377): it is 6x4 floats per box, and it keeps numpy's float32 sin/cos in the loop so the
+device predicate sees bit-identical plane equations.  The N x B point tests, the ordered compaction,
+the gather and the float64 pose transform run in libal3d.so.
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+GRID = 64                     # BEV cells per side
+AABB_PAD = 0.05               # metres; far above the ~1e-4 m rounding slack of the plane test
+_SIGNS = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 1], [0, 1, 0], [1, 0, 0], [1, 0, 1], [1, 1, 1], [1, 1, 0]],
+                  dtype=np.float32) - np.float32(0.5)
+_QUADS = np.array([[0, 1, 2, 3], [7, 6, 5, 4], [0, 3, 7, 4], [1, 5, 6, 2], [0, 4, 5, 1], [3, 2, 6, 7]])
+
+
+def detector_to_waymo(box3d):
+    """CenterPoint [x,y,z,w,l,h,r2] -> Waymo [x,y,z,l,w,h,r1 = -r2 - pi/2] (waymo_common.py:110-111)."""
+    b = np.array(box3d, copy=True)
+    b[:, -1] = -b[:, -1] - np.pi / 2
+    return b[:, [0, 1, 2, 4, 3, 5, -1]]
+
+
+def box_planes_host(boxes):
+    """(B,7) f32 [x,y,z,l,w,h,heading] -> planes (B,6,4) f32 (inward normals, d) and padded
+    rectangles (B,6) f32 [xmin,ymin,zmin,xmax,ymax,zmax]."""
+    boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 7)
+    f0, f1 = np.float32(0), np.float32(1)
+    loc = boxes[:, None, 3:6] * _SIGNS[None]
+    s, c = np.sin(boxes[:, 6])[:, None], np.cos(boxes[:, 6])[:, None]
+    x, y, z = loc[..., 0], loc[..., 1], loc[..., 2]
+    corners = np.stack([x * c + y * s + z * f0, x * (-s) + y * c + z * f0, x * f0 + y * f0 + z * f1], -1).astype(np.float32)
+    corners += boxes[:, None, 0:3]
+    q = corners[:, _QUADS, :]                                 # (B,6,4,3)
+    a = q[:, :, 0] - q[:, :, 1]
+    b = q[:, :, 1] - q[:, :, 2]
+    nx = a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1]
+    ny = a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2]
+    nz = a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]
+    d = -q[:, :, 0, 0] * nx - q[:, :, 0, 1] * ny - q[:, :, 0, 2] * nz
+    planes = np.stack([nx, ny, nz, d], -1).astype(np.float32)
+    pad = np.float32(AABB_PAD) + np.float32(1e-5) * np.abs(corners).max(axis=1)
+    aabb = np.concatenate([corners.min(axis=1) - pad, corners.max(axis=1) + pad], axis=1).astype(np.float32)
+    return np.ascontiguousarray(planes), np.ascontiguousarray(aabb)
+
+
+def _check_overflow(flag, what):
+    code = int(flag.item())
+    if code:
+        names = {1: "cell list capacity", 2: "a point lies inside more than 4 boxes", 3: "per-chunk hit capacity",
+                 4: "output capacity"}
+        raise OverflowError("crop %s: %s (code %d)" % (what, names.get(code, "?"), code))
+
+
+def crop_frames(points, boxes, poses=None, device="cuda", want_xyz=True, hit_cap=None, capacity=None):
+    """points: list of (N_f, >=3) f32 arrays / CUDA tensors; boxes: list of (B_f, 7) f32 Waymo-convention
+    arrays; poses: optional list of 4x4 f64 vehicle->global matrices.
+
+    Returns dict(indices (T,) i32 CUDA -- point index within its frame, ascending per box;
+                 offsets (sum B_f + 1,) i64 CUDA -- box b of frame f owns indices[offsets[k]:offsets[k+1]], k = box_off[f]+b;
+                 box_off (F+1,) i64 host; xyz (T,3) f32; xyz_global (T,3) f64 when poses are given).
+    With ``capacity`` set no host synchronisation happens (the output is over-allocated); otherwise the total
+    count is read back once to size the outputs exactly."""
+    lib = _lib.lib()
+    dev = torch.device(device)
+    F = len(points)
+    pts_t = [torch.as_tensor(p, dtype=torch.float32).to(dev) for p in points]
+    stride = 3
+    pts_all = torch.cat([p[:, :3].contiguous() for p in pts_t], 0) if F else torch.zeros((0, 3), device=dev)
+    n_pts = [int(p.shape[0]) for p in pts_t]
+    pt_off = np.concatenate([[0], np.cumsum(n_pts)]).astype(np.int64)
+    nb = [int(np.asarray(b).reshape(-1, 7).shape[0]) for b in boxes]
+    box_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+    TB = int(box_off[-1])
+    if TB:
+        planes, aabb = box_planes_host(np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 7) for b in boxes], 0))
+    else:
+        planes, aabb = np.zeros((0, 6, 4), np.float32), np.zeros((0, 6), np.float32)
+    max_boxes = max(1, max(nb) if nb else 1)
+    CH = lib.al3d_crop_chunk_points()
+    chunks, frame_chunk_off = [], [0]
+    for f in range(F):
+        k = 0
+        for first in range(0, n_pts[f], CH):
+            chunks.append((f, first, min(CH, n_pts[f] - first), k))
+            k += 1
+        frame_chunk_off.append(len(chunks))
+    n_chunks = len(chunks)
+    hit_cap = int(hit_cap or 1024)
+    cell_cap = 64 * max_boxes + GRID * GRID
+
+    i32 = lambda *s: torch.empty(s, device=dev, dtype=torch.int32)
+    d_planes = torch.from_numpy(planes).to(dev)
+    d_aabb = torch.from_numpy(aabb).to(dev)
+    d_pt_off = torch.from_numpy(pt_off).to(dev)
+    d_box_off = torch.from_numpy(box_off).to(dev)
+    d_chunks = torch.tensor(chunks, dtype=torch.int32, device=dev).reshape(-1, 4)
+    d_fco = torch.tensor(frame_chunk_off, dtype=torch.int64, device=dev)
+    meta = torch.empty((max(F, 1), 4), device=dev, dtype=torch.float32)
+    cell_start = i32(max(F, 1), GRID * GRID + 1)
+    cell_boxes = i32(max(F, 1), cell_cap)
+    overflow = torch.zeros((1,), device=dev, dtype=torch.int32)
+    hits = torch.empty((max(n_chunks, 1), hit_cap, 2), device=dev, dtype=torch.int32)
+    n_hits = i32(max(n_chunks, 1))
+    cbc = i32(max(n_chunks, 1), max_boxes)
+    box_total = i32(max(TB, 1))
+    offsets = torch.zeros((TB + 1,), device=dev, dtype=torch.int64)
+    st = ops._stream()
+    p = lambda t: t.data_ptr()
+
+    _lib.check(lib.al3d_crop_build_grid(p(d_aabb), p(d_box_off), F, GRID, p(meta), p(cell_start), p(cell_boxes), cell_cap,
+                                        p(overflow), st), "crop_build_grid")
+    _lib.check(lib.al3d_crop_hits(p(pts_all), stride, p(d_pt_off), p(d_planes), p(d_box_off), GRID, p(meta), p(cell_start),
+                                  p(cell_boxes), cell_cap, p(d_chunks), n_chunks, p(hits), hit_cap, p(n_hits), p(cbc),
+                                  max_boxes, p(overflow), st), "crop_hits")
+    _lib.check(lib.al3d_crop_scan(p(d_box_off), p(d_fco), F, TB, p(cbc), max_boxes, p(box_total), p(offsets), st), "crop_scan")
+    if capacity is None:
+        _check_overflow(overflow, "hits")
+        capacity = int(offsets[-1].item())                    # the one host read: sizes the outputs exactly
+    out_idx = i32(max(capacity, 1))[:capacity]
+    out_xyz = torch.empty((max(capacity, 1), 3), device=dev, dtype=torch.float32)[:capacity] if want_xyz else None
+    d_poses, out_glob = None, None
+    if poses is not None:
+        d_poses = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(P, dtype=np.float64).reshape(4, 4) for P in poses])
+                                                        if F else np.zeros((0, 4, 4)))).to(dev)
+        out_glob = torch.empty((max(capacity, 1), 3), device=dev, dtype=torch.float64)[:capacity]
+    _lib.check(lib.al3d_crop_fill(p(pts_all), stride, p(d_pt_off), p(d_box_off), p(d_chunks), n_chunks, p(hits), hit_cap,
+                                  p(n_hits), p(cbc), max_boxes, p(offsets), p(d_poses) if d_poses is not None else None,
+                                  capacity, p(out_idx), p(out_xyz) if out_xyz is not None else None,
+                                  p(out_glob) if out_glob is not None else None, p(overflow), st), "crop_fill")
+    return {"indices": out_idx, "offsets": offsets, "box_off": box_off, "xyz": out_xyz, "xyz_global": out_glob,
+            "overflow": overflow, "algorithmic_bytes": int(pts_all.shape[0]) * 12 + TB * 96}
+
+
+def points_in_rbbox(points, rbbox, z_axis=2, origin=(0.5, 0.5, 0.5), device="cuda"):
+    """Same signature and (N, B) bool numpy result as box_np_ops.points_in_rbbox (float32 points)."""
+    if z_axis != 2 or tuple(origin) != (0.5, 0.5, 0.5):
+        raise NotImplementedError("only the lidar convention used by the 3DAL path (z_axis=2, origin 0.5) is built")
+    pts = np.asarray(points)
+    if pts.dtype != np.float32:
+        raise TypeError("GPU crop takes float32 points (the reference's float64 specialisation is label-only)")
+    rb = np.asarray(rbbox, dtype=np.float32).reshape(-1, 7)
+    N, B = pts.shape[0], rb.shape[0]
+    if N == 0 or B == 0:
+        return np.zeros((N, B), dtype=bool)
+    try:
+        res = crop_frames([pts], [rb], device=device, want_xyz=False)
+    except OverflowError:
+        res = crop_frames([pts], [rb], device=device, want_xyz=False, hit_cap=8192)
+    _check_overflow(res["overflow"], "fill")
+    mask = torch.zeros((N, B), device=res["indices"].device, dtype=torch.uint8)
+    _lib.check(_lib.lib().al3d_crop_dense_mask(res["indices"].data_ptr(), res["offsets"].data_ptr(), B, mask.data_ptr(),
+                                               ops._stream()), "crop_dense_mask")
+    return mask.cpu().numpy().astype(bool)

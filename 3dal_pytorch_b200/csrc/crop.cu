@@ -1,0 +1,375 @@
+// Points-in-rotated-box crop for batches of lidar frames: exact reference predicate, ascending index
+// lists per (frame, box), fused gather + float64 pose transform.  Integer / indexing work: bit-exact.
+//
+// Reference: box_np_ops.points_in_rbbox det3d/core/bbox/box_np_ops.py:641-647 ->
+// _points_in_convex_polygon_3d_jit det3d/core/bbox/geometry.py:241-276 (a point is inside iff for all six
+// planes ((px*nx + py*ny) + pz*nz) + d is NOT >= 0, evaluated in float32 without FMA), and the crop
+// materialisation det3d/datasets/waymo/waymo_common.py:168-171 (gather in ascending point order, then
+// pose(4x4 f64) @ [x y z 1]).  The plane equations come from the host (crop.py) so that sin/cos and the
+// corner arithmetic are the reference's own numpy float32 operations.
+//
+// The reference tests every point against every box (N*B*6 plane evaluations per frame).  Here a BEV grid
+// per frame maps a point to the few boxes whose (padded) bounding rectangle covers its cell, so each
+// point does O(1) exact tests and the kernels are bound by reading the points once from HBM.
+//
+// Pipeline (all launches cover the whole batch of frames):
+//   crop_grid_kernel   one CTA per frame: grid extent from the box AABBs, CSR cell -> box lists
+//   crop_hits_kernel   one CTA per chunk of 2048 points: exact tests, ordered (point, box, rank) hit list
+//                      per chunk and per-(chunk, box) counts
+//   crop_scan_kernel   per frame: exclusive scan over chunks for every box; crop_offsets_kernel: global offsets
+//   crop_fill_kernel   scatter indices / xyz / global xyz to their final, ascending positions
+#include "common.cuh"
+#include "../../include/al3d.h"
+
+namespace al3d {
+
+constexpr int kCropChunk = 2048;       // points per CTA of the hits kernel
+constexpr int kCropThreads = 256;
+constexpr int kMaxHitsPerPoint = 4;    // a point inside more boxes than this raises the overflow flag
+
+struct CropGridMeta { float x0, y0, inv_x, inv_y; };
+
+// cell index of a coordinate; the SAME expression is used for points and for box rectangles, and it is
+// monotone in v, so a point inside a rectangle always lands in a cell the rectangle was registered in.
+__device__ __forceinline__ int crop_cell(float v, float v0, float inv, int G)
+{
+    const float c = floorf((v - v0) * inv);
+    return c < 0.f ? -1 : (c >= (float)G ? G : (int)c);
+}
+
+__global__ void __launch_bounds__(kCropThreads)
+crop_grid_kernel(const float *__restrict__ aabb, const int64_t *__restrict__ box_off, int G, CropGridMeta *__restrict__ meta,
+                 int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_boxes, int cell_cap, int32_t *__restrict__ overflow)
+{
+    extern __shared__ int32_t s_cnt[];            // G*G counts, then a scan
+    __shared__ float red[4][kCropThreads / 32];
+    __shared__ int32_t s_total;
+    const int f = blockIdx.x;
+    const int64_t b0 = box_off[f];
+    const int B = (int)(box_off[f + 1] - b0);
+    // ---- extent of the boxes of this frame
+    float xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float *a = aabb + (b0 + b) * 6;
+        xmin = fminf(xmin, a[0]); ymin = fminf(ymin, a[1]);
+        xmax = fmaxf(xmax, a[3]); ymax = fmaxf(ymax, a[4]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { red[0][wid] = xmin; red[1][wid] = ymin; red[2][wid] = xmax; red[3][wid] = ymax; }
+    __syncthreads();
+    for (int w = 0; w < kCropThreads / 32; ++w) {
+        xmin = fminf(xmin, red[0][w]); ymin = fminf(ymin, red[1][w]);
+        xmax = fmaxf(xmax, red[2][w]); ymax = fmaxf(ymax, red[3][w]);
+    }
+    CropGridMeta m;
+    if (B == 0 || !(xmax >= xmin) || !(ymax >= ymin)) { m.x0 = 0.f; m.y0 = 0.f; m.inv_x = 0.f; m.inv_y = 0.f; }
+    else {
+        m.x0 = xmin; m.y0 = ymin;
+        m.inv_x = (float)G / fmaxf(xmax - xmin, 1e-3f) * 0.999f;     // keep xmax inside the last cell
+        m.inv_y = (float)G / fmaxf(ymax - ymin, 1e-3f) * 0.999f;
+    }
+    if (threadIdx.x == 0) meta[f] = m;
+    // ---- count, scan, fill: one thread per cell walks all boxes (ascending box order per cell)
+    const int cells = G * G;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+            const int cy = c / G, cx = c - cy * G;
+            int n = 0;
+            const int base = (pass == 1) ? s_cnt[c] : 0;
+            for (int b = 0; b < B; ++b) {
+                const float *a = aabb + (b0 + b) * 6;
+                int x0c = crop_cell(a[0], m.x0, m.inv_x, G), x1c = crop_cell(a[3], m.x0, m.inv_x, G);
+                int y0c = crop_cell(a[1], m.y0, m.inv_y, G), y1c = crop_cell(a[4], m.y0, m.inv_y, G);
+                x0c = max(x0c, 0); y0c = max(y0c, 0); x1c = min(x1c, G - 1); y1c = min(y1c, G - 1);
+                if (cx >= x0c && cx <= x1c && cy >= y0c && cy <= y1c) {
+                    if (pass == 1 && base + n < cell_cap) cell_boxes[(int64_t)f * cell_cap + base + n] = b;
+                    ++n;
+                }
+            }
+            if (pass == 0) s_cnt[c] = n;
+        }
+        __syncthreads();
+        if (pass == 0) {
+            // exclusive scan of s_cnt (cells <= 16384): serial per 256-cell strip, then strip offsets
+            if (threadIdx.x == 0) {
+                int run = 0;
+                for (int c = 0; c < cells; ++c) { const int v = s_cnt[c]; s_cnt[c] = run; run += v; }
+                s_total = run;
+                if (run > cell_cap) atomicExch(overflow, 1);
+            }
+            __syncthreads();
+            for (int c = threadIdx.x; c < cells; c += blockDim.x) cell_start[(int64_t)f * (cells + 1) + c] = s_cnt[c];
+            if (threadIdx.x == 0) cell_start[(int64_t)f * (cells + 1) + cells] = s_total;
+        }
+    }
+}
+
+// exact reference predicate
+__device__ __forceinline__ bool crop_inside(float px, float py, float pz, const float4 *__restrict__ pl)
+{
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float4 q = __ldg(pl + k);
+        const float sgn = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, q.x), __fmul_rn(py, q.y)), __fmul_rn(pz, q.z)), q.w);
+        if (sgn >= 0.f) return false;
+    }
+    return true;
+}
+
+struct CropChunk { int32_t frame; int32_t first_pt; int32_t n_pts; int32_t chunk_in_frame; };
+
+__global__ void __launch_bounds__(kCropThreads)
+crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
+                 const float *__restrict__ planes, const int64_t *__restrict__ box_off, int G,
+                 const CropGridMeta *__restrict__ meta, const int32_t *__restrict__ cell_start,
+                 const int32_t *__restrict__ cell_boxes, int cell_cap, const CropChunk *__restrict__ chunks,
+                 int2 *__restrict__ hits, int hit_cap, int32_t *__restrict__ n_hits, int32_t *__restrict__ chunk_box_count,
+                 int max_boxes, int32_t *__restrict__ overflow)
+{
+    extern __shared__ int32_t s_box_cnt[];             // per-box hit counters of this chunk (max_boxes)
+    __shared__ int warp_sum[kCropThreads / 32];
+    __shared__ int s_base;
+    const CropChunk ck = chunks[blockIdx.x];
+    const int f = ck.frame;
+    const int64_t b0 = box_off[f];
+    const int B = (int)(box_off[f + 1] - b0);
+    const CropGridMeta m = meta[f];
+    const int cells = G * G;
+    const int32_t *cs = cell_start + (int64_t)f * (cells + 1);
+    const int32_t *cb = cell_boxes + (int64_t)f * cell_cap;
+    const float *pts = points + (pt_off[f] + ck.first_pt) * pt_stride;
+    int2 *my_hits = hits + (int64_t)blockIdx.x * hit_cap;      // .x = point index in frame, .y = box | rank << 16
+    for (int b = threadIdx.x; b < B; b += blockDim.x) s_box_cnt[b] = 0;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+    for (int r0 = 0; r0 < ck.n_pts; r0 += kCropThreads) {
+        const int i = r0 + threadIdx.x;
+        int hb[kMaxHitsPerPoint];
+        int nh = 0;
+        if (i < ck.n_pts) {
+            const float px = __ldg(pts + i * pt_stride), py = __ldg(pts + i * pt_stride + 1), pz = __ldg(pts + i * pt_stride + 2);
+            if (px != px || py != py || pz != pz) {
+                // NaN never satisfies `sign >= 0`: the reference reports such a point inside every box
+                for (int b = 0; b < B; ++b) {
+                    if (crop_inside(px, py, pz, reinterpret_cast<const float4 *>(planes) + (b0 + b) * 6)) {
+                        if (nh < kMaxHitsPerPoint) hb[nh] = b; else atomicExch(overflow, 2);
+                        ++nh;
+                    }
+                }
+            } else {
+                const int cx = crop_cell(px, m.x0, m.inv_x, G), cy = crop_cell(py, m.y0, m.inv_y, G);
+                if (cx >= 0 && cx < G && cy >= 0 && cy < G && m.inv_x > 0.f) {
+                    const int c = cy * G + cx;
+                    const int e1 = min(cs[c + 1], cell_cap);
+                    for (int e = cs[c]; e < e1; ++e) {
+                        const int b = cb[e];
+                        if (crop_inside(px, py, pz, reinterpret_cast<const float4 *>(planes) + (b0 + b) * 6)) {
+                            if (nh < kMaxHitsPerPoint) hb[nh] = b; else atomicExch(overflow, 2);
+                            ++nh;
+                        }
+                    }
+                }
+            }
+            if (nh > kMaxHitsPerPoint) nh = kMaxHitsPerPoint;
+        }
+        // ordered append: exclusive prefix of nh over the block (point order)
+        int incl = nh;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < wid; ++w) before += warp_sum[w];
+        const int at = before + incl - nh;
+        for (int k = 0; k < nh; ++k) {
+            if (at + k < hit_cap) my_hits[at + k] = make_int2(ck.first_pt + i, hb[k]);
+            else atomicExch(overflow, 3);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < kCropThreads / 32; ++w) t += warp_sum[w]; s_base += t; }
+        __syncthreads();
+    }
+    const int total = min(s_base, hit_cap);
+    if (threadIdx.x == 0) n_hits[blockIdx.x] = total;
+    // ---- rank of every hit among the hits of the same box in this chunk (point order): one warp walks the
+    //      ordered list 32 at a time; equal boxes inside a group are ranked by lane.
+    if (wid == 0) {
+        for (int h0 = 0; h0 < total; h0 += 32) {
+            const int h = h0 + lane;
+            const bool act = h < total;
+            const int box = act ? my_hits[h].y : -1 - lane;
+            const unsigned same = __match_any_sync(0xffffffffu, box);
+            if (act) {
+                const int rank = s_box_cnt[box] + __popc(same & ((1u << lane) - 1u));
+                my_hits[h].y = box | (rank << 16);
+            }
+            __syncwarp();
+            if (act && (same >> lane) == 1u) s_box_cnt[box] += __popc(same);      // highest lane of each group updates
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) chunk_box_count[(int64_t)blockIdx.x * max_boxes + b] = s_box_cnt[b];
+}
+
+// per frame: for every box an exclusive scan over the frame's chunks; box totals
+__global__ void crop_scan_kernel(const int64_t *__restrict__ box_off, const int64_t *__restrict__ frame_chunk_off,
+                                 int32_t *__restrict__ chunk_box_count, int max_boxes, int32_t *__restrict__ box_total)
+{
+    const int f = blockIdx.x;
+    const int64_t b0 = box_off[f];
+    const int B = (int)(box_off[f + 1] - b0);
+    const int64_t c0 = frame_chunk_off[f], c1 = frame_chunk_off[f + 1];
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int run = 0;
+        for (int64_t c = c0; c < c1; ++c) {
+            const int v = chunk_box_count[c * max_boxes + b];
+            chunk_box_count[c * max_boxes + b] = run;
+            run += v;
+        }
+        box_total[b0 + b] = run;
+    }
+}
+
+// global exclusive offsets over all boxes of all frames (single CTA)
+__global__ void __launch_bounds__(1024)
+crop_offsets_kernel(const int32_t *__restrict__ box_total, int64_t n_boxes, int64_t *__restrict__ offsets)
+{
+    __shared__ long long part[1024];
+    const int64_t per = (n_boxes + blockDim.x - 1) / blockDim.x;
+    const int64_t lo = (int64_t)threadIdx.x * per, hi = min(lo + per, n_boxes);
+    long long sum = 0;
+    for (int64_t i = lo; i < hi; ++i) sum += box_total[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int t = 0; t < (int)blockDim.x; ++t) { const long long v = part[t]; part[t] = run; run += v; }
+        offsets[n_boxes] = run;
+    }
+    __syncthreads();
+    long long run = part[threadIdx.x];
+    for (int64_t i = lo; i < hi; ++i) { offsets[i] = run; run += box_total[i]; }
+}
+
+__global__ void __launch_bounds__(kCropThreads)
+crop_fill_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
+                 const int64_t *__restrict__ box_off, const CropChunk *__restrict__ chunks, const int2 *__restrict__ hits,
+                 int hit_cap, const int32_t *__restrict__ n_hits, const int32_t *__restrict__ chunk_box_count, int max_boxes,
+                 const int64_t *__restrict__ offsets, const double *__restrict__ poses, int64_t capacity,
+                 int32_t *__restrict__ out_idx, float *__restrict__ out_xyz, double *__restrict__ out_xyz_global,
+                 int32_t *__restrict__ overflow)
+{
+    const CropChunk ck = chunks[blockIdx.x];
+    const int f = ck.frame;
+    const int64_t b0 = box_off[f];
+    const int total = n_hits[blockIdx.x];
+    const int2 *my_hits = hits + (int64_t)blockIdx.x * hit_cap;
+    const double *P = poses ? poses + (int64_t)f * 16 : nullptr;
+    for (int h = threadIdx.x; h < total; h += blockDim.x) {
+        const int2 hr = my_hits[h];
+        const int3 hv = make_int3(hr.x, hr.y & 0xFFFF, hr.y >> 16);
+        const int64_t dst = offsets[b0 + hv.y] + chunk_box_count[(int64_t)blockIdx.x * max_boxes + hv.y] + hv.z;
+        if (dst >= capacity) { atomicExch(overflow, 4); continue; }
+        const float *p = points + (pt_off[f] + hv.x) * pt_stride;
+        const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+        out_idx[dst] = hv.x;
+        if (out_xyz) { out_xyz[dst * 3] = x; out_xyz[dst * 3 + 1] = y; out_xyz[dst * 3 + 2] = z; }
+        if (out_xyz_global && P) {
+            const double dx = x, dy = y, dz = z;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                out_xyz_global[dst * 3 + r] = ((P[r * 4] * dx + P[r * 4 + 1] * dy) + P[r * 4 + 2] * dz) + P[r * 4 + 3];
+        }
+    }
+}
+
+// dense (N, B) uint8 mask from the index lists of ONE frame (drop-in for box_np_ops.points_in_rbbox)
+__global__ void crop_dense_mask_kernel(const int32_t *__restrict__ idx, const int64_t *__restrict__ offsets, int n_boxes,
+                                       uint8_t *__restrict__ mask)
+{
+    const int b = blockIdx.y;
+    const int64_t lo = offsets[b], hi = offsets[b + 1];
+    for (int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x)
+        mask[(int64_t)idx[i] * n_boxes + b] = 1;
+}
+
+}  // namespace al3d
+
+using namespace al3d;
+
+extern "C" int al3d_crop_chunk_points(void) { return kCropChunk; }
+
+extern "C" int al3d_crop_build_grid(const float *aabb, const int64_t *box_off, int n_frames, int G, float *grid_meta,
+                                    int32_t *cell_start, int32_t *cell_boxes, int cell_cap, int32_t *overflow, void *stream)
+{
+    AL3D_CHECK_ARG(aabb && box_off && grid_meta && cell_start && cell_boxes && overflow, "al3d_crop_build_grid: null pointer");
+    AL3D_CHECK_ARG(G >= 1 && G <= 96, "al3d_crop_build_grid: G=%d not in [1,96]", G);
+    if (n_frames <= 0) return 0;
+    crop_grid_kernel<<<n_frames, kCropThreads, (size_t)G * G * sizeof(int32_t), (cudaStream_t)stream>>>(
+        aabb, box_off, G, reinterpret_cast<CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap, overflow);
+    AL3D_CHECK_LAUNCH("crop_grid_kernel");
+    return 0;
+}
+
+extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
+                              const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
+                              const int32_t *cell_boxes, int cell_cap, const int32_t *chunks, int n_chunks, void *hits,
+                              int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes, int32_t *overflow, void *stream)
+{
+    AL3D_CHECK_ARG(points && pt_off && planes && box_off && grid_meta && cell_start && cell_boxes && chunks && hits && n_hits &&
+                   chunk_box_count && overflow, "al3d_crop_hits: null pointer");
+    AL3D_CHECK_ARG(pt_stride >= 3, "al3d_crop_hits: pt_stride=%lld", (long long)pt_stride);
+    AL3D_CHECK_ARG(max_boxes >= 1 && max_boxes <= 12288, "al3d_crop_hits: max_boxes=%d not in [1,12288]", max_boxes);
+    AL3D_CHECK_ARG(hit_cap >= 1 && hit_cap <= 32767, "al3d_crop_hits: hit_cap=%d not in [1,32767]", hit_cap);
+    if (n_chunks <= 0) return 0;
+    crop_hits_kernel<<<n_chunks, kCropThreads, (size_t)max_boxes * sizeof(int32_t), (cudaStream_t)stream>>>(
+        points, pt_stride, pt_off, planes, box_off, G, reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes,
+        cell_cap, reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<int2 *>(hits), hit_cap, n_hits, chunk_box_count,
+        max_boxes, overflow);
+    AL3D_CHECK_LAUNCH("crop_hits_kernel");
+    return 0;
+}
+
+extern "C" int al3d_crop_scan(const int64_t *box_off, const int64_t *frame_chunk_off, int n_frames, int64_t n_boxes,
+                              int32_t *chunk_box_count, int max_boxes, int32_t *box_total, int64_t *offsets, void *stream)
+{
+    AL3D_CHECK_ARG(box_off && frame_chunk_off && chunk_box_count && box_total && offsets, "al3d_crop_scan: null pointer");
+    if (n_frames > 0) {
+        crop_scan_kernel<<<n_frames, 256, 0, (cudaStream_t)stream>>>(box_off, frame_chunk_off, chunk_box_count, max_boxes, box_total);
+        AL3D_CHECK_LAUNCH("crop_scan_kernel");
+    }
+    crop_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(box_total, n_boxes, offsets);
+    AL3D_CHECK_LAUNCH("crop_offsets_kernel");
+    return 0;
+}
+
+extern "C" int al3d_crop_fill(const float *points, int64_t pt_stride, const int64_t *pt_off, const int64_t *box_off,
+                              const int32_t *chunks, int n_chunks, const void *hits, int hit_cap, const int32_t *n_hits,
+                              const int32_t *chunk_box_count, int max_boxes, const int64_t *offsets, const double *poses,
+                              int64_t capacity, int32_t *out_idx, float *out_xyz, double *out_xyz_global, int32_t *overflow,
+                              void *stream)
+{
+    AL3D_CHECK_ARG(points && pt_off && box_off && chunks && hits && n_hits && chunk_box_count && offsets && out_idx && overflow,
+                   "al3d_crop_fill: null pointer");
+    if (n_chunks <= 0) return 0;
+    crop_fill_kernel<<<n_chunks, kCropThreads, 0, (cudaStream_t)stream>>>(
+        points, pt_stride, pt_off, box_off, reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<const int2 *>(hits), hit_cap,
+        n_hits, chunk_box_count, max_boxes, offsets, poses, capacity, out_idx, out_xyz, out_xyz_global, overflow);
+    AL3D_CHECK_LAUNCH("crop_fill_kernel");
+    return 0;
+}
+
+extern "C" int al3d_crop_dense_mask(const int32_t *idx, const int64_t *offsets, int n_boxes, uint8_t *mask, void *stream)
+{
+    AL3D_CHECK_ARG(idx && offsets && mask, "al3d_crop_dense_mask: null pointer");
+    if (n_boxes <= 0) return 0;
+    crop_dense_mask_kernel<<<dim3(8, n_boxes), 256, 0, (cudaStream_t)stream>>>(idx, offsets, n_boxes, mask);
+    AL3D_CHECK_LAUNCH("crop_dense_mask_kernel");
+    return 0;
+}

@@ -106,6 +106,40 @@ int al3d_twostage_retransform(const float *obj_pts, int bs, int m, const float *
 
 
 /* ------------------------------------------------------------------------------------------------
+ * Points-in-rotated-box crop over a batch of lidar frames (integer / indexing work, bit-exact).
+ * Replaces box_np_ops.points_in_rbbox (det3d/core/bbox/box_np_ops.py:641-647 ->
+ * det3d/core/bbox/geometry.py:241-276) and the per-box crop loop of _create_pd_detection
+ * (det3d/datasets/waymo/waymo_common.py:167-171).  Frames are concatenated: points (sum N_f, stride)
+ * f32 with pt_off (F+1) i64; boxes as inward plane equations planes (sum B_f, 6, 4) f32 and padded
+ * axis-aligned rectangles aabb (sum B_f, 6) f32 [xmin ymin zmin xmax ymax zmax] with box_off (F+1) i64
+ * (both computed by the caller with the reference's own float32 numpy arithmetic, crop.py).
+ * `overflow` is a device int32 the kernels set non-zero when a caller-provided capacity is too small.
+ * Order of calls: build_grid -> hits -> scan -> (read offsets[n_boxes] = total, allocate) -> fill.
+ * ---------------------------------------------------------------------------------------------- */
+int al3d_crop_chunk_points(void);      /* points per work chunk (the caller builds the chunk table) */
+int al3d_crop_build_grid(const float *aabb, const int64_t *box_off, int n_frames, int G, float *grid_meta,
+                         int32_t *cell_start, int32_t *cell_boxes, int cell_cap, int32_t *overflow, void *stream);
+/* chunks: (n_chunks, 4) i32 rows [frame, first point in frame, n points, chunk index in frame];
+ * hits: (n_chunks, hit_cap) int2 scratch; chunk_box_count: (n_chunks, max_boxes) i32 scratch. */
+int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
+                   const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
+                   const int32_t *cell_boxes, int cell_cap, const int32_t *chunks, int n_chunks, void *hits,
+                   int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes, int32_t *overflow, void *stream);
+/* frame_chunk_off (F+1) i64; writes box_total (n_boxes) i32 and offsets (n_boxes+1) i64 (exclusive). */
+int al3d_crop_scan(const int64_t *box_off, const int64_t *frame_chunk_off, int n_frames, int64_t n_boxes,
+                   int32_t *chunk_box_count, int max_boxes, int32_t *box_total, int64_t *offsets, void *stream);
+/* out_idx (capacity) i32 point index within its frame, ascending per box; out_xyz (capacity,3) f32 copy
+ * (may be NULL); out_xyz_global (capacity,3) f64 = poses[f] (4x4 row-major f64) applied to [x y z 1]
+ * (may be NULL, needs poses). */
+int al3d_crop_fill(const float *points, int64_t pt_stride, const int64_t *pt_off, const int64_t *box_off,
+                   const int32_t *chunks, int n_chunks, const void *hits, int hit_cap, const int32_t *n_hits,
+                   const int32_t *chunk_box_count, int max_boxes, const int64_t *offsets, const double *poses,
+                   int64_t capacity, int32_t *out_idx, float *out_xyz, double *out_xyz_global, int32_t *overflow,
+                   void *stream);
+/* dense (N, n_boxes) u8 mask (pre-zeroed) of one frame from its index lists. */
+int al3d_crop_dense_mask(const int32_t *idx, const int64_t *offsets, int n_boxes, uint8_t *mask, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 / TMEM, bf16 operands, fp32 accumulate) shared-MLP kernels.
  * Weights are BatchNorm-folded and packed by the caller (3dal_pytorch_b200/engine_bf16.py) into
  * 16 KB blocks of 128 rows x 64 K in the "KP" layout (K/8 planes of rows x 16 bytes), stored in the

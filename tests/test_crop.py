@@ -1,0 +1,110 @@
+"""Crop: host plane setup (CPU) and the CUDA crop against the oracle / golden frame (GPU)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, synth
+from oracle import crop as ocrop
+
+crop = importlib.import_module("3dal_pytorch_b200.crop")
+
+
+def _random_boxes(rng, nb, spread=20.0):
+    return np.concatenate([rng.normal(0, spread, (nb, 2)), rng.normal(0.5, 0.5, (nb, 1)), rng.uniform(0.4, 11, (nb, 3)),
+                           rng.uniform(-7, 7, (nb, 1))], 1).astype(np.float32)
+
+
+def test_host_planes_bitwise_equal_to_oracle():
+    rng = np.random.default_rng(0)
+    boxes = _random_boxes(rng, 2000)
+    planes, aabb = crop.box_planes_host(boxes)
+    assert np.array_equal(planes, ocrop.box_planes(boxes))
+    corners = ocrop.box_corners(boxes)
+    assert np.all(aabb[:, :3] < corners.min(1)) and np.all(aabb[:, 3:] > corners.max(1))
+    assert np.array_equal(crop.detector_to_waymo(boxes), ocrop.detector_to_waymo(boxes))
+
+
+def _check_against_oracle(points, boxes, poses, res):
+    off = res["offsets"].cpu().numpy()
+    idx = res["indices"].cpu().numpy()
+    xyz = res["xyz"].cpu().numpy()
+    glob = res["xyz_global"].cpu().numpy() if res["xyz_global"] is not None else None
+    box_off = res["box_off"]
+    for f in range(len(points)):
+        ridx, rxyz = ocrop.crop_frame(np.asarray(points[f], dtype=np.float32), np.asarray(boxes[f], np.float32).reshape(-1, 7),
+                                      poses[f] if poses is not None else np.eye(4))
+        for b in range(len(ridx)):
+            k = box_off[f] + b
+            got = idx[off[k]:off[k + 1]]
+            assert np.array_equal(got, ridx[b]), (f, b, len(got), len(ridx[b]))           # bit-exact, ascending
+            assert np.array_equal(xyz[off[k]:off[k + 1]], np.asarray(points[f])[ridx[b], :3])
+            if glob is not None and len(got):
+                ref = rxyz[b]
+                assert np.allclose(glob[off[k]:off[k + 1]], ref, rtol=1e-12, atol=1e-9)   # f64 transform: FP, not bitwise
+    assert off[-1] == len(idx)
+
+
+@pytest.mark.gpu
+def test_crop_golden_frame():
+    z = np.load(os.path.join(GOLDEN, "crop_frame.npz"))
+    box = crop.detector_to_waymo(z["det_boxes"])
+    assert np.array_equal(box, z["waymo_boxes"])
+    res = crop.crop_frames([z["points"]], [box], [z["pose"]])
+    off = res["offsets"].cpu().numpy()
+    assert np.array_equal(off, z["offsets"])
+    assert np.array_equal(res["indices"].cpu().numpy(), z["indices"])
+    assert np.allclose(res["xyz_global"].cpu().numpy(), z["xyz_global"], rtol=1e-12, atol=1e-9)
+    m = crop.points_in_rbbox(z["points"], box)
+    ref = ocrop.points_in_boxes(z["points"], box)
+    assert m.dtype == np.bool_ and np.array_equal(m, ref)
+
+
+@pytest.mark.gpu
+def test_crop_ragged_batch_and_edge_cases():
+    rng = np.random.default_rng(3)
+    frames = synth.lidar_frames(3, n_points=30000, n_boxes=60, seed=5)
+    points = [f["points"] for f in frames] + [np.zeros((0, 3), np.float32), rng.normal(0, 5, (777, 3)).astype(np.float32)]
+    boxes = [crop.detector_to_waymo(f["det_boxes"]) for f in frames] + [_random_boxes(rng, 5), np.zeros((0, 7), np.float32)]
+    poses = [f["pose"] for f in frames] + [np.eye(4), np.eye(4)]
+    # heavy overlap (up to 4 boxes over the same points), a NaN point and a point exactly on a face
+    dense = rng.uniform(-1, 1, (5000, 3)).astype(np.float32)
+    dense[17] = np.nan
+    dense[18] = [1.0, 0.0, 0.0]
+    ob = np.array([[0, 0, 0, 2, 2, 2, 0.0], [0.1, 0, 0, 2, 2, 2, 0.3], [0, 0.1, 0, 3, 1, 2, -0.4], [5, 5, 0, 1, 1, 1, 0.0]], np.float32)
+    points.append(dense); boxes.append(ob); poses.append(frames[0]["pose"])
+    res = crop.crop_frames(points, boxes, poses, hit_cap=8192)
+    assert int(res["overflow"].item()) == 0
+    _check_against_oracle(points, boxes, poses, res)
+    # NaN point is "inside" every box, exactly like the reference predicate
+    off = res["offsets"].cpu().numpy(); idx = res["indices"].cpu().numpy()
+    k = res["box_off"][5] + 3
+    assert 17 in idx[off[k]:off[k + 1]]
+
+
+@pytest.mark.gpu
+def test_crop_overflow_is_reported():
+    rng = np.random.default_rng(1)
+    pts = rng.uniform(-0.5, 0.5, (4096, 3)).astype(np.float32)
+    boxes = np.tile(np.array([[0, 0, 0, 4, 4, 4, 0.0]], np.float32), (6, 1))      # every point inside 6 boxes
+    with pytest.raises(OverflowError):
+        crop.crop_frames([pts], [boxes], hit_cap=8192)
+
+
+@pytest.mark.gpu
+def test_crop_waymo_sized_frame_property():
+    """Full-size frame (180k points, 200 boxes): index lists are ascending, disjoint from outside points and
+    consistent with a dense recomputation on a random subset of boxes."""
+    fr = synth.lidar_frames(1, seed=9)[0]
+    box = crop.detector_to_waymo(fr["det_boxes"])
+    res = crop.crop_frames([fr["points"]], [box], [fr["pose"]])
+    off = res["offsets"].cpu().numpy(); idx = res["indices"].cpu().numpy()
+    for b in range(box.shape[0]):
+        seg = idx[off[b]:off[b + 1]]
+        assert np.all(np.diff(seg) > 0)
+    sel = np.random.default_rng(0).choice(box.shape[0], 12, replace=False)
+    ref = ocrop.points_in_boxes(fr["points"], box[sel])
+    for j, b in enumerate(sel):
+        assert np.array_equal(idx[off[b]:off[b + 1]], np.nonzero(ref[:, j])[0])
