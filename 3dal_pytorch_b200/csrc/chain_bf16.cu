@@ -158,6 +158,58 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_kp, const uint8_t *__restrict
     if (threadIdx.x < 32) tmem_dealloc<256>(tmem);
 }
 
+// Same product with the A operand staged in TMEM: every thread packs its row of A (fp32 in global memory)
+// to bf16 pairs and tcgen05.st's them to columns [256, 256 + K/2); checks the A-from-TMEM conventions.
+__global__ void __launch_bounds__(128)
+umma_selftest_ts_kernel(const float *__restrict__ a, const uint8_t *__restrict__ b_kp, int N, int K, float *__restrict__ d)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *sb = smem;
+    const int b_bytes = N * K * 2;
+    for (int i = threadIdx.x * 16; i < b_bytes; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(sb + i) = *reinterpret_cast<const uint4 *>(b_kp + i);
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int row = threadIdx.x;
+    const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = pack_bf16x2(a[row * K + k0 + 2 * i], a[row * K + k0 + 2 * i + 1]);
+        tmem_st16(tmem + lane_addr + 256 + k0 / 2, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            const uint64_t db = make_desc(smem_u32(sb) + (k0 / 8) * N * 16, N);
+            mma_bf16_ts(tmem, tmem + 256 + k0 / 2, db, idesc, k0 > 0 ? 1u : 0u);
+        }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0, 0xE002);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (c0 + i < N) d[row * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
+}
+
 // ================================================================================================
 // chain_max_kernel
 // ================================================================================================
@@ -726,6 +778,18 @@ extern "C" int al3d_umma_selftest(const void *a_kp, const void *b_kp, int N, int
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const uint8_t *)a_kp, (const uint8_t *)b_kp, N, K, d_out, swap_lbo_sbo);
     AL3D_CHECK_LAUNCH("umma_selftest_kernel");
+    return 0;
+}
+
+extern "C" int al3d_umma_selftest_ts(const float *a, const void *b_kp, int N, int K, float *d_out, void *stream)
+{
+    AL3D_CHECK_ARG(a && b_kp && d_out, "al3d_umma_selftest_ts: null pointer");
+    AL3D_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && K >= 32 && K % 32 == 0 && K <= 512, "al3d_umma_selftest_ts: bad N=%d K=%d", N, K);
+    const size_t smem = (size_t)N * K * 2;
+    AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_umma_selftest_ts: tile too large");
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_ts_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, (const uint8_t *)b_kp, N, K, d_out);
+    AL3D_CHECK_LAUNCH("umma_selftest_ts_kernel");
     return 0;
 }
 

@@ -194,3 +194,15 @@ def umma_selftest(a, b, swap=False):
                "umma_selftest")
     check_abort("umma_selftest_kernel")
     return d
+
+
+def umma_selftest_ts(a, b):
+    """Like umma_selftest but the kernel stages A in TMEM (A-from-TMEM MMA)."""
+    N, K = b.shape
+    d = torch.empty((128, N), device=a.device, dtype=torch.float32)
+    bk = kp_pack(b)
+    a = a.contiguous().float()
+    _lib.check(_lib.lib().al3d_umma_selftest_ts(a.data_ptr(), bk.data_ptr(), N, K, d.data_ptr(), ops._stream()),
+               "umma_selftest_ts")
+    check_abort("umma_selftest_ts_kernel")
+    return d

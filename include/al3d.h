@@ -187,6 +187,8 @@ int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, int64_t sb,
 /* D(128,N) fp32 = A(128,K) . B(N,K)^T from KP-packed bf16 operands with one tcgen05.mma chain:
  * unit test of the descriptor / layout conventions. */
 int al3d_umma_selftest(const void *a_kp, const void *b_kp, int N, int K, float *d_out, int swap_lbo_sbo, void *stream);
+/* Same product with A (128,K) fp32 row-major packed to bf16 and staged in TMEM by the kernel (A-from-TMEM MMA). */
+int al3d_umma_selftest_ts(const float *a, const void *b_kp, int N, int K, float *d_out, void *stream);
 
 /* Reads (and clears) the device-side watchdog code: non-zero means a tensor-core kernel gave up on
  * an mbarrier wait (protocol bug) and its outputs are invalid.  Synchronises the device. */

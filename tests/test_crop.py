@@ -40,10 +40,10 @@ def _check_against_oracle(points, boxes, poses, res):
             k = box_off[f] + b
             got = idx[off[k]:off[k + 1]]
             assert np.array_equal(got, ridx[b]), (f, b, len(got), len(ridx[b]))           # bit-exact, ascending
-            assert np.array_equal(xyz[off[k]:off[k + 1]], np.asarray(points[f])[ridx[b], :3])
+            assert np.array_equal(xyz[off[k]:off[k + 1]], np.asarray(points[f])[ridx[b], :3], equal_nan=True)
             if glob is not None and len(got):
                 ref = rxyz[b]
-                assert np.allclose(glob[off[k]:off[k + 1]], ref, rtol=1e-12, atol=1e-9)   # f64 transform: FP, not bitwise
+                assert np.allclose(glob[off[k]:off[k + 1]], ref, rtol=1e-12, atol=1e-9, equal_nan=True)   # f64 transform: FP, not bitwise
     assert off[-1] == len(idx)
 
 

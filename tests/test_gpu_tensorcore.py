@@ -28,6 +28,16 @@ def test_umma_selftest(N, K):
         pytest.fail("descriptor convention wrong: err(lbo=R*16,sbo=128)=%g err(swapped)=%g" % (err, rel_err(d2.cpu(), ref.cpu())))
 
 
+@pytest.mark.parametrize("N,K", [(64, 64), (128, 64), (128, 128), (256, 256), (64, 512)])
+def test_umma_selftest_a_from_tmem(N, K):
+    torch.manual_seed(N * 1000 + K + 1)
+    a = torch.randn(128, K, device=DEV)
+    b = torch.randn(N, K, device=DEV)
+    ref = a.to(torch.bfloat16).float() @ b.to(torch.bfloat16).float().t()
+    d = eb.umma_selftest_ts(a, b)
+    assert rel_err(d.cpu(), ref.cpu()) < 1e-5, rel_err(d.cpu(), ref.cpu())
+
+
 def _dev(fw):
     return {k: (w.to(DEV), b.to(DEV)) for k, (w, b) in fw.items()}
 
