@@ -442,16 +442,29 @@ done:
 }
 
 // ================================================================================================
-// seg_pass2_kernel
+// seg_pass2_kernel -- activations stay in TMEM
+//
+// Per 128-point tile every layer is D[points x channels] = A[points x K] * W^T with the A operand read from
+// TENSOR MEMORY (tcgen05.mma, A-from-TMEM): the epilogue warps turn an fp32 accumulator into the next layer's
+// bf16 operand in place (tcgen05.ld -> bias + ReLU -> cvt.bf16x2 -> tcgen05.st), so shared memory carries
+// nothing but the streamed weight blocks (13-stage ring) and the MMA only fetches B from it.
+//
+// TMEM columns (fp32 accumulators / packed bf16 operands, 2 channels per column):
+//   [0,256)    D2 = dconv2 accumulator; later A3 (its bf16 image): channels 0..127 at [0,64), 128..255 at [128,192)
+//   [256,448)  three 64-column dconv1 chunk buffers D1b[0..2]; each is rewritten in place as the bf16 operand of
+//              dconv2's partial sum (channels 0..31 at +0, 32..63 at +32).  D1b[2] first holds conv2's accumulator.
+//              Later D3 = dconv3 accumulator at [256,384) and A4 (its bf16 image) at [256,288) + [320,352)
+//   [448,480)  A2 = conv2 output (64 ch);  [480,512)  A1 = conv1 output (64 ch)
+//   [384,512)  finally D4 = dconv4 accumulator
 // ================================================================================================
 struct Pass2Params {
     const float *x; int64_t sb, sc, sp; int bs, n; int c_in;
-    const float *w1_w, *w1_b;          // conv1 fp32 (64, 8) padded, (64)
+    const float *w1_w, *w1_b;          // conv1 fp32 (8, 64) transposed + padded, (64)
     const float *b2;                   // conv2 bias (64)
     const float *gbias;                // (bs, 512) per-object dconv1 bias (global-feature half + folded BN bias)
     const float *bd2, *bd3, *bd4;      // dconv2-4 biases (256),(128),(128)
     const float *w5, *b5;              // dconv5 fp32 (2,128), (2)
-    const uint8_t *wstream;            // 27 packed blocks
+    const uint8_t *wstream;            // 31 packed blocks (16 KB slots), consumption order
     float *logits;                     // (bs, n, 2)
     uint8_t *mask;                     // (bs, n)
     int tiles_per_obj; int n_items;    // items = bs * tiles_per_obj
@@ -463,19 +476,48 @@ struct Pass2Params {
     do { if (p.dbg && blockIdx.x == 0 && it_local < 4 && ts_i < 64)                            \
              p.dbg[((role) * 4 + it_local) * 64 + ts_i++] = clock64(); } while (0)
 
-constexpr int kP2Stages = 4;
+constexpr int kP2Stages = 13;
+constexpr int kP2Blocks = 31;
+constexpr uint32_t kColD2 = 0, kColD1 = 256, kColA2 = 448, kColA1 = 480, kColD3 = 256, kColD4 = 384;
 struct Pass2Smem {
-    uint8_t bufD2[65536];              // dconv2 output (256 ch); first 16 KB doubles as the conv1 output
-    uint8_t ring[2][32768];            // dconv1 128-channel chunks; ring[0] doubles as the dconv3 output
-    uint8_t bufA2[16384];              // conv2 output (64 ch), lives until the last dconv1 chunk
     uint8_t wring[kP2Stages][kStageBytes];
     float w1_w[64 * 8], w1_b[64], b2[64], gb[512], bd2[256], bd3[128], bd4[128], w5[256], b5[2];
     float lpart[2 * kTile];            // logits partial sums of the upper column half
     uint64_t w_full[kP2Stages], w_empty[kP2Stages];
     uint64_t act_ready, acc_ready;
-    uint64_t d1_full[2], d1_act[2], ring_free[2];
+    uint64_t d1_full[3], d1_act[3];
     uint32_t tmem_base;
 };
+
+// bytes of weight block `blk` of the per-tile stream (64-row blocks are 8 KB, 128-row blocks 16 KB)
+__device__ __forceinline__ uint32_t p2_block_bytes(int blk)
+{
+    // 0: conv2; 1-3: d1 chunks 0-2; then 5 groups {P, P, d1}; then 3 groups {P, P}; then dconv3 x4, dconv4 x2
+    if (blk <= 3) return 8192;
+    if (blk < 19) return ((blk - 4) % 3 == 2) ? 8192 : 16384;
+    return 16384;
+}
+
+// 32 fp32 accumulator columns -> bias + ReLU -> 16 packed bf16x2 words
+__device__ __forceinline__ void pack_act32(const uint32_t (&v)[32], const float *bias, uint32_t (&o)[16])
+{
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 b = *reinterpret_cast<const float4 *>(bias + j * 4);
+        o[2 * j] = relu_pack_bf16x2(__uint_as_float(v[4 * j]) + b.x, __uint_as_float(v[4 * j + 1]) + b.y);
+        o[2 * j + 1] = relu_pack_bf16x2(__uint_as_float(v[4 * j + 2]) + b.z, __uint_as_float(v[4 * j + 3]) + b.w);
+    }
+}
+
+// 4 MMAs (K = 64) with A in TMEM: a_col[s] is the TMEM column of K-slice s (8 columns each)
+__device__ __forceinline__ void mma_ts_k64(uint32_t tmem_d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                           uint32_t b_addr, uint32_t rows_b, uint32_t idesc, bool accumulate_first)
+{
+    const uint32_t a[4] = {a0, a1, a2, a3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        mma_bf16_ts(tmem_d, a[k], make_desc(b_addr + k * 2 * rows_b * 16, rows_b), idesc, (accumulate_first || k > 0) ? 1u : 0u);
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 seg_pass2_kernel(const Pass2Params p)
@@ -493,7 +535,7 @@ seg_pass2_kernel(const Pass2Params p)
         for (int i = 0; i < kP2Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
         mbar_init(&s.act_ready, kEpiThreads);
         mbar_init(&s.acc_ready, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kEpiThreads); mbar_init(&s.ring_free[i], 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kEpiThreads); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<512>(&s.tmem_base);
@@ -501,19 +543,18 @@ seg_pass2_kernel(const Pass2Params p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
-    // TMEM columns: [0,256) dconv2 accumulator (conv2 uses [0,64) first); [256,384) / [384,512) dconv1
-    // chunk buffers, reused by dconv3 / dconv4.
 
     if (warp == 0) {
+        // ------------------------------------------------------------ weight producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int it_local = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
                 int ts_i = 0;
-                for (int blk = 0; blk < 27; ++blk) {
+                for (int blk = 0; blk < kP2Blocks; ++blk) {
                     if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0xA100 + stage)) goto done;
                     AL3D_TS(2);
-                    const uint32_t bytes = (blk == 0) ? 64 * 64 * 2 : kStageBytes;
+                    const uint32_t bytes = p2_block_bytes(blk);
                     mbar_arrive_expect_tx(&s.w_full[stage], bytes);
                     bulk_g2s(s.wring[stage], p.wstream + (size_t)blk * kStageBytes, bytes, &s.w_full[stage]);
                     if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
@@ -521,10 +562,9 @@ seg_pass2_kernel(const Pass2Params p)
             }
         }
     } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            int stage = 0; uint32_t wphase = 0, act_phase = 0, d1a_phase[2] = {0, 0};
-            const uint32_t aX = smem_u32(s.bufD2), aA2 = smem_u32(s.bufA2), aD2 = smem_u32(s.bufD2);
-            const uint32_t aRing[2] = {smem_u32(s.ring[0]), smem_u32(s.ring[1])};
+            int stage = 0; uint32_t wphase = 0, act_phase = 0, d1a_phase[3] = {0, 0, 0};
             const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128);
 #define P2_NEXT_W(code)                                                          \
             if (!mbar_wait(&s.w_full[stage], wphase, code + stage)) goto done;   \
@@ -533,90 +573,105 @@ seg_pass2_kernel(const Pass2Params p)
 #define P2_REL_W()                                                               \
             mma_commit(&s.w_empty[stage]);                                       \
             if (++stage == kP2Stages) { stage = 0; wphase ^= 1; }
+#define P2_WAIT_ACT(code)                                                        \
+            if (!mbar_wait(&s.act_ready, act_phase, code)) goto done;            \
+            AL3D_TS(0);                                                          \
+            act_phase ^= 1; tc_fence_after();
             int it_local = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
                 int ts_i = 0;
                 AL3D_TS(0);
-                // conv2 : A = conv1 output (64 ch) in bufD2[0:16K]
-                if (!mbar_wait(&s.act_ready, act_phase, 0xA200)) goto done;
-                AL3D_TS(0);
-                act_phase ^= 1; tc_fence_after();
+                // conv2: A1 (TMEM) x W2 -> D1b[2]
+                P2_WAIT_ACT(0xA200)
                 P2_NEXT_W(0xA300)
-                mma_block_k64(tmem, aX, 128, smem_u32(s.wring[stage]), 64, id64, false);
+                mma_ts_k64(tmem + kColD1 + 128, tmem + kColA1, tmem + kColA1 + 8, tmem + kColA1 + 16, tmem + kColA1 + 24,
+                           smem_u32(s.wring[stage]), 64, id64, false);
                 P2_REL_W()
                 mma_commit(&s.acc_ready);
-                // dconv1 chunks interleaved with dconv2 partial sums
-                if (!mbar_wait(&s.act_ready, act_phase, 0xA201)) goto done;    // conv2 output in bufA2
-                AL3D_TS(0);
-                act_phase ^= 1; tc_fence_after();
-                for (int kc = 0; kc < 4; ++kc) {
-                    // dconv1 chunk kc -> TMEM 256 + (kc&1)*128.  The buffer was drained by the epilogue of
-                    // chunk kc-2, which the d1_act wait of partial kc-2 (below) already observed.
+                // dconv1 chunks 0..2: A2 x Wd1[chunk] -> D1b[j]
+                P2_WAIT_ACT(0xA201)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
                     P2_NEXT_W(0xA310)
-                    mma_block_k64(tmem + 256 + (kc & 1) * 128, aA2, 128, smem_u32(s.wring[stage]), 128, id128, false);
+                    mma_ts_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24,
+                               smem_u32(s.wring[stage]), 64, id64, false);
                     P2_REL_W()
-                    mma_commit(&s.d1_full[kc & 1]);
-                    if (kc >= 1) {
-                        const int pc = kc - 1, sl = pc & 1;                   // dconv2 partial for chunk kc-1
-                        if (!mbar_wait(&s.d1_act[sl], d1a_phase[sl], 0xA400 + pc)) goto done;
-                        AL3D_TS(0);
-                        d1a_phase[sl] ^= 1; tc_fence_after();
-                        for (int nc = 0; nc < 2; ++nc)
-                            for (int kb = 0; kb < 2; ++kb) {
-                                P2_NEXT_W(0xA320)
-                                mma_block_k64(tmem + nc * 128, aRing[sl] + kb * 8 * kPlane, 128, smem_u32(s.wring[stage]), 128, id128, pc > 0 || kb > 0);
-                                P2_REL_W()
-                            }
-                        mma_commit(&s.ring_free[sl]);
+                    mma_commit(&s.d1_full[j]);
+                }
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) {
+                    const int j = kc % 3;
+                    if (!mbar_wait(&s.d1_act[j], d1a_phase[j], 0xA400 + kc)) goto done;
+                    AL3D_TS(0);
+                    d1a_phase[j] ^= 1; tc_fence_after();
+                    const uint32_t a = tmem + kColD1 + j * 64;        // bf16 image of chunk kc (in place)
+#pragma unroll
+                    for (int nc = 0; nc < 2; ++nc) {
+                        P2_NEXT_W(0xA320)
+                        mma_ts_k64(tmem + kColD2 + nc * 128, a, a + 8, a + 32, a + 40, smem_u32(s.wring[stage]), 128, id128, kc > 0);
+                        P2_REL_W()
+                    }
+                    if (kc + 3 < 8) {
+                        // the MMA pipe executes in issue order, so this overwrite of D1b[j] happens after the
+                        // partial sums above have consumed it
+                        P2_NEXT_W(0xA330)
+                        mma_ts_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24,
+                                   smem_u32(s.wring[stage]), 64, id64, false);
+                        P2_REL_W()
+                        mma_commit(&s.d1_full[j]);
                     }
                 }
-                {
-                    const int pc = 3, sl = 1;
-                    if (!mbar_wait(&s.d1_act[sl], d1a_phase[sl], 0xA400 + pc)) goto done;
-                    AL3D_TS(0);
-                    d1a_phase[sl] ^= 1; tc_fence_after();
-                    for (int nc = 0; nc < 2; ++nc)
-                        for (int kb = 0; kb < 2; ++kb) {
-                            P2_NEXT_W(0xA330)
-                            mma_block_k64(tmem + nc * 128, aRing[sl] + kb * 8 * kPlane, 128, smem_u32(s.wring[stage]), 128, id128, true);
-                            P2_REL_W()
-                        }
-                    mma_commit(&s.ring_free[sl]);
-                    mma_commit(&s.acc_ready);                                  // dconv2 accumulator complete
-                }
-                // dconv3 : A = bufD2 (256 ch) -> TMEM 256..383
-                if (!mbar_wait(&s.act_ready, act_phase, 0xA202)) goto done;
-                AL3D_TS(0);
-                act_phase ^= 1; tc_fence_after();
+                mma_commit(&s.acc_ready);                                  // dconv2 accumulator complete
+                // dconv3: A3 x Wd3 -> D3
+                P2_WAIT_ACT(0xA202)
+#pragma unroll
                 for (int kb = 0; kb < 4; ++kb) {
+                    const uint32_t a = tmem + kColD2 + (kb >> 1) * 128 + (kb & 1) * 32;
                     P2_NEXT_W(0xA340)
-                    mma_block_k64(tmem + 256, aD2 + kb * 8 * kPlane, 128, smem_u32(s.wring[stage]), 128, id128, kb > 0);
+                    mma_ts_k64(tmem + kColD3, a, a + 8, a + 16, a + 24, smem_u32(s.wring[stage]), 128, id128, kb > 0);
                     P2_REL_W()
                 }
                 mma_commit(&s.acc_ready);
-                // dconv4 : A = ring[0] (128 ch) -> TMEM 384..511
-                if (!mbar_wait(&s.act_ready, act_phase, 0xA203)) goto done;
-                AL3D_TS(0);
-                act_phase ^= 1; tc_fence_after();
+                // dconv4: A4 x Wd4 -> D4
+                P2_WAIT_ACT(0xA203)
+#pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
+                    const uint32_t a = tmem + kColD3 + kb * 64;
                     P2_NEXT_W(0xA350)
-                    mma_block_k64(tmem + 384, aRing[0] + kb * 8 * kPlane, 128, smem_u32(s.wring[stage]), 128, id128, kb > 0);
+                    mma_ts_k64(tmem + kColD4, a, a + 8, a + 16, a + 24, smem_u32(s.wring[stage]), 128, id128, kb > 0);
                     P2_REL_W()
                 }
                 mma_commit(&s.acc_ready);
             }
 #undef P2_NEXT_W
 #undef P2_REL_W
+#undef P2_WAIT_ACT
         }
     } else {
+        // ------------------------------------------------------------ epilogue warps (256 threads)
         const int row = epi_row(), half = epi_half();
         const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
-        const int etid = threadIdx.x - 64;                      // 0..255 among the epilogue threads
-        uint32_t acc_phase = 0, d1f_phase[2] = {0, 0}, rf_phase[2] = {0, 0};
+        const uint32_t tl = tmem + lane_addr;
+        const int etid = threadIdx.x - 64;
+        uint32_t acc_phase = 0, d1f_phase[3] = {0, 0, 0};
         int cur_obj = -1;
         int it_local = 0;
         const bool ts_on = (threadIdx.x == 64);
 #define AL3D_TSE() do { if (ts_on) AL3D_TS(1); } while (0)
+#define P2_PUBLISH(bar) do { tmem_st_wait(); tc_fence_before(); mbar_arrive(bar); } while (0)
+        // software prefetch of the tile's input point (hides the global-memory latency behind the previous tile)
+        float xv[8];
+        auto load_x = [&](int item, float (&dst)[8]) {
+            if (item < p.n_items) {
+                const int b = item / p.tiles_per_obj, t = item % p.tiles_per_obj;
+                int pidx = t * kTile + row;
+                if (pidx > p.n - 1) pidx = p.n - 1;
+                const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) dst[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+            }
+        };
+        load_x(blockIdx.x, xv);
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
             int ts_i = 0;
             AL3D_TSE();
@@ -624,82 +679,103 @@ seg_pass2_kernel(const Pass2Params p)
             const int pidx_raw = t * kTile + row;
             const bool valid = pidx_raw < p.n;
             const int pidx = valid ? pidx_raw : p.n - 1;
-            // per-object dconv1 bias: reload when the object changes.  The first barrier makes sure every
-            // epilogue thread is past the previous item's dconv1 epilogues (the only readers of s.gb).
             if (b != cur_obj) {
+                // every epilogue thread is past the previous item's dconv1 epilogues (the only readers of s.gb)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int i = etid; i < 512; i += kEpiThreads) s.gb[i] = __ldg(p.gbias + (int64_t)b * 512 + i);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_obj = b;
             }
-            // ---- conv1 on CUDA cores -> bufD2[0:16K]; each half computes 32 of the 64 channels
+            // ---- conv1 on CUDA cores: this thread's 32 channels -> 16 packed words -> A1
             {
-                const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
-                float xv[8];
+                uint32_t o[16];
+                const int ch0 = half * 32;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
-                AL3D_TSE();
-                first_layer(s.bufD2, row, xv, p.c_in, 64, half * 32, 32, s.w1_w, s.w1_b);
-                fence_proxy_async_smem();
-                mbar_arrive(&s.act_ready);
+                for (int g = 0; g < 4; ++g) {
+                    float4 a0 = *reinterpret_cast<const float4 *>(s.w1_b + ch0 + g * 8);
+                    float4 a1 = *reinterpret_cast<const float4 *>(s.w1_b + ch0 + g * 8 + 4);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (c >= p.c_in) break;
+                        const float4 w0v = *reinterpret_cast<const float4 *>(s.w1_w + c * 64 + ch0 + g * 8);
+                        const float4 w1v = *reinterpret_cast<const float4 *>(s.w1_w + c * 64 + ch0 + g * 8 + 4);
+                        const float xx = xv[c];
+                        a0.x = fmaf(xx, w0v.x, a0.x); a0.y = fmaf(xx, w0v.y, a0.y); a0.z = fmaf(xx, w0v.z, a0.z); a0.w = fmaf(xx, w0v.w, a0.w);
+                        a1.x = fmaf(xx, w1v.x, a1.x); a1.y = fmaf(xx, w1v.y, a1.y); a1.z = fmaf(xx, w1v.z, a1.z); a1.w = fmaf(xx, w1v.w, a1.w);
+                    }
+                    o[g * 4 + 0] = relu_pack_bf16x2(a0.x, a0.y); o[g * 4 + 1] = relu_pack_bf16x2(a0.z, a0.w);
+                    o[g * 4 + 2] = relu_pack_bf16x2(a1.x, a1.y); o[g * 4 + 3] = relu_pack_bf16x2(a1.z, a1.w);
+                }
+                tmem_st16(tl + kColA1 + half * 16, o);
+                P2_PUBLISH(&s.act_ready);
                 AL3D_TSE();
             }
-            // ---- conv2 epilogue -> bufA2 (32 columns per thread)
+            load_x(item + gridDim.x, xv);                              // prefetch the next tile's point
+            // ---- conv2 epilogue: D1b[2] -> A2
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB100)) goto done;
             AL3D_TSE();
             acc_phase ^= 1; tc_fence_after();
-            epilogue_cols<32>(tmem + lane_addr, s.bufA2, half * 32, row, s.b2);
-            tc_fence_before(); fence_proxy_async_smem();
-            mbar_arrive(&s.act_ready);
-            AL3D_TSE();
-            // ---- dconv1 chunk epilogues -> ring (64 columns per thread)
-            for (int kc = 0; kc < 4; ++kc) {
-                const int sl = kc & 1;
-                if (!mbar_wait(&s.d1_full[sl], d1f_phase[sl], 0xB200 + kc)) goto done;
-                d1f_phase[sl] ^= 1;
-                // the ring slot is free once dconv2's partial for the chunk that used it last has completed
-                if (kc >= 2) {
-                    if (!mbar_wait(&s.ring_free[sl], rf_phase[sl], 0xB300 + kc)) goto done;
-                    rf_phase[sl] ^= 1;
-                }
-                AL3D_TSE();
-                tc_fence_after();
-                {
-                    uint32_t v0[32], v1[32];
-                    const uint32_t ta = tmem + lane_addr + 256 + sl * 128 + half * 64;
-                    tmem_ld32(ta, v0);
-                    tmem_ld32(ta + 32, v1);
-                    tmem_ld_wait();
-                    AL3D_TSE();
-                    store_act32(s.ring[sl], (half * 64) >> 3, row, v0, s.gb + kc * 128 + half * 64);
-                    store_act32(s.ring[sl], (half * 64 + 32) >> 3, row, v1, s.gb + kc * 128 + half * 64 + 32);
-                    AL3D_TSE();
-                }
-                tc_fence_before(); fence_proxy_async_smem();
-                AL3D_TSE();
-                mbar_arrive(&s.d1_act[sl]);
+            {
+                uint32_t v[32], o[16];
+                tmem_ld32(tl + kColD1 + 128 + half * 32, v);
+                tmem_ld_wait();
+                pack_act32(v, s.b2 + half * 32, o);
+                tmem_st16(tl + kColA2 + half * 16, o);
+                P2_PUBLISH(&s.act_ready);
                 AL3D_TSE();
             }
-            // ---- dconv2 epilogue -> bufD2 (128 columns per thread)
+            // ---- dconv1 chunk epilogues, in place
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+                const int j = kc % 3;
+                if (!mbar_wait(&s.d1_full[j], d1f_phase[j], 0xB200 + kc)) goto done;
+                AL3D_TSE();
+                d1f_phase[j] ^= 1; tc_fence_after();
+                uint32_t v[32], o[16];
+                const uint32_t ta = tl + kColD1 + j * 64 + half * 32;
+                tmem_ld32(ta, v);
+                tmem_ld_wait();
+                pack_act32(v, s.gb + kc * 64 + half * 32, o);
+                tmem_st16(ta, o);
+                P2_PUBLISH(&s.d1_act[j]);
+                AL3D_TSE();
+            }
+            // ---- dconv2 epilogue: D2 -> A3 in place (this thread: 128 columns in two batches)
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB101)) goto done;
             AL3D_TSE();
             acc_phase ^= 1; tc_fence_after();
-            epilogue_cols<128>(tmem + lane_addr, s.bufD2, half * 128, row, s.bd2);
-            tc_fence_before(); fence_proxy_async_smem();
-            mbar_arrive(&s.act_ready);
-            AL3D_TSE();
-            // ---- dconv3 epilogue -> ring[0] (both ring slots are idle: wait out their last partials)
-            for (int sl = 0; sl < 2; ++sl) {
-                if (!mbar_wait(&s.ring_free[sl], rf_phase[sl], 0xB310 + sl)) goto done;
-                rf_phase[sl] ^= 1;
+#pragma unroll
+            for (int bt = 0; bt < 2; ++bt) {
+                uint32_t v0[32], v1[32], o0[16], o1[16];
+                const uint32_t src = tl + kColD2 + half * 128 + bt * 64;
+                tmem_ld32(src, v0);
+                tmem_ld32(src + 32, v1);
+                tmem_ld_wait();
+                pack_act32(v0, s.bd2 + half * 128 + bt * 64, o0);
+                pack_act32(v1, s.bd2 + half * 128 + bt * 64 + 32, o1);
+                const uint32_t dst = tl + kColD2 + half * 128 + bt * 32;
+                tmem_st16(dst, o0);
+                tmem_st16(dst + 16, o1);
             }
+            P2_PUBLISH(&s.act_ready);
+            AL3D_TSE();
+            // ---- dconv3 epilogue: D3 -> A4 in place (64 columns)
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB102)) goto done;
             AL3D_TSE();
             acc_phase ^= 1; tc_fence_after();
-            epilogue_cols<64>(tmem + lane_addr + 256, s.ring[0], half * 64, row, s.bd3);
-            tc_fence_before(); fence_proxy_async_smem();
-            mbar_arrive(&s.act_ready);
-            AL3D_TSE();
+            {
+                uint32_t v0[32], v1[32], o0[16], o1[16];
+                const uint32_t src = tl + kColD3 + half * 64;
+                tmem_ld32(src, v0);
+                tmem_ld32(src + 32, v1);
+                tmem_ld_wait();
+                pack_act32(v0, s.bd3 + half * 64, o0);
+                pack_act32(v1, s.bd3 + half * 64 + 32, o1);
+                tmem_st16(src, o0);
+                tmem_st16(src + 16, o1);
+                P2_PUBLISH(&s.act_ready);
+                AL3D_TSE();
+            }
             // ---- dconv4 epilogue: bias + ReLU in fp32, then the 128 -> 2 layer, logits and mask.
             //      Each half reduces 64 channels; the upper half hands its partial sums over in smem and the
             //      lower half adds them in a fixed order (deterministic).
@@ -709,8 +785,8 @@ seg_pass2_kernel(const Pass2Params p)
             {
                 uint32_t v0[32], v1[32];
                 const int c0 = half * 64;
-                tmem_ld32(tmem + lane_addr + 384 + c0, v0);
-                tmem_ld32(tmem + lane_addr + 384 + c0 + 32, v1);
+                tmem_ld32(tl + kColD4 + c0, v0);
+                tmem_ld32(tl + kColD4 + c0 + 32, v1);
                 tmem_ld_wait();
                 tc_fence_before();
                 float l0a = 0.f, l1a = 0.f, l0b = 0.f, l1b = 0.f;
@@ -746,12 +822,14 @@ seg_pass2_kernel(const Pass2Params p)
                 AL3D_TSE();
             }
         }
+#undef P2_PUBLISH
     }
 done:
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
+
 
 }  // namespace al3d
 
@@ -876,6 +954,7 @@ extern "C" int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, 
     p.n_items = (int)items;
     const int grid = std::min(p.n_items, num_sms());
     const size_t smem = sizeof(Pass2Smem) + 128;
+    static_assert(sizeof(Pass2Smem) + 128 <= 232448, "Pass2Smem exceeds the 227 KB opt-in limit");
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(seg_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     seg_pass2_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
     AL3D_CHECK_LAUNCH("seg_pass2_kernel");

@@ -88,17 +88,21 @@ class SegPack:
         wd1, wd2, wd3, wd4 = (fw[k][0] for k in ("dconv1", "dconv2", "dconv3", "dconv4"))
         blocks = [_block(fw["conv2"][0])]
 
-        def d1(kc):
-            return [_block(wd1[kc * 128:(kc + 1) * 128, 0:64])]
+        def d1(c):                     # dconv1 chunk c: 64 output channels x the 64 per-point input channels
+            return [_block(wd1[c * 64:(c + 1) * 64, 0:64])]
 
-        def d2(pc):
-            return [_block(wd2[nc * 128:(nc + 1) * 128, pc * 128 + kb * 64: pc * 128 + kb * 64 + 64])
-                    for nc in range(2) for kb in range(2)]
+        def d2(pc):                    # dconv2 partial sum over input channels pc*64..+64, two 128-row halves
+            return [_block(wd2[nc * 128:(nc + 1) * 128, pc * 64:(pc + 1) * 64]) for nc in range(2)]
 
-        blocks += d1(0) + d1(1) + d2(0) + d1(2) + d2(1) + d1(3) + d2(2) + d2(3)
+        # issue order of the MMA thread in seg_pass2_kernel
+        blocks += d1(0) + d1(1) + d1(2)
+        for kc in range(8):
+            blocks += d2(kc)
+            if kc + 3 < 8:
+                blocks += d1(kc + 3)
         blocks += [_block(wd3[:, kb * 64:(kb + 1) * 64]) for kb in range(4)]
         blocks += [_block(wd4[:, kb * 64:(kb + 1) * 64]) for kb in range(2)]
-        assert len(blocks) == 27
+        assert len(blocks) == 31
         self.t = {"w1_w": _pad8(fw["conv1"][0]), "w1_b": fw["conv1"][1].contiguous(), "b2": fw["conv2"][1].contiguous(),
                   "bd2": fw["dconv2"][1].contiguous(), "bd3": fw["dconv3"][1].contiguous(),
                   "bd4": fw["dconv4"][1].contiguous(), "w5": fw["dconv5"][0].contiguous(),

@@ -56,17 +56,29 @@ def test_pass2_stream_order_matches_kernel_schedule():
     fw = fold_state_dict(sd, "ins_seg", spec.seg_layers(4))
     pack = eb.pack_seg(fw, 4)
     blocks = _blocks(pack.t["wstream"])
-    assert blocks.shape[0] == 27
+    assert blocks.shape[0] == 31
     bf = lambda n: fw[n][0].to(torch.bfloat16).float()
     wd1, wd2, wd3, wd4 = bf("dconv1"), bf("dconv2"), bf("dconv3"), bf("dconv4")
     expect = [("conv2", bf("conv2"), 64)]
-    d1 = lambda kc: [("d1_%d" % kc, wd1[kc * 128:(kc + 1) * 128, :64], 128)]
-    d2 = lambda pc: [("d2_%d_%d_%d" % (pc, nc, kb), wd2[nc * 128:(nc + 1) * 128, pc * 128 + kb * 64: pc * 128 + kb * 64 + 64], 128)
-                     for nc in range(2) for kb in range(2)]
+    d1 = lambda c: [("d1_%d" % c, wd1[c * 64:(c + 1) * 64, :64], 64)]
+    d2 = lambda pc: [("d2_%d_%d" % (pc, nc), wd2[nc * 128:(nc + 1) * 128, pc * 64:(pc + 1) * 64], 128) for nc in range(2)]
     # issue order of the MMA thread in seg_pass2_kernel
-    expect += d1(0) + d1(1) + d2(0) + d1(2) + d2(1) + d1(3) + d2(2) + d2(3)
+    expect += d1(0) + d1(1) + d1(2)
+    for kc in range(8):
+        expect += d2(kc)
+        if kc + 3 < 8:
+            expect += d1(kc + 3)
     expect += [("d3_%d" % kb, wd3[:, kb * 64:(kb + 1) * 64], 128) for kb in range(4)]
     expect += [("d4_%d" % kb, wd4[:, kb * 64:(kb + 1) * 64], 128) for kb in range(2)]
+    assert len(expect) == 31
+    # block sizes the producer warp copies (p2_block_bytes in csrc/chain_bf16.cu)
+    def block_bytes(blk):
+        if blk <= 3:
+            return 8192
+        if blk < 19:
+            return 8192 if (blk - 4) % 3 == 2 else 16384
+        return 16384
+    assert [rows * 128 for _, _, rows in expect] == [block_bytes(i) for i in range(31)]
     for i, (name, w, rows) in enumerate(expect):
         assert torch.equal(kp_unpack(blocks[i][: rows * 64].float(), rows, 64), w), name
     assert pack.struct.c_in == 4 and pack.w_glob.shape == (512, 1024)
