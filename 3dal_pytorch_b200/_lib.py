@@ -30,6 +30,9 @@ _SIGNATURES = {
     "al3d_crop_scan": [_vp, _vp, _i, _i64, _vp, _i, _vp, _vp, _vp],
     "al3d_crop_fill": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "al3d_crop_dense_mask": [_vp, _vp, _i, _vp, _vp],
+    "al3d_track_points_prep": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "al3d_boxseq_prep": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "al3d_loss_forward": [_vp, _vp, _i64] + [_vp] * 10 + [_i, _vp, _i, _vp, _vp],
     "al3d_chain_maxpool_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
     "al3d_seg_pass2_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp],
     "al3d_umma_selftest": [_vp, _vp, _i, _i, _vp, _i, _vp],

@@ -140,6 +140,42 @@ int al3d_crop_fill(const float *points, int64_t pt_stride, const int64_t *pt_off
 int al3d_crop_dense_mask(const int32_t *idx, const int64_t *offsets, int n_boxes, uint8_t *mask, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Device-side track preparation (dataset-side merge / resample / canonical-frame transform).
+ * Replaces the numpy part of STATICTRACK.__getitem__ (tools/static_model.py:541-547,569-570) and of
+ * DYNAMICTRACK.__getitem__ (tools/dynamic_model.py:429-453,503-507).  float64 arithmetic like the reference,
+ * rounded to float32 once on output.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* out[b,j,0:3] = Rz(-heading_b) (inv_pose_b [p;1] - centre_b), p = src_xyz[choice[b,j]] (or the origin when
+ * choice[b,j] < 0: the reference's zero-padded frames go through the same transform); with c_out == 4
+ * out[b,j,3] = 0.1 * (j / time_block - time_center).  src_xyz (rows,3) f64 global frame; choice (bs,n_out)
+ * i64 absolute row indices (the resample of :546-547 / :431-437, drawn by the caller); inv_pose (bs,16) f64
+ * row-major; init_box (bs, box_stride) f64 with centre in columns 0..2 and heading in column heading_col;
+ * out (bs, n_out, c_out) f32 point-major. */
+int al3d_track_points_prep(const double *src_xyz, const int64_t *choice, int bs, int n_out, const double *inv_pose,
+                           const double *init_box, int box_stride, int heading_col, int c_out, int time_block,
+                           int time_center, float *out, void *stream);
+
+/* box (bs, steps, 8) f64 global-frame [x y z l w h heading dt] -> out (bs, steps, 8) f32 step-major in the
+ * vehicle frame of inv_pose, relative to the centre step (transform_box tools/dynamic_model.py:511-525, :452,
+ * :506-507); init_box (bs, 8) f64 receives the centre step before the subtraction (:489), may be NULL. */
+int al3d_boxseq_prep(const double *box, int bs, int steps, int center_step, const double *inv_pose, float *out,
+                     double *init_box, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss forward (evaluation / logging; no backward).  Replaces FrustumPointNetLossOneBoxEst.forward
+ * tools/static_model.py:348-425 (each head set of ...TwoBoxEst :427-517; DynamicModelLoss
+ * tools/dynamic_model.py:321-398).  out6 = [mask NLL, centre Huber(2), heading CE, size CE, heading-residual
+ * Huber(1), size-residual Huber(1)], unweighted means; logits == NULL skips the mask term (out6[0] = 0).
+ * mask_label (M) f32 0/1; class labels i64; partial_ws (n_partial) f32 scratch.
+ * ---------------------------------------------------------------------------------------------- */
+int al3d_loss_forward(const float *logits, const float *mask_label, int64_t M, const float *center,
+                      const float *center_label, const float *heading_scores, const int64_t *heading_cls_label,
+                      const float *heading_res_norm, const float *heading_res_label, const float *size_scores,
+                      const int64_t *size_cls_label, const float *size_res_norm, const float *size_res_label, int bs,
+                      float *partial_ws, int n_partial, float *out6, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 / TMEM, bf16 operands, fp32 accumulate) shared-MLP kernels.
  * Weights are BatchNorm-folded and packed by the caller (3dal_pytorch_b200/engine_bf16.py) into
  * 16 KB blocks of 128 rows x 64 K in the "KP" layout (K/8 planes of rows x 16 bytes), stored in the
