@@ -34,6 +34,7 @@ _SIGNATURES = {
     "al3d_boxseq_prep": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "al3d_loss_forward": [_vp, _vp, _i64] + [_vp] * 10 + [_i, _vp, _i, _vp, _vp],
     "al3d_chain_maxpool_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
+    "al3d_seg_pass1_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
     "al3d_seg_pass2_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp],
     "al3d_umma_selftest": [_vp, _vp, _i, _i, _vp, _i, _vp],
     "al3d_umma_selftest_ts": [_vp, _vp, _i, _i, _vp, _vp],

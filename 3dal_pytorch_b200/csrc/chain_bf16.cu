@@ -831,6 +831,274 @@ done:
 }
 
 
+// ================================================================================================
+// seg_pass1_kernel -- ins_seg conv1..conv5 + max over points, tiles processed in PAIRS
+//
+// conv2-4 run with their activations in TMEM (as in seg_pass2_kernel), their 32 KB of weights resident in
+// shared memory.  conv4's output of both tiles of a pair is written to one 256-row shared-memory operand, and
+// conv5 is computed transposed with N = 256 points per MMA: every streamed 16 KB block of conv5 weights is
+// used for 256 points instead of 128, halving the L2 -> smem weight traffic that bounded the 128-point
+// version, and the max over points stays a per-thread reduction over TMEM columns.
+//
+// TMEM: tile X uses columns [0,256), tile Y [256,512) during the front layers
+//   (+0 A1 | +32 D(conv2) | +96 A2 | +128 D(conv3) | +192 A3 | D(conv4) reuses +0..+127);
+// conv5 then double-buffers its 256-column accumulators over the same two halves.
+// ================================================================================================
+struct Pass1Params {
+    const float *x; int64_t sb, sc, sp; int bs, n; int c_in;
+    const float *w1_w, *w1_b;          // conv1 fp32 (8, 64) transposed + padded, (64)
+    const float *b2, *b3, *b4, *b5;    // conv2-5 biases (64),(64),(128),(1024)
+    const uint8_t *wfront;             // conv2, conv3 (64 rows x 64 K, 8 KB each in 16 KB slots), conv4 (128 x 64)
+    const uint8_t *w5stream;           // 16 blocks of 128 channels x 64 K, order (chunk, k-block)
+    float *out;                        // (bs, 1024) zero-initialised
+    int splits, n_items;
+};
+
+constexpr int kP1Stages = 7;
+struct Pass1Smem {
+    uint8_t out4[16 * 4096];           // conv4 output of the tile pair: KP tile of 256 rows x 128 channels
+    uint8_t wfront[32768];             // resident conv2 (8 KB) | conv3 (8 KB) | conv4 (16 KB) weights
+    uint8_t wring[kP1Stages][kStageBytes];
+    float w1_w[64 * 8], w1_b[64], b2[64], b3[64], b4[128];
+    uint64_t w_full[kP1Stages], w_empty[kP1Stages];
+    uint64_t res_full, out4_ready;
+    uint64_t act[2], acc[2];           // per tile of the pair
+    uint64_t last_full[2], last_empty[2];
+    uint32_t tmem_base;
+};
+
+// conv1 on CUDA cores for 32 output channels starting at ch0 -> 16 packed bf16x2 words
+__device__ __forceinline__ void conv1_pack32(const float (&xv)[8], int c_in, const float *w_t, const float *bias, int ch0,
+                                             uint32_t (&o)[16])
+{
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float4 a0 = *reinterpret_cast<const float4 *>(bias + ch0 + g * 8);
+        float4 a1 = *reinterpret_cast<const float4 *>(bias + ch0 + g * 8 + 4);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= c_in) break;
+            const float4 w0v = *reinterpret_cast<const float4 *>(w_t + c * 64 + ch0 + g * 8);
+            const float4 w1v = *reinterpret_cast<const float4 *>(w_t + c * 64 + ch0 + g * 8 + 4);
+            const float xx = xv[c];
+            a0.x = fmaf(xx, w0v.x, a0.x); a0.y = fmaf(xx, w0v.y, a0.y); a0.z = fmaf(xx, w0v.z, a0.z); a0.w = fmaf(xx, w0v.w, a0.w);
+            a1.x = fmaf(xx, w1v.x, a1.x); a1.y = fmaf(xx, w1v.y, a1.y); a1.z = fmaf(xx, w1v.z, a1.z); a1.w = fmaf(xx, w1v.w, a1.w);
+        }
+        o[g * 4 + 0] = relu_pack_bf16x2(a0.x, a0.y); o[g * 4 + 1] = relu_pack_bf16x2(a0.z, a0.w);
+        o[g * 4 + 2] = relu_pack_bf16x2(a1.x, a1.y); o[g * 4 + 3] = relu_pack_bf16x2(a1.z, a1.w);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+seg_pass1_kernel(const Pass1Params p)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Pass1Smem &s = *reinterpret_cast<Pass1Smem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < 64 * 8; i += kThreads) s.w1_w[i] = p.w1_w[i];
+    for (int i = threadIdx.x; i < 64; i += kThreads) { s.w1_b[i] = p.w1_b[i]; s.b2[i] = p.b2[i]; s.b3[i] = p.b3[i]; }
+    for (int i = threadIdx.x; i < 128; i += kThreads) s.b4[i] = p.b4[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kP1Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+        mbar_init(&s.res_full, 1);
+        mbar_init(&s.out4_ready, 2 * kEpiThreads);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s.act[i], kEpiThreads); mbar_init(&s.acc[i], 1);
+            mbar_init(&s.last_full[i], 1); mbar_init(&s.last_empty[i], kEpiThreads);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&s.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    const int tiles_per_obj = (p.n + kTile - 1) / kTile;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ producer: resident front weights, then W5 ring
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&s.res_full, 8192 + 8192 + 16384);
+            bulk_g2s(s.wfront, p.wfront, 8192, &s.res_full);
+            bulk_g2s(s.wfront + 8192, p.wfront + kStageBytes, 8192, &s.res_full);
+            bulk_g2s(s.wfront + 16384, p.wfront + 2 * kStageBytes, 16384, &s.res_full);
+            int stage = 0; uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int sp_i = item % p.splits;
+                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+                for (int t = t0; t < t1; t += 2) {
+                    for (int blk = 0; blk < 16; ++blk) {
+                        if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x9100 + stage)) goto done;
+                        mbar_arrive_expect_tx(&s.w_full[stage], kStageBytes);
+                        bulk_g2s(s.wring[stage], p.w5stream + (size_t)blk * kStageBytes, kStageBytes, &s.w_full[stage]);
+                        if (++stage == kP1Stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0; uint32_t wphase = 0, act_phase[2] = {0, 0}, le_phase[2] = {0, 0}, o4_phase = 0;
+            const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128), id256 = make_idesc_bf16(128, 256);
+            const uint32_t wf0 = smem_u32(s.wfront), wf1 = wf0 + 8192, wf2 = wf0 + 16384;
+            const uint32_t a_out4 = smem_u32(s.out4);
+            if (!mbar_wait(&s.res_full, 0, 0x9200)) goto done;
+            tc_fence_after();
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int sp_i = item % p.splits;
+                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+                for (int t = t0; t < t1; t += 2) {
+                    // front layers, the two tiles interleaved: while the epilogue converts X, the tensor core works on Y
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint32_t base = tmem + q * 256;
+                            if (!mbar_wait(&s.act[q], act_phase[q], 0x9300 + l * 2 + q)) goto done;
+                            act_phase[q] ^= 1; tc_fence_after();
+                            if (l == 0)      mma_ts_k64(base + 32, base, base + 8, base + 16, base + 24, wf0, 64, id64, false);
+                            else if (l == 1) mma_ts_k64(base + 128, base + 96, base + 104, base + 112, base + 120, wf1, 64, id64, false);
+                            else             mma_ts_k64(base, base + 192, base + 200, base + 208, base + 216, wf2, 128, id128, false);
+                            mma_commit(&s.acc[q]);
+                        }
+                    }
+                    // conv5, transposed, N = 256 points (both tiles): D^T[128 channels x 256 points]
+                    if (!mbar_wait(&s.out4_ready, o4_phase, 0x9400)) goto done;
+                    o4_phase ^= 1; tc_fence_after();
+#pragma unroll 1
+                    for (int cc = 0; cc < 8; ++cc) {
+                        const int b = cc & 1;
+                        if (!mbar_wait(&s.last_empty[b], le_phase[b] ^ 1, 0x9500 + b)) goto done;
+                        le_phase[b] ^= 1; tc_fence_after();
+                        for (int kb = 0; kb < 2; ++kb) {
+                            if (!mbar_wait(&s.w_full[stage], wphase, 0x9600 + stage)) goto done;
+                            tc_fence_after();
+                            mma_block_k64(tmem + b * 256, smem_u32(s.wring[stage]), 128, a_out4 + kb * 8 * 4096, 256, id256, kb > 0);
+                            mma_commit(&s.w_empty[stage]);
+                            if (++stage == kP1Stages) { stage = 0; wphase ^= 1; }
+                        }
+                        mma_commit(&s.last_full[b]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (256 threads)
+        const int row = epi_row(), half = epi_half();
+        const uint32_t tl = tmem + ((uint32_t)(row & ~31) << 16);
+        uint32_t acc_phase[2] = {0, 0}, lf_phase[2] = {0, 0};
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int b = item / p.splits, sp_i = item % p.splits;
+            const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+            float rmax[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
+            for (int t = t0; t < t1; t += 2) {
+                // ---- conv1 of both tiles (an odd tail pair repeats its tile: the max is idempotent under duplicates)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int tq = (t + q < t1) ? t + q : t1 - 1;
+                    int pidx = tq * kTile + row;
+                    if (pidx > p.n - 1) pidx = p.n - 1;
+                    const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
+                    float xv[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+                    uint32_t o[16];
+                    conv1_pack32(xv, p.c_in, s.w1_w, s.w1_b, half * 32, o);
+                    tmem_st16(tl + q * 256 + half * 16, o);
+                    tmem_st_wait(); tc_fence_before();
+                    mbar_arrive(&s.act[q]);
+                }
+                // ---- conv2, conv3 epilogues: accumulator -> packed operand of the next layer
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8100 + l * 2 + q)) goto done;
+                        acc_phase[q] ^= 1; tc_fence_after();
+                        uint32_t v[32], o[16];
+                        const uint32_t src = tl + q * 256 + (l == 0 ? 32 : 128) + half * 32;
+                        const uint32_t dst = tl + q * 256 + (l == 0 ? 96 : 192) + half * 16;
+                        tmem_ld32(src, v);
+                        tmem_ld_wait();
+                        pack_act32(v, (l == 0 ? s.b2 : s.b3) + half * 32, o);
+                        tmem_st16(dst, o);
+                        tmem_st_wait(); tc_fence_before();
+                        mbar_arrive(&s.act[q]);
+                    }
+                }
+                // ---- conv4 epilogue: 64 of the 128 channels of this row -> shared-memory operand of conv5
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8200 + q)) goto done;
+                    acc_phase[q] ^= 1; tc_fence_after();
+                    uint32_t v0[32], v1[32], o0[16], o1[16];
+                    const uint32_t src = tl + q * 256 + half * 64;
+                    tmem_ld32(src, v0);
+                    tmem_ld32(src + 32, v1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    pack_act32(v0, s.b4 + half * 64, o0);
+                    pack_act32(v1, s.b4 + half * 64 + 32, o1);
+                    uint8_t *dst = s.out4 + (size_t)(half * 8) * 4096 + (size_t)(q * kTile + row) * 16;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        *reinterpret_cast<uint4 *>(dst + (size_t)j * 4096) = make_uint4(o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
+                        *reinterpret_cast<uint4 *>(dst + (size_t)(4 + j) * 4096) = make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&s.out4_ready);
+                }
+                // ---- conv5: this thread owns channel (cc*128 + row) and 128 of the pair's 256 points
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int bsel = cc & 1;
+                    if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0x8300 + cc)) goto done;
+                    lf_phase[bsel] ^= 1; tc_fence_after();
+                    float m0 = rmax[cc], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+                    for (int c0 = 0; c0 < 128; c0 += 64) {
+                        uint32_t v0[32], v1[32];
+                        const uint32_t ta = tl + bsel * 256 + half * 128 + c0;
+                        tmem_ld32(ta, v0);
+                        tmem_ld32(ta + 32, v1);
+                        tmem_ld_wait();
+                        if (c0 == 64) { tc_fence_before(); mbar_arrive(&s.last_empty[bsel]); }   // all values are in registers
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            m0 = fmax3(m0, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
+                            m1 = fmax3(m1, __uint_as_float(v0[i + 2]), __uint_as_float(v0[i + 3]));
+                            m2 = fmax3(m2, __uint_as_float(v0[i + 4]), __uint_as_float(v0[i + 5]));
+                            m3 = fmax3(m3, __uint_as_float(v0[i + 6]), __uint_as_float(v0[i + 7]));
+                            m0 = fmax3(m0, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
+                            m1 = fmax3(m1, __uint_as_float(v1[i + 2]), __uint_as_float(v1[i + 3]));
+                            m2 = fmax3(m2, __uint_as_float(v1[i + 4]), __uint_as_float(v1[i + 5]));
+                            m3 = fmax3(m3, __uint_as_float(v1[i + 6]), __uint_as_float(v1[i + 7]));
+                        }
+                    }
+                    rmax[cc] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                }
+            }
+            // ---- publish: relu(max + bias) >= 0, so integer atomicMax on the bit pattern is exact
+            if (t1 > t0) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int ch = cc * 128 + row;
+                    const float v = fmaxf(rmax[cc] + __ldg(p.b5 + ch), 0.f);
+                    atomicMax(reinterpret_cast<int *>(p.out + (int64_t)b * 1024 + ch), __float_as_int(v));
+                }
+            }
+        }
+    }
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 }  // namespace al3d
 
 using namespace al3d;
@@ -933,6 +1201,32 @@ extern "C" int al3d_chain_maxpool_bf16(const al3d_chain_weights *w, const float 
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(chain_max_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     chain_max_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
     AL3D_CHECK_LAUNCH("chain_max_kernel");
+    return 0;
+}
+
+extern "C" int al3d_seg_pass1_bf16(const al3d_pass1_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
+                                   int bs, int n, float *out, void *stream)
+{
+    AL3D_CHECK_ARG(w && x && out, "al3d_seg_pass1_bf16: null pointer");
+    AL3D_CHECK_ARG(w->c_in >= 1 && w->c_in <= 8, "al3d_seg_pass1_bf16: c_in=%d", w->c_in);
+    AL3D_CHECK_ARG(bs >= 0 && n >= 1, "al3d_seg_pass1_bf16: bad shape");
+    if (bs == 0) return 0;
+    Pass1Params p;
+    p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n; p.c_in = w->c_in;
+    p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.b3 = w->b3; p.b4 = w->b4; p.b5 = w->b5;
+    p.wfront = (const uint8_t *)w->wfront; p.w5stream = (const uint8_t *)w->w5stream; p.out = out;
+    const int tiles = (n + kTile - 1) / kTile;
+    const int sms = num_sms();
+    int splits = 1;
+    if (bs < 2 * sms) splits = (int)std::min<int64_t>((tiles + 1) / 2, ceil_div(2 * sms, bs));
+    p.splits = std::max(splits, 1);
+    p.n_items = bs * p.splits;
+    const int grid = std::min(p.n_items, sms);
+    const size_t smem = sizeof(Pass1Smem) + 128;
+    static_assert(sizeof(Pass1Smem) + 128 <= 232448, "Pass1Smem exceeds the 227 KB opt-in limit");
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(seg_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    seg_pass1_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    AL3D_CHECK_LAUNCH("seg_pass1_kernel");
     return 0;
 }
 

@@ -24,6 +24,12 @@ class ChainWeightsStruct(ctypes.Structure):
                 ("last_b", ctypes.c_void_p), ("wstream", ctypes.c_void_p)]
 
 
+class Pass1WeightsStruct(ctypes.Structure):
+    _fields_ = [("c_in", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("w1_w", ctypes.c_void_p), ("w1_b", ctypes.c_void_p), ("b2", ctypes.c_void_p), ("b3", ctypes.c_void_p),
+                ("b4", ctypes.c_void_p), ("b5", ctypes.c_void_p), ("wfront", ctypes.c_void_p), ("w5stream", ctypes.c_void_p)]
+
+
 class Pass2WeightsStruct(ctypes.Structure):
     _fields_ = [("c_in", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("w1_w", ctypes.c_void_p), ("w1_b", ctypes.c_void_p), ("b2", ctypes.c_void_p),
@@ -112,6 +118,16 @@ class SegPack:
         for k, v in self.t.items():
             setattr(s, k, v.data_ptr())
         self.struct = s
+        # pass 1 (conv1-5 + max), specialised kernel: conv2-4 resident, conv5 streamed in (chunk, k-block) order
+        self.t1 = {"w1_w": self.t["w1_w"], "w1_b": self.t["w1_b"], "b2": self.t["b2"], "b3": fw["conv3"][1].contiguous(),
+                   "b4": fw["conv4"][1].contiguous(), "b5": fw["conv5"][1].contiguous(),
+                   "wfront": torch.cat([_block(fw["conv2"][0]), _block(fw["conv3"][0]), _block(fw["conv4"][0])]).contiguous(),
+                   "w5stream": torch.cat(_layer_blocks(fw["conv5"][0])).contiguous()}
+        s1 = Pass1WeightsStruct()
+        s1.c_in = c_in
+        for k, v in self.t1.items():
+            setattr(s1, k, v.data_ptr())
+        self.struct1 = s1
         # the 1024-wide half of dconv1 acts on the per-object global feature: kept fp32
         self.w_glob = wd1[:, 64:]
         self.b_d1 = fw["dconv1"][1]
@@ -168,10 +184,24 @@ def chain_maxpool(pack, x):
     return out
 
 
+def seg_pass1(pack, pts):
+    """ins_seg conv1-5 + max: pts (bs,C,n) any strides -> (bs,1024) fp32 global feature."""
+    ops._need_cuda(pts)
+    bs, C, n = pts.shape
+    out = torch.zeros((bs, 1024), device=pts.device, dtype=torch.float32)
+    sb, sc, sp = pts.stride()
+    with _timed("seg_pass1_kernel"):
+        _lib.check(_lib.lib().al3d_seg_pass1_bf16(ctypes.byref(pack.struct1), pts.data_ptr(), sb, sc, sp, bs, n,
+                                                  out.data_ptr(), ops._stream()), "seg_pass1_bf16")
+    if CHECK_ABORT:
+        check_abort("seg_pass1_kernel")
+    return out
+
+
 def seg_forward(pack, fw, pts):
     """-> logits (bs,n,2) f32, mask (bs,n) bool."""
     bs, C, n = pts.shape
-    g = chain_maxpool(pack.pass1, pts)
+    g = seg_pass1(pack, pts)
     gbias = ops.linear(g, pack.w_glob, pack.b_d1, act=ops.ACT_NONE, K=1024)
     logits = torch.empty((bs, n, 2), device=pts.device, dtype=torch.float32)
     mask = torch.empty((bs, n), device=pts.device, dtype=torch.bool)

@@ -283,7 +283,7 @@ def main():
         # dominant kernel: segmentation pass 2 (dconv1..dconv5).  Algorithmic MACs per point are the
         # factored count of SURVEY.md 8d; the conv1-2 recompute is not credited.
         macs_pt = {"seg_pass2_kernel": 64 * 512 + 512 * 256 + 256 * 128 + 128 * 128 + 128 * 2,
-                   "chain_max_kernel[last=1024]": 3 * 64 + 64 * 64 + 64 * 64 + 64 * 128 + 128 * 1024}
+                   "seg_pass1_kernel": 3 * 64 + 64 * 64 + 64 * 64 + 64 * 128 + 128 * 1024}
         dom = max((k for k in kernel_ms if k in macs_pt), key=lambda k: kernel_ms[k], default=None)
         roofline = None
         if dom is not None:

@@ -203,6 +203,21 @@ typedef struct al3d_chain_weights {
 int al3d_chain_maxpool_bf16(const al3d_chain_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
                             int bs, int n, float *out, void *stream);
 
+typedef struct al3d_pass1_weights {
+    int32_t c_in;
+    int32_t reserved;
+    const float *w1_w, *w1_b;          /* ins_seg.conv1 folded fp32: (8,64) transposed + padded, (64)  */
+    const float *b2, *b3, *b4, *b5;    /* conv2-5 biases (64),(64),(128),(1024)                         */
+    const void  *wfront;               /* conv2, conv3, conv4 packed bf16, one 16 KB slot each          */
+    const void  *w5stream;             /* conv5: 16 packed blocks of 128 channels x 64 K, (chunk, k-block) order */
+} al3d_pass1_weights;
+
+/* First half of PointNetInstanceSeg.forward (tools/static_model.py:279-284): conv1..conv5 (+BN+ReLU) and the
+ * max over the n points of each object -> out (bs,1024), which must be zero-filled by the caller.
+ * Specialised, faster variant of al3d_chain_maxpool_bf16 for the segmentation widths (tile pairs, N = 256). */
+int al3d_seg_pass1_bf16(const al3d_pass1_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
+                        int bs, int n, float *out, void *stream);
+
 typedef struct al3d_pass2_weights {
     int32_t c_in;
     int32_t reserved;

@@ -62,7 +62,7 @@ def test_chain_maxpool_trunks(kind, block, table, C, n, bs):
     assert torch.equal(got, got2)
 
 
-@pytest.mark.parametrize("C,n,bs", [(3, 4096, 2), (4, 5120, 2), (3, 1000, 3), (3, 77, 40)])
+@pytest.mark.parametrize("C,n,bs", [(3, 4096, 2), (4, 5120, 2), (3, 1000, 3), (3, 77, 40), (3, 300, 310)])
 def test_seg_bf16_against_numerics_model(C, n, bs):
     kind = "dynamic" if C == 4 else "static_one"
     sd = synth.random_state_dict(kind, seed=6)
@@ -70,9 +70,11 @@ def test_seg_bf16_against_numerics_model(C, n, bs):
     torch.manual_seed(1)
     x = (torch.randn(bs, n, C, device=DEV) * torch.tensor([2.0, 2.0, 0.7, 0.2][:C], device=DEV)).transpose(2, 1)
     pack = eb.pack_seg(fw, C)
-    g = eb.chain_maxpool(pack.pass1, x)
+    g = eb.chain_maxpool(pack.pass1, x)                     # generic chain kernel on the segmentation widths
     emu_g = emulate_chain_bf16(fw, ["conv1", "conv2", "conv3", "conv4", "conv5"], x)
     assert rel_err(g.cpu(), emu_g.cpu()) < 2e-3
+    g1 = eb.seg_pass1(pack, x)                              # specialised tile-pair kernel
+    assert rel_err(g1.cpu(), emu_g.cpu()) < 2e-3, rel_err(g1.cpu(), emu_g.cpu())
     logits, mask = eb.seg_forward(pack, fw, x)
     emu = emulate_seg_bf16(fw, x)
     assert rel_err(logits.cpu(), emu.cpu()) < 5e-3, rel_err(logits.cpu(), emu.cpu())
