@@ -476,18 +476,30 @@ struct Pass2Params {
     do { if (p.dbg && blockIdx.x == 0 && it_local < 4 && ts_i < 64)                            \
              p.dbg[((role) * 4 + it_local) * 64 + ts_i++] = clock64(); } while (0)
 
-constexpr int kP2Stages = 13;
+constexpr int kP2Stages = 3;
 constexpr int kP2Blocks = 31;
+constexpr int kP2ResidentBytes = 163840;
 constexpr uint32_t kColD2 = 0, kColD1 = 256, kColA2 = 448, kColA1 = 480, kColD3 = 256, kColD4 = 384;
 struct Pass2Smem {
+    uint8_t wres[kP2ResidentBytes];    // weight blocks kept for the whole kernel (see p2_resident_off)
     uint8_t wring[kP2Stages][kStageBytes];
-    float w1_w[64 * 8], w1_b[64], b2[64], gb[512], bd2[256], bd3[128], bd4[128], w5[256], b5[2];
-    float lpart[2 * kTile];            // logits partial sums of the upper column half
+    float w1_w[64 * 8], w1_b[64], b2[64], gb[2][512], bd2[256], bd3[128], bd4[128], w5[256], b5[2];
+    float lpart[2][2 * kTile];         // logits partial sums of the upper column half (double-buffered by tile parity)
     uint64_t w_full[kP2Stages], w_empty[kP2Stages];
+    uint64_t res_full;
     uint64_t act_ready, acc_ready;
     uint64_t d1_full[3], d1_act[3];
     uint32_t tmem_base;
 };
+
+// Weight blocks that stay resident in shared memory: every CTA would otherwise re-read all 424 KB of weights
+// from L2 for each 128-point tile, and the chip-wide L2 -> SM throughput (~41 B/cycle/SM measured) is what
+// bounds the kernel.  Resident: conv2, dconv1 chunks 0-2, dconv2 partial 0 (the tile's start-up) and all of
+// dconv3 / dconv4 (the serial tail).  Returns the byte offset in Pass2Smem::wres, or -1 for a streamed block.
+__host__ __device__ constexpr int p2_resident_off(int blk)
+{
+    return blk <= 3 ? blk * 8192 : (blk <= 5 ? 32768 + (blk - 4) * 16384 : (blk >= 25 ? 65536 + (blk - 25) * 16384 : -1));
+}
 
 // bytes of weight block `blk` of the per-tile stream (64-row blocks are 8 KB, 128-row blocks 16 KB)
 __device__ __forceinline__ uint32_t p2_block_bytes(int blk)
@@ -533,6 +545,7 @@ seg_pass2_kernel(const Pass2Params p)
     if (threadIdx.x < 2) s.b5[threadIdx.x] = p.b5[threadIdx.x];
     if (threadIdx.x == 0) {
         for (int i = 0; i < kP2Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+        mbar_init(&s.res_full, 1);
         mbar_init(&s.act_ready, kEpiThreads);
         mbar_init(&s.acc_ready, 1);
         for (int i = 0; i < 3; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kEpiThreads); }
@@ -547,11 +560,16 @@ seg_pass2_kernel(const Pass2Params p)
     if (warp == 0) {
         // ------------------------------------------------------------ weight producer
         if (lane == 0) {
+            mbar_arrive_expect_tx(&s.res_full, kP2ResidentBytes);
+            for (int blk = 0; blk < kP2Blocks; ++blk)
+                if (p2_resident_off(blk) >= 0)
+                    bulk_g2s(s.wres + p2_resident_off(blk), p.wstream + (size_t)blk * kStageBytes, p2_block_bytes(blk), &s.res_full);
             int stage = 0; uint32_t phase = 0;
             int it_local = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
                 int ts_i = 0;
                 for (int blk = 0; blk < kP2Blocks; ++blk) {
+                    if (p2_resident_off(blk) >= 0) continue;
                     if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0xA100 + stage)) goto done;
                     AL3D_TS(2);
                     const uint32_t bytes = p2_block_bytes(blk);
@@ -566,80 +584,90 @@ seg_pass2_kernel(const Pass2Params p)
         if (lane == 0) {
             int stage = 0; uint32_t wphase = 0, act_phase = 0, d1a_phase[3] = {0, 0, 0};
             const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128);
-#define P2_NEXT_W(code)                                                          \
-            if (!mbar_wait(&s.w_full[stage], wphase, code + stage)) goto done;   \
-            AL3D_TS(0);                                                          \
-            tc_fence_after();
-#define P2_REL_W()                                                               \
-            mma_commit(&s.w_empty[stage]);                                       \
-            if (++stage == kP2Stages) { stage = 0; wphase ^= 1; }
+            // weight block `blk` of the tile: resident blocks have a fixed address, streamed ones come from the ring
+#define P2_NEXT_W(blk)                                                                   \
+            uint32_t wb_;                                                                \
+            if (p2_resident_off(blk) >= 0) wb_ = smem_u32(s.wres) + p2_resident_off(blk);  \
+            else {                                                                       \
+                if (!mbar_wait(&s.w_full[stage], wphase, 0xA300 + (blk))) goto done;     \
+                tc_fence_after();                                                        \
+                wb_ = smem_u32(s.wring[stage]);                                          \
+            }                                                                            \
+            AL3D_TS(0);
+#define P2_REL_W(blk)                                                                    \
+            if (p2_resident_off(blk) < 0) {                                              \
+                mma_commit(&s.w_empty[stage]);                                           \
+                if (++stage == kP2Stages) { stage = 0; wphase ^= 1; }                    \
+            }
 #define P2_WAIT_ACT(code)                                                        \
             if (!mbar_wait(&s.act_ready, act_phase, code)) goto done;            \
             AL3D_TS(0);                                                          \
             act_phase ^= 1; tc_fence_after();
+            if (!mbar_wait(&s.res_full, 0, 0xA2FF)) goto done;
+            tc_fence_after();
             int it_local = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
                 int ts_i = 0;
                 AL3D_TS(0);
-                // conv2: A1 (TMEM) x W2 -> D1b[2]
+                // conv2: A1 (TMEM) x W2 -> D1b[2]                                   (block 0)
                 P2_WAIT_ACT(0xA200)
-                P2_NEXT_W(0xA300)
-                mma_ts_k64(tmem + kColD1 + 128, tmem + kColA1, tmem + kColA1 + 8, tmem + kColA1 + 16, tmem + kColA1 + 24,
-                           smem_u32(s.wring[stage]), 64, id64, false);
-                P2_REL_W()
+                {
+                    P2_NEXT_W(0)
+                    mma_ts_k64(tmem + kColD1 + 128, tmem + kColA1, tmem + kColA1 + 8, tmem + kColA1 + 16, tmem + kColA1 + 24, wb_, 64, id64, false);
+                    P2_REL_W(0)
+                }
                 mma_commit(&s.acc_ready);
-                // dconv1 chunks 0..2: A2 x Wd1[chunk] -> D1b[j]
+                // dconv1 chunks 0..2: A2 x Wd1[chunk] -> D1b[j]                     (blocks 1..3)
                 P2_WAIT_ACT(0xA201)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    P2_NEXT_W(0xA310)
-                    mma_ts_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24,
-                               smem_u32(s.wring[stage]), 64, id64, false);
-                    P2_REL_W()
+                    P2_NEXT_W(1 + j)
+                    mma_ts_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, wb_, 64, id64, false);
+                    P2_REL_W(1 + j)
                     mma_commit(&s.d1_full[j]);
                 }
 #pragma unroll
                 for (int kc = 0; kc < 8; ++kc) {
                     const int j = kc % 3;
+                    const int blk0 = kc < 5 ? 4 + 3 * kc : 19 + 2 * (kc - 5);       // first block of this group
                     if (!mbar_wait(&s.d1_act[j], d1a_phase[j], 0xA400 + kc)) goto done;
                     AL3D_TS(0);
                     d1a_phase[j] ^= 1; tc_fence_after();
                     const uint32_t a = tmem + kColD1 + j * 64;        // bf16 image of chunk kc (in place)
 #pragma unroll
                     for (int nc = 0; nc < 2; ++nc) {
-                        P2_NEXT_W(0xA320)
-                        mma_ts_k64(tmem + kColD2 + nc * 128, a, a + 8, a + 32, a + 40, smem_u32(s.wring[stage]), 128, id128, kc > 0);
-                        P2_REL_W()
+                        P2_NEXT_W(blk0 + nc)
+                        mma_ts_k64(tmem + kColD2 + nc * 128, a, a + 8, a + 32, a + 40, wb_, 128, id128, kc > 0);
+                        P2_REL_W(blk0 + nc)
                     }
                     if (kc + 3 < 8) {
                         // the MMA pipe executes in issue order, so this overwrite of D1b[j] happens after the
                         // partial sums above have consumed it
-                        P2_NEXT_W(0xA330)
-                        mma_ts_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24,
-                                   smem_u32(s.wring[stage]), 64, id64, false);
-                        P2_REL_W()
+                        P2_NEXT_W(blk0 + 2)
+                        mma_ts_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, wb_, 64, id64, false);
+                        P2_REL_W(blk0 + 2)
                         mma_commit(&s.d1_full[j]);
                     }
                 }
                 mma_commit(&s.acc_ready);                                  // dconv2 accumulator complete
-                // dconv3: A3 x Wd3 -> D3
+                // dconv3: A3 x Wd3 -> D3                                            (blocks 25..28)
                 P2_WAIT_ACT(0xA202)
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb) {
                     const uint32_t a = tmem + kColD2 + (kb >> 1) * 128 + (kb & 1) * 32;
-                    P2_NEXT_W(0xA340)
-                    mma_ts_k64(tmem + kColD3, a, a + 8, a + 16, a + 24, smem_u32(s.wring[stage]), 128, id128, kb > 0);
-                    P2_REL_W()
+                    P2_NEXT_W(25 + kb)
+                    mma_ts_k64(tmem + kColD3, a, a + 8, a + 16, a + 24, wb_, 128, id128, kb > 0);
+                    P2_REL_W(25 + kb)
                 }
                 mma_commit(&s.acc_ready);
-                // dconv4: A4 x Wd4 -> D4
+                // dconv4: A4 x Wd4 -> D4                                            (blocks 29, 30)
                 P2_WAIT_ACT(0xA203)
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
                     const uint32_t a = tmem + kColD3 + kb * 64;
-                    P2_NEXT_W(0xA350)
-                    mma_ts_k64(tmem + kColD4, a, a + 8, a + 16, a + 24, smem_u32(s.wring[stage]), 128, id128, kb > 0);
-                    P2_REL_W()
+                    P2_NEXT_W(29 + kb)
+                    mma_ts_k64(tmem + kColD4, a, a + 8, a + 16, a + 24, wb_, 128, id128, kb > 0);
+                    P2_REL_W(29 + kb)
                 }
                 mma_commit(&s.acc_ready);
             }
@@ -654,7 +682,6 @@ seg_pass2_kernel(const Pass2Params p)
         const uint32_t tl = tmem + lane_addr;
         const int etid = threadIdx.x - 64;
         uint32_t acc_phase = 0, d1f_phase[3] = {0, 0, 0};
-        int cur_obj = -1;
         int it_local = 0;
         const bool ts_on = (threadIdx.x == 64);
 #define AL3D_TSE() do { if (ts_on) AL3D_TS(1); } while (0)
@@ -679,12 +706,11 @@ seg_pass2_kernel(const Pass2Params p)
             const int pidx_raw = t * kTile + row;
             const bool valid = pidx_raw < p.n;
             const int pidx = valid ? pidx_raw : p.n - 1;
-            if (b != cur_obj) {
-                // every epilogue thread is past the previous item's dconv1 epilogues (the only readers of s.gb)
+            const int par = it_local & 1;
+            if (it_local == 0) {
+                // first tile of this CTA: load its per-object dconv1 bias; later tiles find it prefetched (below)
+                for (int i = etid; i < 512; i += kEpiThreads) s.gb[0][i] = __ldg(p.gbias + (int64_t)b * 512 + i);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                for (int i = etid; i < 512; i += kEpiThreads) s.gb[i] = __ldg(p.gbias + (int64_t)b * 512 + i);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                cur_obj = b;
             }
             // ---- conv1 on CUDA cores: this thread's 32 channels -> 16 packed words -> A1
             {
@@ -711,6 +737,12 @@ seg_pass2_kernel(const Pass2Params p)
                 AL3D_TSE();
             }
             load_x(item + gridDim.x, xv);                              // prefetch the next tile's point
+            if (item + (int)gridDim.x < p.n_items) {
+                // ... and its per-object bias into the other buffer: nobody reads gb[par ^ 1] during this tile,
+                // and the bar.sync of the logits epilogue below orders these writes before the next tile's reads
+                const int nb = (item + (int)gridDim.x) / p.tiles_per_obj;
+                for (int i = etid; i < 512; i += kEpiThreads) s.gb[par ^ 1][i] = __ldg(p.gbias + (int64_t)nb * 512 + i);
+            }
             // ---- conv2 epilogue: D1b[2] -> A2
             if (!mbar_wait(&s.acc_ready, acc_phase, 0xB100)) goto done;
             AL3D_TSE();
@@ -735,7 +767,7 @@ seg_pass2_kernel(const Pass2Params p)
                 const uint32_t ta = tl + kColD1 + j * 64 + half * 32;
                 tmem_ld32(ta, v);
                 tmem_ld_wait();
-                pack_act32(v, s.gb + kc * 64 + half * 32, o);
+                pack_act32(v, s.gb[par] + kc * 64 + half * 32, o);
                 tmem_st16(ta, o);
                 P2_PUBLISH(&s.d1_act[j]);
                 AL3D_TSE();
@@ -809,16 +841,15 @@ seg_pass2_kernel(const Pass2Params p)
                     a = fmaxf(__uint_as_float(v1[i + 3]) + bb1.w, 0.f); l0b = fmaf(a, wa1.w, l0b); l1b = fmaf(a, wb1.w, l1b);
                 }
                 const float l0 = l0a + l0b, l1 = l1a + l1b;
-                if (half == 1) { s.lpart[row] = l0; s.lpart[kTile + row] = l1; }
+                if (half == 1) { s.lpart[par][row] = l0; s.lpart[par][kTile + row] = l1; }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (half == 0 && valid) {
-                    const float f0 = (s.b5[0] + l0) + s.lpart[row];
-                    const float f1 = (s.b5[1] + l1) + s.lpart[kTile + row];
+                    const float f0 = (s.b5[0] + l0) + s.lpart[par][row];
+                    const float f1 = (s.b5[1] + l1) + s.lpart[par][kTile + row];
                     const int64_t o = (int64_t)b * p.n + pidx;
                     *reinterpret_cast<float2 *>(p.logits + o * 2) = make_float2(f0, f1);
                     p.mask[o] = (f0 < f1) ? 1 : 0;
                 }
-                asm volatile("bar.sync 2, 256;" ::: "memory");     // lpart may be rewritten by the next item
                 AL3D_TSE();
             }
         }
