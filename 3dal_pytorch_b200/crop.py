@@ -59,6 +59,105 @@ def _check_overflow(flag, what):
         raise OverflowError("crop %s: %s (code %d)" % (what, names.get(code, "?"), code))
 
 
+class CropPlan:
+    """Device-resident state of a batch crop: inputs uploaded, scratch allocated.  ``run()`` only launches the
+    kernels (grid build -> hits -> scan -> fill), so it can be timed / replayed without host work."""
+
+    def __init__(self, points, boxes, poses=None, device="cuda", want_xyz=True, hit_cap=None):
+        lib = _lib.lib()
+        dev = torch.device(device)
+        self.dev, self.want_xyz = dev, want_xyz
+        F = self.F = len(points)
+        pts_t = [torch.as_tensor(p, dtype=torch.float32).to(dev) for p in points]
+        self.pts_all = torch.cat([p[:, :3].contiguous() for p in pts_t], 0) if F else torch.zeros((0, 3), device=dev)
+        n_pts = [int(p.shape[0]) for p in pts_t]
+        pt_off = np.concatenate([[0], np.cumsum(n_pts)]).astype(np.int64)
+        nb = [int(np.asarray(b).reshape(-1, 7).shape[0]) for b in boxes]
+        self.box_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+        TB = self.TB = int(self.box_off[-1])
+        if TB:
+            planes, aabb = box_planes_host(np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 7) for b in boxes], 0))
+        else:
+            planes, aabb = np.zeros((0, 6, 4), np.float32), np.zeros((0, 6), np.float32)
+        self.max_boxes = max(1, max(nb) if nb else 1)
+        CH = lib.al3d_crop_chunk_points()
+        chunks, frame_chunk_off = [], [0]
+        for f in range(F):
+            for k, first in enumerate(range(0, n_pts[f], CH)):
+                chunks.append((f, first, min(CH, n_pts[f] - first), k))
+            frame_chunk_off.append(len(chunks))
+        self.n_chunks = len(chunks)
+        self.hit_cap = int(hit_cap or 1024)
+        self.cell_cap = 64 * self.max_boxes + GRID * GRID
+        i32 = lambda *s: torch.empty(s, device=dev, dtype=torch.int32)
+        self.d_planes = torch.from_numpy(planes).to(dev)
+        self.d_aabb = torch.from_numpy(aabb).to(dev)
+        self.d_pt_off = torch.from_numpy(pt_off).to(dev)
+        self.d_box_off = torch.from_numpy(self.box_off).to(dev)
+        self.d_chunks = torch.tensor(chunks, dtype=torch.int32, device=dev).reshape(-1, 4)
+        self.d_fco = torch.tensor(frame_chunk_off, dtype=torch.int64, device=dev)
+        self.meta = torch.empty((max(F, 1), 4), device=dev, dtype=torch.float32)
+        self.cell_start = i32(max(F, 1), GRID * GRID + 1)
+        self.cell_boxes = i32(max(F, 1), self.cell_cap)
+        self.overflow = torch.zeros((1,), device=dev, dtype=torch.int32)
+        self.hits = torch.empty((max(self.n_chunks, 1), self.hit_cap, 2), device=dev, dtype=torch.int32)
+        self.n_hits = i32(max(self.n_chunks, 1))
+        self.cbc = i32(max(self.n_chunks, 1), self.max_boxes)
+        self.box_total = i32(max(TB, 1))
+        self.offsets = torch.zeros((TB + 1,), device=dev, dtype=torch.int64)
+        self.d_poses = None
+        if poses is not None:
+            self.d_poses = torch.from_numpy(np.ascontiguousarray(
+                np.stack([np.asarray(P, dtype=np.float64).reshape(4, 4) for P in poses]) if F else np.zeros((0, 4, 4)))).to(dev)
+        self.capacity = None
+        self.out_idx = self.out_xyz = self.out_glob = None
+        # algorithmic bytes (SURVEY 8d): every point read once (12 B) + plane equations; the writes are added per run
+        self.read_bytes = int(self.pts_all.shape[0]) * 12 + TB * 96
+
+    def _alloc_outputs(self, capacity):
+        dev = self.dev
+        self.capacity = int(capacity)
+        c = max(self.capacity, 1)
+        self.out_idx = torch.empty((c,), device=dev, dtype=torch.int32)[: self.capacity]
+        self.out_xyz = torch.empty((c, 3), device=dev, dtype=torch.float32)[: self.capacity] if self.want_xyz else None
+        self.out_glob = torch.empty((c, 3), device=dev, dtype=torch.float64)[: self.capacity] if self.d_poses is not None else None
+
+    def count(self):
+        """grid build + hits + scan (everything that does not need the output size)."""
+        lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
+        _lib.check(lib.al3d_crop_build_grid(p(self.d_aabb), p(self.d_box_off), self.F, GRID, p(self.meta), p(self.cell_start),
+                                            p(self.cell_boxes), self.cell_cap, p(self.overflow), st), "crop_build_grid")
+        _lib.check(lib.al3d_crop_hits(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_planes), p(self.d_box_off), GRID, p(self.meta),
+                                      p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.d_chunks), self.n_chunks,
+                                      p(self.hits), self.hit_cap, p(self.n_hits), p(self.cbc), self.max_boxes, p(self.overflow), st),
+                   "crop_hits")
+        _lib.check(lib.al3d_crop_scan(p(self.d_box_off), p(self.d_fco), self.F, self.TB, p(self.cbc), self.max_boxes,
+                                      p(self.box_total), p(self.offsets), st), "crop_scan")
+
+    def fill(self):
+        lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr() if t is not None else None)
+        _lib.check(lib.al3d_crop_fill(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_box_off), p(self.d_chunks), self.n_chunks,
+                                      p(self.hits), self.hit_cap, p(self.n_hits), p(self.cbc), self.max_boxes, p(self.offsets),
+                                      p(self.d_poses), self.capacity, p(self.out_idx), p(self.out_xyz), p(self.out_glob),
+                                      p(self.overflow), st), "crop_fill")
+
+    def run(self, capacity=None):
+        """One full crop.  Without ``capacity`` (and without a previous run) the total is read back once to size the
+        outputs; afterwards the same buffers are reused and nothing synchronises with the host."""
+        self.count()
+        if capacity is not None and self.capacity != capacity:
+            self._alloc_outputs(capacity)
+        if self.capacity is None:
+            _check_overflow(self.overflow, "hits")
+            self._alloc_outputs(int(self.offsets[-1].item()))
+        self.fill()
+        return self.result()
+
+    def result(self):
+        return {"indices": self.out_idx, "offsets": self.offsets, "box_off": self.box_off, "xyz": self.out_xyz,
+                "xyz_global": self.out_glob, "overflow": self.overflow, "read_bytes": self.read_bytes}
+
+
 def crop_frames(points, boxes, poses=None, device="cuda", want_xyz=True, hit_cap=None, capacity=None):
     """points: list of (N_f, >=3) f32 arrays / CUDA tensors; boxes: list of (B_f, 7) f32 Waymo-convention
     arrays; poses: optional list of 4x4 f64 vehicle->global matrices.
@@ -68,75 +167,7 @@ def crop_frames(points, boxes, poses=None, device="cuda", want_xyz=True, hit_cap
                  box_off (F+1,) i64 host; xyz (T,3) f32; xyz_global (T,3) f64 when poses are given).
     With ``capacity`` set no host synchronisation happens (the output is over-allocated); otherwise the total
     count is read back once to size the outputs exactly."""
-    lib = _lib.lib()
-    dev = torch.device(device)
-    F = len(points)
-    pts_t = [torch.as_tensor(p, dtype=torch.float32).to(dev) for p in points]
-    stride = 3
-    pts_all = torch.cat([p[:, :3].contiguous() for p in pts_t], 0) if F else torch.zeros((0, 3), device=dev)
-    n_pts = [int(p.shape[0]) for p in pts_t]
-    pt_off = np.concatenate([[0], np.cumsum(n_pts)]).astype(np.int64)
-    nb = [int(np.asarray(b).reshape(-1, 7).shape[0]) for b in boxes]
-    box_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
-    TB = int(box_off[-1])
-    if TB:
-        planes, aabb = box_planes_host(np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 7) for b in boxes], 0))
-    else:
-        planes, aabb = np.zeros((0, 6, 4), np.float32), np.zeros((0, 6), np.float32)
-    max_boxes = max(1, max(nb) if nb else 1)
-    CH = lib.al3d_crop_chunk_points()
-    chunks, frame_chunk_off = [], [0]
-    for f in range(F):
-        k = 0
-        for first in range(0, n_pts[f], CH):
-            chunks.append((f, first, min(CH, n_pts[f] - first), k))
-            k += 1
-        frame_chunk_off.append(len(chunks))
-    n_chunks = len(chunks)
-    hit_cap = int(hit_cap or 1024)
-    cell_cap = 64 * max_boxes + GRID * GRID
-
-    i32 = lambda *s: torch.empty(s, device=dev, dtype=torch.int32)
-    d_planes = torch.from_numpy(planes).to(dev)
-    d_aabb = torch.from_numpy(aabb).to(dev)
-    d_pt_off = torch.from_numpy(pt_off).to(dev)
-    d_box_off = torch.from_numpy(box_off).to(dev)
-    d_chunks = torch.tensor(chunks, dtype=torch.int32, device=dev).reshape(-1, 4)
-    d_fco = torch.tensor(frame_chunk_off, dtype=torch.int64, device=dev)
-    meta = torch.empty((max(F, 1), 4), device=dev, dtype=torch.float32)
-    cell_start = i32(max(F, 1), GRID * GRID + 1)
-    cell_boxes = i32(max(F, 1), cell_cap)
-    overflow = torch.zeros((1,), device=dev, dtype=torch.int32)
-    hits = torch.empty((max(n_chunks, 1), hit_cap, 2), device=dev, dtype=torch.int32)
-    n_hits = i32(max(n_chunks, 1))
-    cbc = i32(max(n_chunks, 1), max_boxes)
-    box_total = i32(max(TB, 1))
-    offsets = torch.zeros((TB + 1,), device=dev, dtype=torch.int64)
-    st = ops._stream()
-    p = lambda t: t.data_ptr()
-
-    _lib.check(lib.al3d_crop_build_grid(p(d_aabb), p(d_box_off), F, GRID, p(meta), p(cell_start), p(cell_boxes), cell_cap,
-                                        p(overflow), st), "crop_build_grid")
-    _lib.check(lib.al3d_crop_hits(p(pts_all), stride, p(d_pt_off), p(d_planes), p(d_box_off), GRID, p(meta), p(cell_start),
-                                  p(cell_boxes), cell_cap, p(d_chunks), n_chunks, p(hits), hit_cap, p(n_hits), p(cbc),
-                                  max_boxes, p(overflow), st), "crop_hits")
-    _lib.check(lib.al3d_crop_scan(p(d_box_off), p(d_fco), F, TB, p(cbc), max_boxes, p(box_total), p(offsets), st), "crop_scan")
-    if capacity is None:
-        _check_overflow(overflow, "hits")
-        capacity = int(offsets[-1].item())                    # the one host read: sizes the outputs exactly
-    out_idx = i32(max(capacity, 1))[:capacity]
-    out_xyz = torch.empty((max(capacity, 1), 3), device=dev, dtype=torch.float32)[:capacity] if want_xyz else None
-    d_poses, out_glob = None, None
-    if poses is not None:
-        d_poses = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(P, dtype=np.float64).reshape(4, 4) for P in poses])
-                                                        if F else np.zeros((0, 4, 4)))).to(dev)
-        out_glob = torch.empty((max(capacity, 1), 3), device=dev, dtype=torch.float64)[:capacity]
-    _lib.check(lib.al3d_crop_fill(p(pts_all), stride, p(d_pt_off), p(d_box_off), p(d_chunks), n_chunks, p(hits), hit_cap,
-                                  p(n_hits), p(cbc), max_boxes, p(offsets), p(d_poses) if d_poses is not None else None,
-                                  capacity, p(out_idx), p(out_xyz) if out_xyz is not None else None,
-                                  p(out_glob) if out_glob is not None else None, p(overflow), st), "crop_fill")
-    return {"indices": out_idx, "offsets": offsets, "box_off": box_off, "xyz": out_xyz, "xyz_global": out_glob,
-            "overflow": overflow, "algorithmic_bytes": int(pts_all.shape[0]) * 12 + TB * 96}
+    return CropPlan(points, boxes, poses, device=device, want_xyz=want_xyz, hit_cap=hit_cap).run(capacity)
 
 
 def points_in_rbbox(points, rbbox, z_axis=2, origin=(0.5, 0.5, 0.5), device="cuda"):

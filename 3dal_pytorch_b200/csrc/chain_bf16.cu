@@ -883,6 +883,7 @@ struct Pass1Params {
     const uint8_t *w5stream;           // 16 blocks of 128 channels x 64 K, order (chunk, k-block)
     float *out;                        // (bs, 1024) zero-initialised
     int splits, n_items;
+    long long *dbg;                    // optional clock64 timeline (al3d_set_debug_buffer), else NULL
 };
 
 constexpr int kP1Stages = 7;
@@ -977,10 +978,13 @@ seg_pass1_kernel(const Pass1Params p)
             const uint32_t a_out4 = smem_u32(s.out4);
             if (!mbar_wait(&s.res_full, 0, 0x9200)) goto done;
             tc_fence_after();
+            int it_local = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int sp_i = item % p.splits;
                 const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
-                for (int t = t0; t < t1; t += 2) {
+                for (int t = t0; t < t1; t += 2, ++it_local) {
+                    int ts_i = 0;
+                    AL3D_TS(0);
                     // front layers, the two tiles interleaved: while the epilogue converts X, the tensor core works on Y
 #pragma unroll
                     for (int l = 0; l < 3; ++l) {
@@ -988,6 +992,7 @@ seg_pass1_kernel(const Pass1Params p)
                         for (int q = 0; q < 2; ++q) {
                             const uint32_t base = tmem + q * 256;
                             if (!mbar_wait(&s.act[q], act_phase[q], 0x9300 + l * 2 + q)) goto done;
+                            AL3D_TS(0);
                             act_phase[q] ^= 1; tc_fence_after();
                             if (l == 0)      mma_ts_k64(base + 32, base, base + 8, base + 16, base + 24, wf0, 64, id64, false);
                             else if (l == 1) mma_ts_k64(base + 128, base + 96, base + 104, base + 112, base + 120, wf1, 64, id64, false);
@@ -997,14 +1002,17 @@ seg_pass1_kernel(const Pass1Params p)
                     }
                     // conv5, transposed, N = 256 points (both tiles): D^T[128 channels x 256 points]
                     if (!mbar_wait(&s.out4_ready, o4_phase, 0x9400)) goto done;
+                    AL3D_TS(0);
                     o4_phase ^= 1; tc_fence_after();
 #pragma unroll 1
                     for (int cc = 0; cc < 8; ++cc) {
                         const int b = cc & 1;
                         if (!mbar_wait(&s.last_empty[b], le_phase[b] ^ 1, 0x9500 + b)) goto done;
+                        AL3D_TS(0);
                         le_phase[b] ^= 1; tc_fence_after();
                         for (int kb = 0; kb < 2; ++kb) {
                             if (!mbar_wait(&s.w_full[stage], wphase, 0x9600 + stage)) goto done;
+                            AL3D_TS(0);
                             tc_fence_after();
                             mma_block_k64(tmem + b * 256, smem_u32(s.wring[stage]), 128, a_out4 + kb * 8 * 4096, 256, id256, kb > 0);
                             mma_commit(&s.w_empty[stage]);
@@ -1020,28 +1028,58 @@ seg_pass1_kernel(const Pass1Params p)
         const int row = epi_row(), half = epi_half();
         const uint32_t tl = tmem + ((uint32_t)(row & ~31) << 16);
         uint32_t acc_phase[2] = {0, 0}, lf_phase[2] = {0, 0};
+        int it_local = 0;
+        const bool ts_on = (threadIdx.x == 64);
+        float xq[2][8];
+        auto load_pair = [&](int ob, int t, int t1) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int tq = (t + q < t1) ? t + q : t1 - 1;
+                int pidx = tq * kTile + row;
+                if (pidx > p.n - 1) pidx = p.n - 1;
+                const float *px = p.x + (int64_t)ob * p.sb + (int64_t)pidx * p.sp;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) xq[q][c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+            }
+        };
+        if ((int)blockIdx.x < p.n_items) {
+            const int sp0 = blockIdx.x % p.splits;
+            const int f0 = (int)((int64_t)tiles_per_obj * sp0 / p.splits), f1 = (int)((int64_t)tiles_per_obj * (sp0 + 1) / p.splits);
+            if (f0 < f1) load_pair(blockIdx.x / p.splits, f0, f1);
+        }
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int b = item / p.splits, sp_i = item % p.splits;
             const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
             float rmax[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
-            for (int t = t0; t < t1; t += 2) {
-                // ---- conv1 of both tiles (an odd tail pair repeats its tile: the max is idempotent under duplicates)
+            for (int t = t0; t < t1; t += 2, ++it_local) {
+                int ts_i = 0;
+                AL3D_TSE();
+                // ---- conv1 of both tiles (an odd tail pair repeats its tile: the max is idempotent under duplicates).
+                //      The input points were prefetched during the previous pair's conv5 phase.
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const int tq = (t + q < t1) ? t + q : t1 - 1;
-                    int pidx = tq * kTile + row;
-                    if (pidx > p.n - 1) pidx = p.n - 1;
-                    const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
-                    float xv[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
                     uint32_t o[16];
-                    conv1_pack32(xv, p.c_in, s.w1_w, s.w1_b, half * 32, o);
+                    conv1_pack32(xq[q], p.c_in, s.w1_w, s.w1_b, half * 32, o);
                     tmem_st16(tl + q * 256 + half * 16, o);
                     tmem_st_wait(); tc_fence_before();
                     mbar_arrive(&s.act[q]);
+                    AL3D_TSE();
+                }
+                // prefetch the next pair of this item (or the first pair of the CTA's next item)
+                {
+                    int nb = b, nt = t + 2, nt1 = t1;
+                    if (nt >= t1) {
+                        const int nitem = item + gridDim.x;
+                        if (nitem < p.n_items) {
+                            const int nsp = nitem % p.splits;
+                            nb = nitem / p.splits;
+                            nt = (int)((int64_t)tiles_per_obj * nsp / p.splits);
+                            nt1 = (int)((int64_t)tiles_per_obj * (nsp + 1) / p.splits);
+                        } else nt = -1;
+                    }
+                    if (nt >= 0 && nt < nt1) load_pair(nb, nt, nt1);
                 }
                 // ---- conv2, conv3 epilogues: accumulator -> packed operand of the next layer
 #pragma unroll
@@ -1049,6 +1087,7 @@ seg_pass1_kernel(const Pass1Params p)
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8100 + l * 2 + q)) goto done;
+                        AL3D_TSE();
                         acc_phase[q] ^= 1; tc_fence_after();
                         uint32_t v[32], o[16];
                         const uint32_t src = tl + q * 256 + (l == 0 ? 32 : 128) + half * 32;
@@ -1059,12 +1098,14 @@ seg_pass1_kernel(const Pass1Params p)
                         tmem_st16(dst, o);
                         tmem_st_wait(); tc_fence_before();
                         mbar_arrive(&s.act[q]);
+                        AL3D_TSE();
                     }
                 }
                 // ---- conv4 epilogue: 64 of the 128 channels of this row -> shared-memory operand of conv5
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8200 + q)) goto done;
+                    AL3D_TSE();
                     acc_phase[q] ^= 1; tc_fence_after();
                     uint32_t v0[32], v1[32], o0[16], o1[16];
                     const uint32_t src = tl + q * 256 + half * 64;
@@ -1082,12 +1123,14 @@ seg_pass1_kernel(const Pass1Params p)
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&s.out4_ready);
+                    AL3D_TSE();
                 }
                 // ---- conv5: this thread owns channel (cc*128 + row) and 128 of the pair's 256 points
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
                     const int bsel = cc & 1;
                     if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0x8300 + cc)) goto done;
+                    AL3D_TSE();
                     lf_phase[bsel] ^= 1; tc_fence_after();
                     float m0 = rmax[cc], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
@@ -1111,6 +1154,7 @@ seg_pass1_kernel(const Pass1Params p)
                         }
                     }
                     rmax[cc] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    AL3D_TSE();
                 }
             }
             // ---- publish: relu(max + bias) >= 0, so integer atomicMax on the bit pattern is exact
@@ -1246,6 +1290,7 @@ extern "C" int al3d_seg_pass1_bf16(const al3d_pass1_weights *w, const float *x, 
     p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n; p.c_in = w->c_in;
     p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.b3 = w->b3; p.b4 = w->b4; p.b5 = w->b5;
     p.wfront = (const uint8_t *)w->wfront; p.w5stream = (const uint8_t *)w->w5stream; p.out = out;
+    p.dbg = g_debug_buffer ? g_debug_buffer + 3 * 4 * 64 : nullptr;      // second half of the debug buffer
     const int tiles = (n + kTile - 1) / kTile;
     const int sms = num_sms();
     int splits = 1;

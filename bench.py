@@ -73,9 +73,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def wait_first_sample(self, keep_busy, timeout=5.0):
+        """nvidia-smi takes a while to start on an 8-GPU box: keep the GPU under load (extra untimed steps)
+        until the first sample has arrived, so that the timed region is covered."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            keep_busy()
+            torch.cuda.synchronize()
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
@@ -83,7 +94,10 @@ class ClockSampler:
         self.thr.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r[1:] for r in self.rows if t_begin is None or (t_begin - 0.05 <= r[0] <= t_end + 0.1)]
+        if not rows:                      # region shorter than the sampling period: use the loaded samples around it
+            rows = [r[1:] for r in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -149,8 +163,9 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "auto-labeled objects/sec", "value": val, "unit": "objects/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "static one-box Frustum-PointNet forward + decode, %d tracks x %d pts per GPU" % (args.tracks, N_POINTS),
-                       "sample": sample},
+            "config": {"workload": "static one-box Frustum-PointNet forward + box decode, %d tracks x %d pts per GPU"
+                                   " (BASELINE.json configs[2])" % (args.tracks, N_POINTS),
+                       "tracks_per_gpu": args.tracks, "points": N_POINTS, "sample": sample},
             "cpu_baseline": {"value": val, "unit": "objects/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -230,15 +245,21 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
+    sampler.wait_first_sample(step)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_begin = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    t_end = sampler.mark()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     if os.environ.get("AL3D_CUDA_PROFILER_RANGE") == "1":
         torch.cuda.cudart().cudaProfilerStop()
     launches = lib.LAUNCHES - launches0

@@ -245,8 +245,9 @@ int al3d_umma_selftest_ts(const float *a, const void *b_kp, int N, int K, float 
  * an mbarrier wait (protocol bug) and its outputs are invalid.  Synchronises the device. */
 int al3d_tc_abort_code(int *code_host);
 
-/* Development aid: when set to a device buffer of 3*4*64 int64, CTA 0 of al3d_seg_pass2_bf16 records a
- * clock64 timeline of its first four tiles (role-major: MMA thread, epilogue thread, producer).  Pass
+/* Development aid: when set to a device buffer of 2*3*4*64 int64, CTA 0 of al3d_seg_pass2_bf16 (first half)
+ * and of al3d_seg_pass1_bf16 (second half) record a clock64 timeline of their first four tiles / tile pairs
+ * (role-major: MMA thread, epilogue thread, producer).  Pass
  * NULL to switch it off (the default).  This pointer is the only mutable global besides the error text. */
 int al3d_set_debug_buffer(void *dev_ptr);
 

@@ -24,15 +24,22 @@ data = synth.static_tracks_device(1024, seed=0, device=dev)
 pts = data["pts_pm"].transpose(2, 1)
 for _ in range(2):
     model(pts, data["init_box"], None)
-dbg = torch.zeros(3 * 4 * 64, dtype=torch.int64, device=dev)
+dbg = torch.zeros(2 * 3 * 4 * 64, dtype=torch.int64, device=dev)
 lib.check(lib.lib().al3d_set_debug_buffer(dbg.data_ptr()), "set_debug_buffer")
 model(pts, data["init_box"], None)
 torch.cuda.synchronize()
 lib.check(lib.lib().al3d_set_debug_buffer(None), "set_debug_buffer")
-d = dbg.cpu().view(3, 4, 64)
-t0 = int(d[d > 0].min())
-for role, name in enumerate(["mma", "epilogue", "producer"]):
-    for it in range(4):
-        ts = [int(v) - t0 for v in d[role, it] if v > 0]
-        print(name, "item", it, "n=%d" % len(ts), "start=%d" % (ts[0] if ts else -1), "end=%d" % (ts[-1] if ts else -1))
-        print("   deltas:", [b - a for a, b in zip(ts, ts[1:])])
+dd = dbg.cpu().view(2, 3, 4, 64)
+for k, kern in enumerate(["seg_pass2_kernel", "seg_pass1_kernel"]):
+    d = dd[k]
+    if not bool((d > 0).any()):
+        continue
+    t0 = int(d[d > 0].min())
+    print("==== " + kern)
+    for role, name in enumerate(["mma", "epilogue", "producer"]):
+        for it in range(4):
+            ts = [int(v) - t0 for v in d[role, it] if v > 0]
+            if not ts:
+                continue
+            print(name, "item", it, "n=%d" % len(ts), "start=%d" % ts[0], "end=%d" % ts[-1])
+            print("   deltas:", [b - a for a, b in zip(ts, ts[1:])])
