@@ -54,7 +54,7 @@ def box_planes_host(boxes):
 def _check_overflow(flag, what):
     code = int(flag.item())
     if code:
-        names = {1: "cell list capacity", 2: "a point lies inside more than 4 boxes", 3: "per-chunk hit capacity",
+        names = {1: "cell list capacity", 2: "a point lies inside more than 8 boxes", 3: "per-chunk hit capacity",
                  4: "output capacity"}
         raise OverflowError("crop %s: %s (code %d)" % (what, names.get(code, "?"), code))
 

@@ -25,7 +25,7 @@ namespace al3d {
 
 constexpr int kCropChunk = 2048;       // points per CTA of the hits kernel
 constexpr int kCropThreads = 256;
-constexpr int kMaxHitsPerPoint = 4;    // a point inside more boxes than this raises the overflow flag
+constexpr int kMaxHitsPerPoint = 8;    // a point inside more boxes than this raises the overflow flag
 
 struct CropGridMeta { float x0, y0, inv_x, inv_y; };
 

@@ -69,7 +69,7 @@ def test_crop_ragged_batch_and_edge_cases():
     points = [f["points"] for f in frames] + [np.zeros((0, 3), np.float32), rng.normal(0, 5, (777, 3)).astype(np.float32)]
     boxes = [crop.detector_to_waymo(f["det_boxes"]) for f in frames] + [_random_boxes(rng, 5), np.zeros((0, 7), np.float32)]
     poses = [f["pose"] for f in frames] + [np.eye(4), np.eye(4)]
-    # heavy overlap (up to 4 boxes over the same points), a NaN point and a point exactly on a face
+    # heavy overlap (several boxes over the same points), a NaN point and a point exactly on a face
     dense = rng.uniform(-1, 1, (5000, 3)).astype(np.float32)
     dense[17] = np.nan
     dense[18] = [1.0, 0.0, 0.0]
@@ -88,7 +88,7 @@ def test_crop_ragged_batch_and_edge_cases():
 def test_crop_overflow_is_reported():
     rng = np.random.default_rng(1)
     pts = rng.uniform(-0.5, 0.5, (4096, 3)).astype(np.float32)
-    boxes = np.tile(np.array([[0, 0, 0, 4, 4, 4, 0.0]], np.float32), (6, 1))      # every point inside 6 boxes
+    boxes = np.tile(np.array([[0, 0, 0, 4, 4, 4, 0.0]], np.float32), (10, 1))     # every point inside 10 boxes
     with pytest.raises(OverflowError):
         crop.crop_frames([pts], [boxes], hit_cap=8192)
 
