@@ -87,7 +87,7 @@ class CropPlan:
                 chunks.append((f, first, min(CH, n_pts[f] - first), k))
             frame_chunk_off.append(len(chunks))
         self.n_chunks = len(chunks)
-        self.hit_cap = int(hit_cap or 1024)
+        self.hit_cap = int(hit_cap or 512)          # hits per chunk of 2048 points; <= 16384
         self.cell_cap = 64 * self.max_boxes + GRID * GRID
         i32 = lambda *s: torch.empty(s, device=dev, dtype=torch.int32)
         self.d_planes = torch.from_numpy(planes).to(dev)
@@ -122,17 +122,28 @@ class CropPlan:
         self.out_xyz = torch.empty((c, 3), device=dev, dtype=torch.float32)[: self.capacity] if self.want_xyz else None
         self.out_glob = torch.empty((c, 3), device=dev, dtype=torch.float64)[: self.capacity] if self.d_poses is not None else None
 
-    def count(self):
-        """grid build + hits + scan (everything that does not need the output size)."""
+    def grid(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
         _lib.check(lib.al3d_crop_build_grid(p(self.d_aabb), p(self.d_box_off), self.F, GRID, p(self.meta), p(self.cell_start),
                                             p(self.cell_boxes), self.cell_cap, p(self.overflow), st), "crop_build_grid")
+
+    def hits_pass(self):
+        lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
         _lib.check(lib.al3d_crop_hits(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_planes), p(self.d_box_off), GRID, p(self.meta),
                                       p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.d_chunks), self.n_chunks,
                                       p(self.hits), self.hit_cap, p(self.n_hits), p(self.cbc), self.max_boxes, p(self.overflow), st),
                    "crop_hits")
+
+    def scan(self):
+        lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
         _lib.check(lib.al3d_crop_scan(p(self.d_box_off), p(self.d_fco), self.F, self.TB, p(self.cbc), self.max_boxes,
                                       p(self.box_total), p(self.offsets), st), "crop_scan")
+
+    def count(self):
+        """grid build + hits + scan (everything that does not need the output size)."""
+        self.grid()
+        self.hits_pass()
+        self.scan()
 
     def fill(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr() if t is not None else None)
@@ -184,7 +195,7 @@ def points_in_rbbox(points, rbbox, z_axis=2, origin=(0.5, 0.5, 0.5), device="cud
     try:
         res = crop_frames([pts], [rb], device=device, want_xyz=False)
     except OverflowError:
-        res = crop_frames([pts], [rb], device=device, want_xyz=False, hit_cap=8192)
+        res = crop_frames([pts], [rb], device=device, want_xyz=False, hit_cap=16384)
     _check_overflow(res["overflow"], "fill")
     mask = torch.zeros((N, B), device=res["indices"].device, dtype=torch.uint8)
     _lib.check(_lib.lib().al3d_crop_dense_mask(res["indices"].data_ptr(), res["offsets"].data_ptr(), B, mask.data_ptr(),

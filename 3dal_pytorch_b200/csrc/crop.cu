@@ -41,12 +41,14 @@ __global__ void __launch_bounds__(kCropThreads)
 crop_grid_kernel(const float *__restrict__ aabb, const int64_t *__restrict__ box_off, int G, CropGridMeta *__restrict__ meta,
                  int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_boxes, int cell_cap, int32_t *__restrict__ overflow)
 {
-    extern __shared__ int32_t s_cnt[];            // G*G counts, then a scan
+    extern __shared__ int32_t s_cnt[];            // G*G counts -> exclusive offsets; then G*G fill cursors
     __shared__ float red[4][kCropThreads / 32];
-    __shared__ int32_t s_total;
+    __shared__ int32_t s_warp[kCropThreads / 32];
     const int f = blockIdx.x;
     const int64_t b0 = box_off[f];
     const int B = (int)(box_off[f + 1] - b0);
+    const int cells = G * G;
+    int32_t *s_cur = s_cnt + cells;
     // ---- extent of the boxes of this frame
     float xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -60,6 +62,7 @@ crop_grid_kernel(const float *__restrict__ aabb, const int64_t *__restrict__ box
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) { red[0][wid] = xmin; red[1][wid] = ymin; red[2][wid] = xmax; red[3][wid] = ymax; }
+    for (int c = threadIdx.x; c < 2 * cells; c += blockDim.x) s_cnt[c] = 0;
     __syncthreads();
     for (int w = 0; w < kCropThreads / 32; ++w) {
         xmin = fminf(xmin, red[0][w]); ymin = fminf(ymin, red[1][w]);
@@ -73,37 +76,59 @@ crop_grid_kernel(const float *__restrict__ aabb, const int64_t *__restrict__ box
         m.inv_y = (float)G / fmaxf(ymax - ymin, 1e-3f) * 0.999f;
     }
     if (threadIdx.x == 0) meta[f] = m;
-    // ---- count, scan, fill: one thread per cell walks all boxes (ascending box order per cell)
-    const int cells = G * G;
+    // ---- pass 0: every box adds itself to the counters of the cells its rectangle covers (integer adds commute);
+    //      pass 1: it appends its id through a per-cell cursor; the short lists are sorted afterwards, so the
+    //      final cell -> box lists are in ascending box order whatever the order of the atomics.
     for (int pass = 0; pass < 2; ++pass) {
-        for (int c = threadIdx.x; c < cells; c += blockDim.x) {
-            const int cy = c / G, cx = c - cy * G;
-            int n = 0;
-            const int base = (pass == 1) ? s_cnt[c] : 0;
-            for (int b = 0; b < B; ++b) {
-                const float *a = aabb + (b0 + b) * 6;
-                int x0c = crop_cell(a[0], m.x0, m.inv_x, G), x1c = crop_cell(a[3], m.x0, m.inv_x, G);
-                int y0c = crop_cell(a[1], m.y0, m.inv_y, G), y1c = crop_cell(a[4], m.y0, m.inv_y, G);
-                x0c = max(x0c, 0); y0c = max(y0c, 0); x1c = min(x1c, G - 1); y1c = min(y1c, G - 1);
-                if (cx >= x0c && cx <= x1c && cy >= y0c && cy <= y1c) {
-                    if (pass == 1 && base + n < cell_cap) cell_boxes[(int64_t)f * cell_cap + base + n] = b;
-                    ++n;
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            const float *a = aabb + (b0 + b) * 6;
+            int x0c = crop_cell(a[0], m.x0, m.inv_x, G), x1c = crop_cell(a[3], m.x0, m.inv_x, G);
+            int y0c = crop_cell(a[1], m.y0, m.inv_y, G), y1c = crop_cell(a[4], m.y0, m.inv_y, G);
+            x0c = max(x0c, 0); y0c = max(y0c, 0); x1c = min(x1c, G - 1); y1c = min(y1c, G - 1);
+            for (int cy = y0c; cy <= y1c; ++cy)
+                for (int cx = x0c; cx <= x1c; ++cx) {
+                    const int c = cy * G + cx;
+                    if (pass == 0) atomicAdd(&s_cnt[c], 1);
+                    else {
+                        const int at = s_cnt[c] + atomicAdd(&s_cur[c], 1);
+                        if (at < cell_cap) cell_boxes[(int64_t)f * cell_cap + at] = b;
+                    }
                 }
-            }
-            if (pass == 0) s_cnt[c] = n;
         }
         __syncthreads();
         if (pass == 0) {
-            // exclusive scan of s_cnt (cells <= 16384): serial per 256-cell strip, then strip offsets
-            if (threadIdx.x == 0) {
-                int run = 0;
-                for (int c = 0; c < cells; ++c) { const int v = s_cnt[c]; s_cnt[c] = run; run += v; }
-                s_total = run;
-                if (run > cell_cap) atomicExch(overflow, 1);
-            }
+            // block-wide exclusive scan of the per-cell counts: contiguous strips per thread
+            const int per = (cells + kCropThreads - 1) / kCropThreads;
+            const int lo = min(threadIdx.x * per, cells), hi = min(lo + per, cells);
+            int sum = 0;
+            for (int c = lo; c < hi; ++c) sum += s_cnt[c];
+            int incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) s_warp[wid] = incl;
             __syncthreads();
+            int base = incl - sum;
+            for (int w = 0; w < wid; ++w) base += s_warp[w];
+            for (int c = lo; c < hi; ++c) { const int v = s_cnt[c]; s_cnt[c] = base; base += v; }
+            __syncthreads();
+            int total = 0;
+            for (int w = 0; w < kCropThreads / 32; ++w) total += s_warp[w];
+            if (threadIdx.x == 0) {
+                cell_start[(int64_t)f * (cells + 1) + cells] = total;
+                if (total > cell_cap) atomicExch(overflow, 1);
+            }
             for (int c = threadIdx.x; c < cells; c += blockDim.x) cell_start[(int64_t)f * (cells + 1) + c] = s_cnt[c];
-            if (threadIdx.x == 0) cell_start[(int64_t)f * (cells + 1) + cells] = s_total;
+        }
+    }
+    // ---- sort every cell's list (a handful of entries): insertion sort by one thread per cell
+    __threadfence_block();
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+        const int lo = s_cnt[c], n = min(s_cur[c], max(cell_cap - lo, 0));
+        int32_t *l = cell_boxes + (int64_t)f * cell_cap + lo;
+        for (int i = 1; i < n; ++i) {
+            const int v = l[i];
+            int j = i - 1;
+            while (j >= 0 && l[j] > v) { l[j + 1] = l[j]; --j; }
+            l[j + 1] = v;
         }
     }
 }
@@ -122,6 +147,9 @@ __device__ __forceinline__ bool crop_inside(float px, float py, float pz, const 
 
 struct CropChunk { int32_t frame; int32_t first_pt; int32_t n_pts; int32_t chunk_in_frame; };
 
+constexpr int kCropWarps = kCropThreads / 32;
+constexpr int kCropWarpPts = kCropChunk / kCropWarps;     // consecutive points owned by one warp
+
 __global__ void __launch_bounds__(kCropThreads)
 crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
                  const float *__restrict__ planes, const int64_t *__restrict__ box_off, int G,
@@ -130,9 +158,14 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                  int2 *__restrict__ hits, int hit_cap, int32_t *__restrict__ n_hits, int32_t *__restrict__ chunk_box_count,
                  int max_boxes, int32_t *__restrict__ overflow)
 {
-    extern __shared__ int32_t s_box_cnt[];             // per-box hit counters of this chunk (max_boxes)
-    __shared__ int warp_sum[kCropThreads / 32];
-    __shared__ int s_base;
+    // Each warp owns kCropWarpPts CONSECUTIVE points and walks them 32 at a time, appending its hits (in point
+    // order) to a private staging list in shared memory; one block-wide prefix over the eight warp totals then
+    // gives every warp its place in the chunk's ordered hit list.  No block barrier inside the point loop.
+    extern __shared__ int32_t s_dyn[];
+    int32_t *s_box_cnt = s_dyn;                                        // per-box hit counters (max_boxes)
+    int2 *s_stage = reinterpret_cast<int2 *>(s_dyn + ((max_boxes + 1) & ~1));   // kCropWarps x stage_cap
+    __shared__ int warp_total[kCropWarps];
+    const int stage_cap = min(hit_cap, kCropWarpPts * kMaxHitsPerPoint); // per warp (its worst case); the chunk total is capped at hit_cap
     const CropChunk ck = chunks[blockIdx.x];
     const int f = ck.frame;
     const int64_t b0 = box_off[f];
@@ -142,22 +175,24 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     const int32_t *cs = cell_start + (int64_t)f * (cells + 1);
     const int32_t *cb = cell_boxes + (int64_t)f * cell_cap;
     const float *pts = points + (pt_off[f] + ck.first_pt) * pt_stride;
+    const float4 *pl = reinterpret_cast<const float4 *>(planes) + b0 * 6;
     int2 *my_hits = hits + (int64_t)blockIdx.x * hit_cap;      // .x = point index in frame, .y = box | rank << 16
     for (int b = threadIdx.x; b < B; b += blockDim.x) s_box_cnt[b] = 0;
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int2 *stage = s_stage + (size_t)wid * stage_cap;
+    int wcount = 0;
 
-    for (int r0 = 0; r0 < ck.n_pts; r0 += kCropThreads) {
-        const int i = r0 + threadIdx.x;
+    const int w_lo = wid * kCropWarpPts, w_hi = min(w_lo + kCropWarpPts, ck.n_pts);
+    for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
+        const int i = i0 + lane;
         int hb[kMaxHitsPerPoint];
         int nh = 0;
-        if (i < ck.n_pts) {
+        if (i < w_hi) {
             const float px = __ldg(pts + i * pt_stride), py = __ldg(pts + i * pt_stride + 1), pz = __ldg(pts + i * pt_stride + 2);
             if (px != px || py != py || pz != pz) {
                 // NaN never satisfies `sign >= 0`: the reference reports such a point inside every box
                 for (int b = 0; b < B; ++b) {
-                    if (crop_inside(px, py, pz, reinterpret_cast<const float4 *>(planes) + (b0 + b) * 6)) {
+                    if (crop_inside(px, py, pz, pl + b * 6)) {
                         if (nh < kMaxHitsPerPoint) hb[nh] = b; else atomicExch(overflow, 2);
                         ++nh;
                     }
@@ -166,10 +201,10 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                 const int cx = crop_cell(px, m.x0, m.inv_x, G), cy = crop_cell(py, m.y0, m.inv_y, G);
                 if (cx >= 0 && cx < G && cy >= 0 && cy < G && m.inv_x > 0.f) {
                     const int c = cy * G + cx;
-                    const int e1 = min(cs[c + 1], cell_cap);
-                    for (int e = cs[c]; e < e1; ++e) {
-                        const int b = cb[e];
-                        if (crop_inside(px, py, pz, reinterpret_cast<const float4 *>(planes) + (b0 + b) * 6)) {
+                    const int e1 = min(__ldg(cs + c + 1), cell_cap);
+                    for (int e = __ldg(cs + c); e < e1; ++e) {
+                        const int b = __ldg(cb + e);
+                        if (crop_inside(px, py, pz, pl + b * 6)) {
                             if (nh < kMaxHitsPerPoint) hb[nh] = b; else atomicExch(overflow, 2);
                             ++nh;
                         }
@@ -178,24 +213,31 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
             }
             if (nh > kMaxHitsPerPoint) nh = kMaxHitsPerPoint;
         }
-        // ordered append: exclusive prefix of nh over the block (point order)
+        const unsigned any = __ballot_sync(0xffffffffu, nh > 0);
+        if (any == 0) continue;                                        // the common case: nothing inside any box
         int incl = nh;
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) warp_sum[wid] = incl;
-        __syncthreads();
-        int before = s_base;
-        for (int w = 0; w < wid; ++w) before += warp_sum[w];
-        const int at = before + incl - nh;
-        for (int k = 0; k < nh; ++k) {
-            if (at + k < hit_cap) my_hits[at + k] = make_int2(ck.first_pt + i, hb[k]);
-            else atomicExch(overflow, 3);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < kCropThreads / 32; ++w) t += warp_sum[w]; s_base += t; }
-        __syncthreads();
+        const int at = wcount + incl - nh;
+#pragma unroll
+        for (int k = 0; k < kMaxHitsPerPoint; ++k)
+            if (k < nh) {
+                if (at + k < stage_cap) stage[at + k] = make_int2(ck.first_pt + i, hb[k]);
+                else atomicExch(overflow, 3);
+            }
+        wcount += __shfl_sync(0xffffffffu, incl, 31);
     }
-    const int total = min(s_base, hit_cap);
+    if (wcount > stage_cap) wcount = stage_cap;
+    if (lane == 0) warp_total[wid] = wcount;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < kCropWarps; ++w) { if (w < wid) before += warp_total[w]; total += warp_total[w]; }
+    for (int h = lane; h < wcount; h += 32) {
+        if (before + h < hit_cap) my_hits[before + h] = stage[h];
+        else atomicExch(overflow, 3);
+    }
+    total = min(total, hit_cap);
     if (threadIdx.x == 0) n_hits[blockIdx.x] = total;
+    __syncthreads();
     // ---- rank of every hit among the hits of the same box in this chunk (point order): one warp walks the
     //      ordered list 32 at a time; equal boxes inside a group are ranked by lane.
     if (wid == 0) {
@@ -309,9 +351,9 @@ extern "C" int al3d_crop_build_grid(const float *aabb, const int64_t *box_off, i
                                     int32_t *cell_start, int32_t *cell_boxes, int cell_cap, int32_t *overflow, void *stream)
 {
     AL3D_CHECK_ARG(aabb && box_off && grid_meta && cell_start && cell_boxes && overflow, "al3d_crop_build_grid: null pointer");
-    AL3D_CHECK_ARG(G >= 1 && G <= 96, "al3d_crop_build_grid: G=%d not in [1,96]", G);
+    AL3D_CHECK_ARG(G >= 1 && G <= 64, "al3d_crop_build_grid: G=%d not in [1,64]", G);
     if (n_frames <= 0) return 0;
-    crop_grid_kernel<<<n_frames, kCropThreads, (size_t)G * G * sizeof(int32_t), (cudaStream_t)stream>>>(
+    crop_grid_kernel<<<n_frames, kCropThreads, (size_t)2 * G * G * sizeof(int32_t), (cudaStream_t)stream>>>(
         aabb, box_off, G, reinterpret_cast<CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap, overflow);
     AL3D_CHECK_LAUNCH("crop_grid_kernel");
     return 0;
@@ -326,9 +368,13 @@ extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int6
                    chunk_box_count && overflow, "al3d_crop_hits: null pointer");
     AL3D_CHECK_ARG(pt_stride >= 3, "al3d_crop_hits: pt_stride=%lld", (long long)pt_stride);
     AL3D_CHECK_ARG(max_boxes >= 1 && max_boxes <= 12288, "al3d_crop_hits: max_boxes=%d not in [1,12288]", max_boxes);
-    AL3D_CHECK_ARG(hit_cap >= 1 && hit_cap <= 32767, "al3d_crop_hits: hit_cap=%d not in [1,32767]", hit_cap);
+    AL3D_CHECK_ARG(hit_cap >= 1 && hit_cap <= 16384, "al3d_crop_hits: hit_cap=%d not in [1,16384]", hit_cap);
     if (n_chunks <= 0) return 0;
-    crop_hits_kernel<<<n_chunks, kCropThreads, (size_t)max_boxes * sizeof(int32_t), (cudaStream_t)stream>>>(
+    const size_t smem = (size_t)((max_boxes + 1) & ~1) * sizeof(int32_t) +
+                        (size_t)kCropWarps * std::min(hit_cap, kCropWarpPts * kMaxHitsPerPoint) * sizeof(int2);
+    AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_crop_hits: hit_cap=%d x max_boxes=%d needs too much shared memory", hit_cap, max_boxes);
+    if (smem > 48 * 1024) AL3D_CHECK_CUDA(cudaFuncSetAttribute(crop_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    crop_hits_kernel<<<n_chunks, kCropThreads, smem, (cudaStream_t)stream>>>(
         points, pt_stride, pt_off, planes, box_off, G, reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes,
         cell_cap, reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<int2 *>(hits), hit_cap, n_hits, chunk_box_count,
         max_boxes, overflow);

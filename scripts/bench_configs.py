@@ -50,6 +50,11 @@ def bench_crop(n_frames):
     total = int(res["offsets"][-1].item())
     assert int(res["overflow"].item()) == 0
     ms = timed(lambda: plan.run())
+    # cumulative prefixes of the valid launch sequence (the scan rewrites its input in place, so stages cannot
+    # be replayed on their own); per-stage time = difference of consecutive prefixes
+    seqs = [("grid",), ("grid", "hits_pass"), ("grid", "hits_pass", "scan"), ("grid", "hits_pass", "scan", "fill")]
+    cum = [timed(lambda q=q: [getattr(plan, k)() for k in q]) for q in seqs]
+    stage_ms = {"grid": cum[0], "hits": cum[1] - cum[0], "scan": cum[2] - cum[1], "fill": cum[3] - cum[2]}
     n_points = int(plan.pts_all.shape[0])
     alg_bytes = plan.read_bytes + total * (4 + 12)                  # + 4 B index + 12 B xyz per inside point
     moved = alg_bytes + total * 24                                  # the f64 global xyz is extra output
@@ -60,7 +65,7 @@ def bench_crop(n_frames):
         ocrop.crop_frame(frames[f]["points"], boxes[f], poses[f])
     cpu_s_per_frame = (time.perf_counter() - t0) / min(2, n_frames)
     print(json.dumps({"bench": "crop", "frames": n_frames, "points": n_points, "boxes": int(plan.TB), "inside": total,
-                      "ms": ms, "frames_per_s": n_frames / (ms * 1e-3), "algorithmic_bytes": alg_bytes,
+                      "ms": ms, "stage_ms": stage_ms, "frames_per_s": n_frames / (ms * 1e-3), "algorithmic_bytes": alg_bytes,
                       "achieved_gbs": alg_bytes / (ms * 1e-3) / 1e9, "achieved_gbs_incl_f64_output": moved / (ms * 1e-3) / 1e9,
                       "hbm_peak_gbs": PEAKS["hbm_gbs"], "frac_of_measured_hbm": alg_bytes / (ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"],
                       "cpu_oracle_s_per_frame_1thread": cpu_s_per_frame,

@@ -75,7 +75,7 @@ def test_crop_ragged_batch_and_edge_cases():
     dense[18] = [1.0, 0.0, 0.0]
     ob = np.array([[0, 0, 0, 2, 2, 2, 0.0], [0.1, 0, 0, 2, 2, 2, 0.3], [0, 0.1, 0, 3, 1, 2, -0.4], [5, 5, 0, 1, 1, 1, 0.0]], np.float32)
     points.append(dense); boxes.append(ob); poses.append(frames[0]["pose"])
-    res = crop.crop_frames(points, boxes, poses, hit_cap=8192)
+    res = crop.crop_frames(points, boxes, poses, hit_cap=16384)
     assert int(res["overflow"].item()) == 0
     _check_against_oracle(points, boxes, poses, res)
     # NaN point is "inside" every box, exactly like the reference predicate
@@ -90,7 +90,7 @@ def test_crop_overflow_is_reported():
     pts = rng.uniform(-0.5, 0.5, (4096, 3)).astype(np.float32)
     boxes = np.tile(np.array([[0, 0, 0, 4, 4, 4, 0.0]], np.float32), (10, 1))     # every point inside 10 boxes
     with pytest.raises(OverflowError):
-        crop.crop_frames([pts], [boxes], hit_cap=8192)
+        crop.crop_frames([pts], [boxes], hit_cap=16384)
 
 
 @pytest.mark.gpu
