@@ -26,7 +26,7 @@ _SIGNATURES = {
     "al3d_twostage_retransform": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "al3d_crop_chunk_points": [],
     "al3d_crop_build_grid": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
-    "al3d_crop_hits": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp],
+    "al3d_crop_hits": [_vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp],
     "al3d_crop_scan": [_vp, _vp, _i, _i64, _vp, _i, _vp, _vp, _vp],
     "al3d_crop_fill": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "al3d_crop_dense_mask": [_vp, _vp, _i, _vp, _vp],

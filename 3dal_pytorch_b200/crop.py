@@ -129,7 +129,7 @@ class CropPlan:
 
     def hits_pass(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
-        _lib.check(lib.al3d_crop_hits(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_planes), p(self.d_box_off), GRID, p(self.meta),
+        _lib.check(lib.al3d_crop_hits(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_planes), p(self.d_aabb), p(self.d_box_off), GRID, p(self.meta),
                                       p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.d_chunks), self.n_chunks,
                                       p(self.hits), self.hit_cap, p(self.n_hits), p(self.cbc), self.max_boxes, p(self.overflow), st),
                    "crop_hits")

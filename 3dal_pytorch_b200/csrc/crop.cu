@@ -149,21 +149,26 @@ struct CropChunk { int32_t frame; int32_t first_pt; int32_t n_pts; int32_t chunk
 
 constexpr int kCropWarps = kCropThreads / 32;
 constexpr int kCropWarpPts = kCropChunk / kCropWarps;     // consecutive points owned by one warp
+constexpr int kCropQueue = 320;                           // per-warp candidate queue (>= 31 + 32 * kMaxHitsPerPoint)
 
 __global__ void __launch_bounds__(kCropThreads)
 crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
-                 const float *__restrict__ planes, const int64_t *__restrict__ box_off, int G,
+                 const float *__restrict__ planes, const float *__restrict__ aabb, const int64_t *__restrict__ box_off, int G,
                  const CropGridMeta *__restrict__ meta, const int32_t *__restrict__ cell_start,
                  const int32_t *__restrict__ cell_boxes, int cell_cap, const CropChunk *__restrict__ chunks,
                  int2 *__restrict__ hits, int hit_cap, int32_t *__restrict__ n_hits, int32_t *__restrict__ chunk_box_count,
                  int max_boxes, int32_t *__restrict__ overflow)
 {
-    // Each warp owns kCropWarpPts CONSECUTIVE points and walks them 32 at a time, appending its hits (in point
-    // order) to a private staging list in shared memory; one block-wide prefix over the eight warp totals then
-    // gives every warp its place in the chunk's ordered hit list.  No block barrier inside the point loop.
+    // Each warp owns kCropWarpPts CONSECUTIVE points and walks them 32 at a time.  A lane looks up the boxes
+    // registered in its point's BEV cell and keeps those whose padded bounding box contains the point; these
+    // (point, box) pairs go, in point order, into a per-warp queue.  Whenever 32 pairs are queued the warp runs
+    // the exact six-plane predicate on them in lock-step (no divergence) and appends the hits, still in point
+    // order, to its staging list.  One block-wide prefix over the eight warp totals then places every warp's
+    // list in the chunk's ordered hit list.  No block barrier inside the point loop.
     extern __shared__ int32_t s_dyn[];
     int32_t *s_box_cnt = s_dyn;                                        // per-box hit counters (max_boxes)
-    int2 *s_stage = reinterpret_cast<int2 *>(s_dyn + ((max_boxes + 1) & ~1));   // kCropWarps x stage_cap
+    int2 *s_queue = reinterpret_cast<int2 *>(s_dyn + ((max_boxes + 1) & ~1));   // kCropWarps x kCropQueue
+    int2 *s_stage = s_queue + kCropWarps * kCropQueue;                  // kCropWarps x stage_cap
     __shared__ int warp_total[kCropWarps];
     const int stage_cap = min(hit_cap, kCropWarpPts * kMaxHitsPerPoint); // per warp (its worst case); the chunk total is capped at hit_cap
     const CropChunk ck = chunks[blockIdx.x];
@@ -176,27 +181,54 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     const int32_t *cb = cell_boxes + (int64_t)f * cell_cap;
     const float *pts = points + (pt_off[f] + ck.first_pt) * pt_stride;
     const float4 *pl = reinterpret_cast<const float4 *>(planes) + b0 * 6;
+    const float2 *bb = reinterpret_cast<const float2 *>(aabb) + b0 * 3;
     int2 *my_hits = hits + (int64_t)blockIdx.x * hit_cap;      // .x = point index in frame, .y = box | rank << 16
     for (int b = threadIdx.x; b < B; b += blockDim.x) s_box_cnt[b] = 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int2 *queue = s_queue + wid * kCropQueue;
     int2 *stage = s_stage + (size_t)wid * stage_cap;
-    int wcount = 0;
+    int wcount = 0, qhead = 0, qcount = 0;
+
+    // exact test of up to 32 queued pairs (one per lane), hits appended in queue order
+    auto drain = [&](int n) {
+        bool hit = false;
+        int2 e = make_int2(0, 0);
+        if (lane < n) {
+            int at = qhead + lane;
+            if (at >= kCropQueue) at -= kCropQueue;
+            e = queue[at];
+            if (e.y & (1 << 30)) { hit = true; e.y &= ~(1 << 30); }     // NaN point: already decided
+            else {
+                const float *q = pts + (int64_t)e.x * pt_stride;
+                hit = crop_inside(__ldg(q), __ldg(q + 1), __ldg(q + 2), pl + e.y * 6);
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) {
+            const int at = wcount + __popc(bal & ((1u << lane) - 1u));
+            if (at < stage_cap) stage[at] = make_int2(ck.first_pt + e.x, e.y);
+            else atomicExch(overflow, 3);
+        }
+        wcount += __popc(bal);
+        qhead += n; if (qhead >= kCropQueue) qhead -= kCropQueue;
+        qcount -= n;
+    };
 
     const int w_lo = wid * kCropWarpPts, w_hi = min(w_lo + kCropWarpPts, ck.n_pts);
     for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
         const int i = i0 + lane;
-        int hb[kMaxHitsPerPoint];
-        int nh = 0;
+        int cand[kMaxHitsPerPoint];
+        int nc = 0;
         if (i < w_hi) {
             const float px = __ldg(pts + i * pt_stride), py = __ldg(pts + i * pt_stride + 1), pz = __ldg(pts + i * pt_stride + 2);
             if (px != px || py != py || pz != pz) {
-                // NaN never satisfies `sign >= 0`: the reference reports such a point inside every box
-                for (int b = 0; b < B; ++b) {
+                // NaN never satisfies `sign >= 0`: the reference reports such a point inside every box.  Rare:
+                // handled in place, outside the queue.
+                for (int b = 0; b < B; ++b)
                     if (crop_inside(px, py, pz, pl + b * 6)) {
-                        if (nh < kMaxHitsPerPoint) hb[nh] = b; else atomicExch(overflow, 2);
-                        ++nh;
+                        if (nc < kMaxHitsPerPoint) cand[nc] = b | (1 << 30); else atomicExch(overflow, 2);   // bit 30: already exact
+                        ++nc;
                     }
-                }
             } else {
                 const int cx = crop_cell(px, m.x0, m.inv_x, G), cy = crop_cell(py, m.y0, m.inv_y, G);
                 if (cx >= 0 && cx < G && cy >= 0 && cy < G && m.inv_x > 0.f) {
@@ -204,28 +236,35 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                     const int e1 = min(__ldg(cs + c + 1), cell_cap);
                     for (int e = __ldg(cs + c); e < e1; ++e) {
                         const int b = __ldg(cb + e);
-                        if (crop_inside(px, py, pz, pl + b * 6)) {
-                            if (nh < kMaxHitsPerPoint) hb[nh] = b; else atomicExch(overflow, 2);
-                            ++nh;
+                        const float2 lo = __ldg(bb + b * 3), mid = __ldg(bb + b * 3 + 1), hi = __ldg(bb + b * 3 + 2);
+                        // aabb = [xmin ymin | zmin xmax | ymax zmax], padded: never rejects a point the exact test accepts
+                        if (px >= lo.x && py >= lo.y && pz >= mid.x && px <= mid.y && py <= hi.x && pz <= hi.y) {
+                            if (nc < kMaxHitsPerPoint) cand[nc] = b; else atomicExch(overflow, 2);
+                            ++nc;
                         }
                     }
                 }
             }
-            if (nh > kMaxHitsPerPoint) nh = kMaxHitsPerPoint;
+            if (nc > kMaxHitsPerPoint) nc = kMaxHitsPerPoint;
         }
-        const unsigned any = __ballot_sync(0xffffffffu, nh > 0);
-        if (any == 0) continue;                                        // the common case: nothing inside any box
-        int incl = nh;
+        const unsigned any = __ballot_sync(0xffffffffu, nc > 0);
+        if (any == 0) continue;                                        // the common case: no candidate at all
+        int incl = nc;
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int at = wcount + incl - nh;
+        int at = qhead + qcount + incl - nc;
 #pragma unroll
         for (int k = 0; k < kMaxHitsPerPoint; ++k)
-            if (k < nh) {
-                if (at + k < stage_cap) stage[at + k] = make_int2(ck.first_pt + i, hb[k]);
-                else atomicExch(overflow, 3);
+            if (k < nc) {
+                int a2 = at + k;
+                while (a2 >= kCropQueue) a2 -= kCropQueue;
+                queue[a2] = make_int2(i, cand[k]);
             }
-        wcount += __shfl_sync(0xffffffffu, incl, 31);
+        qcount += __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        while (qcount >= 32) drain(32);
     }
+    __syncwarp();
+    while (qcount > 0) drain(min(qcount, 32));
     if (wcount > stage_cap) wcount = stage_cap;
     if (lane == 0) warp_total[wid] = wcount;
     __syncthreads();
@@ -360,22 +399,22 @@ extern "C" int al3d_crop_build_grid(const float *aabb, const int64_t *box_off, i
 }
 
 extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
-                              const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
+                              const float *aabb, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
                               const int32_t *cell_boxes, int cell_cap, const int32_t *chunks, int n_chunks, void *hits,
                               int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes, int32_t *overflow, void *stream)
 {
-    AL3D_CHECK_ARG(points && pt_off && planes && box_off && grid_meta && cell_start && cell_boxes && chunks && hits && n_hits &&
+    AL3D_CHECK_ARG(points && pt_off && planes && aabb && box_off && grid_meta && cell_start && cell_boxes && chunks && hits && n_hits &&
                    chunk_box_count && overflow, "al3d_crop_hits: null pointer");
     AL3D_CHECK_ARG(pt_stride >= 3, "al3d_crop_hits: pt_stride=%lld", (long long)pt_stride);
     AL3D_CHECK_ARG(max_boxes >= 1 && max_boxes <= 12288, "al3d_crop_hits: max_boxes=%d not in [1,12288]", max_boxes);
     AL3D_CHECK_ARG(hit_cap >= 1 && hit_cap <= 16384, "al3d_crop_hits: hit_cap=%d not in [1,16384]", hit_cap);
     if (n_chunks <= 0) return 0;
-    const size_t smem = (size_t)((max_boxes + 1) & ~1) * sizeof(int32_t) +
+    const size_t smem = (size_t)((max_boxes + 1) & ~1) * sizeof(int32_t) + (size_t)kCropWarps * kCropQueue * sizeof(int2) +
                         (size_t)kCropWarps * std::min(hit_cap, kCropWarpPts * kMaxHitsPerPoint) * sizeof(int2);
     AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_crop_hits: hit_cap=%d x max_boxes=%d needs too much shared memory", hit_cap, max_boxes);
     if (smem > 48 * 1024) AL3D_CHECK_CUDA(cudaFuncSetAttribute(crop_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     crop_hits_kernel<<<n_chunks, kCropThreads, smem, (cudaStream_t)stream>>>(
-        points, pt_stride, pt_off, planes, box_off, G, reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes,
+        points, pt_stride, pt_off, planes, aabb, box_off, G, reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes,
         cell_cap, reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<int2 *>(hits), hit_cap, n_hits, chunk_box_count,
         max_boxes, overflow);
     AL3D_CHECK_LAUNCH("crop_hits_kernel");

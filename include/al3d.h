@@ -122,7 +122,7 @@ int al3d_crop_build_grid(const float *aabb, const int64_t *box_off, int n_frames
 /* chunks: (n_chunks, 4) i32 rows [frame, first point in frame, n points, chunk index in frame];
  * hits: (n_chunks, hit_cap) int2 scratch; chunk_box_count: (n_chunks, max_boxes) i32 scratch. */
 int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
-                   const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
+                   const float *aabb, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
                    const int32_t *cell_boxes, int cell_cap, const int32_t *chunks, int n_chunks, void *hits,
                    int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes, int32_t *overflow, void *stream);
 /* frame_chunk_off (F+1) i64; writes box_total (n_boxes) i32 and offsets (n_boxes+1) i64 (exclusive). */
