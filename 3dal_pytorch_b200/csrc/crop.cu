@@ -133,16 +133,21 @@ crop_grid_kernel(const float *__restrict__ aabb, const int64_t *__restrict__ box
     }
 }
 
-// exact reference predicate
+// exact reference predicate.  The reference rejects at the first plane with sign >= 0; "inside" is therefore the
+// AND over the six planes of !(sign >= 0) (a NaN sign never rejects), which lets all six plane equations be
+// loaded up front (one memory round trip instead of six dependent ones) without changing any result.
 __device__ __forceinline__ bool crop_inside(float px, float py, float pz, const float4 *__restrict__ pl)
 {
+    float4 q[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) q[k] = __ldg(pl + k);
+    bool in = true;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        const float4 q = __ldg(pl + k);
-        const float sgn = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, q.x), __fmul_rn(py, q.y)), __fmul_rn(pz, q.z)), q.w);
-        if (sgn >= 0.f) return false;
+        const float sgn = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, q[k].x), __fmul_rn(py, q[k].y)), __fmul_rn(pz, q[k].z)), q[k].w);
+        in = in && !(sgn >= 0.f);
     }
-    return true;
+    return in;
 }
 
 struct CropChunk { int32_t frame; int32_t first_pt; int32_t n_pts; int32_t chunk_in_frame; };
@@ -215,53 +220,75 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     };
 
     const int w_lo = wid * kCropWarpPts, w_hi = min(w_lo + kCropWarpPts, ck.n_pts);
-    for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
-        const int i = i0 + lane;
-        int cand[kMaxHitsPerPoint];
-        int nc = 0;
-        if (i < w_hi) {
-            const float px = __ldg(pts + i * pt_stride), py = __ldg(pts + i * pt_stride + 1), pz = __ldg(pts + i * pt_stride + 2);
-            if (px != px || py != py || pz != pz) {
-                // NaN never satisfies `sign >= 0`: the reference reports such a point inside every box.  Rare:
-                // handled in place, outside the queue.
-                for (int b = 0; b < B; ++b)
-                    if (crop_inside(px, py, pz, pl + b * 6)) {
-                        if (nc < kMaxHitsPerPoint) cand[nc] = b | (1 << 30); else atomicExch(overflow, 2);   // bit 30: already exact
-                        ++nc;
-                    }
-            } else {
-                const int cx = crop_cell(px, m.x0, m.inv_x, G), cy = crop_cell(py, m.y0, m.inv_y, G);
+    constexpr int U = 4;                       // points per lane per outer iteration: U independent load chains in flight
+    for (int i0 = w_lo; i0 < w_hi; i0 += 32 * U) {
+        float px[U], py[U], pz[U];
+        int e0[U], e1[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 + k * 32 + lane;
+            px[k] = py[k] = pz[k] = 0.f;
+            if (i < w_hi) {
+                px[k] = __ldg(pts + i * pt_stride); py[k] = __ldg(pts + i * pt_stride + 1); pz[k] = __ldg(pts + i * pt_stride + 2);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 + k * 32 + lane;
+            e0[k] = e1[k] = 0;
+            const bool isnan_k = (px[k] != px[k] || py[k] != py[k] || pz[k] != pz[k]);
+            if (i < w_hi && !isnan_k) {
+                const int cx = crop_cell(px[k], m.x0, m.inv_x, G), cy = crop_cell(py[k], m.y0, m.inv_y, G);
                 if (cx >= 0 && cx < G && cy >= 0 && cy < G && m.inv_x > 0.f) {
                     const int c = cy * G + cx;
-                    const int e1 = min(__ldg(cs + c + 1), cell_cap);
-                    for (int e = __ldg(cs + c); e < e1; ++e) {
+                    e0[k] = __ldg(cs + c);
+                    e1[k] = min(__ldg(cs + c + 1), cell_cap);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 + k * 32 + lane;
+            int cand[kMaxHitsPerPoint];
+            int nc = 0;
+            if (i < w_hi) {
+                if (px[k] != px[k] || py[k] != py[k] || pz[k] != pz[k]) {
+                    // NaN never satisfies `sign >= 0`: the reference reports such a point inside every box.  Rare:
+                    // decided in place, flagged so that the queue does not test it again.
+                    for (int b = 0; b < B; ++b)
+                        if (crop_inside(px[k], py[k], pz[k], pl + b * 6)) {
+                            if (nc < kMaxHitsPerPoint) cand[nc] = b | (1 << 30); else atomicExch(overflow, 2);
+                            ++nc;
+                        }
+                } else {
+                    for (int e = e0[k]; e < e1[k]; ++e) {
                         const int b = __ldg(cb + e);
                         const float2 lo = __ldg(bb + b * 3), mid = __ldg(bb + b * 3 + 1), hi = __ldg(bb + b * 3 + 2);
                         // aabb = [xmin ymin | zmin xmax | ymax zmax], padded: never rejects a point the exact test accepts
-                        if (px >= lo.x && py >= lo.y && pz >= mid.x && px <= mid.y && py <= hi.x && pz <= hi.y) {
+                        if (px[k] >= lo.x && py[k] >= lo.y && pz[k] >= mid.x && px[k] <= mid.y && py[k] <= hi.x && pz[k] <= hi.y) {
                             if (nc < kMaxHitsPerPoint) cand[nc] = b; else atomicExch(overflow, 2);
                             ++nc;
                         }
                     }
                 }
+                if (nc > kMaxHitsPerPoint) nc = kMaxHitsPerPoint;
             }
-            if (nc > kMaxHitsPerPoint) nc = kMaxHitsPerPoint;
-        }
-        const unsigned any = __ballot_sync(0xffffffffu, nc > 0);
-        if (any == 0) continue;                                        // the common case: no candidate at all
-        int incl = nc;
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        int at = qhead + qcount + incl - nc;
+            const unsigned any = __ballot_sync(0xffffffffu, nc > 0);
+            if (any == 0) continue;                                    // the common case: no candidate at all
+            int incl = nc;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int at = qhead + qcount + incl - nc;
 #pragma unroll
-        for (int k = 0; k < kMaxHitsPerPoint; ++k)
-            if (k < nc) {
-                int a2 = at + k;
-                while (a2 >= kCropQueue) a2 -= kCropQueue;
-                queue[a2] = make_int2(i, cand[k]);
-            }
-        qcount += __shfl_sync(0xffffffffu, incl, 31);
-        __syncwarp();
-        while (qcount >= 32) drain(32);
+            for (int j = 0; j < kMaxHitsPerPoint; ++j)
+                if (j < nc) {
+                    int a2 = at + j;
+                    while (a2 >= kCropQueue) a2 -= kCropQueue;
+                    queue[a2] = make_int2(i, cand[j]);
+                }
+            qcount += __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            while (qcount >= 32) drain(32);
+        }
     }
     __syncwarp();
     while (qcount > 0) drain(min(qcount, 32));
@@ -270,28 +297,30 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     __syncthreads();
     int before = 0, total = 0;
     for (int w = 0; w < kCropWarps; ++w) { if (w < wid) before += warp_total[w]; total += warp_total[w]; }
-    for (int h = lane; h < wcount; h += 32) {
-        if (before + h < hit_cap) my_hits[before + h] = stage[h];
-        else atomicExch(overflow, 3);
-    }
+    if (before + wcount > hit_cap) atomicExch(overflow, 3);
     total = min(total, hit_cap);
     if (threadIdx.x == 0) n_hits[blockIdx.x] = total;
-    __syncthreads();
     // ---- rank of every hit among the hits of the same box in this chunk (point order): one warp walks the
     //      ordered list 32 at a time; equal boxes inside a group are ranked by lane.
     if (wid == 0) {
-        for (int h0 = 0; h0 < total; h0 += 32) {
-            const int h = h0 + lane;
-            const bool act = h < total;
-            const int box = act ? my_hits[h].y : -1 - lane;
-            const unsigned same = __match_any_sync(0xffffffffu, box);
-            if (act) {
-                const int rank = s_box_cnt[box] + __popc(same & ((1u << lane) - 1u));
-                my_hits[h].y = box | (rank << 16);
+        int g0 = 0;                                                    // global position of the current warp list
+        for (int w = 0; w < kCropWarps; ++w) {
+            const int cnt = warp_total[w];
+            int2 *l = s_stage + (size_t)w * stage_cap;
+            for (int h0 = 0; h0 < cnt; h0 += 32) {
+                const int h = h0 + lane;
+                const bool act = h < cnt;
+                const int2 e = act ? l[h] : make_int2(0, -1 - lane);
+                const unsigned same = __match_any_sync(0xffffffffu, e.y);
+                if (act) {
+                    const int rank = s_box_cnt[e.y] + __popc(same & ((1u << lane) - 1u));
+                    if (g0 + h < hit_cap) my_hits[g0 + h] = make_int2(e.x, e.y | (rank << 16));
+                }
+                __syncwarp();
+                if (act && (same >> lane) == 1u) s_box_cnt[e.y] += __popc(same);  // highest lane of each group updates
+                __syncwarp();
             }
-            __syncwarp();
-            if (act && (same >> lane) == 1u) s_box_cnt[box] += __popc(same);      // highest lane of each group updates
-            __syncwarp();
+            g0 += cnt;
         }
     }
     __syncthreads();
