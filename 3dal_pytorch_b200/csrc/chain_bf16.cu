@@ -455,7 +455,8 @@ done:
 //              dconv2's partial sum (channels 0..31 at +0, 32..63 at +32).  D1b[2] first holds conv2's accumulator.
 //              Later D3 = dconv3 accumulator at [256,384) and A4 (its bf16 image) at [256,288) + [320,352)
 //   [448,480)  A2 = conv2 output (64 ch);  [480,512)  A1 = conv1 output (64 ch)
-//   [384,512)  finally D4 = dconv4 accumulator
+//   [0,128)    finally D4 = dconv4 accumulator (over the dead A3), which leaves [384,512) free for the NEXT tile's
+//              conv1 / conv2 (A1, A2, conv2 accumulator) while this tile's dconv3 / dconv4 are still running
 // ================================================================================================
 struct Pass2Params {
     const float *x; int64_t sb, sc, sp; int bs, n; int c_in;
@@ -479,7 +480,7 @@ struct Pass2Params {
 constexpr int kP2Stages = 3;
 constexpr int kP2Blocks = 31;
 constexpr int kP2ResidentBytes = 163840;
-constexpr uint32_t kColD2 = 0, kColD1 = 256, kColA2 = 448, kColA1 = 480, kColD3 = 256, kColD4 = 384;
+constexpr uint32_t kColD2 = 0, kColD1 = 256, kColA2 = 448, kColA1 = 480, kColD3 = 256, kColD4 = 0;
 struct Pass2Smem {
     uint8_t wres[kP2ResidentBytes];    // weight blocks kept for the whole kernel (see p2_resident_off)
     uint8_t wring[kP2Stages][kStageBytes];
@@ -487,7 +488,7 @@ struct Pass2Smem {
     float lpart[2][2 * kTile];         // logits partial sums of the upper column half (double-buffered by tile parity)
     uint64_t w_full[kP2Stages], w_empty[kP2Stages];
     uint64_t res_full;
-    uint64_t act_ready, acc_ready;
+    uint64_t act_f, acc_f, act_t, acc_t;   // front stream (conv1 / conv2 of the next tile) and tail stream (dconv2-4)
     uint64_t d1_full[3], d1_act[3];
     uint32_t tmem_base;
 };
@@ -521,6 +522,28 @@ __device__ __forceinline__ void pack_act32(const uint32_t (&v)[32], const float 
     }
 }
 
+// conv1 on CUDA cores for 32 output channels starting at ch0 -> 16 packed bf16x2 words
+__device__ __forceinline__ void conv1_pack32(const float (&xv)[8], int c_in, const float *w_t, const float *bias, int ch0,
+                                             uint32_t (&o)[16])
+{
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float4 a0 = *reinterpret_cast<const float4 *>(bias + ch0 + g * 8);
+        float4 a1 = *reinterpret_cast<const float4 *>(bias + ch0 + g * 8 + 4);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= c_in) break;
+            const float4 w0v = *reinterpret_cast<const float4 *>(w_t + c * 64 + ch0 + g * 8);
+            const float4 w1v = *reinterpret_cast<const float4 *>(w_t + c * 64 + ch0 + g * 8 + 4);
+            const float xx = xv[c];
+            a0.x = fmaf(xx, w0v.x, a0.x); a0.y = fmaf(xx, w0v.y, a0.y); a0.z = fmaf(xx, w0v.z, a0.z); a0.w = fmaf(xx, w0v.w, a0.w);
+            a1.x = fmaf(xx, w1v.x, a1.x); a1.y = fmaf(xx, w1v.y, a1.y); a1.z = fmaf(xx, w1v.z, a1.z); a1.w = fmaf(xx, w1v.w, a1.w);
+        }
+        o[g * 4 + 0] = relu_pack_bf16x2(a0.x, a0.y); o[g * 4 + 1] = relu_pack_bf16x2(a0.z, a0.w);
+        o[g * 4 + 2] = relu_pack_bf16x2(a1.x, a1.y); o[g * 4 + 3] = relu_pack_bf16x2(a1.z, a1.w);
+    }
+}
+
 // 4 MMAs (K = 64) with A in TMEM: a_col[s] is the TMEM column of K-slice s (8 columns each)
 __device__ __forceinline__ void mma_ts_k64(uint32_t tmem_d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                            uint32_t b_addr, uint32_t rows_b, uint32_t idesc, bool accumulate_first)
@@ -546,8 +569,8 @@ seg_pass2_kernel(const Pass2Params p)
     if (threadIdx.x == 0) {
         for (int i = 0; i < kP2Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
         mbar_init(&s.res_full, 1);
-        mbar_init(&s.act_ready, kEpiThreads);
-        mbar_init(&s.acc_ready, 1);
+        mbar_init(&s.act_f, kEpiThreads); mbar_init(&s.act_t, kEpiThreads);
+        mbar_init(&s.acc_f, 1); mbar_init(&s.acc_t, 1);
         for (int i = 0; i < 3; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kEpiThreads); }
         fence_barrier_init();
     }
@@ -581,8 +604,11 @@ seg_pass2_kernel(const Pass2Params p)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
+        // Two interleaved streams per CTA: the "tail" of tile t (dconv3, dconv4) and the "front" of tile t+1
+        // (conv2), each with its own pair of barriers (act_t/acc_t, act_f/acc_f), so that the next tile's conv1/conv2
+        // are computed while this tile's serial tail is in flight.
         if (lane == 0) {
-            int stage = 0; uint32_t wphase = 0, act_phase = 0, d1a_phase[3] = {0, 0, 0};
+            int stage = 0; uint32_t wphase = 0, actf_phase = 0, actt_phase = 0, d1a_phase[3] = {0, 0, 0};
             const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128);
             // weight block `blk` of the tile: resident blocks have a fixed address, streamed ones come from the ring
 #define P2_NEXT_W(blk)                                                                   \
@@ -599,26 +625,29 @@ seg_pass2_kernel(const Pass2Params p)
                 mma_commit(&s.w_empty[stage]);                                           \
                 if (++stage == kP2Stages) { stage = 0; wphase ^= 1; }                    \
             }
-#define P2_WAIT_ACT(code)                                                        \
-            if (!mbar_wait(&s.act_ready, act_phase, code)) goto done;            \
-            AL3D_TS(0);                                                          \
-            act_phase ^= 1; tc_fence_after();
+#define P2_WAIT(bar, ph, code)                                                           \
+            if (!mbar_wait(&(bar), ph, code)) goto done;                                 \
+            AL3D_TS(0);                                                                  \
+            ph ^= 1; tc_fence_after();
+#define P2_ISSUE_CONV2()                                                                 \
+            {                                                                            \
+                P2_WAIT(s.act_f, actf_phase, 0xA200)                                     \
+                P2_NEXT_W(0)                                                             \
+                mma_ts_k64(tmem + kColD1 + 128, tmem + kColA1, tmem + kColA1 + 8, tmem + kColA1 + 16, tmem + kColA1 + 24, wb_, 64, id64, false); \
+                P2_REL_W(0)                                                              \
+                mma_commit(&s.acc_f);                                                    \
+            }
             if (!mbar_wait(&s.res_full, 0, 0xA2FF)) goto done;
             tc_fence_after();
             int it_local = 0;
+            int ts_i = 0;
+            if ((int)blockIdx.x < p.n_items) P2_ISSUE_CONV2()                 // front of the first tile
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
-                int ts_i = 0;
+                ts_i = 0;
                 AL3D_TS(0);
-                // conv2: A1 (TMEM) x W2 -> D1b[2]                                   (block 0)
-                P2_WAIT_ACT(0xA200)
-                {
-                    P2_NEXT_W(0)
-                    mma_ts_k64(tmem + kColD1 + 128, tmem + kColA1, tmem + kColA1 + 8, tmem + kColA1 + 16, tmem + kColA1 + 24, wb_, 64, id64, false);
-                    P2_REL_W(0)
-                }
-                mma_commit(&s.acc_ready);
+                const bool has_next = item + (int)gridDim.x < p.n_items;
                 // dconv1 chunks 0..2: A2 x Wd1[chunk] -> D1b[j]                     (blocks 1..3)
-                P2_WAIT_ACT(0xA201)
+                P2_WAIT(s.act_f, actf_phase, 0xA201)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     P2_NEXT_W(1 + j)
@@ -649,9 +678,9 @@ seg_pass2_kernel(const Pass2Params p)
                         mma_commit(&s.d1_full[j]);
                     }
                 }
-                mma_commit(&s.acc_ready);                                  // dconv2 accumulator complete
+                mma_commit(&s.acc_t);                                      // dconv2 accumulator complete
                 // dconv3: A3 x Wd3 -> D3                                            (blocks 25..28)
-                P2_WAIT_ACT(0xA202)
+                P2_WAIT(s.act_t, actt_phase, 0xA202)
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb) {
                     const uint32_t a = tmem + kColD2 + (kb >> 1) * 128 + (kb & 1) * 32;
@@ -659,9 +688,11 @@ seg_pass2_kernel(const Pass2Params p)
                     mma_ts_k64(tmem + kColD3, a, a + 8, a + 16, a + 24, wb_, 128, id128, kb > 0);
                     P2_REL_W(25 + kb)
                 }
-                mma_commit(&s.acc_ready);
-                // dconv4: A4 x Wd4 -> D4                                            (blocks 29, 30)
-                P2_WAIT_ACT(0xA203)
+                mma_commit(&s.acc_t);
+                // front of the next tile: conv2 on its conv1 output (A1 at [480,512) -> D1b[2]; both are free now)
+                if (has_next) P2_ISSUE_CONV2()
+                // dconv4: A4 x Wd4 -> D4 (over the dead A3 at columns 0..127)       (blocks 29, 30)
+                P2_WAIT(s.act_t, actt_phase, 0xA203)
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
                     const uint32_t a = tmem + kColD3 + kb * 64;
@@ -669,11 +700,12 @@ seg_pass2_kernel(const Pass2Params p)
                     mma_ts_k64(tmem + kColD4, a, a + 8, a + 16, a + 24, wb_, 128, id128, kb > 0);
                     P2_REL_W(29 + kb)
                 }
-                mma_commit(&s.acc_ready);
+                mma_commit(&s.acc_t);
             }
 #undef P2_NEXT_W
 #undef P2_REL_W
-#undef P2_WAIT_ACT
+#undef P2_WAIT
+#undef P2_ISSUE_CONV2
         }
     } else {
         // ------------------------------------------------------------ epilogue warps (256 threads)
@@ -681,8 +713,9 @@ seg_pass2_kernel(const Pass2Params p)
         const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
         const uint32_t tl = tmem + lane_addr;
         const int etid = threadIdx.x - 64;
-        uint32_t acc_phase = 0, d1f_phase[3] = {0, 0, 0};
+        uint32_t accf_phase = 0, acct_phase = 0, d1f_phase[3] = {0, 0, 0};
         int it_local = 0;
+        int ts_i = 0;
         const bool ts_on = (threadIdx.x == 64);
 #define AL3D_TSE() do { if (ts_on) AL3D_TS(1); } while (0)
 #define P2_PUBLISH(bar) do { tmem_st_wait(); tc_fence_before(); mbar_arrive(bar); } while (0)
@@ -698,63 +731,50 @@ seg_pass2_kernel(const Pass2Params p)
                 for (int c = 0; c < 8; ++c) dst[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
             }
         };
-        load_x(blockIdx.x, xv);
+        // front, part 1: conv1 on CUDA cores (this thread: 32 channels) -> A1, then prefetch the following tile's point
+        auto front_conv1 = [&](int next_item) {
+            uint32_t o[16];
+            conv1_pack32(xv, p.c_in, s.w1_w, s.w1_b, half * 32, o);
+            tmem_st16(tl + kColA1 + half * 16, o);
+            P2_PUBLISH(&s.act_f);
+            load_x(next_item, xv);
+        };
+        // front, part 2: conv2 accumulator (D1b[2]) -> A2
+        auto front_conv2 = [&]() -> bool {
+            if (!mbar_wait(&s.acc_f, accf_phase, 0xB100)) return false;
+            accf_phase ^= 1; tc_fence_after();
+            uint32_t v[32], o[16];
+            tmem_ld32(tl + kColD1 + 128 + half * 32, v);
+            tmem_ld_wait();
+            pack_act32(v, s.b2 + half * 32, o);
+            tmem_st16(tl + kColA2 + half * 16, o);
+            P2_PUBLISH(&s.act_f);
+            return true;
+        };
+        if ((int)blockIdx.x < p.n_items) {
+            // first tile of this CTA: its per-object dconv1 bias and its front are not hidden behind a previous tile
+            const int b0 = blockIdx.x / p.tiles_per_obj;
+            for (int i = etid; i < 512; i += kEpiThreads) s.gb[0][i] = __ldg(p.gbias + (int64_t)b0 * 512 + i);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            load_x(blockIdx.x, xv);
+            front_conv1(blockIdx.x + gridDim.x);
+            if (!front_conv2()) goto done;
+        }
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
-            int ts_i = 0;
+            ts_i = 0;
             AL3D_TSE();
             const int b = item / p.tiles_per_obj, t = item % p.tiles_per_obj;
             const int pidx_raw = t * kTile + row;
             const bool valid = pidx_raw < p.n;
             const int pidx = valid ? pidx_raw : p.n - 1;
             const int par = it_local & 1;
-            if (it_local == 0) {
-                // first tile of this CTA: load its per-object dconv1 bias; later tiles find it prefetched (below)
-                for (int i = etid; i < 512; i += kEpiThreads) s.gb[0][i] = __ldg(p.gbias + (int64_t)b * 512 + i);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-            // ---- conv1 on CUDA cores: this thread's 32 channels -> 16 packed words -> A1
-            {
-                uint32_t o[16];
-                const int ch0 = half * 32;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float4 a0 = *reinterpret_cast<const float4 *>(s.w1_b + ch0 + g * 8);
-                    float4 a1 = *reinterpret_cast<const float4 *>(s.w1_b + ch0 + g * 8 + 4);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        if (c >= p.c_in) break;
-                        const float4 w0v = *reinterpret_cast<const float4 *>(s.w1_w + c * 64 + ch0 + g * 8);
-                        const float4 w1v = *reinterpret_cast<const float4 *>(s.w1_w + c * 64 + ch0 + g * 8 + 4);
-                        const float xx = xv[c];
-                        a0.x = fmaf(xx, w0v.x, a0.x); a0.y = fmaf(xx, w0v.y, a0.y); a0.z = fmaf(xx, w0v.z, a0.z); a0.w = fmaf(xx, w0v.w, a0.w);
-                        a1.x = fmaf(xx, w1v.x, a1.x); a1.y = fmaf(xx, w1v.y, a1.y); a1.z = fmaf(xx, w1v.z, a1.z); a1.w = fmaf(xx, w1v.w, a1.w);
-                    }
-                    o[g * 4 + 0] = relu_pack_bf16x2(a0.x, a0.y); o[g * 4 + 1] = relu_pack_bf16x2(a0.z, a0.w);
-                    o[g * 4 + 2] = relu_pack_bf16x2(a1.x, a1.y); o[g * 4 + 3] = relu_pack_bf16x2(a1.z, a1.w);
-                }
-                tmem_st16(tl + kColA1 + half * 16, o);
-                P2_PUBLISH(&s.act_ready);
-                AL3D_TSE();
-            }
-            load_x(item + gridDim.x, xv);                              // prefetch the next tile's point
-            if (item + (int)gridDim.x < p.n_items) {
-                // ... and its per-object bias into the other buffer: nobody reads gb[par ^ 1] during this tile,
+            const int next_item = item + (int)gridDim.x;
+            const bool has_next = next_item < p.n_items;
+            if (has_next) {
+                // the next tile's per-object bias goes into the other buffer: nobody reads gb[par ^ 1] during this tile,
                 // and the bar.sync of the logits epilogue below orders these writes before the next tile's reads
-                const int nb = (item + (int)gridDim.x) / p.tiles_per_obj;
+                const int nb = next_item / p.tiles_per_obj;
                 for (int i = etid; i < 512; i += kEpiThreads) s.gb[par ^ 1][i] = __ldg(p.gbias + (int64_t)nb * 512 + i);
-            }
-            // ---- conv2 epilogue: D1b[2] -> A2
-            if (!mbar_wait(&s.acc_ready, acc_phase, 0xB100)) goto done;
-            AL3D_TSE();
-            acc_phase ^= 1; tc_fence_after();
-            {
-                uint32_t v[32], o[16];
-                tmem_ld32(tl + kColD1 + 128 + half * 32, v);
-                tmem_ld_wait();
-                pack_act32(v, s.b2 + half * 32, o);
-                tmem_st16(tl + kColA2 + half * 16, o);
-                P2_PUBLISH(&s.act_ready);
-                AL3D_TSE();
             }
             // ---- dconv1 chunk epilogues, in place
 #pragma unroll
@@ -773,9 +793,9 @@ seg_pass2_kernel(const Pass2Params p)
                 AL3D_TSE();
             }
             // ---- dconv2 epilogue: D2 -> A3 in place (this thread: 128 columns in two batches)
-            if (!mbar_wait(&s.acc_ready, acc_phase, 0xB101)) goto done;
+            if (!mbar_wait(&s.acc_t, acct_phase, 0xB101)) goto done;
             AL3D_TSE();
-            acc_phase ^= 1; tc_fence_after();
+            acct_phase ^= 1; tc_fence_after();
 #pragma unroll
             for (int bt = 0; bt < 2; ++bt) {
                 uint32_t v0[32], v1[32], o0[16], o1[16];
@@ -789,12 +809,15 @@ seg_pass2_kernel(const Pass2Params p)
                 tmem_st16(dst, o0);
                 tmem_st16(dst + 16, o1);
             }
-            P2_PUBLISH(&s.act_ready);
+            P2_PUBLISH(&s.act_t);
+            AL3D_TSE();
+            // ---- while dconv3 runs: conv1 of the NEXT tile (A1 lives at [480,512), free since the chunk MMAs finished)
+            if (has_next) front_conv1(next_item + (int)gridDim.x);
             AL3D_TSE();
             // ---- dconv3 epilogue: D3 -> A4 in place (64 columns)
-            if (!mbar_wait(&s.acc_ready, acc_phase, 0xB102)) goto done;
+            if (!mbar_wait(&s.acc_t, acct_phase, 0xB102)) goto done;
             AL3D_TSE();
-            acc_phase ^= 1; tc_fence_after();
+            acct_phase ^= 1; tc_fence_after();
             {
                 uint32_t v0[32], v1[32], o0[16], o1[16];
                 const uint32_t src = tl + kColD3 + half * 64;
@@ -805,15 +828,18 @@ seg_pass2_kernel(const Pass2Params p)
                 pack_act32(v1, s.bd3 + half * 64 + 32, o1);
                 tmem_st16(src, o0);
                 tmem_st16(src + 16, o1);
-                P2_PUBLISH(&s.act_ready);
+                P2_PUBLISH(&s.act_t);
                 AL3D_TSE();
             }
+            // ---- while dconv4 runs: conv2 epilogue of the NEXT tile (D1b[2] -> A2 at [448,480))
+            if (has_next) { if (!front_conv2()) goto done; }
+            AL3D_TSE();
             // ---- dconv4 epilogue: bias + ReLU in fp32, then the 128 -> 2 layer, logits and mask.
             //      Each half reduces 64 channels; the upper half hands its partial sums over in smem and the
             //      lower half adds them in a fixed order (deterministic).
-            if (!mbar_wait(&s.acc_ready, acc_phase, 0xB103)) goto done;
+            if (!mbar_wait(&s.acc_t, acct_phase, 0xB103)) goto done;
             AL3D_TSE();
-            acc_phase ^= 1; tc_fence_after();
+            acct_phase ^= 1; tc_fence_after();
             {
                 uint32_t v0[32], v1[32];
                 const int c0 = half * 64;
@@ -898,28 +924,6 @@ struct Pass1Smem {
     uint64_t last_full[2], last_empty[2];
     uint32_t tmem_base;
 };
-
-// conv1 on CUDA cores for 32 output channels starting at ch0 -> 16 packed bf16x2 words
-__device__ __forceinline__ void conv1_pack32(const float (&xv)[8], int c_in, const float *w_t, const float *bias, int ch0,
-                                             uint32_t (&o)[16])
-{
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        float4 a0 = *reinterpret_cast<const float4 *>(bias + ch0 + g * 8);
-        float4 a1 = *reinterpret_cast<const float4 *>(bias + ch0 + g * 8 + 4);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            if (c >= c_in) break;
-            const float4 w0v = *reinterpret_cast<const float4 *>(w_t + c * 64 + ch0 + g * 8);
-            const float4 w1v = *reinterpret_cast<const float4 *>(w_t + c * 64 + ch0 + g * 8 + 4);
-            const float xx = xv[c];
-            a0.x = fmaf(xx, w0v.x, a0.x); a0.y = fmaf(xx, w0v.y, a0.y); a0.z = fmaf(xx, w0v.z, a0.z); a0.w = fmaf(xx, w0v.w, a0.w);
-            a1.x = fmaf(xx, w1v.x, a1.x); a1.y = fmaf(xx, w1v.y, a1.y); a1.z = fmaf(xx, w1v.z, a1.z); a1.w = fmaf(xx, w1v.w, a1.w);
-        }
-        o[g * 4 + 0] = relu_pack_bf16x2(a0.x, a0.y); o[g * 4 + 1] = relu_pack_bf16x2(a0.z, a0.w);
-        o[g * 4 + 2] = relu_pack_bf16x2(a1.x, a1.y); o[g * 4 + 3] = relu_pack_bf16x2(a1.z, a1.w);
-    }
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 seg_pass1_kernel(const Pass1Params p)
