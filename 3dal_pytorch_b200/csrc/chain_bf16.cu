@@ -210,6 +210,63 @@ umma_selftest_ts_kernel(const float *__restrict__ a, const uint8_t *__restrict__
     if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
 }
 
+// CTA-pair variant (cluster of 2, cta_group::2): D(256 x N) = A(256 x K) * B(N x K)^T.  CTA r stages rows
+// [128r, 128r+128) of A in its TMEM and rows [r*N/2, (r+1)*N/2) of B (KP-packed, N/2 rows) in its shared memory;
+// the leader issues the M = 256 MMAs; each CTA reads back its 128 rows of D.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+umma_selftest_pair_kernel(const float *__restrict__ a, const uint8_t *__restrict__ b_kp_halves, int N, int K, float *__restrict__ d)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t rank = cluster_ctarank();
+    const int half_bytes = (N / 2) * K * 2;
+    const uint8_t *src = b_kp_halves + (size_t)rank * half_bytes;
+    for (int i = threadIdx.x * 16; i < half_bytes; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(smem + i) = *reinterpret_cast<const uint4 *>(src + i);
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc_pair<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int row = threadIdx.x;
+    const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
+    const float *arow = a + (size_t)(rank * 128 + row) * K;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = pack_bf16x2(arow[k0 + 2 * i], arow[k0 + 2 * i + 1]);
+        tmem_st16(tmem + lane_addr + 256 + k0 / 2, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                         // both CTAs' operands and barriers are ready
+    tc_fence_after();
+    if (rank == 0 && threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(256, N);
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            const uint64_t db = make_desc(smem_u32(smem) + (k0 / 8) * (N / 2) * 16, N / 2);
+            mma_bf16_ts_pair(tmem, tmem + 256 + k0 / 2, db, idesc, k0 > 0 ? 1u : 0u);
+        }
+        mma_commit_pair(&bar, 0x3);
+    }
+    mbar_wait(&bar, 0, 0xE003);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (c0 + i < N) d[(size_t)(rank * 128 + row) * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (threadIdx.x < 32) tmem_dealloc_pair<512>(tmem);
+}
+
 // ================================================================================================
 // chain_max_kernel
 // ================================================================================================
@@ -1215,6 +1272,17 @@ extern "C" int al3d_umma_selftest_ts(const float *a, const void *b_kp, int N, in
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_selftest_ts_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, (const uint8_t *)b_kp, N, K, d_out);
     AL3D_CHECK_LAUNCH("umma_selftest_ts_kernel");
+    return 0;
+}
+
+extern "C" int al3d_umma_selftest_pair(const float *a, const void *b_kp_halves, int N, int K, float *d_out, void *stream)
+{
+    AL3D_CHECK_ARG(a && b_kp_halves && d_out, "al3d_umma_selftest_pair: null pointer");
+    AL3D_CHECK_ARG(N >= 32 && N <= 256 && N % 32 == 0 && K >= 32 && K % 32 == 0 && K <= 512, "al3d_umma_selftest_pair: bad N=%d K=%d", N, K);
+    const size_t smem = (size_t)(N / 2) * K * 2;
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_pair_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(a, (const uint8_t *)b_kp_halves, N, K, d_out);
+    AL3D_CHECK_LAUNCH("umma_selftest_pair_kernel");
     return 0;
 }
 

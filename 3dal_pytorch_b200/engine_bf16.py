@@ -240,3 +240,15 @@ def umma_selftest_ts(a, b):
                "umma_selftest_ts")
     check_abort("umma_selftest_ts_kernel")
     return d
+
+
+def umma_selftest_pair(a, b):
+    """CTA-pair MMA check: a (256,K), b (N,K) -> (256,N) via cta_group::2 (B split in two N/2-row halves)."""
+    N, K = b.shape
+    d = torch.empty((256, N), device=a.device, dtype=torch.float32)
+    bk = torch.cat([kp_pack(b[: N // 2]), kp_pack(b[N // 2:])]).contiguous()
+    a = a.contiguous().float()
+    _lib.check(_lib.lib().al3d_umma_selftest_pair(a.data_ptr(), bk.data_ptr(), N, K, d.data_ptr(), ops._stream()),
+               "umma_selftest_pair")
+    check_abort("umma_selftest_pair_kernel")
+    return d

@@ -240,6 +240,9 @@ int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, int64_t sb,
 int al3d_umma_selftest(const void *a_kp, const void *b_kp, int N, int K, float *d_out, int swap_lbo_sbo, void *stream);
 /* Same product with A (128,K) fp32 row-major packed to bf16 and staged in TMEM by the kernel (A-from-TMEM MMA). */
 int al3d_umma_selftest_ts(const float *a, const void *b_kp, int N, int K, float *d_out, void *stream);
+/* CTA-pair (cluster of 2, cta_group::2) variant: a (256,K) fp32, b_kp_halves = two KP-packed halves of B (N/2 rows each),
+ * d_out (256,N).  Checks the 2-SM MMA conventions. */
+int al3d_umma_selftest_pair(const float *a, const void *b_kp_halves, int N, int K, float *d_out, void *stream);
 
 /* Reads (and clears) the device-side watchdog code: non-zero means a tensor-core kernel gave up on
  * an mbarrier wait (protocol bug) and its outputs are invalid.  Synchronises the device. */

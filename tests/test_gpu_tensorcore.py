@@ -38,6 +38,16 @@ def test_umma_selftest_a_from_tmem(N, K):
     assert rel_err(d.cpu(), ref.cpu()) < 1e-5, rel_err(d.cpu(), ref.cpu())
 
 
+@pytest.mark.parametrize("N,K", [(64, 64), (128, 64), (128, 128), (256, 256)])
+def test_umma_selftest_cta_pair(N, K):
+    torch.manual_seed(N * 1000 + K + 2)
+    a = torch.randn(256, K, device=DEV)
+    b = torch.randn(N, K, device=DEV)
+    ref = a.to(torch.bfloat16).float() @ b.to(torch.bfloat16).float().t()
+    d = eb.umma_selftest_pair(a, b)
+    assert rel_err(d.cpu(), ref.cpu()) < 1e-5, rel_err(d.cpu(), ref.cpu())
+
+
 def _dev(fw):
     return {k: (w.to(DEV), b.to(DEV)) for k, (w, b) in fw.items()}
 
