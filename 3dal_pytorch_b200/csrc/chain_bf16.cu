@@ -522,7 +522,7 @@ struct Pass2Params {
     const float *gbias;                // (bs, 512) per-object dconv1 bias (global-feature half + folded BN bias)
     const float *bd2, *bd3, *bd4;      // dconv2-4 biases (256),(128),(128)
     const float *w5, *b5;              // dconv5 fp32 (2,128), (2)
-    const uint8_t *wstream;            // 31 packed blocks (16 KB slots), consumption order
+    const uint8_t *wstream;            // two per-CTA halves (kP2HalfBytes each) of the 31 packed blocks, tightly packed
     float *logits;                     // (bs, n, 2)
     uint8_t *mask;                     // (bs, n)
     int tiles_per_obj; int n_items;    // items = bs * tiles_per_obj
@@ -534,39 +534,38 @@ struct Pass2Params {
     do { if (p.dbg && blockIdx.x == 0 && it_local < 4 && ts_i < 64)                            \
              p.dbg[((role) * 4 + it_local) * 64 + ts_i++] = clock64(); } while (0)
 
-constexpr int kP2Stages = 3;
 constexpr int kP2Blocks = 31;
-constexpr int kP2ResidentBytes = 163840;
 constexpr uint32_t kColD2 = 0, kColD1 = 256, kColA2 = 448, kColA1 = 480, kColD3 = 256, kColD4 = 0;
+
+// The kernel runs as CTA PAIRS (cluster of 2, tcgen05 cta_group::2): one M = 256 MMA covers the 128-point tiles of
+// both CTAs, and each CTA holds only HALF of every weight block (N/2 rows of B).  That halves the weight bytes
+// per SM -- the per-SM L2 -> smem ingress (~41 B/cycle measured) is what bounded the single-CTA version -- and makes
+// the whole 424 KB weight set fit: 212 KB per CTA stay resident in shared memory for the life of the kernel, so
+// there is no weight streaming at all.
+// Per-tile block list (order of use): 0 conv2 | 1-3 dconv1 chunks 0-2 | 5 groups {dconv2 partial a, b, dconv1 chunk}
+// | 3 groups {dconv2 partial a, b} | 25-28 dconv3 | 29-30 dconv4.  64-row blocks are 8 KB, 128-row blocks 16 KB;
+// a CTA keeps half of each.
+__host__ __device__ constexpr uint32_t p2_block_bytes(int blk)
+{
+    return blk <= 3 ? 8192u : (blk < 19 ? ((blk - 4) % 3 == 2 ? 8192u : 16384u) : 16384u);
+}
+__host__ __device__ constexpr uint32_t p2_half_off(int blk)
+{
+    uint32_t off = 0;
+    for (int i = 0; i < blk; ++i) off += p2_block_bytes(i) / 2;
+    return off;
+}
+constexpr uint32_t kP2HalfBytes = p2_half_off(kP2Blocks);      // 217088 bytes of weights per CTA
 struct Pass2Smem {
-    uint8_t wres[kP2ResidentBytes];    // weight blocks kept for the whole kernel (see p2_resident_off)
-    uint8_t wring[kP2Stages][kStageBytes];
+    uint8_t wres[kP2HalfBytes];        // this CTA's half of every weight block, resident
     float w1_w[64 * 8], w1_b[64], b2[64], gb[2][512], bd2[256], bd3[128], bd4[128], w5[256], b5[2];
     float lpart[2][2 * kTile];         // logits partial sums of the upper column half (double-buffered by tile parity)
-    uint64_t w_full[kP2Stages], w_empty[kP2Stages];
-    uint64_t res_full;
+    uint64_t res_full, res_peer;       // weights landed in this CTA / in the peer (leader only)
     uint64_t act_f, acc_f, act_t, acc_t;   // front stream (conv1 / conv2 of the next tile) and tail stream (dconv2-4)
     uint64_t d1_full[3], d1_act[3];
     uint32_t tmem_base;
 };
-
-// Weight blocks that stay resident in shared memory: every CTA would otherwise re-read all 424 KB of weights
-// from L2 for each 128-point tile, and the chip-wide L2 -> SM throughput (~41 B/cycle/SM measured) is what
-// bounds the kernel.  Resident: conv2, dconv1 chunks 0-2, dconv2 partial 0 (the tile's start-up) and all of
-// dconv3 / dconv4 (the serial tail).  Returns the byte offset in Pass2Smem::wres, or -1 for a streamed block.
-__host__ __device__ constexpr int p2_resident_off(int blk)
-{
-    return blk <= 3 ? blk * 8192 : (blk <= 5 ? 32768 + (blk - 4) * 16384 : (blk >= 25 ? 65536 + (blk - 25) * 16384 : -1));
-}
-
-// bytes of weight block `blk` of the per-tile stream (64-row blocks are 8 KB, 128-row blocks 16 KB)
-__device__ __forceinline__ uint32_t p2_block_bytes(int blk)
-{
-    // 0: conv2; 1-3: d1 chunks 0-2; then 5 groups {P, P, d1}; then 3 groups {P, P}; then dconv3 x4, dconv4 x2
-    if (blk <= 3) return 8192;
-    if (blk < 19) return ((blk - 4) % 3 == 2) ? 8192 : 16384;
-    return 16384;
-}
+static_assert(sizeof(Pass2Smem) + 128 <= 232448, "Pass2Smem exceeds the 227 KB opt-in limit");
 
 // 32 fp32 accumulator columns -> bias + ReLU -> 16 packed bf16x2 words
 __device__ __forceinline__ void pack_act32(const uint32_t (&v)[32], const float *bias, uint32_t (&o)[16])
@@ -611,12 +610,23 @@ __device__ __forceinline__ void mma_ts_k64(uint32_t tmem_d, uint32_t a0, uint32_
         mma_bf16_ts(tmem_d, a[k], make_desc(b_addr + k * 2 * rows_b * 16, rows_b), idesc, (accumulate_first || k > 0) ? 1u : 0u);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// CTA-pair version: M = 256 (128 rows in each CTA's TMEM), B = this block's rows split over the two CTAs
+__device__ __forceinline__ void mma_pair_k64(uint32_t tmem_d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                             uint32_t b_addr, uint32_t rows_half, uint32_t idesc, bool accumulate_first)
+{
+    const uint32_t a[4] = {a0, a1, a2, a3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        mma_bf16_ts_pair(tmem_d, a[k], make_desc(b_addr + k * 2 * rows_half * 16, rows_half), idesc, (accumulate_first || k > 0) ? 1u : 0u);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 seg_pass2_kernel(const Pass2Params p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Pass2Smem &s = *reinterpret_cast<Pass2Smem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();            // 0 = leader (issues the pair's MMAs), 1 = peer
 
     for (int i = threadIdx.x; i < 64 * 8; i += kThreads) s.w1_w[i] = p.w1_w[i];
     for (int i = threadIdx.x; i < 64; i += kThreads) { s.w1_b[i] = p.w1_b[i]; s.b2[i] = p.b2[i]; }
@@ -624,143 +634,115 @@ seg_pass2_kernel(const Pass2Params p)
     for (int i = threadIdx.x; i < 128; i += kThreads) { s.bd3[i] = p.bd3[i]; s.bd4[i] = p.bd4[i]; }
     if (threadIdx.x < 2) s.b5[threadIdx.x] = p.b5[threadIdx.x];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kP2Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
-        mbar_init(&s.res_full, 1);
-        mbar_init(&s.act_f, kEpiThreads); mbar_init(&s.act_t, kEpiThreads);
+        mbar_init(&s.res_full, 1); mbar_init(&s.res_peer, 1);
+        // epilogue -> MMA barriers live in the leader and collect the arrivals of BOTH CTAs' epilogue threads
+        mbar_init(&s.act_f, 2 * kEpiThreads); mbar_init(&s.act_t, 2 * kEpiThreads);
         mbar_init(&s.acc_f, 1); mbar_init(&s.acc_t, 1);
-        for (int i = 0; i < 3; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kEpiThreads); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], 2 * kEpiThreads); }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc<512>(&s.tmem_base);
+    if (warp == 0) tmem_alloc_pair<512>(&s.tmem_base);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                                  // both CTAs' barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
+    // both CTAs of a pair run the same number of rounds; a CTA whose item index is past the end recomputes the last
+    // item without writing anything ("ghost"), so the pair's shared MMA stream never changes shape
+    const int n_rounds = (p.n_items + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ weight producer
+        // ------------------------------------------------------------ weight loader: this CTA's half of every block, once
         if (lane == 0) {
-            mbar_arrive_expect_tx(&s.res_full, kP2ResidentBytes);
-            for (int blk = 0; blk < kP2Blocks; ++blk)
-                if (p2_resident_off(blk) >= 0)
-                    bulk_g2s(s.wres + p2_resident_off(blk), p.wstream + (size_t)blk * kStageBytes, p2_block_bytes(blk), &s.res_full);
-            int stage = 0; uint32_t phase = 0;
-            int it_local = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
-                int ts_i = 0;
-                for (int blk = 0; blk < kP2Blocks; ++blk) {
-                    if (p2_resident_off(blk) >= 0) continue;
-                    if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0xA100 + stage)) goto done;
-                    AL3D_TS(2);
-                    const uint32_t bytes = p2_block_bytes(blk);
-                    mbar_arrive_expect_tx(&s.w_full[stage], bytes);
-                    bulk_g2s(s.wring[stage], p.wstream + (size_t)blk * kStageBytes, bytes, &s.w_full[stage]);
-                    if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
-                }
+            mbar_arrive_expect_tx(&s.res_full, kP2HalfBytes);
+            const uint8_t *src = p.wstream + (size_t)crank * kP2HalfBytes;
+            for (uint32_t off = 0; off < kP2HalfBytes; off += 16384) {
+                const uint32_t bytes = (kP2HalfBytes - off) < 16384u ? (kP2HalfBytes - off) : 16384u;
+                bulk_g2s(s.wres + off, src + off, bytes, &s.res_full);
+            }
+            if (crank != 0) {
+                // tell the leader that the peer's weights are in place
+                if (!mbar_wait(&s.res_full, 0, 0xA1F0)) goto done;
+                mbar_arrive_remote(&s.res_peer, 0);
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        // Two interleaved streams per CTA: the "tail" of tile t (dconv3, dconv4) and the "front" of tile t+1
-        // (conv2), each with its own pair of barriers (act_t/acc_t, act_f/acc_f), so that the next tile's conv1/conv2
-        // are computed while this tile's serial tail is in flight.
-        if (lane == 0) {
-            int stage = 0; uint32_t wphase = 0, actf_phase = 0, actt_phase = 0, d1a_phase[3] = {0, 0, 0};
-            const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128);
-            // weight block `blk` of the tile: resident blocks have a fixed address, streamed ones come from the ring
-#define P2_NEXT_W(blk)                                                                   \
-            uint32_t wb_;                                                                \
-            if (p2_resident_off(blk) >= 0) wb_ = smem_u32(s.wres) + p2_resident_off(blk);  \
-            else {                                                                       \
-                if (!mbar_wait(&s.w_full[stage], wphase, 0xA300 + (blk))) goto done;     \
-                tc_fence_after();                                                        \
-                wb_ = smem_u32(s.wring[stage]);                                          \
-            }                                                                            \
-            AL3D_TS(0);
-#define P2_REL_W(blk)                                                                    \
-            if (p2_resident_off(blk) < 0) {                                              \
-                mma_commit(&s.w_empty[stage]);                                           \
-                if (++stage == kP2Stages) { stage = 0; wphase ^= 1; }                    \
-            }
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        // Two interleaved streams: the "tail" of round r (dconv3, dconv4) and the "front" of round r+1 (conv2), each
+        // with its own pair of barriers, so the next tiles' conv1/conv2 are computed while this round's serial tail is
+        // in flight.  Every MMA is a cta_group::2 instruction covering both CTAs' tiles; every commit is multicast to
+        // both CTAs' barriers.
+        if (lane == 0 && crank == 0) {
+            uint32_t actf_phase = 0, actt_phase = 0, d1a_phase[3] = {0, 0, 0};
+            const uint32_t id64 = make_idesc_bf16(256, 64), id128 = make_idesc_bf16(256, 128);
+            const uint32_t wres = smem_u32(s.wres);
+#define P2_W(blk) (wres + p2_half_off(blk))
 #define P2_WAIT(bar, ph, code)                                                           \
-            if (!mbar_wait(&(bar), ph, code)) goto done;                                 \
+            if (!mbar_wait_cluster(&(bar), ph, code)) goto done;                         \
             AL3D_TS(0);                                                                  \
             ph ^= 1; tc_fence_after();
 #define P2_ISSUE_CONV2()                                                                 \
             {                                                                            \
                 P2_WAIT(s.act_f, actf_phase, 0xA200)                                     \
-                P2_NEXT_W(0)                                                             \
-                mma_ts_k64(tmem + kColD1 + 128, tmem + kColA1, tmem + kColA1 + 8, tmem + kColA1 + 16, tmem + kColA1 + 24, wb_, 64, id64, false); \
-                P2_REL_W(0)                                                              \
-                mma_commit(&s.acc_f);                                                    \
+                mma_pair_k64(tmem + kColD1 + 128, tmem + kColA1, tmem + kColA1 + 8, tmem + kColA1 + 16, tmem + kColA1 + 24, P2_W(0), 32, id64, false); \
+                mma_commit_pair(&s.acc_f, 0x3);                                          \
             }
-            if (!mbar_wait(&s.res_full, 0, 0xA2FF)) goto done;
+            if (!mbar_wait(&s.res_full, 0, 0xA2FE)) goto done;
+            if (!mbar_wait_cluster(&s.res_peer, 0, 0xA2FF)) goto done;
             tc_fence_after();
             int it_local = 0;
             int ts_i = 0;
-            if ((int)blockIdx.x < p.n_items) P2_ISSUE_CONV2()                 // front of the first tile
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+            if (n_rounds > 0) P2_ISSUE_CONV2()                               // front of the first round
+            for (int r = 0; r < n_rounds; ++r, ++it_local) {
                 ts_i = 0;
                 AL3D_TS(0);
-                const bool has_next = item + (int)gridDim.x < p.n_items;
+                const bool has_next = r + 1 < n_rounds;
                 // dconv1 chunks 0..2: A2 x Wd1[chunk] -> D1b[j]                     (blocks 1..3)
                 P2_WAIT(s.act_f, actf_phase, 0xA201)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    P2_NEXT_W(1 + j)
-                    mma_ts_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, wb_, 64, id64, false);
-                    P2_REL_W(1 + j)
-                    mma_commit(&s.d1_full[j]);
+                    mma_pair_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, P2_W(1 + j), 32, id64, false);
+                    mma_commit_pair(&s.d1_full[j], 0x3);
                 }
 #pragma unroll
                 for (int kc = 0; kc < 8; ++kc) {
                     const int j = kc % 3;
                     const int blk0 = kc < 5 ? 4 + 3 * kc : 19 + 2 * (kc - 5);       // first block of this group
-                    if (!mbar_wait(&s.d1_act[j], d1a_phase[j], 0xA400 + kc)) goto done;
+                    if (!mbar_wait_cluster(&s.d1_act[j], d1a_phase[j], 0xA400 + kc)) goto done;
                     AL3D_TS(0);
                     d1a_phase[j] ^= 1; tc_fence_after();
                     const uint32_t a = tmem + kColD1 + j * 64;        // bf16 image of chunk kc (in place)
 #pragma unroll
-                    for (int nc = 0; nc < 2; ++nc) {
-                        P2_NEXT_W(blk0 + nc)
-                        mma_ts_k64(tmem + kColD2 + nc * 128, a, a + 8, a + 32, a + 40, wb_, 128, id128, kc > 0);
-                        P2_REL_W(blk0 + nc)
-                    }
+                    for (int nc = 0; nc < 2; ++nc)
+                        mma_pair_k64(tmem + kColD2 + nc * 128, a, a + 8, a + 32, a + 40, P2_W(blk0 + nc), 64, id128, kc > 0);
                     if (kc + 3 < 8) {
                         // the MMA pipe executes in issue order, so this overwrite of D1b[j] happens after the
                         // partial sums above have consumed it
-                        P2_NEXT_W(blk0 + 2)
-                        mma_ts_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, wb_, 64, id64, false);
-                        P2_REL_W(blk0 + 2)
-                        mma_commit(&s.d1_full[j]);
+                        mma_pair_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, P2_W(blk0 + 2), 32, id64, false);
+                        mma_commit_pair(&s.d1_full[j], 0x3);
                     }
                 }
-                mma_commit(&s.acc_t);                                      // dconv2 accumulator complete
+                mma_commit_pair(&s.acc_t, 0x3);                            // dconv2 accumulator complete
                 // dconv3: A3 x Wd3 -> D3                                            (blocks 25..28)
                 P2_WAIT(s.act_t, actt_phase, 0xA202)
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb) {
                     const uint32_t a = tmem + kColD2 + (kb >> 1) * 128 + (kb & 1) * 32;
-                    P2_NEXT_W(25 + kb)
-                    mma_ts_k64(tmem + kColD3, a, a + 8, a + 16, a + 24, wb_, 128, id128, kb > 0);
-                    P2_REL_W(25 + kb)
+                    mma_pair_k64(tmem + kColD3, a, a + 8, a + 16, a + 24, P2_W(25 + kb), 64, id128, kb > 0);
                 }
-                mma_commit(&s.acc_t);
-                // front of the next tile: conv2 on its conv1 output (A1 at [480,512) -> D1b[2]; both are free now)
+                mma_commit_pair(&s.acc_t, 0x3);
+                // front of the next round: conv2 on its conv1 output (A1 at [480,512) -> D1b[2]; both are free now)
                 if (has_next) P2_ISSUE_CONV2()
                 // dconv4: A4 x Wd4 -> D4 (over the dead A3 at columns 0..127)       (blocks 29, 30)
                 P2_WAIT(s.act_t, actt_phase, 0xA203)
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
                     const uint32_t a = tmem + kColD3 + kb * 64;
-                    P2_NEXT_W(29 + kb)
-                    mma_ts_k64(tmem + kColD4, a, a + 8, a + 16, a + 24, wb_, 128, id128, kb > 0);
-                    P2_REL_W(29 + kb)
+                    mma_pair_k64(tmem + kColD4, a, a + 8, a + 16, a + 24, P2_W(29 + kb), 64, id128, kb > 0);
                 }
-                mma_commit(&s.acc_t);
+                mma_commit_pair(&s.acc_t, 0x3);
             }
-#undef P2_NEXT_W
-#undef P2_REL_W
+#undef P2_W
 #undef P2_WAIT
 #undef P2_ISSUE_CONV2
         }
@@ -775,11 +757,13 @@ seg_pass2_kernel(const Pass2Params p)
         int ts_i = 0;
         const bool ts_on = (threadIdx.x == 64);
 #define AL3D_TSE() do { if (ts_on) AL3D_TS(1); } while (0)
-#define P2_PUBLISH(bar) do { tmem_st_wait(); tc_fence_before(); mbar_arrive(bar); } while (0)
+        // the epilogue -> MMA barriers are the leader's: the peer CTA arrives on them through the cluster address space
+#define P2_PUBLISH(bar) do { tmem_st_wait(); tc_fence_before(); if (crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); } while (0)
         // software prefetch of the tile's input point (hides the global-memory latency behind the previous tile)
         float xv[8];
         auto load_x = [&](int item, float (&dst)[8]) {
-            if (item < p.n_items) {
+            if (item > p.n_items - 1) item = p.n_items - 1;        // ghost round: recompute the last item
+            {
                 const int b = item / p.tiles_per_obj, t = item % p.tiles_per_obj;
                 int pidx = t * kTile + row;
                 if (pidx > p.n - 1) pidx = p.n - 1;
@@ -808,29 +792,32 @@ seg_pass2_kernel(const Pass2Params p)
             P2_PUBLISH(&s.act_f);
             return true;
         };
-        if ((int)blockIdx.x < p.n_items) {
+        if (n_rounds > 0) {
             // first tile of this CTA: its per-object dconv1 bias and its front are not hidden behind a previous tile
-            const int b0 = blockIdx.x / p.tiles_per_obj;
+            const int b0 = min((int)blockIdx.x, p.n_items - 1) / p.tiles_per_obj;
             for (int i = etid; i < 512; i += kEpiThreads) s.gb[0][i] = __ldg(p.gbias + (int64_t)b0 * 512 + i);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             load_x(blockIdx.x, xv);
             front_conv1(blockIdx.x + gridDim.x);
             if (!front_conv2()) goto done;
         }
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it_local) {
+        for (int r = 0; r < n_rounds; ++r, ++it_local) {
             ts_i = 0;
             AL3D_TSE();
+            const int item_raw = (int)blockIdx.x + r * (int)gridDim.x;
+            const bool ghost = item_raw >= p.n_items;
+            const int item = ghost ? p.n_items - 1 : item_raw;
             const int b = item / p.tiles_per_obj, t = item % p.tiles_per_obj;
             const int pidx_raw = t * kTile + row;
-            const bool valid = pidx_raw < p.n;
-            const int pidx = valid ? pidx_raw : p.n - 1;
+            const bool valid = !ghost && pidx_raw < p.n;
+            const int pidx = pidx_raw < p.n ? pidx_raw : p.n - 1;
             const int par = it_local & 1;
-            const int next_item = item + (int)gridDim.x;
-            const bool has_next = next_item < p.n_items;
+            const int next_item = item_raw + (int)gridDim.x;
+            const bool has_next = r + 1 < n_rounds;                // uniform over the CTA pair
             if (has_next) {
                 // the next tile's per-object bias goes into the other buffer: nobody reads gb[par ^ 1] during this tile,
                 // and the bar.sync of the logits epilogue below orders these writes before the next tile's reads
-                const int nb = next_item / p.tiles_per_obj;
+                const int nb = min(next_item, p.n_items - 1) / p.tiles_per_obj;
                 for (int i = etid; i < 512; i += kEpiThreads) s.gb[par ^ 1][i] = __ldg(p.gbias + (int64_t)nb * 512 + i);
             }
             // ---- dconv1 chunk epilogues, in place
@@ -941,7 +928,8 @@ seg_pass2_kernel(const Pass2Params p)
 done:
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem);
+    cluster_sync_all();                                  // the pair's MMAs touch both CTAs: leave together
+    if (warp == 0) tmem_dealloc_pair<512>(tmem);
 }
 
 
@@ -1394,11 +1382,11 @@ extern "C" int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, 
     const int64_t items = (int64_t)bs * p.tiles_per_obj;
     AL3D_CHECK_ARG(items < (1ll << 31), "al3d_seg_pass2_bf16: too many tiles");
     p.n_items = (int)items;
-    const int grid = std::min(p.n_items, num_sms());
+    int grid = std::min(p.n_items, num_sms());
+    grid = ((grid + 1) / 2) * 2;                         // whole CTA pairs; a ghost CTA recomputes the last tile without output
     const size_t smem = sizeof(Pass2Smem) + 128;
-    static_assert(sizeof(Pass2Smem) + 128 <= 232448, "Pass2Smem exceeds the 227 KB opt-in limit");
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(seg_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    seg_pass2_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    seg_pass2_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);     // __cluster_dims__(2,1,1)
     AL3D_CHECK_LAUNCH("seg_pass2_kernel");
     return 0;
 }

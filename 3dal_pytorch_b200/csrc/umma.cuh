@@ -66,6 +66,31 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, uint32
     return true;
 }
 
+// Same wait with cluster-scope acquire: for barriers whose arrivals come from the peer CTA of a pair.
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity, uint32_t code)
+{
+    const long long t0 = clock64();
+    int spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return true;
+        if ((++spins & 1023) == 0) {
+            if (*(volatile unsigned int *)&g_abort != 0) return false;
+            if (clock64() - t0 > kWaitTimeoutCycles) {
+                atomicCAS(&g_abort, 0u, code);
+                return false;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

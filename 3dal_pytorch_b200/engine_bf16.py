@@ -92,27 +92,32 @@ class SegPack:
     def __init__(self, fw, c_in):
         self.pass1 = ChainPack(fw, ["conv1", "conv2", "conv3", "conv4", "conv5"])
         wd1, wd2, wd3, wd4 = (fw[k][0] for k in ("dconv1", "dconv2", "dconv3", "dconv4"))
-        blocks = [_block(fw["conv2"][0])]
+        mats = [fw["conv2"][0]]                     # weight sub-matrices (rows x 64 K) in the MMA thread's order of use
 
         def d1(c):                     # dconv1 chunk c: 64 output channels x the 64 per-point input channels
-            return [_block(wd1[c * 64:(c + 1) * 64, 0:64])]
+            return [wd1[c * 64:(c + 1) * 64, 0:64]]
 
         def d2(pc):                    # dconv2 partial sum over input channels pc*64..+64, two 128-row halves
-            return [_block(wd2[nc * 128:(nc + 1) * 128, pc * 64:(pc + 1) * 64]) for nc in range(2)]
+            return [wd2[nc * 128:(nc + 1) * 128, pc * 64:(pc + 1) * 64] for nc in range(2)]
 
-        # issue order of the MMA thread in seg_pass2_kernel
-        blocks += d1(0) + d1(1) + d1(2)
+        mats += d1(0) + d1(1) + d1(2)
         for kc in range(8):
-            blocks += d2(kc)
+            mats += d2(kc)
             if kc + 3 < 8:
-                blocks += d1(kc + 3)
-        blocks += [_block(wd3[:, kb * 64:(kb + 1) * 64]) for kb in range(4)]
-        blocks += [_block(wd4[:, kb * 64:(kb + 1) * 64]) for kb in range(2)]
-        assert len(blocks) == 31
+                mats += d1(kc + 3)
+        mats += [wd3[:, kb * 64:(kb + 1) * 64] for kb in range(4)]
+        mats += [wd4[:, kb * 64:(kb + 1) * 64] for kb in range(2)]
+        assert len(mats) == 31
+        self.p2_mats = mats
+        # the kernel runs as CTA pairs (cta_group::2): CTA r keeps rows [r*R/2, (r+1)*R/2) of every block, KP-packed,
+        # tightly concatenated; the two per-CTA images follow each other
+        halves = [torch.cat([kp_pack(m[r * (m.shape[0] // 2):(r + 1) * (m.shape[0] // 2)]) for m in mats]) for r in range(2)]
+        assert halves[0].numel() * 2 == 217088
+        wstream2 = torch.cat(halves).contiguous()
         self.t = {"w1_w": _pad8(fw["conv1"][0]), "w1_b": fw["conv1"][1].contiguous(), "b2": fw["conv2"][1].contiguous(),
                   "bd2": fw["dconv2"][1].contiguous(), "bd3": fw["dconv3"][1].contiguous(),
                   "bd4": fw["dconv4"][1].contiguous(), "w5": fw["dconv5"][0].contiguous(),
-                  "b5": fw["dconv5"][1].contiguous(), "wstream": torch.cat(blocks).contiguous()}
+                  "b5": fw["dconv5"][1].contiguous(), "wstream": wstream2}
         s = Pass2WeightsStruct()
         s.c_in = c_in
         for k, v in self.t.items():

@@ -225,7 +225,7 @@ typedef struct al3d_pass2_weights {
     const float *b2;               /* conv2 bias (64)                                               */
     const float *bd2, *bd3, *bd4;  /* dconv2-4 biases (256),(128),(128)                             */
     const float *w5, *b5;          /* dconv5 fp32 (2,128), (2)                                      */
-    const void  *wstream;          /* 31 packed bf16 blocks: conv2, dconv1/dconv2 interleaved, dconv3, dconv4 */
+    const void  *wstream;          /* two per-CTA halves of the 31 packed bf16 blocks (conv2, dconv1/dconv2 interleaved, dconv3, dconv4) */
 } al3d_pass2_weights;
 
 /* Second half of PointNetInstanceSeg.forward (tools/static_model.py:286-295) + the mask of

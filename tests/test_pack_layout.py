@@ -55,30 +55,39 @@ def test_pass2_stream_order_matches_kernel_schedule():
     sd = synth.random_state_dict("dynamic", seed=2)
     fw = fold_state_dict(sd, "ins_seg", spec.seg_layers(4))
     pack = eb.pack_seg(fw, 4)
-    blocks = _blocks(pack.t["wstream"])
-    assert blocks.shape[0] == 31
     bf = lambda n: fw[n][0].to(torch.bfloat16).float()
     wd1, wd2, wd3, wd4 = bf("dconv1"), bf("dconv2"), bf("dconv3"), bf("dconv4")
-    expect = [("conv2", bf("conv2"), 64)]
-    d1 = lambda c: [("d1_%d" % c, wd1[c * 64:(c + 1) * 64, :64], 64)]
-    d2 = lambda pc: [("d2_%d_%d" % (pc, nc), wd2[nc * 128:(nc + 1) * 128, pc * 64:(pc + 1) * 64], 128) for nc in range(2)]
-    # issue order of the MMA thread in seg_pass2_kernel
+    expect = [("conv2", bf("conv2"))]
+    d1 = lambda c: [("d1_%d" % c, wd1[c * 64:(c + 1) * 64, :64])]
+    d2 = lambda pc: [("d2_%d_%d" % (pc, nc), wd2[nc * 128:(nc + 1) * 128, pc * 64:(pc + 1) * 64]) for nc in range(2)]
+    # order of use by the MMA thread in seg_pass2_kernel
     expect += d1(0) + d1(1) + d1(2)
     for kc in range(8):
         expect += d2(kc)
         if kc + 3 < 8:
             expect += d1(kc + 3)
-    expect += [("d3_%d" % kb, wd3[:, kb * 64:(kb + 1) * 64], 128) for kb in range(4)]
-    expect += [("d4_%d" % kb, wd4[:, kb * 64:(kb + 1) * 64], 128) for kb in range(2)]
+    expect += [("d3_%d" % kb, wd3[:, kb * 64:(kb + 1) * 64]) for kb in range(4)]
+    expect += [("d4_%d" % kb, wd4[:, kb * 64:(kb + 1) * 64]) for kb in range(2)]
     assert len(expect) == 31
-    # block sizes the producer warp copies (p2_block_bytes in csrc/chain_bf16.cu)
+
+    # p2_block_bytes / p2_half_off of csrc/chain_bf16.cu
     def block_bytes(blk):
         if blk <= 3:
             return 8192
         if blk < 19:
             return 8192 if (blk - 4) % 3 == 2 else 16384
         return 16384
-    assert [rows * 128 for _, _, rows in expect] == [block_bytes(i) for i in range(31)]
-    for i, (name, w, rows) in enumerate(expect):
-        assert torch.equal(kp_unpack(blocks[i][: rows * 64].float(), rows, 64), w), name
+    assert [w.shape[0] * 128 for _, w in expect] == [block_bytes(i) for i in range(31)]
+    half_total = sum(block_bytes(i) // 2 for i in range(31))
+    assert half_total == 217088
+    stream = pack.t["wstream"]
+    assert stream.numel() * 2 == 2 * half_total
+    # CTA r of a pair holds rows [r*R/2, (r+1)*R/2) of every block (cta_group::2 splits B's N rows over the two CTAs)
+    for r in range(2):
+        off = r * half_total // 2
+        for i, (name, w) in enumerate(expect):
+            rows = w.shape[0] // 2
+            got = kp_unpack(stream[off: off + rows * 64].float(), rows, 64)
+            assert torch.equal(got, w[r * rows:(r + 1) * rows]), (name, r)
+            off += rows * 64
     assert pack.struct.c_in == 4 and pack.w_glob.shape == (512, 1024)
