@@ -72,7 +72,7 @@ def test_chain_maxpool_trunks(kind, block, table, C, n, bs):
     assert torch.equal(got, got2)
 
 
-@pytest.mark.parametrize("C,n,bs", [(3, 4096, 2), (4, 5120, 2), (3, 1000, 3), (3, 77, 40), (3, 300, 310)])
+@pytest.mark.parametrize("C,n,bs", [(3, 4096, 2), (4, 5120, 2), (3, 1000, 3), (3, 77, 40), (3, 300, 310), (3, 100, 1), (3, 129, 1)])
 def test_seg_bf16_against_numerics_model(C, n, bs):
     kind = "dynamic" if C == 4 else "static_one"
     sd = synth.random_state_dict(kind, seed=6)
