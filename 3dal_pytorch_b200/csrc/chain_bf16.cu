@@ -267,6 +267,61 @@ umma_selftest_pair_kernel(const float *__restrict__ a, const uint8_t *__restrict
     if (threadIdx.x < 32) tmem_dealloc_pair<512>(tmem);
 }
 
+// CTA-pair variant with BOTH operands in shared memory (the transposed conv5 of seg_pass1_kernel): CTA r stages rows
+// [128r, 128r+128) of A as a 128-row KP tile, and its N/2 = 64 rows of B as rows [64,128) of a 128-row KP tile (a
+// sub-tile descriptor: plane stride 2048 B), exactly how the kernel addresses half of a tile's conv4 output.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+umma_selftest_pair_ss_kernel(const uint8_t *__restrict__ a_kp_halves, const uint8_t *__restrict__ b_kp_halves, int K, float *__restrict__ d)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t rank = cluster_ctarank();
+    const int N = 128;
+    uint8_t *sa = smem, *sbt = smem + 128 * K * 2;               // A tile | B container tile (128 rows)
+    const int a_bytes = 128 * K * 2;
+    for (int i = threadIdx.x * 16; i < a_bytes; i += blockDim.x * 16)
+        *reinterpret_cast<uint4 *>(sa + i) = *reinterpret_cast<const uint4 *>(a_kp_halves + (size_t)rank * a_bytes + i);
+    // B half: 64 rows x K, KP-packed with 64-row planes in global memory -> rows 64..127 of the 128-row container
+    const uint8_t *bsrc = b_kp_halves + (size_t)rank * 64 * K * 2;
+    for (int i = threadIdx.x; i < (K / 8) * 64; i += blockDim.x) {
+        const int plane = i / 64, r = i % 64;
+        *reinterpret_cast<uint4 *>(sbt + plane * 2048 + (64 + r) * 16) = *reinterpret_cast<const uint4 *>(bsrc + plane * 1024 + r * 16);
+    }
+    fence_proxy_async_smem();
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc_pair<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (rank == 0 && threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(256, N);
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            const uint64_t da = make_desc(smem_u32(sa) + (k0 / 8) * 2048, 128);
+            const uint64_t db = make_desc_lbo(smem_u32(sbt) + 64 * 16 + (k0 / 8) * 2048, 2048);
+            mma_bf16_ss_pair(tmem, da, db, idesc, k0 > 0 ? 1u : 0u);
+        }
+        mma_commit_pair(&bar, 0x3);
+    }
+    mbar_wait(&bar, 0, 0xE004);
+    tc_fence_after();
+    const int row = threadIdx.x;
+    const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[(size_t)(rank * 128 + row) * N + c0 + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (threadIdx.x < 32) tmem_dealloc_pair<512>(tmem);
+}
+
 // ================================================================================================
 // chain_max_kernel
 // ================================================================================================
@@ -1271,6 +1326,17 @@ extern "C" int al3d_umma_selftest_pair(const float *a, const void *b_kp_halves, 
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_selftest_pair_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(a, (const uint8_t *)b_kp_halves, N, K, d_out);
     AL3D_CHECK_LAUNCH("umma_selftest_pair_kernel");
+    return 0;
+}
+
+extern "C" int al3d_umma_selftest_pair_ss(const void *a_kp_halves, const void *b_kp_halves, int K, float *d_out, void *stream)
+{
+    AL3D_CHECK_ARG(a_kp_halves && b_kp_halves && d_out, "al3d_umma_selftest_pair_ss: null pointer");
+    AL3D_CHECK_ARG(K >= 16 && K % 16 == 0 && K <= 256, "al3d_umma_selftest_pair_ss: bad K=%d", K);
+    const size_t smem = (size_t)2 * 128 * K * 2;
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_pair_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_pair_ss_kernel<<<2, 128, smem, (cudaStream_t)stream>>>((const uint8_t *)a_kp_halves, (const uint8_t *)b_kp_halves, K, d_out);
+    AL3D_CHECK_LAUNCH("umma_selftest_pair_ss_kernel");
     return 0;
 }
 

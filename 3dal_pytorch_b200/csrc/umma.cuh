@@ -190,6 +190,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t rows, boo
     return d;                                   // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE (0)
 }
 
+// Descriptor of a sub-tile of rows inside a KP tile whose planes are `plane_bytes` apart (e.g. 64 rows of a 128-row tile).
+__device__ __forceinline__ uint64_t make_desc_lbo(uint32_t saddr, uint32_t plane_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((plane_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((128u >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N)
 {
@@ -229,6 +240,16 @@ __device__ __forceinline__ void mma_bf16_ts_pair(uint32_t tmem_d, uint32_t tmem_
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// CTA-pair MMA with both operands in shared memory: each CTA supplies 128 rows of A and N/2 rows of B (same offsets).
+__device__ __forceinline__ void mma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // commit for CTA-pair MMAs: arrives on the mbarrier at the same offset in every CTA of cta_mask

@@ -257,3 +257,15 @@ def umma_selftest_pair(a, b):
                "umma_selftest_pair")
     check_abort("umma_selftest_pair_kernel")
     return d
+
+
+def umma_selftest_pair_ss(a, b):
+    """CTA-pair MMA with both operands in shared memory: a (256,K), b (128,K) -> (256,128)."""
+    K = b.shape[1]
+    d = torch.empty((256, 128), device=a.device, dtype=torch.float32)
+    ak = torch.cat([kp_pack(a[:128]), kp_pack(a[128:])]).contiguous()
+    bk = torch.cat([kp_pack(b[:64]), kp_pack(b[64:])]).contiguous()
+    _lib.check(_lib.lib().al3d_umma_selftest_pair_ss(ak.data_ptr(), bk.data_ptr(), K, d.data_ptr(), ops._stream()),
+               "umma_selftest_pair_ss")
+    check_abort("umma_selftest_pair_ss_kernel")
+    return d

@@ -243,6 +243,9 @@ int al3d_umma_selftest_ts(const float *a, const void *b_kp, int N, int K, float 
 /* CTA-pair (cluster of 2, cta_group::2) variant: a (256,K) fp32, b_kp_halves = two KP-packed halves of B (N/2 rows each),
  * d_out (256,N).  Checks the 2-SM MMA conventions. */
 int al3d_umma_selftest_pair(const float *a, const void *b_kp_halves, int N, int K, float *d_out, void *stream);
+/* CTA-pair variant with both operands in shared memory, N = 128: a_kp_halves = two KP tiles of 128 rows, b_kp_halves =
+ * two KP tiles of 64 rows (staged by the kernel as a sub-tile of a 128-row tile).  d_out (256,128). */
+int al3d_umma_selftest_pair_ss(const void *a_kp_halves, const void *b_kp_halves, int K, float *d_out, void *stream);
 
 /* Reads (and clears) the device-side watchdog code: non-zero means a tensor-core kernel gave up on
  * an mbarrier wait (protocol bug) and its outputs are invalid.  Synchronises the device. */

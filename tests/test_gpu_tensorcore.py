@@ -48,6 +48,16 @@ def test_umma_selftest_cta_pair(N, K):
     assert rel_err(d.cpu(), ref.cpu()) < 1e-5, rel_err(d.cpu(), ref.cpu())
 
 
+@pytest.mark.parametrize("K", [64, 128])
+def test_umma_selftest_cta_pair_ss(K):
+    torch.manual_seed(K + 3)
+    a = torch.randn(256, K, device=DEV)
+    b = torch.randn(128, K, device=DEV)
+    ref = a.to(torch.bfloat16).float() @ b.to(torch.bfloat16).float().t()
+    d = eb.umma_selftest_pair_ss(a, b)
+    assert rel_err(d.cpu(), ref.cpu()) < 1e-5, rel_err(d.cpu(), ref.cpu())
+
+
 def _dev(fw):
     return {k: (w.to(DEV), b.to(DEV)) for k, (w, b) in fw.items()}
 
