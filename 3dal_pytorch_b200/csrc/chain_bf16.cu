@@ -690,10 +690,11 @@ seg_pass2_kernel(const Pass2Params p)
     if (threadIdx.x < 2) s.b5[threadIdx.x] = p.b5[threadIdx.x];
     if (threadIdx.x == 0) {
         mbar_init(&s.res_full, 1); mbar_init(&s.res_peer, 1);
-        // epilogue -> MMA barriers live in the leader and collect the arrivals of BOTH CTAs' epilogue threads
-        mbar_init(&s.act_f, 2 * kEpiThreads); mbar_init(&s.act_t, 2 * kEpiThreads);
+        // epilogue -> MMA barriers live in the leader and collect one arrival per epilogue WARP of BOTH CTAs (an elected
+        // lane arrives after the warp has synchronised: 8 remote transactions per hand-off instead of 256)
+        mbar_init(&s.act_f, 2 * kEpiThreads / 32); mbar_init(&s.act_t, 2 * kEpiThreads / 32);
         mbar_init(&s.acc_f, 1); mbar_init(&s.acc_t, 1);
-        for (int i = 0; i < 3; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], 2 * kEpiThreads); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], 2 * kEpiThreads / 32); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc_pair<512>(&s.tmem_base);
@@ -813,7 +814,8 @@ seg_pass2_kernel(const Pass2Params p)
         const bool ts_on = (threadIdx.x == 64);
 #define AL3D_TSE() do { if (ts_on) AL3D_TS(1); } while (0)
         // the epilogue -> MMA barriers are the leader's: the peer CTA arrives on them through the cluster address space
-#define P2_PUBLISH(bar) do { tmem_st_wait(); tc_fence_before(); if (crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); } while (0)
+#define P2_PUBLISH(bar) do { tmem_st_wait(); tc_fence_before(); __syncwarp();                                          \
+                             if (lane == 0) { if (crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); } } while (0)
         // software prefetch of the tile's input point (hides the global-memory latency behind the previous tile)
         float xv[8];
         auto load_x = [&](int item, float (&dst)[8]) {
