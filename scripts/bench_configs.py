@@ -2,7 +2,8 @@
   crop      configs[3], crop stage: 200 Waymo-shaped frames x ~180k points x 200 boxes -> achieved HBM GB/s
   dynamic   configs[1]: dynamic model forward, 64 tracks x (5x1024 points + 101 boxes), plus a large batch
   static32  configs[0] on the GPU: static one- and two-box forward, 32 tracks x 4096 points (fp32 and bf16)
-Usage (GPU box): python scripts/bench_configs.py [crop|dynamic|static32|all] [--frames N]"""
+  sweep     configs[3] end to end: crop -> regroup -> track prep -> static model -> decoded boxes
+Usage (GPU box): python scripts/bench_configs.py [crop|sweep|dynamic|static32|all] [--frames N]"""
 import argparse
 import importlib
 import json
@@ -72,6 +73,30 @@ def bench_crop(n_frames):
                       "speedup_vs_cpu_oracle": cpu_s_per_frame * n_frames / (ms * 1e-3)}))
 
 
+def bench_sweep(n_frames):
+    """configs[3]: crop -> regroup -> track prep -> seg -> gather -> box head -> decode, inputs resident on the device."""
+    sweep = importlib.import_module("3dal_pytorch_b200.sweep")
+    frames = synth.lidar_frames(n_frames, seed=4)
+    for f in frames:
+        f["points"] = torch.from_numpy(f["points"]).to(DEV)
+    sd = synth.random_state_dict("static_one", seed=synth.REFERENCE_SEED)
+    m = sm.StaticModelOneBoxEst().to(DEV).eval()
+    m.load_state_dict(sd)
+    m.precision = "bf16"
+    sw = sweep.StaticSweep(m)
+    out = sw.run(frames)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    iters = 3
+    for _ in range(iters):
+        out = sw.run(frames)
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / iters
+    print(json.dumps({"bench": "sweep", "frames": n_frames, "tracks": int(out["boxes"].shape[0]),
+                      "points_per_frame": int(frames[0]["points"].shape[0]), "ms_wall_incl_host_plane_setup": ms,
+                      "frames_per_s": n_frames / (ms * 1e-3), "boxes_per_s": n_frames * 200 / (ms * 1e-3)}))
+
+
 def _calibrated(kind, cls, pts, aux):
     sd = synth.random_state_dict(kind, seed=synth.REFERENCE_SEED)
     m = cls().to(DEV).eval()
@@ -119,6 +144,8 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.what in ("crop", "all"):
         bench_crop(a.frames)
+    if a.what in ("sweep", "all"):
+        bench_sweep(a.frames)
     if a.what in ("dynamic", "all"):
         bench_dynamic()
     if a.what in ("static32", "all"):
