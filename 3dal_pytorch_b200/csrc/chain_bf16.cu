@@ -1280,6 +1280,306 @@ done:
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// ================================================================================================
+// trunk_pair_kernel -- the box-head / embedding trunks: conv1 (CUDA cores) -> conv2 -> conv3 -> conv4 + max over points
+// (tools/static_model.py:330-334, tools/dynamic_model.py:241-245, 278-282), same ideas as seg_pass1_kernel:
+// tiles are processed in PAIRS; conv2 / conv3 read their A operand from TMEM (conv2's output is converted in place);
+// conv3's output of both tiles goes to one 256-row shared-memory operand and conv4 is computed transposed
+// (M = 128 channels, N = 256 points), so every streamed conv4 block serves 256 points and the max over points is a
+// per-thread reduction.  All weights stream through one ring (conv2 / conv3 blocks twice per pair, conv4 once).
+// TMEM (front, one tile at a time): [0,W0/2) A1 | [64,64+M1) D(conv2), its bf16 image in place | [256,256+M2) D(conv3);
+// conv4 then double-buffers 2 x 256 columns.
+// ================================================================================================
+struct TrunkParams {
+    const float *x; int64_t sb, sc, sp; int bs, n; int c_in;
+    const float *w0_w, *w0_b, *mid_b, *last_b;
+    const uint8_t *wstream;            // 16 KB slots: conv2 (k-blocks) | conv3 (row-chunk, k-block) | conv4 (chunk, k-block)
+    float *out;                        // (bs, 512) zero-initialised
+    int splits, n_items;
+};
+
+template <int W0, int M1, int M2>
+struct TrunkCfg {
+    static constexpr int kNkb2 = W0 / 64, kRows2 = M1, kNc3 = M2 / 128, kNkb3 = M1 / 64, kNkb4 = M2 / 64;
+    static constexpr int kFrontBlocks = kNkb2 + kNc3 * kNkb3, kLastBlocks = 4 * kNkb4;
+    static constexpr int kOut3Bytes = (M2 / 8) * 4096;                 // KP tile of 256 rows x M2 channels
+    static constexpr int kStages = (232448 - 1024 - kOut3Bytes - 4096 - (W0 * 9 + M1 + M2) * 4) / kStageBytes;
+    static constexpr uint32_t kColA1 = 0, kColD2 = 64, kColD3 = 256;
+};
+
+template <int W0, int M1, int M2>
+__global__ void __launch_bounds__(kThreads, 1)
+trunk_pair_kernel(const TrunkParams p)
+{
+    using C = TrunkCfg<W0, M1, M2>;
+    constexpr int S = C::kStages;
+    static_assert(S >= 3 && S <= 12, "weight ring depth");
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t *const s_out3 = smem_raw;
+    uint8_t *const s_ring = smem_raw + C::kOut3Bytes;
+    float *const s_w0w = reinterpret_cast<float *>(s_ring + (size_t)S * kStageBytes);
+    float *const s_w0b = s_w0w + W0 * 8;
+    float *const s_b2 = s_w0b + W0;
+    float *const s_b3 = s_b2 + M1;
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(s_b3 + M2);
+    uint64_t *const w_full = bars, *const w_empty = bars + 12;
+    uint64_t *const act = bars + 24, *const acc = bars + 25, *const out3_ready = bars + 26;
+    uint64_t *const last_full = bars + 27, *const last_empty = bars + 29;
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(bars + 31);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < W0 * 8; i += kThreads) s_w0w[i] = p.w0_w[i];
+    for (int i = threadIdx.x; i < W0; i += kThreads) s_w0b[i] = p.w0_b[i];
+    for (int i = threadIdx.x; i < M1 + M2; i += kThreads) s_b2[i] = p.mid_b[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        mbar_init(act, kEpiThreads / 32); mbar_init(acc, 1);
+        mbar_init(out3_ready, 2 * kEpiThreads / 32);
+        for (int i = 0; i < 2; ++i) { mbar_init(&last_full[i], 1); mbar_init(&last_empty[i], kEpiThreads / 32); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int tiles_per_obj = (p.n + kTile - 1) / kTile;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ weight producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            auto push = [&](int blk, uint32_t bytes) -> bool {
+                if (!mbar_wait(&w_empty[stage], phase ^ 1, 0x7100 + stage)) return false;
+                mbar_arrive_expect_tx(&w_full[stage], bytes);
+                bulk_g2s(s_ring + (size_t)stage * kStageBytes, p.wstream + (size_t)blk * kStageBytes, bytes, &w_full[stage]);
+                if (++stage == S) { stage = 0; phase ^= 1; }
+                return true;
+            };
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int sp_i = item % p.splits;
+                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+                for (int t = t0; t < t1; t += 2) {
+                    for (int q = 0; q < 2; ++q) {
+                        for (int b = 0; b < C::kNkb2; ++b) if (!push(b, C::kRows2 * 128)) goto done;
+                        for (int b = 0; b < C::kNc3 * C::kNkb3; ++b) if (!push(C::kNkb2 + b, kStageBytes)) goto done;
+                    }
+                    for (int b = 0; b < C::kLastBlocks; ++b) if (!push(C::kFrontBlocks + b, kStageBytes)) goto done;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0; uint32_t wphase = 0, act_phase = 0, o3_phase = 0, le_phase[2] = {0, 0};
+            const uint32_t id2 = make_idesc_bf16(128, M1), id128 = make_idesc_bf16(128, 128), id256 = make_idesc_bf16(128, 256);
+            const uint32_t a_out3 = smem_u32(s_out3), ring = smem_u32(s_ring);
+#define TK_NEXT_W(code) if (!mbar_wait(&w_full[stage], wphase, code)) goto done; tc_fence_after(); const uint32_t wb_ = ring + stage * kStageBytes;
+#define TK_REL_W() mma_commit(&w_empty[stage]); if (++stage == S) { stage = 0; wphase ^= 1; }
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int sp_i = item % p.splits;
+                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+                for (int t = t0; t < t1; t += 2) {
+                    for (int q = 0; q < 2; ++q) {
+                        // conv2: A1 (TMEM) x W2 -> D2
+                        if (!mbar_wait(act, act_phase, 0x7200)) goto done;
+                        act_phase ^= 1; tc_fence_after();
+#pragma unroll
+                        for (int kb = 0; kb < C::kNkb2; ++kb) {
+                            TK_NEXT_W(0x7300)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                mma_bf16_ts(tmem + C::kColD2, tmem + C::kColA1 + (kb * 4 + k) * 8, make_desc(wb_ + k * 2 * C::kRows2 * 16, C::kRows2),
+                                            id2, (kb > 0 || k > 0) ? 1u : 0u);
+                            TK_REL_W()
+                        }
+                        mma_commit(acc);
+                        // conv3: A2 (bf16 image of D2, in place: channels < M1/2 at +0, the rest at +M1/2) x W3 -> D3
+                        if (!mbar_wait(act, act_phase, 0x7201)) goto done;
+                        act_phase ^= 1; tc_fence_after();
+#pragma unroll
+                        for (int nc = 0; nc < C::kNc3; ++nc)
+#pragma unroll
+                            for (int kb = 0; kb < C::kNkb3; ++kb) {
+                                TK_NEXT_W(0x7310)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int k0 = (kb * 4 + k) * 16;                      // first channel of this K step
+                                    const int hf = k0 / (M1 / 2);
+                                    const uint32_t acol = tmem + C::kColD2 + hf * (M1 / 2) + (k0 - hf * (M1 / 2)) / 2;
+                                    mma_bf16_ts(tmem + C::kColD3 + nc * 128, acol, make_desc(wb_ + k * 2 * 128 * 16, 128), id128, (kb > 0 || k > 0) ? 1u : 0u);
+                                }
+                                TK_REL_W()
+                            }
+                        mma_commit(acc);
+                    }
+                    // conv4, transposed, N = 256 points (both tiles)
+                    if (!mbar_wait(out3_ready, o3_phase, 0x7400)) goto done;
+                    o3_phase ^= 1; tc_fence_after();
+#pragma unroll 1
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int b = cc & 1;
+                        if (!mbar_wait(&last_empty[b], le_phase[b] ^ 1, 0x7500 + b)) goto done;
+                        le_phase[b] ^= 1; tc_fence_after();
+                        for (int kb = 0; kb < C::kNkb4; ++kb) {
+                            TK_NEXT_W(0x7600)
+                            mma_block_k64(tmem + b * 256, wb_, 128, a_out3 + kb * 8 * 4096, 256, id256, kb > 0);
+                            TK_REL_W()
+                        }
+                        mma_commit(&last_full[b]);
+                    }
+                }
+            }
+#undef TK_NEXT_W
+#undef TK_REL_W
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (256 threads)
+        const int row = epi_row(), half = epi_half();
+        const uint32_t tl = tmem + ((uint32_t)(row & ~31) << 16);
+        uint32_t acc_phase = 0, lf_phase[2] = {0, 0};
+#define TK_ARRIVE(bar) do { __syncwarp(); if (lane == 0) mbar_arrive(bar); } while (0)
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int b = item / p.splits, sp_i = item % p.splits;
+            const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+            float rmax[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rmax[i] = -INFINITY;
+            for (int t = t0; t < t1; t += 2) {
+#pragma unroll 1
+                for (int q = 0; q < 2; ++q) {
+                    // ---- conv1 on CUDA cores: this thread's W0/2 channels -> A1 (an odd tail pair repeats its tile)
+                    {
+                        const int tq = (t + q < t1) ? t + q : t1 - 1;
+                        int pidx = tq * kTile + row;
+                        if (pidx > p.n - 1) pidx = p.n - 1;
+                        const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
+                        float xv[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+#pragma unroll
+                        for (int g = 0; g < W0 / 64; ++g) {
+                            uint32_t o[16];
+                            const int ch0 = half * (W0 / 2) + g * 32;
+#pragma unroll
+                            for (int gg = 0; gg < 4; ++gg) {
+                                float4 a0 = *reinterpret_cast<const float4 *>(s_w0b + ch0 + gg * 8);
+                                float4 a1 = *reinterpret_cast<const float4 *>(s_w0b + ch0 + gg * 8 + 4);
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    if (c >= p.c_in) break;
+                                    const float4 w0v = *reinterpret_cast<const float4 *>(s_w0w + c * W0 + ch0 + gg * 8);
+                                    const float4 w1v = *reinterpret_cast<const float4 *>(s_w0w + c * W0 + ch0 + gg * 8 + 4);
+                                    const float xx = xv[c];
+                                    a0.x = fmaf(xx, w0v.x, a0.x); a0.y = fmaf(xx, w0v.y, a0.y); a0.z = fmaf(xx, w0v.z, a0.z); a0.w = fmaf(xx, w0v.w, a0.w);
+                                    a1.x = fmaf(xx, w1v.x, a1.x); a1.y = fmaf(xx, w1v.y, a1.y); a1.z = fmaf(xx, w1v.z, a1.z); a1.w = fmaf(xx, w1v.w, a1.w);
+                                }
+                                o[gg * 4 + 0] = relu_pack_bf16x2(a0.x, a0.y); o[gg * 4 + 1] = relu_pack_bf16x2(a0.z, a0.w);
+                                o[gg * 4 + 2] = relu_pack_bf16x2(a1.x, a1.y); o[gg * 4 + 3] = relu_pack_bf16x2(a1.z, a1.w);
+                            }
+                            tmem_st16(tl + C::kColA1 + ch0 / 2, o);
+                        }
+                        tmem_st_wait(); tc_fence_before();
+                        TK_ARRIVE(act);
+                    }
+                    // ---- conv2 epilogue: D2 -> its bf16 image, in place (this thread: M1/2 columns)
+                    if (!mbar_wait(acc, acc_phase, 0x6100)) goto done;
+                    acc_phase ^= 1; tc_fence_after();
+#pragma unroll
+                    for (int g = 0; g < M1 / 64; ++g) {
+                        uint32_t v[32], o[16];
+                        const uint32_t src = tl + C::kColD2 + half * (M1 / 2) + g * 32;
+                        tmem_ld32(src, v);
+                        tmem_ld_wait();
+                        pack_act32(v, s_b2 + half * (M1 / 2) + g * 32, o);
+                        tmem_st16(tl + C::kColD2 + half * (M1 / 2) + g * 16, o);
+                    }
+                    tmem_st_wait(); tc_fence_before();
+                    TK_ARRIVE(act);
+                    // ---- conv3 epilogue: D3 -> shared-memory operand of conv4 (this thread: M2/2 channels of its row)
+                    if (!mbar_wait(acc, acc_phase, 0x6101)) goto done;
+                    acc_phase ^= 1; tc_fence_after();
+#pragma unroll
+                    for (int g = 0; g < M2 / 64; ++g) {
+                        uint32_t v[32], o[16];
+                        const int c0 = half * (M2 / 2) + g * 32;
+                        tmem_ld32(tl + C::kColD3 + c0, v);
+                        tmem_ld_wait();
+                        pack_act32(v, s_b3 + c0, o);
+                        uint8_t *dst = s_out3 + (size_t)(c0 / 8) * 4096 + (size_t)(q * kTile + row) * 16;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4 *>(dst + (size_t)j * 4096) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    }
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    TK_ARRIVE(out3_ready);
+                }
+                // ---- conv4: this thread owns channel (cc*128 + row) and 128 of the pair's 256 points
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int bsel = cc & 1;
+                    if (!mbar_wait(&last_full[bsel], lf_phase[bsel], 0x6300 + cc)) goto done;
+                    lf_phase[bsel] ^= 1; tc_fence_after();
+                    float m0 = rmax[cc], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+                    for (int c0 = 0; c0 < 128; c0 += 64) {
+                        uint32_t v0[32], v1[32];
+                        const uint32_t ta = tl + bsel * 256 + half * 128 + c0;
+                        tmem_ld32(ta, v0);
+                        tmem_ld32(ta + 32, v1);
+                        tmem_ld_wait();
+                        if (c0 == 64) { tc_fence_before(); TK_ARRIVE(&last_empty[bsel]); }   // all values are in registers
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            m0 = fmax3(m0, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
+                            m1 = fmax3(m1, __uint_as_float(v0[i + 2]), __uint_as_float(v0[i + 3]));
+                            m2 = fmax3(m2, __uint_as_float(v0[i + 4]), __uint_as_float(v0[i + 5]));
+                            m3 = fmax3(m3, __uint_as_float(v0[i + 6]), __uint_as_float(v0[i + 7]));
+                            m0 = fmax3(m0, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
+                            m1 = fmax3(m1, __uint_as_float(v1[i + 2]), __uint_as_float(v1[i + 3]));
+                            m2 = fmax3(m2, __uint_as_float(v1[i + 4]), __uint_as_float(v1[i + 5]));
+                            m3 = fmax3(m3, __uint_as_float(v1[i + 6]), __uint_as_float(v1[i + 7]));
+                        }
+                    }
+                    rmax[cc] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                }
+            }
+            if (t1 > t0) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int ch = cc * 128 + row;
+                    const float v = fmaxf(rmax[cc] + __ldg(p.last_b + ch), 0.f);
+                    atomicMax(reinterpret_cast<int *>(p.out + (int64_t)b * 512 + ch), __float_as_int(v));
+                }
+            }
+        }
+#undef TK_ARRIVE
+    }
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+template <int W0, int M1, int M2>
+static int launch_trunk_pair(const TrunkParams &p0, int bs, int n, cudaStream_t stream, int sms)
+{
+    using C = TrunkCfg<W0, M1, M2>;
+    TrunkParams p = p0;
+    const int tiles = (n + kTile - 1) / kTile;
+    int splits = 1;
+    if (bs < 2 * sms) splits = (int)std::min<int64_t>((tiles + 1) / 2, ceil_div(2 * sms, bs));
+    p.splits = std::max(splits, 1);
+    p.n_items = bs * p.splits;
+    const int grid = std::min(p.n_items, sms);
+    const size_t smem = (size_t)C::kOut3Bytes + (size_t)C::kStages * kStageBytes + (size_t)(W0 * 9 + M1 + M2) * 4 + 32 * 8 + 128;
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(trunk_pair_kernel<W0, M1, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trunk_pair_kernel<W0, M1, M2><<<grid, kThreads, smem, stream>>>(p);
+    AL3D_CHECK_LAUNCH("trunk_pair_kernel");
+    return 0;
+}
+
 }  // namespace al3d
 
 using namespace al3d;
@@ -1374,6 +1674,17 @@ extern "C" int al3d_chain_maxpool_bf16(const al3d_chain_weights *w, const float 
     AL3D_CHECK_ARG(w->last % 256 == 0 && w->last >= 256 && w->last <= 1024, "al3d_chain_maxpool_bf16: last=%d", w->last);
     AL3D_CHECK_ARG(bs >= 0 && n >= 1, "al3d_chain_maxpool_bf16: bad shape");
     if (bs == 0) return 0;
+    if (w->n_mid == 2 && w->last == 512) {
+        // the three trunks of the models: specialised tile-pair kernels (the generic chain kernel below keeps any other shape)
+        TrunkParams tp;
+        tp.x = x; tp.sb = sb; tp.sc = sc; tp.sp = sp; tp.bs = bs; tp.n = n; tp.c_in = w->c_in;
+        tp.w0_w = w->w0_w; tp.w0_b = w->w0_b; tp.mid_b = w->mid_b; tp.last_b = w->last_b;
+        tp.wstream = (const uint8_t *)w->wstream; tp.out = out; tp.splits = 1; tp.n_items = 0;
+        const int sms_ = num_sms();
+        if (w->w0 == 128 && w->mid[0] == 128 && w->mid[1] == 256) return launch_trunk_pair<128, 128, 256>(tp, bs, n, (cudaStream_t)stream, sms_);
+        if (w->w0 == 64 && w->mid[0] == 128 && w->mid[1] == 256) return launch_trunk_pair<64, 128, 256>(tp, bs, n, (cudaStream_t)stream, sms_);
+        if (w->w0 == 64 && w->mid[0] == 64 && w->mid[1] == 128) return launch_trunk_pair<64, 64, 128>(tp, bs, n, (cudaStream_t)stream, sms_);
+    }
     ChainParams p;
     p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n;
     p.c_in = w->c_in; p.w0 = w->w0; p.n_mid = w->n_mid;
