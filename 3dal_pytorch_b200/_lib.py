@@ -40,6 +40,7 @@ _SIGNATURES = {
     "al3d_umma_selftest_ts": [_vp, _vp, _i, _i, _vp, _vp],
     "al3d_umma_selftest_pair": [_vp, _vp, _i, _i, _vp, _vp],
     "al3d_umma_selftest_pair_ss": [_vp, _vp, _i, _vp, _vp],
+    "al3d_mma_microbench": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "al3d_tc_abort_code": [_vp],
     "al3d_set_debug_buffer": [_vp],
 }

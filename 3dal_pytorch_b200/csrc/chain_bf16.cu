@@ -13,6 +13,7 @@
 // Both are persistent, warp-specialised: warp 0 streams packed weight blocks with cp.async.bulk into a
 // ring, warp 1 (one thread) issues tcgen05.mma, warps 2-5 own the 128 TMEM lanes and run every
 // epilogue.  BatchNorm is folded into the weights by the host; ReLU and bias are applied in the epilogue.
+#include <cstdlib>
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/al3d.h"
@@ -577,19 +578,21 @@ struct Pass2Params {
     const float *gbias;                // (bs, 512) per-object dconv1 bias (global-feature half + folded BN bias)
     const float *bd2, *bd3, *bd4;      // dconv2-4 biases (256),(128),(128)
     const float *w5, *b5;              // dconv5 fp32 (2,128), (2)
-    const uint8_t *wstream;            // two per-CTA halves (kP2HalfBytes each) of the 31 packed blocks, tightly packed
+    const uint8_t *wstream;            // two per-CTA halves (kP2HalfBytes each) of the 23 packed blocks, tightly packed
     float *logits;                     // (bs, n, 2)
     uint8_t *mask;                     // (bs, n)
     int tiles_per_obj; int n_items;    // items = bs * tiles_per_obj
     long long *dbg;                    // optional clock64 timeline of CTA 0 (al3d_set_debug_buffer), else NULL
+    int dbg_skip;                      // first recorded tile of the timeline (environment AL3D_DEBUG_SKIP)
 };
 
 // timeline stamps: role 0 = MMA thread, 1 = epilogue thread 0, 2 = producer; 64 stamps x 4 items each
 #define AL3D_TS(role)                                                                         \
-    do { if (p.dbg && blockIdx.x == 0 && it_local < 4 && ts_i < 64)                            \
-             p.dbg[((role) * 4 + it_local) * 64 + ts_i++] = clock64(); } while (0)
+    do { const int ts_it = it_local - p.dbg_skip;                                             \
+         if (p.dbg && blockIdx.x == 0 && ts_it >= 0 && ts_it < 4 && ts_i < 64)                 \
+             p.dbg[((role) * 4 + ts_it) * 64 + ts_i++] = clock64(); } while (0)
 
-constexpr int kP2Blocks = 31;
+constexpr int kP2Blocks = 23;
 constexpr uint32_t kColD2 = 0, kColD1 = 256, kColA2 = 448, kColA1 = 480, kColD3 = 256, kColD4 = 0;
 
 // The kernel runs as CTA PAIRS (cluster of 2, tcgen05 cta_group::2): one M = 256 MMA covers the 128-point tiles of
@@ -597,12 +600,12 @@ constexpr uint32_t kColD2 = 0, kColD1 = 256, kColA2 = 448, kColA1 = 480, kColD3 
 // per SM -- the per-SM L2 -> smem ingress (~41 B/cycle measured) is what bounded the single-CTA version -- and makes
 // the whole 424 KB weight set fit: 212 KB per CTA stay resident in shared memory for the life of the kernel, so
 // there is no weight streaming at all.
-// Per-tile block list (order of use): 0 conv2 | 1-3 dconv1 chunks 0-2 | 5 groups {dconv2 partial a, b, dconv1 chunk}
-// | 3 groups {dconv2 partial a, b} | 25-28 dconv3 | 29-30 dconv4.  64-row blocks are 8 KB, 128-row blocks 16 KB;
-// a CTA keeps half of each.
+// Per-tile block list (order of use): 0 conv2 | 1-3 dconv1 chunks 0-2 | 4-13 five groups {dconv2 partial, dconv1 chunk}
+// | 14-16 dconv2 partials | 17-20 dconv3 | 21-22 dconv4.  64-row blocks are 8 KB, 128-row blocks 16 KB, the 256-row
+// dconv2 partials 32 KB; a CTA keeps half of each (one KP tile of R/2 rows).
 __host__ __device__ constexpr uint32_t p2_block_bytes(int blk)
 {
-    return blk <= 3 ? 8192u : (blk < 19 ? ((blk - 4) % 3 == 2 ? 8192u : 16384u) : 16384u);
+    return blk <= 3 ? 8192u : (blk < 14 ? ((blk - 4) % 2 == 0 ? 32768u : 8192u) : (blk < 17 ? 32768u : 16384u));
 }
 __host__ __device__ constexpr uint32_t p2_half_off(int blk)
 {
@@ -633,19 +636,22 @@ __device__ __forceinline__ void pack_act32(const uint32_t (&v)[32], const float 
     }
 }
 
-// conv1 on CUDA cores for 32 output channels starting at ch0 -> 16 packed bf16x2 words
-__device__ __forceinline__ void conv1_pack32(const float (&xv)[8], int c_in, const float *w_t, const float *bias, int ch0,
-                                             uint32_t (&o)[16])
+// conv1 on CUDA cores for 32 output channels starting at ch0 -> 16 packed bf16x2 words.
+// CIN > 0: compile-time channel count (all weight loads are hoisted; the runtime-bounded loop is latency-bound with
+// two warps per scheduler); CIN == 0: runtime c_in <= 8.  WS: channel count of the layer (row stride of w_t).
+template <int CIN, int WS>
+__device__ __forceinline__ void conv1_pack32_t(const float (&xv)[8], int c_in, const float *w_t, const float *bias, int ch0,
+                                               uint32_t (&o)[16])
 {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         float4 a0 = *reinterpret_cast<const float4 *>(bias + ch0 + g * 8);
         float4 a1 = *reinterpret_cast<const float4 *>(bias + ch0 + g * 8 + 4);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            if (c >= c_in) break;
-            const float4 w0v = *reinterpret_cast<const float4 *>(w_t + c * 64 + ch0 + g * 8);
-            const float4 w1v = *reinterpret_cast<const float4 *>(w_t + c * 64 + ch0 + g * 8 + 4);
+        for (int c = 0; c < (CIN > 0 ? CIN : 8); ++c) {
+            if (CIN == 0 && c >= c_in) break;
+            const float4 w0v = *reinterpret_cast<const float4 *>(w_t + c * WS + ch0 + g * 8);
+            const float4 w1v = *reinterpret_cast<const float4 *>(w_t + c * WS + ch0 + g * 8 + 4);
             const float xx = xv[c];
             a0.x = fmaf(xx, w0v.x, a0.x); a0.y = fmaf(xx, w0v.y, a0.y); a0.z = fmaf(xx, w0v.z, a0.z); a0.w = fmaf(xx, w0v.w, a0.w);
             a1.x = fmaf(xx, w1v.x, a1.x); a1.y = fmaf(xx, w1v.y, a1.y); a1.z = fmaf(xx, w1v.z, a1.z); a1.w = fmaf(xx, w1v.w, a1.w);
@@ -653,6 +659,14 @@ __device__ __forceinline__ void conv1_pack32(const float (&xv)[8], int c_in, con
         o[g * 4 + 0] = relu_pack_bf16x2(a0.x, a0.y); o[g * 4 + 1] = relu_pack_bf16x2(a0.z, a0.w);
         o[g * 4 + 2] = relu_pack_bf16x2(a1.x, a1.y); o[g * 4 + 3] = relu_pack_bf16x2(a1.z, a1.w);
     }
+}
+template <int WS = 64>
+__device__ __forceinline__ void conv1_pack32(const float (&xv)[8], int c_in, const float *w_t, const float *bias, int ch0,
+                                             uint32_t (&o)[16])
+{
+    if (c_in == 3)      conv1_pack32_t<3, WS>(xv, c_in, w_t, bias, ch0, o);     // static model (x, y, z)
+    else if (c_in == 4) conv1_pack32_t<4, WS>(xv, c_in, w_t, bias, ch0, o);     // dynamic model (x, y, z, t)
+    else                conv1_pack32_t<0, WS>(xv, c_in, w_t, bias, ch0, o);
 }
 
 // 4 MMAs (K = 64) with A in TMEM: a_col[s] is the TMEM column of K-slice s (8 columns each)
@@ -730,7 +744,7 @@ seg_pass2_kernel(const Pass2Params p)
         // both CTAs' barriers.
         if (lane == 0 && crank == 0) {
             uint32_t actf_phase = 0, actt_phase = 0, d1a_phase[3] = {0, 0, 0};
-            const uint32_t id64 = make_idesc_bf16(256, 64), id128 = make_idesc_bf16(256, 128);
+            const uint32_t id64 = make_idesc_bf16(256, 64), id128 = make_idesc_bf16(256, 128), id256 = make_idesc_bf16(256, 256);
             const uint32_t wres = smem_u32(s.wres);
 #define P2_W(blk) (wres + p2_half_off(blk))
 #define P2_WAIT(bar, ph, code)                                                           \
@@ -760,43 +774,45 @@ seg_pass2_kernel(const Pass2Params p)
                     mma_pair_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, P2_W(1 + j), 32, id64, false);
                     mma_commit_pair(&s.d1_full[j], 0x3);
                 }
+                AL3D_TS(0);
 #pragma unroll
                 for (int kc = 0; kc < 8; ++kc) {
                     const int j = kc % 3;
-                    const int blk0 = kc < 5 ? 4 + 3 * kc : 19 + 2 * (kc - 5);       // first block of this group
+                    const int blk0 = kc < 5 ? 4 + 2 * kc : 14 + (kc - 5);           // dconv2 block of this group
                     if (!mbar_wait_cluster(&s.d1_act[j], d1a_phase[j], 0xA400 + kc)) goto done;
                     AL3D_TS(0);
                     d1a_phase[j] ^= 1; tc_fence_after();
                     const uint32_t a = tmem + kColD1 + j * 64;        // bf16 image of chunk kc (in place)
-#pragma unroll
-                    for (int nc = 0; nc < 2; ++nc)
-                        mma_pair_k64(tmem + kColD2 + nc * 128, a, a + 8, a + 32, a + 40, P2_W(blk0 + nc), 64, id128, kc > 0);
+                    // one N = 256 instruction per K slice: the issuing thread, not the tensor pipe, bounded the N = 128 form
+                    mma_pair_k64(tmem + kColD2, a, a + 8, a + 32, a + 40, P2_W(blk0), 128, id256, kc > 0);
                     if (kc + 3 < 8) {
                         // the MMA pipe executes in issue order, so this overwrite of D1b[j] happens after the
                         // partial sums above have consumed it
-                        mma_pair_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, P2_W(blk0 + 2), 32, id64, false);
+                        mma_pair_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, P2_W(blk0 + 1), 32, id64, false);
                         mma_commit_pair(&s.d1_full[j], 0x3);
                     }
                 }
                 mma_commit_pair(&s.acc_t, 0x3);                            // dconv2 accumulator complete
-                // dconv3: A3 x Wd3 -> D3                                            (blocks 25..28)
+                // dconv3: A3 x Wd3 -> D3                                            (blocks 17..20)
                 P2_WAIT(s.act_t, actt_phase, 0xA202)
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb) {
                     const uint32_t a = tmem + kColD2 + (kb >> 1) * 128 + (kb & 1) * 32;
-                    mma_pair_k64(tmem + kColD3, a, a + 8, a + 16, a + 24, P2_W(25 + kb), 64, id128, kb > 0);
+                    mma_pair_k64(tmem + kColD3, a, a + 8, a + 16, a + 24, P2_W(17 + kb), 64, id128, kb > 0);
                 }
                 mma_commit_pair(&s.acc_t, 0x3);
+                AL3D_TS(0);
                 // front of the next round: conv2 on its conv1 output (A1 at [480,512) -> D1b[2]; both are free now)
                 if (has_next) P2_ISSUE_CONV2()
-                // dconv4: A4 x Wd4 -> D4 (over the dead A3 at columns 0..127)       (blocks 29, 30)
+                // dconv4: A4 x Wd4 -> D4 (over the dead A3 at columns 0..127)       (blocks 21, 22)
                 P2_WAIT(s.act_t, actt_phase, 0xA203)
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
                     const uint32_t a = tmem + kColD3 + kb * 64;
-                    mma_pair_k64(tmem + kColD4, a, a + 8, a + 16, a + 24, P2_W(29 + kb), 64, id128, kb > 0);
+                    mma_pair_k64(tmem + kColD4, a, a + 8, a + 16, a + 24, P2_W(21 + kb), 64, id128, kb > 0);
                 }
                 mma_commit_pair(&s.acc_t, 0x3);
+                AL3D_TS(0);
             }
 #undef P2_W
 #undef P2_WAIT
@@ -834,7 +850,9 @@ seg_pass2_kernel(const Pass2Params p)
             uint32_t o[16];
             conv1_pack32(xv, p.c_in, s.w1_w, s.w1_b, half * 32, o);
             tmem_st16(tl + kColA1 + half * 16, o);
+            AL3D_TSE();
             P2_PUBLISH(&s.act_f);
+            AL3D_TSE();
             load_x(next_item, xv);
         };
         // front, part 2: conv2 accumulator (D1b[2]) -> A2
@@ -909,6 +927,7 @@ seg_pass2_kernel(const Pass2Params p)
                 const uint32_t dst = tl + kColD2 + half * 128 + bt * 32;
                 tmem_st16(dst, o0);
                 tmem_st16(dst + 16, o1);
+                AL3D_TSE();
             }
             P2_PUBLISH(&s.act_t);
             AL3D_TSE();
@@ -948,6 +967,7 @@ seg_pass2_kernel(const Pass2Params p)
                 tmem_ld32(tl + kColD4 + c0 + 32, v1);
                 tmem_ld_wait();
                 tc_fence_before();
+                AL3D_TSE();
                 float l0a = 0.f, l1a = 0.f, l0b = 0.f, l1b = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -969,7 +989,9 @@ seg_pass2_kernel(const Pass2Params p)
                 }
                 const float l0 = l0a + l0b, l1 = l1a + l1b;
                 if (half == 1) { s.lpart[par][row] = l0; s.lpart[par][kTile + row] = l1; }
+                AL3D_TSE();
                 asm volatile("bar.sync 2, 256;" ::: "memory");
+                AL3D_TSE();
                 if (half == 0 && valid) {
                     const float f0 = (s.b5[0] + l0) + s.lpart[par][row];
                     const float f1 = (s.b5[1] + l1) + s.lpart[par][kTile + row];
@@ -1012,6 +1034,7 @@ struct Pass1Params {
     float *out;                        // (bs, 1024) zero-initialised
     int splits, n_items;
     long long *dbg;                    // optional clock64 timeline (al3d_set_debug_buffer), else NULL
+    int dbg_skip;                      // first recorded tile pair of the timeline (environment AL3D_DEBUG_SKIP)
 };
 
 constexpr int kP1Stages = 7;
@@ -1027,7 +1050,8 @@ struct Pass1Smem {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kP1Threads = kThreads + 32;     // producer, MMA issuer, 8 epilogue warps, second MMA issuer
+__global__ void __launch_bounds__(kP1Threads, 1)
 seg_pass1_kernel(const Pass1Params p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -1078,7 +1102,8 @@ seg_pass1_kernel(const Pass1Params p)
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            int stage = 0; uint32_t wphase = 0, act_phase[2] = {0, 0}, le_phase[2] = {0, 0}, o4_phase = 0;
+            uint32_t act_phase[2] = {0, 0}, le_phase[2] = {0, 0}, o4_phase = 0;
+            int pair_count = 0;
             const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128), id256 = make_idesc_bf16(128, 256);
             const uint32_t wf0 = smem_u32(s.wfront), wf1 = wf0 + 8192, wf2 = wf0 + 16384;
             const uint32_t a_out4 = smem_u32(s.out4);
@@ -1106,25 +1131,58 @@ seg_pass1_kernel(const Pass1Params p)
                             mma_commit(&s.acc[q]);
                         }
                     }
-                    // conv5, transposed, N = 256 points (both tiles): D^T[128 channels x 256 points]
+                    // conv5, transposed, N = 256 points (both tiles): D^T[128 channels x 256 points]; this thread issues
+                    // the even channel chunks (accumulator buffer 0), the second issuer (warp 10) the odd ones
                     if (!mbar_wait(&s.out4_ready, o4_phase, 0x9400)) goto done;
                     AL3D_TS(0);
                     o4_phase ^= 1; tc_fence_after();
 #pragma unroll 1
-                    for (int cc = 0; cc < 8; ++cc) {
-                        const int b = cc & 1;
-                        if (!mbar_wait(&s.last_empty[b], le_phase[b] ^ 1, 0x9500 + b)) goto done;
+                    for (int cc = 0; cc < 8; cc += 2) {
+                        if (!mbar_wait(&s.last_empty[0], le_phase[0] ^ 1, 0x9500)) goto done;
                         AL3D_TS(0);
-                        le_phase[b] ^= 1; tc_fence_after();
+                        le_phase[0] ^= 1; tc_fence_after();
                         for (int kb = 0; kb < 2; ++kb) {
-                            if (!mbar_wait(&s.w_full[stage], wphase, 0x9600 + stage)) goto done;
+                            const int g = pair_count * 16 + cc * 2 + kb, stage = g % kP1Stages;
+                            if (!mbar_wait(&s.w_full[stage], (uint32_t)(g / kP1Stages) & 1u, 0x9600 + stage)) goto done;
                             AL3D_TS(0);
                             tc_fence_after();
-                            mma_block_k64(tmem + b * 256, smem_u32(s.wring[stage]), 128, a_out4 + kb * 8 * 4096, 256, id256, kb > 0);
+                            mma_block_k64(tmem, smem_u32(s.wring[stage]), 128, a_out4 + kb * 8 * 4096, 256, id256, kb > 0);
                             mma_commit(&s.w_empty[stage]);
-                            if (++stage == kP1Stages) { stage = 0; wphase ^= 1; }
                         }
-                        mma_commit(&s.last_full[b]);
+                        mma_commit(&s.last_full[0]);
+                    }
+                    ++pair_count;
+                }
+            }
+        }
+    } else if (warp == kThreads / 32) {
+        // ------------------------------------------------------------ second MMA issuer: odd conv5 chunks (buffer 1).
+        // One thread cannot keep the tensor pipe busy here: per chunk it spends ~1.4k cycles on 8 N = 256 instructions,
+        // three waits and three commits against 1.0k cycles of execution (scripts/mma_microbench.py), so the chunks
+        // alternate between two issuing threads.  Chunks are independent (own accumulator buffer, own barriers).
+        if (lane == 0) {
+            uint32_t le_phase1 = 0, o4_phase = 0;
+            const uint32_t id256 = make_idesc_bf16(128, 256);
+            const uint32_t a_out4 = smem_u32(s.out4);
+            int pair_count = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int sp_i = item % p.splits;
+                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+                for (int t = t0; t < t1; t += 2, ++pair_count) {
+                    if (!mbar_wait(&s.out4_ready, o4_phase, 0x9401)) goto done;
+                    o4_phase ^= 1; tc_fence_after();
+#pragma unroll 1
+                    for (int cc = 1; cc < 8; cc += 2) {
+                        if (!mbar_wait(&s.last_empty[1], le_phase1 ^ 1, 0x9501)) goto done;
+                        le_phase1 ^= 1; tc_fence_after();
+                        for (int kb = 0; kb < 2; ++kb) {
+                            const int g = pair_count * 16 + cc * 2 + kb, stage = g % kP1Stages;
+                            if (!mbar_wait(&s.w_full[stage], (uint32_t)(g / kP1Stages) & 1u, 0x9610 + stage)) goto done;
+                            tc_fence_after();
+                            mma_block_k64(tmem + 256, smem_u32(s.wring[stage]), 128, a_out4 + kb * 8 * 4096, 256, id256, kb > 0);
+                            mma_commit(&s.w_empty[stage]);
+                        }
+                        mma_commit(&s.last_full[1]);
                     }
                 }
             }
@@ -1461,22 +1519,7 @@ trunk_pair_kernel(const TrunkParams p)
                         for (int g = 0; g < W0 / 64; ++g) {
                             uint32_t o[16];
                             const int ch0 = half * (W0 / 2) + g * 32;
-#pragma unroll
-                            for (int gg = 0; gg < 4; ++gg) {
-                                float4 a0 = *reinterpret_cast<const float4 *>(s_w0b + ch0 + gg * 8);
-                                float4 a1 = *reinterpret_cast<const float4 *>(s_w0b + ch0 + gg * 8 + 4);
-#pragma unroll
-                                for (int c = 0; c < 8; ++c) {
-                                    if (c >= p.c_in) break;
-                                    const float4 w0v = *reinterpret_cast<const float4 *>(s_w0w + c * W0 + ch0 + gg * 8);
-                                    const float4 w1v = *reinterpret_cast<const float4 *>(s_w0w + c * W0 + ch0 + gg * 8 + 4);
-                                    const float xx = xv[c];
-                                    a0.x = fmaf(xx, w0v.x, a0.x); a0.y = fmaf(xx, w0v.y, a0.y); a0.z = fmaf(xx, w0v.z, a0.z); a0.w = fmaf(xx, w0v.w, a0.w);
-                                    a1.x = fmaf(xx, w1v.x, a1.x); a1.y = fmaf(xx, w1v.y, a1.y); a1.z = fmaf(xx, w1v.z, a1.z); a1.w = fmaf(xx, w1v.w, a1.w);
-                                }
-                                o[gg * 4 + 0] = relu_pack_bf16x2(a0.x, a0.y); o[gg * 4 + 1] = relu_pack_bf16x2(a0.z, a0.w);
-                                o[gg * 4 + 2] = relu_pack_bf16x2(a1.x, a1.y); o[gg * 4 + 3] = relu_pack_bf16x2(a1.z, a1.w);
-                            }
+                            conv1_pack32<W0>(xv, p.c_in, s_w0w, s_w0b, ch0, o);
                             tmem_st16(tl + C::kColA1 + ch0 / 2, o);
                         }
                         tmem_st_wait(); tc_fence_before();
@@ -1586,6 +1629,11 @@ using namespace al3d;
 
 static long long *g_debug_buffer = nullptr;
 extern "C" int al3d_set_debug_buffer(void *dev_ptr) { g_debug_buffer = (long long *)dev_ptr; return 0; }
+static int debug_skip()
+{
+    const char *e = g_debug_buffer ? std::getenv("AL3D_DEBUG_SKIP") : nullptr;
+    return e ? std::atoi(e) : 0;
+}
 
 extern "C" int al3d_tc_abort_code(int *code_host)
 {
@@ -1730,6 +1778,7 @@ extern "C" int al3d_seg_pass1_bf16(const al3d_pass1_weights *w, const float *x, 
     p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.b3 = w->b3; p.b4 = w->b4; p.b5 = w->b5;
     p.wfront = (const uint8_t *)w->wfront; p.w5stream = (const uint8_t *)w->w5stream; p.out = out;
     p.dbg = g_debug_buffer ? g_debug_buffer + 3 * 4 * 64 : nullptr;      // second half of the debug buffer
+    p.dbg_skip = debug_skip();
     const int tiles = (n + kTile - 1) / kTile;
     const int sms = num_sms();
     int splits = 1;
@@ -1740,7 +1789,7 @@ extern "C" int al3d_seg_pass1_bf16(const al3d_pass1_weights *w, const float *x, 
     const size_t smem = sizeof(Pass1Smem) + 128;
     static_assert(sizeof(Pass1Smem) + 128 <= 232448, "Pass1Smem exceeds the 227 KB opt-in limit");
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(seg_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    seg_pass1_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    seg_pass1_kernel<<<grid, kP1Threads, smem, (cudaStream_t)stream>>>(p);
     AL3D_CHECK_LAUNCH("seg_pass1_kernel");
     return 0;
 }
@@ -1756,7 +1805,7 @@ extern "C" int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, 
     p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n; p.c_in = w->c_in;
     p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.gbias = gbias;
     p.bd2 = w->bd2; p.bd3 = w->bd3; p.bd4 = w->bd4; p.w5 = w->w5; p.b5 = w->b5;
-    p.wstream = (const uint8_t *)w->wstream; p.logits = logits; p.mask = mask; p.dbg = g_debug_buffer;
+    p.wstream = (const uint8_t *)w->wstream; p.logits = logits; p.mask = mask; p.dbg = g_debug_buffer; p.dbg_skip = debug_skip();
     p.tiles_per_obj = (n + kTile - 1) / kTile;
     const int64_t items = (int64_t)bs * p.tiles_per_obj;
     AL3D_CHECK_ARG(items < (1ll << 31), "al3d_seg_pass2_bf16: too many tiles");

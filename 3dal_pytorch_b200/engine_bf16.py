@@ -97,8 +97,8 @@ class SegPack:
         def d1(c):                     # dconv1 chunk c: 64 output channels x the 64 per-point input channels
             return [wd1[c * 64:(c + 1) * 64, 0:64]]
 
-        def d2(pc):                    # dconv2 partial sum over input channels pc*64..+64, two 128-row halves
-            return [wd2[nc * 128:(nc + 1) * 128, pc * 64:(pc + 1) * 64] for nc in range(2)]
+        def d2(pc):                    # dconv2 partial sum over input channels pc*64..+64: all 256 rows, one N = 256 MMA
+            return [wd2[:, pc * 64:(pc + 1) * 64]]
 
         mats += d1(0) + d1(1) + d1(2)
         for kc in range(8):
@@ -107,7 +107,7 @@ class SegPack:
                 mats += d1(kc + 3)
         mats += [wd3[:, kb * 64:(kb + 1) * 64] for kb in range(4)]
         mats += [wd4[:, kb * 64:(kb + 1) * 64] for kb in range(2)]
-        assert len(mats) == 31
+        assert len(mats) == 23
         self.p2_mats = mats
         # the kernel runs as CTA pairs (cta_group::2): CTA r keeps rows [r*R/2, (r+1)*R/2) of every block, KP-packed,
         # tightly concatenated; the two per-CTA images follow each other

@@ -12,7 +12,7 @@ from . import ops
 
 
 class StaticAutoLabeler:
-    def __init__(self, model, chunk_tracks=1024):
+    def __init__(self, model, chunk_tracks=2048):
         self.model = model
         self.chunk = int(chunk_tracks)
         self._staging = None

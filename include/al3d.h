@@ -225,7 +225,7 @@ typedef struct al3d_pass2_weights {
     const float *b2;               /* conv2 bias (64)                                               */
     const float *bd2, *bd3, *bd4;  /* dconv2-4 biases (256),(128),(128)                             */
     const float *w5, *b5;          /* dconv5 fp32 (2,128), (2)                                      */
-    const void  *wstream;          /* two per-CTA halves of the 31 packed bf16 blocks (conv2, dconv1/dconv2 interleaved, dconv3, dconv4) */
+    const void  *wstream;          /* two per-CTA halves of the 23 packed bf16 blocks (conv2, dconv1/dconv2 interleaved, dconv3, dconv4) */
 } al3d_pass2_weights;
 
 /* Second half of PointNetInstanceSeg.forward (tools/static_model.py:286-295) + the mask of
@@ -246,6 +246,15 @@ int al3d_umma_selftest_pair(const float *a, const void *b_kp_halves, int N, int 
 /* CTA-pair variant with both operands in shared memory, N = 128: a_kp_halves = two KP tiles of 128 rows, b_kp_halves =
  * two KP tiles of 64 rows (staged by the kernel as a sub-tile of a 128-row tile).  d_out (256,128). */
 int al3d_umma_selftest_pair_ss(const void *a_kp_halves, const void *b_kp_halves, int K, float *d_out, void *stream);
+
+/* Development aid: issue n_mma tcgen05.mma (M = 128, N, K = 16; mode 0 = both operands in shared memory, 1 = A from
+ * TMEM) from one thread on each of n_ctas CTAs, a commit every commit_every MMAs (0 = only at the end).
+ * background: bit 0 = four warps read the accumulator columns with tcgen05.ld meanwhile, bit 1 = one thread streams
+ * 16 KB blocks from src_1mib (device, >= 1 MiB) into shared memory meanwhile.
+ * out (6 int64, CTA 0): issue cycles, cycles to completion, issue cycles of the first 8, background blocks, background
+ * loads, scratch.  scripts/mma_microbench.py. */
+int al3d_mma_microbench(int N, int n_mma, int commit_every, int mode, int n_ctas, int background, const void *src_1mib,
+                        long long *out, void *stream);
 
 /* Reads (and clears) the device-side watchdog code: non-zero means a tensor-core kernel gave up on
  * an mbarrier wait (protocol bug) and its outputs are invalid.  Synchronises the device. */

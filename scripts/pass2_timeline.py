@@ -1,4 +1,5 @@
-"""Development aid: clock64 timeline of CTA 0 of seg_pass2_kernel (first four tiles).
+"""Development aid: clock64 timeline of CTA 0 of seg_pass2_kernel / seg_pass1_kernel (four tiles / tile pairs, starting at
+tile AL3D_DEBUG_SKIP of the CTA; AL3D_TIMELINE_TRACKS tracks, default 1024).
 Usage (GPU box): python scripts/pass2_timeline.py > gpurun_out/timeline.txt"""
 import importlib
 import os
@@ -20,7 +21,7 @@ dev = "cuda:0"
 model = sm.StaticModelOneBoxEst().to(dev).eval()
 model.load_state_dict(synth.random_state_dict("static_one", seed=1))
 model.precision = "bf16"
-data = synth.static_tracks_device(1024, seed=0, device=dev)
+data = synth.static_tracks_device(int(os.environ.get("AL3D_TIMELINE_TRACKS", "1024")), seed=0, device=dev)
 pts = data["pts_pm"].transpose(2, 1)
 for _ in range(2):
     model(pts, data["init_box"], None)

@@ -59,7 +59,7 @@ def test_pass2_stream_order_matches_kernel_schedule():
     wd1, wd2, wd3, wd4 = bf("dconv1"), bf("dconv2"), bf("dconv3"), bf("dconv4")
     expect = [("conv2", bf("conv2"))]
     d1 = lambda c: [("d1_%d" % c, wd1[c * 64:(c + 1) * 64, :64])]
-    d2 = lambda pc: [("d2_%d_%d" % (pc, nc), wd2[nc * 128:(nc + 1) * 128, pc * 64:(pc + 1) * 64]) for nc in range(2)]
+    d2 = lambda pc: [("d2_%d" % pc, wd2[:, pc * 64:(pc + 1) * 64])]
     # order of use by the MMA thread in seg_pass2_kernel
     expect += d1(0) + d1(1) + d1(2)
     for kc in range(8):
@@ -68,17 +68,19 @@ def test_pass2_stream_order_matches_kernel_schedule():
             expect += d1(kc + 3)
     expect += [("d3_%d" % kb, wd3[:, kb * 64:(kb + 1) * 64]) for kb in range(4)]
     expect += [("d4_%d" % kb, wd4[:, kb * 64:(kb + 1) * 64]) for kb in range(2)]
-    assert len(expect) == 31
+    assert len(expect) == 23
 
     # p2_block_bytes / p2_half_off of csrc/chain_bf16.cu
     def block_bytes(blk):
         if blk <= 3:
             return 8192
-        if blk < 19:
-            return 8192 if (blk - 4) % 3 == 2 else 16384
+        if blk < 14:
+            return 32768 if (blk - 4) % 2 == 0 else 8192
+        if blk < 17:
+            return 32768
         return 16384
-    assert [w.shape[0] * 128 for _, w in expect] == [block_bytes(i) for i in range(31)]
-    half_total = sum(block_bytes(i) // 2 for i in range(31))
+    assert [w.shape[0] * 128 for _, w in expect] == [block_bytes(i) for i in range(23)]
+    half_total = sum(block_bytes(i) // 2 for i in range(23))
     assert half_total == 217088
     stream = pack.t["wstream"]
     assert stream.numel() * 2 == 2 * half_total
