@@ -1047,6 +1047,7 @@ struct Pass1Smem {
     uint64_t res_full, out4_ready;
     uint64_t act[2], acc[2];           // per tile of the pair
     uint64_t last_full[2], last_empty[2];
+    uint64_t stagger;                  // first half of chunk 0 of a pair has executed: the second issuer may start
     uint32_t tmem_base;
 };
 
@@ -1064,9 +1065,10 @@ seg_pass1_kernel(const Pass1Params p)
     if (threadIdx.x == 0) {
         for (int i = 0; i < kP1Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
         mbar_init(&s.res_full, 1);
-        mbar_init(&s.out4_ready, 2 * kEpiThreads);
+        mbar_init(&s.out4_ready, kEpiThreads);
+        mbar_init(&s.stagger, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s.act[i], kEpiThreads); mbar_init(&s.acc[i], 1);
+            mbar_init(&s.act[i], kEpiThreads / 2); mbar_init(&s.acc[i], 1);
             mbar_init(&s.last_full[i], 1); mbar_init(&s.last_empty[i], kEpiThreads);
         }
         fence_barrier_init();
@@ -1148,6 +1150,7 @@ seg_pass1_kernel(const Pass1Params p)
                             tc_fence_after();
                             mma_block_k64(tmem, smem_u32(s.wring[stage]), 128, a_out4 + kb * 8 * 4096, 256, id256, kb > 0);
                             mma_commit(&s.w_empty[stage]);
+                            if (cc == 0 && kb == 0) mma_commit(&s.stagger);
                         }
                         mma_commit(&s.last_full[0]);
                     }
@@ -1170,6 +1173,9 @@ seg_pass1_kernel(const Pass1Params p)
                 const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
                 for (int t = t0; t < t1; t += 2, ++pair_count) {
                     if (!mbar_wait(&s.out4_ready, o4_phase, 0x9401)) goto done;
+                    // start half a chunk behind the first issuer: the two chunks in flight then finish half a chunk apart,
+                    // and the pipe always has one of them to run while the epilogue drains the other's accumulator
+                    if (!mbar_wait(&s.stagger, o4_phase, 0x9402)) goto done;
                     o4_phase ^= 1; tc_fence_after();
 #pragma unroll 1
                     for (int cc = 1; cc < 8; cc += 2) {
@@ -1191,25 +1197,27 @@ seg_pass1_kernel(const Pass1Params p)
         // ------------------------------------------------------------ epilogue warps (256 threads)
         const int row = epi_row(), half = epi_half();
         const uint32_t tl = tmem + ((uint32_t)(row & ~31) << 16);
-        uint32_t acc_phase[2] = {0, 0}, lf_phase[2] = {0, 0};
+        uint32_t acc_phase = 0, lf_phase[2] = {0, 0};
         int it_local = 0;
         const bool ts_on = (threadIdx.x == 64);
-        float xq[2][8];
-        auto load_pair = [&](int ob, int t, int t1) {
+        // Front layers: warps 2-5 own tile X of the pair, warps 6-9 tile Y (q = half), each thread one whole point
+        // row, so the two tiles' serial chains (conv1 -> conv2 -> conv3 -> conv4, three tensor-core round trips) run
+        // side by side instead of interleaved in one thread's program order.
+        const int q = half;
+        const uint32_t tq_base = tl + q * 256;
+        float xv[8];
+        auto load_x = [&](int ob, int t, int t1) {
+            const int tq = (t + q < t1) ? t + q : t1 - 1;
+            int pidx = tq * kTile + row;
+            if (pidx > p.n - 1) pidx = p.n - 1;
+            const float *px = p.x + (int64_t)ob * p.sb + (int64_t)pidx * p.sp;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int tq = (t + q < t1) ? t + q : t1 - 1;
-                int pidx = tq * kTile + row;
-                if (pidx > p.n - 1) pidx = p.n - 1;
-                const float *px = p.x + (int64_t)ob * p.sb + (int64_t)pidx * p.sp;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) xq[q][c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
-            }
+            for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
         };
         if ((int)blockIdx.x < p.n_items) {
             const int sp0 = blockIdx.x % p.splits;
             const int f0 = (int)((int64_t)tiles_per_obj * sp0 / p.splits), f1 = (int)((int64_t)tiles_per_obj * (sp0 + 1) / p.splits);
-            if (f0 < f1) load_pair(blockIdx.x / p.splits, f0, f1);
+            if (f0 < f1) load_x(blockIdx.x / p.splits, f0, f1);
         }
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int b = item / p.splits, sp_i = item % p.splits;
@@ -1220,13 +1228,14 @@ seg_pass1_kernel(const Pass1Params p)
             for (int t = t0; t < t1; t += 2, ++it_local) {
                 int ts_i = 0;
                 AL3D_TSE();
-                // ---- conv1 of both tiles (an odd tail pair repeats its tile: the max is idempotent under duplicates).
-                //      The input points were prefetched during the previous pair's conv5 phase.
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    uint32_t o[16];
-                    conv1_pack32(xq[q], p.c_in, s.w1_w, s.w1_b, half * 32, o);
-                    tmem_st16(tl + q * 256 + half * 16, o);
+                // ---- conv1 of this thread's tile (an odd tail pair repeats its tile: the max is idempotent under
+                //      duplicates).  The input point was prefetched during the previous pair's conv5 phase.
+                {
+                    uint32_t o0[16], o1[16];
+                    conv1_pack32(xv, p.c_in, s.w1_w, s.w1_b, 0, o0);
+                    conv1_pack32(xv, p.c_in, s.w1_w, s.w1_b, 32, o1);
+                    tmem_st16(tq_base, o0);
+                    tmem_st16(tq_base + 16, o1);
                     tmem_st_wait(); tc_fence_before();
                     mbar_arrive(&s.act[q]);
                     AL3D_TSE();
@@ -1243,52 +1252,52 @@ seg_pass1_kernel(const Pass1Params p)
                             nt1 = (int)((int64_t)tiles_per_obj * (nsp + 1) / p.splits);
                         } else nt = -1;
                     }
-                    if (nt >= 0 && nt < nt1) load_pair(nb, nt, nt1);
+                    if (nt >= 0 && nt < nt1) load_x(nb, nt, nt1);
                 }
-                // ---- conv2, conv3 epilogues: accumulator -> packed operand of the next layer
+                // ---- conv2, conv3 epilogues: accumulator (64 columns) -> packed operand of the next layer
 #pragma unroll
                 for (int l = 0; l < 2; ++l) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8100 + l * 2 + q)) goto done;
-                        AL3D_TSE();
-                        acc_phase[q] ^= 1; tc_fence_after();
-                        uint32_t v[32], o[16];
-                        const uint32_t src = tl + q * 256 + (l == 0 ? 32 : 128) + half * 32;
-                        const uint32_t dst = tl + q * 256 + (l == 0 ? 96 : 192) + half * 16;
-                        tmem_ld32(src, v);
-                        tmem_ld_wait();
-                        pack_act32(v, (l == 0 ? s.b2 : s.b3) + half * 32, o);
-                        tmem_st16(dst, o);
-                        tmem_st_wait(); tc_fence_before();
-                        mbar_arrive(&s.act[q]);
-                        AL3D_TSE();
-                    }
-                }
-                // ---- conv4 epilogue: 64 of the 128 channels of this row -> shared-memory operand of conv5
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8200 + q)) goto done;
+                    if (!mbar_wait(&s.acc[q], acc_phase, 0x8100 + l * 2 + q)) goto done;
                     AL3D_TSE();
-                    acc_phase[q] ^= 1; tc_fence_after();
+                    acc_phase ^= 1; tc_fence_after();
                     uint32_t v0[32], v1[32], o0[16], o1[16];
-                    const uint32_t src = tl + q * 256 + half * 64;
+                    const uint32_t src = tq_base + (l == 0 ? 32 : 128);
+                    const uint32_t dst = tq_base + (l == 0 ? 96 : 192);
                     tmem_ld32(src, v0);
                     tmem_ld32(src + 32, v1);
                     tmem_ld_wait();
-                    tc_fence_before();
-                    pack_act32(v0, s.b4 + half * 64, o0);
-                    pack_act32(v1, s.b4 + half * 64 + 32, o1);
-                    uint8_t *dst = s.out4 + (size_t)(half * 8) * 4096 + (size_t)(q * kTile + row) * 16;
+                    pack_act32(v0, (l == 0 ? s.b2 : s.b3), o0);
+                    pack_act32(v1, (l == 0 ? s.b2 : s.b3) + 32, o1);
+                    tmem_st16(dst, o0);
+                    tmem_st16(dst + 16, o1);
+                    tmem_st_wait(); tc_fence_before();
+                    mbar_arrive(&s.act[q]);
+                    AL3D_TSE();
+                }
+                // ---- conv4 epilogue: the 128 channels of this row -> shared-memory operand of conv5
+                if (!mbar_wait(&s.acc[q], acc_phase, 0x8200 + q)) goto done;
+                AL3D_TSE();
+                acc_phase ^= 1; tc_fence_after();
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t v0[32], v1[32], o0[16], o1[16];
+                    const uint32_t src = tq_base + hh * 64;
+                    tmem_ld32(src, v0);
+                    tmem_ld32(src + 32, v1);
+                    tmem_ld_wait();
+                    pack_act32(v0, s.b4 + hh * 64, o0);
+                    pack_act32(v1, s.b4 + hh * 64 + 32, o1);
+                    uint8_t *dst = s.out4 + (size_t)(hh * 8) * 4096 + (size_t)(q * kTile + row) * 16;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         *reinterpret_cast<uint4 *>(dst + (size_t)j * 4096) = make_uint4(o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
                         *reinterpret_cast<uint4 *>(dst + (size_t)(4 + j) * 4096) = make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
                     }
-                    fence_proxy_async_smem();
-                    mbar_arrive(&s.out4_ready);
-                    AL3D_TSE();
                 }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&s.out4_ready);
+                AL3D_TSE();
                 // ---- conv5: this thread owns channel (cc*128 + row) and 128 of the pair's 256 points
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
