@@ -586,10 +586,11 @@ struct Pass2Params {
     int dbg_skip;                      // first recorded tile of the timeline (environment AL3D_DEBUG_SKIP)
 };
 
-// timeline stamps: role 0 = MMA thread, 1 = epilogue thread 0, 2 = producer; 64 stamps x 4 items each
+// timeline stamps: role 0 = MMA thread, 1 = epilogue thread 0 (CTA 0), 2 = epilogue thread 0 of CTA 1 (pass 2: the
+// peer of the pair; its clock is another SM's, compare durations only); 64 stamps x 4 items each
 #define AL3D_TS(role)                                                                         \
     do { const int ts_it = it_local - p.dbg_skip;                                             \
-         if (p.dbg && blockIdx.x == 0 && ts_it >= 0 && ts_it < 4 && ts_i < 64)                 \
+         if (p.dbg && blockIdx.x == ((role) == 2 ? 1 : 0) && ts_it >= 0 && ts_it < 4 && ts_i < 64) \
              p.dbg[((role) * 4 + ts_it) * 64 + ts_i++] = clock64(); } while (0)
 
 constexpr int kP2Blocks = 23;
@@ -619,8 +620,8 @@ struct Pass2Smem {
     float w1_w[64 * 8], w1_b[64], b2[64], gb[2][512], bd2[256], bd3[128], bd4[128], w5[256], b5[2];
     float lpart[2][2 * kTile];         // logits partial sums of the upper column half (double-buffered by tile parity)
     uint64_t res_full, res_peer;       // weights landed in this CTA / in the peer (leader only)
-    uint64_t act_f, acc_f, act_t, acc_t;   // front stream (conv1 / conv2 of the next tile) and tail stream (dconv2-4)
-    uint64_t d1_full[3], d1_act[3];
+    uint64_t act_f, act_f2, acc_f, act_t, acc_t;   // front stream (conv1 -> act_f, conv2 epilogue -> act_f2 of the next tile), tail stream
+    uint64_t d1_full[3], d1_act[3], d1_free[3];    // dconv1 chunk buffers: accumulator ready / bf16 image ready / consumed
     uint32_t tmem_base;
 };
 static_assert(sizeof(Pass2Smem) + 128 <= 232448, "Pass2Smem exceeds the 227 KB opt-in limit");
@@ -689,7 +690,7 @@ __device__ __forceinline__ void mma_pair_k64(uint32_t tmem_d, uint32_t a0, uint3
         mma_bf16_ts_pair(tmem_d, a[k], make_desc(b_addr + k * 2 * rows_half * 16, rows_half), idesc, (accumulate_first || k > 0) ? 1u : 0u);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + 32, 1)
 seg_pass2_kernel(const Pass2Params p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -706,7 +707,8 @@ seg_pass2_kernel(const Pass2Params p)
         mbar_init(&s.res_full, 1); mbar_init(&s.res_peer, 1);
         // epilogue -> MMA barriers live in the leader and collect one arrival per epilogue WARP of BOTH CTAs (an elected
         // lane arrives after the warp has synchronised: 8 remote transactions per hand-off instead of 256)
-        mbar_init(&s.act_f, 2 * kEpiThreads / 32); mbar_init(&s.act_t, 2 * kEpiThreads / 32);
+        mbar_init(&s.act_f, 2 * kEpiThreads / 32); mbar_init(&s.act_f2, 2 * kEpiThreads / 32); mbar_init(&s.act_t, 2 * kEpiThreads / 32);
+        for (int i = 0; i < 3; ++i) mbar_init(&s.d1_free[i], 1);
         mbar_init(&s.acc_f, 1); mbar_init(&s.acc_t, 1);
         for (int i = 0; i < 3; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], 2 * kEpiThreads / 32); }
         fence_barrier_init();
@@ -733,7 +735,7 @@ seg_pass2_kernel(const Pass2Params p)
             if (crank != 0) {
                 // tell the leader that the peer's weights are in place
                 if (!mbar_wait(&s.res_full, 0, 0xA1F0)) goto done;
-                mbar_arrive_remote(&s.res_peer, 0);
+                mbar_arrive_remote_release(&s.res_peer, 0);
             }
         }
     } else if (warp == 1) {
@@ -767,14 +769,6 @@ seg_pass2_kernel(const Pass2Params p)
                 ts_i = 0;
                 AL3D_TS(0);
                 const bool has_next = r + 1 < n_rounds;
-                // dconv1 chunks 0..2: A2 x Wd1[chunk] -> D1b[j]                     (blocks 1..3)
-                P2_WAIT(s.act_f, actf_phase, 0xA201)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    mma_pair_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, P2_W(1 + j), 32, id64, false);
-                    mma_commit_pair(&s.d1_full[j], 0x3);
-                }
-                AL3D_TS(0);
 #pragma unroll
                 for (int kc = 0; kc < 8; ++kc) {
                     const int j = kc % 3;
@@ -785,12 +779,7 @@ seg_pass2_kernel(const Pass2Params p)
                     const uint32_t a = tmem + kColD1 + j * 64;        // bf16 image of chunk kc (in place)
                     // one N = 256 instruction per K slice: the issuing thread, not the tensor pipe, bounded the N = 128 form
                     mma_pair_k64(tmem + kColD2, a, a + 8, a + 32, a + 40, P2_W(blk0), 128, id256, kc > 0);
-                    if (kc + 3 < 8) {
-                        // the MMA pipe executes in issue order, so this overwrite of D1b[j] happens after the
-                        // partial sums above have consumed it
-                        mma_pair_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24, P2_W(blk0 + 1), 32, id64, false);
-                        mma_commit_pair(&s.d1_full[j], 0x3);
-                    }
+                    if (kc + 3 < 8) mma_commit_pair(&s.d1_free[j], 0x1);   // chunk kc + 3 may overwrite D1b[j] once this has run
                 }
                 mma_commit_pair(&s.acc_t, 0x3);                            // dconv2 accumulator complete
                 // dconv3: A3 x Wd3 -> D3                                            (blocks 17..20)
@@ -812,11 +801,43 @@ seg_pass2_kernel(const Pass2Params p)
                     mma_pair_k64(tmem + kColD4, a, a + 8, a + 16, a + 24, P2_W(21 + kb), 64, id128, kb > 0);
                 }
                 mma_commit_pair(&s.acc_t, 0x3);
+                // D3 / A4 lived over D1b[0], D1b[1]: the next round's first two dconv1 chunks may go once dconv4 has run
+                mma_commit_pair(&s.d1_free[0], 0x1);
+                mma_commit_pair(&s.d1_free[1], 0x1);
                 AL3D_TS(0);
             }
 #undef P2_W
 #undef P2_WAIT
 #undef P2_ISSUE_CONV2
+        }
+    } else if (warp == kThreads / 32) {
+        // ------------------------------------------------------------ second MMA issuer (leader CTA only): dconv1 chunks.
+        // One issuing thread spends ~780 cycles per chunk group (a barrier wait, eight instructions, a commit) against
+        // ~640 cycles of tensor-pipe work, so the dconv1 chunks are issued from their own thread.  Its MMAs are not
+        // ordered against the first issuer's: d1_free[j] (committed behind the partial sum that read D1b[j], and behind
+        // dconv4 for the two buffers D3 / A4 were laid over) says when a chunk buffer may be overwritten.
+        if (lane == 0 && crank == 0) {
+            uint32_t actf2_phase = 0, d1free_phase[3] = {0, 0, 0};
+            const uint32_t id64 = make_idesc_bf16(256, 64);
+            const uint32_t wres = smem_u32(s.wres);
+            if (!mbar_wait(&s.res_full, 0, 0xA3FE)) goto done;
+            if (!mbar_wait_cluster(&s.res_peer, 0, 0xA3FF)) goto done;
+            for (int r = 0; r < n_rounds; ++r) {
+                if (!mbar_wait_cluster(&s.act_f2, actf2_phase, 0xA300)) goto done;      // A2 of this round's tiles is in place
+                actf2_phase ^= 1; tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int j = c % 3;
+                    if ((c >= 3 || (c < 2 && r > 0))) {
+                        if (!mbar_wait(&s.d1_free[j], d1free_phase[j], 0xA310 + c)) goto done;
+                        d1free_phase[j] ^= 1; tc_fence_after();
+                    }
+                    const int blk = c < 3 ? 1 + c : 5 + 2 * (c - 3);
+                    mma_pair_k64(tmem + kColD1 + j * 64, tmem + kColA2, tmem + kColA2 + 8, tmem + kColA2 + 16, tmem + kColA2 + 24,
+                                 wres + p2_half_off(blk), 32, id64, false);
+                    mma_commit_pair(&s.d1_full[j], 0x3);
+                }
+            }
         }
     } else {
         // ------------------------------------------------------------ epilogue warps (256 threads)
@@ -828,7 +849,7 @@ seg_pass2_kernel(const Pass2Params p)
         int it_local = 0;
         int ts_i = 0;
         const bool ts_on = (threadIdx.x == 64);
-#define AL3D_TSE() do { if (ts_on) AL3D_TS(1); } while (0)
+#define AL3D_TSE() do { if (ts_on) { if (blockIdx.x == 0) AL3D_TS(1); else AL3D_TS(2); } } while (0)
         // the epilogue -> MMA barriers are the leader's: the peer CTA arrives on them through the cluster address space
 #define P2_PUBLISH(bar) do { tmem_st_wait(); tc_fence_before(); __syncwarp();                                          \
                              if (lane == 0) { if (crank == 0) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); } } while (0)
@@ -864,7 +885,7 @@ seg_pass2_kernel(const Pass2Params p)
             tmem_ld_wait();
             pack_act32(v, s.b2 + half * 32, o);
             tmem_st16(tl + kColA2 + half * 16, o);
-            P2_PUBLISH(&s.act_f);
+            P2_PUBLISH(&s.act_f2);
             return true;
         };
         if (n_rounds > 0) {
@@ -1823,7 +1844,7 @@ extern "C" int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, 
     grid = ((grid + 1) / 2) * 2;                         // whole CTA pairs; a ghost CTA recomputes the last tile without output
     const size_t smem = sizeof(Pass2Smem) + 128;
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(seg_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    seg_pass2_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);     // __cluster_dims__(2,1,1)
+    seg_pass2_kernel<<<grid, kThreads + 32, smem, (cudaStream_t)stream>>>(p);     // __cluster_dims__(2,1,1)
     AL3D_CHECK_LAUNCH("seg_pass2_kernel");
     return 0;
 }

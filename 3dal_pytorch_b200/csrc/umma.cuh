@@ -120,6 +120,17 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank)
 {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    // default semantics (release at CTA scope), as for a local arrive: the data handed over lives in TMEM and is ordered by
+    // tcgen05.wait::st + tcgen05.fence::before_thread_sync, so no cluster-scope release of generic memory is needed -- the
+    // .release.cluster form stalled the arriving thread for ~250 cycles per hand-over (profiles/r1_pass2_peer_timeline.txt)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+// same with a cluster-scope release: for hand-overs of generic-proxy data (shared / global memory) to the other CTA
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t *bar, uint32_t rank)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 

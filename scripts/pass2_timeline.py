@@ -37,7 +37,7 @@ for k, kern in enumerate(["seg_pass2_kernel", "seg_pass1_kernel"]):
         continue
     t0 = int(d[d > 0].min())
     print("==== " + kern)
-    for role, name in enumerate(["mma", "epilogue", "producer"]):
+    for role, name in enumerate(["mma", "epilogue", "epilogue(CTA 1)"]):
         for it in range(4):
             ts = [int(v) - t0 for v in d[role, it] if v > 0]
             if not ts:
