@@ -32,6 +32,38 @@ constexpr int kThreads = 64 + kEpiThreads; // + producer warp + MMA warp
 __device__ __forceinline__ int epi_row() { return ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31); }
 __device__ __forceinline__ int epi_half() { return ((threadIdx.x >> 5) - 2) >> 2; }
 
+// packed fp32 pairs in one 64-bit register (sm_100 add / fma .f32x2): half the instructions of the scalar form
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_relu(uint64_t a)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+    return f2_pack(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+}
+__device__ __forceinline__ float f2_hsum(uint64_t a)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+    return lo + hi;
+}
+
 __device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi)
 {
     uint32_t d;
@@ -916,7 +948,9 @@ seg_pass2_kernel(const Pass2Params p)
                 const int nb = min(next_item, p.n_items - 1) / p.tiles_per_obj;
                 for (int i = etid; i < 512; i += kEpiThreads) s.gb[par ^ 1][i] = __ldg(p.gbias + (int64_t)nb * 512 + i);
             }
-            // ---- dconv1 chunk epilogues, in place
+            // ---- dconv1 chunk epilogues, in place.  (Moving the next tile's conv1 into these slots was tried: the loop
+            //      is bound by the buffer round trip epilogue -> partial sum -> dconv1 -> epilogue, so every cycle added
+            //      here lengthens it; net loss.)
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc) {
                 const int j = kc % 3;
@@ -989,7 +1023,8 @@ seg_pass2_kernel(const Pass2Params p)
                 tmem_ld_wait();
                 tc_fence_before();
                 AL3D_TSE();
-                float l0a = 0.f, l1a = 0.f, l0b = 0.f, l1b = 0.f;
+                // packed fp32 pairs (add / fma .f32x2): even channels accumulate in the low lane, odd ones in the high lane
+                uint64_t a0e = 0, a1e = 0, a0o = 0, a1o = 0;      // logit 0 / 1 sums over the v0 (e) and v1 (o) column batches
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 bb0 = *reinterpret_cast<const float4 *>(s.bd4 + c0 + i);
@@ -998,16 +1033,17 @@ seg_pass2_kernel(const Pass2Params p)
                     const float4 wb0 = *reinterpret_cast<const float4 *>(s.w5 + 128 + c0 + i);
                     const float4 wa1 = *reinterpret_cast<const float4 *>(s.w5 + c0 + 32 + i);
                     const float4 wb1 = *reinterpret_cast<const float4 *>(s.w5 + 128 + c0 + 32 + i);
-                    float a;
-                    a = fmaxf(__uint_as_float(v0[i + 0]) + bb0.x, 0.f); l0a = fmaf(a, wa0.x, l0a); l1a = fmaf(a, wb0.x, l1a);
-                    a = fmaxf(__uint_as_float(v0[i + 1]) + bb0.y, 0.f); l0a = fmaf(a, wa0.y, l0a); l1a = fmaf(a, wb0.y, l1a);
-                    a = fmaxf(__uint_as_float(v0[i + 2]) + bb0.z, 0.f); l0a = fmaf(a, wa0.z, l0a); l1a = fmaf(a, wb0.z, l1a);
-                    a = fmaxf(__uint_as_float(v0[i + 3]) + bb0.w, 0.f); l0a = fmaf(a, wa0.w, l0a); l1a = fmaf(a, wb0.w, l1a);
-                    a = fmaxf(__uint_as_float(v1[i + 0]) + bb1.x, 0.f); l0b = fmaf(a, wa1.x, l0b); l1b = fmaf(a, wb1.x, l1b);
-                    a = fmaxf(__uint_as_float(v1[i + 1]) + bb1.y, 0.f); l0b = fmaf(a, wa1.y, l0b); l1b = fmaf(a, wb1.y, l1b);
-                    a = fmaxf(__uint_as_float(v1[i + 2]) + bb1.z, 0.f); l0b = fmaf(a, wa1.z, l0b); l1b = fmaf(a, wb1.z, l1b);
-                    a = fmaxf(__uint_as_float(v1[i + 3]) + bb1.w, 0.f); l0b = fmaf(a, wa1.w, l0b); l1b = fmaf(a, wb1.w, l1b);
+                    uint64_t t;
+                    t = f2_relu(f2_add(f2_pack(__uint_as_float(v0[i + 0]), __uint_as_float(v0[i + 1])), f2_pack(bb0.x, bb0.y)));
+                    a0e = f2_fma(t, f2_pack(wa0.x, wa0.y), a0e); a1e = f2_fma(t, f2_pack(wb0.x, wb0.y), a1e);
+                    t = f2_relu(f2_add(f2_pack(__uint_as_float(v0[i + 2]), __uint_as_float(v0[i + 3])), f2_pack(bb0.z, bb0.w)));
+                    a0e = f2_fma(t, f2_pack(wa0.z, wa0.w), a0e); a1e = f2_fma(t, f2_pack(wb0.z, wb0.w), a1e);
+                    t = f2_relu(f2_add(f2_pack(__uint_as_float(v1[i + 0]), __uint_as_float(v1[i + 1])), f2_pack(bb1.x, bb1.y)));
+                    a0o = f2_fma(t, f2_pack(wa1.x, wa1.y), a0o); a1o = f2_fma(t, f2_pack(wb1.x, wb1.y), a1o);
+                    t = f2_relu(f2_add(f2_pack(__uint_as_float(v1[i + 2]), __uint_as_float(v1[i + 3])), f2_pack(bb1.z, bb1.w)));
+                    a0o = f2_fma(t, f2_pack(wa1.z, wa1.w), a0o); a1o = f2_fma(t, f2_pack(wb1.z, wb1.w), a1o);
                 }
+                const float l0a = f2_hsum(a0e), l1a = f2_hsum(a1e), l0b = f2_hsum(a0o), l1b = f2_hsum(a1o);
                 const float l0 = l0a + l0b, l1 = l1a + l1b;
                 if (half == 1) { s.lpart[par][row] = l0; s.lpart[par][kTile + row] = l1; }
                 AL3D_TSE();
