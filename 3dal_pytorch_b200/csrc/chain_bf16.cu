@@ -396,7 +396,7 @@ chain_max_kernel(const ChainParams p)
     uint8_t *const s_wring = s_bufB + p.bufB_bytes;
     ChainSmemTail &s = *reinterpret_cast<ChainSmemTail *>(s_wring + (size_t)p.n_stages * kStageBytes);
     const int kChainStages = p.n_stages;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
 
     for (int i = threadIdx.x; i < p.w0 * 8; i += kThreads) s.w0_w[i] = p.w0_w[i];
     for (int i = threadIdx.x; i < p.w0; i += kThreads) s.w0_b[i] = p.w0_b[i];
@@ -423,7 +423,7 @@ chain_max_kernel(const ChainParams p)
 
     if (warp == 0) {
         // ------------------------------------------------------------ weight producer (one thread)
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int sp_i = item % p.splits;
@@ -448,7 +448,7 @@ chain_max_kernel(const ChainParams p)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t wphase = 0, act_phase = 0, le_phase[2] = {0, 0};
             const uint32_t aA = smem_u32(s_bufA), aB = smem_u32(s_bufB);
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -757,7 +757,7 @@ seg_pass2_kernel(const Pass2Params p)
 
     if (warp == 0) {
         // ------------------------------------------------------------ weight loader: this CTA's half of every block, once
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(&s.res_full, kP2HalfBytes);
             const uint8_t *src = p.wstream + (size_t)crank * kP2HalfBytes;
             for (uint32_t off = 0; off < kP2HalfBytes; off += 16384) {
@@ -776,7 +776,7 @@ seg_pass2_kernel(const Pass2Params p)
         // with its own pair of barriers, so the next tiles' conv1/conv2 are computed while this round's serial tail is
         // in flight.  Every MMA is a cta_group::2 instruction covering both CTAs' tiles; every commit is multicast to
         // both CTAs' barriers.
-        if (lane == 0 && crank == 0) {
+        if (crank == 0 && elect_one_sync()) {
             uint32_t actf_phase = 0, actt_phase = 0, d1a_phase[3] = {0, 0, 0};
             const uint32_t id64 = make_idesc_bf16(256, 64), id128 = make_idesc_bf16(256, 128), id256 = make_idesc_bf16(256, 256);
             const uint32_t wres = smem_u32(s.wres);
@@ -848,7 +848,7 @@ seg_pass2_kernel(const Pass2Params p)
         // ~640 cycles of tensor-pipe work, so the dconv1 chunks are issued from their own thread.  Its MMAs are not
         // ordered against the first issuer's: d1_free[j] (committed behind the partial sum that read D1b[j], and behind
         // dconv4 for the two buffers D3 / A4 were laid over) says when a chunk buffer may be overwritten.
-        if (lane == 0 && crank == 0) {
+        if (crank == 0 && elect_one_sync()) {
             uint32_t actf2_phase = 0, d1free_phase[3] = {0, 0, 0};
             const uint32_t id64 = make_idesc_bf16(256, 64);
             const uint32_t wres = smem_u32(s.wres);
@@ -1114,7 +1114,7 @@ seg_pass1_kernel(const Pass1Params p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Pass1Smem &s = *reinterpret_cast<Pass1Smem *>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
 
     for (int i = threadIdx.x; i < 64 * 8; i += kThreads) s.w1_w[i] = p.w1_w[i];
     for (int i = threadIdx.x; i < 64; i += kThreads) { s.w1_b[i] = p.w1_b[i]; s.b2[i] = p.b2[i]; s.b3[i] = p.b3[i]; }
@@ -1139,7 +1139,7 @@ seg_pass1_kernel(const Pass1Params p)
 
     if (warp == 0) {
         // ------------------------------------------------------------ producer: resident front weights, then W5 ring
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(&s.res_full, 8192 + 8192 + 16384);
             bulk_g2s(s.wfront, p.wfront, 8192, &s.res_full);
             bulk_g2s(s.wfront + 8192, p.wfront + kStageBytes, 8192, &s.res_full);
@@ -1160,7 +1160,7 @@ seg_pass1_kernel(const Pass1Params p)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t act_phase[2] = {0, 0}, le_phase[2] = {0, 0}, o4_phase = 0;
             int pair_count = 0;
             const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128), id256 = make_idesc_bf16(128, 256);
@@ -1220,7 +1220,7 @@ seg_pass1_kernel(const Pass1Params p)
         // One thread cannot keep the tensor pipe busy here: per chunk it spends ~1.4k cycles on 8 N = 256 instructions,
         // three waits and three commits against 1.0k cycles of execution (scripts/mma_microbench.py), so the chunks
         // alternate between two issuing threads.  Chunks are independent (own accumulator buffer, own barriers).
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t le_phase1 = 0, o4_phase = 0;
             const uint32_t id256 = make_idesc_bf16(128, 256);
             const uint32_t a_out4 = smem_u32(s.out4);
@@ -1471,7 +1471,7 @@ trunk_pair_kernel(const TrunkParams p)
 
     if (warp == 0) {
         // ------------------------------------------------------------ weight producer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             auto push = [&](int blk, uint32_t bytes) -> bool {
                 if (!mbar_wait(&w_empty[stage], phase ^ 1, 0x7100 + stage)) return false;
@@ -1494,7 +1494,7 @@ trunk_pair_kernel(const TrunkParams p)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0; uint32_t wphase = 0, act_phase = 0, o3_phase = 0, le_phase[2] = {0, 0};
             const uint32_t id2 = make_idesc_bf16(128, M1), id128 = make_idesc_bf16(128, 128), id256 = make_idesc_bf16(128, 256);
             const uint32_t a_out3 = smem_u32(s_out3), ring = smem_u32(s_ring);

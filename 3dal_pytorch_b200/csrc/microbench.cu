@@ -42,7 +42,7 @@ mma_microbench_kernel(int N, int n_groups, int bg, const uint8_t *src, long long
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
-    if (threadIdx.x == 32) {
+    auto issue = [&]() {
         const uint32_t idesc = make_idesc_bf16(128, N);
         const uint32_t a_addr = smem_u32(s.a), b_addr = smem_u32(s.b);
         uint64_t da[4], db[4];
@@ -72,6 +72,12 @@ mma_microbench_kernel(int N, int n_groups, int bg, const uint8_t *src, long long
             out[2] = t_first - t0;         // issue time of the first 8 MMAs (queue empty)
         }
         s.stop = 1;
+    };
+    if (warp == 1) {
+        // the same loop entered through `lane == 0` or through elect.sync: ptxas wraps every tcgen05 instruction of the
+        // former in an ELECT / branch loop (it cannot prove a single active lane)
+        if (bg & 4) { if (elect_one_sync()) issue(); }
+        else if (threadIdx.x == 32) issue();
     } else if (threadIdx.x == 0 && (bg & 2)) {
         // background: stream 16 KB blocks global -> shared like a weight ring (src: >= 1 MiB)
         uint32_t ph[2] = {0, 0};

@@ -22,6 +22,21 @@ constexpr long long kWaitTimeoutCycles = 1ll << 31;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp, chosen by elect.sync.  Single-thread regions that issue tcgen05 / bulk-copy
+// instructions should be entered through this and not through `lane == 0`: ptxas knows an elect.sync region has exactly
+// one active lane and issues the uniform-datapath instructions (UTCHMMA, UTCBAR ...) directly, whereas in a region it
+// cannot prove single-lane it wraps EVERY such instruction in an ELECT / branch loop over the active lanes.
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {

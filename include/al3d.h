@@ -250,7 +250,8 @@ int al3d_umma_selftest_pair_ss(const void *a_kp_halves, const void *b_kp_halves,
 /* Development aid: issue n_mma tcgen05.mma (M = 128, N, K = 16; mode 0 = both operands in shared memory, 1 = A from
  * TMEM) from one thread on each of n_ctas CTAs, a commit every commit_every MMAs (0 = only at the end).
  * background: bit 0 = four warps read the accumulator columns with tcgen05.ld meanwhile, bit 1 = one thread streams
- * 16 KB blocks from src_1mib (device, >= 1 MiB) into shared memory meanwhile.
+ * 16 KB blocks from src_1mib (device, >= 1 MiB) into shared memory meanwhile, bit 2 = the issuing lane is chosen with
+ * elect.sync instead of `lane == 0`.
  * out (6 int64, CTA 0): issue cycles, cycles to completion, issue cycles of the first 8, background blocks, background
  * loads, scratch.  scripts/mma_microbench.py. */
 int al3d_mma_microbench(int N, int n_mma, int commit_every, int mode, int n_ctas, int background, const void *src_1mib,

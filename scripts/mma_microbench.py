@@ -18,11 +18,11 @@ n_sm = torch.cuda.get_device_properties(0).multi_processor_count
 print("N mode commit_every ctas background | issue_cycles total_cycles cycles_per_mma first8_issue bg_blocks bg_loads")
 n = 2048
 for ctas in (1, n_sm):
-    for bg in (0, 1, 2, 3):
+    for bg in (0, 4, 1, 2, 3):
         for mode in (0, 1):
             for N in (64, 128, 256):
                 for ce in (0, 8, 4):
-                    if bg and ce != 8:
+                    if bg not in (0, 4) and ce != 8:
                         continue
                     for _ in range(2):
                         out.zero_()
