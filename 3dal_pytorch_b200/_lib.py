@@ -66,7 +66,7 @@ def lib():
             fn = getattr(l, name)
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
-        if l.al3d_abi_version() != 1:
+        if l.al3d_abi_version() != 2:
             raise RuntimeError("libal3d.so ABI version mismatch")
         _lib = l
     return _lib

@@ -14,6 +14,7 @@
 // ring, warp 1 (one thread) issues tcgen05.mma, warps 2-5 own the 128 TMEM lanes and run every
 // epilogue.  BatchNorm is folded into the weights by the host; ReLU and bias are applied in the epilogue.
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/al3d.h"
@@ -702,6 +703,34 @@ __device__ __forceinline__ void conv1_pack32(const float (&xv)[8], int c_in, con
     else                conv1_pack32_t<0, WS>(xv, c_in, w_t, bias, ch0, o);
 }
 
+// Constant-bank variants: bias / conv1 weights that live in the kernel parameter block are read as instruction operands
+// (c[0][..]) when every index is a compile-time constant -- no load instruction, no shared-memory bandwidth.  (An
+// LDS.128 broadcast still returns 512 B per warp through the 128 B/clk shared-memory data path: the per-point conv1
+// weights and the epilogue biases, read that way by every epilogue warp, cost more than the arithmetic.)
+template <int OFF, int N>
+__device__ __forceinline__ void pack_act32_cb(const uint32_t (&v)[32], const float (&bias)[N], uint32_t (&o)[16])
+{
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        o[j] = relu_pack_bf16x2(__uint_as_float(v[2 * j]) + bias[OFF + 2 * j], __uint_as_float(v[2 * j + 1]) + bias[OFF + 2 * j + 1]);
+}
+// conv1 for 32 output channels CH0..CH0+31 of a 64-channel layer: w (8 x 64, input-channel-major) and b from the
+// parameter block; same arithmetic order as conv1_pack32 (bias, then input channels in order)
+template <int CIN, int CH0>
+__device__ __forceinline__ void conv1_pack32_cb(const float (&xv)[8], const float (&w)[512], const float (&b)[64], uint32_t (&o)[16])
+{
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float a0 = b[CH0 + 2 * j], a1 = b[CH0 + 2 * j + 1];
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            a0 = fmaf(xv[c], w[c * 64 + CH0 + 2 * j], a0);
+            a1 = fmaf(xv[c], w[c * 64 + CH0 + 2 * j + 1], a1);
+        }
+        o[j] = relu_pack_bf16x2(a0, a1);
+    }
+}
+
 // 4 MMAs (K = 64) with A in TMEM: a_col[s] is the TMEM column of K-slice s (8 columns each)
 __device__ __forceinline__ void mma_ts_k64(uint32_t tmem_d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                            uint32_t b_addr, uint32_t rows_b, uint32_t idesc, bool accumulate_first)
@@ -1070,17 +1099,24 @@ done:
 
 
 // ================================================================================================
-// seg_pass1_kernel -- ins_seg conv1..conv5 + max over points, tiles processed in PAIRS
+// seg_pass1_kernel -- ins_seg conv1..conv5 + max over points, tile PAIRS, warp-specialised pipeline
 //
-// conv2-4 run with their activations in TMEM (as in seg_pass2_kernel), their 32 KB of weights resident in
-// shared memory.  conv4's output of both tiles of a pair is written to one 256-row shared-memory operand, and
-// conv5 is computed transposed with N = 256 points per MMA: every streamed 16 KB block of conv5 weights is
-// used for 256 points instead of 128, halving the L2 -> smem weight traffic that bounded the 128-point
-// version, and the max over points stays a per-thread reduction over TMEM columns.
-//
-// TMEM: tile X uses columns [0,256), tile Y [256,512) during the front layers
-//   (+0 A1 | +32 D(conv2) | +96 A2 | +128 D(conv3) | +192 A3 | D(conv4) reuses +0..+127);
-// conv5 then double-buffers its 256-column accumulators over the same two halves.
+// A STEP is a pair of 128-point tiles (X, Y) of one (object, split) item.  conv5 is computed TRANSPOSED per tile
+// (M = 128 channels, N = 128 points, K = 128; eight channel chunks), so the max over points is a per-thread reduction
+// over TMEM columns and each streamed 16 KB conv5 block serves both tiles (256 points).  While the tensor pipe runs
+// conv5 of step i, the front layers (conv1 on CUDA cores, conv2-4 with their A operand in TMEM and their 32 KB of
+// weights resident in shared memory) of step i+1 run beside it into the other half of a double-buffered shared-memory
+// operand -- nothing of the front sits on conv5's critical path.  Roles (384 threads):
+//   warp 0      producer: resident front weights once, then the conv5 weight ring (cp.async.bulk)
+//   warp 1, 10  conv5 issuers, tile X / tile Y (own accumulator, own barriers; they alternate on the pipe)
+//   warp 11     front issuer: conv2, conv3, conv4 (two N = 64 halves) of the next step's two tiles, interleaved
+//   warps 2-5   reducers: drain the conv5 accumulators (tcgen05.ld), running max in registers, atomicMax per object
+//   warps 6-9   front epilogues: conv1, accumulator -> bf16 operand conversions, conv4 output -> shared memory
+// Every epilogue thread owns one whole point row (TMEM lane) of what it touches, so there are no cross-warp hazards
+// inside a TMEM region.  TMEM: [0,128) conv5 accumulator of X | [128,256) of Y | [256,384) front region of X' |
+// [384,512) front region of Y'.  Front region (128 columns, R = its base):
+//   R+96 A1 (conv1, bf16) -> conv2 -> R+0 D2 (64) -> R+0 A2 (32, in place) -> conv3 -> R+32 D3 (64) -> R+96 A3 (over
+//   the dead A1) -> conv4 channels 0-63 -> R+0 D4a -> shared memory -> conv4 channels 64-127 -> R+0 D4b -> shared memory.
 // ================================================================================================
 struct Pass1Params {
     const float *x; int64_t sb, sc, sp; int bs, n; int c_in;
@@ -1091,42 +1127,83 @@ struct Pass1Params {
     float *out;                        // (bs, 1024) zero-initialised
     int splits, n_items;
     long long *dbg;                    // optional clock64 timeline (al3d_set_debug_buffer), else NULL
-    int dbg_skip;                      // first recorded tile pair of the timeline (environment AL3D_DEBUG_SKIP)
+    int dbg_skip;                      // first recorded step of the timeline (environment AL3D_DEBUG_SKIP)
+    // copies in the parameter block (constant bank): operands of the front warps' arithmetic, no loads
+    float w1c[512], b1c[64], b2c[64], b3c[64], b4c[128];
 };
 
-constexpr int kP1Stages = 7;
+constexpr int kP1Stages = 4;
+constexpr uint32_t kP1FrontCol = 256;  // front regions: X' at 256, Y' at 384
 struct Pass1Smem {
-    uint8_t out4[16 * 4096];           // conv4 output of the tile pair: KP tile of 256 rows x 128 channels
+    uint8_t out4[2][16 * 4096];        // conv4 output of a tile pair: KP tile of 256 rows x 128 channels, double-buffered
     uint8_t wfront[32768];             // resident conv2 (8 KB) | conv3 (8 KB) | conv4 (16 KB) weights
     uint8_t wring[kP1Stages][kStageBytes];
-    float w1_w[64 * 8], w1_b[64], b2[64], b3[64], b4[128];
+    float w1_w[64 * 8], w1_b[64];     // conv2-4 biases are read through the read-only cache (no room here)
     uint64_t w_full[kP1Stages], w_empty[kP1Stages];
-    uint64_t res_full, out4_ready;
-    uint64_t act[2], acc[2];           // per tile of the pair
-    uint64_t last_full[2], last_empty[2];
-    uint64_t stagger;                  // first half of chunk 0 of a pair has executed: the second issuer may start
+    uint64_t res_full;
+    uint64_t out4_ready, out4_free;    // front warps -> conv5 issuers (operand written) and back (operand consumed)
+    uint64_t act[2], acc[2];           // front hand-overs per tile: operand in TMEM / accumulator complete
+    uint64_t c5_full[2], c5_empty[2];  // conv5 accumulator of tile X / Y: complete / drained
     uint32_t tmem_base;
 };
+static_assert(sizeof(Pass1Smem) + 128 <= 232448, "Pass1Smem exceeds the 227 KB opt-in limit");
 
-constexpr int kP1Threads = kThreads + 32;     // producer, MMA issuer, 8 epilogue warps, second MMA issuer
+// Steps of a CTA: items blockIdx.x, blockIdx.x + gridDim.x, ...; within an item tiles t, t+2, ... (two tiles per step)
+struct P1Step { int item, b, t, t1; bool valid; };
+__device__ __forceinline__ void p1_item_range(const Pass1Params &p, int tiles_per_obj, int item, int &b, int &t0, int &t1)
+{
+    const int sp_i = item % p.splits;
+    b = item / p.splits;
+    t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits);
+    t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+}
+__device__ __forceinline__ P1Step p1_seek(const Pass1Params &p, int tiles_per_obj, int stride, P1Step s)
+{
+    s.valid = false;
+    while (s.item < p.n_items) {
+        int t0;
+        p1_item_range(p, tiles_per_obj, s.item, s.b, t0, s.t1);
+        if (t0 < s.t1) { s.t = t0; s.valid = true; break; }
+        s.item += stride;
+    }
+    return s;
+}
+__device__ __forceinline__ P1Step p1_first(const Pass1Params &p, int tiles_per_obj, int first, int stride)
+{
+    P1Step s; s.item = first; s.b = 0; s.t = 0; s.t1 = 0; s.valid = false;
+    return p1_seek(p, tiles_per_obj, stride, s);
+}
+__device__ __forceinline__ P1Step p1_next(const Pass1Params &p, int tiles_per_obj, int stride, P1Step s)
+{
+    if (!s.valid) return s;
+    s.t += 2;
+    if (s.t < s.t1) return s;
+    s.item += stride;
+    return p1_seek(p, tiles_per_obj, stride, s);
+}
+
+constexpr int kP1Threads = kThreads + 64;
 __global__ void __launch_bounds__(kP1Threads, 1)
 seg_pass1_kernel(const Pass1Params p)
 {
+#define P1_TS(role)                                                                                   \
+    do { const int ts_it = it_local - p.dbg_skip;                                                     \
+         if (p.dbg && blockIdx.x == 0 && ts_it >= 0 && ts_it < 4 && ts_i < 64)                         \
+             p.dbg[((role) * 4 + ts_it) * 64 + ts_i++] = clock64(); } while (0)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Pass1Smem &s = *reinterpret_cast<Pass1Smem *>(smem_raw);
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < 64 * 8; i += kThreads) s.w1_w[i] = p.w1_w[i];
-    for (int i = threadIdx.x; i < 64; i += kThreads) { s.w1_b[i] = p.w1_b[i]; s.b2[i] = p.b2[i]; s.b3[i] = p.b3[i]; }
-    for (int i = threadIdx.x; i < 128; i += kThreads) s.b4[i] = p.b4[i];
+    for (int i = threadIdx.x; i < 64 * 8; i += kP1Threads) s.w1_w[i] = p.w1_w[i];
+    for (int i = threadIdx.x; i < 64; i += kP1Threads) s.w1_b[i] = p.w1_b[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kP1Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+        for (int i = 0; i < kP1Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 2); }
         mbar_init(&s.res_full, 1);
-        mbar_init(&s.out4_ready, kEpiThreads);
-        mbar_init(&s.stagger, 1);
+        mbar_init(&s.out4_ready, 2 * 4);                                // front warps x tiles
+        mbar_init(&s.out4_free, 2);                                     // the two conv5 issuers
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s.act[i], kEpiThreads / 2); mbar_init(&s.acc[i], 1);
-            mbar_init(&s.last_full[i], 1); mbar_init(&s.last_empty[i], kEpiThreads);
+            mbar_init(&s.act[i], 4); mbar_init(&s.acc[i], 1);
+            mbar_init(&s.c5_full[i], 1); mbar_init(&s.c5_empty[i], 4);
         }
         fence_barrier_init();
     }
@@ -1136,241 +1213,130 @@ seg_pass1_kernel(const Pass1Params p)
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
     const int tiles_per_obj = (p.n + kTile - 1) / kTile;
+    const int stride = (int)gridDim.x;
+#define P1_ARRIVE(bar) do { __syncwarp(); if (lane == 0) mbar_arrive(bar); } while (0)
 
     if (warp == 0) {
-        // ------------------------------------------------------------ producer: resident front weights, then W5 ring
+        // ------------------------------------------------------------ producer: resident front weights, then the conv5 ring
         if (elect_one_sync()) {
             mbar_arrive_expect_tx(&s.res_full, 8192 + 8192 + 16384);
             bulk_g2s(s.wfront, p.wfront, 8192, &s.res_full);
             bulk_g2s(s.wfront + 8192, p.wfront + kStageBytes, 8192, &s.res_full);
             bulk_g2s(s.wfront + 16384, p.wfront + 2 * kStageBytes, 16384, &s.res_full);
             int stage = 0; uint32_t phase = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int sp_i = item % p.splits;
-                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
-                for (int t = t0; t < t1; t += 2) {
-                    for (int blk = 0; blk < 16; ++blk) {
-                        if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x9100 + stage)) goto done;
-                        mbar_arrive_expect_tx(&s.w_full[stage], kStageBytes);
-                        bulk_g2s(s.wring[stage], p.w5stream + (size_t)blk * kStageBytes, kStageBytes, &s.w_full[stage]);
-                        if (++stage == kP1Stages) { stage = 0; phase ^= 1; }
-                    }
+            for (P1Step st = p1_first(p, tiles_per_obj, blockIdx.x, stride); st.valid; st = p1_next(p, tiles_per_obj, stride, st)) {
+                for (int blk = 0; blk < 16; ++blk) {
+                    if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x9100 + stage)) goto done;
+                    mbar_arrive_expect_tx(&s.w_full[stage], kStageBytes);
+                    bulk_g2s(s.wring[stage], p.w5stream + (size_t)blk * kStageBytes, kStageBytes, &s.w_full[stage]);
+                    if (++stage == kP1Stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
+    } else if (warp == 1 || warp == kThreads / 32) {
+        // ------------------------------------------------------------ conv5 issuers: warp 1 -> tile X, warp 10 -> tile Y
         if (elect_one_sync()) {
-            uint32_t act_phase[2] = {0, 0}, le_phase[2] = {0, 0}, o4_phase = 0;
-            int pair_count = 0;
-            const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128), id256 = make_idesc_bf16(128, 256);
-            const uint32_t wf0 = smem_u32(s.wfront), wf1 = wf0 + 8192, wf2 = wf0 + 16384;
-            const uint32_t a_out4 = smem_u32(s.out4);
+            const int q = (warp == 1) ? 0 : 1;
+            uint32_t o4_phase = 0, ce_phase = 0;
+            const uint32_t id128 = make_idesc_bf16(128, 128);
+            const uint32_t o4[2] = {smem_u32(s.out4[0]), smem_u32(s.out4[1])};
+            const uint32_t d = tmem + q * 128;
+            int ob = 0, g = 0, it_local = 0, ts_i = 0;
+            for (P1Step st = p1_first(p, tiles_per_obj, blockIdx.x, stride); st.valid; st = p1_next(p, tiles_per_obj, stride, st), ++it_local) {
+                ts_i = 0;
+                if (q == 0) P1_TS(0);
+                if (!mbar_wait(&s.out4_ready, o4_phase, 0x9400 + q)) goto done;
+                o4_phase ^= 1; tc_fence_after();
+                if (q == 0) P1_TS(0);
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    if (!mbar_wait(&s.c5_empty[q], ce_phase ^ 1, 0x9500 + q)) goto done;
+                    ce_phase ^= 1; tc_fence_after();
+                    if (q == 0) P1_TS(0);
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb, ++g) {
+                        const int stage = g % kP1Stages;
+                        if (!mbar_wait(&s.w_full[stage], (uint32_t)(g / kP1Stages) & 1u, 0x9600 + stage)) goto done;
+                        tc_fence_after();
+                        const uint32_t wa = smem_u32(s.wring[stage]);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            mma_bf16(d, make_desc(wa + k4 * 4096, 128),
+                                     make_desc_lbo(o4[ob] + q * 2048 + (kb * 8 + k4 * 2) * 4096, 4096), id128, (kb > 0 || k4 > 0) ? 1u : 0u);
+                        mma_commit(&s.w_empty[stage]);           // the stage is free once BOTH tiles' issuers have consumed it
+                    }
+                    mma_commit(&s.c5_full[q]);
+                    if (q == 0) P1_TS(0);
+                }
+                mma_commit(&s.out4_free);                         // this tile's reads of out4[ob] are done
+                ob ^= 1;
+            }
+        }
+    } else if (warp == kThreads / 32 + 1) {
+        // ------------------------------------------------------------ front issuer: conv2, conv3, conv4a, conv4b of both
+        // tiles of every step, interleaved (X, Y, X, Y ...) as the front warps hand the operands over
+        if (elect_one_sync()) {
+            uint32_t act_phase[2] = {0, 0};
+            const uint32_t id64 = make_idesc_bf16(128, 64);
+            const uint32_t wf = smem_u32(s.wfront);
             if (!mbar_wait(&s.res_full, 0, 0x9200)) goto done;
             tc_fence_after();
-            int it_local = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int sp_i = item % p.splits;
-                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
-                for (int t = t0; t < t1; t += 2, ++it_local) {
-                    int ts_i = 0;
-                    AL3D_TS(0);
-                    // front layers, the two tiles interleaved: while the epilogue converts X, the tensor core works on Y
-#pragma unroll
-                    for (int l = 0; l < 3; ++l) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const uint32_t base = tmem + q * 256;
-                            if (!mbar_wait(&s.act[q], act_phase[q], 0x9300 + l * 2 + q)) goto done;
-                            AL3D_TS(0);
-                            act_phase[q] ^= 1; tc_fence_after();
-                            if (l == 0)      mma_ts_k64(base + 32, base, base + 8, base + 16, base + 24, wf0, 64, id64, false);
-                            else if (l == 1) mma_ts_k64(base + 128, base + 96, base + 104, base + 112, base + 120, wf1, 64, id64, false);
-                            else             mma_ts_k64(base, base + 192, base + 200, base + 208, base + 216, wf2, 128, id128, false);
-                            mma_commit(&s.acc[q]);
-                        }
-                    }
-                    // conv5, transposed, N = 256 points (both tiles): D^T[128 channels x 256 points]; this thread issues
-                    // the even channel chunks (accumulator buffer 0), the second issuer (warp 10) the odd ones
-                    if (!mbar_wait(&s.out4_ready, o4_phase, 0x9400)) goto done;
-                    AL3D_TS(0);
-                    o4_phase ^= 1; tc_fence_after();
+            for (P1Step st = p1_first(p, tiles_per_obj, blockIdx.x, stride); st.valid; st = p1_next(p, tiles_per_obj, stride, st)) {
 #pragma unroll 1
-                    for (int cc = 0; cc < 8; cc += 2) {
-                        if (!mbar_wait(&s.last_empty[0], le_phase[0] ^ 1, 0x9500)) goto done;
-                        AL3D_TS(0);
-                        le_phase[0] ^= 1; tc_fence_after();
-                        for (int kb = 0; kb < 2; ++kb) {
-                            const int g = pair_count * 16 + cc * 2 + kb, stage = g % kP1Stages;
-                            if (!mbar_wait(&s.w_full[stage], (uint32_t)(g / kP1Stages) & 1u, 0x9600 + stage)) goto done;
-                            AL3D_TS(0);
-                            tc_fence_after();
-                            mma_block_k64(tmem, smem_u32(s.wring[stage]), 128, a_out4 + kb * 8 * 4096, 256, id256, kb > 0);
-                            mma_commit(&s.w_empty[stage]);
-                            if (cc == 0 && kb == 0) mma_commit(&s.stagger);
+                for (int l = 0; l < 4; ++l) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const uint32_t R = tmem + kP1FrontCol + q * 128;
+                        if (!mbar_wait(&s.act[q], act_phase[q], 0x9300 + l * 2 + q)) goto done;
+                        act_phase[q] ^= 1; tc_fence_after();
+                        if (l == 0)      mma_ts_k64(R, R + 96, R + 104, R + 112, R + 120, wf, 64, id64, false);              // conv2
+                        else if (l == 1) mma_ts_k64(R + 32, R, R + 8, R + 16, R + 24, wf + 8192, 64, id64, false);          // conv3
+                        else {
+                            // conv4, output channels (l-2)*64 .. +64: rows of the 128-row KP tile (plane stride 2048 B)
+                            const uint32_t wb = wf + 16384 + (l - 2) * 64 * 16;
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                mma_bf16_ts(R, R + 96 + k4 * 8, make_desc_lbo(wb + k4 * 4096, 2048), id64, k4 > 0 ? 1u : 0u);
                         }
-                        mma_commit(&s.last_full[0]);
-                    }
-                    ++pair_count;
-                }
-            }
-        }
-    } else if (warp == kThreads / 32) {
-        // ------------------------------------------------------------ second MMA issuer: odd conv5 chunks (buffer 1).
-        // One thread cannot keep the tensor pipe busy here: per chunk it spends ~1.4k cycles on 8 N = 256 instructions,
-        // three waits and three commits against 1.0k cycles of execution (scripts/mma_microbench.py), so the chunks
-        // alternate between two issuing threads.  Chunks are independent (own accumulator buffer, own barriers).
-        if (elect_one_sync()) {
-            uint32_t le_phase1 = 0, o4_phase = 0;
-            const uint32_t id256 = make_idesc_bf16(128, 256);
-            const uint32_t a_out4 = smem_u32(s.out4);
-            int pair_count = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int sp_i = item % p.splits;
-                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
-                for (int t = t0; t < t1; t += 2, ++pair_count) {
-                    if (!mbar_wait(&s.out4_ready, o4_phase, 0x9401)) goto done;
-                    // start half a chunk behind the first issuer: the two chunks in flight then finish half a chunk apart,
-                    // and the pipe always has one of them to run while the epilogue drains the other's accumulator
-                    if (!mbar_wait(&s.stagger, o4_phase, 0x9402)) goto done;
-                    o4_phase ^= 1; tc_fence_after();
-#pragma unroll 1
-                    for (int cc = 1; cc < 8; cc += 2) {
-                        if (!mbar_wait(&s.last_empty[1], le_phase1 ^ 1, 0x9501)) goto done;
-                        le_phase1 ^= 1; tc_fence_after();
-                        for (int kb = 0; kb < 2; ++kb) {
-                            const int g = pair_count * 16 + cc * 2 + kb, stage = g % kP1Stages;
-                            if (!mbar_wait(&s.w_full[stage], (uint32_t)(g / kP1Stages) & 1u, 0x9610 + stage)) goto done;
-                            tc_fence_after();
-                            mma_block_k64(tmem + 256, smem_u32(s.wring[stage]), 128, a_out4 + kb * 8 * 4096, 256, id256, kb > 0);
-                            mma_commit(&s.w_empty[stage]);
-                        }
-                        mma_commit(&s.last_full[1]);
+                        mma_commit(&s.acc[q]);
                     }
                 }
             }
         }
-    } else {
-        // ------------------------------------------------------------ epilogue warps (256 threads)
-        const int row = epi_row(), half = epi_half();
+    } else if (warp < 6) {
+        // ------------------------------------------------------------ reducers (warps 2-5): thread = channel row of a chunk.
+        // (Tried and slower: separate reducer warps per tile -- the two conv5 streams then finish and drain together, or, when
+        // forced to alternate, hold their weight stages too long for the 4-stage ring; all four tcgen05.ld of a tile in flight
+        // at once -- the drain is bound by TMEM bandwidth under the running MMAs, not by load latency.)
+        const int row = epi_row();
         const uint32_t tl = tmem + ((uint32_t)(row & ~31) << 16);
-        uint32_t acc_phase = 0, lf_phase[2] = {0, 0};
-        int it_local = 0;
+        uint32_t cf_phase[2] = {0, 0};
+        int it_local = 0, ts_i = 0;
         const bool ts_on = (threadIdx.x == 64);
-        // Front layers: warps 2-5 own tile X of the pair, warps 6-9 tile Y (q = half), each thread one whole point
-        // row, so the two tiles' serial chains (conv1 -> conv2 -> conv3 -> conv4, three tensor-core round trips) run
-        // side by side instead of interleaved in one thread's program order.
-        const int q = half;
-        const uint32_t tq_base = tl + q * 256;
-        float xv[8];
-        auto load_x = [&](int ob, int t, int t1) {
-            const int tq = (t + q < t1) ? t + q : t1 - 1;
-            int pidx = tq * kTile + row;
-            if (pidx > p.n - 1) pidx = p.n - 1;
-            const float *px = p.x + (int64_t)ob * p.sb + (int64_t)pidx * p.sp;
+        float rmax[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
-        };
-        if ((int)blockIdx.x < p.n_items) {
-            const int sp0 = blockIdx.x % p.splits;
-            const int f0 = (int)((int64_t)tiles_per_obj * sp0 / p.splits), f1 = (int)((int64_t)tiles_per_obj * (sp0 + 1) / p.splits);
-            if (f0 < f1) load_x(blockIdx.x / p.splits, f0, f1);
-        }
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const int b = item / p.splits, sp_i = item % p.splits;
-            const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
-            float rmax[8];
+        for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
+        P1Step cur = p1_first(p, tiles_per_obj, blockIdx.x, stride);
+        while (cur.valid) {
+            const P1Step nxt = p1_next(p, tiles_per_obj, stride, cur);
+            ts_i = 0;
+            if (ts_on) P1_TS(1);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
-            for (int t = t0; t < t1; t += 2, ++it_local) {
-                int ts_i = 0;
-                AL3D_TSE();
-                // ---- conv1 of this thread's tile (an odd tail pair repeats its tile: the max is idempotent under
-                //      duplicates).  The input point was prefetched during the previous pair's conv5 phase.
-                {
-                    uint32_t o0[16], o1[16];
-                    conv1_pack32(xv, p.c_in, s.w1_w, s.w1_b, 0, o0);
-                    conv1_pack32(xv, p.c_in, s.w1_w, s.w1_b, 32, o1);
-                    tmem_st16(tq_base, o0);
-                    tmem_st16(tq_base + 16, o1);
-                    tmem_st_wait(); tc_fence_before();
-                    mbar_arrive(&s.act[q]);
-                    AL3D_TSE();
-                }
-                // prefetch the next pair of this item (or the first pair of the CTA's next item)
-                {
-                    int nb = b, nt = t + 2, nt1 = t1;
-                    if (nt >= t1) {
-                        const int nitem = item + gridDim.x;
-                        if (nitem < p.n_items) {
-                            const int nsp = nitem % p.splits;
-                            nb = nitem / p.splits;
-                            nt = (int)((int64_t)tiles_per_obj * nsp / p.splits);
-                            nt1 = (int)((int64_t)tiles_per_obj * (nsp + 1) / p.splits);
-                        } else nt = -1;
-                    }
-                    if (nt >= 0 && nt < nt1) load_x(nb, nt, nt1);
-                }
-                // ---- conv2, conv3 epilogues: accumulator (64 columns) -> packed operand of the next layer
+            for (int c = 0; c < 8; ++c) {
 #pragma unroll
-                for (int l = 0; l < 2; ++l) {
-                    if (!mbar_wait(&s.acc[q], acc_phase, 0x8100 + l * 2 + q)) goto done;
-                    AL3D_TSE();
-                    acc_phase ^= 1; tc_fence_after();
-                    uint32_t v0[32], v1[32], o0[16], o1[16];
-                    const uint32_t src = tq_base + (l == 0 ? 32 : 128);
-                    const uint32_t dst = tq_base + (l == 0 ? 96 : 192);
-                    tmem_ld32(src, v0);
-                    tmem_ld32(src + 32, v1);
-                    tmem_ld_wait();
-                    pack_act32(v0, (l == 0 ? s.b2 : s.b3), o0);
-                    pack_act32(v1, (l == 0 ? s.b2 : s.b3) + 32, o1);
-                    tmem_st16(dst, o0);
-                    tmem_st16(dst + 16, o1);
-                    tmem_st_wait(); tc_fence_before();
-                    mbar_arrive(&s.act[q]);
-                    AL3D_TSE();
-                }
-                // ---- conv4 epilogue: the 128 channels of this row -> shared-memory operand of conv5
-                if (!mbar_wait(&s.acc[q], acc_phase, 0x8200 + q)) goto done;
-                AL3D_TSE();
-                acc_phase ^= 1; tc_fence_after();
+                for (int q = 0; q < 2; ++q) {
+                    if (!mbar_wait(&s.c5_full[q], cf_phase[q], 0x8300 + c * 2 + q)) goto done;
+                    cf_phase[q] ^= 1; tc_fence_after();
+                    if (ts_on) P1_TS(1);
+                    float m0 = rmax[c], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t v0[32], v1[32], o0[16], o1[16];
-                    const uint32_t src = tq_base + hh * 64;
-                    tmem_ld32(src, v0);
-                    tmem_ld32(src + 32, v1);
-                    tmem_ld_wait();
-                    pack_act32(v0, s.b4 + hh * 64, o0);
-                    pack_act32(v1, s.b4 + hh * 64 + 32, o1);
-                    uint8_t *dst = s.out4 + (size_t)(hh * 8) * 4096 + (size_t)(q * kTile + row) * 16;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        *reinterpret_cast<uint4 *>(dst + (size_t)j * 4096) = make_uint4(o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
-                        *reinterpret_cast<uint4 *>(dst + (size_t)(4 + j) * 4096) = make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
-                    }
-                }
-                tc_fence_before();
-                fence_proxy_async_smem();
-                mbar_arrive(&s.out4_ready);
-                AL3D_TSE();
-                // ---- conv5: this thread owns channel (cc*128 + row) and 128 of the pair's 256 points
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    const int bsel = cc & 1;
-                    if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0x8300 + cc)) goto done;
-                    AL3D_TSE();
-                    lf_phase[bsel] ^= 1; tc_fence_after();
-                    float m0 = rmax[cc], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-                    for (int c0 = 0; c0 < 128; c0 += 64) {
+                    for (int hh = 0; hh < 2; ++hh) {
                         uint32_t v0[32], v1[32];
-                        const uint32_t ta = tl + bsel * 256 + half * 128 + c0;
+                        const uint32_t ta = tl + q * 128 + hh * 64;
                         tmem_ld32(ta, v0);
                         tmem_ld32(ta + 32, v1);
                         tmem_ld_wait();
-                        if (c0 == 64) { tc_fence_before(); mbar_arrive(&s.last_empty[bsel]); }   // all values are in registers
+                        if (hh == 1) { tc_fence_before(); P1_ARRIVE(&s.c5_empty[q]); }     // all 128 values are in registers
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
                             m0 = fmax3(m0, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
@@ -1383,21 +1349,122 @@ seg_pass1_kernel(const Pass1Params p)
                             m3 = fmax3(m3, __uint_as_float(v1[i + 6]), __uint_as_float(v1[i + 7]));
                         }
                     }
-                    rmax[cc] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                    AL3D_TSE();
+                    rmax[c] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    if (ts_on) P1_TS(1);
                 }
             }
-            // ---- publish: relu(max + bias) >= 0, so integer atomicMax on the bit pattern is exact
-            if (t1 > t0) {
+            if (!nxt.valid || nxt.item != cur.item) {
+                // ---- item finished: relu(max + bias) >= 0, so integer atomicMax on the bit pattern is exact
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    const int ch = cc * 128 + row;
-                    const float v = fmaxf(rmax[cc] + __ldg(p.b5 + ch), 0.f);
-                    atomicMax(reinterpret_cast<int *>(p.out + (int64_t)b * 1024 + ch), __float_as_int(v));
+                for (int c = 0; c < 8; ++c) {
+                    const int ch = c * 128 + row;
+                    const float v = fmaxf(rmax[c] + __ldg(p.b5 + ch), 0.f);
+                    atomicMax(reinterpret_cast<int *>(p.out + (int64_t)cur.b * 1024 + ch), __float_as_int(v));
+                    rmax[c] = -INFINITY;
                 }
             }
+            cur = nxt;
+            ++it_local;
+        }
+    } else {
+        // ------------------------------------------------------------ front warps (6-9): thread = point row of both tiles
+        const int row = epi_row();
+        const uint32_t tl = tmem + ((uint32_t)(row & ~31) << 16) + kP1FrontCol;
+        uint32_t acc_phase[2] = {0, 0}, of_phase = 0;
+        int it_local = 0, ts_i = 0;
+        const bool ts_on = (threadIdx.x == 6 * 32);
+        float xq[2][8];
+        auto load_pair = [&](const P1Step &st) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int tq = (st.t + q < st.t1) ? st.t + q : st.t1 - 1;          // odd tail: repeat the last tile (max is idempotent)
+                int pidx = tq * kTile + row;
+                if (pidx > p.n - 1) pidx = p.n - 1;
+                const float *px = p.x + (int64_t)st.b * p.sb + (int64_t)pidx * p.sp;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) xq[q][c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+            }
+        };
+        P1Step cur = p1_first(p, tiles_per_obj, blockIdx.x, stride);
+        if (cur.valid) load_pair(cur);
+        int step = 0;
+        while (cur.valid) {
+            const P1Step nxt = p1_next(p, tiles_per_obj, stride, cur);
+            const int buf = step & 1;
+            ts_i = 0;
+            if (ts_on) P1_TS(2);
+            // ---- conv1 (CUDA cores, 64 channels of this point) -> A1
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint32_t o0[16], o1[16];
+                if (p.c_in == 3)      { conv1_pack32_cb<3, 0>(xq[q], p.w1c, p.b1c, o0); conv1_pack32_cb<3, 32>(xq[q], p.w1c, p.b1c, o1); }
+                else if (p.c_in == 4) { conv1_pack32_cb<4, 0>(xq[q], p.w1c, p.b1c, o0); conv1_pack32_cb<4, 32>(xq[q], p.w1c, p.b1c, o1); }
+                else                  { conv1_pack32(xq[q], p.c_in, s.w1_w, s.w1_b, 0, o0); conv1_pack32(xq[q], p.c_in, s.w1_w, s.w1_b, 32, o1); }
+                tmem_st16(tl + q * 128 + 96, o0);
+                tmem_st16(tl + q * 128 + 112, o1);
+                tmem_st_wait(); tc_fence_before();
+                P1_ARRIVE(&s.act[q]);
+            }
+            if (ts_on) P1_TS(2);
+            if (nxt.valid) load_pair(nxt);                                 // prefetch the next step's points
+            // ---- conv2 / conv3 epilogues: 64 accumulator columns -> bias + ReLU -> bf16 operand of the next layer
+#pragma unroll
+            for (int l = 0; l < 2; ++l) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8100 + l * 2 + q)) goto done;
+                    acc_phase[q] ^= 1; tc_fence_after();
+                    uint32_t v0[32], v1[32], o0[16], o1[16];
+                    const uint32_t R = tl + q * 128;
+                    tmem_ld32(R + (l == 0 ? 0 : 32), v0);
+                    tmem_ld32(R + (l == 0 ? 0 : 32) + 32, v1);
+                    tmem_ld_wait();
+                    if (l == 0) { pack_act32_cb<0>(v0, p.b2c, o0); pack_act32_cb<32>(v1, p.b2c, o1); }
+                    else        { pack_act32_cb<0>(v0, p.b3c, o0); pack_act32_cb<32>(v1, p.b3c, o1); }
+                    tmem_st16(R + (l == 0 ? 0 : 96), o0);
+                    tmem_st16(R + (l == 0 ? 0 : 96) + 16, o1);
+                    tmem_st_wait(); tc_fence_before();
+                    P1_ARRIVE(&s.act[q]);
+                    if (ts_on) P1_TS(2);
+                }
+            }
+            // ---- conv4 epilogues (two 64-channel halves): -> shared-memory operand of conv5, rows of tile q.
+            //      out4[buf] was last read by conv5 two steps ago: wait until both conv5 issuers have released it.
+            if (step >= 2) {
+                if (!mbar_wait(&s.out4_free, of_phase, 0x8400)) goto done;
+                of_phase ^= 1;
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8200 + hh * 2 + q)) goto done;
+                    acc_phase[q] ^= 1; tc_fence_after();
+                    uint32_t v0[32], v1[32], o0[16], o1[16];
+                    const uint32_t R = tl + q * 128;
+                    tmem_ld32(R, v0);
+                    tmem_ld32(R + 32, v1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    if (hh == 0) P1_ARRIVE(&s.act[q]);                     // D4a is in registers: conv4b may overwrite it
+                    if (hh == 0) { pack_act32_cb<0>(v0, p.b4c, o0); pack_act32_cb<32>(v1, p.b4c, o1); }
+                    else         { pack_act32_cb<64>(v0, p.b4c, o0); pack_act32_cb<96>(v1, p.b4c, o1); }
+                    uint8_t *dst = s.out4[buf] + (size_t)(hh * 8) * 4096 + (size_t)(q * kTile + row) * 16;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        *reinterpret_cast<uint4 *>(dst + (size_t)j * 4096) = make_uint4(o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
+                        *reinterpret_cast<uint4 *>(dst + (size_t)(4 + j) * 4096) = make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+                    }
+                    if (hh == 1) { fence_proxy_async_smem(); P1_ARRIVE(&s.out4_ready); }
+                    if (ts_on) P1_TS(2);
+                }
+            }
+            cur = nxt;
+            ++step; ++it_local;
         }
     }
+#undef P1_ARRIVE
+#undef P1_TS
 done:
     tc_fence_before();
     __syncthreads();
@@ -1843,6 +1910,12 @@ extern "C" int al3d_seg_pass1_bf16(const al3d_pass1_weights *w, const float *x, 
     p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n; p.c_in = w->c_in;
     p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.b3 = w->b3; p.b4 = w->b4; p.b5 = w->b5;
     p.wfront = (const uint8_t *)w->wfront; p.w5stream = (const uint8_t *)w->w5stream; p.out = out;
+    AL3D_CHECK_ARG(w->host_consts, "al3d_seg_pass1_bf16: host_consts is null");
+    {
+        const float *h = w->host_consts;
+        std::memcpy(p.w1c, h, sizeof(p.w1c)); std::memcpy(p.b1c, h + 512, sizeof(p.b1c)); std::memcpy(p.b2c, h + 576, sizeof(p.b2c));
+        std::memcpy(p.b3c, h + 640, sizeof(p.b3c)); std::memcpy(p.b4c, h + 704, sizeof(p.b4c));
+    }
     p.dbg = g_debug_buffer ? g_debug_buffer + 3 * 4 * 64 : nullptr;      // second half of the debug buffer
     p.dbg_skip = debug_skip();
     const int tiles = (n + kTile - 1) / kTile;

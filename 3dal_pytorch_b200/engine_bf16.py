@@ -27,7 +27,8 @@ class ChainWeightsStruct(ctypes.Structure):
 class Pass1WeightsStruct(ctypes.Structure):
     _fields_ = [("c_in", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("w1_w", ctypes.c_void_p), ("w1_b", ctypes.c_void_p), ("b2", ctypes.c_void_p), ("b3", ctypes.c_void_p),
-                ("b4", ctypes.c_void_p), ("b5", ctypes.c_void_p), ("wfront", ctypes.c_void_p), ("w5stream", ctypes.c_void_p)]
+                ("b4", ctypes.c_void_p), ("b5", ctypes.c_void_p), ("wfront", ctypes.c_void_p), ("w5stream", ctypes.c_void_p),
+                ("host_consts", ctypes.c_void_p)]
 
 
 class Pass2WeightsStruct(ctypes.Structure):
@@ -132,6 +133,10 @@ class SegPack:
         s1.c_in = c_in
         for k, v in self.t1.items():
             setattr(s1, k, v.data_ptr())
+        # small per-model constants the kernel takes in its parameter block (constant-bank operands): HOST copy
+        self.host_consts = torch.cat([self.t1[k].detach().float().cpu().reshape(-1) for k in ("w1_w", "w1_b", "b2", "b3", "b4")]).contiguous()
+        assert self.host_consts.numel() == 832
+        s1.host_consts = self.host_consts.data_ptr()
         self.struct1 = s1
         # the 1024-wide half of dconv1 acts on the per-object global feature: kept fp32
         self.w_glob = wd1[:, 64:]

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AL3D_ABI_VERSION 1
+#define AL3D_ABI_VERSION 2
 
 /* activation flags for al3d_linear_f32 */
 #define AL3D_ACT_NONE 0
@@ -210,6 +210,8 @@ typedef struct al3d_pass1_weights {
     const float *b2, *b3, *b4, *b5;    /* conv2-5 biases (64),(64),(128),(1024)                         */
     const void  *wfront;               /* conv2, conv3, conv4 packed bf16, one 16 KB slot each          */
     const void  *w5stream;             /* conv5: 16 packed blocks of 128 channels x 64 K, (chunk, k-block) order */
+    const float *host_consts;          /* HOST memory, 832 floats: w1_w (512) | w1_b (64) | b2 (64) | b3 (64) | b4 (128) --
+                                          copied into the kernel parameter block (constant bank operands)          */
 } al3d_pass1_weights;
 
 /* First half of PointNetInstanceSeg.forward (tools/static_model.py:279-284): conv1..conv5 (+BN+ReLU) and the
