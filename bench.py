@@ -238,8 +238,6 @@ def main():
     # ---------------- timed region: inputs resident in HBM
     if os.environ.get("AL3D_CUDA_PROFILER_RANGE") == "1":      # for `ncu --profile-from-start off`
         torch.cuda.cudart().cudaProfilerStart()
-    eb.KERNEL_EVENTS = {}
-    launches0 = lib.LAUNCHES
     sampler = ClockSampler(dev)
     if world > 1:
         dist.barrier()
@@ -250,6 +248,8 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t_begin = sampler.mark()
+    eb.KERNEL_EVENTS = {}                   # per-kernel CUDA events and the launch count cover the K timed steps only
+    launches0 = lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
