@@ -12,10 +12,22 @@ from . import ops
 
 
 class StaticAutoLabeler:
-    def __init__(self, model, chunk_tracks=2048):
+    def __init__(self, model, chunk_tracks=2048, first_chunk_tracks=None):
         self.model = model
         self.chunk = int(chunk_tracks)
+        # the first chunk's H2D copy is the only one not hidden behind compute: keep it small
+        self.first = int(first_chunk_tracks) if first_chunk_tracks else max(1, self.chunk // 4)
         self._staging = None
+
+    def _schedule(self, T):
+        """Chunk boundaries: a short first chunk, then full chunks."""
+        bounds, t0 = [], 0
+        size = min(self.first, self.chunk)
+        while t0 < T:
+            t1 = min(T, t0 + size)
+            bounds.append((t0, t1))
+            t0, size = t1, self.chunk
+        return bounds
 
     @torch.no_grad()
     def label_device(self, pts, init_box, bbox_gt=None):
@@ -45,8 +57,7 @@ class StaticAutoLabeler:
         bufs, copy_stream = self._buffers(n, dev)
         main = torch.cuda.current_stream(dev)
         free_ev = [None, None]
-        for ci, t0 in enumerate(range(0, T, self.chunk)):
-            t1 = min(T, t0 + self.chunk)
+        for ci, (t0, t1) in enumerate(self._schedule(T)):
             k = t1 - t0
             dp, db = bufs[ci & 1]
             with torch.cuda.stream(copy_stream):

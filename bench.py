@@ -221,7 +221,8 @@ def main():
         lg = model(pts[:256], init_box[:256], None)["logits"]
     synth.calibrate_seg_margin(sd, lg, fg_fraction=0.125)
     model.load_state_dict(sd)
-    labeler = pipeline.StaticAutoLabeler(model, chunk_tracks=min(T, int(os.environ.get("AL3D_E2E_CHUNK", "2048"))))
+    labeler = pipeline.StaticAutoLabeler(model, chunk_tracks=min(T, int(os.environ.get("AL3D_E2E_CHUNK", "2048"))),
+                                         first_chunk_tracks=int(os.environ.get("AL3D_E2E_FIRST", "0")) or None)
     gathered = torch.empty((world * T, 7), device=dev, dtype=torch.float32) if world > 1 else None
 
     def step():
