@@ -155,6 +155,7 @@ struct CropChunk { int32_t frame; int32_t first_pt; int32_t n_pts; int32_t chunk
 constexpr int kCropWarps = kCropThreads / 32;
 constexpr int kCropWarpPts = kCropChunk / kCropWarps;     // consecutive points owned by one warp
 constexpr int kCropQueue = 320;                           // per-warp candidate queue (>= 31 + 32 * kMaxHitsPerPoint)
+constexpr int kCropLook = 2;                              // cell-list entries fetched ahead per point
 
 __global__ void __launch_bounds__(kCropThreads)
 crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
@@ -246,6 +247,13 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                 }
             }
         }
+        // the first kCropLook entries of every point's cell list: U * kCropLook independent loads, one round trip
+        // (the per-point loop below used to walk its list one dependent load pair at a time)
+        int bj[U][kCropLook];
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+#pragma unroll
+            for (int j = 0; j < kCropLook; ++j) bj[k][j] = (e0[k] + j < e1[k]) ? __ldg(cb + e0[k] + j) : -1;
 #pragma unroll
         for (int k = 0; k < U; ++k) {
             const int i = i0 + k * 32 + lane;
@@ -261,7 +269,21 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                             ++nc;
                         }
                 } else {
-                    for (int e = e0[k]; e < e1[k]; ++e) {
+                    // padded boxes of the prefetched entries: their loads are independent of each other
+                    float2 lo[kCropLook], mid[kCropLook], hi[kCropLook];
+#pragma unroll
+                    for (int j = 0; j < kCropLook; ++j) {
+                        const int b = max(bj[k][j], 0);
+                        lo[j] = __ldg(bb + b * 3); mid[j] = __ldg(bb + b * 3 + 1); hi[j] = __ldg(bb + b * 3 + 2);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kCropLook; ++j)
+                        if (bj[k][j] >= 0 && px[k] >= lo[j].x && py[k] >= lo[j].y && pz[k] >= mid[j].x && px[k] <= mid[j].y &&
+                            py[k] <= hi[j].x && pz[k] <= hi[j].y) {
+                            if (nc < kMaxHitsPerPoint) cand[nc] = bj[k][j]; else atomicExch(overflow, 2);
+                            ++nc;
+                        }
+                    for (int e = e0[k] + kCropLook; e < e1[k]; ++e) {               // longer lists (rare): the rest, one at a time
                         const int b = __ldg(cb + e);
                         const float2 lo = __ldg(bb + b * 3), mid = __ldg(bb + b * 3 + 1), hi = __ldg(bb + b * 3 + 2);
                         // aabb = [xmin ymin | zmin xmax | ymax zmax], padded: never rejects a point the exact test accepts
@@ -327,7 +349,8 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     for (int b = threadIdx.x; b < B; b += blockDim.x) chunk_box_count[(int64_t)blockIdx.x * max_boxes + b] = s_box_cnt[b];
 }
 
-// per frame: for every box an exclusive scan over the frame's chunks; box totals
+// per frame: for every box an exclusive scan over the frame's chunks; box totals.  One WARP per box: the lanes
+// take 32 consecutive chunks at a time (shuffle scan), so a frame's ~90 chunks cost three round trips, not ninety.
 __global__ void crop_scan_kernel(const int64_t *__restrict__ box_off, const int64_t *__restrict__ frame_chunk_off,
                                  int32_t *__restrict__ chunk_box_count, int max_boxes, int32_t *__restrict__ box_total)
 {
@@ -335,14 +358,18 @@ __global__ void crop_scan_kernel(const int64_t *__restrict__ box_off, const int6
     const int64_t b0 = box_off[f];
     const int B = (int)(box_off[f + 1] - b0);
     const int64_t c0 = frame_chunk_off[f], c1 = frame_chunk_off[f + 1];
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int b = blockIdx.y * n_warps + wid; b < B; b += gridDim.y * n_warps) {
         int run = 0;
-        for (int64_t c = c0; c < c1; ++c) {
-            const int v = chunk_box_count[c * max_boxes + b];
-            chunk_box_count[c * max_boxes + b] = run;
-            run += v;
+        for (int64_t cb = c0; cb < c1; cb += 32) {
+            const int64_t c = cb + lane;
+            const int v = c < c1 ? chunk_box_count[c * max_boxes + b] : 0;
+            int incl = v;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (c < c1) chunk_box_count[c * max_boxes + b] = run + incl - v;
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
-        box_total[b0 + b] = run;
+        if (lane == 0) box_total[b0 + b] = run;
     }
 }
 
@@ -455,7 +482,7 @@ extern "C" int al3d_crop_scan(const int64_t *box_off, const int64_t *frame_chunk
 {
     AL3D_CHECK_ARG(box_off && frame_chunk_off && chunk_box_count && box_total && offsets, "al3d_crop_scan: null pointer");
     if (n_frames > 0) {
-        crop_scan_kernel<<<n_frames, 256, 0, (cudaStream_t)stream>>>(box_off, frame_chunk_off, chunk_box_count, max_boxes, box_total);
+        crop_scan_kernel<<<dim3(n_frames, 4), 256, 0, (cudaStream_t)stream>>>(box_off, frame_chunk_off, chunk_box_count, max_boxes, box_total);
         AL3D_CHECK_LAUNCH("crop_scan_kernel");
     }
     crop_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(box_total, n_boxes, offsets);
