@@ -163,7 +163,7 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                  const CropGridMeta *__restrict__ meta, const int32_t *__restrict__ cell_start,
                  const int32_t *__restrict__ cell_boxes, int cell_cap, const CropChunk *__restrict__ chunks,
                  int2 *__restrict__ hits, int hit_cap, int32_t *__restrict__ n_hits, int32_t *__restrict__ chunk_box_count,
-                 int max_boxes, int32_t *__restrict__ overflow)
+                 int max_boxes, int rank_boxes, int32_t *__restrict__ overflow)
 {
     // Each warp owns kCropWarpPts CONSECUTIVE points and walks them 32 at a time.  A lane looks up the boxes
     // registered in its point's BEV cell and keeps those whose padded bounding box contains the point; these
@@ -177,6 +177,7 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     int2 *s_stage = s_queue + kCropWarps * kCropQueue;                  // kCropWarps x stage_cap
     __shared__ int warp_total[kCropWarps];
     const int stage_cap = min(hit_cap, kCropWarpPts * kMaxHitsPerPoint); // per warp (its worst case); the chunk total is capped at hit_cap
+    int32_t *s_wcnt = reinterpret_cast<int32_t *>(s_stage + (size_t)kCropWarps * stage_cap);   // kCropWarps x rank_boxes per-warp box counts
     const CropChunk ck = chunks[blockIdx.x];
     const int f = ck.frame;
     const int64_t b0 = box_off[f];
@@ -190,6 +191,8 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     const float2 *bb = reinterpret_cast<const float2 *>(aabb) + b0 * 3;
     int2 *my_hits = hits + (int64_t)blockIdx.x * hit_cap;      // .x = point index in frame, .y = box | rank << 16
     for (int b = threadIdx.x; b < B; b += blockDim.x) s_box_cnt[b] = 0;
+    const bool par_rank = B <= rank_boxes;                            // ranking by all warps in parallel (else one warp, serially)
+    if (par_rank) for (int t = threadIdx.x; t < kCropWarps * rank_boxes; t += blockDim.x) s_wcnt[t] = 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int2 *queue = s_queue + wid * kCropQueue;
     int2 *stage = s_stage + (size_t)wid * stage_cap;
@@ -316,14 +319,45 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     while (qcount > 0) drain(min(qcount, 32));
     if (wcount > stage_cap) wcount = stage_cap;
     if (lane == 0) warp_total[wid] = wcount;
+    // ---- rank of every hit among the hits of the same box in this chunk (point order).
+    //      Parallel form: every warp first ranks its own (ordered) list against its own per-box counters -- 32 hits at a
+    //      time, equal boxes inside a group ranked by lane -- then adds the counts of the warps before it.
+    if (par_rank) {
+        int32_t *mine = s_wcnt + wid * rank_boxes;
+        for (int h0 = 0; h0 < wcount; h0 += 32) {
+            const int h = h0 + lane;
+            const bool act = h < wcount;
+            const int2 e = act ? stage[h] : make_int2(0, -1 - lane);
+            const unsigned same = __match_any_sync(0xffffffffu, e.y);
+            if (act) stage[h] = make_int2(e.x, e.y | ((mine[e.y] + __popc(same & ((1u << lane) - 1u))) << 16));
+            __syncwarp();
+            if (act && (same >> lane) == 1u) mine[e.y] += __popc(same);          // highest lane of each group updates
+            __syncwarp();
+        }
+    }
     __syncthreads();
     int before = 0, total = 0;
     for (int w = 0; w < kCropWarps; ++w) { if (w < wid) before += warp_total[w]; total += warp_total[w]; }
     if (before + wcount > hit_cap) atomicExch(overflow, 3);
     total = min(total, hit_cap);
     if (threadIdx.x == 0) n_hits[blockIdx.x] = total;
-    // ---- rank of every hit among the hits of the same box in this chunk (point order): one warp walks the
-    //      ordered list 32 at a time; equal boxes inside a group are ranked by lane.
+    if (par_rank) {
+        for (int h = lane; h < wcount; h += 32) {
+            const int2 e = stage[h];
+            const int box = e.y & 0xFFFF;
+            int prefix = 0;
+            for (int w = 0; w < wid; ++w) prefix += s_wcnt[w * rank_boxes + box];
+            if (before + h < hit_cap) my_hits[before + h] = make_int2(e.x, e.y + (prefix << 16));
+        }
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            int sum = 0;
+#pragma unroll
+            for (int w = 0; w < kCropWarps; ++w) sum += s_wcnt[w * rank_boxes + b];
+            chunk_box_count[(int64_t)blockIdx.x * max_boxes + b] = sum;
+        }
+        return;
+    }
+    // Serial form (frames with more boxes than the per-warp counter table holds): one warp walks the whole ordered list.
     if (wid == 0) {
         int g0 = 0;                                                    // global position of the current warp list
         for (int w = 0; w < kCropWarps; ++w) {
@@ -465,14 +499,16 @@ extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int6
     AL3D_CHECK_ARG(max_boxes >= 1 && max_boxes <= 12288, "al3d_crop_hits: max_boxes=%d not in [1,12288]", max_boxes);
     AL3D_CHECK_ARG(hit_cap >= 1 && hit_cap <= 16384, "al3d_crop_hits: hit_cap=%d not in [1,16384]", hit_cap);
     if (n_chunks <= 0) return 0;
+    const int rank_boxes = max_boxes <= 512 ? max_boxes : 0;          // per-warp box counters for the parallel ranking, if modest
     const size_t smem = (size_t)((max_boxes + 1) & ~1) * sizeof(int32_t) + (size_t)kCropWarps * kCropQueue * sizeof(int2) +
-                        (size_t)kCropWarps * std::min(hit_cap, kCropWarpPts * kMaxHitsPerPoint) * sizeof(int2);
+                        (size_t)kCropWarps * std::min(hit_cap, kCropWarpPts * kMaxHitsPerPoint) * sizeof(int2) +
+                        (size_t)kCropWarps * rank_boxes * sizeof(int32_t);
     AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_crop_hits: hit_cap=%d x max_boxes=%d needs too much shared memory", hit_cap, max_boxes);
     if (smem > 48 * 1024) AL3D_CHECK_CUDA(cudaFuncSetAttribute(crop_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     crop_hits_kernel<<<n_chunks, kCropThreads, smem, (cudaStream_t)stream>>>(
         points, pt_stride, pt_off, planes, aabb, box_off, G, reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes,
         cell_cap, reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<int2 *>(hits), hit_cap, n_hits, chunk_box_count,
-        max_boxes, overflow);
+        max_boxes, rank_boxes, overflow);
     AL3D_CHECK_LAUNCH("crop_hits_kernel");
     return 0;
 }
