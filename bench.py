@@ -225,8 +225,11 @@ def main():
                                          first_chunk_tracks=int(os.environ.get("AL3D_E2E_FIRST", "0")) or None)
     gathered = torch.empty((world * T, 7), device=dev, dtype=torch.float32) if world > 1 else None
 
+    def local_step():
+        return labeler.label_device(pts, init_box)
+
     def step():
-        boxes = labeler.label_device(pts, init_box)
+        boxes = local_step()
         if world > 1:
             dist.all_gather_into_tensor(gathered, boxes)
         return boxes
@@ -244,7 +247,10 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    sampler.wait_first_sample(step)
+    # NOT `step`: every rank leaves this loop after its own number of iterations (when its own nvidia-smi has produced a
+    # sample), and a collective inside it would be called a different number of times per rank -- a deadlock at N >= 4,
+    # where nvidia-smi start-up times differ most.
+    sampler.wait_first_sample(local_step)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
