@@ -198,8 +198,10 @@ def main():
     torch.cuda.set_device(dev)
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # a short collective timeout: a protocol bug should end the run with an error, not sit until the driver's limit
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     synth = importlib.import_module("3dal_pytorch_b200.synth")
     sm = importlib.import_module("3dal_pytorch_b200.static_model")
