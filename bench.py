@@ -273,6 +273,7 @@ def main():
         torch.cuda.cudart().cudaProfilerStop()
     launches = lib.LAUNCHES - launches0
     ms = e0.elapsed_time(e1)
+    eb.check_abort("bench timed region")      # a tensor-core kernel that gave up on a wait would make the number meaningless
     kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in eb.KERNEL_EVENTS.items()}
     eb.KERNEL_EVENTS = None
     if world > 1:
@@ -300,6 +301,7 @@ def main():
         f1.record()
         torch.cuda.synchronize()
         ems = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t0))
+        eb.check_abort("bench e2e region")
         if world > 1:
             t = torch.tensor([ems], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
