@@ -8,7 +8,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libal3d.so")
+# AL3D_LIB selects another build of the same library inside the package directory (the protocol stress tests load
+# libal3d_stress.so, the build with delay-injection hooks, in a subprocess)
+LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ.get("AL3D_LIB", "libal3d.so")))
 
 _vp, _i, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
 
@@ -36,12 +38,16 @@ _SIGNATURES = {
     "al3d_chain_maxpool_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
     "al3d_seg_pass1_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
     "al3d_seg_pass2_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp],
+    "al3d_chain_maxpool_bf16x3": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
+    "al3d_seg_pass2_bf16x3": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp],
     "al3d_umma_selftest": [_vp, _vp, _i, _i, _vp, _i, _vp],
     "al3d_umma_selftest_ts": [_vp, _vp, _i, _i, _vp, _vp],
     "al3d_umma_selftest_pair": [_vp, _vp, _i, _i, _vp, _vp],
     "al3d_umma_selftest_pair_ss": [_vp, _vp, _i, _vp, _vp],
     "al3d_mma_microbench": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "al3d_tc_abort_code": [_vp],
+    "al3d_tc_status_word_host": [_vp],
+    "al3d_tc_configure": [_i, _i],
     "al3d_set_debug_buffer": [_vp],
 }
 _RESTYPES = {"al3d_last_error": ctypes.c_char_p}
@@ -66,7 +72,7 @@ def lib():
             fn = getattr(l, name)
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, ctypes.c_int)
-        if l.al3d_abi_version() != 2:
+        if l.al3d_abi_version() != 3:
             raise RuntimeError("libal3d.so ABI version mismatch")
         _lib = l
     return _lib
@@ -74,7 +80,7 @@ def lib():
 
 # kernels launched through this binding since import (bench.py reports it as gpu_launches)
 LAUNCHES = 0
-_NO_LAUNCH = ("tc_abort_code", "set_debug_buffer", "crop_chunk_points")
+_NO_LAUNCH = ("tc_abort_code", "tc_status_word_host", "tc_configure", "set_debug_buffer", "crop_chunk_points")
 
 
 def check(rc, what=""):

@@ -22,6 +22,17 @@
 namespace al3d {
 using namespace umma;
 
+// Delay-injection hooks of the protocol stress tests.  They are compiled into a second library
+// (libal3d_stress.so, -DAL3D_TC_STRESS_HOOKS) only: the hooks sit inside unrolled loops of kernels whose instruction
+// footprint is already large, and the product library must not pay for them.
+#ifdef AL3D_TC_STRESS_HOOKS
+#define AL3D_STRESS(st, salt) stress_delay(st, salt)
+#define AL3D_STRESS_WARP(st, salt) stress_delay_warp(st, salt)
+#else
+#define AL3D_STRESS(st, salt) do { } while (0)
+#define AL3D_STRESS_WARP(st, salt) do { } while (0)
+#endif
+
 constexpr int kTile = 128;                 // points per tile == TMEM lanes
 constexpr int kStageBytes = 16384;         // one weight block: 128 rows x 64 K bf16
 constexpr int kPlane = kTile * 16;         // bytes of one activation K-plane (128 rows x 16 B)
@@ -151,7 +162,7 @@ __device__ __forceinline__ void first_layer(uint8_t *buf, int row, const float *
 // UMMA self-test: D(128 x N) = A(128 x K) * B(N x K)^T from KP-packed bf16 operands.
 // ================================================================================================
 __global__ void __launch_bounds__(128)
-umma_selftest_kernel(const uint8_t *__restrict__ a_kp, const uint8_t *__restrict__ b_kp, int N, int K, float *__restrict__ d, int swap)
+umma_selftest_kernel(const uint8_t *__restrict__ a_kp, const uint8_t *__restrict__ b_kp, int N, int K, float *__restrict__ d, int swap, const TcStatus wd)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -177,7 +188,7 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_kp, const uint8_t *__restrict
         }
         mma_commit(&bar);
     }
-    mbar_wait(&bar, 0, 0xE001);
+    mbar_wait(&bar, 0, 0xE001, wd);
     tc_fence_after();
     const int row = threadIdx.x;       // warps 0..3 <-> lane quarters 0..3
     for (int c0 = 0; c0 < N; c0 += 32) {
@@ -195,7 +206,7 @@ umma_selftest_kernel(const uint8_t *__restrict__ a_kp, const uint8_t *__restrict
 // Same product with the A operand staged in TMEM: every thread packs its row of A (fp32 in global memory)
 // to bf16 pairs and tcgen05.st's them to columns [256, 256 + K/2); checks the A-from-TMEM conventions.
 __global__ void __launch_bounds__(128)
-umma_selftest_ts_kernel(const float *__restrict__ a, const uint8_t *__restrict__ b_kp, int N, int K, float *__restrict__ d)
+umma_selftest_ts_kernel(const float *__restrict__ a, const uint8_t *__restrict__ b_kp, int N, int K, float *__restrict__ d, const TcStatus wd)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -230,7 +241,7 @@ umma_selftest_ts_kernel(const float *__restrict__ a, const uint8_t *__restrict__
         }
         mma_commit(&bar);
     }
-    mbar_wait(&bar, 0, 0xE002);
+    mbar_wait(&bar, 0, 0xE002, wd);
     tc_fence_after();
     for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
@@ -248,7 +259,7 @@ umma_selftest_ts_kernel(const float *__restrict__ a, const uint8_t *__restrict__
 // [128r, 128r+128) of A in its TMEM and rows [r*N/2, (r+1)*N/2) of B (KP-packed, N/2 rows) in its shared memory;
 // the leader issues the M = 256 MMAs; each CTA reads back its 128 rows of D.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
-umma_selftest_pair_kernel(const float *__restrict__ a, const uint8_t *__restrict__ b_kp_halves, int N, int K, float *__restrict__ d)
+umma_selftest_pair_kernel(const float *__restrict__ a, const uint8_t *__restrict__ b_kp_halves, int N, int K, float *__restrict__ d, const TcStatus wd)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -286,7 +297,7 @@ umma_selftest_pair_kernel(const float *__restrict__ a, const uint8_t *__restrict
         }
         mma_commit_pair(&bar, 0x3);
     }
-    mbar_wait(&bar, 0, 0xE003);
+    mbar_wait(&bar, 0, 0xE003, wd);
     tc_fence_after();
     for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
@@ -305,7 +316,7 @@ umma_selftest_pair_kernel(const float *__restrict__ a, const uint8_t *__restrict
 // [128r, 128r+128) of A as a 128-row KP tile, and its N/2 = 64 rows of B as rows [64,128) of a 128-row KP tile (a
 // sub-tile descriptor: plane stride 2048 B), exactly how the kernel addresses half of a tile's conv4 output.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
-umma_selftest_pair_ss_kernel(const uint8_t *__restrict__ a_kp_halves, const uint8_t *__restrict__ b_kp_halves, int K, float *__restrict__ d)
+umma_selftest_pair_ss_kernel(const uint8_t *__restrict__ a_kp_halves, const uint8_t *__restrict__ b_kp_halves, int K, float *__restrict__ d, const TcStatus wd)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -339,7 +350,7 @@ umma_selftest_pair_ss_kernel(const uint8_t *__restrict__ a_kp_halves, const uint
         }
         mma_commit_pair(&bar, 0x3);
     }
-    mbar_wait(&bar, 0, 0xE004);
+    mbar_wait(&bar, 0, 0xE004, wd);
     tc_fence_after();
     const int row = threadIdx.x;
     const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
@@ -368,6 +379,7 @@ struct ChainParams {
     int splits;                                          // work items per object
     int n_items;
     int bufA_bytes, bufB_bytes, n_stages;                // shared-memory carve-up chosen by the launcher
+    TcStatus wd;                                         // watchdog status word of this launch
 };
 
 constexpr int kChainMaxStages = 12;
@@ -391,6 +403,7 @@ __device__ __forceinline__ int chain_in_width(const ChainParams &p, int l) { ret
 __global__ void __launch_bounds__(kThreads, 1)
 chain_max_kernel(const ChainParams p)
 {
+    const TcStatus &wd = p.wd;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t *const s_bufA = smem_raw;
     uint8_t *const s_bufB = smem_raw + p.bufA_bytes;
@@ -437,7 +450,8 @@ chain_max_kernel(const ChainParams p)
                         const int rows = N < 128 ? N : 128;
                         const int nblk = (N / rows) * (K / 64);
                         for (int i = 0; i < nblk; ++i, ++blk) {
-                            if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0xC100 + stage)) goto done;
+                            AL3D_STRESS(wd, 0xC1);
+                            if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0xC100 + stage, wd)) goto done;
                             const uint32_t bytes = rows * 64 * 2;
                             mbar_arrive_expect_tx(&s.w_full[stage], bytes);
                             bulk_g2s((s_wring + (size_t)stage * kStageBytes), p.wstream + (size_t)blk * kStageBytes, bytes, &s.w_full[stage]);
@@ -461,13 +475,13 @@ chain_max_kernel(const ChainParams p)
                         const int K = chain_in_width(p, l), N = p.mid[l];
                         const int rows = N < 128 ? N : 128;
                         const uint32_t in_addr = (l & 1) ? aB : aA;
-                        if (!mbar_wait(&s.act_ready, act_phase, 0xC200 + l)) goto done;
+                        if (!mbar_wait(&s.act_ready, act_phase, 0xC200 + l, wd)) goto done;
                         act_phase ^= 1;
                         tc_fence_after();
                         const uint32_t idesc = make_idesc_bf16(128, rows);
                         for (int nc = 0; nc < N / rows; ++nc)
                             for (int kb = 0; kb < K / 64; ++kb) {
-                                if (!mbar_wait(&s.w_full[stage], wphase, 0xC300 + stage)) goto done;
+                                if (!mbar_wait(&s.w_full[stage], wphase, 0xC300 + stage, wd)) goto done;
                                 tc_fence_after();
                                 mma_block_k64(tmem + nc * 128, in_addr + kb * 8 * kPlane, 128, smem_u32((s_wring + (size_t)stage * kStageBytes)), rows, idesc, kb > 0);
                                 mma_commit(&s.w_empty[stage]);
@@ -478,17 +492,18 @@ chain_max_kernel(const ChainParams p)
                     // last layer, transposed: D^T[channels x points], double-buffered in TMEM cols 256..511
                     {
                         const uint32_t in_addr = (p.n_mid & 1) ? aB : aA;
-                        if (!mbar_wait(&s.act_ready, act_phase, 0xC2F0)) goto done;
+                        if (!mbar_wait(&s.act_ready, act_phase, 0xC2F0, wd)) goto done;
                         act_phase ^= 1;
                         tc_fence_after();
                         const uint32_t idesc = make_idesc_bf16(128, 128);
                         for (int cc = 0; cc < n_last_chunks; ++cc) {
                             const int b = cc & 1;
-                            if (!mbar_wait(&s.last_empty[b], le_phase[b] ^ 1, 0xC400 + b)) goto done;
+                            AL3D_STRESS(wd, 0xC4);
+                            if (!mbar_wait(&s.last_empty[b], le_phase[b] ^ 1, 0xC400 + b, wd)) goto done;
                             le_phase[b] ^= 1;
                             tc_fence_after();
                             for (int kb = 0; kb < k_last / 64; ++kb) {
-                                if (!mbar_wait(&s.w_full[stage], wphase, 0xC500 + stage)) goto done;
+                                if (!mbar_wait(&s.w_full[stage], wphase, 0xC500 + stage, wd)) goto done;
                                 tc_fence_after();
                                 mma_block_k64(tmem + 256 + b * 128, smem_u32((s_wring + (size_t)stage * kStageBytes)), 128, in_addr + kb * 8 * kPlane, 128, idesc, kb > 0);
                                 mma_commit(&s.w_empty[stage]);
@@ -530,7 +545,8 @@ chain_max_kernel(const ChainParams p)
                 for (int l = 0; l < p.n_mid; ++l) {
                     const int N = p.mid[l];
                     uint8_t *outb = (l & 1) ? s_bufA : s_bufB;
-                    if (!mbar_wait(&s.acc_ready, acc_phase, 0xD100 + l)) goto done;
+                    AL3D_STRESS_WARP(wd, 0xD1);
+                    if (!mbar_wait(&s.acc_ready, acc_phase, 0xD100 + l, wd)) goto done;
                     acc_phase ^= 1;
                     tc_fence_after();
                     epilogue_cols_n(N >> 1, tmem + lane_addr, outb, half * (N >> 1), row, s.mid_b + boff);
@@ -544,7 +560,8 @@ chain_max_kernel(const ChainParams p)
                 for (int cc = 0; cc < 8; ++cc) {
                     if (cc < n_last_chunks) {
                         const int bsel = cc & 1;
-                        if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0xD200 + cc)) goto done;
+                        AL3D_STRESS_WARP(wd, 0xD2);
+                        if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0xD200 + cc, wd)) goto done;
                         lf_phase[bsel] ^= 1;
                         tc_fence_after();
                         uint32_t v0[32], v1[32];
@@ -617,6 +634,7 @@ struct Pass2Params {
     int tiles_per_obj; int n_items;    // items = bs * tiles_per_obj
     long long *dbg;                    // optional clock64 timeline of CTA 0 (al3d_set_debug_buffer), else NULL
     int dbg_skip;                      // first recorded tile of the timeline (environment AL3D_DEBUG_SKIP)
+    TcStatus wd;                       // watchdog status word of this launch
 };
 
 // timeline stamps: role 0 = MMA thread, 1 = epilogue thread 0 (CTA 0), 2 = epilogue thread 0 of CTA 1 (pass 2: the
@@ -754,6 +772,7 @@ __device__ __forceinline__ void mma_pair_k64(uint32_t tmem_d, uint32_t a0, uint3
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + 32, 1)
 seg_pass2_kernel(const Pass2Params p)
 {
+    const TcStatus &wd = p.wd;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Pass2Smem &s = *reinterpret_cast<Pass2Smem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -795,7 +814,7 @@ seg_pass2_kernel(const Pass2Params p)
             }
             if (crank != 0) {
                 // tell the leader that the peer's weights are in place
-                if (!mbar_wait(&s.res_full, 0, 0xA1F0)) goto done;
+                if (!mbar_wait(&s.res_full, 0, 0xA1F0, wd)) goto done;
                 mbar_arrive_remote_release(&s.res_peer, 0);
             }
         }
@@ -811,7 +830,8 @@ seg_pass2_kernel(const Pass2Params p)
             const uint32_t wres = smem_u32(s.wres);
 #define P2_W(blk) (wres + p2_half_off(blk))
 #define P2_WAIT(bar, ph, code)                                                           \
-            if (!mbar_wait_cluster(&(bar), ph, code)) goto done;                         \
+            AL3D_STRESS(wd, 0xA2);                                                      \
+            if (!mbar_wait_cluster(&(bar), ph, code, wd)) goto done;                         \
             AL3D_TS(0);                                                                  \
             ph ^= 1; tc_fence_after();
 #define P2_ISSUE_CONV2()                                                                 \
@@ -820,8 +840,8 @@ seg_pass2_kernel(const Pass2Params p)
                 mma_pair_k64(tmem + kColD1 + 128, tmem + kColA1, tmem + kColA1 + 8, tmem + kColA1 + 16, tmem + kColA1 + 24, P2_W(0), 32, id64, false); \
                 mma_commit_pair(&s.acc_f, 0x3);                                          \
             }
-            if (!mbar_wait(&s.res_full, 0, 0xA2FE)) goto done;
-            if (!mbar_wait_cluster(&s.res_peer, 0, 0xA2FF)) goto done;
+            if (!mbar_wait(&s.res_full, 0, 0xA2FE, wd)) goto done;
+            if (!mbar_wait_cluster(&s.res_peer, 0, 0xA2FF, wd)) goto done;
             tc_fence_after();
             int it_local = 0;
             int ts_i = 0;
@@ -834,7 +854,8 @@ seg_pass2_kernel(const Pass2Params p)
                 for (int kc = 0; kc < 8; ++kc) {
                     const int j = kc % 3;
                     const int blk0 = kc < 5 ? 4 + 2 * kc : 14 + (kc - 5);           // dconv2 block of this group
-                    if (!mbar_wait_cluster(&s.d1_act[j], d1a_phase[j], 0xA400 + kc)) goto done;
+                    AL3D_STRESS(wd, 0xA4);
+                    if (!mbar_wait_cluster(&s.d1_act[j], d1a_phase[j], 0xA400 + kc, wd)) goto done;
                     AL3D_TS(0);
                     d1a_phase[j] ^= 1; tc_fence_after();
                     const uint32_t a = tmem + kColD1 + j * 64;        // bf16 image of chunk kc (in place)
@@ -881,16 +902,17 @@ seg_pass2_kernel(const Pass2Params p)
             uint32_t actf2_phase = 0, d1free_phase[3] = {0, 0, 0};
             const uint32_t id64 = make_idesc_bf16(256, 64);
             const uint32_t wres = smem_u32(s.wres);
-            if (!mbar_wait(&s.res_full, 0, 0xA3FE)) goto done;
-            if (!mbar_wait_cluster(&s.res_peer, 0, 0xA3FF)) goto done;
+            if (!mbar_wait(&s.res_full, 0, 0xA3FE, wd)) goto done;
+            if (!mbar_wait_cluster(&s.res_peer, 0, 0xA3FF, wd)) goto done;
             for (int r = 0; r < n_rounds; ++r) {
-                if (!mbar_wait_cluster(&s.act_f2, actf2_phase, 0xA300)) goto done;      // A2 of this round's tiles is in place
+                if (!mbar_wait_cluster(&s.act_f2, actf2_phase, 0xA300, wd)) goto done;      // A2 of this round's tiles is in place
                 actf2_phase ^= 1; tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const int j = c % 3;
                     if ((c >= 3 || (c < 2 && r > 0))) {
-                        if (!mbar_wait(&s.d1_free[j], d1free_phase[j], 0xA310 + c)) goto done;
+                        AL3D_STRESS(wd, 0xA3);
+                        if (!mbar_wait(&s.d1_free[j], d1free_phase[j], 0xA310 + c, wd)) goto done;
                         d1free_phase[j] ^= 1; tc_fence_after();
                     }
                     const int blk = c < 3 ? 1 + c : 5 + 2 * (c - 3);
@@ -939,7 +961,8 @@ seg_pass2_kernel(const Pass2Params p)
         };
         // front, part 2: conv2 accumulator (D1b[2]) -> A2
         auto front_conv2 = [&]() -> bool {
-            if (!mbar_wait(&s.acc_f, accf_phase, 0xB100)) return false;
+            AL3D_STRESS_WARP(wd, 0xB1);
+            if (!mbar_wait(&s.acc_f, accf_phase, 0xB100, wd)) return false;
             accf_phase ^= 1; tc_fence_after();
             uint32_t v[32], o[16];
             tmem_ld32(tl + kColD1 + 128 + half * 32, v);
@@ -983,7 +1006,8 @@ seg_pass2_kernel(const Pass2Params p)
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc) {
                 const int j = kc % 3;
-                if (!mbar_wait(&s.d1_full[j], d1f_phase[j], 0xB200 + kc)) goto done;
+                AL3D_STRESS_WARP(wd, 0xB2);
+                if (!mbar_wait(&s.d1_full[j], d1f_phase[j], 0xB200 + kc, wd)) goto done;
                 AL3D_TSE();
                 d1f_phase[j] ^= 1; tc_fence_after();
                 uint32_t v[32], o[16];
@@ -996,7 +1020,8 @@ seg_pass2_kernel(const Pass2Params p)
                 AL3D_TSE();
             }
             // ---- dconv2 epilogue: D2 -> A3 in place (this thread: 128 columns in two batches)
-            if (!mbar_wait(&s.acc_t, acct_phase, 0xB101)) goto done;
+            AL3D_STRESS_WARP(wd, 0xB101);
+            if (!mbar_wait(&s.acc_t, acct_phase, 0xB101, wd)) goto done;
             AL3D_TSE();
             acct_phase ^= 1; tc_fence_after();
 #pragma unroll
@@ -1019,7 +1044,8 @@ seg_pass2_kernel(const Pass2Params p)
             if (has_next) front_conv1(next_item + (int)gridDim.x);
             AL3D_TSE();
             // ---- dconv3 epilogue: D3 -> A4 in place (64 columns)
-            if (!mbar_wait(&s.acc_t, acct_phase, 0xB102)) goto done;
+            AL3D_STRESS_WARP(wd, 0xB102);
+            if (!mbar_wait(&s.acc_t, acct_phase, 0xB102, wd)) goto done;
             AL3D_TSE();
             acct_phase ^= 1; tc_fence_after();
             {
@@ -1041,7 +1067,8 @@ seg_pass2_kernel(const Pass2Params p)
             // ---- dconv4 epilogue: bias + ReLU in fp32, then the 128 -> 2 layer, logits and mask.
             //      Each half reduces 64 channels; the upper half hands its partial sums over in smem and the
             //      lower half adds them in a fixed order (deterministic).
-            if (!mbar_wait(&s.acc_t, acct_phase, 0xB103)) goto done;
+            AL3D_STRESS_WARP(wd, 0xB103);
+            if (!mbar_wait(&s.acc_t, acct_phase, 0xB103, wd)) goto done;
             AL3D_TSE();
             acct_phase ^= 1; tc_fence_after();
             {
@@ -1128,6 +1155,7 @@ struct Pass1Params {
     int splits, n_items;
     long long *dbg;                    // optional clock64 timeline (al3d_set_debug_buffer), else NULL
     int dbg_skip;                      // first recorded step of the timeline (environment AL3D_DEBUG_SKIP)
+    TcStatus wd;                       // watchdog status word of this launch
     // copies in the parameter block (constant bank): operands of the front warps' arithmetic, no loads
     float w1c[512], b1c[64], b2c[64], b3c[64], b4c[128];
 };
@@ -1141,7 +1169,12 @@ struct Pass1Smem {
     float w1_w[64 * 8], w1_b[64];     // conv2-4 biases are read through the read-only cache (no room here)
     uint64_t w_full[kP1Stages], w_empty[kP1Stages];
     uint64_t res_full;
-    uint64_t out4_ready, out4_free;    // front warps -> conv5 issuers (operand written) and back (operand consumed)
+    // front warps -> conv5 issuers (operand written) and back (operand consumed): ONE BARRIER PAIR PER out4 BUFFER.  A
+    // parity wait must never be lapped (two completions before the waiter looks).  With a single out4_free the issuers
+    // could complete the phases of steps s-2 AND s-1 before a slow front reached its wait for s-2: the parity aliased
+    // and the pipeline deadlocked (round-1 watchdog 0x9100); a single out4_ready has the mirror-image hazard for a slow
+    // issuer.  Per buffer, the next completion of either barrier needs the other side to have passed its wait first.
+    uint64_t out4_ready[2], out4_free[2];
     uint64_t act[2], acc[2];           // front hand-overs per tile: operand in TMEM / accumulator complete
     uint64_t c5_full[2], c5_empty[2];  // conv5 accumulator of tile X / Y: complete / drained
     uint32_t tmem_base;
@@ -1190,6 +1223,7 @@ seg_pass1_kernel(const Pass1Params p)
     do { const int ts_it = it_local - p.dbg_skip;                                                     \
          if (p.dbg && blockIdx.x == 0 && ts_it >= 0 && ts_it < 4 && ts_i < 64)                         \
              p.dbg[((role) * 4 + ts_it) * 64 + ts_i++] = clock64(); } while (0)
+    const TcStatus &wd = p.wd;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Pass1Smem &s = *reinterpret_cast<Pass1Smem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1199,8 +1233,8 @@ seg_pass1_kernel(const Pass1Params p)
     if (threadIdx.x == 0) {
         for (int i = 0; i < kP1Stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 2); }
         mbar_init(&s.res_full, 1);
-        mbar_init(&s.out4_ready, 2 * 4);                                // front warps x tiles
-        mbar_init(&s.out4_free, 2);                                     // the two conv5 issuers
+        mbar_init(&s.out4_ready[0], 2 * 4); mbar_init(&s.out4_ready[1], 2 * 4);   // front warps x tiles, per out4 buffer
+        mbar_init(&s.out4_free[0], 2); mbar_init(&s.out4_free[1], 2);   // the two conv5 issuers, per out4 buffer
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.act[i], 4); mbar_init(&s.acc[i], 1);
             mbar_init(&s.c5_full[i], 1); mbar_init(&s.c5_empty[i], 4);
@@ -1226,7 +1260,8 @@ seg_pass1_kernel(const Pass1Params p)
             int stage = 0; uint32_t phase = 0;
             for (P1Step st = p1_first(p, tiles_per_obj, blockIdx.x, stride); st.valid; st = p1_next(p, tiles_per_obj, stride, st)) {
                 for (int blk = 0; blk < 16; ++blk) {
-                    if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x9100 + stage)) goto done;
+                    AL3D_STRESS(wd, 0x91);
+                    if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x9100 + stage, wd)) goto done;
                     mbar_arrive_expect_tx(&s.w_full[stage], kStageBytes);
                     bulk_g2s(s.wring[stage], p.w5stream + (size_t)blk * kStageBytes, kStageBytes, &s.w_full[stage]);
                     if (++stage == kP1Stages) { stage = 0; phase ^= 1; }
@@ -1237,7 +1272,7 @@ seg_pass1_kernel(const Pass1Params p)
         // ------------------------------------------------------------ conv5 issuers: warp 1 -> tile X, warp 10 -> tile Y
         if (elect_one_sync()) {
             const int q = (warp == 1) ? 0 : 1;
-            uint32_t o4_phase = 0, ce_phase = 0;
+            uint32_t o4_phase[2] = {0, 0}, ce_phase = 0;
             const uint32_t id128 = make_idesc_bf16(128, 128);
             const uint32_t o4[2] = {smem_u32(s.out4[0]), smem_u32(s.out4[1])};
             const uint32_t d = tmem + q * 128;
@@ -1245,18 +1280,20 @@ seg_pass1_kernel(const Pass1Params p)
             for (P1Step st = p1_first(p, tiles_per_obj, blockIdx.x, stride); st.valid; st = p1_next(p, tiles_per_obj, stride, st), ++it_local) {
                 ts_i = 0;
                 if (q == 0) P1_TS(0);
-                if (!mbar_wait(&s.out4_ready, o4_phase, 0x9400 + q)) goto done;
-                o4_phase ^= 1; tc_fence_after();
+                AL3D_STRESS(wd, 0x94 + q);
+                if (!mbar_wait(&s.out4_ready[ob], o4_phase[ob], 0x9400 + q, wd)) goto done;
+                o4_phase[ob] ^= 1; tc_fence_after();
                 if (q == 0) P1_TS(0);
 #pragma unroll 1
                 for (int c = 0; c < 8; ++c) {
-                    if (!mbar_wait(&s.c5_empty[q], ce_phase ^ 1, 0x9500 + q)) goto done;
+                    AL3D_STRESS(wd, 0x95 + q);
+                    if (!mbar_wait(&s.c5_empty[q], ce_phase ^ 1, 0x9500 + q, wd)) goto done;
                     ce_phase ^= 1; tc_fence_after();
                     if (q == 0) P1_TS(0);
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb, ++g) {
                         const int stage = g % kP1Stages;
-                        if (!mbar_wait(&s.w_full[stage], (uint32_t)(g / kP1Stages) & 1u, 0x9600 + stage)) goto done;
+                        if (!mbar_wait(&s.w_full[stage], (uint32_t)(g / kP1Stages) & 1u, 0x9600 + stage, wd)) goto done;
                         tc_fence_after();
                         const uint32_t wa = smem_u32(s.wring[stage]);
 #pragma unroll
@@ -1268,7 +1305,8 @@ seg_pass1_kernel(const Pass1Params p)
                     mma_commit(&s.c5_full[q]);
                     if (q == 0) P1_TS(0);
                 }
-                mma_commit(&s.out4_free);                         // this tile's reads of out4[ob] are done
+                mma_commit(&s.out4_free[(wd.trap & 2) ? 0 : ob]); // this tile's reads of out4[ob] are done (bit 1 of
+                                                                  // wd.trap: test hook, the round-1 single-barrier protocol)
                 ob ^= 1;
             }
         }
@@ -1279,7 +1317,7 @@ seg_pass1_kernel(const Pass1Params p)
             uint32_t act_phase[2] = {0, 0};
             const uint32_t id64 = make_idesc_bf16(128, 64);
             const uint32_t wf = smem_u32(s.wfront);
-            if (!mbar_wait(&s.res_full, 0, 0x9200)) goto done;
+            if (!mbar_wait(&s.res_full, 0, 0x9200, wd)) goto done;
             tc_fence_after();
             for (P1Step st = p1_first(p, tiles_per_obj, blockIdx.x, stride); st.valid; st = p1_next(p, tiles_per_obj, stride, st)) {
 #pragma unroll 1
@@ -1287,7 +1325,8 @@ seg_pass1_kernel(const Pass1Params p)
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const uint32_t R = tmem + kP1FrontCol + q * 128;
-                        if (!mbar_wait(&s.act[q], act_phase[q], 0x9300 + l * 2 + q)) goto done;
+                        AL3D_STRESS(wd, 0x93);
+                        if (!mbar_wait(&s.act[q], act_phase[q], 0x9300 + l * 2 + q, wd)) goto done;
                         act_phase[q] ^= 1; tc_fence_after();
                         if (l == 0)      mma_ts_k64(R, R + 96, R + 104, R + 112, R + 120, wf, 64, id64, false);              // conv2
                         else if (l == 1) mma_ts_k64(R + 32, R, R + 8, R + 16, R + 24, wf + 8192, 64, id64, false);          // conv3
@@ -1325,7 +1364,8 @@ seg_pass1_kernel(const Pass1Params p)
             for (int c = 0; c < 8; ++c) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    if (!mbar_wait(&s.c5_full[q], cf_phase[q], 0x8300 + c * 2 + q)) goto done;
+                    AL3D_STRESS_WARP(wd, 0x83);
+                    if (!mbar_wait(&s.c5_full[q], cf_phase[q], 0x8300 + c * 2 + q, wd)) goto done;
                     cf_phase[q] ^= 1; tc_fence_after();
                     if (ts_on) P1_TS(1);
                     float m0 = rmax[c], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -1370,7 +1410,7 @@ seg_pass1_kernel(const Pass1Params p)
         // ------------------------------------------------------------ front warps (6-9): thread = point row of both tiles
         const int row = epi_row();
         const uint32_t tl = tmem + ((uint32_t)(row & ~31) << 16) + kP1FrontCol;
-        uint32_t acc_phase[2] = {0, 0}, of_phase = 0;
+        uint32_t acc_phase[2] = {0, 0}, of_phase[2] = {0, 0};
         int it_local = 0, ts_i = 0;
         const bool ts_on = (threadIdx.x == 6 * 32);
         float xq[2][8];
@@ -1412,7 +1452,8 @@ seg_pass1_kernel(const Pass1Params p)
             for (int l = 0; l < 2; ++l) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8100 + l * 2 + q)) goto done;
+                    AL3D_STRESS_WARP(wd, 0x81);
+                    if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8100 + l * 2 + q, wd)) goto done;
                     acc_phase[q] ^= 1; tc_fence_after();
                     uint32_t v0[32], v1[32], o0[16], o1[16];
                     const uint32_t R = tl + q * 128;
@@ -1430,15 +1471,18 @@ seg_pass1_kernel(const Pass1Params p)
             }
             // ---- conv4 epilogues (two 64-channel halves): -> shared-memory operand of conv5, rows of tile q.
             //      out4[buf] was last read by conv5 two steps ago: wait until both conv5 issuers have released it.
+            AL3D_STRESS_WARP(wd, 0x84);
             if (step >= 2) {
-                if (!mbar_wait(&s.out4_free, of_phase, 0x8400)) goto done;
-                of_phase ^= 1;
+                const int fb = (wd.trap & 2) ? 0 : buf;
+                if (!mbar_wait(&s.out4_free[fb], of_phase[fb], 0x8400 + fb, wd)) goto done;
+                of_phase[fb] ^= 1;
             }
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8200 + hh * 2 + q)) goto done;
+                    AL3D_STRESS_WARP(wd, 0x82);
+                    if (!mbar_wait(&s.acc[q], acc_phase[q], 0x8200 + hh * 2 + q, wd)) goto done;
                     acc_phase[q] ^= 1; tc_fence_after();
                     uint32_t v0[32], v1[32], o0[16], o1[16];
                     const uint32_t R = tl + q * 128;
@@ -1455,7 +1499,7 @@ seg_pass1_kernel(const Pass1Params p)
                         *reinterpret_cast<uint4 *>(dst + (size_t)j * 4096) = make_uint4(o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
                         *reinterpret_cast<uint4 *>(dst + (size_t)(4 + j) * 4096) = make_uint4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
                     }
-                    if (hh == 1) { fence_proxy_async_smem(); P1_ARRIVE(&s.out4_ready); }
+                    if (hh == 1) { fence_proxy_async_smem(); P1_ARRIVE(&s.out4_ready[buf]); }
                     if (ts_on) P1_TS(2);
                 }
             }
@@ -1487,6 +1531,7 @@ struct TrunkParams {
     const uint8_t *wstream;            // 16 KB slots: conv2 (k-blocks) | conv3 (row-chunk, k-block) | conv4 (chunk, k-block)
     float *out;                        // (bs, 512) zero-initialised
     int splits, n_items;
+    TcStatus wd;                       // watchdog status word of this launch
 };
 
 template <int W0, int M1, int M2>
@@ -1502,6 +1547,7 @@ template <int W0, int M1, int M2>
 __global__ void __launch_bounds__(kThreads, 1)
 trunk_pair_kernel(const TrunkParams p)
 {
+    const TcStatus &wd = p.wd;
     using C = TrunkCfg<W0, M1, M2>;
     constexpr int S = C::kStages;
     static_assert(S >= 3 && S <= 12, "weight ring depth");
@@ -1541,7 +1587,8 @@ trunk_pair_kernel(const TrunkParams p)
         if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
             auto push = [&](int blk, uint32_t bytes) -> bool {
-                if (!mbar_wait(&w_empty[stage], phase ^ 1, 0x7100 + stage)) return false;
+                AL3D_STRESS(wd, 0x71);
+                if (!mbar_wait(&w_empty[stage], phase ^ 1, 0x7100 + stage, wd)) return false;
                 mbar_arrive_expect_tx(&w_full[stage], bytes);
                 bulk_g2s(s_ring + (size_t)stage * kStageBytes, p.wstream + (size_t)blk * kStageBytes, bytes, &w_full[stage]);
                 if (++stage == S) { stage = 0; phase ^= 1; }
@@ -1565,7 +1612,7 @@ trunk_pair_kernel(const TrunkParams p)
             int stage = 0; uint32_t wphase = 0, act_phase = 0, o3_phase = 0, le_phase[2] = {0, 0};
             const uint32_t id2 = make_idesc_bf16(128, M1), id128 = make_idesc_bf16(128, 128), id256 = make_idesc_bf16(128, 256);
             const uint32_t a_out3 = smem_u32(s_out3), ring = smem_u32(s_ring);
-#define TK_NEXT_W(code) if (!mbar_wait(&w_full[stage], wphase, code)) goto done; tc_fence_after(); const uint32_t wb_ = ring + stage * kStageBytes;
+#define TK_NEXT_W(code) if (!mbar_wait(&w_full[stage], wphase, code, wd)) goto done; tc_fence_after(); const uint32_t wb_ = ring + stage * kStageBytes;
 #define TK_REL_W() mma_commit(&w_empty[stage]); if (++stage == S) { stage = 0; wphase ^= 1; }
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int sp_i = item % p.splits;
@@ -1573,7 +1620,8 @@ trunk_pair_kernel(const TrunkParams p)
                 for (int t = t0; t < t1; t += 2) {
                     for (int q = 0; q < 2; ++q) {
                         // conv2: A1 (TMEM) x W2 -> D2
-                        if (!mbar_wait(act, act_phase, 0x7200)) goto done;
+                        AL3D_STRESS(wd, 0x72);
+                        if (!mbar_wait(act, act_phase, 0x7200, wd)) goto done;
                         act_phase ^= 1; tc_fence_after();
 #pragma unroll
                         for (int kb = 0; kb < C::kNkb2; ++kb) {
@@ -1586,7 +1634,7 @@ trunk_pair_kernel(const TrunkParams p)
                         }
                         mma_commit(acc);
                         // conv3: A2 (bf16 image of D2, in place: channels < M1/2 at +0, the rest at +M1/2) x W3 -> D3
-                        if (!mbar_wait(act, act_phase, 0x7201)) goto done;
+                        if (!mbar_wait(act, act_phase, 0x7201, wd)) goto done;
                         act_phase ^= 1; tc_fence_after();
 #pragma unroll
                         for (int nc = 0; nc < C::kNc3; ++nc)
@@ -1605,12 +1653,13 @@ trunk_pair_kernel(const TrunkParams p)
                         mma_commit(acc);
                     }
                     // conv4, transposed, N = 256 points (both tiles)
-                    if (!mbar_wait(out3_ready, o3_phase, 0x7400)) goto done;
+                    if (!mbar_wait(out3_ready, o3_phase, 0x7400, wd)) goto done;
                     o3_phase ^= 1; tc_fence_after();
 #pragma unroll 1
                     for (int cc = 0; cc < 4; ++cc) {
                         const int b = cc & 1;
-                        if (!mbar_wait(&last_empty[b], le_phase[b] ^ 1, 0x7500 + b)) goto done;
+                        AL3D_STRESS(wd, 0x75);
+                        if (!mbar_wait(&last_empty[b], le_phase[b] ^ 1, 0x7500 + b, wd)) goto done;
                         le_phase[b] ^= 1; tc_fence_after();
                         for (int kb = 0; kb < C::kNkb4; ++kb) {
                             TK_NEXT_W(0x7600)
@@ -1659,7 +1708,8 @@ trunk_pair_kernel(const TrunkParams p)
                         TK_ARRIVE(act);
                     }
                     // ---- conv2 epilogue: D2 -> its bf16 image, in place (this thread: M1/2 columns)
-                    if (!mbar_wait(acc, acc_phase, 0x6100)) goto done;
+                    AL3D_STRESS_WARP(wd, 0x61);
+                    if (!mbar_wait(acc, acc_phase, 0x6100, wd)) goto done;
                     acc_phase ^= 1; tc_fence_after();
 #pragma unroll
                     for (int g = 0; g < M1 / 64; ++g) {
@@ -1673,7 +1723,8 @@ trunk_pair_kernel(const TrunkParams p)
                     tmem_st_wait(); tc_fence_before();
                     TK_ARRIVE(act);
                     // ---- conv3 epilogue: D3 -> shared-memory operand of conv4 (this thread: M2/2 channels of its row)
-                    if (!mbar_wait(acc, acc_phase, 0x6101)) goto done;
+                    AL3D_STRESS_WARP(wd, 0x62);
+                    if (!mbar_wait(acc, acc_phase, 0x6101, wd)) goto done;
                     acc_phase ^= 1; tc_fence_after();
 #pragma unroll
                     for (int g = 0; g < M2 / 64; ++g) {
@@ -1695,7 +1746,8 @@ trunk_pair_kernel(const TrunkParams p)
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     const int bsel = cc & 1;
-                    if (!mbar_wait(&last_full[bsel], lf_phase[bsel], 0x6300 + cc)) goto done;
+                    AL3D_STRESS_WARP(wd, 0x63);
+                    if (!mbar_wait(&last_full[bsel], lf_phase[bsel], 0x6300 + cc, wd)) goto done;
                     lf_phase[bsel] ^= 1; tc_fence_after();
                     float m0 = rmax[cc], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
@@ -1720,6 +1772,11 @@ trunk_pair_kernel(const TrunkParams p)
                     }
                     rmax[cc] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 }
+                // The two warps of a lane quarter split the accumulator COLUMNS, and the next pair's conv1 writes A1 into
+                // columns [0, W0/2) of the same lanes: a warp that ran ahead into the next pair would overwrite conv4
+                // columns its sibling has not read yet (found by the delay-injection stress test).  All epilogue warps
+                // leave the pair together.
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             if (t1 > t0) {
 #pragma unroll
@@ -1768,15 +1825,6 @@ static int debug_skip()
     return e ? std::atoi(e) : 0;
 }
 
-extern "C" int al3d_tc_abort_code(int *code_host)
-{
-    unsigned int v = 0, zero = 0;
-    AL3D_CHECK_CUDA(cudaMemcpyFromSymbol(&v, umma::g_abort, sizeof(v)));
-    if (v != 0) AL3D_CHECK_CUDA(cudaMemcpyToSymbol(umma::g_abort, &zero, sizeof(zero)));
-    if (code_host) *code_host = (int)v;
-    return 0;
-}
-
 extern "C" int al3d_umma_selftest(const void *a_kp, const void *b_kp, int N, int K, float *d_out, int swap_lbo_sbo, void *stream)
 {
     AL3D_CHECK_ARG(a_kp && b_kp && d_out, "al3d_umma_selftest: null pointer");
@@ -1784,7 +1832,9 @@ extern "C" int al3d_umma_selftest(const void *a_kp, const void *b_kp, int N, int
     const size_t smem = (size_t)(128 + N) * K * 2;
     AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_umma_selftest: tile too large");
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const uint8_t *)a_kp, (const uint8_t *)b_kp, N, K, d_out, swap_lbo_sbo);
+    TcStatus wd;
+    if (tc_launch_status(&wd)) return 1;
+    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const uint8_t *)a_kp, (const uint8_t *)b_kp, N, K, d_out, swap_lbo_sbo, wd);
     AL3D_CHECK_LAUNCH("umma_selftest_kernel");
     return 0;
 }
@@ -1796,7 +1846,9 @@ extern "C" int al3d_umma_selftest_ts(const float *a, const void *b_kp, int N, in
     const size_t smem = (size_t)N * K * 2;
     AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_umma_selftest_ts: tile too large");
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_ts_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, (const uint8_t *)b_kp, N, K, d_out);
+    TcStatus wd;
+    if (tc_launch_status(&wd)) return 1;
+    umma_selftest_ts_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, (const uint8_t *)b_kp, N, K, d_out, wd);
     AL3D_CHECK_LAUNCH("umma_selftest_ts_kernel");
     return 0;
 }
@@ -1807,7 +1859,9 @@ extern "C" int al3d_umma_selftest_pair(const float *a, const void *b_kp_halves, 
     AL3D_CHECK_ARG(N >= 32 && N <= 256 && N % 32 == 0 && K >= 32 && K % 32 == 0 && K <= 512, "al3d_umma_selftest_pair: bad N=%d K=%d", N, K);
     const size_t smem = (size_t)(N / 2) * K * 2;
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_pair_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(a, (const uint8_t *)b_kp_halves, N, K, d_out);
+    TcStatus wd;
+    if (tc_launch_status(&wd)) return 1;
+    umma_selftest_pair_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(a, (const uint8_t *)b_kp_halves, N, K, d_out, wd);
     AL3D_CHECK_LAUNCH("umma_selftest_pair_kernel");
     return 0;
 }
@@ -1818,22 +1872,14 @@ extern "C" int al3d_umma_selftest_pair_ss(const void *a_kp_halves, const void *b
     AL3D_CHECK_ARG(K >= 16 && K % 16 == 0 && K <= 256, "al3d_umma_selftest_pair_ss: bad K=%d", K);
     const size_t smem = (size_t)2 * 128 * K * 2;
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(umma_selftest_pair_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_pair_ss_kernel<<<2, 128, smem, (cudaStream_t)stream>>>((const uint8_t *)a_kp_halves, (const uint8_t *)b_kp_halves, K, d_out);
+    TcStatus wd;
+    if (tc_launch_status(&wd)) return 1;
+    umma_selftest_pair_ss_kernel<<<2, 128, smem, (cudaStream_t)stream>>>((const uint8_t *)a_kp_halves, (const uint8_t *)b_kp_halves, K, d_out, wd);
     AL3D_CHECK_LAUNCH("umma_selftest_pair_ss_kernel");
     return 0;
 }
 
-static int num_sms()
-{
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+static int num_sms() { return tc_num_sms(); }      // of the CURRENT device (cached per device ordinal)
 
 extern "C" int al3d_chain_maxpool_bf16(const al3d_chain_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
                                        int bs, int n, float *out, void *stream)
@@ -1861,6 +1907,7 @@ extern "C" int al3d_chain_maxpool_bf16(const al3d_chain_weights *w, const float 
         tp.x = x; tp.sb = sb; tp.sc = sc; tp.sp = sp; tp.bs = bs; tp.n = n; tp.c_in = w->c_in;
         tp.w0_w = w->w0_w; tp.w0_b = w->w0_b; tp.mid_b = w->mid_b; tp.last_b = w->last_b;
         tp.wstream = (const uint8_t *)w->wstream; tp.out = out; tp.splits = 1; tp.n_items = 0;
+        if (tc_launch_status(&tp.wd)) return 1;
         const int sms_ = num_sms();
         if (w->w0 == 128 && w->mid[0] == 128 && w->mid[1] == 256) return launch_trunk_pair<128, 128, 256>(tp, bs, n, (cudaStream_t)stream, sms_);
         if (w->w0 == 64 && w->mid[0] == 128 && w->mid[1] == 256) return launch_trunk_pair<64, 128, 256>(tp, bs, n, (cudaStream_t)stream, sms_);
@@ -1873,6 +1920,7 @@ extern "C" int al3d_chain_maxpool_bf16(const al3d_chain_weights *w, const float 
     p.last = w->last;
     p.w0_w = w->w0_w; p.w0_b = w->w0_b; p.mid_b = w->mid_b; p.last_b = w->last_b;
     p.wstream = (const uint8_t *)w->wstream; p.out = out;
+    if (tc_launch_status(&p.wd)) return 1;
     const int tiles = (n + kTile - 1) / kTile;
     const int sms = num_sms();
     int splits = 1;
@@ -1910,12 +1958,13 @@ extern "C" int al3d_seg_pass1_bf16(const al3d_pass1_weights *w, const float *x, 
     p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n; p.c_in = w->c_in;
     p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.b3 = w->b3; p.b4 = w->b4; p.b5 = w->b5;
     p.wfront = (const uint8_t *)w->wfront; p.w5stream = (const uint8_t *)w->w5stream; p.out = out;
-    AL3D_CHECK_ARG(w->host_consts, "al3d_seg_pass1_bf16: host_consts is null");
+    AL3D_CHECK_ARG(w->consts_host, "al3d_seg_pass1_bf16: consts_host is null");
     {
-        const float *h = w->host_consts;
+        const float *h = w->consts_host;
         std::memcpy(p.w1c, h, sizeof(p.w1c)); std::memcpy(p.b1c, h + 512, sizeof(p.b1c)); std::memcpy(p.b2c, h + 576, sizeof(p.b2c));
         std::memcpy(p.b3c, h + 640, sizeof(p.b3c)); std::memcpy(p.b4c, h + 704, sizeof(p.b4c));
     }
+    if (tc_launch_status(&p.wd)) return 1;
     p.dbg = g_debug_buffer ? g_debug_buffer + 3 * 4 * 64 : nullptr;      // second half of the debug buffer
     p.dbg_skip = debug_skip();
     const int tiles = (n + kTile - 1) / kTile;
@@ -1945,6 +1994,7 @@ extern "C" int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, 
     p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.gbias = gbias;
     p.bd2 = w->bd2; p.bd3 = w->bd3; p.bd4 = w->bd4; p.w5 = w->w5; p.b5 = w->b5;
     p.wstream = (const uint8_t *)w->wstream; p.logits = logits; p.mask = mask; p.dbg = g_debug_buffer; p.dbg_skip = debug_skip();
+    if (tc_launch_status(&p.wd)) return 1;
     p.tiles_per_obj = (n + kTile - 1) / kTile;
     const int64_t items = (int64_t)bs * p.tiles_per_obj;
     AL3D_CHECK_ARG(items < (1ll << 31), "al3d_seg_pass2_bf16: too many tiles");

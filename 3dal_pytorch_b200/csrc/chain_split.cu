@@ -1,0 +1,724 @@
+// Split-precision ("bf16x3") tensor-core kernels: the parity-grade mode of the shared point-wise MLPs.
+//
+// A bf16 operand keeps 8 significant bits; ten chained layers of bf16 x bf16 products leave the segmentation logits
+// ~2e-2 (relative to the largest logit) away from the fp32 reference and flip ~1 % of the mask bits (measured,
+// profiles/r2_parity_per_tensor.jsonl).  fp16 / tf32 operands (11 bits) still miss the 1e-3 bar (~3e-3).  Here every
+// fp32 value x is carried as TWO bf16 numbers, hi = bf16(x) and lo = bf16(x - hi) (16 significant bits together), for
+// activations and weights alike, and every product is evaluated as
+//        a * w  ~=  a_hi * w_hi + a_lo * w_hi + a_hi * w_lo          (a_lo * w_lo ~ 2^-16 relative, dropped)
+// i.e. three tcgen05.mma (kind::f16, fp32 accumulation in TMEM) per K = 16 step instead of one.  The result matches the
+// fp32 reference to ~5e-5 of max|ref| on the logits; a mask bit can only differ where |l1 - l0| is within that error.
+//
+//   split_chain_kernel   first layer (tiny K, CUDA cores) -> 2-3 chained MMA layers, activations (hi | lo planes) in
+//                        shared memory, converted IN PLACE by the epilogue warps -> last layer computed transposed
+//                        (channels on TMEM lanes, points on columns) so the max over points is a per-thread reduction.
+//                        ins_seg conv1-5 + max (tools/static_model.py:279-284) runs it on tile PAIRS (N = 256 points
+//                        per streamed conv5 block); the static box-head trunk (:330-334), PointEmbedding and
+//                        BoxEmbedding trunks (tools/dynamic_model.py:241-245, 278-282) on single tiles.
+//   split_tail_kernel    conv1-2 recomputed, dconv1 (+ per-object global-feature bias) in four 128-channel chunks
+//                        pipelined into dconv2's accumulation, dconv3, dconv4, and the 128 -> 2 logits + mask in fp32
+//                        in the last epilogue (tools/static_model.py:286-295, :59).
+//
+// Both are persistent (one CTA per SM, 320 threads): warp 0 streams the packed weight blocks (hi block, lo block per
+// 128 x 64 tile of W) with cp.async.bulk into a ring, one thread of warp 1 issues every MMA, warps 2-9 own the 128
+// TMEM lanes (two warps per lane quarter, splitting the columns) and run the epilogues.  Every mbarrier that guards
+// a buffer is private to that buffer and strictly ping-pongs with its counterpart, so no parity wait can be lapped.
+#include <algorithm>
+#include "common.cuh"
+#include "umma.cuh"
+#include "../../include/al3d.h"
+
+namespace al3d {
+namespace split {
+using namespace umma;
+
+constexpr int kTile = 128;                 // points per tile == TMEM lanes
+constexpr int kStage = 16384;              // one weight block: <= 128 rows x 64 K bf16
+constexpr int kPlane = kTile * 16;         // one K-plane of a 128-row operand
+constexpr int kEpiThreads = 256;
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kMaxStages = 8;
+
+#ifdef AL3D_TC_STRESS_HOOKS
+#define SPLIT_STRESS(st, salt) stress_delay(st, salt)
+#define SPLIT_STRESS_WARP(st, salt) stress_delay_warp(st, salt)
+#else
+#define SPLIT_STRESS(st, salt) do { } while (0)
+#define SPLIT_STRESS_WARP(st, salt) do { } while (0)
+#endif
+
+__device__ __forceinline__ int epi_row() { return ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31); }
+__device__ __forceinline__ int epi_half() { return ((threadIdx.x >> 5) - 2) >> 2; }
+
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// (a, b) fp32 -> hi = {bf16(a), bf16(b)}, lo = {bf16(a - hi_a), bf16(b - hi_b)}; a sits in the low half (even k).
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+}
+
+// 32 accumulator columns (channels c .. c+31 of this thread's row) -> + bias, ReLU, hi / lo split -> four 16-byte
+// plane rows in each half of the operand buffer.  dst: address of (plane c/8, row) in the hi half.
+__device__ __forceinline__ void store_split32(uint8_t *dst, uint32_t lo_off, uint32_t plane_stride, const uint32_t (&v)[32],
+                                              const float *bias)
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 b0 = *reinterpret_cast<const float4 *>(bias + j * 8);
+        const float4 b1 = *reinterpret_cast<const float4 *>(bias + j * 8 + 4);
+        uint4 h, l;
+        split2(fmaxf(__uint_as_float(v[j * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[j * 8 + 1]) + b0.y, 0.f), h.x, l.x);
+        split2(fmaxf(__uint_as_float(v[j * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[j * 8 + 3]) + b0.w, 0.f), h.y, l.y);
+        split2(fmaxf(__uint_as_float(v[j * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[j * 8 + 5]) + b1.y, 0.f), h.z, l.z);
+        split2(fmaxf(__uint_as_float(v[j * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[j * 8 + 7]) + b1.w, 0.f), h.w, l.w);
+        *reinterpret_cast<uint4 *>(dst + (size_t)j * plane_stride) = h;
+        *reinterpret_cast<uint4 *>(dst + lo_off + (size_t)j * plane_stride) = l;
+    }
+}
+
+// Accumulator columns [c0, c0 + ncols) of this thread's TMEM lane -> split operand planes (ncols multiple of 32).
+__device__ __forceinline__ void epilogue_split(uint32_t taddr, int c0, int ncols, uint8_t *buf, uint32_t lo_off, uint32_t plane_stride,
+                                               int buf_row, const float *bias)
+{
+    for (int c = c0; c < c0 + ncols; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        store_split32(buf + (size_t)(c >> 3) * plane_stride + (size_t)buf_row * 16, lo_off, plane_stride, v, bias + c);
+    }
+}
+
+// First layer on CUDA cores: x[c] (c < c_in) -> output channels [ch0, ch0 + nch) -> split planes.  sw[c * w0 + ch].
+__device__ __forceinline__ void first_layer_split(uint8_t *buf, uint32_t lo_off, int row, const float *xv, int c_in, int w0, int ch0, int nch,
+                                                  const float *sw, const float *sb)
+{
+    for (int ch = ch0; ch < ch0 + nch; ch += 8) {
+        float4 a0 = *reinterpret_cast<const float4 *>(sb + ch), a1 = *reinterpret_cast<const float4 *>(sb + ch + 4);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= c_in) break;
+            const float4 w0v = *reinterpret_cast<const float4 *>(sw + c * w0 + ch);
+            const float4 w1v = *reinterpret_cast<const float4 *>(sw + c * w0 + ch + 4);
+            const float x = xv[c];
+            a0.x = fmaf(x, w0v.x, a0.x); a0.y = fmaf(x, w0v.y, a0.y); a0.z = fmaf(x, w0v.z, a0.z); a0.w = fmaf(x, w0v.w, a0.w);
+            a1.x = fmaf(x, w1v.x, a1.x); a1.y = fmaf(x, w1v.y, a1.y); a1.z = fmaf(x, w1v.z, a1.z); a1.w = fmaf(x, w1v.w, a1.w);
+        }
+        uint4 h, l;
+        split2(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f), h.x, l.x); split2(fmaxf(a0.z, 0.f), fmaxf(a0.w, 0.f), h.y, l.y);
+        split2(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f), h.z, l.z); split2(fmaxf(a1.z, 0.f), fmaxf(a1.w, 0.f), h.w, l.w);
+        uint8_t *dst = buf + (size_t)(ch >> 3) * kPlane + (size_t)row * 16;
+        *reinterpret_cast<uint4 *>(dst) = h;
+        *reinterpret_cast<uint4 *>(dst + lo_off) = l;
+    }
+}
+
+// The weight ring as the MMA issuer sees it.
+struct RingView {
+    uint32_t base;                 // shared-memory address of stage 0
+    uint64_t *full, *empty;
+    int n, stage; uint32_t phase;
+};
+#define SPLIT_RING_NEXT(r, code)                                                   \
+    if (!mbar_wait(&(r).full[(r).stage], (r).phase, (code) + (r).stage, wd)) goto done; \
+    tc_fence_after();                                                              \
+    const uint32_t wst_ = (r).base + (uint32_t)(r).stage * kStage;
+#define SPLIT_RING_RELEASE(r)                                                      \
+    mma_commit(&(r).empty[(r).stage]);                                             \
+    if (++(r).stage == (r).n) { (r).stage = 0; (r).phase ^= 1; }
+
+// One K = 64 block of D[128 x rows] (+)= A[128 x 64] * W[rows x 64]^T in split precision: the hi weight block feeds
+// A_hi and A_lo, the lo weight block A_hi.  a_hi: address of the first of the block's 8 planes (plane stride a_plane).
+// Expands to two ring stages; `first` = the very first MMA of this accumulator (overwrite instead of accumulate).
+#define SPLIT_MMA_BLOCK(r, d_tmem, a_hi, a_lo_off, a_plane, a_rows, w_rows, idesc, first, code)                      \
+    {                                                                                                                \
+        { SPLIT_RING_NEXT(r, code)                                                                                   \
+          _Pragma("unroll")                                                                                          \
+          for (int k_ = 0; k_ < 4; ++k_) {                                                                           \
+              const uint64_t db_ = make_desc(wst_ + k_ * 2 * (w_rows) * 16, (w_rows));                               \
+              mma_bf16((d_tmem), make_desc((a_hi) + k_ * 2 * (a_plane), (a_rows)), db_, (idesc), ((first) && k_ == 0) ? 0u : 1u); \
+              mma_bf16((d_tmem), make_desc((a_hi) + (a_lo_off) + k_ * 2 * (a_plane), (a_rows)), db_, (idesc), 1u);   \
+          }                                                                                                          \
+          SPLIT_RING_RELEASE(r) }                                                                                    \
+        { SPLIT_RING_NEXT(r, code)                                                                                   \
+          _Pragma("unroll")                                                                                          \
+          for (int k_ = 0; k_ < 4; ++k_)                                                                             \
+              mma_bf16((d_tmem), make_desc((a_hi) + k_ * 2 * (a_plane), (a_rows)),                                   \
+                       make_desc(wst_ + k_ * 2 * (w_rows) * 16, (w_rows)), (idesc), 1u);                             \
+          SPLIT_RING_RELEASE(r) }                                                                                    \
+    }
+
+// Transposed form for the max-pooled last layer: D^T[128 channels x n_pts] (+)= W[128 x 64] * Act[n_pts x 64]^T.
+#define SPLIT_MMA_BLOCK_T(r, d_tmem, b_hi, b_lo_off, b_plane, b_rows, idesc, first, code)                            \
+    {                                                                                                                \
+        { SPLIT_RING_NEXT(r, code)                                                                                   \
+          _Pragma("unroll")                                                                                          \
+          for (int k_ = 0; k_ < 4; ++k_) {                                                                           \
+              const uint64_t da_ = make_desc(wst_ + k_ * 4096, 128);                                                 \
+              mma_bf16((d_tmem), da_, make_desc((b_hi) + k_ * 2 * (b_plane), (b_rows)), (idesc), ((first) && k_ == 0) ? 0u : 1u); \
+              mma_bf16((d_tmem), da_, make_desc((b_hi) + (b_lo_off) + k_ * 2 * (b_plane), (b_rows)), (idesc), 1u);   \
+          }                                                                                                          \
+          SPLIT_RING_RELEASE(r) }                                                                                    \
+        { SPLIT_RING_NEXT(r, code)                                                                                   \
+          _Pragma("unroll")                                                                                          \
+          for (int k_ = 0; k_ < 4; ++k_)                                                                             \
+              mma_bf16((d_tmem), make_desc(wst_ + k_ * 4096, 128), make_desc((b_hi) + k_ * 2 * (b_plane), (b_rows)), (idesc), 1u); \
+          SPLIT_RING_RELEASE(r) }                                                                                    \
+    }
+
+// ================================================================================================
+// split_chain_kernel
+// ================================================================================================
+struct ChainParams {
+    const float *x; int64_t sb, sc, sp; int bs, n;       // input (bs, c_in, n), strides in elements
+    int c_in, w0, n_mid, mid[3], last;
+    const float *w0_w, *w0_b, *mid_b, *last_b;           // fp32: (8, w0) transposed + zero-padded, (w0), concat(mid), (last)
+    const uint8_t *wstream;                              // 16 KB slots, (hi, lo) per block, consumption order
+    float *out;                                          // (bs, last) fp32, zero-initialised; max-pooled with atomicMax
+    int splits, n_items;
+    int pair;                                            // 1: the last layer runs on tile pairs (N = 256 points)
+    int act_bytes, pair_bytes, n_stages;                 // shared-memory carve-up chosen by the launcher
+    int front_blocks, last_blocks;                       // 16 KB slots per tile (mid layers) / per unit (last layer)
+    TcStatus wd;
+};
+
+// Dynamic shared memory: [act | pair buffer | weight ring | ChainTail]
+struct ChainTail {
+    float w0_w[128 * 8];
+    float w0_b[128];
+    float mid_b[512];
+    uint64_t w_full[kMaxStages], w_empty[kMaxStages];
+    uint64_t act_ready, acc_ready;
+    uint64_t last_full[2], last_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ int chain_in_width(const ChainParams &p, int l) { return l == 0 ? p.w0 : p.mid[l - 1]; }
+
+__global__ void __launch_bounds__(kThreads, 1)
+split_chain_kernel(const ChainParams p)
+{
+    const TcStatus wd = p.wd;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t *const s_act = smem_raw;
+    uint8_t *const s_pair = smem_raw + p.act_bytes;
+    uint8_t *const s_ring = s_pair + p.pair_bytes;
+    ChainTail &s = *reinterpret_cast<ChainTail *>(s_ring + (size_t)p.n_stages * kStage);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t act_lo = (uint32_t)p.act_bytes / 2, pair_lo = (uint32_t)p.pair_bytes / 2;
+    const int nq = p.pair ? 2 : 1;
+
+    for (int i = threadIdx.x; i < p.w0 * 8; i += kThreads) s.w0_w[i] = p.w0_w[i];
+    for (int i = threadIdx.x; i < p.w0; i += kThreads) s.w0_b[i] = p.w0_b[i];
+    {
+        int tot = 0;
+        for (int l = 0; l < p.n_mid; ++l) tot += p.mid[l];
+        for (int i = threadIdx.x; i < tot; i += kThreads) s.mid_b[i] = p.mid_b[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.n_stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+        mbar_init(&s.act_ready, kEpiThreads / 32);
+        mbar_init(&s.acc_ready, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.last_full[i], 1); mbar_init(&s.last_empty[i], kEpiThreads / 32); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&s.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    const int tiles_per_obj = (p.n + kTile - 1) / kTile;
+    const int n_last_chunks = p.last / 128;
+    const int k_last = p.mid[p.n_mid - 1];
+#define CH_ARRIVE(bar) do { __syncwarp(); if (lane == 0) mbar_arrive(bar); } while (0)
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ weight producer (one thread)
+        if (elect_one_sync()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int sp_i = item % p.splits;
+                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+                for (int t = t0; t < t1; t += nq) {
+                    const int total = nq * p.front_blocks + p.last_blocks;
+                    for (int i = 0; i < total; ++i) {
+                        // slots: the front blocks once per tile of the unit, then the last layer's blocks
+                        const int blk = i < nq * p.front_blocks ? i % p.front_blocks : p.front_blocks + (i - nq * p.front_blocks);
+                        SPLIT_STRESS(wd, 0x51);
+                        if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x5100 + stage, wd)) goto done;
+                        mbar_arrive_expect_tx(&s.w_full[stage], kStage);
+                        bulk_g2s(s_ring + (size_t)stage * kStage, p.wstream + (size_t)blk * kStage, kStage, &s.w_full[stage]);
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (elect_one_sync()) {
+            RingView ring{smem_u32(s_ring), s.w_full, s.w_empty, p.n_stages, 0, 0u};
+            uint32_t act_phase = 0, le_phase[2] = {0, 0};
+            const uint32_t a_act = smem_u32(s_act), a_pair = smem_u32(s_pair);
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int sp_i = item % p.splits;
+                const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+                for (int t = t0; t < t1; t += nq) {
+                    for (int q = 0; q < nq; ++q) {
+                        // mid layers: D[points x channels], input = the activation buffer (converted in place)
+                        for (int l = 0; l < p.n_mid; ++l) {
+                            const int K = chain_in_width(p, l), N = p.mid[l];
+                            const int rows = N < 128 ? N : 128;
+                            SPLIT_STRESS(wd, 0x52);
+                            if (!mbar_wait(&s.act_ready, act_phase, 0x5200 + l, wd)) goto done;
+                            act_phase ^= 1;
+                            tc_fence_after();
+                            const uint32_t idesc = make_idesc_bf16(128, rows);
+                            for (int nc = 0; nc < N / rows; ++nc)
+                                for (int kb = 0; kb < K / 64; ++kb)
+                                    SPLIT_MMA_BLOCK(ring, tmem + nc * 128, a_act + kb * 8 * kPlane, act_lo, kPlane, 128, rows, idesc, kb == 0, 0x5300)
+                            mma_commit(&s.acc_ready);
+                        }
+                    }
+                    // last layer, transposed: D^T[channels x points], double-buffered in TMEM
+                    {
+                        SPLIT_STRESS(wd, 0x52);
+                        if (!mbar_wait(&s.act_ready, act_phase, 0x52F0, wd)) goto done;
+                        act_phase ^= 1;
+                        tc_fence_after();
+                        const uint32_t idesc = make_idesc_bf16(128, p.pair ? 256 : 128);
+                        for (int cc = 0; cc < n_last_chunks; ++cc) {
+                            const int b = cc & 1;
+                            SPLIT_STRESS(wd, 0x54);
+                            if (!mbar_wait(&s.last_empty[b], le_phase[b] ^ 1, 0x5400 + b, wd)) goto done;
+                            le_phase[b] ^= 1;
+                            tc_fence_after();
+                            const uint32_t d = p.pair ? tmem + b * 256 : tmem + 256 + b * 128;
+                            for (int kb = 0; kb < k_last / 64; ++kb) {
+                                if (p.pair) SPLIT_MMA_BLOCK_T(ring, d, a_pair + kb * 8 * 2 * kPlane, pair_lo, 2 * kPlane, 256, idesc, kb == 0, 0x5500)
+                                else        SPLIT_MMA_BLOCK_T(ring, d, a_act + kb * 8 * kPlane, act_lo, kPlane, 128, idesc, kb == 0, 0x5500)
+                            }
+                            mma_commit(&s.last_full[b]);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (256 threads)
+        const int row = epi_row(), half = epi_half();
+        const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
+        uint32_t acc_phase = 0, lf_phase[2] = {0, 0};
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int b = item / p.splits, sp_i = item % p.splits;
+            const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+            float rmax[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
+            for (int t = t0; t < t1; t += nq) {
+                for (int q = 0; q < nq; ++q) {
+                    // ---- first layer (rows past the end of the object replicate its last point, an odd tail pair
+                    //      repeats its tile: the max-pool is idempotent under duplicates)
+                    {
+                        const int tq = (t + q < t1) ? t + q : t1 - 1;
+                        int pidx = tq * kTile + row;
+                        if (pidx > p.n - 1) pidx = p.n - 1;
+                        const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
+                        float xv[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+                        first_layer_split(s_act, act_lo, row, xv, p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b);
+                        fence_proxy_async_smem();
+                        CH_ARRIVE(&s.act_ready);
+                    }
+                    // ---- mid layers: this thread converts columns [half*N/2, (half+1)*N/2) of its row, in place
+                    //      (the layer's MMAs are complete when acc_ready fires); in pair mode the last mid layer
+                    //      writes rows q*128.. of the pair buffer instead
+                    int boff = 0;
+                    for (int l = 0; l < p.n_mid; ++l) {
+                        const int N = p.mid[l];
+                        const bool to_pair = p.pair && l == p.n_mid - 1;
+                        SPLIT_STRESS_WARP(wd, 0x41);
+                        if (!mbar_wait(&s.acc_ready, acc_phase, 0x4100 + l, wd)) goto done;
+                        acc_phase ^= 1;
+                        tc_fence_after();
+                        if (to_pair) epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_pair, pair_lo, 2 * kPlane, q * kTile + row, s.mid_b + boff);
+                        else         epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_act, act_lo, kPlane, row, s.mid_b + boff);
+                        boff += N;
+                        tc_fence_before();
+                        fence_proxy_async_smem();
+                        if (!(to_pair && q == 0)) CH_ARRIVE(&s.act_ready);     // tile X of a pair: the issuer has nothing to wait for yet
+                    }
+                }
+                // ---- last layer: this thread owns channel (cc*128 + row) and half of the unit's points
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    if (cc < n_last_chunks) {
+                        const int bsel = cc & 1;
+                        SPLIT_STRESS_WARP(wd, 0x42);
+                        if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0x4200 + cc, wd)) goto done;
+                        lf_phase[bsel] ^= 1;
+                        tc_fence_after();
+                        float m0 = rmax[cc], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                        const int ncol = p.pair ? 128 : 64;
+                        const uint32_t ta = tmem + lane_addr + (p.pair ? bsel * 256 : 256 + bsel * 128) + half * ncol;
+                        for (int c0 = 0; c0 < ncol; c0 += 64) {
+                            uint32_t v0[32], v1[32];
+                            tmem_ld32(ta + c0, v0);
+                            tmem_ld32(ta + c0 + 32, v1);
+                            tmem_ld_wait();
+                            if (c0 + 64 >= ncol) { tc_fence_before(); CH_ARRIVE(&s.last_empty[bsel]); }   // all values are in registers
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                m0 = fmax3(m0, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
+                                m1 = fmax3(m1, __uint_as_float(v0[i + 2]), __uint_as_float(v0[i + 3]));
+                                m2 = fmax3(m2, __uint_as_float(v0[i + 4]), __uint_as_float(v0[i + 5]));
+                                m3 = fmax3(m3, __uint_as_float(v0[i + 6]), __uint_as_float(v0[i + 7]));
+                                m0 = fmax3(m0, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
+                                m1 = fmax3(m1, __uint_as_float(v1[i + 2]), __uint_as_float(v1[i + 3]));
+                                m2 = fmax3(m2, __uint_as_float(v1[i + 4]), __uint_as_float(v1[i + 5]));
+                                m3 = fmax3(m3, __uint_as_float(v1[i + 6]), __uint_as_float(v1[i + 7]));
+                            }
+                        }
+                        rmax[cc] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    }
+                }
+            }
+            // ---- publish: relu(max + bias) >= 0, so integer atomicMax on the bit pattern is exact
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                if (cc < n_last_chunks && t1 > t0) {
+                    const int ch = cc * 128 + row;
+                    const float v = fmaxf(rmax[cc] + __ldg(p.last_b + ch), 0.f);
+                    atomicMax(reinterpret_cast<int *>(p.out + (int64_t)b * p.last + ch), __float_as_int(v));
+                }
+            }
+        }
+    }
+#undef CH_ARRIVE
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ================================================================================================
+// split_tail_kernel -- second half of the segmentation net in split precision
+//
+// Shared memory: A2 (conv2 output, 64 ch, hi | lo: 32 KB, kept for the four dconv1 chunks) | BIG (128 KB): two
+// chunk buffers CB[0..1] of 128 channels (hi | lo: 64 KB each); earlier in the tile CB[0]'s place holds A1 (conv1
+// output), later all of BIG holds A3 (dconv2 output, 256 ch) and then A4 (dconv3 output, 128 ch) | weight ring.
+// TMEM: D2 = dconv2 accumulator [0,256) | DA [256,384): conv2 accumulator, dconv1 chunks 0 / 2, dconv3 accumulator |
+// DB [384,512): dconv1 chunks 1 / 3, dconv4 accumulator.
+// Weight stream per tile (16 KB slots, hi then lo per block): conv2 | d1(0) | d1(1) | d1(2) | p(0) | d1(3) | p(1) |
+// p(2) | p(3) | dconv3 | dconv4, where d1(c) = dconv1 output channels c*128.., p(c) = dconv2 partial sum over input
+// channels c*128.. as (row half, k block) x 4.
+// ================================================================================================
+struct TailParams {
+    const float *x; int64_t sb, sc, sp; int bs, n; int c_in;
+    const float *w1_w, *w1_b, *b2;     // conv1 fp32 (8, 64) transposed + padded, (64); conv2 bias (64)
+    const float *gbias;                // (bs, 512) per-object dconv1 bias
+    const float *bd2, *bd3, *bd4;      // dconv2-4 biases (256), (128), (128)
+    const float *w5, *b5;              // dconv5 fp32 (2, 128), (2)
+    const uint8_t *wstream;
+    float *logits; uint8_t *mask;
+    int tiles_per_obj, n_items;
+    TcStatus wd;
+};
+constexpr int kTailStages = 3;
+constexpr int kTailBlocks = 2 + 4 * 2 + 4 * 8 + 8 + 4;       // 54 slots per tile
+struct TailSmem {
+    uint8_t a2[32768];
+    uint8_t big[131072];
+    uint8_t ring[kTailStages][kStage];
+    float w1_w[64 * 8], w1_b[64], b2[64], gb[512], bd2[256], bd3[128], bd4[128], w5[256], b5[2];
+    float lpart[2 * kTile];
+    uint64_t w_full[kTailStages], w_empty[kTailStages];
+    uint64_t act, acc;                             // serial hand-overs: operand ready / accumulator complete
+    uint64_t d1_full[2], d1_act[2], cb_free[2];    // per chunk buffer: accumulator ready / operand written / operand consumed
+    uint32_t tmem_base;
+};
+static_assert(sizeof(TailSmem) + 128 <= 232448, "TailSmem exceeds the 227 KB opt-in limit");
+constexpr uint32_t kTD2 = 0, kTDA = 256, kTDB = 384;
+
+__global__ void __launch_bounds__(kThreads, 1)
+split_tail_kernel(const TailParams p)
+{
+    const TcStatus wd = p.wd;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TailSmem &s = *reinterpret_cast<TailSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < 64 * 8; i += kThreads) s.w1_w[i] = p.w1_w[i];
+    for (int i = threadIdx.x; i < 64; i += kThreads) { s.w1_b[i] = p.w1_b[i]; s.b2[i] = p.b2[i]; }
+    for (int i = threadIdx.x; i < 256; i += kThreads) { s.bd2[i] = p.bd2[i]; s.w5[i] = p.w5[i]; }
+    for (int i = threadIdx.x; i < 128; i += kThreads) { s.bd3[i] = p.bd3[i]; s.bd4[i] = p.bd4[i]; }
+    if (threadIdx.x < 2) s.b5[threadIdx.x] = p.b5[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kTailStages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+        mbar_init(&s.act, kEpiThreads / 32); mbar_init(&s.acc, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kEpiThreads / 32); mbar_init(&s.cb_free[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&s.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+#define TL_ARRIVE(bar) do { __syncwarp(); if (lane == 0) mbar_arrive(bar); } while (0)
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ weight producer
+        if (elect_one_sync()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                for (int blk = 0; blk < kTailBlocks; ++blk) {
+                    SPLIT_STRESS(wd, 0x31);
+                    if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x3100 + stage, wd)) goto done;
+                    mbar_arrive_expect_tx(&s.w_full[stage], kStage);
+                    bulk_g2s(s.ring[stage], p.wstream + (size_t)blk * kStage, kStage, &s.w_full[stage]);
+                    if (++stage == kTailStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (elect_one_sync()) {
+            RingView ring{smem_u32(s.ring[0]), s.w_full, s.w_empty, kTailStages, 0, 0u};
+            uint32_t act_phase = 0, d1a_phase[2] = {0, 0};
+            const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128);
+            const uint32_t a2 = smem_u32(s.a2), big = smem_u32(s.big);
+#define TL_WAIT_ACT(code)                                                        \
+            SPLIT_STRESS(wd, 0x32);                                              \
+            if (!mbar_wait(&s.act, act_phase, code, wd)) goto done;              \
+            act_phase ^= 1; tc_fence_after();
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                // conv2: A1 (64 ch in CB[0]'s place, lo half at +16 KB) -> DA
+                TL_WAIT_ACT(0x3200)
+                SPLIT_MMA_BLOCK(ring, tmem + kTDA, big, 16384u, kPlane, 128, 64, id64, true, 0x3300)
+                mma_commit(&s.acc);
+                TL_WAIT_ACT(0x3201)                                  // A2 in place
+                // dconv1 chunk c: A2 x Wd1[c*128.., 0:64] -> DA / DB
+#define TL_ISSUE_D1(c)                                                                                        \
+                { SPLIT_MMA_BLOCK(ring, tmem + (((c) & 1) ? kTDB : kTDA), a2, 16384u, kPlane, 128, 128, id128, true, 0x3310) \
+                  mma_commit(&s.d1_full[(c) & 1]); }
+                TL_ISSUE_D1(0)
+                TL_ISSUE_D1(1)
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int j = c & 1;
+                    SPLIT_STRESS(wd, 0x34);
+                    if (!mbar_wait(&s.d1_act[j], d1a_phase[j], 0x3400 + c, wd)) goto done;     // CB[j] written, DA / DB drained
+                    d1a_phase[j] ^= 1; tc_fence_after();
+                    if (c + 2 < 4) TL_ISSUE_D1(c + 2)
+                    // dconv2 partial sum over input channels c*128..+128: D2[:, nc*128..] += CB[j] x Wd2[nc*128.., c*128..]
+                    const uint32_t cb = big + j * 65536;
+                    for (int nc = 0; nc < 2; ++nc)
+                        for (int kb = 0; kb < 2; ++kb)
+                            SPLIT_MMA_BLOCK(ring, tmem + kTD2 + nc * 128, cb + kb * 8 * kPlane, 32768u, kPlane, 128, 128, id128, c == 0 && kb == 0, 0x3320)
+                    if (c + 2 < 4) mma_commit(&s.cb_free[j]);          // chunk c + 2 may overwrite CB[j] once these have run
+                }
+                mma_commit(&s.acc);                                   // dconv2 accumulator complete
+                // dconv3: A3 (256 ch over all of BIG, lo half at +64 KB) -> DA
+                TL_WAIT_ACT(0x3202)
+                for (int kb = 0; kb < 4; ++kb)
+                    SPLIT_MMA_BLOCK(ring, tmem + kTDA, big + kb * 8 * kPlane, 65536u, kPlane, 128, 128, id128, kb == 0, 0x3330)
+                mma_commit(&s.acc);
+                // dconv4: A4 (128 ch, lo half at +32 KB) -> DB
+                TL_WAIT_ACT(0x3203)
+                for (int kb = 0; kb < 2; ++kb)
+                    SPLIT_MMA_BLOCK(ring, tmem + kTDB, big + kb * 8 * kPlane, 32768u, kPlane, 128, 128, id128, kb == 0, 0x3340)
+                mma_commit(&s.acc);
+            }
+#undef TL_ISSUE_D1
+#undef TL_WAIT_ACT
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (256 threads)
+        const int row = epi_row(), half = epi_half();
+        const uint32_t tl = tmem + ((uint32_t)(row & ~31) << 16);
+        const int etid = threadIdx.x - 64;
+        uint32_t acc_phase = 0, d1f_phase[2] = {0, 0}, cbf_phase[2] = {0, 0};
+#define TL_WAIT_ACC(code)                                                        \
+        SPLIT_STRESS_WARP(wd, 0x21);                                             \
+        if (!mbar_wait(&s.acc, acc_phase, code, wd)) goto done;                  \
+        acc_phase ^= 1; tc_fence_after();
+#define TL_PUBLISH(bar) do { tc_fence_before(); fence_proxy_async_smem(); TL_ARRIVE(bar); } while (0)
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int b = item / p.tiles_per_obj, t = item % p.tiles_per_obj;
+            const int pidx_raw = t * kTile + row;
+            const bool valid = pidx_raw < p.n;
+            const int pidx = valid ? pidx_raw : p.n - 1;
+            // per-object dconv1 bias (nobody reads s.gb between the previous tile's chunk epilogues and this barrier)
+            for (int i = etid; i < 512; i += kEpiThreads) s.gb[i] = __ldg(p.gbias + (int64_t)b * 512 + i);
+            // ---- conv1 on CUDA cores -> A1 (in CB[0]'s place; the previous tile's dconv4 has finished reading A4 there)
+            {
+                const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
+                float xv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+                first_layer_split(s.big, 16384u, row, xv, p.c_in, 64, half * 32, 32, s.w1_w, s.w1_b);
+                TL_PUBLISH(&s.act);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // s.gb complete
+            // ---- conv2 epilogue: DA (64 columns) -> A2
+            TL_WAIT_ACC(0x2100)
+            epilogue_split(tl + kTDA, half * 32, 32, s.a2, 16384u, kPlane, row, s.b2);
+            TL_PUBLISH(&s.act);
+            // ---- dconv1 chunk epilogues: DA / DB (128 columns) + per-object bias -> CB[j]
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int j = c & 1;
+                SPLIT_STRESS_WARP(wd, 0x22);
+                if (!mbar_wait(&s.d1_full[j], d1f_phase[j], 0x2200 + c, wd)) goto done;
+                d1f_phase[j] ^= 1; tc_fence_after();
+                if (c >= 2) {
+                    if (!mbar_wait(&s.cb_free[j], cbf_phase[j], 0x2210 + c, wd)) goto done;     // dconv2 partial c - 2 has read CB[j]
+                    cbf_phase[j] ^= 1;
+                }
+                epilogue_split(tl + (j ? kTDB : kTDA), half * 64, 64, s.big + j * 65536, 32768u, kPlane, row, s.gb + c * 128);
+                TL_PUBLISH(&s.d1_act[j]);
+            }
+            // ---- dconv2 epilogue: D2 (256 columns) -> A3 over all of BIG (every partial sum has been consumed)
+            TL_WAIT_ACC(0x2101)
+            epilogue_split(tl + kTD2, half * 128, 128, s.big, 65536u, kPlane, row, s.bd2);
+            TL_PUBLISH(&s.act);
+            // ---- dconv3 epilogue: DA (128 columns) -> A4
+            TL_WAIT_ACC(0x2102)
+            epilogue_split(tl + kTDA, half * 64, 64, s.big, 32768u, kPlane, row, s.bd3);
+            TL_PUBLISH(&s.act);
+            // ---- dconv4 epilogue: bias + ReLU in fp32, then the 128 -> 2 layer, logits and mask.  Each half reduces
+            //      64 channels; the upper half hands its partial sums over in smem and the lower half adds them in a
+            //      fixed order (deterministic).
+            TL_WAIT_ACC(0x2103)
+            {
+                uint32_t v0[32], v1[32];
+                const int c0 = half * 64;
+                tmem_ld32(tl + kTDB + c0, v0);
+                tmem_ld32(tl + kTDB + c0 + 32, v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                float l0 = 0.f, l1 = 0.f, m0 = 0.f, m1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float ya = fmaxf(__uint_as_float(v0[i]) + s.bd4[c0 + i], 0.f);
+                    const float yb = fmaxf(__uint_as_float(v1[i]) + s.bd4[c0 + 32 + i], 0.f);
+                    l0 = fmaf(ya, s.w5[c0 + i], l0);       l1 = fmaf(ya, s.w5[128 + c0 + i], l1);
+                    m0 = fmaf(yb, s.w5[c0 + 32 + i], m0);  m1 = fmaf(yb, s.w5[128 + c0 + 32 + i], m1);
+                }
+                l0 += m0; l1 += m1;
+                if (half == 1) { s.lpart[row] = l0; s.lpart[kTile + row] = l1; }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (half == 0 && valid) {
+                    const float f0 = (s.b5[0] + l0) + s.lpart[row];
+                    const float f1 = (s.b5[1] + l1) + s.lpart[kTile + row];
+                    const int64_t o = (int64_t)b * p.n + pidx;
+                    *reinterpret_cast<float2 *>(p.logits + o * 2) = make_float2(f0, f1);
+                    p.mask[o] = (f0 < f1) ? 1 : 0;
+                }
+                // the lower half must have read lpart (and everybody s.gb) before the next tile overwrites them
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
+        }
+#undef TL_PUBLISH
+#undef TL_WAIT_ACC
+    }
+#undef TL_ARRIVE
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace split
+}  // namespace al3d
+
+using namespace al3d;
+
+extern "C" int al3d_chain_maxpool_bf16x3(const al3d_split_chain_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
+                                         int bs, int n, float *out, void *stream)
+{
+    using namespace al3d::split;
+    AL3D_CHECK_ARG(w && x && out, "al3d_chain_maxpool_bf16x3: null pointer");
+    AL3D_CHECK_ARG(w->c_in >= 1 && w->c_in <= 8, "al3d_chain_maxpool_bf16x3: c_in=%d", w->c_in);
+    AL3D_CHECK_ARG(w->w0 == 64 || w->w0 == 128, "al3d_chain_maxpool_bf16x3: w0=%d must be 64 or 128", w->w0);
+    AL3D_CHECK_ARG(w->n_mid == 2 || w->n_mid == 3, "al3d_chain_maxpool_bf16x3: n_mid=%d", w->n_mid);
+    int tot = 0, front_blocks = 0, act_w = w->w0, prev = w->w0;
+    for (int l = 0; l < w->n_mid; ++l) {
+        const int N = w->mid[l];
+        AL3D_CHECK_ARG(N == 64 || N == 128 || N == 256, "al3d_chain_maxpool_bf16x3: mid width %d", N);
+        const int rows = std::min(N, 128);
+        front_blocks += 2 * (N / rows) * (prev / 64);
+        if (!(w->pair && l == w->n_mid - 1)) act_w = std::max(act_w, N);
+        prev = N; tot += N;
+    }
+    AL3D_CHECK_ARG(tot <= 512, "al3d_chain_maxpool_bf16x3: widths too large");
+    AL3D_CHECK_ARG(w->last % 128 == 0 && w->last >= 128 && w->last <= 1024, "al3d_chain_maxpool_bf16x3: last=%d", w->last);
+    AL3D_CHECK_ARG(bs >= 0 && n >= 1, "al3d_chain_maxpool_bf16x3: bad shape");
+    if (bs == 0) return 0;
+    ChainParams p;
+    p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n;
+    p.c_in = w->c_in; p.w0 = w->w0; p.n_mid = w->n_mid;
+    for (int l = 0; l < 3; ++l) p.mid[l] = w->mid[l];
+    p.last = w->last;
+    p.w0_w = w->w0_w; p.w0_b = w->w0_b; p.mid_b = w->mid_b; p.last_b = w->last_b;
+    p.wstream = (const uint8_t *)w->wstream; p.out = out;
+    p.pair = w->pair ? 1 : 0;
+    p.front_blocks = front_blocks;
+    p.last_blocks = 2 * (w->last / 128) * (prev / 64);
+    AL3D_CHECK_ARG(w->n_blocks == p.front_blocks + p.last_blocks, "al3d_chain_maxpool_bf16x3: n_blocks=%d, expected %d", w->n_blocks,
+                   p.front_blocks + p.last_blocks);
+    if (tc_launch_status(&p.wd)) return 1;
+    const int tiles = (n + kTile - 1) / kTile;
+    const int units = p.pair ? (tiles + 1) / 2 : tiles;
+    const int sms = tc_num_sms();
+    int splits = 1;
+    if (bs < 2 * sms) splits = (int)std::min<int64_t>(units, ceil_div(2 * sms, bs));
+    p.splits = std::max(splits, 1);
+    p.n_items = bs * p.splits;
+    const int grid = std::min(p.n_items, sms);
+    p.act_bytes = act_w * kTile * 2 * 2;                       // hi | lo
+    p.pair_bytes = p.pair ? prev * 2 * kTile * 2 * 2 : 0;      // 256 rows, hi | lo
+    const int budget = 232448 - 1024;
+    int stages = (budget - p.act_bytes - p.pair_bytes - (int)sizeof(ChainTail)) / kStage;
+    stages = std::min(stages, kMaxStages);
+    AL3D_CHECK_ARG(stages >= 2, "al3d_chain_maxpool_bf16x3: no room for the weight ring (act %d B, pair %d B)", p.act_bytes, p.pair_bytes);
+    p.n_stages = stages;
+    const size_t smem = (size_t)p.act_bytes + p.pair_bytes + (size_t)stages * kStage + sizeof(ChainTail);
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    split_chain_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    AL3D_CHECK_LAUNCH("split_chain_kernel");
+    return 0;
+}
+
+extern "C" int al3d_seg_pass2_bf16x3(const al3d_split_tail_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
+                                     int bs, int n, const float *gbias, float *logits, uint8_t *mask, void *stream)
+{
+    using namespace al3d::split;
+    AL3D_CHECK_ARG(w && x && gbias && logits && mask, "al3d_seg_pass2_bf16x3: null pointer");
+    AL3D_CHECK_ARG(w->c_in >= 1 && w->c_in <= 8, "al3d_seg_pass2_bf16x3: c_in=%d", w->c_in);
+    AL3D_CHECK_ARG(bs >= 0 && n >= 1, "al3d_seg_pass2_bf16x3: bad shape");
+    if (bs == 0) return 0;
+    TailParams p;
+    p.x = x; p.sb = sb; p.sc = sc; p.sp = sp; p.bs = bs; p.n = n; p.c_in = w->c_in;
+    p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.gbias = gbias;
+    p.bd2 = w->bd2; p.bd3 = w->bd3; p.bd4 = w->bd4; p.w5 = w->w5; p.b5 = w->b5;
+    p.wstream = (const uint8_t *)w->wstream; p.logits = logits; p.mask = mask;
+    if (tc_launch_status(&p.wd)) return 1;
+    p.tiles_per_obj = (n + kTile - 1) / kTile;
+    const int64_t items = (int64_t)bs * p.tiles_per_obj;
+    AL3D_CHECK_ARG(items < (1ll << 31), "al3d_seg_pass2_bf16x3: too many tiles");
+    p.n_items = (int)items;
+    const int grid = std::min(p.n_items, tc_num_sms());
+    const size_t smem = sizeof(TailSmem) + 128;
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    split_tail_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    AL3D_CHECK_LAUNCH("split_tail_kernel");
+    return 0;
+}

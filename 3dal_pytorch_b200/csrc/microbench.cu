@@ -22,7 +22,7 @@ struct MicroSmem {
 // CE: commits per group of 8 MMAs (0 = one commit at the very end, 1 = after each group, 2 = after every 4, 8 = every MMA).
 template <int MODE, int CE>
 __global__ void __launch_bounds__(256, 1)
-mma_microbench_kernel(int N, int n_groups, int bg, const uint8_t *src, long long *out)
+mma_microbench_kernel(int N, int n_groups, int bg, const uint8_t *src, long long *out, const TcStatus wd)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     MicroSmem &s = *reinterpret_cast<MicroSmem *>(smem_raw);
@@ -64,7 +64,7 @@ mma_microbench_kernel(int N, int n_groups, int bg, const uint8_t *src, long long
         }
         mma_commit(&s.done);
         const long long t1 = clock64();
-        mbar_wait(&s.done, 0, 0xB000);
+        mbar_wait(&s.done, 0, 0xB000, wd);
         const long long t2 = clock64();
         if (blockIdx.x == 0) {
             out[0] = t1 - t0;              // issue time of the whole sequence
@@ -87,10 +87,10 @@ mma_microbench_kernel(int N, int n_groups, int bg, const uint8_t *src, long long
             const int b = i & 1;
             mbar_arrive_expect_tx(&s.ring_full[b], 16384);
             bulk_g2s(s.ring[b], src + (size_t)((i * 148 + blockIdx.x) & 63) * 16384, 16384, &s.ring_full[b]);
-            if (i > 0) { mbar_wait(&s.ring_full[b ^ 1], ph[b ^ 1], 0xB001); ph[b ^ 1] ^= 1; }
+            if (i > 0) { mbar_wait(&s.ring_full[b ^ 1], ph[b ^ 1], 0xB001, wd); ph[b ^ 1] ^= 1; }
             ++i; ++blocks;
         }
-        mbar_wait(&s.ring_full[(i - 1) & 1], ph[(i - 1) & 1], 0xB002);
+        mbar_wait(&s.ring_full[(i - 1) & 1], ph[(i - 1) & 1], 0xB002, wd);
         if (blockIdx.x == 0) out[3] = blocks;
     } else if (warp >= 4 && (bg & 1)) {
         // background: epilogue-like TMEM reads of the accumulator columns
@@ -118,7 +118,9 @@ static int launch_micro(int N, int n_groups, int n_ctas, int bg, const uint8_t *
 {
     const size_t smem = sizeof(MicroSmem) + 128;
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(mma_microbench_kernel<MODE, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mma_microbench_kernel<MODE, CE><<<n_ctas, 256, smem, stream>>>(N, n_groups, bg, src, out);
+    TcStatus wd;
+    if (tc_launch_status(&wd)) return 1;
+    mma_microbench_kernel<MODE, CE><<<n_ctas, 256, smem, stream>>>(N, n_groups, bg, src, out, wd);
     AL3D_CHECK_LAUNCH("mma_microbench_kernel");
     return 0;
 }

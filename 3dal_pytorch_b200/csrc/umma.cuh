@@ -15,10 +15,26 @@
 namespace al3d {
 namespace umma {
 
-// A wait that exceeds this many clock64 ticks records a code in g_abort and gives up, so that a
-// protocol bug shows up as a reported error instead of a hung GPU.
-static __device__ unsigned int g_abort = 0;
+// Watchdog.  A wait that exceeds kWaitTimeoutCycles clock64 ticks records `code` in the status word of the launch
+// (pinned, host-mapped memory owned by the library, one word per device: the host reads it without any CUDA call) and,
+// unless the launch asked for diagnostics only, traps -- the launch then fails with a CUDA error at the caller's next
+// synchronisation instead of handing back invalid outputs.  There is no device-global state: the word travels in the
+// kernel parameters.
+struct TcStatus {
+    unsigned int *word;      // host-mapped status word (0 = ok)
+    int trap;                // bit 0: __trap() after recording the code (default 1); bit 1: test hook (seg_pass1_kernel)
+    int stress;              // > 0: upper bound (ns) of the pseudo-random delays injected per role (protocol stress tests)
+};
 constexpr long long kWaitTimeoutCycles = 1ll << 31;
+
+static __device__ __noinline__ void watchdog_fire(const TcStatus &st, uint32_t code)
+{
+    if (st.word) {
+        atomicCAS_system(st.word, 0u, code);
+        __threadfence_system();
+    }
+    if (st.trap & 1) __trap();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -35,6 +51,33 @@ __device__ __forceinline__ bool elect_one_sync()
         "@px mov.s32 %0, 1;\n\t}"
         : "+r"(pred));
     return pred != 0;
+}
+
+// Delay injection for the protocol stress tests (a no-op when st.stress == 0; only compiled into libal3d_stress.so).
+// st.stress < 2^24: with probability 1/4 sleep a pseudo-random time below st.stress ns.  Bit 24 set: TARGETED mode --
+// only the hooks of seg_pass1_kernel's front warps (salts 0x81, 0x82, 0x84) sleep, always, for the
+// full (st.stress & 0xFFFFFF) ns: a consistently slow front is what laps the round-1 release protocol.
+__device__ __forceinline__ uint32_t stress_ns_for(const TcStatus &st, uint32_t salt)
+{
+    if (st.stress & (1 << 24)) return (salt == 0x81u || salt == 0x82u || salt == 0x84u) ? ((uint32_t)st.stress & 0xFFFFFFu) : 0u;
+    uint32_t h = ((uint32_t)clock64() ^ (blockIdx.x * 0x9E3779B9u) ^ ((salt + (threadIdx.x >> 5) * 131u) * 0x85EBCA6Bu)) * 0xC2B2AE35u;
+    h ^= h >> 15;
+    return ((h & 3u) == 0u) ? (h >> 8) % (uint32_t)st.stress : 0u;
+}
+__device__ __forceinline__ void stress_delay(const TcStatus &st, uint32_t salt)        // single thread
+{
+    if (st.stress > 0) {
+        const uint32_t ns = stress_ns_for(st, salt);
+        if (ns) __nanosleep(ns);
+    }
+}
+__device__ __forceinline__ void stress_delay_warp(const TcStatus &st, uint32_t salt)   // whole converged warp, same delay
+{
+    if (st.stress > 0) {
+        const uint32_t ns = __shfl_sync(0xFFFFFFFFu, stress_ns_for(st, salt), 0);
+        if (ns) __nanosleep(ns);
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------- mbarrier
@@ -63,26 +106,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-// Returns false if the wait was abandoned (timeout or an earlier abort anywhere on the device).
-__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, uint32_t code)
+// Returns false if the wait was abandoned (timeout; only reachable with st.trap == 0).
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, uint32_t code, const TcStatus &st)
 {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 1023) == 0) {
-            if (*(volatile unsigned int *)&g_abort != 0) return false;
-            if (clock64() - t0 > kWaitTimeoutCycles) {
-                atomicCAS(&g_abort, 0u, code);
-                return false;
-            }
+        if ((++spins & 1023) == 0 && clock64() - t0 > kWaitTimeoutCycles) {
+            watchdog_fire(st, code);
+            return false;
         }
     }
     return true;
 }
 
 // Same wait with cluster-scope acquire: for barriers whose arrivals come from the peer CTA of a pair.
-__device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity, uint32_t code)
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity, uint32_t code, const TcStatus &st)
 {
     const long long t0 = clock64();
     int spins = 0;
@@ -96,12 +136,9 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (ok) return true;
-        if ((++spins & 1023) == 0) {
-            if (*(volatile unsigned int *)&g_abort != 0) return false;
-            if (clock64() - t0 > kWaitTimeoutCycles) {
-                atomicCAS(&g_abort, 0u, code);
-                return false;
-            }
+        if ((++spins & 1023) == 0 && clock64() - t0 > kWaitTimeoutCycles) {
+            watchdog_fire(st, code);
+            return false;
         }
     }
 }
@@ -312,4 +349,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 }
 
 }  // namespace umma
+
+// Host side (tcstatus.cu): the watchdog status of the CURRENT device for a launch (allocates the device's pinned,
+// host-mapped status block on first use) and the SM count of the current device.  Return 0 on success.
+int tc_launch_status(umma::TcStatus *out);
+int tc_num_sms();
 }  // namespace al3d

@@ -135,6 +135,7 @@ def choice_table_numpy_legacy(counts_host, n_pts):
 def mask_and_gather(pts, logits, n_pts, policy, want_indices=False, mask=None):
     """mask: the (bs,n) bool mask already produced by the segmentation epilogue (bf16 mode), or None
     to derive it from the logits here."""
+    from_tc = mask is not None
     if mask is None:
         mask, pos, count = ops.mask_compact(logits=logits)
     else:
@@ -142,7 +143,11 @@ def mask_and_gather(pts, logits, n_pts, policy, want_indices=False, mask=None):
     choice = None
     if policy == "numpy_legacy":
         # the one documented host round-trip: bs counts down, a (bs,n_pts) table up
-        table = choice_table_numpy_legacy(count.cpu().numpy(), n_pts)
+        counts_host = count.cpu().numpy()
+        if from_tc:                           # the mask came from a tensor-core kernel: this D2H is a sync point
+            from . import engine_bf16
+            engine_bf16.check_abort("gather (numpy_legacy count copy)", pts.device)
+        table = choice_table_numpy_legacy(counts_host, n_pts)
         choice = torch.from_numpy(table).to(pts.device, non_blocking=True)
     elif policy != "strided":
         raise ValueError("gather_policy must be 'strided' or 'numpy_legacy'")

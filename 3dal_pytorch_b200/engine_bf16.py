@@ -14,7 +14,6 @@ import torch
 from . import _lib, ops
 
 BLOCK_ELEMS = 8192           # 16 KB of bf16
-CHECK_ABORT = os.environ.get("AL3D_TC_CHECK", "0") == "1"
 
 
 class ChainWeightsStruct(ctypes.Structure):
@@ -28,7 +27,7 @@ class Pass1WeightsStruct(ctypes.Structure):
     _fields_ = [("c_in", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("w1_w", ctypes.c_void_p), ("w1_b", ctypes.c_void_p), ("b2", ctypes.c_void_p), ("b3", ctypes.c_void_p),
                 ("b4", ctypes.c_void_p), ("b5", ctypes.c_void_p), ("wfront", ctypes.c_void_p), ("w5stream", ctypes.c_void_p),
-                ("host_consts", ctypes.c_void_p)]
+                ("consts_host", ctypes.c_void_p)]
 
 
 class Pass2WeightsStruct(ctypes.Structure):
@@ -134,9 +133,9 @@ class SegPack:
         for k, v in self.t1.items():
             setattr(s1, k, v.data_ptr())
         # small per-model constants the kernel takes in its parameter block (constant-bank operands): HOST copy
-        self.host_consts = torch.cat([self.t1[k].detach().float().cpu().reshape(-1) for k in ("w1_w", "w1_b", "b2", "b3", "b4")]).contiguous()
-        assert self.host_consts.numel() == 832
-        s1.host_consts = self.host_consts.data_ptr()
+        self.consts_host = torch.cat([self.t1[k].detach().float().cpu().reshape(-1) for k in ("w1_w", "w1_b", "b2", "b3", "b4")]).contiguous()
+        assert self.consts_host.numel() == 832
+        s1.consts_host = self.consts_host.data_ptr()
         self.struct1 = s1
         # the 1024-wide half of dconv1 acts on the per-object global feature: kept fp32
         self.w_glob = wd1[:, 64:]
@@ -171,12 +170,48 @@ class _timed:
             KERNEL_EVENTS.setdefault(self.name, []).append((self.e0, self.e1))
 
 
-def check_abort(what):
-    code = ctypes.c_int(0)
-    _lib.check(_lib.lib().al3d_tc_abort_code(ctypes.byref(code)), "tc_abort_code")
-    if code.value != 0:
-        raise RuntimeError("libal3d: %s gave up on an mbarrier wait (watchdog code 0x%X); outputs are invalid"
-                           % (what, code.value))
+WATCHDOG_ROLES = {
+    0x6: "trunk_pair_kernel epilogue warps", 0x7: "trunk_pair_kernel producer / MMA issuer",
+    0x8: "seg_pass1_kernel reducer / front warps", 0x9: "seg_pass1_kernel producer / MMA issuers",
+    0xA: "seg_pass2_kernel loader / MMA issuers", 0xB: "seg_pass2_kernel epilogue warps",
+    0xC: "chain_max_kernel producer / MMA issuer", 0xD: "chain_max_kernel epilogue warps", 0xE: "umma selftest",
+}
+_status_words = {}
+
+
+def _status_word(dev_index):
+    """ctypes view of the device's host-mapped watchdog status word (csrc/tcstatus.cu): reading it is a plain
+    host load -- no CUDA call, no synchronisation."""
+    w = _status_words.get(dev_index)
+    if w is None:
+        ptr = ctypes.c_void_p()
+        with torch.cuda.device(dev_index):
+            _lib.check(_lib.lib().al3d_tc_status_word_host(ctypes.byref(ptr)), "tc_status_word_host")
+        w = ctypes.c_uint32.from_address(ptr.value)
+        _status_words[dev_index] = w
+    return w
+
+
+def check_abort(what, device=None):
+    """Raises if a tensor-core kernel on `device` gave up on an mbarrier wait since the last check.  Called by
+    default before every tensor-core launch and at every host synchronisation point of the pipeline; costs one
+    host load.  (The kernel also traps, so the caller's next CUDA synchronisation fails as well.)"""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    w = _status_word(idx)
+    code = w.value
+    if code != 0:
+        w.value = 0
+        raise RuntimeError("libal3d: watchdog code 0x%X (%s) -- a tensor-core kernel gave up on an mbarrier wait; "
+                           "outputs since the last check are invalid (noticed at: %s)"
+                           % (code, WATCHDOG_ROLES.get(code >> 12, "?"), what))
+
+
+def configure_watchdog(trap=True, stress_ns=0, legacy_pass1_release=False):
+    """trap=False: record the code only (diagnostics); stress_ns > 0: inject pseudo-random per-role delays of up to
+    that many ns before the kernels' barrier waits (protocol stress tests); legacy_pass1_release: run seg_pass1_kernel
+    with the round-1 single out4_free barrier (known to deadlock; lets the stress test prove it can detect that)."""
+    _lib.check(_lib.lib().al3d_tc_configure(int(bool(trap)) | (2 if legacy_pass1_release else 0), int(stress_ns)),
+               "tc_configure")
 
 
 def chain_maxpool(pack, x):
@@ -186,11 +221,10 @@ def chain_maxpool(pack, x):
     assert C == pack.c_in, (C, pack.c_in)
     out = torch.zeros((bs, pack.last), device=x.device, dtype=torch.float32)
     sb, sc, sp = x.stride()
+    check_abort("chain_maxpool launch", x.device)
     with _timed("chain_max_kernel[last=%d]" % pack.last):
         _lib.check(_lib.lib().al3d_chain_maxpool_bf16(ctypes.byref(pack.struct), x.data_ptr(), sb, sc, sp, bs, n,
                                                       out.data_ptr(), ops._stream()), "chain_maxpool_bf16")
-    if CHECK_ABORT:
-        check_abort("chain_max_kernel")
     return out
 
 
@@ -200,11 +234,10 @@ def seg_pass1(pack, pts):
     bs, C, n = pts.shape
     out = torch.zeros((bs, 1024), device=pts.device, dtype=torch.float32)
     sb, sc, sp = pts.stride()
+    check_abort("seg_pass1 launch", pts.device)
     with _timed("seg_pass1_kernel"):
         _lib.check(_lib.lib().al3d_seg_pass1_bf16(ctypes.byref(pack.struct1), pts.data_ptr(), sb, sc, sp, bs, n,
                                                   out.data_ptr(), ops._stream()), "seg_pass1_bf16")
-    if CHECK_ABORT:
-        check_abort("seg_pass1_kernel")
     return out
 
 
@@ -216,12 +249,11 @@ def seg_forward(pack, fw, pts):
     logits = torch.empty((bs, n, 2), device=pts.device, dtype=torch.float32)
     mask = torch.empty((bs, n), device=pts.device, dtype=torch.bool)
     sb, sc, sp = pts.stride()
+    check_abort("seg_pass2 launch", pts.device)
     with _timed("seg_pass2_kernel"):
         _lib.check(_lib.lib().al3d_seg_pass2_bf16(ctypes.byref(pack.struct), pts.data_ptr(), sb, sc, sp, bs, n,
                                                   gbias.data_ptr(), logits.data_ptr(), mask.data_ptr(), ops._stream()),
                    "seg_pass2_bf16")
-    if CHECK_ABORT:
-        check_abort("seg_pass2_kernel")
     return logits, mask
 
 
@@ -236,6 +268,7 @@ def umma_selftest(a, b, swap=False):
     ak, bk = kp_pack(a), kp_pack(b)
     _lib.check(_lib.lib().al3d_umma_selftest(ak.data_ptr(), bk.data_ptr(), N, K, d.data_ptr(), int(swap), ops._stream()),
                "umma_selftest")
+    torch.cuda.synchronize()
     check_abort("umma_selftest_kernel")
     return d
 
@@ -248,6 +281,7 @@ def umma_selftest_ts(a, b):
     a = a.contiguous().float()
     _lib.check(_lib.lib().al3d_umma_selftest_ts(a.data_ptr(), bk.data_ptr(), N, K, d.data_ptr(), ops._stream()),
                "umma_selftest_ts")
+    torch.cuda.synchronize()
     check_abort("umma_selftest_ts_kernel")
     return d
 
@@ -260,6 +294,7 @@ def umma_selftest_pair(a, b):
     a = a.contiguous().float()
     _lib.check(_lib.lib().al3d_umma_selftest_pair(a.data_ptr(), bk.data_ptr(), N, K, d.data_ptr(), ops._stream()),
                "umma_selftest_pair")
+    torch.cuda.synchronize()
     check_abort("umma_selftest_pair_kernel")
     return d
 
@@ -272,5 +307,6 @@ def umma_selftest_pair_ss(a, b):
     bk = torch.cat([kp_pack(b[:64]), kp_pack(b[64:])]).contiguous()
     _lib.check(_lib.lib().al3d_umma_selftest_pair_ss(ak.data_ptr(), bk.data_ptr(), K, d.data_ptr(), ops._stream()),
                "umma_selftest_pair_ss")
+    torch.cuda.synchronize()
     check_abort("umma_selftest_pair_ss_kernel")
     return d

@@ -1,0 +1,156 @@
+"""bf16x3 split-precision tensor-core mode (csrc/chain_split.cu): weight packing and launch sequences.
+
+Every folded fp32 weight matrix is split into hi = bf16(W) and lo = bf16(W - hi); each (<=128 rows x 64 K) block is
+stored as a hi slot followed by a lo slot (16 KB each, KP layout of engine_bf16.kp_pack), in the order the kernel's
+MMA thread consumes them.  The kernels split the activations the same way on the fly and evaluate
+a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation: 16 significant bits per operand.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+from .engine_bf16 import BLOCK_ELEMS, _pad8, _timed, check_abort, kp_pack
+
+
+class SplitChainWeightsStruct(ctypes.Structure):
+    _fields_ = [("c_in", ctypes.c_int32), ("w0", ctypes.c_int32), ("n_mid", ctypes.c_int32),
+                ("mid", ctypes.c_int32 * 3), ("last", ctypes.c_int32), ("n_blocks", ctypes.c_int32),
+                ("pair", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("w0_w", ctypes.c_void_p), ("w0_b", ctypes.c_void_p), ("mid_b", ctypes.c_void_p),
+                ("last_b", ctypes.c_void_p), ("wstream", ctypes.c_void_p)]
+
+
+class SplitTailWeightsStruct(ctypes.Structure):
+    _fields_ = [("c_in", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("w1_w", ctypes.c_void_p), ("w1_b", ctypes.c_void_p), ("b2", ctypes.c_void_p),
+                ("bd2", ctypes.c_void_p), ("bd3", ctypes.c_void_p), ("bd4", ctypes.c_void_p),
+                ("w5", ctypes.c_void_p), ("b5", ctypes.c_void_p), ("wstream", ctypes.c_void_p)]
+
+
+def split_hi_lo(w):
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def _slot(w_bf16):
+    flat = kp_pack(w_bf16)
+    out = torch.zeros(BLOCK_ELEMS, dtype=torch.bfloat16, device=w_bf16.device)
+    out[: flat.numel()] = flat
+    return out
+
+
+def _slots(w_blk):
+    """(rows <= 128, 64) fp32 -> [hi slot, lo slot]."""
+    hi, lo = split_hi_lo(w_blk.float())
+    return [_slot(hi), _slot(lo)]
+
+
+def _layer_slots(w):
+    """Slots of one layer in (row-chunk, k-block) order."""
+    N, K = w.shape
+    rows = min(N, 128)
+    out = []
+    for r in range(0, N, rows):
+        for k in range(0, K, 64):
+            out += _slots(w[r:r + rows, k:k + 64])
+    return out
+
+
+class SplitChainPack:
+    def __init__(self, fw, names, pair):
+        first, mids, last = names[0], names[1:-1], names[-1]
+        w0, b0 = fw[first]
+        self.c_in = w0.shape[1]
+        self.t = {"w0_w": _pad8(w0), "w0_b": b0.contiguous(),
+                  "mid_b": torch.cat([fw[m][1] for m in mids]).contiguous(), "last_b": fw[last][1].contiguous()}
+        slots = []
+        for m in mids + [last]:
+            slots += _layer_slots(fw[m][0])
+        self.t["wstream"] = torch.cat(slots).contiguous()
+        s = SplitChainWeightsStruct()
+        s.c_in, s.w0, s.n_mid = self.c_in, w0.shape[0], len(mids)
+        for i in range(3):
+            s.mid[i] = fw[mids[i]][0].shape[0] if i < len(mids) else 0
+        s.last, s.n_blocks, s.pair = fw[last][0].shape[0], len(slots), int(pair)
+        for k in ("w0_w", "w0_b", "mid_b", "last_b", "wstream"):
+            setattr(s, k, self.t[k].data_ptr())
+        self.struct = s
+        self.last = s.last
+
+
+class SplitSegPack:
+    def __init__(self, fw, c_in):
+        self.pass1 = SplitChainPack(fw, ["conv1", "conv2", "conv3", "conv4", "conv5"], pair=True)
+        wd1, wd2, wd3, wd4 = (fw[k][0] for k in ("dconv1", "dconv2", "dconv3", "dconv4"))
+
+        def d1(c):                     # dconv1 output channels c*128..+128 on the 64 per-point input channels
+            return _slots(wd1[c * 128:(c + 1) * 128, 0:64])
+
+        def p(c):                      # dconv2 partial sum over input channels c*128..+128: (row half, k block)
+            out = []
+            for nc in range(2):
+                for kb in range(2):
+                    out += _slots(wd2[nc * 128:(nc + 1) * 128, c * 128 + kb * 64:c * 128 + (kb + 1) * 64])
+            return out
+
+        slots = _slots(fw["conv2"][0]) + d1(0) + d1(1) + d1(2) + p(0) + d1(3) + p(1) + p(2) + p(3)
+        for kb in range(4):
+            slots += _slots(wd3[:, kb * 64:(kb + 1) * 64])
+        for kb in range(2):
+            slots += _slots(wd4[:, kb * 64:(kb + 1) * 64])
+        assert len(slots) == 54
+        self.t = {"w1_w": _pad8(fw["conv1"][0]), "w1_b": fw["conv1"][1].contiguous(), "b2": fw["conv2"][1].contiguous(),
+                  "bd2": fw["dconv2"][1].contiguous(), "bd3": fw["dconv3"][1].contiguous(),
+                  "bd4": fw["dconv4"][1].contiguous(), "w5": fw["dconv5"][0].contiguous(),
+                  "b5": fw["dconv5"][1].contiguous(), "wstream": torch.cat(slots).contiguous()}
+        s = SplitTailWeightsStruct()
+        s.c_in = c_in
+        for k, v in self.t.items():
+            setattr(s, k, v.data_ptr())
+        self.struct = s
+        self.w_glob = wd1[:, 64:]          # the 1024-wide half of dconv1 acts on the per-object global feature: fp32
+        self.b_d1 = fw["dconv1"][1]
+
+
+def pack_seg(fw, c_in):
+    return SplitSegPack(fw, c_in)
+
+
+def pack_trunk(fw):
+    return SplitChainPack(fw, ["conv1", "conv2", "conv3", "conv4"], pair=False)
+
+
+def chain_maxpool(pack, x, name="split_chain_kernel"):
+    """x (bs,C,n) any strides -> (bs,last) fp32 = relu(max over points of the chain)."""
+    ops._need_cuda(x)
+    bs, C, n = x.shape
+    assert C == pack.c_in, (C, pack.c_in)
+    out = torch.zeros((bs, pack.last), device=x.device, dtype=torch.float32)
+    sb, sc, sp = x.stride()
+    check_abort("chain_maxpool_bf16x3 launch", x.device)
+    with _timed("%s[last=%d]" % (name, pack.last)):
+        _lib.check(_lib.lib().al3d_chain_maxpool_bf16x3(ctypes.byref(pack.struct), x.data_ptr(), sb, sc, sp, bs, n,
+                                                        out.data_ptr(), ops._stream()), "chain_maxpool_bf16x3")
+    return out
+
+
+def seg_forward(pack, fw, pts):
+    """-> logits (bs,n,2) f32, mask (bs,n) bool."""
+    bs, C, n = pts.shape
+    g = chain_maxpool(pack.pass1, pts)
+    gbias = ops.linear(g, pack.w_glob, pack.b_d1, act=ops.ACT_NONE, K=1024)
+    logits = torch.empty((bs, n, 2), device=pts.device, dtype=torch.float32)
+    mask = torch.empty((bs, n), device=pts.device, dtype=torch.bool)
+    sb, sc, sp = pts.stride()
+    check_abort("seg_pass2_bf16x3 launch", pts.device)
+    with _timed("split_tail_kernel"):
+        _lib.check(_lib.lib().al3d_seg_pass2_bf16x3(ctypes.byref(pack.struct), pts.data_ptr(), sb, sc, sp, bs, n,
+                                                    gbias.data_ptr(), logits.data_ptr(), mask.data_ptr(), ops._stream()),
+                   "seg_pass2_bf16x3")
+    return logits, mask
+
+
+def trunk_maxpool(pack, fw, x):
+    return chain_maxpool(pack, x)

@@ -74,4 +74,7 @@ class StaticAutoLabeler:
             ev.record(main)
             free_ev[ci & 1] = ev
         main.synchronize()
+        if getattr(self.model, "precision", "fp32") != "fp32":
+            from . import engine_bf16
+            engine_bf16.check_abort("StaticAutoLabeler.label_host", dev)
         return out_host

@@ -7,7 +7,7 @@ reference's static_eval.py / static_train.py can import them unchanged (INTEGRAT
 forward runs entirely in libal3d.so (sm_100a CUDA); the nn.Conv1d / nn.BatchNorm1d / nn.Linear
 children only hold parameters (identical default initialisation and key names) and are never called.
 
-Extra, non-reference attributes: ``precision`` ("fp32" | "bf16") and ``gather_policy``
+Extra, non-reference attributes: ``precision`` ("fp32" SIMT | "bf16x3" split-precision tensor cores | "bf16" fast tensor cores) and ``gather_policy``
 ("strided" device rule | "numpy_legacy" reference RNG replay).
 """
 import numpy as np
@@ -72,21 +72,32 @@ class _AutoLabelBase(nn.Module):
         if pts.dtype != torch.float32:
             raise TypeError("pts must be float32")
 
+    def _tc_engine(self):
+        """Tensor-core engines: "bf16" (fast, csrc/chain_bf16.cu) and "bf16x3" (split precision, parity-grade,
+        csrc/chain_split.cu)."""
+        if self.precision == "bf16":
+            from . import engine_bf16
+            return engine_bf16
+        if self.precision == "bf16x3":
+            from . import engine_split
+            return engine_split
+        raise ValueError("precision must be 'fp32', 'bf16x3' or 'bf16', got %r" % (self.precision,))
+
     def _seg(self, pts):
         fw = self._packs.get("seg_f32", self.ins_seg, lambda: engine.fold_block(self.ins_seg, self.ins_seg._table))
         if self.precision == "fp32":
             return engine.seg_forward_fp32(fw, pts), None
-        from . import engine_bf16
-        pk = self._packs.get("seg_bf16", self.ins_seg, lambda: engine_bf16.pack_seg(fw, self.ins_seg.n_channel))
-        return engine_bf16.seg_forward(pk, fw, pts)
+        eng = self._tc_engine()
+        pk = self._packs.get("seg_" + self.precision, self.ins_seg, lambda: eng.pack_seg(fw, self.ins_seg.n_channel))
+        return eng.seg_forward(pk, fw, pts)
 
     def _trunk(self, key, module, x):
         fw = self._packs.get(key + "_f32", module, lambda: engine.fold_block(module, module._table))
         if self.precision == "fp32":
             return fw, engine.trunk_maxpool_fp32(fw, x)
-        from . import engine_bf16
-        pk = self._packs.get(key + "_bf16", module, lambda: engine_bf16.pack_trunk(fw))
-        return fw, engine_bf16.trunk_maxpool(pk, fw, x)
+        eng = self._tc_engine()
+        pk = self._packs.get(key + "_" + self.precision, module, lambda: eng.pack_trunk(fw))
+        return fw, eng.trunk_maxpool(pk, fw, x)
 
 
 class StaticModelOneBoxEst(_AutoLabelBase):

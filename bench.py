@@ -178,7 +178,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tracks", type=int, default=8192, help="tracks per GPU")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -316,6 +316,8 @@ def main():
         # factored count of SURVEY.md 8d; the conv1-2 recompute is not credited.
         macs_pt = {"seg_pass2_kernel": 64 * 512 + 512 * 256 + 256 * 128 + 128 * 128 + 128 * 2,
                    "seg_pass1_kernel": 3 * 64 + 64 * 64 + 64 * 64 + 64 * 128 + 128 * 1024}
+        macs_pt["split_tail_kernel"] = macs_pt["seg_pass2_kernel"]
+        macs_pt["split_chain_kernel[last=1024]"] = macs_pt["seg_pass1_kernel"]
         dom = max((k for k in kernel_ms if k in macs_pt), key=lambda k: kernel_ms[k], default=None)
         roofline = None
         if dom is not None:
@@ -335,7 +337,7 @@ def main():
         line = {
             "metric": "auto-labeled objects/sec", "value": value, "unit": "objects/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (split bf16 hi+lo operands, fp32 accumulate)", "fp32": "f32"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "static one-box Frustum-PointNet forward + box decode, %d tracks x %d pts per GPU"
                                    " (BASELINE.json configs[2])" % (T, N_POINTS),

@@ -8,7 +8,9 @@
  *   - all pointers are DEVICE pointers unless the name ends in _host.  The library allocates
  *     nothing: inputs, outputs, packed weights and scratch are owned by the caller (PyTorch).
  *   - everything is stream-ordered on `stream` (a cudaStream_t passed as void*); there are no
- *     hidden synchronisations and no mutable global state besides the per-thread error string.
+ *     hidden synchronisations.  Process state is limited to: the per-thread error string, one 64-byte
+ *     pinned watchdog status block per device (al3d_tc_abort_code) and the two diagnostic switches
+ *     al3d_tc_configure / al3d_set_debug_buffer.
  *   - tensors are dense row-major unless strides are passed (in ELEMENTS).
  *
  * Each entry point names the reference code (jacky121298/3DAL_PyTorch, file:line) it replaces.
@@ -25,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AL3D_ABI_VERSION 2
+#define AL3D_ABI_VERSION 3
 
 /* activation flags for al3d_linear_f32 */
 #define AL3D_ACT_NONE 0
@@ -210,7 +212,7 @@ typedef struct al3d_pass1_weights {
     const float *b2, *b3, *b4, *b5;    /* conv2-5 biases (64),(64),(128),(1024)                         */
     const void  *wfront;               /* conv2, conv3, conv4 packed bf16, one 16 KB slot each          */
     const void  *w5stream;             /* conv5: 16 packed blocks of 128 channels x 64 K, (chunk, k-block) order */
-    const float *host_consts;          /* HOST memory, 832 floats: w1_w (512) | w1_b (64) | b2 (64) | b3 (64) | b4 (128) --
+    const float *consts_host;          /* HOST memory, 832 floats: w1_w (512) | w1_b (64) | b2 (64) | b3 (64) | b4 (128) --
                                           copied into the kernel parameter block (constant bank operands)          */
 } al3d_pass1_weights;
 
@@ -237,6 +239,45 @@ typedef struct al3d_pass2_weights {
 int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
                         int bs, int n, const float *gbias, float *logits, uint8_t *mask, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Split-precision ("bf16x3") tensor-core mode: the parity-grade variant of the three kernels above.  Every fp32
+ * activation and weight is carried as hi = bf16(x), lo = bf16(x - hi) and every product is evaluated as
+ * a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (three tcgen05.mma per K step, fp32 accumulation): 16 significant bits per
+ * operand, logits within ~5e-5 of the fp32 reference (bf16: ~2e-2, fp16 / tf32 operands: ~3e-3).
+ * Weights: 16 KB slots, KP layout, a hi slot followed by a lo slot per (<=128 rows x 64 K) block, in consumption order.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct al3d_split_chain_weights {
+    int32_t c_in;            /* input channels (1..8)                                                          */
+    int32_t w0;              /* width of the first layer (CUDA cores): 64 or 128                                */
+    int32_t n_mid;           /* number of chained tensor-core layers: 2 or 3                                    */
+    int32_t mid[3];          /* their widths (64 / 128 / 256)                                                   */
+    int32_t last;            /* width of the max-pooled last layer (multiple of 128, <= 1024)                   */
+    int32_t n_blocks;        /* number of 16 KB slots in wstream                                                */
+    int32_t pair;            /* 1: the last layer runs on pairs of 128-point tiles (its input must fit 128 KB)  */
+    int32_t reserved;
+    const float *w0_w;       /* (8, w0) fp32, transposed, zero rows for c >= c_in                               */
+    const float *w0_b;       /* (w0)                                                                            */
+    const float *mid_b;      /* concatenated fp32 biases of the mid layers                                      */
+    const float *last_b;     /* (last)                                                                          */
+    const void  *wstream;    /* mid layers in (layer, row chunk, k block) order, then the last layer (chunk, k block) */
+} al3d_split_chain_weights;
+/* Same contract as al3d_chain_maxpool_bf16 (ins_seg conv1-5 + max with pair = 1; the three head / embedding trunks). */
+int al3d_chain_maxpool_bf16x3(const al3d_split_chain_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
+                              int bs, int n, float *out, void *stream);
+
+typedef struct al3d_split_tail_weights {
+    int32_t c_in;
+    int32_t reserved;
+    const float *w1_w, *w1_b;      /* ins_seg.conv1 folded fp32: (8,64) transposed + padded, (64)  */
+    const float *b2;               /* conv2 bias (64)                                               */
+    const float *bd2, *bd3, *bd4;  /* dconv2-4 biases (256),(128),(128)                             */
+    const float *w5, *b5;          /* dconv5 fp32 (2,128), (2)                                      */
+    const void  *wstream;          /* 54 slots: conv2 | d1(0) d1(1) d1(2) p(0) d1(3) p(1) p(2) p(3) | dconv3 | dconv4 (csrc/chain_split.cu) */
+} al3d_split_tail_weights;
+/* Same contract as al3d_seg_pass2_bf16. */
+int al3d_seg_pass2_bf16x3(const al3d_split_tail_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,
+                          int bs, int n, const float *gbias, float *logits, uint8_t *mask, void *stream);
+
 /* D(128,N) fp32 = A(128,K) . B(N,K)^T from KP-packed bf16 operands with one tcgen05.mma chain:
  * unit test of the descriptor / layout conventions. */
 int al3d_umma_selftest(const void *a_kp, const void *b_kp, int N, int K, float *d_out, int swap_lbo_sbo, void *stream);
@@ -259,14 +300,24 @@ int al3d_umma_selftest_pair_ss(const void *a_kp_halves, const void *b_kp_halves,
 int al3d_mma_microbench(int N, int n_mma, int commit_every, int mode, int n_ctas, int background, const void *src_1mib,
                         long long *out, void *stream);
 
-/* Reads (and clears) the device-side watchdog code: non-zero means a tensor-core kernel gave up on
- * an mbarrier wait (protocol bug) and its outputs are invalid.  Synchronises the device. */
+/* Watchdog of the tensor-core kernels.  Every mbarrier wait in them is bounded; a wait that gives up (a protocol
+ * bug) records a code in the status word of the device the kernel runs on and traps, so the launch fails with a
+ * CUDA error at the caller's next synchronisation instead of returning invalid outputs.  The status word lives in
+ * pinned host memory mapped into the device (one block per device, allocated at the first tensor-core launch):
+ * al3d_tc_abort_code reads and clears the CURRENT device's word with a plain host load -- no CUDA call, no
+ * synchronisation; it is meaningful for launches the caller has already synchronised with.
+ * al3d_tc_status_word_host returns the word's host address for callers that poll it themselves. */
 int al3d_tc_abort_code(int *code_host);
+int al3d_tc_status_word_host(const void **word_host);
+/* Diagnostics: trap_on_timeout = 0 records the code without trapping; stress_ns > 0 makes every role of the
+ * tensor-core kernels sleep a pseudo-random time (< stress_ns) before its barrier waits, to shake out protocol
+ * races (tests/test_gpu_stress.py).  Defaults: 1, 0 (environment AL3D_TC_TRAP / AL3D_TC_STRESS_NS). */
+int al3d_tc_configure(int trap_on_timeout, int stress_ns);
 
 /* Development aid: when set to a device buffer of 2*3*4*64 int64, CTA 0 of al3d_seg_pass2_bf16 (first half)
  * and of al3d_seg_pass1_bf16 (second half) record a clock64 timeline of their first four tiles / tile pairs
  * (role-major: MMA thread, epilogue thread, producer).  Pass
- * NULL to switch it off (the default).  This pointer is the only mutable global besides the error text. */
+ * NULL to switch it off (the default). */
 int al3d_set_debug_buffer(void *dev_ptr);
 
 #ifdef __cplusplus

@@ -111,16 +111,19 @@ def parse_heads(box_pred):
     return center, h_scores, h_res_n, h_res, s_scores, s_res_n, s_res
 
 
-def _mask_and_gather(pts, logits, n_obj_pts, policy):
-    mask = gather.mask_from_logits(logits)
+def _mask_and_gather(pts, logits, n_obj_pts, policy, mask_override=None):
+    """mask_override: evaluate the stages AFTER the mask on a given (bs,n) bool mask instead of the oracle's own --
+    the parity tests use it to check the box heads of a reduced-precision run whose mask differs from the fp32
+    mask in a few boundary points (the gather, and with it every head, depends on the exact foreground set)."""
+    mask = gather.mask_from_logits(logits) if mask_override is None else torch.as_tensor(mask_override).bool()
     obj, idx = gather.gather_object_pts(pts.cpu().numpy(), mask.cpu().numpy(), n_obj_pts, policy)
     return torch.from_numpy(obj).to(pts.device), mask, idx
 
 
 @torch.no_grad()
-def static_one_forward(sd, pts, init_box, bbox_gt=None, policy="numpy_legacy"):
+def static_one_forward(sd, pts, init_box, bbox_gt=None, policy="numpy_legacy", mask_override=None):
     logits, _ = seg_forward(sd, pts)
-    obj, mask, idx = _mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, policy)
+    obj, mask, idx = _mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, policy, mask_override)
     pred = static_est_forward(sd, "box_est", obj)
     c, hs, hrn, hr, ss, srn, sr = parse_heads(pred)
     return {
@@ -159,9 +162,9 @@ def _rotz(angle):
 
 
 @torch.no_grad()
-def static_two_forward(sd, pts, init_box, bbox_gt, policy="numpy_legacy"):
+def static_two_forward(sd, pts, init_box, bbox_gt, policy="numpy_legacy", mask_override=None):
     logits, _ = seg_forward(sd, pts)
-    obj, mask, idx = _mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, policy)
+    obj, mask, idx = _mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, policy, mask_override)
     pred1 = static_est_forward(sd, "box_est_one", obj)
     c1, hs1, hrn1, hr1, ss1, srn1, sr1 = parse_heads(pred1)
     c1 = c1 + init_box[:, :3]
@@ -200,9 +203,9 @@ def static_two_forward(sd, pts, init_box, bbox_gt, policy="numpy_legacy"):
 
 
 @torch.no_grad()
-def dynamic_forward(sd, pts, box, bbox_gt=None, policy="numpy_legacy"):
+def dynamic_forward(sd, pts, box, bbox_gt=None, policy="numpy_legacy", mask_override=None):
     logits, _ = seg_forward(sd, pts)
-    obj, mask, idx = _mask_and_gather(pts[:, :4, :], logits, NUM_FRAME * NUM_OBJECT_POINT, policy)
+    obj, mask, idx = _mask_and_gather(pts[:, :4, :], logits, NUM_FRAME * NUM_OBJECT_POINT, policy, mask_override)
     pe = embedding_forward(sd, "point_emb", obj)
     be = embedding_forward(sd, "box_emb", box)
     pred = dynamic_est_forward(sd, "box_est", torch.cat([pe, be], dim=1))

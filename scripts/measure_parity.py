@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Per-tensor error of every precision mode against the fp32 oracle at the BASELINE.json config sizes
+(config 1: static 32 x 4096, config 2: dynamic 64 x (5 x 1024 pts + 101 boxes)), with the mask flip rate and the
+margin of the flipped points.  Writes one JSON object per (config, model, precision) line.
+
+    python scripts/measure_parity.py [--out profiles/r2_parity_per_tensor.jsonl] [--precisions fp32,bf16,...]
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import __graft_entry__ as ge
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="")
+    ap.add_argument("--precisions", default="fp32,bf16x3,bf16")
+    ap.add_argument("--fg", type=float, default=0.3)
+    args = ap.parse_args()
+    ge.build()
+    from oracle import models
+    synth = importlib.import_module("3dal_pytorch_b200.synth")
+    sm = importlib.import_module("3dal_pytorch_b200.static_model")
+    dm = importlib.import_module("3dal_pytorch_b200.dynamic_model")
+    dev = torch.device("cuda:0")
+    lines = []
+    cases = [("config1 static 32x4096", "static_one", sm.StaticModelOneBoxEst, 32),
+             ("config1 static 32x4096", "static_two", sm.StaticModelTwoBoxEst, 32),
+             ("config2 dynamic 64x(5x1024+101)", "dynamic", dm.DynamicModel, 64)]
+    for cfg, kind, cls, bs in cases:
+        sd = synth.random_state_dict(kind, seed=synth.REFERENCE_SEED)
+        if kind == "dynamic":
+            d = synth.dynamic_tracks(bs, seed=7)
+            pts = torch.from_numpy(d["pts_pm"]).transpose(2, 1)
+            aux = torch.from_numpy(d["box_sm"]).transpose(2, 1)
+        else:
+            d = synth.static_tracks(bs, n=4096, seed=7)
+            pts = torch.from_numpy(d["pts_pm"]).transpose(2, 1)
+            aux = torch.from_numpy(d["init_box"])
+        gt = torch.from_numpy(d["bbox_gt"])
+        lg, _ = models.seg_forward(sd, pts)
+        synth.calibrate_seg_margin(sd, lg, args.fg)
+        fwd = {"static_one": models.static_one_forward, "static_two": models.static_two_forward,
+               "dynamic": models.dynamic_forward}[kind]
+        if kind == "static_one":
+            ref = fwd(sd, pts, aux, policy="strided")
+        else:
+            ref = fwd(sd, pts, aux, gt, policy="strided")
+        margin = (ref["logits"][..., 1] - ref["logits"][..., 0])
+        model = cls().to(dev).eval()
+        model.load_state_dict(sd)
+        for prec in args.precisions.split(","):
+            model.precision = prec
+            out = model(pts.to(dev), aux.to(dev), gt.to(dev))
+            torch.cuda.synchronize()
+            flips = (out["mask"].cpu() != ref["mask"])
+            rec = {"config": cfg, "model": kind, "precision": prec, "tracks": bs,
+                   "fg_fraction": float(ref["mask"].float().mean()),
+                   "mask_flips": int(flips.sum()), "mask_points": int(flips.numel()),
+                   "max_abs_margin_of_flipped": float(margin[flips].abs().max()) if flips.any() else 0.0,
+                   "margin_std": float(margin.std()), "max_abs_logit": float(ref["logits"].abs().max()),
+                   "objects_with_flips": int(flips.any(dim=1).sum()), "rel_err": {}, "int_mismatch": {}}
+            # everything after the mask depends on the exact foreground set: compare with the oracle evaluated on the
+            # kernel's own mask (== the plain oracle output when no bit flipped)
+            same = ~flips.any(dim=1)
+            ref_h = ref
+            if flips.any():
+                if kind == "static_one":
+                    ref_h = fwd(sd, pts, aux, policy="strided", mask_override=out["mask"].cpu())
+                else:
+                    ref_h = fwd(sd, pts, aux, gt, policy="strided", mask_override=out["mask"].cpu())
+            for k, v in ref_h.items():
+                if k == "mask" or k not in out:
+                    continue
+                g = out[k].cpu()
+                v = torch.as_tensor(v)
+                if v.dtype in (torch.int64, torch.int32):
+                    rec["int_mismatch"][k] = int((g != v).sum())
+                elif k == "logits":
+                    rec["rel_err"][k] = rel(g, torch.as_tensor(ref["logits"]))
+                else:
+                    rec["rel_err"][k] = rel(g, v)
+            lines.append(rec)
+            print(json.dumps(rec))
+    if args.out:
+        with open(os.path.join(ROOT, args.out), "w") as f:
+            for r in lines:
+                f.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -50,7 +50,17 @@ class patched_numpy_rng:
         np.random.choice, np.random.shuffle = self.c, self.s
 
 
-def model_case(name, kind, bs, n, wseed, dseed, fg_fraction, calibrate=True, rng_seed=424242):
+def arrays_checksum(*arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def model_case(name, kind, bs, n, wseed, dseed, fg_fraction, calibrate=True, rng_seed=424242, compact=False):
+    """compact=True (the BASELINE.json config sizes): the inputs are not stored but regenerated from `dseed` by
+    3dal_pytorch_b200.synth (their sha256 is), logits / mask are stored once (they do not depend on the gather
+    policy) and the mask as packed bits."""
     sm, dm, _, _ = refshim.load()
     sd = synth.random_state_dict(kind, seed=wseed, randomize_bn=calibrate)
     if kind == "dynamic":
@@ -72,7 +82,12 @@ def model_case(name, kind, bs, n, wseed, dseed, fg_fraction, calibrate=True, rng
         q, std = synth.calibrate_seg_margin(sd, logits, fg_fraction)
     ref.load_state_dict(sd)
     rec = {"kind": kind, "wseed": wseed, "calibrated": int(calibrate), "calib_q": q, "calib_std": std,
-           "sd_sha256": sd_checksum(sd), "pts_pm": pts_pm, "aux": aux, "bbox_gt": tr["bbox_gt"], "rng_seed": rng_seed}
+           "sd_sha256": sd_checksum(sd), "rng_seed": rng_seed}
+    if compact:
+        rec.update({"compact": 1, "bs": bs, "n": n, "dseed": dseed,
+                    "inputs_sha256": arrays_checksum(pts_pm, aux, tr["bbox_gt"])})
+    else:
+        rec.update({"pts_pm": pts_pm, "aux": aux, "bbox_gt": tr["bbox_gt"]})
     for policy in ("numpy_legacy", "strided"):
         with torch.no_grad():
             if policy == "numpy_legacy":
@@ -82,8 +97,16 @@ def model_case(name, kind, bs, n, wseed, dseed, fg_fraction, calibrate=True, rng
                 with patched_numpy_rng():
                     out = ref(pts, aux_t, gt)
         for k, v in out.items():
-            rec["%s/%s" % (policy, k)] = v.detach().cpu().numpy()
-    counts = rec["strided/mask"].sum(1)
+            v = v.detach().cpu().numpy()
+            if compact and k in ("logits", "mask"):
+                key = "common/" + k
+                v = np.packbits(v, axis=1) if k == "mask" else v
+                if key in rec:
+                    assert np.array_equal(rec[key], v), "logits / mask depend on the gather policy?"
+                rec[key] = v
+            else:
+                rec["%s/%s" % (policy, k)] = v
+    counts = (np.unpackbits(rec["common/mask"], axis=1)[:, :n] if compact else rec["strided/mask"]).sum(1)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
     print(name, "fg counts", counts.tolist(), "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
 
@@ -136,5 +159,9 @@ if __name__ == "__main__":
     model_case("static_two", "static_two", bs=6, n=2048, wseed=102, dseed=2, fg_fraction=0.25)
     model_case("dynamic", "dynamic", bs=3, n=5120, wseed=103, dseed=3, fg_fraction=0.5)
     model_case("static_one_default_init", "static_one", bs=2, n=512, wseed=104, dseed=4, fg_fraction=0.0, calibrate=False)
+    # BASELINE.json config 1 (static 32 x 4096) and config 2 (dynamic 64 x (5 x 1024 points + 101 boxes))
+    model_case("static_one_cfg1", "static_one", bs=32, n=4096, wseed=201, dseed=21, fg_fraction=0.3, compact=True)
+    model_case("static_two_cfg1", "static_two", bs=32, n=4096, wseed=202, dseed=22, fg_fraction=0.3, compact=True)
+    model_case("dynamic_cfg2", "dynamic", bs=64, n=5120, wseed=203, dseed=23, fg_fraction=0.4, compact=True)
     crop_case()
     codec_case()

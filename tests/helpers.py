@@ -33,6 +33,25 @@ def load_model_case(name):
         sd["ins_seg.dconv5.bias"].mul_(1.0 / std)
         sd["ins_seg.dconv5.bias"][1] -= q / std
     assert sd_checksum(sd) == str(z["sd_sha256"]), "weight generator drifted from the golden fixture"
+    if "compact" in z:
+        # BASELINE-size fixtures: inputs regenerated from the seed (checked against the stored hash); logits and the
+        # bit-packed mask are stored once and shown under both policies
+        bs, n = int(z["bs"]), int(z["n"])
+        if kind == "dynamic":
+            tr = synth.dynamic_tracks(bs, npoints=n // 5, seed=int(z["dseed"]))
+            z["pts_pm"], z["aux"] = tr["pts_pm"], tr["box_sm"]
+        else:
+            tr = synth.static_tracks(bs, n=n, seed=int(z["dseed"]))
+            z["pts_pm"], z["aux"] = tr["pts_pm"], tr["init_box"]
+        z["bbox_gt"] = tr["bbox_gt"]
+        h = hashlib.sha256()
+        for a in (z["pts_pm"], z["aux"], z["bbox_gt"]):
+            h.update(np.ascontiguousarray(a).tobytes())
+        assert h.hexdigest() == str(z["inputs_sha256"]), "input generator drifted from the golden fixture"
+        mask = np.unpackbits(z.pop("common/mask"), axis=1)[:, :n].astype(bool)
+        logits = z.pop("common/logits")
+        for policy in ("numpy_legacy", "strided"):
+            z[policy + "/mask"], z[policy + "/logits"] = mask, logits
     pts = torch.from_numpy(z["pts_pm"]).transpose(2, 1)
     aux = torch.from_numpy(z["aux"])
     if kind == "dynamic":

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     l = ctypes.CDLL(_lib.LIB_PATH)
     for name in _declared():
         assert hasattr(l, name), name
-    assert _lib.lib().al3d_abi_version() == 2
+    assert _lib.lib().al3d_abi_version() == 3
     assert _lib.lib().al3d_last_error() is not None
 
 

@@ -18,38 +18,61 @@ dm = importlib.import_module("3dal_pytorch_b200.dynamic_model")
 
 DEV = "cuda:0"
 MODEL = {"static_one": sm.StaticModelOneBoxEst, "static_two": sm.StaticModelTwoBoxEst, "dynamic": dm.DynamicModel}
-# float tolerance of BASELINE.json's north_star: 1e-3 relative (per tensor, to max|ref|).  The fp32
-# path is held to 1e-4; bf16 tensor-core mode states its own tolerance (bf16 has an 8-bit mantissa).
-TOL = {"fp32": 1e-4, "bf16": 3e-2}
+# Float tolerance of BASELINE.json's north_star: 1e-3 relative (per tensor, to max|ref|).  The fp32 SIMT mode is held
+# to 1e-4 and the split-precision tensor-core mode (bf16x3) to the 1e-3 bar itself (measured ~5e-5,
+# profiles/r2_parity_per_tensor.jsonl); plain bf16 (8-bit mantissa) states its own, looser tolerance.
+TOL = {"fp32": 1e-4, "bf16x3": 1e-3, "bf16": 3e-2}
+# A mask bit is `l0 < l1` of OUR logits; against the fp32 reference it may differ only where the reference margin
+# |l1 - l0| is inside the logit tolerance (2 * TOL * max|logit|: both logits can move).
+PRECISIONS = ["fp32", "bf16x3", "bf16"]
 
 
-def _check_outputs(out, z, policy, prec, ref_margin):
+def _check_outputs(out, z, policy, prec, sd, pts, aux, gt):
+    kind = str(z["kind"])
     keys = [k.split("/", 1)[1] for k in z if k.startswith(policy + "/")]
     assert set(keys) == set(out), (sorted(keys), sorted(out))
-    ref_mask = z[policy + "/mask"]
+    ref_logits, ref_mask = z[policy + "/logits"], z[policy + "/mask"]
     got_mask = out["mask"].cpu().numpy()
+    assert got_mask.dtype == ref_mask.dtype and got_mask.shape == ref_mask.shape
+    assert rel_err(out["logits"].cpu().numpy(), ref_logits) < TOL[prec], ("logits", rel_err(out["logits"].cpu().numpy(), ref_logits))
+    # the mask is exactly the comparison of the logits the kernel wrote ...
+    lg = out["logits"].cpu().numpy()
+    assert np.array_equal(got_mask, lg[..., 0] < lg[..., 1])
+    # ... and differs from the reference mask only inside the guard band
     flips = got_mask != ref_mask
-    # a flipped mask bit is only legal inside the guard band of the float tolerance
-    band = TOL[prec] * float(np.abs(z[policy + "/logits"]).max()) * 2
-    assert np.all(np.abs(ref_margin[flips]) <= band), (int(flips.sum()), float(np.abs(ref_margin[flips]).max()), band)
-    same_mask = not flips.any()
+    margin = ref_logits[..., 1] - ref_logits[..., 0]
+    band = TOL[prec] * float(np.abs(ref_logits).max()) * 2
+    assert np.all(np.abs(margin[flips]) <= band), (int(flips.sum()), float(np.abs(margin[flips]).max()), band)
+    # Everything after the mask (gather, box heads, decode, labels) is a function of the exact foreground set, so it
+    # is compared with the reference algorithm evaluated ON THE KERNEL'S MASK (the oracle, bit-identical to the
+    # reference on the reference's own mask: tests/test_oracle_golden.py); when no bit flipped that is the golden
+    # fixture itself.
+    if flips.any():
+        if policy == "numpy_legacy":
+            np.random.seed(int(z["rng_seed"]))
+        ref = models.FORWARDS[kind](sd, pts, aux, gt, policy=policy, mask_override=torch.from_numpy(got_mask))
+        ref = {k: torch.as_tensor(v).cpu().numpy() for k, v in ref.items()}
+    else:
+        ref = {k: z[policy + "/" + k] for k in keys}
     for k in keys:
-        ref = z[policy + "/" + k]
-        got = out[k].cpu().numpy()
-        assert got.shape == ref.shape and got.dtype == ref.dtype, (k, got.shape, ref.shape, got.dtype, ref.dtype)
-        if k == "mask":
+        if k in ("mask", "logits"):
             continue
-        if np.issubdtype(ref.dtype, np.integer):
-            if same_mask and prec == "fp32":
-                assert np.array_equal(got, ref), k
-        elif k == "logits" or same_mask:
-            assert rel_err(got, ref) < TOL[prec], (k, rel_err(got, ref))
+        r, g = ref[k], out[k].cpu().numpy()
+        assert g.shape == r.shape and g.dtype == r.dtype, (k, g.shape, r.shape, g.dtype, r.dtype)
+        if np.issubdtype(r.dtype, np.integer):
+            if prec != "bf16":
+                assert np.array_equal(g, r), k                    # class labels: exact
+            else:
+                assert np.mean(g != r) <= 0.1, k                 # a label may move when the heading sits on a bin edge
+        else:
+            assert rel_err(g, r) < TOL[prec], (k, rel_err(g, r))
     return int(flips.sum())
 
 
-@pytest.mark.parametrize("name", ["static_one", "static_two", "dynamic", "static_one_default_init"])
+@pytest.mark.parametrize("name", ["static_one", "static_two", "dynamic", "static_one_default_init",
+                                  "static_one_cfg1", "static_two_cfg1", "dynamic_cfg2"])
 @pytest.mark.parametrize("policy", ["strided", "numpy_legacy"])
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", PRECISIONS)
 def test_forward_matches_reference_golden(name, policy, prec):
     z, sd, pts, aux, gt = load_model_case(name)
     model = MODEL[str(z["kind"])]().to(DEV).eval()
@@ -60,11 +83,10 @@ def test_forward_matches_reference_golden(name, policy, prec):
         np.random.seed(int(z["rng_seed"]))
     out = model(pts.to(DEV), aux.to(DEV), gt.to(DEV))     # pts keeps the strided (bs,C,n) view
     torch.cuda.synchronize()
-    margin = z[policy + "/logits"][..., 1] - z[policy + "/logits"][..., 0]
-    _check_outputs(out, z, policy, prec, margin)
+    _check_outputs(out, z, policy, prec, sd, pts, aux, gt)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", PRECISIONS)
 def test_contiguous_and_strided_inputs_agree_bitwise(prec):
     z, sd, pts, aux, gt = load_model_case("static_one")
     model = sm.StaticModelOneBoxEst().to(DEV).eval()
@@ -76,7 +98,7 @@ def test_contiguous_and_strided_inputs_agree_bitwise(prec):
         assert torch.equal(a[k], b[k]), k
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", PRECISIONS)
 def test_sharding_by_track_is_bitwise_equivalent(prec):
     """Tracks are independent: running two halves (what two ranks do) == running the whole batch."""
     z, sd, pts, aux, gt = load_model_case("static_two")

@@ -1,0 +1,148 @@
+"""Protocol stress tests of the warp-specialised tcgen05 kernels (round-1 VERDICT item 1).
+
+Every role of the kernels sleeps a pseudo-random time before its mbarrier waits (al3d_tc_configure stress_ns), which
+perturbs the relative speed of producer / MMA issuers / epilogue warps far beyond what load imbalance, concurrent
+copies or co-running processes cause.  A barrier that can be lapped (round 1: seg_pass1's single out4_free guarding
+two buffers) deadlocks within a few launches under these delays; the outputs must stay bit-identical to the
+undisturbed run and the watchdog must stay silent."""
+import importlib
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from helpers import ROOT, synth
+
+pytestmark = pytest.mark.gpu
+STRESS_LIB = "libal3d_stress.so"          # the build with the delay-injection hooks (__graft_entry__.build)
+IN_STRESS_PROCESS = os.environ.get("AL3D_LIB") == STRESS_LIB
+in_stress_process = pytest.mark.skipif(not IN_STRESS_PROCESS, reason="runs in the subprocess that loads " + STRESS_LIB)
+
+
+@pytest.mark.skipif(IN_STRESS_PROCESS, reason="this is the subprocess")
+def test_stress_suite_against_the_hooked_library():
+    """The product library has no delay hooks; run this file again in a subprocess that loads libal3d_stress.so."""
+    env = dict(os.environ, AL3D_LIB=STRESS_LIB)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert "5 passed" in r.stdout, r.stdout[-2000:]
+
+DEV = "cuda:0"
+eb = importlib.import_module("3dal_pytorch_b200.engine_bf16")
+sm = importlib.import_module("3dal_pytorch_b200.static_model")
+dm = importlib.import_module("3dal_pytorch_b200.dynamic_model")
+pipeline = importlib.import_module("3dal_pytorch_b200.pipeline")
+
+
+def _static_model(prec):
+    sd = synth.random_state_dict("static_one", seed=5)
+    m = sm.StaticModelOneBoxEst().to(DEV).eval()
+    m.load_state_dict(sd)
+    m.precision = prec
+    return m
+
+
+@in_stress_process
+@pytest.mark.parametrize("stress_ns", [2000, 20000])
+def test_static_forward_is_bitwise_stable_under_injected_delays(stress_ns):
+    m = _static_model("bf16")
+    d = synth.static_tracks_device(600, n=4096, seed=11, device=DEV)
+    pts, box = d["pts_pm"].transpose(2, 1), d["init_box"]
+    eb.configure_watchdog(trap=False, stress_ns=0)
+    ref = m(pts, box, None)
+    torch.cuda.synchronize()
+    try:
+        eb.configure_watchdog(trap=False, stress_ns=stress_ns)
+        for it in range(6):
+            out = m(pts, box, None)
+            torch.cuda.synchronize()
+            eb.check_abort("stress iteration %d" % it)
+            for k in ref:
+                assert torch.equal(out[k], ref[k]), (it, k)
+    finally:
+        eb.configure_watchdog(trap=True, stress_ns=0)
+
+
+@in_stress_process
+def test_dynamic_forward_is_bitwise_stable_under_injected_delays():
+    sd = synth.random_state_dict("dynamic", seed=6)
+    m = dm.DynamicModel().to(DEV).eval()
+    m.load_state_dict(sd)
+    m.precision = "bf16"
+    d = synth.dynamic_tracks(96, seed=3)
+    pts = torch.from_numpy(d["pts_pm"]).to(DEV).transpose(2, 1)
+    box = torch.from_numpy(d["box_sm"]).to(DEV).transpose(2, 1)
+    eb.configure_watchdog(trap=False, stress_ns=0)
+    ref = m(pts, box, None)
+    torch.cuda.synchronize()
+    try:
+        eb.configure_watchdog(trap=False, stress_ns=5000)
+        for it in range(4):
+            out = m(pts, box, None)
+            torch.cuda.synchronize()
+            eb.check_abort("stress iteration %d" % it)
+            for k in ref:
+                assert torch.equal(out[k], ref[k]), (it, k)
+    finally:
+        eb.configure_watchdog(trap=True, stress_ns=0)
+
+
+@in_stress_process
+def test_label_host_soak_with_concurrent_copies():
+    """Many label_host passes (chunked H2D on a copy stream overlapped with the kernels -- the configuration in which
+    the round-1 build hit its watchdog) with mild injected delays; the boxes must not change and no wait may time out."""
+    m = _static_model("bf16")
+    lab = pipeline.StaticAutoLabeler(m, chunk_tracks=256)
+    d = synth.static_tracks(1024, n=4096, seed=12)
+    pts_host = torch.from_numpy(d["pts_pm"]).pin_memory()
+    box_host = torch.from_numpy(d["init_box"]).pin_memory()
+    eb.configure_watchdog(trap=False, stress_ns=0)
+    ref = lab.label_host(pts_host, box_host).clone()
+    try:
+        eb.configure_watchdog(trap=False, stress_ns=1500)
+        for it in range(40):
+            out = lab.label_host(pts_host, box_host)        # checks the watchdog word at its synchronisation point
+            assert torch.equal(out, ref), it
+    finally:
+        eb.configure_watchdog(trap=True, stress_ns=0)
+
+
+@in_stress_process
+def test_stress_detects_the_round1_pass1_protocol():
+    """seg_pass1_kernel with its round-1 release protocol (one out4_free barrier for both out4 buffers, waited by
+    parity) and consistently slow front warps: the front gets lapped, the pipeline deadlocks and the watchdog reports
+    it -- the failure the driver saw in round 1.  The same delays against the per-buffer protocol are harmless (second
+    half of this test).  Slow by design (a watchdog timeout is ~1 s)."""
+    m = _static_model("bf16")
+    d = synth.static_tracks_device(600, n=4096, seed=11, device=DEV)
+    pts, box = d["pts_pm"].transpose(2, 1), d["init_box"]
+    fired = False
+    try:
+        eb.configure_watchdog(trap=False, stress_ns=(1 << 24) | 8000, legacy_pass1_release=True)      # targeted: slow front warps
+        for it in range(6):
+            m(pts, box, None)
+            torch.cuda.synchronize()
+            try:
+                eb.check_abort("legacy protocol iteration %d" % it)
+            except RuntimeError as e:
+                assert "seg_pass1_kernel" in str(e)
+                fired = True
+                break
+    finally:
+        eb.configure_watchdog(trap=True, stress_ns=0)
+    assert fired, "the injected delays did not trip the round-1 protocol"
+    torch.cuda.synchronize()
+    try:
+        eb.configure_watchdog(trap=False, stress_ns=0)
+        ref = m(pts, box, None)
+        eb.configure_watchdog(trap=False, stress_ns=(1 << 24) | 8000)
+        out = m(pts, box, None)
+        torch.cuda.synchronize()
+        eb.check_abort("per-buffer protocol under the same delays")
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+    finally:
+        eb.configure_watchdog(trap=True, stress_ns=0)

@@ -6,13 +6,11 @@ import numpy as np
 import pytest
 import torch
 
-os.environ["AL3D_TC_CHECK"] = "1"
 from helpers import emulate_chain_bf16, emulate_seg_bf16, fold_state_dict, rel_err, spec, synth  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 eb = importlib.import_module("3dal_pytorch_b200.engine_bf16")
-eb.CHECK_ABORT = True
 
 
 @pytest.mark.parametrize("N,K", [(64, 64), (128, 64), (128, 128), (256, 256), (16, 16), (96, 48), (32, 512)])
@@ -103,3 +101,62 @@ def test_seg_bf16_against_numerics_model(C, n, bs):
     # largest logit over these shapes (a wrong tile, bias or weight block shows up as >= 1e-1).
     assert rel_err(logits.cpu(), emu.cpu()) < 1e-2, rel_err(logits.cpu(), emu.cpu())
     assert torch.equal(mask, logits[..., 0] < logits[..., 1])          # mask is exact w.r.t. our logits
+
+
+# ------------------------------------------------------------------------------------------------ split precision
+es = importlib.import_module("3dal_pytorch_b200.engine_split")
+
+
+def _fp32_chain(fw, names, x):
+    h = x.transpose(2, 1).double()
+    for nm in names[:-1]:
+        w, b = fw[nm]
+        h = torch.relu(h @ w.double().t() + b.double())
+    w, b = fw[names[-1]]
+    return torch.relu((h @ w.double().t()).max(dim=1)[0] + b.double())
+
+
+@pytest.mark.parametrize("kind,block,table,C,n,bs", [
+    ("static_one", "box_est", "static_est_layers", 3, 512, 5),
+    ("dynamic", "point_emb", "point_emb_layers", 4, 2560, 3),
+    ("dynamic", "box_emb", "box_emb_layers", 8, 101, 7),
+    ("static_one", "box_est", "static_est_layers", 3, 130, 300),
+])
+def test_split_chain_trunks_match_fp64(kind, block, table, C, n, bs):
+    """bf16x3 carries 16 significant bits per operand: the pooled features match an fp64 evaluation to ~1e-5."""
+    sd = synth.random_state_dict(kind, seed=5)
+    fw = _dev(fold_state_dict(sd, block, getattr(spec, table)()))
+    torch.manual_seed(0)
+    x = torch.randn(bs, n, C, device=DEV).transpose(2, 1)
+    pack = es.pack_trunk(fw)
+    got = es.chain_maxpool(pack, x)
+    ref = _fp32_chain(fw, ["conv1", "conv2", "conv3", "conv4"], x)
+    assert rel_err(got.cpu(), ref.cpu()) < 1e-4, rel_err(got.cpu(), ref.cpu())
+    assert torch.equal(got, es.chain_maxpool(pack, x.contiguous()))
+
+
+@pytest.mark.parametrize("C,n,bs", [(3, 4096, 2), (4, 5120, 2), (3, 1000, 3), (3, 77, 40), (3, 300, 310), (3, 100, 1), (3, 129, 1),
+                                    (3, 384, 600), (3, 2000, 149)])
+def test_split_seg_matches_fp64(C, n, bs):
+    kind = "dynamic" if C == 4 else "static_one"
+    sd = synth.random_state_dict(kind, seed=6)
+    fw = _dev(fold_state_dict(sd, "ins_seg", spec.seg_layers(C)))
+    torch.manual_seed(1)
+    x = (torch.randn(bs, n, C, device=DEV) * torch.tensor([2.0, 2.0, 0.7, 0.2][:C], device=DEV)).transpose(2, 1)
+    pack = es.pack_seg(fw, C)
+    g = es.chain_maxpool(pack.pass1, x)
+    ref_g = _fp32_chain(fw, ["conv1", "conv2", "conv3", "conv4", "conv5"], x)
+    assert rel_err(g.cpu(), ref_g.cpu()) < 1e-4, rel_err(g.cpu(), ref_g.cpu())
+    logits, mask = es.seg_forward(pack, fw, x)
+    # fp64 evaluation of the second half
+    h = x.transpose(2, 1).double()
+    o1 = torch.relu(h @ fw["conv1"][0].double().t() + fw["conv1"][1].double())
+    o2 = torch.relu(o1 @ fw["conv2"][0].double().t() + fw["conv2"][1].double())
+    wd1, bd1 = fw["dconv1"]
+    gb = ref_g @ wd1[:, 64:].double().t() + bd1.double()
+    d = torch.relu(o2 @ wd1[:, :64].double().t() + gb[:, None, :])
+    for nm in ("dconv2", "dconv3", "dconv4"):
+        d = torch.relu(d @ fw[nm][0].double().t() + fw[nm][1].double())
+    ref = d @ fw["dconv5"][0].double().t() + fw["dconv5"][1].double()
+    assert rel_err(logits.cpu(), ref.cpu()) < 3e-4, rel_err(logits.cpu(), ref.cpu())
+    assert torch.equal(mask, logits[..., 0] < logits[..., 1])

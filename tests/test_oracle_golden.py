@@ -9,7 +9,8 @@ import torch
 from helpers import GOLDEN, load_model_case, rel_err
 from oracle import codecs, crop, gather, models
 
-CASES = ["static_one", "static_two", "dynamic", "static_one_default_init"]
+CASES = ["static_one", "static_two", "dynamic", "static_one_default_init",
+         "static_one_cfg1", "static_two_cfg1", "dynamic_cfg2"]        # *_cfgN: the BASELINE.json config sizes
 
 
 @pytest.mark.parametrize("name", CASES)
