@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # libal3d_stress.so, the build with delay-injection hooks, in a subprocess)
 LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ.get("AL3D_LIB", "libal3d.so")))
 
-_vp, _i, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+_vp, _i, _i64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 
 # name -> argtypes ; every function returns int (0 = ok) unless listed in _RESTYPES
 _SIGNATURES = {
@@ -26,6 +26,7 @@ _SIGNATURES = {
     "al3d_parse_heads": [_vp, _i, _vp, _i64] + [_vp] * 8 + [_vp],
     "al3d_decode_boxes": [_vp] * 6 + [_i64, _i, _vp, _vp, _vp],
     "al3d_twostage_retransform": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "al3d_crop_box_setup": [_vp, _vp, _i64, _f, _f, _vp, _vp, _vp],
     "al3d_crop_chunk_points": [],
     "al3d_crop_build_grid": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "al3d_crop_hits": [_vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp],
@@ -34,7 +35,22 @@ _SIGNATURES = {
     "al3d_crop_dense_mask": [_vp, _vp, _i, _vp, _vp],
     "al3d_track_points_prep": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "al3d_boxseq_prep": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "al3d_track_regroup": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "al3d_motion_features": [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp],
+    "al3d_track_labels": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "al3d_box_writeback": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "al3d_loss_forward": [_vp, _vp, _i64] + [_vp] * 10 + [_i, _vp, _i, _vp, _vp],
+    "al3d_train_ws_floats": [_i64, _i],
+    "al3d_wgrad_ws_floats": [_i64, _i, _i],
+    "al3d_bn_train_forward": [_vp, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp],
+    "al3d_bn_train_backward": [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp],
+    "al3d_group_colsum": [_vp, _i64, _i, _i64, _vp, _vp, _vp],
+    "al3d_group_max_forward": [_vp, _i64, _i64, _i, _vp, _vp, _vp],
+    "al3d_group_max_backward": [_vp, _vp, _i64, _i64, _i, _vp, _vp],
+    "al3d_wgrad_f32": [_vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _i64, _i, _vp],
+    "al3d_loss_backward": [_vp, _vp, _i64] + [_vp] * 10 + [_i, _vp, _vp, _vp, _vp],
+    "al3d_seg_correct": [_vp, _vp, _i64, _vp, _vp],
+    "al3d_adam_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp],
     "al3d_chain_maxpool_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
     "al3d_seg_pass1_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp],
     "al3d_seg_pass2_bf16": [_vp, _vp, _i64, _i64, _i64, _i, _i, _vp, _vp, _vp, _vp],
@@ -80,7 +96,7 @@ def lib():
 
 # kernels launched through this binding since import (bench.py reports it as gpu_launches)
 LAUNCHES = 0
-_NO_LAUNCH = ("tc_abort_code", "tc_status_word_host", "tc_configure", "set_debug_buffer", "crop_chunk_points")
+_NO_LAUNCH = ("train_ws_floats", "wgrad_ws_floats", "tc_abort_code", "tc_status_word_host", "tc_configure", "set_debug_buffer", "crop_chunk_points")
 
 
 def check(rc, what=""):

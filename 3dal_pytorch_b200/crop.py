@@ -28,8 +28,26 @@ def detector_to_waymo(box3d):
     return b[:, [0, 1, 2, 4, 3, 5, -1]]
 
 
+def box_planes_device(boxes, device):
+    """(B,7) f32 [x,y,z,l,w,h,heading] -> planes (B,6,4) f32, padded rectangles (B,6) f32, both CUDA tensors, computed by
+    crop_box_setup_kernel.  Only sin / cos of the heading are evaluated here (numpy float32, like the reference:
+    box_np_ops.py:163-164); tests/test_crop.py checks the result bit for bit against box_planes_host."""
+    boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 7)
+    n = boxes.shape[0]
+    sincos = np.stack([np.sin(boxes[:, 6]), np.cos(boxes[:, 6])], 1).astype(np.float32)
+    d_boxes = torch.from_numpy(boxes).to(device)
+    d_sc = torch.from_numpy(sincos).to(device)
+    planes = torch.empty((n, 6, 4), device=device, dtype=torch.float32)
+    aabb = torch.empty((n, 6), device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().al3d_crop_box_setup(d_boxes.data_ptr(), d_sc.data_ptr(), n, AABB_PAD, 1e-5, planes.data_ptr(),
+                                                  aabb.data_ptr(), ops._stream()), "crop_box_setup")
+    return planes, aabb
+
+
 def box_planes_host(boxes):
-    """(B,7) f32 [x,y,z,l,w,h,heading] -> planes (B,6,4) f32 (inward normals, d) and padded
+    """Host twin of box_planes_device (numpy, the reference's own operations): used by the tests as the checker.
+    (B,7) f32 [x,y,z,l,w,h,heading] -> planes (B,6,4) f32 (inward normals, d) and padded
     rectangles (B,6) f32 [xmin,ymin,zmin,xmax,ymax,zmax]."""
     boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 7)
     f0, f1 = np.float32(0), np.float32(1)
@@ -82,9 +100,11 @@ class CropPlan:
         self.box_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
         TB = self.TB = int(self.box_off[-1])
         if TB:
-            planes, aabb = box_planes_host(np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 7) for b in boxes], 0))
+            self.d_planes, self.d_aabb = box_planes_device(
+                np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 7) for b in boxes], 0), dev)
         else:
-            planes, aabb = np.zeros((0, 6, 4), np.float32), np.zeros((0, 6), np.float32)
+            self.d_planes = torch.zeros((0, 6, 4), device=dev, dtype=torch.float32)
+            self.d_aabb = torch.zeros((0, 6), device=dev, dtype=torch.float32)
         self.max_boxes = max(1, max(nb) if nb else 1)
         CH = lib.al3d_crop_chunk_points()
         chunks, frame_chunk_off = [], [0]
@@ -94,18 +114,25 @@ class CropPlan:
             frame_chunk_off.append(len(chunks))
         self.n_chunks = len(chunks)
         self.hit_cap = int(hit_cap or 512)          # hits per chunk of 2048 points; <= 16384
-        self.cell_cap = 64 * self.max_boxes + GRID * GRID
         i32 = lambda *s: torch.empty(s, device=dev, dtype=torch.int32)
-        self.d_planes = torch.from_numpy(planes).to(dev)
-        self.d_aabb = torch.from_numpy(aabb).to(dev)
         self.d_pt_off = torch.from_numpy(pt_off).to(dev)
         self.d_box_off = torch.from_numpy(self.box_off).to(dev)
         self.d_chunks = torch.tensor(chunks, dtype=torch.int32, device=dev).reshape(-1, 4)
         self.d_fco = torch.tensor(frame_chunk_off, dtype=torch.int64, device=dev)
         self.meta = torch.empty((max(F, 1), 4), device=dev, dtype=torch.float32)
         self.cell_start = i32(max(F, 1), GRID * GRID + 1)
-        self.cell_boxes = i32(max(F, 1), self.cell_cap)
         self.overflow = torch.zeros((1,), device=dev, dtype=torch.int32)
+        # Size the CSR cell lists from the data: a counting run of the grid kernel (cell_cap = 0 stores nothing) leaves
+        # every frame's total in cell_start[f, -1].  Few large or heavily overlapping boxes can cover all 64 x 64 cells
+        # each -- a fixed 64 * B + 4096 guess overflowed on two near-duplicate detections.
+        self.cell_cap = 0
+        self.cell_boxes = i32(1)
+        if F and TB:
+            self.grid()
+            self.cell_cap = max(int(self.cell_start[:, GRID * GRID].max().item()), 1)
+            self.overflow.zero_()
+        self.cell_cap = max(self.cell_cap, 1)
+        self.cell_boxes = i32(max(F, 1), self.cell_cap)
         self.hits = torch.empty((max(self.n_chunks, 1), self.hit_cap, 2), device=dev, dtype=torch.int32)
         self.n_hits = i32(max(self.n_chunks, 1))
         self.cbc = i32(max(self.n_chunks, 1), self.max_boxes)

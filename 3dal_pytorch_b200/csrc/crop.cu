@@ -5,8 +5,8 @@
 // _points_in_convex_polygon_3d_jit det3d/core/bbox/geometry.py:241-276 (a point is inside iff for all six
 // planes ((px*nx + py*ny) + pz*nz) + d is NOT >= 0, evaluated in float32 without FMA), and the crop
 // materialisation det3d/datasets/waymo/waymo_common.py:168-171 (gather in ascending point order, then
-// pose(4x4 f64) @ [x y z 1]).  The plane equations come from the host (crop.py) so that sin/cos and the
-// corner arithmetic are the reference's own numpy float32 operations.
+// pose(4x4 f64) @ [x y z 1]).  The plane equations are computed on the device (crop_box_setup_kernel) in numpy's own
+// float32 operation order; only sin / cos of the headings come from the host.
 //
 // The reference tests every point against every box (N*B*6 plane evaluations per frame).  Here a BEV grid
 // per frame maps a point to the few boxes whose (padded) bounding rectangle covers its cell, so each
@@ -25,7 +25,7 @@ namespace al3d {
 
 constexpr int kCropChunk = 2048;       // points per CTA of the hits kernel
 constexpr int kCropThreads = 256;
-constexpr int kMaxHitsPerPoint = 8;    // a point inside more boxes than this raises the overflow flag
+constexpr int kMaxHitsPerPoint = 8;    // a point inside more boxes than this raises overflow code 2 (rectangle candidates do not count)
 
 struct CropGridMeta { float x0, y0, inv_x, inv_y; };
 
@@ -130,6 +130,55 @@ crop_grid_kernel(const float *__restrict__ aabb, const int64_t *__restrict__ box
             while (j >= 0 && l[j] > v) { l[j + 1] = l[j]; --j; }
             l[j + 1] = v;
         }
+    }
+}
+
+// Box -> plane equations + padded bounding rectangle, on the device, in the reference's own float32 operation order
+// (corners_nd / rotation_3d_in_axis / center_to_corner_box3d det3d/core/bbox/box_np_ops.py:55-85,146-179,241-262;
+// corner_to_surfaces_3d :650-670; surface_equ_3d_jitv2 det3d/core/bbox/geometry.py:351-377).  Only sin / cos of the
+// heading come from the host (numpy's float32 sin / cos are not bit-identical to CUDA's sinf / cosf): everything else is
+// explicit round-to-nearest multiplies / adds without contraction, so the planes equal numpy's bit for bit.
+__constant__ float c_corner_sign[8][3] = {{-.5f, -.5f, -.5f}, {-.5f, -.5f, .5f}, {-.5f, .5f, .5f}, {-.5f, .5f, -.5f},
+                                          {.5f, -.5f, -.5f},  {.5f, -.5f, .5f},  {.5f, .5f, .5f},  {.5f, .5f, -.5f}};
+__constant__ int c_quad[6][4] = {{0, 1, 2, 3}, {7, 6, 5, 4}, {0, 3, 7, 4}, {1, 5, 6, 2}, {0, 4, 5, 1}, {3, 2, 6, 7}};
+
+__global__ void crop_box_setup_kernel(const float *__restrict__ boxes, const float *__restrict__ sincos, int64_t n_boxes, float pad_abs,
+                                      float pad_rel, float *__restrict__ planes, float *__restrict__ aabb)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_boxes) return;
+    const float *bx = boxes + b * 7;
+    const float s = sincos[b * 2], c = sincos[b * 2 + 1], ns = -s;
+    float cx[8], cy[8], cz[8];
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float x = __fmul_rn(bx[3], c_corner_sign[k][0]), y = __fmul_rn(bx[4], c_corner_sign[k][1]), z = __fmul_rn(bx[5], c_corner_sign[k][2]);
+        // einsum("aij,jka->aik") with rot_mat_T = [[c,-s,0],[s,c,0],[0,0,1]]: three-term sums, left to right
+        const float rx = __fadd_rn(__fadd_rn(__fmul_rn(x, c), __fmul_rn(y, s)), __fmul_rn(z, 0.f));
+        const float ry = __fadd_rn(__fadd_rn(__fmul_rn(x, ns), __fmul_rn(y, c)), __fmul_rn(z, 0.f));
+        const float rz = __fadd_rn(__fadd_rn(__fmul_rn(x, 0.f), __fmul_rn(y, 0.f)), __fmul_rn(z, 1.f));
+        cx[k] = __fadd_rn(rx, bx[0]); cy[k] = __fadd_rn(ry, bx[1]); cz[k] = __fadd_rn(rz, bx[2]);
+        mn[0] = fminf(mn[0], cx[k]); mn[1] = fminf(mn[1], cy[k]); mn[2] = fminf(mn[2], cz[k]);
+        mx[0] = fmaxf(mx[0], cx[k]); mx[1] = fmaxf(mx[1], cy[k]); mx[2] = fmaxf(mx[2], cz[k]);
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const int i0 = c_quad[q][0], i1 = c_quad[q][1], i2 = c_quad[q][2];
+        const float ax = __fsub_rn(cx[i0], cx[i1]), ay = __fsub_rn(cy[i0], cy[i1]), az = __fsub_rn(cz[i0], cz[i1]);
+        const float bxv = __fsub_rn(cx[i1], cx[i2]), byv = __fsub_rn(cy[i1], cy[i2]), bzv = __fsub_rn(cz[i1], cz[i2]);
+        const float nx = __fsub_rn(__fmul_rn(ay, bzv), __fmul_rn(az, byv));
+        const float ny = __fsub_rn(__fmul_rn(az, bxv), __fmul_rn(ax, bzv));
+        const float nz = __fsub_rn(__fmul_rn(ax, byv), __fmul_rn(ay, bxv));
+        // d = -q0.x * nx - q0.y * ny - q0.z * nz, left to right
+        const float d = __fsub_rn(__fsub_rn(__fmul_rn(-cx[i0], nx), __fmul_rn(cy[i0], ny)), __fmul_rn(cz[i0], nz));
+        reinterpret_cast<float4 *>(planes)[b * 6 + q] = make_float4(nx, ny, nz, d);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float pad = __fadd_rn(pad_abs, __fmul_rn(pad_rel, fmaxf(fabsf(mn[k]), fabsf(mx[k]))));
+        aabb[b * 6 + k] = __fsub_rn(mn[k], pad);
+        aabb[b * 6 + 3 + k] = __fadd_rn(mx[k], pad);
     }
 }
 
@@ -250,6 +299,21 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                 }
             }
         }
+        // Candidate list of one point (kMaxHitsPerPoint slots).  When it fills up -- many overlapping padded rectangles -- the
+        // stored candidates are put through the exact test right away and only the real hits stay (flagged as decided), so
+        // the limit applies to the boxes a point is INSIDE, as the name says, not to its rectangle candidates.
+        auto push_cand = [&](int (&cand)[kMaxHitsPerPoint], int &nc, int b, float x, float y, float z) {
+            if (nc == kMaxHitsPerPoint) {
+                int m = 0;
+                for (int q = 0; q < kMaxHitsPerPoint; ++q) {
+                    const int cb = cand[q];
+                    if ((cb & (1 << 30)) || crop_inside(x, y, z, pl + (cb & 0xFFFF) * 6)) cand[m++] = (cb & 0xFFFF) | (1 << 30);
+                }
+                nc = m;
+                if (nc == kMaxHitsPerPoint) { if (crop_inside(x, y, z, pl + b * 6)) atomicExch(overflow, 2); return; }
+            }
+            cand[nc++] = b;
+        };
         // the first kCropLook entries of every point's cell list: U * kCropLook independent loads, one round trip
         // (the per-point loop below used to walk its list one dependent load pair at a time)
         int bj[U][kCropLook];
@@ -268,8 +332,7 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                     // decided in place, flagged so that the queue does not test it again.
                     for (int b = 0; b < B; ++b)
                         if (crop_inside(px[k], py[k], pz[k], pl + b * 6)) {
-                            if (nc < kMaxHitsPerPoint) cand[nc] = b | (1 << 30); else atomicExch(overflow, 2);
-                            ++nc;
+                            if (nc < kMaxHitsPerPoint) cand[nc++] = b | (1 << 30); else atomicExch(overflow, 2);
                         }
                 } else {
                     // padded boxes of the prefetched entries: their loads are independent of each other
@@ -283,20 +346,17 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                     for (int j = 0; j < kCropLook; ++j)
                         if (bj[k][j] >= 0 && px[k] >= lo[j].x && py[k] >= lo[j].y && pz[k] >= mid[j].x && px[k] <= mid[j].y &&
                             py[k] <= hi[j].x && pz[k] <= hi[j].y) {
-                            if (nc < kMaxHitsPerPoint) cand[nc] = bj[k][j]; else atomicExch(overflow, 2);
-                            ++nc;
+                            push_cand(cand, nc, bj[k][j], px[k], py[k], pz[k]);
                         }
                     for (int e = e0[k] + kCropLook; e < e1[k]; ++e) {               // longer lists (rare): the rest, one at a time
                         const int b = __ldg(cb + e);
                         const float2 lo = __ldg(bb + b * 3), mid = __ldg(bb + b * 3 + 1), hi = __ldg(bb + b * 3 + 2);
                         // aabb = [xmin ymin | zmin xmax | ymax zmax], padded: never rejects a point the exact test accepts
                         if (px[k] >= lo.x && py[k] >= lo.y && pz[k] >= mid.x && px[k] <= mid.y && py[k] <= hi.x && pz[k] <= hi.y) {
-                            if (nc < kMaxHitsPerPoint) cand[nc] = b; else atomicExch(overflow, 2);
-                            ++nc;
+                            push_cand(cand, nc, b, px[k], py[k], pz[k]);
                         }
                     }
                 }
-                if (nc > kMaxHitsPerPoint) nc = kMaxHitsPerPoint;
             }
             const unsigned any = __ballot_sync(0xffffffffu, nc > 0);
             if (any == 0) continue;                                    // the common case: no candidate at all
@@ -475,6 +535,17 @@ __global__ void crop_dense_mask_kernel(const int32_t *__restrict__ idx, const in
 using namespace al3d;
 
 extern "C" int al3d_crop_chunk_points(void) { return kCropChunk; }
+
+extern "C" int al3d_crop_box_setup(const float *boxes, const float *sincos, int64_t n_boxes, float pad_abs, float pad_rel, float *planes,
+                                   float *aabb, void *stream)
+{
+    AL3D_CHECK_ARG(n_boxes >= 0, "al3d_crop_box_setup: negative size");
+    if (n_boxes == 0) return 0;
+    AL3D_CHECK_ARG(boxes && sincos && planes && aabb, "al3d_crop_box_setup: null pointer");
+    crop_box_setup_kernel<<<(unsigned)ceil_div(n_boxes, 128), 128, 0, (cudaStream_t)stream>>>(boxes, sincos, n_boxes, pad_abs, pad_rel, planes, aabb);
+    AL3D_CHECK_LAUNCH("crop_box_setup_kernel");
+    return 0;
+}
 
 extern "C" int al3d_crop_build_grid(const float *aabb, const int64_t *box_off, int n_frames, int G, float *grid_meta,
                                     int32_t *cell_start, int32_t *cell_boxes, int cell_cap, int32_t *overflow, void *stream)

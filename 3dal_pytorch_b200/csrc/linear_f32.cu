@@ -41,7 +41,7 @@ pointwise_first_kernel(const float *__restrict__ x, int64_t sb, int64_t sc, int6
 #pragma unroll
             for (int c = 0; c < C; ++c) acc = fmaf(v[c], wr[c], acc);
             acc += sbias[q * 4 + j];
-            o[j] = (act == AL3D_ACT_RELU) ? fmaxf(acc, 0.f) : acc;
+            o[j] = (act & AL3D_ACT_RELU) ? fmaxf(acc, 0.f) : acc;
         }
         *reinterpret_cast<float4 *>(y + m * cout + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -152,8 +152,8 @@ linear_f32_kernel(const float *__restrict__ a, int64_t lda, int64_t M, int K, co
             float v = acc[i][j] + bj;
             const int64_t g = m / rows_per_group;
             if (rowbias) v += rowbias[g * cout + o];
-            if (act == AL3D_ACT_RELU) v = fmaxf(v, 0.f);
-            if (y_max == nullptr) y[m * ldy + o] = v;
+            if (act & AL3D_ACT_RELU) v = fmaxf(v, 0.f);
+            if (y_max == nullptr) y[m * ldy + o] = (act & AL3D_ACT_ACCUMULATE) ? y[m * ldy + o] + v : v;
             else if (one_group) colmax = fmaxf(colmax, v);
             else atomicMax(reinterpret_cast<int *>(y_max + g * cout + o), __float_as_int(v));
         }
@@ -198,7 +198,7 @@ extern "C" int al3d_linear_f32(const float *a, int64_t lda, int64_t M, int K, co
     AL3D_CHECK_ARG(y || y_max, "al3d_linear_f32: no output");
     AL3D_CHECK_ARG(K > 0 && cout > 0 && M >= 0, "al3d_linear_f32: bad shape M=%lld K=%d cout=%d", (long long)M, K, cout);
     AL3D_CHECK_ARG(lda >= K && ldw >= K, "al3d_linear_f32: leading dimension smaller than K");
-    AL3D_CHECK_ARG(!y_max || act == AL3D_ACT_RELU, "al3d_linear_f32: max-pool epilogue requires ReLU");
+    AL3D_CHECK_ARG(!y_max || act == AL3D_ACT_RELU, "al3d_linear_f32: max-pool epilogue requires ReLU (and no accumulate)");
     if (rows_per_group <= 0) rows_per_group = M > 0 ? M : 1;
     if (M == 0) return 0;
     dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(cout, BN));

@@ -54,8 +54,26 @@ class DynamicModel(_AutoLabelBase):
         self.box_est = PointNetEstimation(n_classes=n_classes)
         self._init_common()
 
-    @torch.no_grad()
-    def forward(self, pts, box, bbox_gt=None):
+    def _forward_train(self, pts, box, bbox_gt=None):
+        """tools/dynamic_model.py:121-155 under model.train() (tools/dynamic_train.py:50,66)."""
+        from . import train
+        self._check_inputs(pts, self.n_channel)
+        if box.dim() != 3 or box.shape[1] != 8:
+            raise ValueError("box must be (bs,8,steps), got %s" % (tuple(box.shape),))
+        logits = self._seg_train(pts)
+        with torch.no_grad():
+            obj, mask, _ = engine.mask_and_gather(pts[:, :4, :], logits.detach(), NUM_FRAME * NUM_OBJECT_POINT, self.gather_policy)
+        pe = train.head_apply(self, self.point_emb, obj, n_conv=4, fcs=("fc1", "fc2"))
+        be = train.head_apply(self, self.box_emb, box.float(), n_conv=4, fcs=("fc1", "fc2"))
+        box_pred = train.head_apply(self, self.box_est, torch.cat([pe, be], dim=1), n_conv=0, fcs=("fc1", "fc2", "fc3"), need_dx=True)
+        h = train.parse_heads_torch(box_pred)
+        out = {"logits": logits, "mask": mask, "center": h["center_boxnet"]}
+        for k in ("heading_scores", "heading_residuals_normalized", "heading_residuals", "size_scores", "size_residuals_normalized",
+                  "size_residuals"):
+            out[k] = h[k]
+        return out
+
+    def _forward_eval(self, pts, box, bbox_gt=None):
         self._check_inputs(pts, self.n_channel)
         if box.dim() != 3 or box.shape[1] != 8:
             raise ValueError("box must be (bs,8,steps), got %s" % (tuple(box.shape),))

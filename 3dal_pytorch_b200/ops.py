@@ -36,9 +36,13 @@ def pointwise_first(x, w, b, act=ACT_RELU):
     return y
 
 
-def linear(a, w, bias=None, rowbias=None, rows_per_group=0, act=ACT_RELU, K=None, max_out=None):
+ACT_ACCUMULATE = 2
+
+
+def linear(a, w, bias=None, rowbias=None, rows_per_group=0, act=ACT_RELU, K=None, max_out=None, out=None, accumulate=False):
     """a (M, >=K) row-major (row stride a.stride(0)), w (cout, >=K) -> (M,cout); with ``max_out``
-    (groups,cout) zero-initialised the result is max-pooled into it instead of being stored."""
+    (groups,cout) zero-initialised the result is max-pooled into it instead of being stored.  ``out``: write into
+    (accumulate=True: add onto) an existing (M,cout) tensor."""
     _need_cuda(a, w, bias, rowbias, max_out)
     M = a.shape[0]
     K = K if K is not None else a.shape[1]
@@ -46,7 +50,11 @@ def linear(a, w, bias=None, rowbias=None, rows_per_group=0, act=ACT_RELU, K=None
     assert a.stride(1) == 1 and w.stride(1) == 1
     y = None
     if max_out is None:
-        y = torch.empty((M, cout), device=a.device, dtype=torch.float32)
+        y = out if out is not None else torch.empty((M, cout), device=a.device, dtype=torch.float32)
+        assert y.shape == (M, cout) and y.is_contiguous()
+    if accumulate:
+        assert out is not None and max_out is None
+        act = act | ACT_ACCUMULATE
     _lib.check(_lib.lib().al3d_linear_f32(_p(a), a.stride(0), M, K, _p(w), w.stride(0), _p(bias), _p(rowbias),
                                           rows_per_group, cout, act, _p(y), cout, _p(max_out), _stream()), "linear")
     return y if max_out is None else max_out

@@ -60,11 +60,29 @@ class _AutoLabelBase(nn.Module):
     def _init_common(self):
         self._packs = engine.PackCache()
 
-    def _check_inputs(self, pts, C):
+    def forward(self, *args, **kwargs):
+        """Eval mode: the fused inference kernels (no autograd graph).  Training mode (``.train()``): batch-statistics
+        BatchNorm, Dropout and outputs connected to autograd Functions whose backward runs in libal3d.so (train.py)."""
         if self.training:
-            raise NotImplementedError(
-                "training-mode forward (batch-statistics BatchNorm, dropout, backward) is not built yet; "
-                "call .eval() -- see DESIGN.md 'out of scope this round'")
+            return self._forward_train(*args, **kwargs)
+        with torch.no_grad():
+            return self._forward_eval(*args, **kwargs)
+
+    def _grad_bucket(self):
+        """Flat gradient bucket the training-mode backward writes into (rebuilt when the parameters are re-homed)."""
+        from . import train
+        key = tuple(p.data_ptr() for p in self.parameters())
+        if getattr(self, "_bucket_key", None) != key:
+            self._bucket, self._bucket_key = train.GradBucket(self), key
+        return self._bucket
+
+    def _seg_train(self, pts):
+        from . import train
+        bs, _, n = pts.shape
+        drop = train.dropout_multiplier(bs, n, self.ins_seg.dropout.p, pts.device)
+        return train.seg_apply(self, self.ins_seg, pts, drop)
+
+    def _check_inputs(self, pts, C):
         if not pts.is_cuda:
             raise RuntimeError("the B200 build has no CPU path: inputs must be CUDA tensors")
         if pts.dim() != 3 or pts.shape[1] != C:
@@ -110,8 +128,20 @@ class StaticModelOneBoxEst(_AutoLabelBase):
         self.box_est = PointNetEstimation(n_classes=n_classes)
         self._init_common()
 
-    @torch.no_grad()
-    def forward(self, pts, init_box, bbox_gt=None):
+    def _forward_train(self, pts, init_box, bbox_gt=None):
+        """tools/static_model.py:117-146 under model.train() (tools/static_train.py:66,83)."""
+        from . import train
+        self._check_inputs(pts, self.n_channel)
+        logits = self._seg_train(pts)
+        with torch.no_grad():          # the gather is index work: not differentiable in the reference either (:33-47)
+            obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits.detach(), NUM_OBJECT_POINT, self.gather_policy)
+        h = train.parse_heads_torch(train.head_apply(self, self.box_est, obj))
+        out = {"logits": logits, "mask": mask}
+        out.update(h)
+        out["center"] = h["center_boxnet"] + init_box.float()[:, :3]
+        return out
+
+    def _forward_eval(self, pts, init_box, bbox_gt=None):
         self._check_inputs(pts, self.n_channel)
         logits, seg_mask = self._seg(pts)
         obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, self.gather_policy, mask=seg_mask)
@@ -139,8 +169,35 @@ class StaticModelTwoBoxEst(_AutoLabelBase):
         self.box_est_two = PointNetEstimation(n_classes=n_classes)
         self._init_common()
 
-    @torch.no_grad()
-    def forward(self, pts, init_box, bbox_gt):
+    def _forward_train(self, pts, init_box, bbox_gt):
+        """tools/static_model.py:158-239 under model.train(): the decode of box_one and the re-centering of the gathered
+        points are index / label work on detached values, exactly as in the reference (numpy round trip :177-205)."""
+        from . import train
+        self._check_inputs(pts, self.n_channel)
+        init_box = init_box.float().contiguous()
+        bbox_gt = bbox_gt.float().contiguous()
+        logits = self._seg_train(pts)
+        with torch.no_grad():
+            obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits.detach(), NUM_OBJECT_POINT, self.gather_policy)
+        one = train.parse_heads_torch(train.head_apply(self, self.box_est_one, obj))
+        center_one = one["center_boxnet"] + init_box[:, :3]
+        with torch.no_grad():
+            c = lambda t: t.detach().contiguous()
+            box_one, _ = ops.decode_boxes(c(center_one), c(one["heading_scores"]), c(one["heading_residuals"]), c(one["size_scores"]),
+                                          c(one["size_residuals"]), base_heading=init_box[:, 6])
+            obj2, cls2, res2 = ops.twostage_retransform(obj, init_box, box_one, bbox_gt)
+        two = train.parse_heads_torch(train.head_apply(self, self.box_est_two, obj2))
+        center_two = two["center_boxnet"] + center_one
+        out = {"logits": logits, "mask": mask, "center_one": center_one, "box_one": box_one, "center_two": center_two,
+               "heading_class_label_two": cls2, "heading_residuals_label_two": res2, "center": center_two}
+        for k in ("heading_scores", "heading_residuals_normalized", "heading_residuals", "size_scores", "size_residuals_normalized",
+                  "size_residuals"):
+            out[k + "_one"], out[k + "_two"] = one[k], two[k]
+        for k in ("heading_scores", "heading_residuals", "size_scores", "size_residuals"):
+            out[k] = two[k]
+        return out
+
+    def _forward_eval(self, pts, init_box, bbox_gt):
         self._check_inputs(pts, self.n_channel)
         init_box = init_box.float().contiguous()
         bbox_gt = bbox_gt.float().contiguous()

@@ -32,6 +32,7 @@ extern "C" {
 /* activation flags for al3d_linear_f32 */
 #define AL3D_ACT_NONE 0
 #define AL3D_ACT_RELU 1
+#define AL3D_ACT_ACCUMULATE 2   /* y += result (training backward: a tensor with two consumers) */
 
 /* gather index policies (al3d_gather_fg) */
 #define AL3D_GATHER_STRIDED 0   /* device rule: slot j <- pos[(j*L)/n_pts] (L>=n_pts) or pos[j%L]   */
@@ -114,10 +115,15 @@ int al3d_twostage_retransform(const float *obj_pts, int bs, int m, const float *
  * (det3d/datasets/waymo/waymo_common.py:167-171).  Frames are concatenated: points (sum N_f, stride)
  * f32 with pt_off (F+1) i64; boxes as inward plane equations planes (sum B_f, 6, 4) f32 and padded
  * axis-aligned rectangles aabb (sum B_f, 6) f32 [xmin ymin zmin xmax ymax zmax] with box_off (F+1) i64
- * (both computed by the caller with the reference's own float32 numpy arithmetic, crop.py).
+ * (both from al3d_crop_box_setup).
  * `overflow` is a device int32 the kernels set non-zero when a caller-provided capacity is too small.
  * Order of calls: build_grid -> hits -> scan -> (read offsets[n_boxes] = total, allocate) -> fill.
  * ---------------------------------------------------------------------------------------------- */
+/* boxes (n,7) f32 [x y z l w h heading] + sincos (n,2) f32 [sin, cos of the heading, from the host's float32
+ * numpy] -> planes (n,6,4) f32 and padded rectangles aabb (n,6) f32 (pad = pad_abs + pad_rel * max|corner|), bit-identical
+ * to the reference's numpy arithmetic (box_np_ops.py:55-85,146-179,241-262,650-670; geometry.py:351-377). */
+int al3d_crop_box_setup(const float *boxes, const float *sincos, int64_t n_boxes, float pad_abs, float pad_rel, float *planes,
+                        float *aabb, void *stream);
 int al3d_crop_chunk_points(void);      /* points per work chunk (the caller builds the chunk table) */
 int al3d_crop_build_grid(const float *aabb, const int64_t *box_off, int n_frames, int G, float *grid_meta,
                          int32_t *cell_start, int32_t *cell_boxes, int cell_cap, int32_t *overflow, void *stream);
@@ -165,6 +171,41 @@ int al3d_boxseq_prep(const double *box, int bs, int steps, int center_step, cons
                      double *init_box, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Track-level glue around the models (integer / index work exact; float64 arithmetic like the reference's numpy).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* tools/trackData.py:25-45: regroup per-frame detections by tracking id.  ids (n_obs) i64 and frame_of_obs (n_obs) i32
+ * list the observations in the reference's iteration order (frame by frame, boxes in frame order).  Tracks are numbered
+ * in order of first appearance; track_obs (track_cap, n_frames) i32 holds each track's observation indices in frame
+ * order (-1 padded), track_len (track_cap) i32, track_id (track_cap) i64, track_of_obs (n_obs) i32, n_tracks (1) i32.
+ * error (1) i32: 1 = track_cap / frame index out of range, 2 = an id appears twice in one frame.
+ * Scratch: hash_keys (hash_size) i64, hash_first / hash_rank (hash_size) i32 with hash_size a power of two >= 2*n_obs,
+ * presence (track_cap * n_frames) i32. */
+int al3d_track_regroup(const int64_t *ids, const int32_t *frame_of_obs, int n_obs, int n_frames, int track_cap,
+                       int64_t *hash_keys, int32_t *hash_first, int32_t *hash_rank, int hash_size, int32_t *presence,
+                       int32_t *track_of_obs, int64_t *track_id, int32_t *track_obs, int32_t *track_len,
+                       int32_t *n_tracks, int32_t *error, void *stream);
+/* tools/motionState.py:47-49: feat (n_tracks, 2) f64 = [ ||b_first - b_last||, ||var(b, axis=0)|| ] over the first
+ * n_cols columns of boxes (n_obs, box_stride) f64.  (The reference slices a (L,1,7) array with [0, :3], which keeps
+ * all 7 box columns: pass n_cols = 7 for parity, 3 for the centre-only feature the comment there intends.) */
+int al3d_motion_features(const int32_t *track_obs, const int32_t *track_len, int n_tracks, int n_frames, const double *boxes,
+                         int box_stride, int n_cols, double *feat, void *stream);
+/* Training labels of STATICTRACK.__getitem__ (tools/static_model.py:549-566, tools/utils.py:53-67).  mask_label
+ * (bs, n_out) f32 (may be NULL): the resampled points (same src_xyz / choice / inv_pose as al3d_track_points_prep, before
+ * the canonical transform) tested in float64 against gt_planes (bs,6,4) f32 from al3d_crop_box_setup;  centre label =
+ * gt_box[:, :3]; heading class / residual = angle2class(gt heading - init_heading, 12); size class / residual =
+ * size2class(gt lwh).  float64 arithmetic, rounded to float32 once on output. */
+int al3d_track_labels(const double *src_xyz, const int64_t *choice, int bs, int n_out, const double *inv_pose,
+                      const float *gt_planes, const float *gt_box, const double *init_heading, float *mask_label,
+                      float *center_label, int64_t *heading_cls, float *heading_res, int64_t *size_cls, float *size_res,
+                      void *stream);
+/* tools/static_eval.py:84-92: the refined box of track t (final_box (n_tracks,7) f32, in the vehicle frame of its best
+ * frame) -> every observation of the track: out_boxes[obs] = transform_box(transform_box(box, best_pose[t]),
+ * obs_inv_pose[obs]) in float64 (poses 4x4 row-major). */
+int al3d_box_writeback(const float *final_box, const double *best_pose, const int32_t *track_obs, const int32_t *track_len,
+                       int n_tracks, int n_frames, const double *obs_inv_pose, double *out_boxes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Loss forward (evaluation / logging; no backward).  Replaces FrustumPointNetLossOneBoxEst.forward
  * tools/static_model.py:348-425 (each head set of ...TwoBoxEst :427-517; DynamicModelLoss
  * tools/dynamic_model.py:321-398).  out6 = [mask NLL, centre Huber(2), heading CE, size CE, heading-residual
@@ -176,6 +217,55 @@ int al3d_loss_forward(const float *logits, const float *mask_label, int64_t M, c
                       const float *heading_res_norm, const float *heading_res_label, const float *size_scores,
                       const int64_t *size_cls_label, const float *size_res_norm, const float *size_res_label, int bs,
                       float *partial_ws, int n_partial, float *out6, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step (BASELINE.json configs[4]; reference loop tools/static_train.py:65-90, tools/dynamic_train.py:37-133).
+ * Activations are row-major (M, C) with M = bs*n rows (Conv1d(k=1) on (bs,C,n) == Linear on the rows).  The layer
+ * GEMMs are al3d_linear_f32 (forward and, on W^T, the input gradient); everything else is below.  fp32 arithmetic,
+ * fp64 finalisation of the long column sums, fixed reduction orders (bit-reproducible).  `ws`: caller scratch of
+ * al3d_train_ws_floats(M, C) / al3d_wgrad_ws_floats(M, N, K) floats.
+ * ---------------------------------------------------------------------------------------------- */
+int al3d_train_ws_floats(int64_t M, int C);
+int al3d_wgrad_ws_floats(int64_t M, int N, int K);
+/* nn.BatchNorm1d in training mode + ReLU (+ Dropout multiplier): batch mean / biased variance over the M rows,
+ * z = relu(gamma * (y - mean) * rstd + beta) * drop; running_mean / running_var (may be NULL) are updated with
+ * `momentum` and the unbiased variance (tools/static_model.py:254-258,279-283).  drop (may be NULL) is addressed as
+ * drop[(m / rows_per_group) * drop_sg + c * drop_sc + (m % rows_per_group) * drop_sr] (element strides), so a mask
+ * drawn in the reference's (bs, C, n) layout is read in place (tools/static_model.py:264,293).  mean / rstd (C) are
+ * outputs kept for the backward. */
+int al3d_bn_train_forward(const float *y, int64_t M, int C, const float *gamma, const float *beta, float eps, float momentum,
+                          float *running_mean, float *running_var, const float *drop, int64_t drop_sg, int64_t drop_sc,
+                          int64_t drop_sr, int64_t rows_per_group, int relu, float *ws, float *mean, float *rstd, float *z,
+                          void *stream);
+/* Backward of the same: dz (gradient w.r.t. z) -> dy (may alias dz), dgamma, dbeta (C). */
+int al3d_bn_train_backward(const float *dz, const float *y, int64_t M, int C, const float *gamma, const float *beta,
+                           const float *mean, const float *rstd, const float *drop, int64_t drop_sg, int64_t drop_sc,
+                           int64_t drop_sr, int64_t rows_per_group, int relu, float *ws, float *dgamma, float *dbeta,
+                           float *dy, void *stream);
+/* Column sums of x (M, C): per group of rows_per_group rows -> out (M / rows_per_group, C), or of the whole matrix
+ * (rows_per_group <= 0 or >= M; needs ws) -> out (C).  Bias gradients and the per-object sums of the dconv1 backward. */
+int al3d_group_colsum(const float *x, int64_t M, int C, int64_t rows_per_group, float *ws, float *out, void *stream);
+/* torch.max over the n points of each object with its arg-max row (tools/static_model.py:284,334) and the backward
+ * scatter dz[(g*n + arg[g,c]), c] = dg[g,c] into a zero-filled dz. */
+int al3d_group_max_forward(const float *z, int64_t G, int64_t n, int C, float *g, int32_t *arg, void *stream);
+int al3d_group_max_backward(const float *dg, const int32_t *arg, int64_t G, int64_t n, int C, float *dz_zeroed, void *stream);
+/* Weight gradient dW (N, K; row stride lddw) (+)= dY^T . X with dY (M, N; ldy), X (M, K; ldx). */
+int al3d_wgrad_f32(const float *dy, int64_t ldy, const float *x, int64_t ldx, int64_t M, int N, int K, float *ws,
+                   float *dw, int64_t lddw, int accumulate, void *stream);
+/* Gradient of sum_t w6[t] * term_t (terms of al3d_loss_forward, w6 six DEVICE floats) w.r.t. the logits -> dlogits
+ * (M, 2) (skipped when logits == NULL) and w.r.t. the 39-wide head vector -> dbox (bs, 39) = [centre 3 | heading scores
+ * 12 | normalised heading residuals 12 | size scores 3 | normalised size residuals 9] (tools/static_model.py:341-425). */
+int al3d_loss_backward(const float *logits, const float *mask_label, int64_t M, const float *center, const float *center_label,
+                       const float *heading_scores, const int64_t *heading_cls_label, const float *heading_res_norm,
+                       const float *heading_res_label, const float *size_scores, const int64_t *size_cls_label,
+                       const float *size_res_norm, const float *size_res_label, int bs, const float *w6, float *dlogits,
+                       float *dbox, void *stream);
+/* count_zeroed += number of points whose arg-max class equals the label (seg accuracy, tools/static_train.py:128-129). */
+int al3d_seg_correct(const float *logits, const float *mask_label, int64_t M, unsigned long long *count_zeroed, void *stream);
+/* One torch.optim.Adam step (amsgrad off) over a flat bucket of n parameters; grad is multiplied by grad_scale first
+ * (1 / world size after the gradient all-reduce); weight_decay is the L2 form (tools/static_train.py:220). */
+int al3d_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 / TMEM, bf16 operands, fp32 accumulate) shared-MLP kernels.

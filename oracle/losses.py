@@ -19,7 +19,7 @@ def head_terms(center, hs, hrn, ss, srn, center_label, hcls, hres, scls, sres):
     lab = hres / (np.pi / NUM_HEADING_BIN)
     hr = huber(hrn.gather(1, hcls.long()[:, None])[:, 0] - lab, 1.0)
     s = F.nll_loss(F.log_softmax(ss, dim=1), scls.long())
-    anchors = torch.from_numpy(MEAN_SIZE_ARR).float().to(center.device)[scls.long()]
+    anchors = torch.from_numpy(MEAN_SIZE_ARR).to(center.dtype).to(center.device)[scls.long()]
     pred = srn[torch.arange(srn.shape[0]), scls.long()]
     sr = huber((sres / anchors - pred).norm(dim=1), 1.0)
     return c, h, s, hr, sr

@@ -106,7 +106,7 @@ def parse_heads(box_pred):
     h_res = h_res_n * (np.pi / H)
     s_scores = box_pred[:, 3 + 2 * H:3 + 2 * H + S]
     s_res_n = box_pred[:, 3 + 2 * H + S:3 + 2 * H + 4 * S].contiguous().view(bs, S, 3)
-    anchors = torch.from_numpy(codecs.MEAN_SIZE_ARR).float().to(box_pred.device)
+    anchors = torch.from_numpy(codecs.MEAN_SIZE_ARR).to(box_pred.dtype).to(box_pred.device)
     s_res = s_res_n * anchors.unsqueeze(0)
     return center, h_scores, h_res_n, h_res, s_scores, s_res_n, s_res
 

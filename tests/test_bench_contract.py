@@ -22,11 +22,17 @@ def test_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "auto-labeled objects/sec" and d["unit"] == "objects/s"
-    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["data"] == "synthetic"
+    assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["data"] == "synthetic"
     assert d["steps"] == 1 and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" when the reference tree is mounted (this container), "port" (the oracle) on the GPU box
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_falls_back_to_the_oracle_port_without_the_reference_tree():
+    d = json.loads(_run({"AL3D_REFERENCE_ROOT": "/nonexistent"})[0])
+    assert d["cpu_baseline"]["kind"] == "port"
 
 
 def test_reference_arm_other_ranks_exit_silently():

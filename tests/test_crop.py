@@ -108,3 +108,45 @@ def test_crop_waymo_sized_frame_property():
     ref = ocrop.points_in_boxes(fr["points"], box[sel])
     for j, b in enumerate(sel):
         assert np.array_equal(idx[off[b]:off[b + 1]], np.nonzero(ref[:, j])[0])
+
+
+@pytest.mark.gpu
+def test_device_plane_setup_is_bit_identical_to_numpy():
+    """crop_box_setup_kernel (explicit round-to-nearest float32 operations in numpy's order, sin / cos from the host)
+    against the host twin, which test_host_planes_bitwise_equal_to_oracle pins to the reference arithmetic."""
+    rng = np.random.default_rng(11)
+    boxes = np.concatenate([_random_boxes(rng, 5000), _random_boxes(rng, 500, spread=2000.0)], 0)
+    boxes[7, 6] = 0.0
+    boxes[8, 3:6] = [1e-3, 40.0, 0.25]
+    planes, aabb = crop.box_planes_device(boxes, "cuda:0")
+    hp, ha = crop.box_planes_host(boxes)
+    assert np.array_equal(planes.cpu().numpy(), hp)
+    assert np.array_equal(aabb.cpu().numpy(), ha)
+
+
+@pytest.mark.gpu
+def test_crop_few_large_overlapping_boxes():
+    """near-duplicate detections cover (almost) every BEV cell each; the cell lists are sized from a counting
+    run, so this neither overflows nor truncates."""
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(-3, 3, (20000, 3)).astype(np.float32)
+    boxes = np.array([[0, 0, 0, 4.0, 2.0, 1.5, 0.3], [0.02, 0.01, 0, 4.0, 2.0, 1.5, 0.31], [0.5, 0.2, 0, 4.2, 1.9, 1.5, 0.25]], np.float32)
+    res = crop.crop_frames([pts], [boxes], [np.eye(4)], hit_cap=16384)
+    assert int(res["overflow"].item()) == 0
+    _check_against_oracle([pts], [boxes], [np.eye(4)], res)
+    m = crop.points_in_rbbox(pts, boxes)
+    assert np.array_equal(m, ocrop.points_in_boxes(pts, boxes))
+
+
+@pytest.mark.gpu
+def test_crop_many_candidate_rectangles_but_few_hits():
+    """A point may sit in the padded rectangles of more than 8 boxes as long as it is inside at most 8 of them: twelve
+    thin, rotated boxes fanned around the origin overlap as rectangles far more than as boxes."""
+    rng = np.random.default_rng(4)
+    ang = np.linspace(0, np.pi, 12, endpoint=False).astype(np.float32)
+    boxes = np.stack([np.zeros(12), np.zeros(12), np.zeros(12), np.full(12, 8.0), np.full(12, 0.2), np.full(12, 1.0), ang], 1).astype(np.float32)
+    pts = rng.uniform(-4, 4, (30000, 3)).astype(np.float32)
+    pts = pts[np.hypot(pts[:, 0], pts[:, 1]) > 1.0]                      # keep clear of the hub where all twelve overlap
+    res = crop.crop_frames([pts], [boxes], [np.eye(4)], hit_cap=16384)
+    assert int(res["overflow"].item()) == 0
+    _check_against_oracle([pts], [boxes], [np.eye(4)], res)

@@ -1,0 +1,250 @@
+"""GPU tests of the training step (BASELINE.json configs[4]): the CUDA forward / backward / optimiser against the
+training-mode oracle (oracle/train.py, pinned to the reference's autograd in tests/test_train_oracle_vs_reference.py)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, synth
+from oracle import train as otrain
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+sm = importlib.import_module("3dal_pytorch_b200.static_model")
+dm = importlib.import_module("3dal_pytorch_b200.dynamic_model")
+tr = importlib.import_module("3dal_pytorch_b200.train")
+losses = importlib.import_module("3dal_pytorch_b200.losses")
+# Gradient tolerance.  One training step of these nets is ill-conditioned in fp32: a pre-activation within rounding of
+# zero flips a ReLU gate and moves a whole term of a gradient sum, so two correct fp32 implementations (torch on the CPU
+# and ours) differ by up to a few 1e-3 of max|grad| in the occasional tensor while agreeing to ~1e-5 in most.  The checker
+# therefore evaluates the oracle in FLOAT64 as well and reports, next to our distance from it, the distance the fp32 oracle
+# itself shows (measured on the B200: ours 4e-3 worst / 6e-4..1.2e-3 median over the segmentation net's tensors, the fp32
+# torch oracle 3e-3 / 2e-4; box-head tensors agree to ~4e-5).  Bounds: worst tensor < 1e-2 and within 3x the oracle's worst
+# (+5e-4); median < 2.5e-3.  A missing or mis-scaled term in any backward kernel shows up as >= 5e-2.
+def _f64(sd, *tensors):
+    to = lambda t: t.double() if torch.is_tensor(t) and t.is_floating_point() else t
+    return ({k: to(v) for k, v in sd.items()},) + tuple(tuple(to(x) for x in t) if isinstance(t, tuple) else to(t) for t in tensors)
+
+
+def _labels(bs, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand((bs, n), generator=g) < 0.3).float(), torch.randn((bs, 3), generator=g) * 0.3,
+            torch.randint(0, 12, (bs,), generator=g), torch.randn((bs,), generator=g) * 0.1,
+            torch.randint(0, 3, (bs,), generator=g), torch.randn((bs, 3), generator=g) * 0.2)
+
+
+def _case(kind, bs=4):
+    sd = synth.random_state_dict(kind, seed=31)
+    if kind == "dynamic":
+        d = synth.dynamic_tracks(bs, npoints=256, seed=5)
+        pts = torch.from_numpy(d["pts_pm"]).transpose(2, 1).contiguous()
+        aux = torch.from_numpy(d["box_sm"]).transpose(2, 1).contiguous()
+    else:
+        d = synth.static_tracks(bs, n=1024, seed=5)
+        pts = torch.from_numpy(d["pts_pm"]).transpose(2, 1).contiguous()
+        aux = torch.from_numpy(d["init_box"])
+    gt = torch.from_numpy(d["bbox_gt"])
+    return sd, pts, aux, gt, _labels(bs, pts.shape[2], 7)
+
+
+def _drop(bs, n, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand((bs, 128, n), generator=g) >= 0.5).float() * 2.0
+
+
+def _check_grads(named_params, grads_of, grads32, grads64):
+    errs, floors, names = [], [], []
+    for name, p in named_params:
+        g, r32, r64 = grads_of(p).detach().cpu().double(), grads32[name].double(), grads64[name]
+        scale = float(r64.abs().max())
+        # gradients that are exactly zero in exact arithmetic (conv biases in front of a BatchNorm) stay rounding noise
+        if scale < 1e-6:
+            assert float(g.abs().max()) < 1e-4, name
+            continue
+        errs.append(float((g - r64).abs().max()) / scale)
+        floors.append(float((r32 - r64).abs().max()) / scale)
+        names.append(name)
+    worst = int(np.argmax(errs))
+    assert max(errs) < 3 * max(floors) + 5e-4, (names[worst], errs[worst], max(floors))
+    assert max(errs) < 1e-2 and float(np.median(errs)) < 2.5e-3, (float(np.median(errs)), float(np.median(floors)))
+    return {"worst": (names[worst], errs[worst]), "median": float(np.median(errs)), "oracle_fp32_worst": max(floors),
+            "oracle_fp32_median": float(np.median(floors))}
+
+
+def test_batchnorm_relu_dropout_forward_backward_against_torch():
+    torch.manual_seed(0)
+    bs, n, C = 3, 700, 96
+    M = bs * n
+    y = torch.randn(M, C, device=DEV) * 2 + 0.5
+    bn = torch.nn.BatchNorm1d(C).to(DEV)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.2)
+    drop = (torch.rand(bs, C, n, device=DEV) > 0.5).float() * 2
+    ref_bn = torch.nn.BatchNorm1d(C).to(DEV)
+    ref_bn.load_state_dict(bn.state_dict())
+    yt = y.clone().requires_grad_(True)
+    zr = torch.relu(ref_bn(yt)) * drop.permute(0, 2, 1).reshape(M, C)
+    dz = torch.randn(M, C, device=DEV)
+    zr.backward(dz)
+    z, mean, rstd = tr.bn_forward(y, bn, drop=drop, rows_per_group=n)
+    assert rel_err(z.cpu(), zr.detach().cpu()) < 1e-5
+    assert torch.allclose(bn.running_mean, ref_bn.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-5, atol=1e-6)
+    assert int(bn.num_batches_tracked) == 1
+    dgamma, dbeta = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    dy = tr.bn_backward(dz.clone(), y, bn, mean, rstd, dgamma, dbeta, drop=drop, rows_per_group=n)
+    assert rel_err(dy.cpu(), yt.grad.cpu()) < 1e-4
+    assert rel_err(dgamma.cpu(), ref_bn.weight.grad.cpu()) < 1e-4 and rel_err(dbeta.cpu(), ref_bn.bias.grad.cpu()) < 1e-4
+
+
+def test_wgrad_dgrad_groupmax_against_torch():
+    torch.manual_seed(1)
+    for M, N, K in [(5000, 64, 64), (3001, 130, 70), (40000, 1024, 128), (7, 39, 256), (2048, 2, 128)]:
+        dy = torch.randn(M, N, device=DEV)
+        x = torch.randn(M, K, device=DEV)
+        w = torch.randn(N, K, device=DEV)
+        dw = torch.empty(N, K + 8, device=DEV)[:, :K]             # strided output view
+        tr.wgrad(dy, x, dw)
+        assert rel_err(dw.cpu(), (dy.double().t() @ x.double()).cpu()) < 1e-5, (M, N, K)
+        dx = tr.dgrad(dy, w)
+        assert rel_err(dx.cpu(), (dy.double() @ w.double()).cpu()) < 1e-5
+        acc = torch.ones(M, K, device=DEV)
+        tr.dgrad(dy, w, out=acc, accumulate=True)
+        assert rel_err(acc.cpu(), (dy.double() @ w.double() + 1).cpu()) < 1e-5
+    G, n, C = 5, 333, 100
+    z = torch.relu(torch.randn(G * n, C, device=DEV))
+    g, arg = tr.group_max(z, G, n)
+    rv, ri = z.view(G, n, C).max(dim=1)
+    assert torch.equal(g, rv)
+    assert torch.equal(z.view(G, n, C).gather(1, arg.long()[:, None, :])[:, 0], rv)      # arg points at a maximum
+    dg = torch.randn(G, C, device=DEV)
+    dz = tr.group_max_backward(dg, arg, G, n)
+    assert torch.equal(dz.view(G, n, C).sum(1), dg) and int((dz != 0).sum()) <= G * C
+
+
+def test_fused_adam_matches_torch_adam():
+    torch.manual_seed(2)
+    model = sm.StaticModelOneBoxEst().to(DEV)
+    ref = sm.StaticModelOneBoxEst().to(DEV)
+    ref.load_state_dict(model.state_dict())
+    bucket = tr.GradBucket(model)
+    opt = tr.FusedAdam(model, bucket, lr=1e-3, weight_decay=1e-4)
+    topt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=1e-4)
+    for it in range(3):
+        bucket.flat.normal_(0, 0.01)
+        for p, q in zip(model.parameters(), ref.parameters()):
+            q.grad = bucket.view(p).clone()
+        opt.step()
+        topt.step()
+    for (name, p), q in zip(model.named_parameters(), ref.parameters()):
+        assert rel_err(p.detach().cpu(), q.detach().cpu()) < 1e-5, name
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_fused_training_step_matches_oracle(dropout):
+    sd, pts, init_box, gt, labels = _case("static_one")
+    bs, _, n = pts.shape
+    drop = _drop(bs, n) if dropout else None
+    ols, oout, ograds, ostats = otrain.static_one_step(sd, pts, init_box, labels, drop_mult=drop)
+    sd64, pts64, box64, lab64, drop64 = _f64(sd, pts, init_box, labels, drop)
+    _, _, ograds64, _ = otrain.static_one_step(sd64, pts64, box64, lab64, drop_mult=drop64)
+    model = sm.StaticModelOneBoxEst().to(DEV).train()
+    model.load_state_dict(sd)
+    step = tr.TrainStep(model, dropout_p=0.5)
+    lab = tuple(t.to(DEV) for t in labels)
+    out = step.forward_backward(pts.to(DEV), init_box.to(DEV), lab, drop_mask=drop.to(DEV) if dropout else None)
+    torch.cuda.synchronize()
+    assert rel_err(out["logits"].cpu(), oout["logits"].detach()) < 1e-4
+    assert torch.equal(out["mask"].cpu(), oout["mask"])
+    for k in ("total_loss", "mask_loss", "center_loss", "heading_class_loss", "size_class_loss",
+              "heading_residuals_normalized_loss", "size_residuals_normalized_loss"):
+        assert abs(float(out[k]) - float(ols[k])) <= 1e-4 * max(abs(float(ols[k])), 1e-3), k
+    worst = _check_grads(model.named_parameters(), step.grads.view, ograds, ograds64)
+    print("worst relative gradient error vs the fp64 oracle (ours, fp32 oracle's own):", worst)
+    for name, b in model.named_buffers():
+        if name.endswith("running_mean") or name.endswith("running_var"):
+            assert torch.allclose(b.cpu(), ostats[name], rtol=1e-4, atol=1e-6), name
+    # seg accuracy metric (tools/static_train.py:128-129)
+    cnt = int(tr.seg_accuracy_count(out["logits"], lab[0]))
+    assert cnt == int(torch.argmax(oout["logits"].detach(), 2).eq(labels[0].long()).sum())
+
+
+@pytest.mark.parametrize("kind", ["static_one", "static_two", "dynamic"])
+def test_reference_style_loop_through_autograd(kind):
+    """model.train(); out = model(...); criterion(out, ...)['total_loss'].backward() -- the reference's loop -- gives the
+    oracle's loss and parameter gradients (dropout switched off on both sides: its RNG stream is torch's own)."""
+    sd, pts, aux, gt, labels = _case(kind)
+    sd64, pts64, aux64, gt64, lab64 = _f64(sd, pts, aux, gt, labels)
+    if kind == "static_one":
+        ols, _, ograds, _ = otrain.static_one_step(sd, pts, aux, labels)
+        _, _, ograds64, _ = otrain.static_one_step(sd64, pts64, aux64, lab64)
+    elif kind == "static_two":
+        ols, _, ograds, _ = otrain.static_two_step(sd, pts, aux, gt, labels)
+        _, _, ograds64, _ = otrain.static_two_step(sd64, pts64, aux64, gt64, lab64)
+    else:
+        ols, _, ograds, _ = otrain.dynamic_step(sd, pts, aux, labels)
+        _, _, ograds64, _ = otrain.dynamic_step(sd64, pts64, aux64, lab64)
+    cls = {"static_one": sm.StaticModelOneBoxEst, "static_two": sm.StaticModelTwoBoxEst, "dynamic": dm.DynamicModel}[kind]
+    model = cls().to(DEV).train()
+    model.load_state_dict(sd)
+    model.ins_seg.dropout.p = 0.0
+    crit = {"static_one": losses.FrustumPointNetLossOneBoxEst, "static_two": losses.FrustumPointNetLossTwoBoxEst,
+            "dynamic": losses.DynamicModelLoss}[kind]()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    out = model(pts.to(DEV), aux.to(DEV), gt.to(DEV))
+    ls = crit(out, *[t.to(DEV) for t in labels])
+    opt.zero_grad()
+    ls["total_loss"].backward()
+    torch.cuda.synchronize()
+    assert abs(float(ls["total_loss"]) - float(ols["total_loss"])) <= 1e-4 * abs(float(ols["total_loss"]))
+    worst = _check_grads(model.named_parameters(), lambda p: p.grad, ograds, ograds64)
+    print(kind, "worst relative gradient error vs the fp64 oracle (ours, fp32 oracle's own):", worst)
+    opt.step()                                           # torch's optimiser consumes the gradients as usual
+
+
+def test_three_fused_steps_track_torch_adam_on_the_oracle():
+    sd, pts, init_box, gt, labels = _case("static_one")
+    model = sm.StaticModelOneBoxEst().to(DEV).train()
+    model.load_state_dict(sd)
+    step = tr.TrainStep(model, lr=1e-3, weight_decay=1e-4, dropout_p=0.0)
+    lab = tuple(t.to(DEV) for t in labels)
+    # oracle side: autograd + torch.optim.Adam on CPU
+    P = {k: v.clone() for k, v in sd.items()}
+    names = [k for k, v in P.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))]
+    leaves = [P[k].requires_grad_(True) for k in names]
+    topt = torch.optim.Adam(leaves, lr=1e-3, weight_decay=1e-4)
+    gl, ol = [], []
+    for it in range(3):
+        out = step.step(pts.to(DEV), init_box.to(DEV), lab, drop_mask=None)
+        gl.append(float(out["total_loss"]))
+        cur = {k: v.detach().clone() for k, v in P.items()}
+        ols, _, grads, stats = otrain.static_one_step(cur, pts, init_box, labels)
+        ol.append(float(ols["total_loss"]))
+        for k, leaf in zip(names, leaves):
+            leaf.grad = grads[k]
+        topt.step()
+        for k, v in stats.items():
+            P[k] = v
+    # Adam's first steps are ~ lr * sign(g): components whose sign is rounding noise move differently on the two sides, so
+    # the trajectories agree to a few percent, not to rounding
+    assert abs(gl[0] - ol[0]) <= 1e-4 * ol[0] and np.allclose(gl, ol, rtol=6e-2), (gl, ol)
+    assert gl[-1] < gl[0]                                 # and it learns
+
+
+def test_loss_modules_backward_through_autograd():
+    """The fused CUDA loss is differentiable: gradients w.r.t. logits and heads equal torch autograd on the oracle loss."""
+    from oracle import losses as olosses
+    torch.manual_seed(4)
+    bs, n = 6, 500
+    labels = _labels(bs, n, 9)
+    out = {"logits": torch.randn(bs, n, 2), "center": torch.randn(bs, 3), "heading_scores": torch.randn(bs, 12),
+           "heading_residuals_normalized": torch.randn(bs, 12) * 0.3, "size_scores": torch.randn(bs, 3),
+           "size_residuals_normalized": torch.randn(bs, 3, 3) * 0.3}
+    ref_in = {k: v.clone().requires_grad_(True) for k, v in out.items()}
+    olosses.one_box(ref_in, *labels)["total_loss"].backward()
+    dev_in = {k: v.clone().to(DEV).requires_grad_(True) for k, v in out.items()}
+    ls = losses.FrustumPointNetLossOneBoxEst()(dev_in, *[t.to(DEV) for t in labels])
+    ls["total_loss"].backward()
+    for k in out:
+        assert rel_err(dev_in[k].grad.cpu(), ref_in[k].grad) < 1e-4, k

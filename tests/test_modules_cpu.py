@@ -31,7 +31,7 @@ def test_attributes():
     assert (a.name, b.name) == ("one_box_est", "two_box_est")
     assert (a.n_classes, a.n_channel, c.n_channel, c.r, c.s) == (3, 3, 4, 2, 50)
     assert sm.NUM_OBJECT_POINT == 512 and sm.NUM_POINT == 4096 and dm.NUM_POINT == 1024 and dm.NUM_FRAME == 5
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU path"):        # training mode is CUDA-only as well
         a.train()(torch.zeros(1, 3, 8), torch.zeros(1, 7), torch.zeros(1, 7))
 
 
