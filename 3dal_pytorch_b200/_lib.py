@@ -26,12 +26,15 @@ _SIGNATURES = {
     "al3d_parse_heads": [_vp, _i, _vp, _i64] + [_vp] * 8 + [_vp],
     "al3d_decode_boxes": [_vp] * 6 + [_i64, _i, _vp, _vp, _vp],
     "al3d_twostage_retransform": [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "al3d_fc_chain": [_vp, _i, _vp],
     "al3d_crop_box_setup": [_vp, _vp, _i64, _f, _f, _vp, _vp, _vp],
     "al3d_crop_chunk_points": [],
-    "al3d_crop_build_grid": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
-    "al3d_crop_hits": [_vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp],
+    "al3d_crop_occ_words": [],
+    "al3d_crop_build_grid": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "al3d_crop_hits": [_vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp],
     "al3d_crop_scan": [_vp, _vp, _i, _i64, _vp, _i, _vp, _vp, _vp],
-    "al3d_crop_fill": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "al3d_crop_fill": [_vp, _i64, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "al3d_crop_hit_bytes": [],
     "al3d_crop_dense_mask": [_vp, _vp, _i, _vp, _vp],
     "al3d_track_points_prep": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "al3d_boxseq_prep": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -39,6 +42,7 @@ _SIGNATURES = {
     "al3d_motion_features": [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp],
     "al3d_track_labels": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "al3d_box_writeback": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "al3d_match_iou3d": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "al3d_loss_forward": [_vp, _vp, _i64] + [_vp] * 10 + [_i, _vp, _i, _vp, _vp],
     "al3d_train_ws_floats": [_i64, _i],
     "al3d_wgrad_ws_floats": [_i64, _i, _i],
@@ -96,7 +100,7 @@ def lib():
 
 # kernels launched through this binding since import (bench.py reports it as gpu_launches)
 LAUNCHES = 0
-_NO_LAUNCH = ("train_ws_floats", "wgrad_ws_floats", "tc_abort_code", "tc_status_word_host", "tc_configure", "set_debug_buffer", "crop_chunk_points")
+_NO_LAUNCH = ("train_ws_floats", "wgrad_ws_floats", "tc_abort_code", "tc_status_word_host", "tc_configure", "set_debug_buffer", "crop_chunk_points", "crop_occ_words", "crop_hit_bytes")
 
 
 def check(rc, what=""):

@@ -28,7 +28,7 @@ def detector_to_waymo(box3d):
     return b[:, [0, 1, 2, 4, 3, 5, -1]]
 
 
-def box_planes_device(boxes, device):
+def box_planes_device(boxes, device, return_inputs=False):
     """(B,7) f32 [x,y,z,l,w,h,heading] -> planes (B,6,4) f32, padded rectangles (B,6) f32, both CUDA tensors, computed by
     crop_box_setup_kernel.  Only sin / cos of the heading are evaluated here (numpy float32, like the reference:
     box_np_ops.py:163-164); tests/test_crop.py checks the result bit for bit against box_planes_host."""
@@ -42,6 +42,8 @@ def box_planes_device(boxes, device):
     with torch.cuda.device(device):
         _lib.check(_lib.lib().al3d_crop_box_setup(d_boxes.data_ptr(), d_sc.data_ptr(), n, AABB_PAD, 1e-5, planes.data_ptr(),
                                                   aabb.data_ptr(), ops._stream()), "crop_box_setup")
+    if return_inputs:
+        return planes, aabb, d_boxes, d_sc
     return planes, aabb
 
 
@@ -78,8 +80,7 @@ def box_planes_host(boxes):
 def _check_overflow(flag, what):
     code = int(flag.item())
     if code:
-        names = {1: "cell list capacity", 2: "a point lies inside more than 8 boxes", 3: "per-chunk hit capacity",
-                 4: "output capacity"}
+        names = {1: "cell list capacity", 3: "hit capacity of a chunk segment (raise hit_cap)", 4: "output capacity"}
         raise OverflowError("crop %s: %s (code %d)" % (what, names.get(code, "?"), code))
 
 
@@ -100,11 +101,13 @@ class CropPlan:
         self.box_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
         TB = self.TB = int(self.box_off[-1])
         if TB:
-            self.d_planes, self.d_aabb = box_planes_device(
-                np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 7) for b in boxes], 0), dev)
+            self.d_planes, self.d_aabb, self.d_boxes, self.d_sincos = box_planes_device(
+                np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 7) for b in boxes], 0), dev, return_inputs=True)
         else:
             self.d_planes = torch.zeros((0, 6, 4), device=dev, dtype=torch.float32)
             self.d_aabb = torch.zeros((0, 6), device=dev, dtype=torch.float32)
+            self.d_boxes = torch.zeros((0, 7), device=dev, dtype=torch.float32)
+            self.d_sincos = torch.zeros((0, 2), device=dev, dtype=torch.float32)
         self.max_boxes = max(1, max(nb) if nb else 1)
         CH = lib.al3d_crop_chunk_points()
         chunks, frame_chunk_off = [], [0]
@@ -113,13 +116,16 @@ class CropPlan:
                 chunks.append((f, first, min(CH, n_pts[f] - first), k))
             frame_chunk_off.append(len(chunks))
         self.n_chunks = len(chunks)
-        self.hit_cap = int(hit_cap or 512)          # hits per chunk of 2048 points; <= 16384
+        # hits per WARP segment (512 consecutive points) of a chunk; the synthetic Waymo-shaped frames average ~50
+        self.hit_cap = int(hit_cap or 256)
+        self.n_seg = 8                               # warps per chunk CTA (csrc/crop.cu kCropWarps)
         i32 = lambda *s: torch.empty(s, device=dev, dtype=torch.int32)
         self.d_pt_off = torch.from_numpy(pt_off).to(dev)
         self.d_box_off = torch.from_numpy(self.box_off).to(dev)
         self.d_chunks = torch.tensor(chunks, dtype=torch.int32, device=dev).reshape(-1, 4)
         self.d_fco = torch.tensor(frame_chunk_off, dtype=torch.int64, device=dev)
-        self.meta = torch.empty((max(F, 1), 4), device=dev, dtype=torch.float32)
+        self.meta = torch.empty((max(F, 1), 8), device=dev, dtype=torch.float32)
+        self.occ = torch.zeros((max(F, 1), lib.al3d_crop_occ_words()), device=dev, dtype=torch.int32)
         self.cell_start = i32(max(F, 1), GRID * GRID + 1)
         self.overflow = torch.zeros((1,), device=dev, dtype=torch.int32)
         # Size the CSR cell lists from the data: a counting run of the grid kernel (cell_cap = 0 stores nothing) leaves
@@ -133,8 +139,8 @@ class CropPlan:
             self.overflow.zero_()
         self.cell_cap = max(self.cell_cap, 1)
         self.cell_boxes = i32(max(F, 1), self.cell_cap)
-        self.hits = torch.empty((max(self.n_chunks, 1), self.hit_cap, 2), device=dev, dtype=torch.int32)
-        self.n_hits = i32(max(self.n_chunks, 1))
+        self.hits = torch.empty((max(self.n_chunks, 1), self.n_seg, self.hit_cap, lib.al3d_crop_hit_bytes() // 4), device=dev, dtype=torch.int32)
+        self.n_hits = i32(max(self.n_chunks, 1), self.n_seg)
         self.cbc = i32(max(self.n_chunks, 1), self.max_boxes)
         self.box_total = i32(max(TB, 1))
         self.offsets = torch.zeros((TB + 1,), device=dev, dtype=torch.int64)
@@ -157,13 +163,14 @@ class CropPlan:
 
     def grid(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
-        _lib.check(lib.al3d_crop_build_grid(p(self.d_aabb), p(self.d_box_off), self.F, GRID, p(self.meta), p(self.cell_start),
-                                            p(self.cell_boxes), self.cell_cap, p(self.overflow), st), "crop_build_grid")
+        _lib.check(lib.al3d_crop_build_grid(p(self.d_aabb), p(self.d_boxes), p(self.d_sincos), p(self.d_box_off), self.F, GRID,
+                                            p(self.meta), p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.occ),
+                                            p(self.overflow), st), "crop_build_grid")
 
     def hits_pass(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
         _lib.check(lib.al3d_crop_hits(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_planes), p(self.d_aabb), p(self.d_box_off), GRID, p(self.meta),
-                                      p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.d_chunks), self.n_chunks,
+                                      p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.occ), p(self.d_chunks), self.n_chunks,
                                       p(self.hits), self.hit_cap, p(self.n_hits), p(self.cbc), self.max_boxes, p(self.overflow), st),
                    "crop_hits")
 
@@ -180,7 +187,7 @@ class CropPlan:
 
     def fill(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr() if t is not None else None)
-        _lib.check(lib.al3d_crop_fill(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_box_off), p(self.d_chunks), self.n_chunks,
+        _lib.check(lib.al3d_crop_fill(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_box_off), self.F, p(self.d_chunks), self.n_chunks,
                                       p(self.hits), self.hit_cap, p(self.n_hits), p(self.cbc), self.max_boxes, p(self.offsets),
                                       p(self.d_poses), self.capacity, p(self.out_idx), p(self.out_xyz), p(self.out_glob),
                                       p(self.overflow), st), "crop_fill")
@@ -228,7 +235,7 @@ def points_in_rbbox(points, rbbox, z_axis=2, origin=(0.5, 0.5, 0.5), device="cud
     try:
         res = crop_frames([pts], [rb], device=device, want_xyz=False)
     except OverflowError:
-        res = crop_frames([pts], [rb], device=device, want_xyz=False, hit_cap=16384)
+        res = crop_frames([pts], [rb], device=device, want_xyz=False, hit_cap=512 * B)
     _check_overflow(res["overflow"], "fill")
     mask = torch.zeros((N, B), device=res["indices"].device, dtype=torch.uint8)
     _lib.check(_lib.lib().al3d_crop_dense_mask(res["indices"].data_ptr(), res["offsets"].data_ptr(), B, mask.data_ptr(),

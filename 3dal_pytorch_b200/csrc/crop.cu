@@ -23,26 +23,35 @@
 
 namespace al3d {
 
-constexpr int kCropChunk = 2048;       // points per CTA of the hits kernel
+constexpr int kCropChunk = 4096;       // points per CTA of the hits kernel
 constexpr int kCropThreads = 256;
-constexpr int kMaxHitsPerPoint = 8;    // a point inside more boxes than this raises overflow code 2 (rectangle candidates do not count)
+constexpr int kOccRes = 256;           // fine occupancy bitmap per frame: kOccRes x kOccRes bits (8 KB)
+constexpr int kOccWords = kOccRes * kOccRes / 32;
 
-struct CropGridMeta { float x0, y0, inv_x, inv_y; };
+// per frame: BEV grid origin / scale of the coarse cell lists (x0, y0, inv_x, inv_y), scale of the fine occupancy
+// bitmap (inv_fx, inv_fy) and the z range covered by any (padded) box
+struct CropGridMeta { float x0, y0, inv_x, inv_y, inv_fx, inv_fy, zmin, zmax; };
 
 // cell index of a coordinate; the SAME expression is used for points and for box rectangles, and it is
 // monotone in v, so a point inside a rectangle always lands in a cell the rectangle was registered in.
 __device__ __forceinline__ int crop_cell(float v, float v0, float inv, int G)
 {
+#ifdef CROP_CELL_FLOOR
     const float c = floorf((v - v0) * inv);
     return c < 0.f ? -1 : (c >= (float)G ? G : (int)c);
+#else
+    // float -> int with round-down saturates at the int range; clamp to [-1, G] ("left of / right of the grid")
+    return max(-1, min(__float2int_rd((v - v0) * inv), G));
+#endif
 }
 
 __global__ void __launch_bounds__(kCropThreads)
-crop_grid_kernel(const float *__restrict__ aabb, const int64_t *__restrict__ box_off, int G, CropGridMeta *__restrict__ meta,
-                 int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_boxes, int cell_cap, int32_t *__restrict__ overflow)
+crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes, const float *__restrict__ sincos,
+                 const int64_t *__restrict__ box_off, int G, CropGridMeta *__restrict__ meta, int32_t *__restrict__ cell_start,
+                 int32_t *__restrict__ cell_boxes, int cell_cap, uint32_t *__restrict__ occ, int32_t *__restrict__ overflow)
 {
-    extern __shared__ int32_t s_cnt[];            // G*G counts -> exclusive offsets; then G*G fill cursors
-    __shared__ float red[4][kCropThreads / 32];
+    extern __shared__ int32_t s_cnt[];            // G*G counts -> exclusive offsets; then G*G fill cursors; then the occupancy bitmap
+    __shared__ float red[6][kCropThreads / 32];
     __shared__ int32_t s_warp[kCropThreads / 32];
     const int f = blockIdx.x;
     const int64_t b0 = box_off[f];
@@ -50,32 +59,64 @@ crop_grid_kernel(const float *__restrict__ aabb, const int64_t *__restrict__ box
     const int cells = G * G;
     int32_t *s_cur = s_cnt + cells;
     // ---- extent of the boxes of this frame
-    float xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
+    float xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY, zmin = INFINITY, zmax = -INFINITY;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const float *a = aabb + (b0 + b) * 6;
-        xmin = fminf(xmin, a[0]); ymin = fminf(ymin, a[1]);
-        xmax = fmaxf(xmax, a[3]); ymax = fmaxf(ymax, a[4]);
+        xmin = fminf(xmin, a[0]); ymin = fminf(ymin, a[1]); zmin = fminf(zmin, a[2]);
+        xmax = fmaxf(xmax, a[3]); ymax = fmaxf(ymax, a[4]); zmax = fmaxf(zmax, a[5]);
     }
     for (int o = 16; o > 0; o >>= 1) {
         xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
         xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o)); zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) { red[0][wid] = xmin; red[1][wid] = ymin; red[2][wid] = xmax; red[3][wid] = ymax; }
-    for (int c = threadIdx.x; c < 2 * cells; c += blockDim.x) s_cnt[c] = 0;
+    if (lane == 0) { red[0][wid] = xmin; red[1][wid] = ymin; red[2][wid] = xmax; red[3][wid] = ymax; red[4][wid] = zmin; red[5][wid] = zmax; }
+    uint32_t *s_occ = reinterpret_cast<uint32_t *>(s_cnt + 2 * cells);
+    for (int c = threadIdx.x; c < 2 * cells + kOccWords; c += blockDim.x) s_cnt[c] = 0;
     __syncthreads();
     for (int w = 0; w < kCropThreads / 32; ++w) {
         xmin = fminf(xmin, red[0][w]); ymin = fminf(ymin, red[1][w]);
         xmax = fmaxf(xmax, red[2][w]); ymax = fmaxf(ymax, red[3][w]);
+        zmin = fminf(zmin, red[4][w]); zmax = fmaxf(zmax, red[5][w]);
     }
     CropGridMeta m;
-    if (B == 0 || !(xmax >= xmin) || !(ymax >= ymin)) { m.x0 = 0.f; m.y0 = 0.f; m.inv_x = 0.f; m.inv_y = 0.f; }
-    else {
+    float fsx = 0.f, fsy = 0.f;                                       // fine cell size
+    if (B == 0 || !(xmax >= xmin) || !(ymax >= ymin)) {
+        m.x0 = 0.f; m.y0 = 0.f; m.inv_x = 0.f; m.inv_y = 0.f; m.inv_fx = 0.f; m.inv_fy = 0.f; m.zmin = INFINITY; m.zmax = -INFINITY;
+    } else {
+        const float ex = fmaxf(xmax - xmin, 1e-3f), ey = fmaxf(ymax - ymin, 1e-3f);
         m.x0 = xmin; m.y0 = ymin;
-        m.inv_x = (float)G / fmaxf(xmax - xmin, 1e-3f) * 0.999f;     // keep xmax inside the last cell
-        m.inv_y = (float)G / fmaxf(ymax - ymin, 1e-3f) * 0.999f;
+        m.inv_x = (float)G / ex * 0.999f;                            // keep xmax inside the last cell
+        m.inv_y = (float)G / ey * 0.999f;
+        m.inv_fx = (float)kOccRes / ex * 0.999f;
+        m.inv_fy = (float)kOccRes / ey * 0.999f;
+        m.zmin = zmin; m.zmax = zmax;
+        fsx = 1.f / m.inv_fx; fsy = 1.f / m.inv_fy;
     }
     if (threadIdx.x == 0) meta[f] = m;
+    // ---- fine occupancy bitmap: a bit is set if the cell can contain a point of some box.  Conservative: the cell
+    //      centre lies inside the box footprint grown by the cell's half diagonal plus the rectangle padding (which
+    //      already exceeds the rounding slack of the exact test by orders of magnitude) plus 1 cm.
+    if (occ != nullptr && m.inv_fx > 0.f) {
+        const float hd = 0.5f * sqrtf(fsx * fsx + fsy * fsy);
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            const float *a = aabb + (b0 + b) * 6;
+            const float *bx = boxes + (b0 + b) * 7;
+            const float sn = sincos[(b0 + b) * 2], cs = sincos[(b0 + b) * 2 + 1];
+            const float grow = hd + 0.5f * ((a[3] - a[0]) - (fabsf(bx[3] * cs) + fabsf(bx[4] * sn))) + 0.01f;   // half diagonal + rectangle pad + 1 cm
+            const float hl = 0.5f * bx[3] + fmaxf(grow, hd + 0.06f), hw = 0.5f * bx[4] + fmaxf(grow, hd + 0.06f);
+            int cx0 = max(crop_cell(a[0], m.x0, m.inv_fx, kOccRes), 0), cx1 = min(crop_cell(a[3], m.x0, m.inv_fx, kOccRes), kOccRes - 1);
+            int cy0 = max(crop_cell(a[1], m.y0, m.inv_fy, kOccRes), 0), cy1 = min(crop_cell(a[4], m.y0, m.inv_fy, kOccRes), kOccRes - 1);
+            for (int cy = cy0; cy <= cy1; ++cy)
+                for (int cx = cx0; cx <= cx1; ++cx) {
+                    const float dx = m.x0 + ((float)cx + 0.5f) * fsx - bx[0], dy = m.y0 + ((float)cy + 0.5f) * fsy - bx[1];
+                    // world = [[c, s], [-s, c]] local  (rotation_3d_in_axis)  ->  local = [[c, -s], [s, c]] world
+                    const float lx = dx * cs - dy * sn, ly = dx * sn + dy * cs;
+                    if (fabsf(lx) <= hl && fabsf(ly) <= hw) atomicOr(&s_occ[(cy * kOccRes + cx) >> 5], 1u << ((cy * kOccRes + cx) & 31));
+                }
+        }
+    }
     // ---- pass 0: every box adds itself to the counters of the cells its rectangle covers (integer adds commute);
     //      pass 1: it appends its id through a per-cell cursor; the short lists are sorted afterwards, so the
     //      final cell -> box lists are in ascending box order whatever the order of the atomics.
@@ -119,6 +160,7 @@ crop_grid_kernel(const float *__restrict__ aabb, const int64_t *__restrict__ box
             for (int c = threadIdx.x; c < cells; c += blockDim.x) cell_start[(int64_t)f * (cells + 1) + c] = s_cnt[c];
         }
     }
+    if (occ != nullptr) for (int w = threadIdx.x; w < kOccWords; w += blockDim.x) occ[(int64_t)f * kOccWords + w] = s_occ[w];
     // ---- sort every cell's list (a handful of entries): insertion sort by one thread per cell
     __threadfence_block();
     for (int c = threadIdx.x; c < cells; c += blockDim.x) {
@@ -201,32 +243,44 @@ __device__ __forceinline__ bool crop_inside(float px, float py, float pz, const 
 
 struct CropChunk { int32_t frame; int32_t first_pt; int32_t n_pts; int32_t chunk_in_frame; };
 
+// one hit: point index in its frame, box | rank << 16 (rank among the chunk's hits of that box).  (Carrying the point's
+// xyz in the record as well was measured: +60 us in the hits pass for the wider stores, nothing gained in the fill.)
+struct __align__(8) CropHit { int32_t idx, box_rank; };          // one 8-byte store per hit
+static_assert(sizeof(CropHit) == 8, "CropHit");
 constexpr int kCropWarps = kCropThreads / 32;
 constexpr int kCropWarpPts = kCropChunk / kCropWarps;     // consecutive points owned by one warp
-constexpr int kCropQueue = 320;                           // per-warp candidate queue (>= 31 + 32 * kMaxHitsPerPoint)
-constexpr int kCropLook = 2;                              // cell-list entries fetched ahead per point
+constexpr int kCropIter = 128;                            // points per warp iteration: 4 consecutive points per lane
+constexpr int kCropQueue = 256;                           // per-warp candidate queue (power of two, >= 31 left over + kCropIter new)
 
-__global__ void __launch_bounds__(kCropThreads)
+// streaming load (the points are read once: do not let them evict the hit lists / counters from L2)
+__device__ __forceinline__ float4 ldg_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+
+#ifndef CROP_MINB
+#define CROP_MINB 4          // measured (profiles/r2_crop_variants.txt): 4 -> 0.419 ms, 3 -> 0.429, 2 -> 0.547, 1 -> 0.557 (occupancy)
+#endif
+__global__ void __launch_bounds__(kCropThreads, CROP_MINB)
 crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
                  const float *__restrict__ planes, const float *__restrict__ aabb, const int64_t *__restrict__ box_off, int G,
                  const CropGridMeta *__restrict__ meta, const int32_t *__restrict__ cell_start,
-                 const int32_t *__restrict__ cell_boxes, int cell_cap, const CropChunk *__restrict__ chunks,
-                 int2 *__restrict__ hits, int hit_cap, int32_t *__restrict__ n_hits, int32_t *__restrict__ chunk_box_count,
-                 int max_boxes, int rank_boxes, int32_t *__restrict__ overflow)
+                 const int32_t *__restrict__ cell_boxes, int cell_cap, const uint32_t *__restrict__ occ,
+                 const CropChunk *__restrict__ chunks, CropHit *__restrict__ hits, int hit_cap, int32_t *__restrict__ n_hits,
+                 int32_t *__restrict__ chunk_box_count, int max_boxes, int rank_boxes, int32_t *__restrict__ overflow)
 {
-    // Each warp owns kCropWarpPts CONSECUTIVE points and walks them 32 at a time.  A lane looks up the boxes
-    // registered in its point's BEV cell and keeps those whose padded bounding box contains the point; these
-    // (point, box) pairs go, in point order, into a per-warp queue.  Whenever 32 pairs are queued the warp runs
-    // the exact six-plane predicate on them in lock-step (no divergence) and appends the hits, still in point
-    // order, to its staging list.  One block-wide prefix over the eight warp totals then places every warp's
-    // list in the chunk's ordered hit list.  No block barrier inside the point loop.
+    // Each warp owns kCropWarpPts CONSECUTIVE points and streams them 128 at a time (four consecutive points per lane,
+    // three 16-byte loads).  Stage 1 is a cheap filter: z range of the frame's boxes, then one bit of the frame's fine
+    // occupancy bitmap (is there any box footprint near this BEV cell?).  ~85 % of the points end here.  The survivors
+    // are compacted, in point order, into a per-warp queue.  Stage 2 takes DENSE batches of 32 queued points -- every
+    // lane busy -- looks up the boxes registered in the point's coarse BEV cell, rejects by the padded rectangle and
+    // runs the exact six-plane predicate; the hits (point, box) go, in point order and ascending box order, to the
+    // warp's staging list.  No block barrier inside the point loop; no limit on the number of boxes a point is in.
+    // The hit list of a chunk is kept as eight per-warp segments of hit_cap entries in global memory (L2-resident while
+    // the chunk is processed): hits[(chunk * 8 + warp) * hit_cap + i], n_hits[chunk * 8 + warp].
     extern __shared__ int32_t s_dyn[];
     int32_t *s_box_cnt = s_dyn;                                        // per-box hit counters (max_boxes)
-    int2 *s_queue = reinterpret_cast<int2 *>(s_dyn + ((max_boxes + 1) & ~1));   // kCropWarps x kCropQueue
-    int2 *s_stage = s_queue + kCropWarps * kCropQueue;                  // kCropWarps x stage_cap
+    float4 *s_queue = reinterpret_cast<float4 *>(s_dyn + ((max_boxes + 3) & ~3));   // kCropWarps x kCropQueue
     __shared__ int warp_total[kCropWarps];
-    const int stage_cap = min(hit_cap, kCropWarpPts * kMaxHitsPerPoint); // per warp (its worst case); the chunk total is capped at hit_cap
-    int32_t *s_wcnt = reinterpret_cast<int32_t *>(s_stage + (size_t)kCropWarps * stage_cap);   // kCropWarps x rank_boxes per-warp box counts
+    const int stage_cap = hit_cap;
+    int32_t *s_wcnt = reinterpret_cast<int32_t *>(s_queue + kCropWarps * kCropQueue);   // kCropWarps x rank_boxes per-warp box counts
     const CropChunk ck = chunks[blockIdx.x];
     const int f = ck.frame;
     const int64_t b0 = box_off[f];
@@ -235,180 +289,158 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     const int cells = G * G;
     const int32_t *cs = cell_start + (int64_t)f * (cells + 1);
     const int32_t *cb = cell_boxes + (int64_t)f * cell_cap;
+    const uint32_t *oc = occ + (int64_t)f * kOccWords;
     const float *pts = points + (pt_off[f] + ck.first_pt) * pt_stride;
     const float4 *pl = reinterpret_cast<const float4 *>(planes) + b0 * 6;
     const float2 *bb = reinterpret_cast<const float2 *>(aabb) + b0 * 3;
-    int2 *my_hits = hits + (int64_t)blockIdx.x * hit_cap;      // .x = point index in frame, .y = box | rank << 16
     for (int b = threadIdx.x; b < B; b += blockDim.x) s_box_cnt[b] = 0;
     const bool par_rank = B <= rank_boxes;                            // ranking by all warps in parallel (else one warp, serially)
     if (par_rank) for (int t = threadIdx.x; t < kCropWarps * rank_boxes; t += blockDim.x) s_wcnt[t] = 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int2 *queue = s_queue + wid * kCropQueue;
-    int2 *stage = s_stage + (size_t)wid * stage_cap;
+    float4 *queue = s_queue + wid * kCropQueue;
+    CropHit *stage = hits + ((int64_t)blockIdx.x * kCropWarps + wid) * hit_cap;
     int wcount = 0, qhead = 0, qcount = 0;
+    const bool vec = pt_stride == 3 && (reinterpret_cast<uintptr_t>(pts) & 15) == 0;
+    const bool grid_ok = m.inv_fx > 0.f;
 
-    // exact test of up to 32 queued pairs (one per lane), hits appended in queue order
+    // stage 2 on up to 32 queued points (one per lane): exact tests, hits appended in (point, box) order
     auto drain = [&](int n) {
-        bool hit = false;
-        int2 e = make_int2(0, 0);
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        int e0 = 0, len = 0, cnt = 0;
+        unsigned mask = 0;
+        bool all_boxes = false;
         if (lane < n) {
-            int at = qhead + lane;
-            if (at >= kCropQueue) at -= kCropQueue;
-            e = queue[at];
-            if (e.y & (1 << 30)) { hit = true; e.y &= ~(1 << 30); }     // NaN point: already decided
-            else {
-                const float *q = pts + (int64_t)e.x * pt_stride;
-                hit = crop_inside(__ldg(q), __ldg(q + 1), __ldg(q + 2), pl + e.y * 6);
+            e = queue[(qhead + lane) & (kCropQueue - 1)];
+            if (e.x != e.x || e.y != e.y || e.z != e.z) {
+                // NaN never satisfies `sign >= 0`: the reference reports such a point inside every box it is tested against
+                all_boxes = true; len = B;
+            } else {
+                const int cx = crop_cell(e.x, m.x0, m.inv_x, G), cy = crop_cell(e.y, m.y0, m.inv_y, G);
+                if (cx >= 0 && cx < G && cy >= 0 && cy < G) {
+                    e0 = __ldg(cs + cy * G + cx);
+                    len = min(__ldg(cs + cy * G + cx + 1), cell_cap) - e0;
+                }
+            }
+            // pass 1: count (and, for lists of up to 32 entries, remember which entries hit)
+            for (int k = 0; k < len; ++k) {
+                const int b = all_boxes ? k : __ldg(cb + e0 + k);
+                bool hit;
+                if (all_boxes) hit = crop_inside(e.x, e.y, e.z, pl + b * 6);
+                else {
+                    const float2 lo = __ldg(bb + b * 3), mid = __ldg(bb + b * 3 + 1), hi = __ldg(bb + b * 3 + 2);
+                    // aabb = [xmin ymin | zmin xmax | ymax zmax], padded: never rejects a point the exact test accepts
+                    hit = e.x >= lo.x && e.y >= lo.y && e.z >= mid.x && e.x <= mid.y && e.y <= hi.x && e.z <= hi.y &&
+                          crop_inside(e.x, e.y, e.z, pl + b * 6);
+                }
+                if (hit) { ++cnt; if (k < 32) mask |= 1u << k; }
             }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) {
-            const int at = wcount + __popc(bal & ((1u << lane) - 1u));
-            if (at < stage_cap) stage[at] = make_int2(ck.first_pt + e.x, e.y);
-            else atomicExch(overflow, 3);
+        int incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        // a batch that does not fit is dropped as a whole (warp-uniform decision): the segment never has holes
+        const bool fits = wcount + total <= stage_cap;
+        if (!fits && lane == 0) atomicExch(overflow, 3);
+        if (cnt > 0 && fits) {
+            int at = wcount + incl - cnt;
+            const int pidx = ck.first_pt + __float_as_int(e.w);
+            if (len <= 32) {
+                while (mask) {
+                    const int k = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    stage[at++] = CropHit{pidx, all_boxes ? k : __ldg(cb + e0 + k)};
+                }
+            } else {
+                // long list (heavily overlapping boxes, or a NaN point in a frame with many boxes): walk it again
+                for (int k = 0; k < len; ++k) {
+                    const int b = all_boxes ? k : __ldg(cb + e0 + k);
+                    if (crop_inside(e.x, e.y, e.z, pl + b * 6)) stage[at++] = CropHit{pidx, b};
+                }
+            }
         }
-        wcount += __popc(bal);
-        qhead += n; if (qhead >= kCropQueue) qhead -= kCropQueue;
+        if (fits) wcount += total;
+        qhead = (qhead + n) & (kCropQueue - 1);
         qcount -= n;
+        __syncwarp();
     };
 
     const int w_lo = wid * kCropWarpPts, w_hi = min(w_lo + kCropWarpPts, ck.n_pts);
-    constexpr int U = 4;                       // points per lane per outer iteration: U independent load chains in flight
-    for (int i0 = w_lo; i0 < w_hi; i0 += 32 * U) {
-        float px[U], py[U], pz[U];
-        int e0[U], e1[U];
+    // (Issuing the next iteration's loads before filtering this one was measured: slower -- the extra registers cost an
+    // occupancy step, and with four CTAs per SM other warps already cover the load latency.)
+    for (int base = w_lo; base < w_hi; base += kCropIter) {
+        const int i0 = base + lane * 4;
+        float px[4], py[4], pz[4];
+        if (vec && i0 + 3 < w_hi) {
+            const float4 a = ldg_stream4(pts + (int64_t)i0 * 3), b = ldg_stream4(pts + (int64_t)i0 * 3 + 4), c = ldg_stream4(pts + (int64_t)i0 * 3 + 8);
+            px[0] = a.x; py[0] = a.y; pz[0] = a.z; px[1] = a.w; py[1] = b.x; pz[1] = b.y;
+            px[2] = b.z; py[2] = b.w; pz[2] = c.x; px[3] = c.y; py[3] = c.z; pz[3] = c.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const int i = i0 + k * 32 + lane;
-            px[k] = py[k] = pz[k] = 0.f;
-            if (i < w_hi) {
-                px[k] = __ldg(pts + i * pt_stride); py[k] = __ldg(pts + i * pt_stride + 1); pz[k] = __ldg(pts + i * pt_stride + 2);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const int i = i0 + k * 32 + lane;
-            e0[k] = e1[k] = 0;
-            const bool isnan_k = (px[k] != px[k] || py[k] != py[k] || pz[k] != pz[k]);
-            if (i < w_hi && !isnan_k) {
-                const int cx = crop_cell(px[k], m.x0, m.inv_x, G), cy = crop_cell(py[k], m.y0, m.inv_y, G);
-                if (cx >= 0 && cx < G && cy >= 0 && cy < G && m.inv_x > 0.f) {
-                    const int c = cy * G + cx;
-                    e0[k] = __ldg(cs + c);
-                    e1[k] = min(__ldg(cs + c + 1), cell_cap);
+            for (int j = 0; j < 4; ++j) {
+                px[j] = py[j] = pz[j] = 0.f;
+                if (i0 + j < w_hi) {
+                    const float *q = pts + (int64_t)(i0 + j) * pt_stride;
+                    px[j] = __ldg(q); py[j] = __ldg(q + 1); pz[j] = __ldg(q + 2);
                 }
             }
         }
-        // Candidate list of one point (kMaxHitsPerPoint slots).  When it fills up -- many overlapping padded rectangles -- the
-        // stored candidates are put through the exact test right away and only the real hits stay (flagged as decided), so
-        // the limit applies to the boxes a point is INSIDE, as the name says, not to its rectangle candidates.
-        auto push_cand = [&](int (&cand)[kMaxHitsPerPoint], int &nc, int b, float x, float y, float z) {
-            if (nc == kMaxHitsPerPoint) {
-                int m = 0;
-                for (int q = 0; q < kMaxHitsPerPoint; ++q) {
-                    const int cb = cand[q];
-                    if ((cb & (1 << 30)) || crop_inside(x, y, z, pl + (cb & 0xFFFF) * 6)) cand[m++] = (cb & 0xFFFF) | (1 << 30);
-                }
-                nc = m;
-                if (nc == kMaxHitsPerPoint) { if (crop_inside(x, y, z, pl + b * 6)) atomicExch(overflow, 2); return; }
-            }
-            cand[nc++] = b;
-        };
-        // the first kCropLook entries of every point's cell list: U * kCropLook independent loads, one round trip
-        // (the per-point loop below used to walk its list one dependent load pair at a time)
-        int bj[U][kCropLook];
+        unsigned pass = 0;
 #pragma unroll
-        for (int k = 0; k < U; ++k)
-#pragma unroll
-            for (int j = 0; j < kCropLook; ++j) bj[k][j] = (e0[k] + j < e1[k]) ? __ldg(cb + e0[k] + j) : -1;
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const int i = i0 + k * 32 + lane;
-            int cand[kMaxHitsPerPoint];
-            int nc = 0;
-            if (i < w_hi) {
-                if (px[k] != px[k] || py[k] != py[k] || pz[k] != pz[k]) {
-                    // NaN never satisfies `sign >= 0`: the reference reports such a point inside every box.  Rare:
-                    // decided in place, flagged so that the queue does not test it again.
-                    for (int b = 0; b < B; ++b)
-                        if (crop_inside(px[k], py[k], pz[k], pl + b * 6)) {
-                            if (nc < kMaxHitsPerPoint) cand[nc++] = b | (1 << 30); else atomicExch(overflow, 2);
-                        }
-                } else {
-                    // padded boxes of the prefetched entries: their loads are independent of each other
-                    float2 lo[kCropLook], mid[kCropLook], hi[kCropLook];
-#pragma unroll
-                    for (int j = 0; j < kCropLook; ++j) {
-                        const int b = max(bj[k][j], 0);
-                        lo[j] = __ldg(bb + b * 3); mid[j] = __ldg(bb + b * 3 + 1); hi[j] = __ldg(bb + b * 3 + 2);
-                    }
-#pragma unroll
-                    for (int j = 0; j < kCropLook; ++j)
-                        if (bj[k][j] >= 0 && px[k] >= lo[j].x && py[k] >= lo[j].y && pz[k] >= mid[j].x && px[k] <= mid[j].y &&
-                            py[k] <= hi[j].x && pz[k] <= hi[j].y) {
-                            push_cand(cand, nc, bj[k][j], px[k], py[k], pz[k]);
-                        }
-                    for (int e = e0[k] + kCropLook; e < e1[k]; ++e) {               // longer lists (rare): the rest, one at a time
-                        const int b = __ldg(cb + e);
-                        const float2 lo = __ldg(bb + b * 3), mid = __ldg(bb + b * 3 + 1), hi = __ldg(bb + b * 3 + 2);
-                        // aabb = [xmin ymin | zmin xmax | ymax zmax], padded: never rejects a point the exact test accepts
-                        if (px[k] >= lo.x && py[k] >= lo.y && pz[k] >= mid.x && px[k] <= mid.y && py[k] <= hi.x && pz[k] <= hi.y) {
-                            push_cand(cand, nc, b, px[k], py[k], pz[k]);
-                        }
+        for (int j = 0; j < 4; ++j) {
+            bool ok = false;
+            if (i0 + j < w_hi) {
+                if (px[j] != px[j] || py[j] != py[j] || pz[j] != pz[j]) ok = B > 0;            // NaN: inside every box
+                else if (grid_ok && pz[j] >= m.zmin && pz[j] <= m.zmax) {
+                    const int cx = crop_cell(px[j], m.x0, m.inv_fx, kOccRes), cy = crop_cell(py[j], m.y0, m.inv_fy, kOccRes);
+                    if (cx >= 0 && cx < kOccRes && cy >= 0 && cy < kOccRes) {
+                        const int bit = cy * kOccRes + cx;
+                        ok = (__ldg(oc + (bit >> 5)) >> (bit & 31)) & 1u;
                     }
                 }
             }
-            const unsigned any = __ballot_sync(0xffffffffu, nc > 0);
-            if (any == 0) continue;                                    // the common case: no candidate at all
-            int incl = nc;
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            const int at = qhead + qcount + incl - nc;
-#pragma unroll
-            for (int j = 0; j < kMaxHitsPerPoint; ++j)
-                if (j < nc) {
-                    int a2 = at + j;
-                    while (a2 >= kCropQueue) a2 -= kCropQueue;
-                    queue[a2] = make_int2(i, cand[j]);
-                }
-            qcount += __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();
-            while (qcount >= 32) drain(32);
+            pass |= ok ? (1u << j) : 0u;
         }
+        const int cnt = __popc(pass);
+        int incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        int at = qhead + qcount + incl - cnt;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (pass & (1u << j)) queue[(at++) & (kCropQueue - 1)] = make_float4(px[j], py[j], pz[j], __int_as_float(i0 + j));
+        qcount += total;
+        __syncwarp();
+        while (qcount >= 32) drain(32);
     }
     __syncwarp();
     while (qcount > 0) drain(min(qcount, 32));
-    if (wcount > stage_cap) wcount = stage_cap;
-    if (lane == 0) warp_total[wid] = wcount;
+    if (lane == 0) { warp_total[wid] = wcount; n_hits[(int64_t)blockIdx.x * kCropWarps + wid] = wcount; }
+    __syncwarp();
     // ---- rank of every hit among the hits of the same box in this chunk (point order).
-    //      Parallel form: every warp first ranks its own (ordered) list against its own per-box counters -- 32 hits at a
+    //      Parallel form: every warp first ranks its own (ordered) segment against its own per-box counters -- 32 hits at a
     //      time, equal boxes inside a group ranked by lane -- then adds the counts of the warps before it.
     if (par_rank) {
         int32_t *mine = s_wcnt + wid * rank_boxes;
         for (int h0 = 0; h0 < wcount; h0 += 32) {
             const int h = h0 + lane;
             const bool act = h < wcount;
-            const int2 e = act ? stage[h] : make_int2(0, -1 - lane);
-            const unsigned same = __match_any_sync(0xffffffffu, e.y);
-            if (act) stage[h] = make_int2(e.x, e.y | ((mine[e.y] + __popc(same & ((1u << lane) - 1u))) << 16));
+            const int box = act ? stage[h].box_rank : -1 - lane;
+            const unsigned same = __match_any_sync(0xffffffffu, box);
+            if (act) stage[h].box_rank = box | ((mine[box] + __popc(same & ((1u << lane) - 1u))) << 16);
             __syncwarp();
-            if (act && (same >> lane) == 1u) mine[e.y] += __popc(same);          // highest lane of each group updates
+            if (act && (same >> lane) == 1u) mine[box] += __popc(same);          // highest lane of each group updates
             __syncwarp();
         }
-    }
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int w = 0; w < kCropWarps; ++w) { if (w < wid) before += warp_total[w]; total += warp_total[w]; }
-    if (before + wcount > hit_cap) atomicExch(overflow, 3);
-    total = min(total, hit_cap);
-    if (threadIdx.x == 0) n_hits[blockIdx.x] = total;
-    if (par_rank) {
-        for (int h = lane; h < wcount; h += 32) {
-            const int2 e = stage[h];
-            const int box = e.y & 0xFFFF;
-            int prefix = 0;
-            for (int w = 0; w < wid; ++w) prefix += s_wcnt[w * rank_boxes + box];
-            if (before + h < hit_cap) my_hits[before + h] = make_int2(e.x, e.y + (prefix << 16));
-        }
+        __syncthreads();
+        if (wid > 0)
+            for (int h = lane; h < wcount; h += 32) {
+                const int br = stage[h].box_rank;
+                const int box = br & 0xFFFF;
+                int prefix = 0;
+                for (int w = 0; w < wid; ++w) prefix += s_wcnt[w * rank_boxes + box];
+                if (prefix) stage[h].box_rank = br + (prefix << 16);
+            }
         for (int b = threadIdx.x; b < B; b += blockDim.x) {
             int sum = 0;
 #pragma unroll
@@ -417,34 +449,31 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
         }
         return;
     }
-    // Serial form (frames with more boxes than the per-warp counter table holds): one warp walks the whole ordered list.
+    // Serial form (frames with more boxes than the per-warp counter table holds): one warp walks the segments in order.
+    __threadfence_block();
+    __syncthreads();
     if (wid == 0) {
-        int g0 = 0;                                                    // global position of the current warp list
         for (int w = 0; w < kCropWarps; ++w) {
             const int cnt = warp_total[w];
-            int2 *l = s_stage + (size_t)w * stage_cap;
+            CropHit *l = hits + ((int64_t)blockIdx.x * kCropWarps + w) * hit_cap;
             for (int h0 = 0; h0 < cnt; h0 += 32) {
                 const int h = h0 + lane;
                 const bool act = h < cnt;
-                const int2 e = act ? l[h] : make_int2(0, -1 - lane);
-                const unsigned same = __match_any_sync(0xffffffffu, e.y);
-                if (act) {
-                    const int rank = s_box_cnt[e.y] + __popc(same & ((1u << lane) - 1u));
-                    if (g0 + h < hit_cap) my_hits[g0 + h] = make_int2(e.x, e.y | (rank << 16));
-                }
+                const int box = act ? l[h].box_rank : -1 - lane;
+                const unsigned same = __match_any_sync(0xffffffffu, box);
+                if (act) l[h].box_rank = box | ((s_box_cnt[box] + __popc(same & ((1u << lane) - 1u))) << 16);
                 __syncwarp();
-                if (act && (same >> lane) == 1u) s_box_cnt[e.y] += __popc(same);  // highest lane of each group updates
+                if (act && (same >> lane) == 1u) s_box_cnt[box] += __popc(same);  // highest lane of each group updates
                 __syncwarp();
             }
-            g0 += cnt;
         }
     }
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x) chunk_box_count[(int64_t)blockIdx.x * max_boxes + b] = s_box_cnt[b];
 }
 
-// per frame: for every box an exclusive scan over the frame's chunks; box totals.  One WARP per box: the lanes
-// take 32 consecutive chunks at a time (shuffle scan), so a frame's ~90 chunks cost three round trips, not ninety.
+// per frame: exclusive scan over the frame's chunks for every box, and the box totals.  One thread per box (a warp reads
+// 32 consecutive boxes of a chunk's row: coalesced), the frame's chunks walked in order.
 __global__ void crop_scan_kernel(const int64_t *__restrict__ box_off, const int64_t *__restrict__ frame_chunk_off,
                                  int32_t *__restrict__ chunk_box_count, int max_boxes, int32_t *__restrict__ box_total)
 {
@@ -452,70 +481,104 @@ __global__ void crop_scan_kernel(const int64_t *__restrict__ box_off, const int6
     const int64_t b0 = box_off[f];
     const int B = (int)(box_off[f + 1] - b0);
     const int64_t c0 = frame_chunk_off[f], c1 = frame_chunk_off[f + 1];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    for (int b = blockIdx.y * n_warps + wid; b < B; b += gridDim.y * n_warps) {
+    for (int b = blockIdx.y * blockDim.x + threadIdx.x; b < B; b += gridDim.y * blockDim.x) {
         int run = 0;
-        for (int64_t cb = c0; cb < c1; cb += 32) {
-            const int64_t c = cb + lane;
-            const int v = c < c1 ? chunk_box_count[c * max_boxes + b] : 0;
-            int incl = v;
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (c < c1) chunk_box_count[c * max_boxes + b] = run + incl - v;
-            run += __shfl_sync(0xffffffffu, incl, 31);
+        int64_t c = c0;
+        for (; c + 4 <= c1; c += 4) {                      // four independent loads in flight
+            int32_t *p = chunk_box_count + c * max_boxes + b;
+            const int v0 = p[0], v1 = p[max_boxes], v2 = p[2 * (int64_t)max_boxes], v3 = p[3 * (int64_t)max_boxes];
+            p[0] = run; p[max_boxes] = run + v0; p[2 * (int64_t)max_boxes] = run + v0 + v1; p[3 * (int64_t)max_boxes] = run + v0 + v1 + v2;
+            run += v0 + v1 + v2 + v3;
         }
-        if (lane == 0) box_total[b0 + b] = run;
+        for (; c < c1; ++c) {
+            int32_t *p = chunk_box_count + c * max_boxes + b;
+            const int v = *p;
+            *p = run;
+            run += v;
+        }
+        box_total[b0 + b] = run;
     }
 }
 
-// global exclusive offsets over all boxes of all frames (single CTA)
+// global exclusive offsets over all boxes of all frames.  CTA k owns the 1024 boxes [1024 k, 1024 k + 1024): it sums the
+// totals in front of its tile itself (n_boxes is tens of thousands: a few coalesced loads per thread) and scans its tile.
 __global__ void __launch_bounds__(1024)
 crop_offsets_kernel(const int32_t *__restrict__ box_total, int64_t n_boxes, int64_t *__restrict__ offsets)
 {
-    __shared__ long long part[1024];
-    const int64_t per = (n_boxes + blockDim.x - 1) / blockDim.x;
-    const int64_t lo = (int64_t)threadIdx.x * per, hi = min(lo + per, n_boxes);
-    long long sum = 0;
-    for (int64_t i = lo; i < hi; ++i) sum += box_total[i];
-    part[threadIdx.x] = sum;
+    __shared__ long long red[32];
+    __shared__ long long warp_incl[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * 1024;
+    long long before = 0;
+    for (int64_t i = threadIdx.x; i < t0; i += 1024) before += box_total[i];
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) red[w] = before;
+    const int64_t i = t0 + threadIdx.x;
+    const long long v = i < n_boxes ? box_total[i] : 0;
+    long long incl = v;
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_incl[w] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        long long run = 0;
-        for (int t = 0; t < (int)blockDim.x; ++t) { const long long v = part[t]; part[t] = run; run += v; }
-        offsets[n_boxes] = run;
-    }
-    __syncthreads();
-    long long run = part[threadIdx.x];
-    for (int64_t i = lo; i < hi; ++i) { offsets[i] = run; run += box_total[i]; }
+    long long base = 0;
+    for (int k = 0; k < 32; ++k) base += red[k];                 // fixed order
+    for (int k = 0; k < w; ++k) base += warp_incl[k];
+    if (i < n_boxes) offsets[i] = base + incl - v;
+    if (i == n_boxes - 1) offsets[n_boxes] = base + incl;
+    if (n_boxes == 0 && blockIdx.x == 0 && threadIdx.x == 0) offsets[0] = 0;
 }
 
 __global__ void __launch_bounds__(kCropThreads)
-crop_fill_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
-                 const int64_t *__restrict__ box_off, const CropChunk *__restrict__ chunks, const int2 *__restrict__ hits,
+crop_fill_kernel(const int64_t *__restrict__ box_off, const CropChunk *__restrict__ chunks, const CropHit *__restrict__ hits,
                  int hit_cap, const int32_t *__restrict__ n_hits, const int32_t *__restrict__ chunk_box_count, int max_boxes,
-                 const int64_t *__restrict__ offsets, const double *__restrict__ poses, int64_t capacity,
-                 int32_t *__restrict__ out_idx, float *__restrict__ out_xyz, double *__restrict__ out_xyz_global,
-                 int32_t *__restrict__ overflow)
+                 const int64_t *__restrict__ offsets, int64_t capacity, int32_t *__restrict__ out_idx, int32_t *__restrict__ overflow)
 {
+    // destination of a hit = global offset of its box + hits of that box in earlier chunks of the frame + rank in this chunk.
+    // Only the 4-byte point index is scattered here; the coordinates are gathered by crop_materialise_kernel, which writes
+    // every box's list front to back (seven scattered stores per hit in this kernel were what bounded it).
     const CropChunk ck = chunks[blockIdx.x];
-    const int f = ck.frame;
-    const int64_t b0 = box_off[f];
-    const int total = n_hits[blockIdx.x];
-    const int2 *my_hits = hits + (int64_t)blockIdx.x * hit_cap;
-    const double *P = poses ? poses + (int64_t)f * 16 : nullptr;
-    for (int h = threadIdx.x; h < total; h += blockDim.x) {
-        const int2 hr = my_hits[h];
-        const int3 hv = make_int3(hr.x, hr.y & 0xFFFF, hr.y >> 16);
-        const int64_t dst = offsets[b0 + hv.y] + chunk_box_count[(int64_t)blockIdx.x * max_boxes + hv.y] + hv.z;
+    const int64_t b0 = box_off[ck.frame];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = min(n_hits[(int64_t)blockIdx.x * kCropWarps + wid], hit_cap);          // this warp's segment
+    const CropHit *my_hits = hits + ((int64_t)blockIdx.x * kCropWarps + wid) * hit_cap;
+    for (int h = lane; h < total; h += 32) {
+        const CropHit hr = my_hits[h];
+        const int box = hr.box_rank & 0xFFFF;
+        const int64_t dst = offsets[b0 + box] + chunk_box_count[(int64_t)blockIdx.x * max_boxes + box] + (hr.box_rank >> 16);
         if (dst >= capacity) { atomicExch(overflow, 4); continue; }
-        const float *p = points + (pt_off[f] + hv.x) * pt_stride;
-        const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-        out_idx[dst] = hv.x;
-        if (out_xyz) { out_xyz[dst * 3] = x; out_xyz[dst * 3 + 1] = y; out_xyz[dst * 3 + 2] = z; }
-        if (out_xyz_global && P) {
-            const double dx = x, dy = y, dz = z;
+        out_idx[dst] = hr.idx;
+    }
+}
+
+// one warp per (frame, box): out_xyz[k] = points[idx[k]] and out_xyz_global[k] = pose_f [x y z 1] for the box's index list,
+// written front to back (coalesced); waymo_common.py:169-171.
+__global__ void __launch_bounds__(256)
+crop_materialise_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
+                        const int64_t *__restrict__ box_off, const int64_t *__restrict__ offsets, const double *__restrict__ poses,
+                        int64_t capacity, const int32_t *__restrict__ idx, float *__restrict__ out_xyz, double *__restrict__ out_xyz_global)
+{
+    const int f = blockIdx.x;
+    const int64_t b0 = box_off[f];
+    const int B = (int)(box_off[f + 1] - b0);
+    const int lane = threadIdx.x & 31;
+    const float *fpts = points + pt_off[f] * pt_stride;
+    const double *P = poses ? poses + (int64_t)f * 16 : nullptr;
+    double Pm[12];
+    if (P) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-                out_xyz_global[dst * 3 + r] = ((P[r * 4] * dx + P[r * 4 + 1] * dy) + P[r * 4 + 2] * dz) + P[r * 4 + 3];
+        for (int i = 0; i < 12; ++i) Pm[i] = P[i];
+    }
+    for (int b = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += gridDim.y * (blockDim.x >> 5)) {
+        const int64_t lo = offsets[b0 + b], hi = min(offsets[b0 + b + 1], capacity);
+        for (int64_t k = lo + lane; k < hi; k += 32) {
+            const float *q = fpts + (int64_t)idx[k] * pt_stride;
+            const float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
+            if (out_xyz) { out_xyz[k * 3] = x; out_xyz[k * 3 + 1] = y; out_xyz[k * 3 + 2] = z; }
+            if (out_xyz_global && P) {
+                const double dx = x, dy = y, dz = z;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    out_xyz_global[k * 3 + r] = ((Pm[r * 4] * dx + Pm[r * 4 + 1] * dy) + Pm[r * 4 + 2] * dz) + Pm[r * 4 + 3];
+            }
         }
     }
 }
@@ -547,38 +610,42 @@ extern "C" int al3d_crop_box_setup(const float *boxes, const float *sincos, int6
     return 0;
 }
 
-extern "C" int al3d_crop_build_grid(const float *aabb, const int64_t *box_off, int n_frames, int G, float *grid_meta,
-                                    int32_t *cell_start, int32_t *cell_boxes, int cell_cap, int32_t *overflow, void *stream)
+extern "C" int al3d_crop_occ_words(void) { return kOccWords; }
+
+extern "C" int al3d_crop_build_grid(const float *aabb, const float *boxes, const float *sincos, const int64_t *box_off, int n_frames, int G,
+                                    float *grid_meta, int32_t *cell_start, int32_t *cell_boxes, int cell_cap, uint32_t *occ,
+                                    int32_t *overflow, void *stream)
 {
     AL3D_CHECK_ARG(aabb && box_off && grid_meta && cell_start && cell_boxes && overflow, "al3d_crop_build_grid: null pointer");
+    AL3D_CHECK_ARG(!occ || (boxes && sincos), "al3d_crop_build_grid: the occupancy bitmap needs boxes and sincos");
     AL3D_CHECK_ARG(G >= 1 && G <= 64, "al3d_crop_build_grid: G=%d not in [1,64]", G);
     if (n_frames <= 0) return 0;
-    crop_grid_kernel<<<n_frames, kCropThreads, (size_t)2 * G * G * sizeof(int32_t), (cudaStream_t)stream>>>(
-        aabb, box_off, G, reinterpret_cast<CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap, overflow);
+    const size_t smem = (size_t)(2 * G * G + kOccWords) * sizeof(int32_t);
+    crop_grid_kernel<<<n_frames, kCropThreads, smem, (cudaStream_t)stream>>>(
+        aabb, boxes, sincos, box_off, G, reinterpret_cast<CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap, occ, overflow);
     AL3D_CHECK_LAUNCH("crop_grid_kernel");
     return 0;
 }
 
 extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
                               const float *aabb, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
-                              const int32_t *cell_boxes, int cell_cap, const int32_t *chunks, int n_chunks, void *hits,
+                              const int32_t *cell_boxes, int cell_cap, const uint32_t *occ, const int32_t *chunks, int n_chunks, void *hits,
                               int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes, int32_t *overflow, void *stream)
 {
-    AL3D_CHECK_ARG(points && pt_off && planes && aabb && box_off && grid_meta && cell_start && cell_boxes && chunks && hits && n_hits &&
+    AL3D_CHECK_ARG(points && pt_off && planes && aabb && box_off && grid_meta && cell_start && cell_boxes && occ && chunks && hits && n_hits &&
                    chunk_box_count && overflow, "al3d_crop_hits: null pointer");
     AL3D_CHECK_ARG(pt_stride >= 3, "al3d_crop_hits: pt_stride=%lld", (long long)pt_stride);
     AL3D_CHECK_ARG(max_boxes >= 1 && max_boxes <= 12288, "al3d_crop_hits: max_boxes=%d not in [1,12288]", max_boxes);
-    AL3D_CHECK_ARG(hit_cap >= 1 && hit_cap <= 16384, "al3d_crop_hits: hit_cap=%d not in [1,16384]", hit_cap);
+    AL3D_CHECK_ARG(hit_cap >= 1 && hit_cap <= (1 << 20), "al3d_crop_hits: hit_cap=%d not in [1, 2^20]", hit_cap);
     if (n_chunks <= 0) return 0;
     const int rank_boxes = max_boxes <= 512 ? max_boxes : 0;          // per-warp box counters for the parallel ranking, if modest
-    const size_t smem = (size_t)((max_boxes + 1) & ~1) * sizeof(int32_t) + (size_t)kCropWarps * kCropQueue * sizeof(int2) +
-                        (size_t)kCropWarps * std::min(hit_cap, kCropWarpPts * kMaxHitsPerPoint) * sizeof(int2) +
+    const size_t smem = (size_t)((max_boxes + 3) & ~3) * sizeof(int32_t) + (size_t)kCropWarps * kCropQueue * sizeof(float4) +
                         (size_t)kCropWarps * rank_boxes * sizeof(int32_t);
     AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_crop_hits: hit_cap=%d x max_boxes=%d needs too much shared memory", hit_cap, max_boxes);
     if (smem > 48 * 1024) AL3D_CHECK_CUDA(cudaFuncSetAttribute(crop_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     crop_hits_kernel<<<n_chunks, kCropThreads, smem, (cudaStream_t)stream>>>(
         points, pt_stride, pt_off, planes, aabb, box_off, G, reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes,
-        cell_cap, reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<int2 *>(hits), hit_cap, n_hits, chunk_box_count,
+        cell_cap, occ, reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<CropHit *>(hits), hit_cap, n_hits, chunk_box_count,
         max_boxes, rank_boxes, overflow);
     AL3D_CHECK_LAUNCH("crop_hits_kernel");
     return 0;
@@ -589,15 +656,17 @@ extern "C" int al3d_crop_scan(const int64_t *box_off, const int64_t *frame_chunk
 {
     AL3D_CHECK_ARG(box_off && frame_chunk_off && chunk_box_count && box_total && offsets, "al3d_crop_scan: null pointer");
     if (n_frames > 0) {
-        crop_scan_kernel<<<dim3(n_frames, 4), 256, 0, (cudaStream_t)stream>>>(box_off, frame_chunk_off, chunk_box_count, max_boxes, box_total);
+        crop_scan_kernel<<<dim3(n_frames, 1), 256, 0, (cudaStream_t)stream>>>(box_off, frame_chunk_off, chunk_box_count, max_boxes, box_total);
         AL3D_CHECK_LAUNCH("crop_scan_kernel");
     }
-    crop_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(box_total, n_boxes, offsets);
+    crop_offsets_kernel<<<(unsigned)std::max<int64_t>(ceil_div(n_boxes, 1024), 1), 1024, 0, (cudaStream_t)stream>>>(box_total, n_boxes, offsets);
     AL3D_CHECK_LAUNCH("crop_offsets_kernel");
     return 0;
 }
 
-extern "C" int al3d_crop_fill(const float *points, int64_t pt_stride, const int64_t *pt_off, const int64_t *box_off,
+extern "C" int al3d_crop_hit_bytes(void) { return (int)sizeof(CropHit); }
+
+extern "C" int al3d_crop_fill(const float *points, int64_t pt_stride, const int64_t *pt_off, const int64_t *box_off, int n_frames,
                               const int32_t *chunks, int n_chunks, const void *hits, int hit_cap, const int32_t *n_hits,
                               const int32_t *chunk_box_count, int max_boxes, const int64_t *offsets, const double *poses,
                               int64_t capacity, int32_t *out_idx, float *out_xyz, double *out_xyz_global, int32_t *overflow,
@@ -605,11 +674,17 @@ extern "C" int al3d_crop_fill(const float *points, int64_t pt_stride, const int6
 {
     AL3D_CHECK_ARG(points && pt_off && box_off && chunks && hits && n_hits && chunk_box_count && offsets && out_idx && overflow,
                    "al3d_crop_fill: null pointer");
-    if (n_chunks <= 0) return 0;
-    crop_fill_kernel<<<n_chunks, kCropThreads, 0, (cudaStream_t)stream>>>(
-        points, pt_stride, pt_off, box_off, reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<const int2 *>(hits), hit_cap,
-        n_hits, chunk_box_count, max_boxes, offsets, poses, capacity, out_idx, out_xyz, out_xyz_global, overflow);
+    if (n_chunks <= 0 || n_frames <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    crop_fill_kernel<<<n_chunks, kCropThreads, 0, st>>>(box_off, reinterpret_cast<const CropChunk *>(chunks),
+                                                        reinterpret_cast<const CropHit *>(hits), hit_cap, n_hits, chunk_box_count, max_boxes,
+                                                        offsets, capacity, out_idx, overflow);
     AL3D_CHECK_LAUNCH("crop_fill_kernel");
+    if (out_xyz || (out_xyz_global && poses)) {
+        crop_materialise_kernel<<<dim3(n_frames, (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(max_boxes, 8), 16))), 256, 0, st>>>(
+            points, pt_stride, pt_off, box_off, offsets, poses, capacity, out_idx, out_xyz, out_xyz_global);
+        AL3D_CHECK_LAUNCH("crop_materialise_kernel");
+    }
     return 0;
 }
 

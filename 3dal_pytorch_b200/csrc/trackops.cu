@@ -249,6 +249,86 @@ __global__ void box_writeback_kernel(const float *__restrict__ final_box, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// det <-> GT matching by rotated 3-D IoU (det3d/datasets/waymo/waymo_common.py:173-188: boxes_iou3d_gpu of one detection
+// against the frame's GT boxes, arg-max, threshold 0.75 applied by the caller).  IoU3D = BEV overlap x height overlap /
+// (vol_a + vol_b - overlap) as in det3d/ops/iou3d_nms/iou3d_nms_utils.py:35-72.  The BEV overlap is computed by
+// clipping rectangle A, expressed in B's local frame, against B's four sides (Sutherland-Hodgman) and the shoelace
+// formula; float32 like the reference kernel.  Footprint convention as in the crop: length along the direction -heading.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clip_axis(const float (*in)[2], int n, float (*out)[2], int axis, float bound, bool keep_less)
+{
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        const float *p = in[i], *q = in[(i + 1) % n];
+        const bool pin = keep_less ? p[axis] <= bound : p[axis] >= bound;
+        const bool qin = keep_less ? q[axis] <= bound : q[axis] >= bound;
+        if (pin) { out[m][0] = p[0]; out[m][1] = p[1]; ++m; }
+        if (pin != qin) {
+            const float t = (bound - p[axis]) / (q[axis] - p[axis]);
+            out[m][axis] = bound;
+            out[m][1 - axis] = p[1 - axis] + t * (q[1 - axis] - p[1 - axis]);
+            ++m;
+        }
+    }
+    return m;
+}
+
+__device__ float bev_overlap(const float *a, const float *b)
+{
+    // corners of A (local (+-l/2, +-w/2), world = centre + [[c, s], [-s, c]] local), then into B's local frame
+    const float ca = cosf(a[6]), sa = sinf(a[6]), cb = cosf(b[6]), sb = sinf(b[6]);
+    float poly[2][10][2];
+    const float sx[4] = {0.5f, 0.5f, -0.5f, -0.5f}, sy[4] = {0.5f, -0.5f, -0.5f, 0.5f};
+    for (int k = 0; k < 4; ++k) {
+        const float lx = sx[k] * a[3], ly = sy[k] * a[4];
+        const float wx = a[0] + lx * ca + ly * sa - b[0], wy = a[1] - lx * sa + ly * ca - b[1];
+        poly[0][k][0] = wx * cb - wy * sb;                       // local = [[c, -s], [s, c]] world
+        poly[0][k][1] = wx * sb + wy * cb;
+    }
+    int n = 4;
+    n = clip_axis(poly[0], n, poly[1], 0, 0.5f * b[3], true);
+    if (n < 3) return 0.f;
+    n = clip_axis(poly[1], n, poly[0], 0, -0.5f * b[3], false);
+    if (n < 3) return 0.f;
+    n = clip_axis(poly[0], n, poly[1], 1, 0.5f * b[4], true);
+    if (n < 3) return 0.f;
+    n = clip_axis(poly[1], n, poly[0], 1, -0.5f * b[4], false);
+    if (n < 3) return 0.f;
+    float area = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const float *p = poly[0][i], *q = poly[0][(i + 1) % n];
+        area += p[0] * q[1] - q[0] * p[1];
+    }
+    return 0.5f * fabsf(area);
+}
+
+__global__ void match_iou3d_kernel(const float *__restrict__ det, const int32_t *__restrict__ det_frame, int64_t n_det,
+                                   const float *__restrict__ gt, const int64_t *__restrict__ gt_off, int32_t *__restrict__ best_idx,
+                                   float *__restrict__ best_iou)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_det) return;
+    const float *a = det + i * 7;
+    const int f = det_frame[i];
+    const int64_t g0 = gt_off[f], g1 = gt_off[f + 1];
+    const float a_max = a[2] + a[5] / 2.f, a_min = a[2] - a[5] / 2.f, vol_a = a[3] * a[4] * a[5];
+    int best = -1;
+    float bi = -1.f;
+    for (int64_t j = g0; j < g1; ++j) {
+        const float *b = gt + j * 7;
+        const float oh = fmaxf(fminf(a_max, b[2] + b[5] / 2.f) - fmaxf(a_min, b[2] - b[5] / 2.f), 0.f);
+        float iou = 0.f;
+        if (oh > 0.f) {
+            const float o3 = bev_overlap(a, b) * oh;
+            iou = o3 / fmaxf(vol_a + b[3] * b[4] * b[5] - o3, 1e-6f);
+        }
+        if (iou > bi) { bi = iou; best = (int)(j - g0); }          // np.argmax: first maximum
+    }
+    best_idx[i] = best;
+    best_iou[i] = best < 0 ? 0.f : bi;
+}
+
 }  // namespace trackops
 }  // namespace al3d
 
@@ -334,5 +414,16 @@ extern "C" int al3d_box_writeback(const float *final_box, const double *best_pos
     box_writeback_kernel<<<n_tracks, 64, 0, (cudaStream_t)stream>>>(final_box, best_pose, track_obs, track_len, n_tracks, n_frames, obs_inv_pose,
                                                                     out_boxes);
     AL3D_CHECK_LAUNCH("box_writeback_kernel");
+    return 0;
+}
+
+extern "C" int al3d_match_iou3d(const float *det, const int32_t *det_frame, int64_t n_det, const float *gt, const int64_t *gt_off,
+                                int32_t *best_idx, float *best_iou, void *stream)
+{
+    AL3D_CHECK_ARG(n_det >= 0, "al3d_match_iou3d: negative size");
+    if (n_det == 0) return 0;
+    AL3D_CHECK_ARG(det && det_frame && gt_off && best_idx && best_iou, "al3d_match_iou3d: null pointer");
+    match_iou3d_kernel<<<(unsigned)ceil_div(n_det, 128), 128, 0, (cudaStream_t)stream>>>(det, det_frame, n_det, gt, gt_off, best_idx, best_iou);
+    AL3D_CHECK_LAUNCH("match_iou3d_kernel");
     return 0;
 }

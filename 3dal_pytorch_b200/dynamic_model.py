@@ -73,19 +73,20 @@ class DynamicModel(_AutoLabelBase):
             out[k] = h[k]
         return out
 
-    def _forward_eval(self, pts, box, bbox_gt=None):
+    def _forward_eval(self, pts, box, bbox_gt=None, want_box=False):
         self._check_inputs(pts, self.n_channel)
         if box.dim() != 3 or box.shape[1] != 8:
             raise ValueError("box must be (bs,8,steps), got %s" % (tuple(box.shape),))
         logits, seg_mask = self._seg(pts)
         obj, mask, _ = engine.mask_and_gather(pts[:, :4, :], logits, NUM_FRAME * NUM_OBJECT_POINT, self.gather_policy, mask=seg_mask)
         fwp, gp = self._trunk("point_emb", self.point_emb, obj)
-        pe = engine.fc_chain(fwp, gp, ("fc1", "fc2"))
+        pe = ops.fc_chain(gp, self._fc_t("point_emb", self.point_emb, fwp, ("fc1", "fc2")))
         fwb, gb = self._trunk("box_emb", self.box_emb, box.float())
-        be = engine.fc_chain(fwb, gb, ("fc1", "fc2"))
+        be = ops.fc_chain(gb, self._fc_t("box_emb", self.box_emb, fwb, ("fc1", "fc2")))
         fwe = self._packs.get("box_est_f32", self.box_est, lambda: engine.fold_block(self.box_est, self.box_est._table))
-        box_pred = engine.fc_chain(fwe, torch.cat([pe, be], dim=1), ("fc1", "fc2", "fc3"))
-        out = ops.parse_heads(box_pred)
+        # cat[point_e, box_e] (tools/dynamic_model.py:137) is read in place as two inputs of the fused head
+        out = ops.fc_chain(pe, self._fc_t("box_est", self.box_est, fwe, ("fc1", "fc2", "fc3")), x1=be, heads=True, want_box=want_box)
+        self._last_box = out.get("_box")
         return {
             "logits": logits, "mask": mask, "center": out["center"], "heading_scores": out["heading_scores"],
             "heading_residuals_normalized": out["heading_residuals_normalized"],

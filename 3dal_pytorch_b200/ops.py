@@ -1,6 +1,8 @@
 """Tensor-level wrappers over the C ABI (include/al3d.h).  Every function takes CUDA tensors,
 launches on the current PyTorch stream and returns tensors; PyTorch only provides device memory
 and streams here -- all arithmetic happens inside libal3d.so."""
+import ctypes
+
 import numpy as np
 import torch
 
@@ -106,6 +108,61 @@ def parse_heads(box_pred, add=None):
                                            _p(o["heading_residuals_normalized"]), _p(o["heading_residuals"]),
                                            _p(o["size_scores"]), _p(o["size_residuals_normalized"]),
                                            _p(o["size_residuals"]), _stream()), "parse_heads")
+    return o
+
+
+class FcChainDesc(ctypes.Structure):
+    _fields_ = [("x0", ctypes.c_void_p), ("k0", ctypes.c_int32), ("pad0", ctypes.c_int32), ("ld0", ctypes.c_int64),
+                ("x1", ctypes.c_void_p), ("k1", ctypes.c_int32), ("pad1", ctypes.c_int32), ("ld1", ctypes.c_int64),
+                ("n_layers", ctypes.c_int32), ("width", ctypes.c_int32 * 3), ("relu", ctypes.c_int32 * 3), ("heads", ctypes.c_int32),
+                ("wt", ctypes.c_void_p * 3), ("bias", ctypes.c_void_p * 3),
+                ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64),
+                ("add", ctypes.c_void_p), ("add_stride", ctypes.c_int64),
+                ("base_heading", ctypes.c_void_p), ("base_stride", ctypes.c_int64),
+                ("center_boxnet", ctypes.c_void_p), ("center", ctypes.c_void_p), ("heading_scores", ctypes.c_void_p),
+                ("heading_res_norm", ctypes.c_void_p), ("heading_res", ctypes.c_void_p), ("size_scores", ctypes.c_void_p),
+                ("size_res_norm", ctypes.c_void_p), ("size_res", ctypes.c_void_p), ("box", ctypes.c_void_p), ("cls", ctypes.c_void_p)]
+
+
+def fc_chain(x0, layers, x1=None, heads=False, add=None, base_heading=None, want_box=False):
+    """The fused FC chain (csrc/heads.cu): x0 (bs,k0) [+ x1 (bs,k1) concatenated] through up to three layers given as
+    (W^T (K,N) contiguous, bias (N), relu) in ONE launch.  heads=False -> (bs, N_last) tensor.  heads=True (39-wide last
+    layer) -> dict of the parsed head tensors (centre = centre_boxnet + add[:, :3]) and, with want_box, the decoded
+    (bs,7) box (heading base = base_heading) and (bs,2) classes."""
+    _need_cuda(x0, x1, add, base_heading)
+    bs = x0.shape[0]
+    dev = x0.device
+    assert x0.stride(1) == 1 and (x1 is None or x1.stride(1) == 1) and 1 <= len(layers) <= 3
+    d = FcChainDesc()
+    d.x0, d.k0, d.ld0 = x0.data_ptr(), x0.shape[1], x0.stride(0)
+    if x1 is not None:
+        d.x1, d.k1, d.ld1 = x1.data_ptr(), x1.shape[1], x1.stride(0)
+    d.n_layers = len(layers)
+    for i, (wt, b, relu) in enumerate(layers):
+        assert wt.is_contiguous() and b.is_contiguous()
+        d.width[i], d.relu[i], d.wt[i], d.bias[i] = wt.shape[1], int(relu), wt.data_ptr(), b.data_ptr()
+    d.heads = int(heads)
+    f = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+    if not heads:
+        out = f(bs, layers[-1][0].shape[1])
+        d.out, d.ldo = out.data_ptr(), out.stride(0)
+        _lib.check(_lib.lib().al3d_fc_chain(ctypes.byref(d), bs, _stream()), "fc_chain")
+        return out
+    o = {"center_boxnet": f(bs, 3), "center": f(bs, 3), "heading_scores": f(bs, 12),
+         "heading_residuals_normalized": f(bs, 12), "heading_residuals": f(bs, 12), "size_scores": f(bs, 3),
+         "size_residuals_normalized": f(bs, 3, 3), "size_residuals": f(bs, 3, 3)}
+    d.center_boxnet, d.center, d.heading_scores = o["center_boxnet"].data_ptr(), o["center"].data_ptr(), o["heading_scores"].data_ptr()
+    d.heading_res_norm, d.heading_res = o["heading_residuals_normalized"].data_ptr(), o["heading_residuals"].data_ptr()
+    d.size_scores, d.size_res_norm, d.size_res = o["size_scores"].data_ptr(), o["size_residuals_normalized"].data_ptr(), o["size_residuals"].data_ptr()
+    if add is not None:
+        d.add, d.add_stride = add.data_ptr(), add.stride(0)
+    if want_box:
+        o["_box"] = f(bs, 7)
+        o["_cls"] = torch.empty((bs, 2), device=dev, dtype=torch.int32)
+        d.box, d.cls = o["_box"].data_ptr(), o["_cls"].data_ptr()
+        if base_heading is not None:
+            d.base_heading, d.base_stride = base_heading.data_ptr(), base_heading.stride(0)
+    _lib.check(_lib.lib().al3d_fc_chain(ctypes.byref(d), bs, _stream()), "fc_chain")
     return o
 
 

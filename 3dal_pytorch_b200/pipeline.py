@@ -32,10 +32,8 @@ class StaticAutoLabeler:
     @torch.no_grad()
     def label_device(self, pts, init_box, bbox_gt=None):
         """pts (bs,3,n) CUDA (any strides), init_box (bs,7) -> boxes (bs,7) f32 [centre, l, w, h, heading]."""
-        out = self.model(pts, init_box, bbox_gt if bbox_gt is not None else init_box)
-        base = out["box_one"][:, 6] if self.model.name == "two_box_est" else init_box[:, 6]
-        boxes, _ = ops.decode_boxes(out["center"], out["heading_scores"], out["heading_residuals"],
-                                    out["size_scores"], out["size_residuals"], base_heading=base)
+        # the decode (tools/static_eval.py:270-288) runs in the epilogue of the fused head kernel
+        _, boxes = self.model.forward_boxes(pts, init_box, bbox_gt if bbox_gt is not None else init_box)
         return boxes
 
     def _buffers(self, n, dev):

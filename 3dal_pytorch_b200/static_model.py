@@ -68,6 +68,13 @@ class _AutoLabelBase(nn.Module):
         with torch.no_grad():
             return self._forward_eval(*args, **kwargs)
 
+    def forward_boxes(self, *args):
+        """Eval forward that also returns the decoded (bs,7) boxes (tools/static_eval.py:270-288) from the same fused
+        head launch: (output dict, boxes)."""
+        with torch.no_grad():
+            out = self._forward_eval(*args, want_box=True)
+        return out, self._last_box
+
     def _grad_bucket(self):
         """Flat gradient bucket the training-mode backward writes into (rebuilt when the parameters are re-homed)."""
         from . import train
@@ -109,6 +116,10 @@ class _AutoLabelBase(nn.Module):
         pk = self._packs.get("seg_" + self.precision, self.ins_seg, lambda: eng.pack_seg(fw, self.ins_seg.n_channel))
         return eng.seg_forward(pk, fw, pts)
 
+    def _fc_t(self, key, module, fw, names):
+        """Transposed FC weights of a head for the fused kernel, cached with the other packs."""
+        return self._packs.get(key + "_fc_t", module, lambda: engine.fc_layers_t(fw, names))
+
     def _trunk(self, key, module, x):
         fw = self._packs.get(key + "_f32", module, lambda: engine.fold_block(module, module._table))
         if self.precision == "fp32":
@@ -141,13 +152,15 @@ class StaticModelOneBoxEst(_AutoLabelBase):
         out["center"] = h["center_boxnet"] + init_box.float()[:, :3]
         return out
 
-    def _forward_eval(self, pts, init_box, bbox_gt=None):
+    def _forward_eval(self, pts, init_box, bbox_gt=None, want_box=False):
         self._check_inputs(pts, self.n_channel)
         logits, seg_mask = self._seg(pts)
         obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, self.gather_policy, mask=seg_mask)
         fw, g = self._trunk("box_est", self.box_est, obj)
-        box_pred = engine.fc_chain(fw, g, ("fc1", "fc2", "fc3"))
-        out = ops.parse_heads(box_pred, add=init_box.float())
+        init_box = init_box.float()
+        out = ops.fc_chain(g, self._fc_t("box_est", self.box_est, fw, ("fc1", "fc2", "fc3")), heads=True, add=init_box,
+                           base_heading=init_box[:, 6], want_box=want_box)
+        self._last_box = out.get("_box")
         return {
             "logits": logits, "mask": mask, "center_boxnet": out["center_boxnet"],
             "heading_scores": out["heading_scores"],
@@ -197,19 +210,21 @@ class StaticModelTwoBoxEst(_AutoLabelBase):
             out[k] = two[k]
         return out
 
-    def _forward_eval(self, pts, init_box, bbox_gt):
+    def _forward_eval(self, pts, init_box, bbox_gt, want_box=False):
         self._check_inputs(pts, self.n_channel)
         init_box = init_box.float().contiguous()
         bbox_gt = bbox_gt.float().contiguous()
         logits, seg_mask = self._seg(pts)
         obj, mask, _ = engine.mask_and_gather(pts[:, :3, :], logits, NUM_OBJECT_POINT, self.gather_policy, mask=seg_mask)
         fw1, g1 = self._trunk("box_est_one", self.box_est_one, obj)
-        one = ops.parse_heads(engine.fc_chain(fw1, g1, ("fc1", "fc2", "fc3")), add=init_box)
-        box_one, _ = ops.decode_boxes(one["center"], one["heading_scores"], one["heading_residuals"],
-                                      one["size_scores"], one["size_residuals"], base_heading=init_box[:, 6])
+        one = ops.fc_chain(g1, self._fc_t("box_est_one", self.box_est_one, fw1, ("fc1", "fc2", "fc3")), heads=True, add=init_box,
+                           base_heading=init_box[:, 6], want_box=True)
+        box_one = one["_box"]
         obj2, cls2, res2 = ops.twostage_retransform(obj, init_box, box_one, bbox_gt)
         fw2, g2 = self._trunk("box_est_two", self.box_est_two, obj2)
-        two = ops.parse_heads(engine.fc_chain(fw2, g2, ("fc1", "fc2", "fc3")), add=one["center"])
+        two = ops.fc_chain(g2, self._fc_t("box_est_two", self.box_est_two, fw2, ("fc1", "fc2", "fc3")), heads=True, add=one["center"],
+                           base_heading=box_one[:, 6], want_box=want_box)
+        self._last_box = two.get("_box")
         return {
             "logits": logits, "mask": mask,
             "heading_scores_one": one["heading_scores"],

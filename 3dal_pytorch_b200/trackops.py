@@ -96,3 +96,15 @@ def box_writeback(final_box, best_pose, groups, obs_inv_pose):
                                              _p(groups["track_len"]), T, F, _p(obs_inv_pose.double().contiguous()), _p(out), ops._stream()),
                "box_writeback")
     return out
+
+
+def match_detections(det, det_frame, gt, gt_off, iou_threshold=0.75):
+    """det (n,7) f32 CUDA, det_frame (n,) i32, gt (m,7) f32, gt_off (F+1,) i64 -> (match (n,) i32 index of the matched GT
+    box within its frame or -1, best_iou (n,) f32): det3d/datasets/waymo/waymo_common.py:173-188 (arg-max IoU3D > 0.75)."""
+    ops._need_cuda(det, det_frame, gt, gt_off)
+    n = det.shape[0]
+    best = torch.empty((n,), device=det.device, dtype=torch.int32)
+    iou = torch.empty((n,), device=det.device, dtype=torch.float32)
+    _lib.check(_lib.lib().al3d_match_iou3d(_p(det.float().contiguous()), _p(det_frame.contiguous()), n, _p(gt.float().contiguous()),
+                                           _p(gt_off.contiguous()), _p(best), _p(iou), ops._stream()), "match_iou3d")
+    return torch.where(iou > iou_threshold, best, torch.full_like(best, -1)), iou

@@ -108,6 +108,26 @@ int al3d_twostage_retransform(const float *obj_pts, int bs, int m, const float *
                               float *heading_res_label, void *stream);
 
 
+/* Fused FC chain of a box head / embedding in one launch (csrc/heads.cu): up to three Linear (+ folded BatchNorm)
+ * (+ ReLU) layers on (bs, k0 [+ k1]) fp32 rows (x1: optional second input, concatenated -- the dynamic head's
+ * cat[point_e, box_e], tools/dynamic_model.py:137), weights TRANSPOSED (K, N) row-major.  With heads = 1 the last layer is
+ * the 39-wide head vector and the epilogue does parse_output_to_tensors (tools/static_model.py:64-96), the centre
+ * residual add (:132,174,211) and, when box != NULL, the decode of al3d_decode_boxes (tools/static_eval.py:270-288).
+ * Replaces PointNetEstimation fc1-fc3 (tools/static_model.py:336-338; tools/dynamic_model.py:307-311) and the embedding
+ * FC layers (tools/dynamic_model.py:247-248, 284-285).  Every output pointer may be NULL. */
+typedef struct al3d_fc_chain_desc {
+    const float *x0; int32_t k0; int32_t pad0; int64_t ld0;
+    const float *x1; int32_t k1; int32_t pad1; int64_t ld1;
+    int32_t n_layers; int32_t width[3]; int32_t relu[3]; int32_t heads;
+    const float *wt[3]; const float *bias[3];
+    float *out; int64_t ldo;
+    const float *add; int64_t add_stride;
+    const float *base_heading; int64_t base_stride;
+    float *center_boxnet, *center, *heading_scores, *heading_res_norm, *heading_res, *size_scores, *size_res_norm, *size_res, *box;
+    int32_t *cls;
+} al3d_fc_chain_desc;
+int al3d_fc_chain(const al3d_fc_chain_desc *d, int bs, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Points-in-rotated-box crop over a batch of lidar frames (integer / indexing work, bit-exact).
  * Replaces box_np_ops.points_in_rbbox (det3d/core/bbox/box_np_ops.py:641-647 ->
@@ -125,13 +145,22 @@ int al3d_twostage_retransform(const float *obj_pts, int bs, int m, const float *
 int al3d_crop_box_setup(const float *boxes, const float *sincos, int64_t n_boxes, float pad_abs, float pad_rel, float *planes,
                         float *aabb, void *stream);
 int al3d_crop_chunk_points(void);      /* points per work chunk (the caller builds the chunk table) */
-int al3d_crop_build_grid(const float *aabb, const int64_t *box_off, int n_frames, int G, float *grid_meta,
-                         int32_t *cell_start, int32_t *cell_boxes, int cell_cap, int32_t *overflow, void *stream);
+int al3d_crop_occ_words(void);         /* 32-bit words of one frame's fine occupancy bitmap */
+int al3d_crop_hit_bytes(void);         /* bytes of one hit record of al3d_crop_hits / al3d_crop_fill */
+/* Per frame: grid_meta (n_frames, 8) f32, the coarse G x G cell -> box lists (CSR: cell_start (n_frames, G*G+1),
+ * cell_boxes (n_frames, cell_cap); with cell_cap = 0 nothing is stored and cell_start[f, G*G] receives the capacity
+ * the frame needs) and, when occ != NULL, the fine occupancy bitmap occ (n_frames, al3d_crop_occ_words()) u32 rasterised
+ * from the rotated box footprints (boxes (n,7) + sincos (n,2) as for al3d_crop_box_setup). */
+int al3d_crop_build_grid(const float *aabb, const float *boxes, const float *sincos, const int64_t *box_off, int n_frames, int G,
+                         float *grid_meta, int32_t *cell_start, int32_t *cell_boxes, int cell_cap, uint32_t *occ,
+                         int32_t *overflow, void *stream);
 /* chunks: (n_chunks, 4) i32 rows [frame, first point in frame, n points, chunk index in frame];
- * hits: (n_chunks, hit_cap) int2 scratch; chunk_box_count: (n_chunks, max_boxes) i32 scratch. */
+ * hits: (n_chunks, 8, hit_cap) records of al3d_crop_hit_bytes() bytes, scratch (one ordered segment per warp of the
+ * chunk's CTA: point index, box | rank << 16), n_hits (n_chunks, 8) i32;
+ * chunk_box_count: (n_chunks, max_boxes) i32 scratch. */
 int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
                    const float *aabb, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
-                   const int32_t *cell_boxes, int cell_cap, const int32_t *chunks, int n_chunks, void *hits,
+                   const int32_t *cell_boxes, int cell_cap, const uint32_t *occ, const int32_t *chunks, int n_chunks, void *hits,
                    int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes, int32_t *overflow, void *stream);
 /* frame_chunk_off (F+1) i64; writes box_total (n_boxes) i32 and offsets (n_boxes+1) i64 (exclusive). */
 int al3d_crop_scan(const int64_t *box_off, const int64_t *frame_chunk_off, int n_frames, int64_t n_boxes,
@@ -139,7 +168,7 @@ int al3d_crop_scan(const int64_t *box_off, const int64_t *frame_chunk_off, int n
 /* out_idx (capacity) i32 point index within its frame, ascending per box; out_xyz (capacity,3) f32 copy
  * (may be NULL); out_xyz_global (capacity,3) f64 = poses[f] (4x4 row-major f64) applied to [x y z 1]
  * (may be NULL, needs poses). */
-int al3d_crop_fill(const float *points, int64_t pt_stride, const int64_t *pt_off, const int64_t *box_off,
+int al3d_crop_fill(const float *points, int64_t pt_stride, const int64_t *pt_off, const int64_t *box_off, int n_frames,
                    const int32_t *chunks, int n_chunks, const void *hits, int hit_cap, const int32_t *n_hits,
                    const int32_t *chunk_box_count, int max_boxes, const int64_t *offsets, const double *poses,
                    int64_t capacity, int32_t *out_idx, float *out_xyz, double *out_xyz_global, int32_t *overflow,
@@ -204,6 +233,14 @@ int al3d_track_labels(const double *src_xyz, const int64_t *choice, int bs, int 
  * obs_inv_pose[obs]) in float64 (poses 4x4 row-major). */
 int al3d_box_writeback(const float *final_box, const double *best_pose, const int32_t *track_obs, const int32_t *track_len,
                        int n_tracks, int n_frames, const double *obs_inv_pose, double *out_boxes, void *stream);
+
+/* det <-> GT matching (det3d/datasets/waymo/waymo_common.py:173-188): for every detection (n_det,7) f32 [x y z l w h
+ * heading] of frame det_frame[i], the GT box of that frame (gt (sum M_f,7), gt_off (F+1) i64) with the largest rotated
+ * 3-D IoU (det3d/ops/iou3d_nms/iou3d_nms_utils.py:35-72): best_idx (index within the frame, -1 if the frame has no GT)
+ * and best_iou.  The caller applies the 0.75 threshold.  float32; parity with the external pcdet kernel is unpinned
+ * (SURVEY.md 8c): checked against an independent float64 restatement and analytic cases. */
+int al3d_match_iou3d(const float *det, const int32_t *det_frame, int64_t n_det, const float *gt, const int64_t *gt_off,
+                     int32_t *best_idx, float *best_iou, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Loss forward (evaluation / logging; no backward).  Replaces FrustumPointNetLossOneBoxEst.forward

@@ -42,3 +42,45 @@ def static_labels(point_vehicle, bbox_gt, init_heading):
     hc, hr = codecs.angle2class(bbox_gt[-1] - init_heading, 12)
     sc, sr = codecs.size2class(bbox_gt[3:6])
     return mask, bbox_gt[:3], hc, hr, sc, sr
+
+
+def _rect_corners(b):
+    c, s = np.cos(b[6]), np.sin(b[6])
+    loc = np.array([[0.5, 0.5], [0.5, -0.5], [-0.5, -0.5], [-0.5, 0.5]]) * b[3:5]
+    return np.stack([b[0] + loc[:, 0] * c + loc[:, 1] * s, b[1] - loc[:, 0] * s + loc[:, 1] * c], 1)
+
+
+def _clip(poly, a, b):
+    """Keep the part of `poly` on the left of the directed line a -> b (float64 Sutherland-Hodgman)."""
+    out = []
+    n = len(poly)
+    side = lambda p: (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0])
+    for i in range(n):
+        p, q = poly[i], poly[(i + 1) % n]
+        sp, sq = side(p), side(q)
+        if sp >= 0:
+            out.append(p)
+        if (sp >= 0) != (sq >= 0):
+            t = sp / (sp - sq)
+            out.append(p + t * (q - p))
+    return out
+
+
+def iou3d(a, b):
+    """Rotated 3-D IoU of two [x y z l w h heading] boxes, float64 (det3d/ops/iou3d_nms/iou3d_nms_utils.py:35-72 semantics;
+    the BEV overlap by clipping A against the four sides of B in WORLD coordinates -- an independent formulation)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    oh = max(min(a[2] + a[5] / 2, b[2] + b[5] / 2) - max(a[2] - a[5] / 2, b[2] - b[5] / 2), 0.0)
+    poly = list(_rect_corners(a))
+    cb = _rect_corners(b)
+    # orientation of cb: make it counter-clockwise so that "left of the edge" is inside
+    area2 = sum(cb[i][0] * cb[(i + 1) % 4][1] - cb[(i + 1) % 4][0] * cb[i][1] for i in range(4))
+    if area2 < 0:
+        cb = cb[::-1]
+    for i in range(4):
+        poly = _clip(poly, cb[i], cb[(i + 1) % 4])
+        if len(poly) < 3:
+            return 0.0
+    ov = 0.5 * abs(sum(poly[i][0] * poly[(i + 1) % len(poly)][1] - poly[(i + 1) % len(poly)][0] * poly[i][1] for i in range(len(poly))))
+    o3 = ov * oh
+    return o3 / max(a[3] * a[4] * a[5] + b[3] * b[4] * b[5] - o3, 1e-6)

@@ -90,7 +90,9 @@ def test_crop_overflow_is_reported():
     pts = rng.uniform(-0.5, 0.5, (4096, 3)).astype(np.float32)
     boxes = np.tile(np.array([[0, 0, 0, 4, 4, 4, 0.0]], np.float32), (10, 1))     # every point inside 10 boxes
     with pytest.raises(OverflowError):
-        crop.crop_frames([pts], [boxes], hit_cap=16384)
+        crop.crop_frames([pts], [boxes], hit_cap=1024)                           # 512 points x 10 boxes per warp segment
+    res = crop.crop_frames([pts], [boxes], [np.eye(4)], hit_cap=8192)             # enough room: no limit on boxes per point
+    _check_against_oracle([pts], [boxes], [np.eye(4)], res)
 
 
 @pytest.mark.gpu

@@ -53,3 +53,36 @@ def test_shard_ranges_partition_exactly():
             assert r[0][0] == 0 and r[-1][1] == total
             assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
             assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
+
+
+def _grad_worker(rank, world, port, out_dir):
+    """Training configuration (BASELINE.json configs[4]): every rank fills its flat gradient bucket, ONE all-reduce sums
+    them, the optimiser applies 1 / world -- the result equals the gradient of the concatenated batch's mean loss."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        train = importlib.import_module("3dal_pytorch_b200.train")
+        sm = importlib.import_module("3dal_pytorch_b200.static_model")
+        torch.manual_seed(0)
+        model = sm.StaticModelOneBoxEst()                       # parameter container only: no forward on the CPU
+        bucket = train.GradBucket(model)
+        assert bucket.flat.numel() == sum(p.numel() for p in model.parameters()) == 1481513
+        g = torch.Generator().manual_seed(100)
+        per_rank = [torch.randn(bucket.flat.numel(), generator=g) for _ in range(world)]
+        bucket.flat.copy_(per_rank[rank])
+        bucket.attach()
+        w = dict(model.named_parameters())["box_est.fc3.weight"]
+        assert w.grad.data_ptr() == bucket.view(w).data_ptr()  # p.grad is a view of the bucket
+        scale = train.allreduce_gradients(bucket)
+        assert scale == 1.0 / world
+        assert torch.allclose(bucket.flat * scale, sum(per_rank) / world)
+        assert torch.equal(w.grad, bucket.view(w))
+        open(os.path.join(out_dir, "g%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_flat_bucket_gradient_allreduce(tmp_path):
+    mp.spawn(_grad_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "g0") and os.path.exists(tmp_path / "g1")

@@ -198,3 +198,38 @@ def test_decode_and_retransform_match_oracle():
         assert rel_err(o2[i].cpu(), p) < 1e-5
         cid, res = codecs.angle2class_f32((gt[i, 6] - box_one[i, 6]).numpy(), 12)
         assert int(c2[i]) == cid and np.float32(r2[i].item()) == np.float32(res), i
+
+
+def test_fused_fc_heads_match_the_layer_by_layer_path():
+    """csrc/heads.cu (one launch: fc1 -> fc2 -> fc3 -> parse -> centre add -> decode) against al3d_linear_f32 per layer +
+    al3d_parse_heads + al3d_decode_boxes.  Same fp32 arithmetic, another summation order: floats to 1e-5, classes exact."""
+    from helpers import fold_state_dict, spec
+    eng = importlib.import_module("3dal_pytorch_b200.engine")
+    torch.manual_seed(7)
+    for bs in (1, 16, 37, 300):
+        sd = synth.random_state_dict("static_one", seed=9)
+        fw = {k: (w.to(DEV), b.to(DEV)) for k, (w, b) in fold_state_dict(sd, "box_est", spec.static_est_layers()).items()}
+        g = torch.relu(torch.randn(bs, 512, device=DEV))
+        init_box = torch.randn(bs, 7, device=DEV)
+        ref_pred = eng.fc_chain(fw, g, ("fc1", "fc2", "fc3"))
+        ref = ops.parse_heads(ref_pred, add=init_box)
+        ref_box, ref_cls = ops.decode_boxes(ref["center"], ref["heading_scores"], ref["heading_residuals"], ref["size_scores"],
+                                            ref["size_residuals"], base_heading=init_box[:, 6])
+        got = ops.fc_chain(g, eng.fc_layers_t(fw, ("fc1", "fc2", "fc3")), heads=True, add=init_box, base_heading=init_box[:, 6],
+                           want_box=True)
+        for k in ref:
+            assert rel_err(got[k].cpu(), ref[k].cpu()) < 1e-5, (bs, k)
+        assert torch.equal(got["_cls"], ref_cls) and rel_err(got["_box"].cpu(), ref_box.cpu()) < 1e-5
+    # dynamic head: two concatenated inputs, embeddings without a head epilogue
+    sd = synth.random_state_dict("dynamic", seed=9)
+    fwe = {k: (w.to(DEV), b.to(DEV)) for k, (w, b) in fold_state_dict(sd, "box_est", spec.dynamic_est_layers()).items()}
+    fwp = {k: (w.to(DEV), b.to(DEV)) for k, (w, b) in fold_state_dict(sd, "point_emb", spec.point_emb_layers()).items()}
+    gp = torch.relu(torch.randn(50, 512, device=DEV))
+    pe_ref = eng.fc_chain(fwp, gp, ("fc1", "fc2"))
+    pe = ops.fc_chain(gp, eng.fc_layers_t(fwp, ("fc1", "fc2")))
+    assert rel_err(pe.cpu(), pe_ref.cpu()) < 1e-5
+    be = torch.relu(torch.randn(50, 128, device=DEV))
+    ref = ops.parse_heads(eng.fc_chain(fwe, torch.cat([pe_ref, be], 1), ("fc1", "fc2", "fc3")))
+    got = ops.fc_chain(pe_ref, eng.fc_layers_t(fwe, ("fc1", "fc2", "fc3")), x1=be, heads=True)
+    for k in ref:
+        assert rel_err(got[k].cpu(), ref[k].cpu()) < 1e-5, k

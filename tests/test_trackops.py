@@ -127,3 +127,49 @@ def test_track_labels_match_oracle():
         assert np.array_equal(out["center_label"][b].cpu().numpy(), c)
         assert int(out["heading_class_label"][b]) == hc and np.float32(out["heading_residuals_label"][b].item()) == np.float32(hr)
         assert int(out["size_class_label"][b]) == sc and np.array_equal(out["size_residual_label"][b].cpu().numpy(), sr.astype(np.float32))
+
+
+def test_oracle_iou3d_analytic_cases():
+    a = np.array([0, 0, 0, 4, 2, 2, 0.0])
+    assert abs(otrack.iou3d(a, a) - 1.0) < 1e-12
+    assert otrack.iou3d(a, np.array([10, 0, 0, 4, 2, 2, 0.3])) == 0.0
+    b = np.array([2, 0, 0, 4, 2, 2, 0.0])                                   # half overlap along the length
+    assert abs(otrack.iou3d(a, b) - (2 * 2 * 2) / (16 + 16 - 8)) < 1e-12
+    c = np.array([0, 0, 1, 4, 2, 2, np.pi / 2])                             # crossed, half the height
+    assert abs(otrack.iou3d(a, c) - (2 * 2 * 1) / (16 + 16 - 4)) < 1e-9
+    d = np.array([0, 0, 0, 4, 2, 2, np.pi])                                 # same footprint, flipped heading
+    assert abs(otrack.iou3d(a, d) - 1.0) < 1e-9
+
+
+@pytest.mark.gpu
+def test_match_iou3d_against_float64_restatement():
+    rng = np.random.default_rng(6)
+    F = 12
+    dets, frames, gts, gt_off = [], [], [], [0]
+    for f in range(F):
+        m = int(rng.integers(0, 9))
+        g = np.concatenate([rng.uniform(-20, 20, (m, 2)), rng.normal(0.8, 0.3, (m, 1)), rng.uniform(0.6, 6, (m, 3)), rng.uniform(-4, 4, (m, 1))], 1)
+        gts.append(g); gt_off.append(gt_off[-1] + m)
+        for k in range(int(rng.integers(0, 12))):
+            if m and rng.random() < 0.7:
+                d = g[rng.integers(0, m)] + np.concatenate([rng.normal(0, 0.15, 3), rng.normal(0, 0.1, 3), rng.normal(0, 0.05, 1)])
+            else:
+                d = np.concatenate([rng.uniform(-20, 20, 2), [0.8], rng.uniform(0.6, 6, 3), rng.uniform(-4, 4, 1)])
+            dets.append(d); frames.append(f)
+    det = np.asarray(dets, np.float32); gt = np.concatenate(gts, 0).astype(np.float32)
+    match, iou = tops.match_detections(torch.from_numpy(det).to(DEV), torch.tensor(frames, dtype=torch.int32, device=DEV),
+                                       torch.from_numpy(gt).to(DEV), torch.tensor(gt_off, dtype=torch.int64, device=DEV))
+    match, iou = match.cpu().numpy(), iou.cpu().numpy()
+    n_matched = 0
+    for i, (d, f) in enumerate(zip(det, frames)):
+        cand = gt[gt_off[f]:gt_off[f + 1]]
+        ref = np.array([otrack.iou3d(d, g) for g in cand]) if len(cand) else np.zeros(0)
+        if len(cand) == 0:
+            assert match[i] == -1 and iou[i] == 0.0
+            continue
+        assert abs(iou[i] - ref.max()) < 2e-4, (i, iou[i], ref.max())
+        if ref.max() > 0.75 + 1e-3:
+            assert match[i] == int(np.argmax(ref)); n_matched += 1
+        elif ref.max() < 0.75 - 1e-3:
+            assert match[i] == -1
+    assert n_matched > 10
