@@ -636,6 +636,262 @@ done:
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+
+// ================================================================================================
+// split_tail_pair_kernel -- the same computation on CTA PAIRS (cluster of 2, tcgen05 cta_group::2)
+//
+// EXPERIMENT, off by default (engine_split.USE_PAIR_KERNEL): split_tail_kernel streams 864 KB of weight slots per
+// 128-point tile (~21 k cycles at the measured ~41 B/cycle per-SM L2 -> smem ingress, against ~20.7 k cycles of tensor
+// work).  Here one M = 256 MMA covers the 128-point tiles of both CTAs of a pair and each CTA holds only HALF of every
+// weight slot (N/2 rows of B): the bytes per SM halve and the same 48 KB of ring hold six stages.  Measured: 39.6 ms
+// against 37.3 ms -- the weight stream was not the limiter (the unhidden epilogues are), and the pair adds a cluster round
+// trip to every hand-over.
+// Every activation buffer, TMEM column and the order of the weight stream are those of split_tail_kernel.
+//   leader (cluster rank 0), warp 1: issues every MMA (cta_group::2) and every commit (multicast to both CTAs)
+//   both CTAs, warp 0: stream their half slots;  peer, warp 1: forwards "my half of slot s has landed" to the leader
+//   both CTAs, warps 2-9: epilogues of their own tile; hand-overs to the issuer arrive on the LEADER's barriers
+// ================================================================================================
+constexpr int kPairStages = 6;
+constexpr int kHalfStage = kStage / 2;
+struct TailPairSmem {
+    uint8_t a2[32768];
+    uint8_t big[131072];
+    uint8_t ring[kPairStages][kHalfStage];
+    float w1_w[64 * 8], w1_b[64], b2[64], gb[512], bd2[256], bd3[128], bd4[128], w5[256], b5[2];
+    float lpart[2 * kTile];
+    uint64_t w_full[kPairStages], w_empty[kPairStages], w_peer[kPairStages];   // w_peer: leader only (peer's half landed)
+    uint64_t act, acc;                             // act: leader only, one arrival per epilogue warp of BOTH CTAs
+    uint64_t d1_full[2], d1_act[2], cb_free[2];    // d1_act: leader only
+    uint32_t tmem_base;
+};
+static_assert(sizeof(TailPairSmem) + 128 <= 232448, "TailPairSmem exceeds the 227 KB opt-in limit");
+
+// One K = 64 block on the pair: D[256 x rows] (+)= A[256 x 64] * W[rows x 64]^T, rows/2 of W in each CTA.
+#define PAIR_RING_NEXT(code)                                                                        \
+    if (!mbar_wait(&s.w_full[stage], wphase, (code) + stage, wd)) goto done;                         \
+    if (!mbar_wait_cluster(&s.w_peer[stage], wphase, (code) + 8 + stage, wd)) goto done;             \
+    tc_fence_after();                                                                                \
+    const uint32_t wst_ = ring0 + (uint32_t)stage * kHalfStage;
+#define PAIR_RING_RELEASE()                                                                         \
+    mma_commit_pair(&s.w_empty[stage], 0x3);                                                         \
+    if (++stage == kPairStages) { stage = 0; wphase ^= 1; }
+#define PAIR_MMA_BLOCK(d_tmem, a_hi, a_lo_off, w_rows, idesc, first, code)                                           \
+    {                                                                                                                \
+        { PAIR_RING_NEXT(code)                                                                                       \
+          _Pragma("unroll")                                                                                          \
+          for (int k_ = 0; k_ < 4; ++k_) {                                                                           \
+              const uint64_t db_ = make_desc(wst_ + k_ * 2 * ((w_rows) / 2) * 16, (w_rows) / 2);                     \
+              mma_bf16_ss_pair((d_tmem), make_desc((a_hi) + k_ * 2 * kPlane, 128), db_, (idesc), ((first) && k_ == 0) ? 0u : 1u); \
+              mma_bf16_ss_pair((d_tmem), make_desc((a_hi) + (a_lo_off) + k_ * 2 * kPlane, 128), db_, (idesc), 1u);   \
+          }                                                                                                          \
+          PAIR_RING_RELEASE() }                                                                                      \
+        { PAIR_RING_NEXT(code)                                                                                       \
+          _Pragma("unroll")                                                                                          \
+          for (int k_ = 0; k_ < 4; ++k_)                                                                             \
+              mma_bf16_ss_pair((d_tmem), make_desc((a_hi) + k_ * 2 * kPlane, 128),                                   \
+                               make_desc(wst_ + k_ * 2 * ((w_rows) / 2) * 16, (w_rows) / 2), (idesc), 1u);           \
+          PAIR_RING_RELEASE() }                                                                                      \
+    }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+split_tail_pair_kernel(const TailParams p)
+{
+    const TcStatus wd = p.wd;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TailPairSmem &s = *reinterpret_cast<TailPairSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+
+    for (int i = threadIdx.x; i < 64 * 8; i += kThreads) s.w1_w[i] = p.w1_w[i];
+    for (int i = threadIdx.x; i < 64; i += kThreads) { s.w1_b[i] = p.w1_b[i]; s.b2[i] = p.b2[i]; }
+    for (int i = threadIdx.x; i < 256; i += kThreads) { s.bd2[i] = p.bd2[i]; s.w5[i] = p.w5[i]; }
+    for (int i = threadIdx.x; i < 128; i += kThreads) { s.bd3[i] = p.bd3[i]; s.bd4[i] = p.bd4[i]; }
+    if (threadIdx.x < 2) s.b5[threadIdx.x] = p.b5[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kPairStages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); mbar_init(&s.w_peer[i], 1); }
+        mbar_init(&s.act, 2 * kEpiThreads / 32); mbar_init(&s.acc, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], 2 * kEpiThreads / 32); mbar_init(&s.cb_free[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc_pair<512>(&s.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // both CTAs' barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    // both CTAs of a pair run the same number of rounds; a CTA whose item is past the end recomputes the last item
+    // without writing ("ghost"), so the pair's shared MMA stream never changes shape
+    const int n_rounds = (p.n_items + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ weight producer: this CTA's half of every slot
+        if (elect_one_sync()) {
+            int stage = 0; uint32_t phase = 0;
+            const uint8_t *src = p.wstream + (size_t)crank * kTailBlocks * kHalfStage;
+            for (int r = 0; r < n_rounds; ++r)
+                for (int blk = 0; blk < kTailBlocks; ++blk) {
+                    SPLIT_STRESS(wd, 0x11);
+                    if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x1100 + stage, wd)) goto done;
+                    mbar_arrive_expect_tx(&s.w_full[stage], kHalfStage);
+                    bulk_g2s(s.ring[stage], src + (size_t)blk * kHalfStage, kHalfStage, &s.w_full[stage]);
+                    if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        if (crank != 0) {
+            // ------------------------------------------------------------ peer: forward "my half has landed" to the leader
+            if (elect_one_sync()) {
+                int stage = 0; uint32_t phase = 0;
+                for (int r = 0; r < n_rounds; ++r)
+                    for (int blk = 0; blk < kTailBlocks; ++blk) {
+                        if (!mbar_wait(&s.w_full[stage], phase, 0x1200 + stage, wd)) goto done;
+                        // default semantics: the half slot was written by this CTA's TMA (complete before the barrier
+                        // flipped) and is read by this CTA's tensor core; nothing generic crosses the CTA boundary.  The
+                        // .release.cluster form stalls ~250 cycles per arrive and made this forwarding loop the bottleneck
+                        // of the whole kernel (58.7 ms instead of 37.3 ms of the single-CTA kernel).
+                        mbar_arrive_remote(&s.w_peer[stage], 0);
+                        if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+                    }
+            }
+        } else if (elect_one_sync()) {
+            // ------------------------------------------------------------ leader: MMA issuer of the pair
+            int stage = 0; uint32_t wphase = 0;
+            uint32_t act_phase = 0, d1a_phase[2] = {0, 0};
+            const uint32_t id64 = make_idesc_bf16(256, 64), id128 = make_idesc_bf16(256, 128);
+            const uint32_t a2 = smem_u32(s.a2), big = smem_u32(s.big), ring0 = smem_u32(s.ring[0]);
+#define TP_WAIT_ACT(code)                                                        \
+            SPLIT_STRESS(wd, 0x12);                                              \
+            if (!mbar_wait_cluster(&s.act, act_phase, code, wd)) goto done;      \
+            act_phase ^= 1; tc_fence_after();
+#define TP_ISSUE_D1(c)                                                                                        \
+            { PAIR_MMA_BLOCK(tmem + (((c) & 1) ? kTDB : kTDA), a2, 16384u, 128, id128, true, 0x1310)         \
+              mma_commit_pair(&s.d1_full[(c) & 1], 0x3); }
+            for (int r = 0; r < n_rounds; ++r) {
+                TP_WAIT_ACT(0x1300)
+                PAIR_MMA_BLOCK(tmem + kTDA, big, 16384u, 64, id64, true, 0x1320)              // conv2
+                mma_commit_pair(&s.acc, 0x3);
+                TP_WAIT_ACT(0x1301)
+                TP_ISSUE_D1(0)
+                TP_ISSUE_D1(1)
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int j = c & 1;
+                    SPLIT_STRESS(wd, 0x14);
+                    if (!mbar_wait_cluster(&s.d1_act[j], d1a_phase[j], 0x1400 + c, wd)) goto done;
+                    d1a_phase[j] ^= 1; tc_fence_after();
+                    if (c + 2 < 4) TP_ISSUE_D1(c + 2)
+                    const uint32_t cb = big + j * 65536;
+                    for (int nc = 0; nc < 2; ++nc)
+                        for (int kb = 0; kb < 2; ++kb)
+                            PAIR_MMA_BLOCK(tmem + kTD2 + nc * 128, cb + kb * 8 * kPlane, 32768u, 128, id128, c == 0 && kb == 0, 0x1330)
+                    if (c + 2 < 4) mma_commit_pair(&s.cb_free[j], 0x3);
+                }
+                mma_commit_pair(&s.acc, 0x3);
+                TP_WAIT_ACT(0x1302)
+                for (int kb = 0; kb < 4; ++kb)
+                    PAIR_MMA_BLOCK(tmem + kTDA, big + kb * 8 * kPlane, 65536u, 128, id128, kb == 0, 0x1340)      // dconv3
+                mma_commit_pair(&s.acc, 0x3);
+                TP_WAIT_ACT(0x1303)
+                for (int kb = 0; kb < 2; ++kb)
+                    PAIR_MMA_BLOCK(tmem + kTDB, big + kb * 8 * kPlane, 32768u, 128, id128, kb == 0, 0x1350)      // dconv4
+                mma_commit_pair(&s.acc, 0x3);
+            }
+#undef TP_ISSUE_D1
+#undef TP_WAIT_ACT
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (256 threads), own tile
+        const int row = epi_row(), half = epi_half();
+        const uint32_t tl = tmem + ((uint32_t)(row & ~31) << 16);
+        const int etid = threadIdx.x - 64;
+        uint32_t acc_phase = 0, d1f_phase[2] = {0, 0}, cbf_phase[2] = {0, 0};
+#define TP_WAIT_ACC(code)                                                        \
+        SPLIT_STRESS_WARP(wd, 0x01);                                             \
+        if (!mbar_wait(&s.acc, acc_phase, code, wd)) goto done;                  \
+        acc_phase ^= 1; tc_fence_after();
+        // the operand was written to this CTA's shared memory through the generic proxy and is consumed by MMAs the OTHER
+        // CTA's thread issues: proxy fence, then a cluster-scope release on the leader's barrier
+#define TP_PUBLISH(bar) do { tc_fence_before(); fence_proxy_async_smem(); __syncwarp();                                  \
+                             if (lane == 0) { if (crank == 0) mbar_arrive(bar); else mbar_arrive_remote_release(bar, 0); } } while (0)
+        for (int r = 0; r < n_rounds; ++r) {
+            const int item_raw = (int)blockIdx.x + r * (int)gridDim.x;
+            const bool ghost = item_raw >= p.n_items;
+            const int item = ghost ? p.n_items - 1 : item_raw;
+            const int b = item / p.tiles_per_obj, t = item % p.tiles_per_obj;
+            const int pidx_raw = t * kTile + row;
+            const bool valid = !ghost && pidx_raw < p.n;
+            const int pidx = pidx_raw < p.n ? pidx_raw : p.n - 1;
+            for (int i = etid; i < 512; i += kEpiThreads) s.gb[i] = __ldg(p.gbias + (int64_t)b * 512 + i);
+            {
+                const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
+                float xv[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+                first_layer_split(s.big, 16384u, row, xv, p.c_in, 64, half * 32, 32, s.w1_w, s.w1_b);
+                TP_PUBLISH(&s.act);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // s.gb complete
+            TP_WAIT_ACC(0x0100)
+            epilogue_split(tl + kTDA, half * 32, 32, s.a2, 16384u, kPlane, row, s.b2);
+            TP_PUBLISH(&s.act);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int j = c & 1;
+                SPLIT_STRESS_WARP(wd, 0x02);
+                if (!mbar_wait(&s.d1_full[j], d1f_phase[j], 0x0200 + c, wd)) goto done;
+                d1f_phase[j] ^= 1; tc_fence_after();
+                if (c >= 2) {
+                    if (!mbar_wait(&s.cb_free[j], cbf_phase[j], 0x0210 + c, wd)) goto done;
+                    cbf_phase[j] ^= 1;
+                }
+                epilogue_split(tl + (j ? kTDB : kTDA), half * 64, 64, s.big + j * 65536, 32768u, kPlane, row, s.gb + c * 128);
+                TP_PUBLISH(&s.d1_act[j]);
+            }
+            TP_WAIT_ACC(0x0101)
+            epilogue_split(tl + kTD2, half * 128, 128, s.big, 65536u, kPlane, row, s.bd2);
+            TP_PUBLISH(&s.act);
+            TP_WAIT_ACC(0x0102)
+            epilogue_split(tl + kTDA, half * 64, 64, s.big, 32768u, kPlane, row, s.bd3);
+            TP_PUBLISH(&s.act);
+            TP_WAIT_ACC(0x0103)
+            {
+                uint32_t v0[32], v1[32];
+                const int c0 = half * 64;
+                tmem_ld32(tl + kTDB + c0, v0);
+                tmem_ld32(tl + kTDB + c0 + 32, v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                float l0 = 0.f, l1 = 0.f, m0 = 0.f, m1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float ya = fmaxf(__uint_as_float(v0[i]) + s.bd4[c0 + i], 0.f);
+                    const float yb = fmaxf(__uint_as_float(v1[i]) + s.bd4[c0 + 32 + i], 0.f);
+                    l0 = fmaf(ya, s.w5[c0 + i], l0);       l1 = fmaf(ya, s.w5[128 + c0 + i], l1);
+                    m0 = fmaf(yb, s.w5[c0 + 32 + i], m0);  m1 = fmaf(yb, s.w5[128 + c0 + 32 + i], m1);
+                }
+                l0 += m0; l1 += m1;
+                if (half == 1) { s.lpart[row] = l0; s.lpart[kTile + row] = l1; }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (half == 0 && valid) {
+                    const float f0 = (s.b5[0] + l0) + s.lpart[row];
+                    const float f1 = (s.b5[1] + l1) + s.lpart[kTile + row];
+                    const int64_t o = (int64_t)b * p.n + pidx;
+                    *reinterpret_cast<float2 *>(p.logits + o * 2) = make_float2(f0, f1);
+                    p.mask[o] = (f0 < f1) ? 1 : 0;
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
+        }
+#undef TP_PUBLISH
+#undef TP_WAIT_ACC
+    }
+done:
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // the pair's MMAs touch both CTAs: leave together
+    if (warp == 0) tmem_dealloc_pair<512>(tmem);
+}
+
 }  // namespace split
 }  // namespace al3d
 
@@ -715,6 +971,18 @@ extern "C" int al3d_seg_pass2_bf16x3(const al3d_split_tail_weights *w, const flo
     const int64_t items = (int64_t)bs * p.tiles_per_obj;
     AL3D_CHECK_ARG(items < (1ll << 31), "al3d_seg_pass2_bf16x3: too many tiles");
     p.n_items = (int)items;
+    if (w->wstream_pair != nullptr && p.n_items >= 2) {
+        // CTA pairs: each CTA streams its half of every weight slot (two per-CTA images in wstream_pair)
+        p.wstream = (const uint8_t *)w->wstream_pair;
+        int grid = std::min(p.n_items, tc_num_sms());
+        grid = ((grid + 1) / 2) * 2;                     // whole pairs; a ghost CTA recomputes the last tile without output
+        if (grid > tc_num_sms()) grid -= 2;
+        const size_t smem = sizeof(TailPairSmem) + 128;
+        AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_tail_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        split_tail_pair_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);     // __cluster_dims__(2,1,1)
+        AL3D_CHECK_LAUNCH("split_tail_pair_kernel");
+        return 0;
+    }
     const int grid = std::min(p.n_items, tc_num_sms());
     const size_t smem = sizeof(TailSmem) + 128;
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -6,6 +6,7 @@ MMA thread consumes them.  The kernels split the activations the same way on the
 a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation: 16 significant bits per operand.
 """
 import ctypes
+import os
 
 import torch
 
@@ -25,7 +26,13 @@ class SplitTailWeightsStruct(ctypes.Structure):
     _fields_ = [("c_in", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("w1_w", ctypes.c_void_p), ("w1_b", ctypes.c_void_p), ("b2", ctypes.c_void_p),
                 ("bd2", ctypes.c_void_p), ("bd3", ctypes.c_void_p), ("bd4", ctypes.c_void_p),
-                ("w5", ctypes.c_void_p), ("b5", ctypes.c_void_p), ("wstream", ctypes.c_void_p)]
+                ("w5", ctypes.c_void_p), ("b5", ctypes.c_void_p), ("wstream", ctypes.c_void_p), ("wstream_pair", ctypes.c_void_p)]
+
+# The CTA-pair (cta_group::2) variant of the tail kernel halves the weight bytes per SM and doubles the ring depth; measured
+# it is NOT faster (39.6 ms vs 37.3 ms at 8192 x 4096: the kernel is bound by its unhidden epilogues, not by the weight
+# stream, and every hand-over gains a cluster round trip), so it is off by default.  AL3D_SPLIT_PAIR=1 selects it; the
+# tests keep it bit-identical to the single-CTA kernel.
+USE_PAIR_KERNEL = os.environ.get("AL3D_SPLIT_PAIR", "0") == "1"
 
 
 def split_hi_lo(w):
@@ -45,6 +52,27 @@ def _slots(w_blk):
     """(rows <= 128, 64) fp32 -> [hi slot, lo slot]."""
     hi, lo = split_hi_lo(w_blk.float())
     return [_slot(hi), _slot(lo)]
+
+
+def _half_slot(w_bf16):
+    flat = kp_pack(w_bf16)
+    out = torch.zeros(BLOCK_ELEMS // 2, dtype=torch.bfloat16, device=w_bf16.device)
+    out[: flat.numel()] = flat
+    return out
+
+
+def _pair_images(blocks):
+    """blocks: list of (rows <= 128, 64) fp32 weight blocks in consumption order -> the two per-CTA images of the CTA-pair
+    kernel: CTA r keeps rows [r*R/2, (r+1)*R/2) of every block, as 8 KB half slots (hi then lo)."""
+    imgs = []
+    for r in range(2):
+        parts = []
+        for w in blocks:
+            R = w.shape[0]
+            hi, lo = split_hi_lo(w[r * (R // 2):(r + 1) * (R // 2)].float())
+            parts += [_half_slot(hi), _half_slot(lo)]
+        imgs.append(torch.cat(parts))
+    return torch.cat(imgs).contiguous()
 
 
 def _layer_slots(w):
@@ -86,20 +114,14 @@ class SplitSegPack:
         wd1, wd2, wd3, wd4 = (fw[k][0] for k in ("dconv1", "dconv2", "dconv3", "dconv4"))
 
         def d1(c):                     # dconv1 output channels c*128..+128 on the 64 per-point input channels
-            return _slots(wd1[c * 128:(c + 1) * 128, 0:64])
+            return [wd1[c * 128:(c + 1) * 128, 0:64]]
 
         def p(c):                      # dconv2 partial sum over input channels c*128..+128: (row half, k block)
-            out = []
-            for nc in range(2):
-                for kb in range(2):
-                    out += _slots(wd2[nc * 128:(nc + 1) * 128, c * 128 + kb * 64:c * 128 + (kb + 1) * 64])
-            return out
+            return [wd2[nc * 128:(nc + 1) * 128, c * 128 + kb * 64:c * 128 + (kb + 1) * 64] for nc in range(2) for kb in range(2)]
 
-        slots = _slots(fw["conv2"][0]) + d1(0) + d1(1) + d1(2) + p(0) + d1(3) + p(1) + p(2) + p(3)
-        for kb in range(4):
-            slots += _slots(wd3[:, kb * 64:(kb + 1) * 64])
-        for kb in range(2):
-            slots += _slots(wd4[:, kb * 64:(kb + 1) * 64])
+        blocks = [fw["conv2"][0]] + d1(0) + d1(1) + d1(2) + p(0) + d1(3) + p(1) + p(2) + p(3)
+        blocks += [wd3[:, kb * 64:(kb + 1) * 64] for kb in range(4)] + [wd4[:, kb * 64:(kb + 1) * 64] for kb in range(2)]
+        slots = [sl for blk in blocks for sl in _slots(blk)]
         assert len(slots) == 54
         self.t = {"w1_w": _pad8(fw["conv1"][0]), "w1_b": fw["conv1"][1].contiguous(), "b2": fw["conv2"][1].contiguous(),
                   "bd2": fw["dconv2"][1].contiguous(), "bd3": fw["dconv3"][1].contiguous(),
@@ -109,6 +131,9 @@ class SplitSegPack:
         s.c_in = c_in
         for k, v in self.t.items():
             setattr(s, k, v.data_ptr())
+        if USE_PAIR_KERNEL:
+            self.t["wstream_pair"] = _pair_images(blocks)
+            s.wstream_pair = self.t["wstream_pair"].data_ptr()
         self.struct = s
         self.w_glob = wd1[:, 64:]          # the 1024-wide half of dconv1 acts on the per-object global feature: fp32
         self.b_d1 = fw["dconv1"][1]
@@ -145,7 +170,7 @@ def seg_forward(pack, fw, pts):
     mask = torch.empty((bs, n), device=pts.device, dtype=torch.bool)
     sb, sc, sp = pts.stride()
     check_abort("seg_pass2_bf16x3 launch", pts.device)
-    with _timed("split_tail_kernel"):
+    with _timed("split_tail_kernel"):        # (the CTA-pair variant when pack.struct.wstream_pair is set)
         _lib.check(_lib.lib().al3d_seg_pass2_bf16x3(ctypes.byref(pack.struct), pts.data_ptr(), sb, sc, sp, bs, n,
                                                     gbias.data_ptr(), logits.data_ptr(), mask.data_ptr(), ops._stream()),
                    "seg_pass2_bf16x3")

@@ -400,6 +400,8 @@ typedef struct al3d_split_tail_weights {
     const float *bd2, *bd3, *bd4;  /* dconv2-4 biases (256),(128),(128)                             */
     const float *w5, *b5;          /* dconv5 fp32 (2,128), (2)                                      */
     const void  *wstream;          /* 54 slots: conv2 | d1(0) d1(1) d1(2) p(0) d1(3) p(1) p(2) p(3) | dconv3 | dconv4 (csrc/chain_split.cu) */
+    const void  *wstream_pair;     /* NULL, or the same 54 slots as two per-CTA images of 8 KB half slots (CTA r: rows
+                                      [r*R/2, (r+1)*R/2) of every block): selects the CTA-pair (cta_group::2) kernel */
 } al3d_split_tail_weights;
 /* Same contract as al3d_seg_pass2_bf16. */
 int al3d_seg_pass2_bf16x3(const al3d_split_tail_weights *w, const float *x, int64_t sb, int64_t sc, int64_t sp,

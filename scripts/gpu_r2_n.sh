@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/n_build.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_tensorcore.py -m gpu -x -q -k "split" > gpurun_out/n_tc.log 2>&1; echo "tc rc=$?"
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-crop --no-e2e --no-fast-mode > gpurun_out/n_bench1.json 2> gpurun_out/n_bench1.err; echo "bench rc=$?"
+tail -3 gpurun_out/n_tc.log; python -c "
+import json;d=json.loads(open('gpurun_out/n_bench1.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['kernel_ms'],d['roofline']['executed_frac'])"

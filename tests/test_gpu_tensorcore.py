@@ -160,3 +160,23 @@ def test_split_seg_matches_fp64(C, n, bs):
     ref = d @ fw["dconv5"][0].double().t() + fw["dconv5"][1].double()
     assert rel_err(logits.cpu(), ref.cpu()) < 3e-4, rel_err(logits.cpu(), ref.cpu())
     assert torch.equal(mask, logits[..., 0] < logits[..., 1])
+
+
+def test_split_tail_pair_kernel_equals_single_cta_kernel():
+    """The CTA-pair (cta_group::2) tail kernel issues the same MMAs in the same order as the single-CTA one: bit-identical
+    logits, for even / odd tile counts (ghost CTA) and ragged last tiles."""
+    sd = synth.random_state_dict("static_one", seed=6)
+    fw = _dev(fold_state_dict(sd, "ins_seg", spec.seg_layers(3)))
+    torch.manual_seed(2)
+    for n, bs in [(4096, 3), (1000, 3), (129, 1), (300, 311), (128, 1)]:
+        x = (torch.randn(bs, n, 3, device=DEV) * torch.tensor([2.0, 2.0, 0.7], device=DEV)).transpose(2, 1)
+        keep = es.USE_PAIR_KERNEL
+        try:
+            es.USE_PAIR_KERNEL = True
+            lp, mp = es.seg_forward(es.pack_seg(fw, 3), fw, x)
+            es.USE_PAIR_KERNEL = False
+            ls, ms = es.seg_forward(es.pack_seg(fw, 3), fw, x)
+        finally:
+            es.USE_PAIR_KERNEL = keep
+        torch.cuda.synchronize()
+        assert torch.equal(lp, ls) and torch.equal(mp, ms), (n, bs)
