@@ -82,7 +82,7 @@ def bench_sweep(n_frames):
     sd = synth.random_state_dict("static_one", seed=synth.REFERENCE_SEED)
     m = sm.StaticModelOneBoxEst().to(DEV).eval()
     m.load_state_dict(sd)
-    m.precision = "bf16"
+    m.precision = "bf16x3"
     sw = sweep.StaticSweep(m)
     out = sw.run(frames)
     torch.cuda.synchronize()
@@ -101,7 +101,7 @@ def _calibrated(kind, cls, pts, aux):
     sd = synth.random_state_dict(kind, seed=synth.REFERENCE_SEED)
     m = cls().to(DEV).eval()
     m.load_state_dict(sd)
-    m.precision = "bf16"
+    m.precision = "bf16x3"
     with torch.no_grad():
         lg = m(pts[:64], aux[:64], aux[:64] if kind != "dynamic" else None)["logits"]
     synth.calibrate_seg_margin(sd, lg, fg_fraction=0.125 if kind != "dynamic" else 0.5)
@@ -116,7 +116,7 @@ def bench_dynamic():
         pts = torch.from_numpy(np.tile(tr["pts_pm"], (rep, 1, 1))[:bs]).to(DEV).transpose(2, 1)
         box = torch.from_numpy(np.tile(tr["box_sm"], (rep, 1, 1))[:bs]).to(DEV).transpose(2, 1)
         m = _calibrated("dynamic", dm.DynamicModel, pts, box)
-        for prec in ("bf16", "fp32") if bs == 64 else ("bf16",):
+        for prec in ("bf16x3", "bf16", "fp32") if bs == 64 else ("bf16x3", "bf16"):
             m.precision = prec
             ms = timed(lambda: m(pts, box, None), iters=5)
             fl = spec.flops_per_object("dynamic", 5120)
@@ -130,7 +130,7 @@ def bench_static32():
     ib, gt = torch.from_numpy(tr["init_box"]).to(DEV), torch.from_numpy(tr["bbox_gt"]).to(DEV)
     for kind, cls in (("static_one", sm.StaticModelOneBoxEst), ("static_two", sm.StaticModelTwoBoxEst)):
         m = _calibrated(kind, cls, pts, ib)
-        for prec in ("bf16", "fp32"):
+        for prec in ("bf16x3", "bf16", "fp32"):
             m.precision = prec
             ms = timed(lambda: m(pts, ib, gt), iters=10)
             print(json.dumps({"bench": "static32", "model": kind, "tracks": 32, "precision": prec, "ms": ms,
