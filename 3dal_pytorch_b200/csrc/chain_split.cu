@@ -411,14 +411,23 @@ done:
 // ================================================================================================
 // split_tail_kernel -- second half of the segmentation net in split precision
 //
-// Shared memory: A2 (conv2 output, 64 ch, hi | lo: 32 KB, kept for the four dconv1 chunks) | BIG (128 KB): two
-// chunk buffers CB[0..1] of 128 channels (hi | lo: 64 KB each); earlier in the tile CB[0]'s place holds A1 (conv1
-// output), later all of BIG holds A3 (dconv2 output, 256 ch) and then A4 (dconv3 output, 128 ch) | weight ring.
-// TMEM: D2 = dconv2 accumulator [0,256) | DA [256,384): conv2 accumulator, dconv1 chunks 0 / 2, dconv3 accumulator |
-// DB [384,512): dconv1 chunks 1 / 3, dconv4 accumulator.
-// Weight stream per tile (16 KB slots, hi then lo per block): conv2 | d1(0) | d1(1) | d1(2) | p(0) | d1(3) | p(1) |
-// p(2) | p(3) | dconv3 | dconv4, where d1(c) = dconv1 output channels c*128.., p(c) = dconv2 partial sum over input
-// channels c*128.. as (row half, k block) x 4.
+// Shared memory: A2 (32 KB: conv1 output A1, converted in place into the conv2 output A2, kept for the four dconv1
+// chunks) | BIG (128 KB): two chunk buffers CB[0..1] of 128 channels (hi | lo: 64 KB each); later all of BIG holds A3
+// (dconv2 output, 256 ch) and then A4 (dconv3 output, 128 ch) | weight ring.
+// TMEM: D2 = dconv2 accumulator [0,256); once it is drained, dconv4's accumulator sits in [0,128) and the NEXT tile's
+// conv2 accumulator in [128,192) | DA [256,384): dconv1 chunks 0 / 2, dconv3 accumulator | DB [384,512): chunks 1 / 3.
+//
+// Software pipeline across tiles (measured with scripts/split_timeline.py; profiles/r2_split_tail_timeline.txt): the
+// front of tile k+1 -- input loads, conv1 on CUDA cores, conv2, dconv1 chunks 0 and 1 -- runs UNDER tile k's dconv3 /
+// dconv4, whose shared-memory and TMEM regions are disjoint from it by then; the dconv2 and dconv3 epilogues hand their
+// output over per 64-channel K slab so the next layer's MMAs start after the first slab; and tile k's logits are
+// computed from registers after chunk 0 of tile k+1 has been handed to the issuer.
+// Weight stream image (16 KB slots, hi then lo per block): conv2 | d1(0) | d1(1) | d1(2) | p(0) | d1(3) | p(1) | p(2) |
+// p(3) | dconv3 | dconv4, where d1(c) = dconv1 output channels c*128.., p(c) = dconv2 partial sum over input channels
+// c*128.. as (row half, k block) x 4.  Steady-state consumption order per tile: d1(2) .. dconv3 | conv2' | dconv4 |
+// d1(0)' | d1(1)' (primes: next tile).
+// Every mbarrier is private to one buffer / accumulator and completes exactly once (a1/a2/c2/d2/a3/d3/a4/d4) or twice
+// (d1_full/d1_act per chunk buffer, strictly alternating with its consumer) per tile, so no parity wait can be lapped.
 // ================================================================================================
 struct TailParams {
     const float *x; int64_t sb, sc, sp; int bs, n; int c_in;
@@ -433,6 +442,7 @@ struct TailParams {
 };
 constexpr int kTailStages = 3;
 constexpr int kTailBlocks = 2 + 4 * 2 + 4 * 8 + 8 + 4;       // 54 slots per tile
+constexpr int kBlkConv2 = 0, kBlkD1a = 2, kBlkSteady = 6, kBlkD4 = 50;   // conv2 (2) | d1(0), d1(1) (4) | d1(2) .. dconv3 (44) | dconv4 (4)
 struct TailSmem {
     uint8_t a2[32768];
     uint8_t big[131072];
@@ -440,12 +450,26 @@ struct TailSmem {
     float w1_w[64 * 8], w1_b[64], b2[64], gb[512], bd2[256], bd3[128], bd4[128], w5[256], b5[2];
     float lpart[2 * kTile];
     uint64_t w_full[kTailStages], w_empty[kTailStages];
-    uint64_t act, acc;                             // serial hand-overs: operand ready / accumulator complete
+    uint64_t a1_ready, c2_full, a2_ready;          // front of a tile: conv1 output written / conv2 accumulator / conv2 output written
     uint64_t d1_full[2], d1_act[2], cb_free[2];    // per chunk buffer: accumulator ready / operand written / operand consumed
+    uint64_t d2_full, a3_ready[4], d3_full, a4_ready[2], d4_full;
     uint32_t tmem_base;
 };
 static_assert(sizeof(TailSmem) + 128 <= 232448, "TailSmem exceeds the 227 KB opt-in limit");
-constexpr uint32_t kTD2 = 0, kTDA = 256, kTDB = 384;
+constexpr uint32_t kTD2 = 0, kTDA = 256, kTDB = 384, kTD4 = 0, kTC2 = 128;
+
+// Timeline build (scripts/split_timeline.py): CTA 0's MMA issuer and first epilogue thread stamp (id, %clock) pairs into
+// the scratch area behind the status word.
+#ifdef AL3D_SPLIT_TIMELINE
+#define TL_STAMP(id) do { if (blockIdx.x == 0 && tl_n < 1500) { unsigned int c_; asm volatile("mov.u32 %0, %%clock;" : "=r"(c_)); \
+                          tl_buf[tl_n * 2] = (unsigned int)(id); tl_buf[tl_n * 2 + 1] = c_; ++tl_n; } } while (0)
+#define TL_STAMP_DECL(off) unsigned int *tl_buf = p.wd.word + (off); int tl_n = 0;
+#define TL_STAMP_E(id) do { if (etid == 0) TL_STAMP(id); } while (0)
+#else
+#define TL_STAMP(id) do { } while (0)
+#define TL_STAMP_E(id) do { } while (0)
+#define TL_STAMP_DECL(off)
+#endif
 
 __global__ void __launch_bounds__(kThreads, 1)
 split_tail_kernel(const TailParams p)
@@ -461,9 +485,13 @@ split_tail_kernel(const TailParams p)
     for (int i = threadIdx.x; i < 128; i += kThreads) { s.bd3[i] = p.bd3[i]; s.bd4[i] = p.bd4[i]; }
     if (threadIdx.x < 2) s.b5[threadIdx.x] = p.b5[threadIdx.x];
     if (threadIdx.x == 0) {
+        constexpr int kW = kEpiThreads / 32;
         for (int i = 0; i < kTailStages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
-        mbar_init(&s.act, kEpiThreads / 32); mbar_init(&s.acc, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kEpiThreads / 32); mbar_init(&s.cb_free[i], 1); }
+        mbar_init(&s.a1_ready, kW); mbar_init(&s.c2_full, 1); mbar_init(&s.a2_ready, kW);
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.d1_full[i], 1); mbar_init(&s.d1_act[i], kW); mbar_init(&s.cb_free[i], 1); }
+        mbar_init(&s.d2_full, 1); mbar_init(&s.d3_full, 1); mbar_init(&s.d4_full, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&s.a3_ready[i], kW);
+        for (int i = 0; i < 2; ++i) mbar_init(&s.a4_ready[i], kW);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<512>(&s.tmem_base);
@@ -471,51 +499,75 @@ split_tail_kernel(const TailParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
+    const int item0 = blockIdx.x, stride = gridDim.x;
 #define TL_ARRIVE(bar) do { __syncwarp(); if (lane == 0) mbar_arrive(bar); } while (0)
 
-    if (warp == 0) {
+    if (item0 >= p.n_items) {
+        // nothing to do for this CTA
+    } else if (warp == 0) {
         // ------------------------------------------------------------ weight producer
         if (elect_one_sync()) {
             int stage = 0; uint32_t phase = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                for (int blk = 0; blk < kTailBlocks; ++blk) {
-                    SPLIT_STRESS(wd, 0x31);
-                    if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x3100 + stage, wd)) goto done;
-                    mbar_arrive_expect_tx(&s.w_full[stage], kStage);
-                    bulk_g2s(s.ring[stage], p.wstream + (size_t)blk * kStage, kStage, &s.w_full[stage]);
-                    if (++stage == kTailStages) { stage = 0; phase ^= 1; }
-                }
+#define TL_PUSH(first, count)                                                                         \
+            for (int blk = (first); blk < (first) + (count); ++blk) {                                 \
+                SPLIT_STRESS(wd, 0x31);                                                               \
+                if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x3100 + stage, wd)) goto done;          \
+                const uint32_t bytes_ = blk < kBlkD1a ? kStage / 2 : kStage;   /* conv2: 64 rows */   \
+                mbar_arrive_expect_tx(&s.w_full[stage], bytes_);                                      \
+                bulk_g2s(s.ring[stage], p.wstream + (size_t)blk * kStage, bytes_, &s.w_full[stage]);  \
+                if (++stage == kTailStages) { stage = 0; phase ^= 1; }                                \
             }
+            TL_PUSH(kBlkConv2, 2)
+            TL_PUSH(kBlkD1a, 4)
+            for (int item = item0; item < p.n_items; item += stride) {
+                const bool has_next = item + stride < p.n_items;
+                TL_PUSH(kBlkSteady, kBlkD4 - kBlkSteady)
+                if (has_next) { TL_PUSH(kBlkConv2, 2) }
+                TL_PUSH(kBlkD4, 4)
+                if (has_next) { TL_PUSH(kBlkD1a, 4) }
+            }
+#undef TL_PUSH
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (elect_one_sync()) {
             RingView ring{smem_u32(s.ring[0]), s.w_full, s.w_empty, kTailStages, 0, 0u};
-            uint32_t act_phase = 0, d1a_phase[2] = {0, 0};
+            uint32_t d1a_phase[2] = {0, 0};
             const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128);
             const uint32_t a2 = smem_u32(s.a2), big = smem_u32(s.big);
-#define TL_WAIT_ACT(code)                                                        \
+            TL_STAMP_DECL(1024)
+#define TL_WAIT(bar, par, code)                                                  \
             SPLIT_STRESS(wd, 0x32);                                              \
-            if (!mbar_wait(&s.act, act_phase, code, wd)) goto done;              \
-            act_phase ^= 1; tc_fence_after();
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                // conv2: A1 (64 ch in CB[0]'s place, lo half at +16 KB) -> DA
-                TL_WAIT_ACT(0x3200)
-                SPLIT_MMA_BLOCK(ring, tmem + kTDA, big, 16384u, kPlane, 128, 64, id64, true, 0x3300)
-                mma_commit(&s.acc);
-                TL_WAIT_ACT(0x3201)                                  // A2 in place
-                // dconv1 chunk c: A2 x Wd1[c*128.., 0:64] -> DA / DB
+            if (!mbar_wait(bar, par, code, wd)) goto done;                       \
+            tc_fence_after();
+            // dconv1 chunk c: A2 x Wd1[c*128.., 0:64] -> DA / DB
 #define TL_ISSUE_D1(c)                                                                                        \
-                { SPLIT_MMA_BLOCK(ring, tmem + (((c) & 1) ? kTDB : kTDA), a2, 16384u, kPlane, 128, 128, id128, true, 0x3310) \
-                  mma_commit(&s.d1_full[(c) & 1]); }
-                TL_ISSUE_D1(0)
-                TL_ISSUE_D1(1)
+            { SPLIT_MMA_BLOCK(ring, tmem + (((c) & 1) ? kTDB : kTDA), a2, 16384u, kPlane, 128, 128, id128, true, 0x3310) \
+              mma_commit(&s.d1_full[(c) & 1]); }
+            // front of a tile: conv2 on A1 (in A2's place, lo half at +16 KB) -> [kTC2, +64); then chunks 0 and 1
+#define TL_ISSUE_CONV2(par)                                                                                   \
+            { TL_WAIT(&s.a1_ready, par, 0x3200)                                                               \
+              SPLIT_MMA_BLOCK(ring, tmem + kTC2, a2, 16384u, kPlane, 128, 64, id64, true, 0x3300)             \
+              mma_commit(&s.c2_full); }
+#define TL_ISSUE_D1_FIRST(par)                                                                                \
+            { TL_WAIT(&s.a2_ready, par, 0x3201)                                                               \
+              TL_ISSUE_D1(0)                                                                                  \
+              TL_ISSUE_D1(1) }
+            TL_ISSUE_CONV2(0u)
+            TL_ISSUE_D1_FIRST(0u)
+            uint32_t k = 0;                                            // local tile counter; once-per-tile barriers: parity k & 1
+            for (int item = item0; item < p.n_items; item += stride, ++k) {
+                const bool has_next = item + stride < p.n_items;
+                const uint32_t par = k & 1;
+                TL_STAMP(0x100);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int j = c & 1;
                     SPLIT_STRESS(wd, 0x34);
-                    if (!mbar_wait(&s.d1_act[j], d1a_phase[j], 0x3400 + c, wd)) goto done;     // CB[j] written, DA / DB drained
+                    // CB[j] written, DA / DB drained (c == 0: also the previous tile's dconv4 accumulator in [0,128))
+                    if (!mbar_wait(&s.d1_act[j], d1a_phase[j], 0x3400 + c, wd)) goto done;
                     d1a_phase[j] ^= 1; tc_fence_after();
+                    TL_STAMP(0x110 + c);
                     if (c + 2 < 4) TL_ISSUE_D1(c + 2)
                     // dconv2 partial sum over input channels c*128..+128: D2[:, nc*128..] += CB[j] x Wd2[nc*128.., c*128..]
                     const uint32_t cb = big + j * 65536;
@@ -523,87 +575,142 @@ split_tail_kernel(const TailParams p)
                         for (int kb = 0; kb < 2; ++kb)
                             SPLIT_MMA_BLOCK(ring, tmem + kTD2 + nc * 128, cb + kb * 8 * kPlane, 32768u, kPlane, 128, 128, id128, c == 0 && kb == 0, 0x3320)
                     if (c + 2 < 4) mma_commit(&s.cb_free[j]);          // chunk c + 2 may overwrite CB[j] once these have run
+                    TL_STAMP(0x120 + c);
                 }
-                mma_commit(&s.acc);                                   // dconv2 accumulator complete
-                // dconv3: A3 (256 ch over all of BIG, lo half at +64 KB) -> DA
-                TL_WAIT_ACT(0x3202)
-                for (int kb = 0; kb < 4; ++kb)
+                mma_commit(&s.d2_full);
+                // dconv3: A3 (256 ch over all of BIG, lo half at +64 KB) -> DA, slab by slab
+                for (int kb = 0; kb < 4; ++kb) {
+                    TL_WAIT(&s.a3_ready[kb], par, 0x3500 + kb)
+                    TL_STAMP(0x130 + kb);
                     SPLIT_MMA_BLOCK(ring, tmem + kTDA, big + kb * 8 * kPlane, 65536u, kPlane, 128, 128, id128, kb == 0, 0x3330)
-                mma_commit(&s.acc);
-                // dconv4: A4 (128 ch, lo half at +32 KB) -> DB
-                TL_WAIT_ACT(0x3203)
-                for (int kb = 0; kb < 2; ++kb)
-                    SPLIT_MMA_BLOCK(ring, tmem + kTDB, big + kb * 8 * kPlane, 32768u, kPlane, 128, 128, id128, kb == 0, 0x3340)
-                mma_commit(&s.acc);
+                }
+                mma_commit(&s.d3_full);
+                TL_STAMP(0x138);
+                if (has_next) TL_ISSUE_CONV2(par ^ 1)                  // D2 is drained: every A3 slab has been written
+                TL_STAMP(0x139);
+                // dconv4: A4 (128 ch, lo half at +32 KB) -> [0,128)
+                for (int kb = 0; kb < 2; ++kb) {
+                    TL_WAIT(&s.a4_ready[kb], par, 0x3600 + kb)
+                    TL_STAMP(0x140 + kb);
+                    SPLIT_MMA_BLOCK(ring, tmem + kTD4, big + kb * 8 * kPlane, 32768u, kPlane, 128, 128, id128, kb == 0, 0x3340)
+                }
+                mma_commit(&s.d4_full);
+                TL_STAMP(0x148);
+                if (has_next) TL_ISSUE_D1_FIRST(par ^ 1)               // DA: dconv3's accumulator drained (A4 written); DB: chunk 3 drained
+                TL_STAMP(0x149);
             }
+#undef TL_ISSUE_D1_FIRST
+#undef TL_ISSUE_CONV2
 #undef TL_ISSUE_D1
-#undef TL_WAIT_ACT
+#undef TL_WAIT
         }
     } else {
         // ------------------------------------------------------------ epilogue warps (256 threads)
         const int row = epi_row(), half = epi_half();
         const uint32_t tl = tmem + ((uint32_t)(row & ~31) << 16);
         const int etid = threadIdx.x - 64;
-        uint32_t acc_phase = 0, d1f_phase[2] = {0, 0}, cbf_phase[2] = {0, 0};
-#define TL_WAIT_ACC(code)                                                        \
+        uint32_t d1f_phase[2] = {0, 0}, cbf_phase[2] = {0, 0};
+        TL_STAMP_DECL(8192)
+#define TL_WAIT(bar, par, code)                                                  \
         SPLIT_STRESS_WARP(wd, 0x21);                                             \
-        if (!mbar_wait(&s.acc, acc_phase, code, wd)) goto done;                  \
-        acc_phase ^= 1; tc_fence_after();
+        if (!mbar_wait(bar, par, code, wd)) goto done;                           \
+        tc_fence_after();
 #define TL_PUBLISH(bar) do { tc_fence_before(); fence_proxy_async_smem(); TL_ARRIVE(bar); } while (0)
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const int b = item / p.tiles_per_obj, t = item % p.tiles_per_obj;
-            const int pidx_raw = t * kTile + row;
-            const bool valid = pidx_raw < p.n;
-            const int pidx = valid ? pidx_raw : p.n - 1;
-            // per-object dconv1 bias (nobody reads s.gb between the previous tile's chunk epilogues and this barrier)
-            for (int i = etid; i < 512; i += kEpiThreads) s.gb[i] = __ldg(p.gbias + (int64_t)b * 512 + i);
-            // ---- conv1 on CUDA cores -> A1 (in CB[0]'s place; the previous tile's dconv4 has finished reading A4 there)
-            {
-                const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
-                float xv[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
-                first_layer_split(s.big, 16384u, row, xv, p.c_in, 64, half * 32, 32, s.w1_w, s.w1_b);
-                TL_PUBLISH(&s.act);
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");            // s.gb complete
-            // ---- conv2 epilogue: DA (64 columns) -> A2
-            TL_WAIT_ACC(0x2100)
-            epilogue_split(tl + kTDA, half * 32, 32, s.a2, 16384u, kPlane, row, s.b2);
-            TL_PUBLISH(&s.act);
-            // ---- dconv1 chunk epilogues: DA / DB (128 columns) + per-object bias -> CB[j]
+        // input point + per-object bias of a tile -> registers (the loads are issued early, consumed by TL_FRONT)
+        float xv[8], gbv[2];
+#define TL_LOAD(item_, b_, pidx_, valid_)                                                                     \
+        {                                                                                                     \
+            b_ = (item_) / p.tiles_per_obj;                                                                   \
+            const int pr_ = ((item_) % p.tiles_per_obj) * kTile + row;                                        \
+            valid_ = pr_ < p.n; pidx_ = valid_ ? pr_ : p.n - 1;                                               \
+            const float *px_ = p.x + (int64_t)(b_) * p.sb + (int64_t)(pidx_) * p.sp;                          \
+            _Pragma("unroll")                                                                                 \
+            for (int c_ = 0; c_ < 8; ++c_) xv[c_] = (c_ < p.c_in) ? __ldg(px_ + c_ * p.sc) : 0.f;             \
+            gbv[0] = __ldg(p.gbias + (int64_t)(b_) * 512 + etid);                                             \
+            gbv[1] = __ldg(p.gbias + (int64_t)(b_) * 512 + 256 + etid);                                       \
+        }
+        // conv1 on CUDA cores -> A1 in A2's place (every dconv1 chunk of the previous tile has read A2); per-object
+        // bias -> s.gb (every chunk epilogue of the previous tile has read it)
+#define TL_FRONT()                                                                                            \
+        {                                                                                                     \
+            s.gb[etid] = gbv[0]; s.gb[256 + etid] = gbv[1];                                                   \
+            first_layer_split(s.a2, 16384u, row, xv, p.c_in, 64, half * 32, 32, s.w1_w, s.w1_b);              \
+            TL_PUBLISH(&s.a1_ready);                                                                          \
+            asm volatile("bar.sync 1, 256;" ::: "memory");            /* s.gb complete; s.lpart consumed */   \
+        }
+        // conv2 epilogue: [kTC2, +64) -> A2, in place of A1
+#define TL_CONV2_EPI(par)                                                                                     \
+        {                                                                                                     \
+            TL_WAIT(&s.c2_full, par, 0x2100)                                                                  \
+            epilogue_split(tl + kTC2, half * 32, 32, s.a2, 16384u, kPlane, row, s.b2);                        \
+            TL_PUBLISH(&s.a2_ready);                                                                          \
+        }
+        // dconv1 chunk epilogue: DA / DB (128 columns) + per-object bias -> CB[c & 1]
+#define TL_CHUNK_EPI(c)                                                                                       \
+        {                                                                                                     \
+            const int j_ = (c) & 1;                                                                           \
+            SPLIT_STRESS_WARP(wd, 0x22);                                                                      \
+            if (!mbar_wait(&s.d1_full[j_], d1f_phase[j_], 0x2200 + (c), wd)) goto done;                       \
+            d1f_phase[j_] ^= 1; tc_fence_after();                                                             \
+            if ((c) >= 2) {                                                                                   \
+                if (!mbar_wait(&s.cb_free[j_], cbf_phase[j_], 0x2210 + (c), wd)) goto done;   /* dconv2 partial c - 2 has read CB[j] */ \
+                cbf_phase[j_] ^= 1;                                                                           \
+            }                                                                                                 \
+            epilogue_split(tl + (j_ ? kTDB : kTDA), half * 64, 64, s.big + j_ * 65536, 32768u, kPlane, row, s.gb + (c) * 128); \
+            TL_PUBLISH(&s.d1_act[j_]);                                                                        \
+        }
+        int b, pidx; bool valid;
+        TL_LOAD(item0, b, pidx, valid)
+        TL_FRONT()
+        TL_CONV2_EPI(0u)
+        TL_CHUNK_EPI(0)
+        uint32_t k = 0;
+        for (int item = item0; item < p.n_items; item += stride, ++k) {
+            const bool has_next = item + stride < p.n_items;
+            const uint32_t par = k & 1;
+            int nb = 0, npidx = 0; bool nvalid = false;
+            TL_STAMP_E(0x200);
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int j = c & 1;
-                SPLIT_STRESS_WARP(wd, 0x22);
-                if (!mbar_wait(&s.d1_full[j], d1f_phase[j], 0x2200 + c, wd)) goto done;
-                d1f_phase[j] ^= 1; tc_fence_after();
-                if (c >= 2) {
-                    if (!mbar_wait(&s.cb_free[j], cbf_phase[j], 0x2210 + c, wd)) goto done;     // dconv2 partial c - 2 has read CB[j]
-                    cbf_phase[j] ^= 1;
-                }
-                epilogue_split(tl + (j ? kTDB : kTDA), half * 64, 64, s.big + j * 65536, 32768u, kPlane, row, s.gb + c * 128);
-                TL_PUBLISH(&s.d1_act[j]);
+            for (int c = 1; c < 4; ++c) TL_CHUNK_EPI(c)
+            TL_STAMP_E(0x201);
+            if (has_next) TL_LOAD(item + stride, nb, npidx, nvalid)
+            // ---- dconv2 epilogue: D2 (256 columns) -> A3 over all of BIG (every partial sum has been consumed), per K slab
+            TL_WAIT(&s.d2_full, par, 0x2101)
+            TL_STAMP_E(0x202);
+#pragma unroll 1
+            for (int kb = 0; kb < 4; ++kb) {
+                epilogue_split(tl + kTD2, kb * 64 + half * 32, 32, s.big, 65536u, kPlane, row, s.bd2);
+                TL_PUBLISH(&s.a3_ready[kb]);
             }
-            // ---- dconv2 epilogue: D2 (256 columns) -> A3 over all of BIG (every partial sum has been consumed)
-            TL_WAIT_ACC(0x2101)
-            epilogue_split(tl + kTD2, half * 128, 128, s.big, 65536u, kPlane, row, s.bd2);
-            TL_PUBLISH(&s.act);
-            // ---- dconv3 epilogue: DA (128 columns) -> A4
-            TL_WAIT_ACC(0x2102)
-            epilogue_split(tl + kTDA, half * 64, 64, s.big, 32768u, kPlane, row, s.bd3);
-            TL_PUBLISH(&s.act);
-            // ---- dconv4 epilogue: bias + ReLU in fp32, then the 128 -> 2 layer, logits and mask.  Each half reduces
-            //      64 channels; the upper half hands its partial sums over in smem and the lower half adds them in a
-            //      fixed order (deterministic).
-            TL_WAIT_ACC(0x2103)
+            TL_STAMP_E(0x203);
+            if (has_next) TL_FRONT()
+            TL_STAMP_E(0x204);
+            // ---- dconv3 epilogue: DA (128 columns) -> A4, per K slab
+            TL_WAIT(&s.d3_full, par, 0x2102)
+            TL_STAMP_E(0x205);
+#pragma unroll 1
+            for (int kb = 0; kb < 2; ++kb) {
+                epilogue_split(tl + kTDA, kb * 64 + half * 32, 32, s.big, 32768u, kPlane, row, s.bd3);
+                TL_PUBLISH(&s.a4_ready[kb]);
+            }
+            TL_STAMP_E(0x206);
+            if (has_next) TL_CONV2_EPI(par ^ 1)
+            TL_STAMP_E(0x207);
+            // ---- dconv4 epilogue: accumulator -> registers; chunk 0 of the next tile goes first (the issuer is waiting
+            //      for it), then bias + ReLU in fp32, the 128 -> 2 layer, logits and mask from the registers.  Each half
+            //      reduces 64 channels; the upper half hands its partial sums over in smem and the lower half adds them in
+            //      a fixed order (deterministic).
+            TL_WAIT(&s.d4_full, par, 0x2103)
+            TL_STAMP_E(0x208);
             {
                 uint32_t v0[32], v1[32];
                 const int c0 = half * 64;
-                tmem_ld32(tl + kTDB + c0, v0);
-                tmem_ld32(tl + kTDB + c0 + 32, v1);
+                tmem_ld32(tl + kTD4 + c0, v0);
+                tmem_ld32(tl + kTD4 + c0 + 32, v1);
                 tmem_ld_wait();
                 tc_fence_before();
+                if (has_next) TL_CHUNK_EPI(0)
+                TL_STAMP_E(0x209);
                 float l0 = 0.f, l1 = 0.f, m0 = 0.f, m1 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -622,12 +729,17 @@ split_tail_kernel(const TailParams p)
                     *reinterpret_cast<float2 *>(p.logits + o * 2) = make_float2(f0, f1);
                     p.mask[o] = (f0 < f1) ? 1 : 0;
                 }
-                // the lower half must have read lpart (and everybody s.gb) before the next tile overwrites them
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                // s.lpart is rewritten one tile later, after the bar.sync in that tile's TL_FRONT
             }
+            TL_STAMP_E(0x20a);
+            b = nb; pidx = npidx; valid = nvalid;
         }
+#undef TL_CHUNK_EPI
+#undef TL_CONV2_EPI
+#undef TL_FRONT
+#undef TL_LOAD
 #undef TL_PUBLISH
-#undef TL_WAIT_ACC
+#undef TL_WAIT
     }
 #undef TL_ARRIVE
 done:

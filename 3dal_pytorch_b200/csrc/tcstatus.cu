@@ -2,8 +2,10 @@
 //
 // Every tcgen05 kernel bounds its mbarrier waits (umma.cuh).  A wait that gives up records a code in the status word
 // of the device it runs on -- pinned host memory mapped into the device's address space, so the host can read it with
-// a plain load, without a CUDA call and without synchronising -- and traps.  One 64-byte block per device, allocated
+// a plain load, without a CUDA call and without synchronising -- and traps.  One 64 KB block per device, allocated
 // at the first tensor-core launch on that device and kept for the life of the process; nothing else is allocated.
+// Word 0 is the status word; words 1024.. are a scratch area that only the timeline build of chain_split.cu
+// (-DAL3D_SPLIT_TIMELINE, scripts/split_timeline.py) writes.
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -15,6 +17,7 @@ namespace al3d {
 
 namespace {
 constexpr int kMaxDevices = 64;
+constexpr size_t kSlotBytes = 65536;
 struct Slot { unsigned int *host = nullptr; unsigned int *dev = nullptr; int sms = 0; };
 Slot g_slot[kMaxDevices];
 std::mutex g_mu;
@@ -35,8 +38,8 @@ int slot_for_current_device(Slot **out)
     Slot &s = g_slot[dev];
     if (!s.host) {
         void *h = nullptr, *d = nullptr;
-        AL3D_CHECK_CUDA(cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable));
-        std::memset(h, 0, 64);
+        AL3D_CHECK_CUDA(cudaHostAlloc(&h, kSlotBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        std::memset(h, 0, kSlotBytes);
         AL3D_CHECK_CUDA(cudaHostGetDevicePointer(&d, h, 0));
         int sms = 0;
         AL3D_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
