@@ -98,7 +98,7 @@ __device__ __forceinline__ void epilogue_split(uint32_t taddr, int c0, int ncols
 
 // First layer on CUDA cores: x[c] (c < c_in) -> output channels [ch0, ch0 + nch) -> split planes.  sw[c * w0 + ch].
 __device__ __forceinline__ void first_layer_split(uint8_t *buf, uint32_t lo_off, int row, const float *xv, int c_in, int w0, int ch0, int nch,
-                                                  const float *sw, const float *sb)
+                                                  const float *sw, const float *sb, uint32_t plane_stride = kPlane)
 {
     for (int ch = ch0; ch < ch0 + nch; ch += 8) {
         float4 a0 = *reinterpret_cast<const float4 *>(sb + ch), a1 = *reinterpret_cast<const float4 *>(sb + ch + 4);
@@ -114,7 +114,7 @@ __device__ __forceinline__ void first_layer_split(uint8_t *buf, uint32_t lo_off,
         uint4 h, l;
         split2(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f), h.x, l.x); split2(fmaxf(a0.z, 0.f), fmaxf(a0.w, 0.f), h.y, l.y);
         split2(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f), h.z, l.z); split2(fmaxf(a1.z, 0.f), fmaxf(a1.w, 0.f), h.w, l.w);
-        uint8_t *dst = buf + (size_t)(ch >> 3) * kPlane + (size_t)row * 16;
+        uint8_t *dst = buf + (size_t)(ch >> 3) * plane_stride + (size_t)row * 16;
         *reinterpret_cast<uint4 *>(dst) = h;
         *reinterpret_cast<uint4 *>(dst + lo_off) = l;
     }
@@ -172,6 +172,30 @@ struct RingView {
               mma_bf16((d_tmem), make_desc(wst_ + k_ * 4096, 128), make_desc((b_hi) + k_ * 2 * (b_plane), (b_rows)), (idesc), 1u); \
           SPLIT_RING_RELEASE(r) }                                                                                    \
     }
+
+// Timeline builds (scripts/split_timeline.py; -DAL3D_SPLIT_TIMELINE: split_tail_kernel, -DAL3D_CHAIN_TIMELINE:
+// split_chain_kernel in pair mode): CTA 0's MMA issuer and first epilogue thread stamp (id, %clock) pairs into the
+// scratch area behind the status word.
+#ifdef AL3D_SPLIT_TIMELINE
+#define TL_STAMP(id) do { if (blockIdx.x == 0 && tl_n < 1500) { unsigned int c_; asm volatile("mov.u32 %0, %%clock;" : "=r"(c_)); \
+                          tl_buf[tl_n * 2] = (unsigned int)(id); tl_buf[tl_n * 2 + 1] = c_; ++tl_n; } } while (0)
+#define TL_STAMP_DECL(off) unsigned int *tl_buf = p.wd.word + (off); int tl_n = 0;
+#define TL_STAMP_E(id) do { if (etid == 0) TL_STAMP(id); } while (0)
+#else
+#define TL_STAMP(id) do { } while (0)
+#define TL_STAMP_E(id) do { } while (0)
+#define TL_STAMP_DECL(off)
+#endif
+#ifdef AL3D_CHAIN_TIMELINE
+#define CH_STAMP(id) do { if (p.pair && blockIdx.x == 0 && tl_n < 1500) { unsigned int c_; asm volatile("mov.u32 %0, %%clock;" : "=r"(c_)); \
+                          tl_buf[tl_n * 2] = (unsigned int)(id); tl_buf[tl_n * 2 + 1] = c_; ++tl_n; } } while (0)
+#define CH_STAMP_DECL(off) unsigned int *tl_buf = p.wd.word + (off); int tl_n = 0;
+#define CH_STAMP_E(id) do { if (etid == 0) CH_STAMP(id); } while (0)
+#else
+#define CH_STAMP(id) do { } while (0)
+#define CH_STAMP_E(id) do { } while (0)
+#define CH_STAMP_DECL(off)
+#endif
 
 // ================================================================================================
 // split_chain_kernel
@@ -265,11 +289,13 @@ split_chain_kernel(const ChainParams p)
         if (elect_one_sync()) {
             RingView ring{smem_u32(s_ring), s.w_full, s.w_empty, p.n_stages, 0, 0u};
             uint32_t act_phase = 0, le_phase[2] = {0, 0};
+            CH_STAMP_DECL(1024)
             const uint32_t a_act = smem_u32(s_act), a_pair = smem_u32(s_pair);
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int sp_i = item % p.splits;
                 const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
                 for (int t = t0; t < t1; t += nq) {
+                    CH_STAMP(0x100);
                     for (int q = 0; q < nq; ++q) {
                         // mid layers: D[points x channels], input = the activation buffer (converted in place)
                         for (int l = 0; l < p.n_mid; ++l) {
@@ -279,6 +305,7 @@ split_chain_kernel(const ChainParams p)
                             if (!mbar_wait(&s.act_ready, act_phase, 0x5200 + l, wd)) goto done;
                             act_phase ^= 1;
                             tc_fence_after();
+                            CH_STAMP(0x110 + q * 4 + l);
                             const uint32_t idesc = make_idesc_bf16(128, rows);
                             for (int nc = 0; nc < N / rows; ++nc)
                                 for (int kb = 0; kb < K / 64; ++kb)
@@ -292,6 +319,7 @@ split_chain_kernel(const ChainParams p)
                         if (!mbar_wait(&s.act_ready, act_phase, 0x52F0, wd)) goto done;
                         act_phase ^= 1;
                         tc_fence_after();
+                        CH_STAMP(0x120);
                         const uint32_t idesc = make_idesc_bf16(128, p.pair ? 256 : 128);
                         for (int cc = 0; cc < n_last_chunks; ++cc) {
                             const int b = cc & 1;
@@ -305,6 +333,7 @@ split_chain_kernel(const ChainParams p)
                                 else        SPLIT_MMA_BLOCK_T(ring, d, a_act + kb * 8 * kPlane, act_lo, kPlane, 128, idesc, kb == 0, 0x5500)
                             }
                             mma_commit(&s.last_full[b]);
+                            CH_STAMP(0x130 + cc);
                         }
                     }
                 }
@@ -315,6 +344,9 @@ split_chain_kernel(const ChainParams p)
         const int row = epi_row(), half = epi_half();
         const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
         uint32_t acc_phase = 0, lf_phase[2] = {0, 0};
+        const int etid = threadIdx.x - 64;
+        (void)etid;
+        CH_STAMP_DECL(8192)
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int b = item / p.splits, sp_i = item % p.splits;
             const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
@@ -322,6 +354,7 @@ split_chain_kernel(const ChainParams p)
 #pragma unroll
             for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
             for (int t = t0; t < t1; t += nq) {
+                CH_STAMP_E(0x200);
                 for (int q = 0; q < nq; ++q) {
                     // ---- first layer (rows past the end of the object replicate its last point, an odd tail pair
                     //      repeats its tile: the max-pool is idempotent under duplicates)
@@ -336,6 +369,7 @@ split_chain_kernel(const ChainParams p)
                         first_layer_split(s_act, act_lo, row, xv, p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b);
                         fence_proxy_async_smem();
                         CH_ARRIVE(&s.act_ready);
+                        CH_STAMP_E(0x210 + q * 8);
                     }
                     // ---- mid layers: this thread converts columns [half*N/2, (half+1)*N/2) of its row, in place
                     //      (the layer's MMAs are complete when acc_ready fires); in pair mode the last mid layer
@@ -348,12 +382,14 @@ split_chain_kernel(const ChainParams p)
                         if (!mbar_wait(&s.acc_ready, acc_phase, 0x4100 + l, wd)) goto done;
                         acc_phase ^= 1;
                         tc_fence_after();
+                        CH_STAMP_E(0x211 + q * 8 + l * 2);
                         if (to_pair) epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_pair, pair_lo, 2 * kPlane, q * kTile + row, s.mid_b + boff);
                         else         epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_act, act_lo, kPlane, row, s.mid_b + boff);
                         boff += N;
                         tc_fence_before();
                         fence_proxy_async_smem();
                         if (!(to_pair && q == 0)) CH_ARRIVE(&s.act_ready);     // tile X of a pair: the issuer has nothing to wait for yet
+                        CH_STAMP_E(0x212 + q * 8 + l * 2);
                     }
                 }
                 // ---- last layer: this thread owns channel (cc*128 + row) and half of the unit's points
@@ -365,6 +401,7 @@ split_chain_kernel(const ChainParams p)
                         if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0x4200 + cc, wd)) goto done;
                         lf_phase[bsel] ^= 1;
                         tc_fence_after();
+                        CH_STAMP_E(0x230 + cc * 2);
                         float m0 = rmax[cc], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
                         const int ncol = p.pair ? 128 : 64;
                         const uint32_t ta = tmem + lane_addr + (p.pair ? bsel * 256 : 256 + bsel * 128) + half * ncol;
@@ -387,6 +424,7 @@ split_chain_kernel(const ChainParams p)
                             }
                         }
                         rmax[cc] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                        CH_STAMP_E(0x231 + cc * 2);
                     }
                 }
             }
@@ -407,6 +445,309 @@ done:
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
+
+// ================================================================================================
+// split_chain_pair_kernel -- the chain on TILE PAIRS (ins_seg conv1-5 + max, tools/static_model.py:279-284)
+//
+// A unit is two 128-point tiles X, Y of one object; the last layer runs transposed on both at once (N = 256 points per
+// streamed 128-channel block, which halves its weight traffic per point).  Measured with scripts/split_timeline.py
+// (profiles/r2_split_chain_timeline_before.txt) the first cut of this path spent 44 % of a unit in the strictly serial
+// front of the two tiles, so here
+//   * the two tiles' fronts are INTERLEAVED: X lives in the activation buffer, Y in the Y rows of the pair buffer
+//     (which is where its last mid layer lands anyway; in-place conversion as everywhere), with accumulators in TMEM
+//     columns [0,128) / [128,256) and barriers of their own, so one tile's epilogue runs under the other's MMAs;
+//   * the next unit's input points are loaded, and X's first layer is computed into the (idle) activation buffer,
+//     UNDER the current unit's last layer, and X's first MMA layer is queued right behind the last streamed block --
+//     it only needs TMEM buffer 0, which the second-to-last block has left by then.
+// Weight stream image: the mid layers' blocks, then the last layer's; consumption order per unit: every mid layer's
+// blocks twice (X, Y), then the last layer's.
+// ================================================================================================
+struct PairTail {
+    float w0_w[128 * 8];
+    float w0_b[128];
+    float mid_b[512];
+    uint64_t w_full[kMaxStages], w_empty[kMaxStages];
+    uint64_t act_ready[2], acc_ready[2];           // per tile of the pair: operand written / accumulator complete
+    uint64_t pair_ready;                           // both tiles' last mid layer written into the pair buffer
+    uint64_t last_full[2], last_empty[2];
+    uint32_t tmem_base;
+};
+
+struct UnitIter { int item, t, t1; };
+__device__ __forceinline__ void unit_span(const ChainParams &p, int tiles_per_obj, int item, int &t0, int &t1)
+{
+    const int sp_i = item % p.splits;
+    t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits);
+    t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
+}
+__device__ __forceinline__ bool unit_first(const ChainParams &p, int tiles_per_obj, UnitIter &u)
+{
+    u.item = blockIdx.x;
+    if (u.item >= p.n_items) return false;
+    unit_span(p, tiles_per_obj, u.item, u.t, u.t1);
+    return true;
+}
+__device__ __forceinline__ bool unit_next(const ChainParams &p, int tiles_per_obj, const UnitIter &c, UnitIter &n)
+{
+    if (c.t + 2 < c.t1) { n = c; n.t += 2; return true; }
+    n.item = c.item + gridDim.x;
+    if (n.item >= p.n_items) return false;
+    unit_span(p, tiles_per_obj, n.item, n.t, n.t1);
+    return true;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+split_chain_pair_kernel(const ChainParams p)
+{
+    const TcStatus wd = p.wd;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t *const s_act = smem_raw;
+    uint8_t *const s_pair = smem_raw + p.act_bytes;
+    uint8_t *const s_ring = s_pair + p.pair_bytes;
+    PairTail &s = *reinterpret_cast<PairTail *>(s_ring + (size_t)p.n_stages * kStage);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t act_lo = (uint32_t)p.act_bytes / 2, pair_lo = (uint32_t)p.pair_bytes / 2;
+
+    for (int i = threadIdx.x; i < p.w0 * 8; i += kThreads) s.w0_w[i] = p.w0_w[i];
+    for (int i = threadIdx.x; i < p.w0; i += kThreads) s.w0_b[i] = p.w0_b[i];
+    {
+        int tot = 0;
+        for (int l = 0; l < p.n_mid; ++l) tot += p.mid[l];
+        for (int i = threadIdx.x; i < tot; i += kThreads) s.mid_b[i] = p.mid_b[i];
+    }
+    if (threadIdx.x == 0) {
+        constexpr int kW = kEpiThreads / 32;
+        for (int i = 0; i < p.n_stages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s.act_ready[i], kW); mbar_init(&s.acc_ready[i], 1);
+            mbar_init(&s.last_full[i], 1); mbar_init(&s.last_empty[i], kW);
+        }
+        mbar_init(&s.pair_ready, 2 * kW);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&s.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    const int tiles_per_obj = (p.n + kTile - 1) / kTile;
+    const int n_last_chunks = p.last / 128;
+    const int k_last = p.mid[p.n_mid - 1];
+#define CH_ARRIVE(bar) do { __syncwarp(); if (lane == 0) mbar_arrive(bar); } while (0)
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ weight producer (one thread)
+        if (elect_one_sync()) {
+            int stage = 0; uint32_t phase = 0;
+#define CP_PUSH(blk_, bytes_)                                                                               \
+            {                                                                                               \
+                SPLIT_STRESS(wd, 0x51);                                                                     \
+                if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x5100 + stage, wd)) goto done;                \
+                mbar_arrive_expect_tx(&s.w_full[stage], (bytes_));                                          \
+                bulk_g2s(s_ring + (size_t)stage * kStage, p.wstream + (size_t)(blk_) * kStage, (bytes_), &s.w_full[stage]); \
+                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }                                       \
+            }
+            UnitIter u, nx;
+            for (bool ok = unit_first(p, tiles_per_obj, u); ok; ok = unit_next(p, tiles_per_obj, u, nx), u = nx) {
+                int off = 0;
+                for (int l = 0; l < p.n_mid; ++l) {
+                    const int nb = 2 * (chain_in_width(p, l) / 64);
+                    const uint32_t bytes = (uint32_t)p.mid[l] * 128u;          // rows x 64 bf16
+                    for (int q = 0; q < 2; ++q)
+                        for (int i = 0; i < nb; ++i) CP_PUSH(off + i, bytes)
+                    off += nb;
+                }
+                for (int i = 0; i < p.last_blocks; ++i) CP_PUSH(p.front_blocks + i, (uint32_t)kStage)
+            }
+#undef CP_PUSH
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (elect_one_sync()) {
+            RingView ring{smem_u32(s_ring), s.w_full, s.w_empty, p.n_stages, 0, 0u};
+            uint32_t act_phase[2] = {0, 0}, pair_phase = 0, le_phase[2] = {0, 0};
+            const uint32_t a_act = smem_u32(s_act), a_pair = smem_u32(s_pair);
+            CH_STAMP_DECL(1024)
+            UnitIter u, nx;
+            for (bool ok = unit_first(p, tiles_per_obj, u); ok; ok = unit_next(p, tiles_per_obj, u, nx), u = nx) {
+                CH_STAMP(0x100);
+                // TMEM buffer 0 (columns [0,256)) holds the front's accumulators: the previous unit's second-to-last
+                // streamed block must have been drained from it (buffer 1 may still be in use)
+                SPLIT_STRESS(wd, 0x54);
+                if (!mbar_wait(&s.last_empty[0], le_phase[0] ^ 1, 0x5410, wd)) goto done;
+                tc_fence_after();
+                for (int l = 0; l < p.n_mid; ++l) {
+                    const int K = chain_in_width(p, l), N = p.mid[l];
+                    const uint32_t idesc = make_idesc_bf16(128, N);
+                    for (int q = 0; q < 2; ++q) {
+                        SPLIT_STRESS(wd, 0x52);
+                        if (!mbar_wait(&s.act_ready[q], act_phase[q], 0x5200 + q * 16 + l, wd)) goto done;
+                        act_phase[q] ^= 1;
+                        tc_fence_after();
+                        CH_STAMP(0x110 + l * 2 + q);
+                        const uint32_t a_hi = q ? a_pair + kTile * 16 : a_act, a_lo = q ? pair_lo : act_lo;
+                        const uint32_t a_pl = q ? 2 * kPlane : kPlane, a_rows = q ? 2 * kTile : kTile;
+                        for (int kb = 0; kb < K / 64; ++kb)
+                            SPLIT_MMA_BLOCK(ring, tmem + q * 128, a_hi + kb * 8 * a_pl, a_lo, a_pl, a_rows, N, idesc, kb == 0, 0x5300)
+                        mma_commit(&s.acc_ready[q]);
+                    }
+                }
+                // last layer, transposed: D^T[channels x 256 points], double-buffered in TMEM
+                SPLIT_STRESS(wd, 0x52);
+                if (!mbar_wait(&s.pair_ready, pair_phase, 0x52F0, wd)) goto done;
+                pair_phase ^= 1;
+                tc_fence_after();
+                CH_STAMP(0x120);
+                const uint32_t idesc = make_idesc_bf16(128, 256);
+                for (int cc = 0; cc < n_last_chunks; ++cc) {
+                    const int b = cc & 1;
+                    SPLIT_STRESS(wd, 0x54);
+                    if (!mbar_wait(&s.last_empty[b], le_phase[b] ^ 1, 0x5400 + b, wd)) goto done;
+                    le_phase[b] ^= 1;
+                    tc_fence_after();
+                    for (int kb = 0; kb < k_last / 64; ++kb)
+                        SPLIT_MMA_BLOCK_T(ring, tmem + b * 256, a_pair + kb * 8 * 2 * kPlane, pair_lo, 2 * kPlane, 256, idesc, kb == 0, 0x5500)
+                    mma_commit(&s.last_full[b]);
+                    CH_STAMP(0x130 + cc);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (256 threads)
+        const int row = epi_row(), half = epi_half();
+        const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
+        const int etid = threadIdx.x - 64;
+        (void)etid;
+        uint32_t acc_phase[2] = {0, 0}, lf_phase[2] = {0, 0};
+        CH_STAMP_DECL(8192)
+        float xv[2][8];
+        // input points of a unit -> registers (rows past the end of the object replicate its last point, an odd tail
+        // pair repeats its tile: the max-pool is idempotent under duplicates)
+#define CP_LOAD(u_)                                                                                           \
+        {                                                                                                     \
+            const int b_ = (u_).item / p.splits;                                                              \
+            _Pragma("unroll")                                                                                 \
+            for (int q_ = 0; q_ < 2; ++q_) {                                                                  \
+                const int tq_ = ((u_).t + q_ < (u_).t1) ? (u_).t + q_ : (u_).t1 - 1;                          \
+                int pidx_ = tq_ * kTile + row;                                                                \
+                if (pidx_ > p.n - 1) pidx_ = p.n - 1;                                                         \
+                const float *px_ = p.x + (int64_t)b_ * p.sb + (int64_t)pidx_ * p.sp;                          \
+                _Pragma("unroll")                                                                             \
+                for (int c_ = 0; c_ < 8; ++c_) xv[q_][c_] = (c_ < p.c_in) ? __ldg(px_ + c_ * p.sc) : 0.f;     \
+            }                                                                                                 \
+        }
+        // first layer of tile X -> activation buffer
+#define CP_FIRST_X()                                                                                          \
+        {                                                                                                     \
+            first_layer_split(s_act, act_lo, row, xv[0], p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b); \
+            fence_proxy_async_smem();                                                                         \
+            CH_ARRIVE(&s.act_ready[0]);                                                                       \
+        }
+        UnitIter u, nx;
+        bool ok = unit_first(p, tiles_per_obj, u);
+        if (ok) {
+            CP_LOAD(u)
+            CP_FIRST_X()
+        }
+        float rmax[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
+        while (ok) {
+            const bool has_next = unit_next(p, tiles_per_obj, u, nx);
+            CH_STAMP_E(0x200);
+            // ---- first layer of tile Y -> the Y rows of the pair buffer (the previous unit's last layer has read it:
+            //      this thread has seen its final accumulator)
+            first_layer_split(s_pair, pair_lo, kTile + row, xv[1], p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b, 2 * kPlane);
+            fence_proxy_async_smem();
+            CH_ARRIVE(&s.act_ready[1]);
+            CH_STAMP_E(0x201);
+            // ---- mid layers, X and Y alternating: this thread converts columns [half*N/2, (half+1)*N/2) of its row,
+            //      in place (the layer's MMAs are complete when acc_ready fires); the last mid layer of both tiles
+            //      lands in the pair buffer
+            int boff = 0;
+            for (int l = 0; l < p.n_mid; ++l) {
+                const int N = p.mid[l];
+                const bool last_mid = l == p.n_mid - 1;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    SPLIT_STRESS_WARP(wd, 0x41);
+                    if (!mbar_wait(&s.acc_ready[q], acc_phase[q], 0x4100 + q * 16 + l, wd)) goto done;
+                    acc_phase[q] ^= 1;
+                    tc_fence_after();
+                    CH_STAMP_E(0x210 + l * 4 + q * 2);
+                    if (q == 1 || last_mid) epilogue_split(tmem + lane_addr + q * 128, half * (N >> 1), N >> 1, s_pair, pair_lo, 2 * kPlane, q * kTile + row, s.mid_b + boff);
+                    else                    epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_act, act_lo, kPlane, row, s.mid_b + boff);
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    CH_ARRIVE(last_mid ? &s.pair_ready : &s.act_ready[q]);
+                    CH_STAMP_E(0x211 + l * 4 + q * 2);
+                }
+                boff += N;
+            }
+            // ---- last layer: this thread owns channel (cc*128 + row) and half of the unit's points.  Under it: the
+            //      next unit's input loads (after block 0) and tile X's first layer (after block 2; the activation
+            //      buffer is idle -- X's last mid layer has been read out of it)
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                if (cc < n_last_chunks) {
+                    const int bsel = cc & 1;
+                    SPLIT_STRESS_WARP(wd, 0x42);
+                    if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0x4200 + cc, wd)) goto done;
+                    lf_phase[bsel] ^= 1;
+                    tc_fence_after();
+                    CH_STAMP_E(0x230 + cc * 2);
+                    float m0 = rmax[cc], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                    const uint32_t ta = tmem + lane_addr + bsel * 256 + half * 128;
+#pragma unroll
+                    for (int c0 = 0; c0 < 128; c0 += 64) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(ta + c0, v0);
+                        tmem_ld32(ta + c0 + 32, v1);
+                        tmem_ld_wait();
+                        if (c0 + 64 >= 128) { tc_fence_before(); CH_ARRIVE(&s.last_empty[bsel]); }   // all values are in registers
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            m0 = fmax3(m0, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
+                            m1 = fmax3(m1, __uint_as_float(v0[i + 2]), __uint_as_float(v0[i + 3]));
+                            m2 = fmax3(m2, __uint_as_float(v0[i + 4]), __uint_as_float(v0[i + 5]));
+                            m3 = fmax3(m3, __uint_as_float(v0[i + 6]), __uint_as_float(v0[i + 7]));
+                            m0 = fmax3(m0, __uint_as_float(v1[i]), __uint_as_float(v1[i + 1]));
+                            m1 = fmax3(m1, __uint_as_float(v1[i + 2]), __uint_as_float(v1[i + 3]));
+                            m2 = fmax3(m2, __uint_as_float(v1[i + 4]), __uint_as_float(v1[i + 5]));
+                            m3 = fmax3(m3, __uint_as_float(v1[i + 6]), __uint_as_float(v1[i + 7]));
+                        }
+                    }
+                    rmax[cc] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    CH_STAMP_E(0x231 + cc * 2);
+                    if (has_next && cc == 0) CP_LOAD(nx)
+                    if (has_next && cc == (n_last_chunks > 2 ? 2 : n_last_chunks - 1)) CP_FIRST_X()
+                }
+            }
+            // ---- end of the object's share: publish relu(max + bias) >= 0, so integer atomicMax on the bit pattern is exact
+            if (!has_next || nx.item != u.item) {
+                const int b = u.item / p.splits;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    if (cc < n_last_chunks) {
+                        const int ch = cc * 128 + row;
+                        const float v = fmaxf(rmax[cc] + __ldg(p.last_b + ch), 0.f);
+                        atomicMax(reinterpret_cast<int *>(p.out + (int64_t)b * p.last + ch), __float_as_int(v));
+                        rmax[cc] = -INFINITY;
+                    }
+                }
+            }
+            u = nx; ok = has_next;
+        }
+#undef CP_FIRST_X
+#undef CP_LOAD
+    }
+#undef CH_ARRIVE
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 
 // ================================================================================================
 // split_tail_kernel -- second half of the segmentation net in split precision
@@ -458,18 +799,6 @@ struct TailSmem {
 static_assert(sizeof(TailSmem) + 128 <= 232448, "TailSmem exceeds the 227 KB opt-in limit");
 constexpr uint32_t kTD2 = 0, kTDA = 256, kTDB = 384, kTD4 = 0, kTC2 = 128;
 
-// Timeline build (scripts/split_timeline.py): CTA 0's MMA issuer and first epilogue thread stamp (id, %clock) pairs into
-// the scratch area behind the status word.
-#ifdef AL3D_SPLIT_TIMELINE
-#define TL_STAMP(id) do { if (blockIdx.x == 0 && tl_n < 1500) { unsigned int c_; asm volatile("mov.u32 %0, %%clock;" : "=r"(c_)); \
-                          tl_buf[tl_n * 2] = (unsigned int)(id); tl_buf[tl_n * 2 + 1] = c_; ++tl_n; } } while (0)
-#define TL_STAMP_DECL(off) unsigned int *tl_buf = p.wd.word + (off); int tl_n = 0;
-#define TL_STAMP_E(id) do { if (etid == 0) TL_STAMP(id); } while (0)
-#else
-#define TL_STAMP(id) do { } while (0)
-#define TL_STAMP_E(id) do { } while (0)
-#define TL_STAMP_DECL(off)
-#endif
 
 __global__ void __launch_bounds__(kThreads, 1)
 split_tail_kernel(const TailParams p)
@@ -1059,6 +1388,17 @@ extern "C" int al3d_chain_maxpool_bf16x3(const al3d_split_chain_weights *w, cons
     AL3D_CHECK_ARG(stages >= 2, "al3d_chain_maxpool_bf16x3: no room for the weight ring (act %d B, pair %d B)", p.act_bytes, p.pair_bytes);
     p.n_stages = stages;
     const size_t smem = (size_t)p.act_bytes + p.pair_bytes + (size_t)stages * kStage + sizeof(ChainTail);
+    if (p.pair) {
+        // tile Y's front lives in the pair buffer, both fronts' accumulators in TMEM buffer 0
+        static_assert(sizeof(PairTail) <= sizeof(ChainTail) + 64, "PairTail must fit the ChainTail budget");
+        AL3D_CHECK_ARG(act_w <= prev && prev <= 128, "al3d_chain_maxpool_bf16x3: pair mode needs mid widths <= 128 (got %d, %d)", act_w, prev);
+        for (int l = 0; l < w->n_mid; ++l) AL3D_CHECK_ARG(w->mid[l] <= 128, "al3d_chain_maxpool_bf16x3: pair mode, mid width %d", w->mid[l]);
+        const size_t smem_pair = smem - sizeof(ChainTail) + sizeof(PairTail);
+        AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_chain_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
+        split_chain_pair_kernel<<<grid, kThreads, smem_pair, (cudaStream_t)stream>>>(p);
+        AL3D_CHECK_LAUNCH("split_chain_pair_kernel");
+        return 0;
+    }
     AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     split_chain_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
     AL3D_CHECK_LAUNCH("split_chain_kernel");

@@ -1,7 +1,7 @@
 """Cycle timeline of split_tail_kernel (CTA 0: MMA issuer + first epilogue thread).
 
   python scripts/split_timeline.py build     # here: compile chain_split.cu with -DAL3D_SPLIT_TIMELINE -> libal3d_timeline.so
-  python scripts/split_timeline.py run       # on the GPU: run the tail kernel once, print per-phase cycle statistics
+  python scripts/split_timeline.py run [tail|chain]   # on the GPU: one forward, per-phase cycle statistics of CTA 0
 """
 import ctypes
 import importlib
@@ -14,22 +14,27 @@ sys.path.insert(0, ROOT)
 LIB = os.path.join(ROOT, "3dal_pytorch_b200", "libal3d_timeline.so")
 
 
+def _lib_path(which):
+    return LIB if which == "tail" else LIB.replace("timeline", "timeline_chain")
+
+
 def build():
     import __graft_entry__ as g
     g.build()
     objdir = os.path.join(g.CSRC, "_obj")
-    obj = os.path.join(objdir, "chain_split.timeline.o")
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    subprocess.check_call([nvcc] + g.NVCC_COMPILE + ["-DAL3D_SPLIT_TIMELINE", "-I", os.path.join(ROOT, "include"), "-c",
-                                                   os.path.join(g.CSRC, "chain_split.cu"), "-o", obj])
     objs = [os.path.join(objdir, f) for f in sorted(os.listdir(objdir))
-            if f.endswith(".o") and ".stress." not in f and ".timeline." not in f and f != "chain_split.o"]
-    subprocess.check_call([nvcc] + g.NVCC_LINK + ["-o", LIB] + objs + [obj, "-lcuda"])
-    print("built", LIB)
+            if f.endswith(".o") and ".stress." not in f and ".timeline" not in f and f != "chain_split.o"]
+    for which, define in (("tail", "-DAL3D_SPLIT_TIMELINE"), ("chain", "-DAL3D_CHAIN_TIMELINE")):
+        obj = os.path.join(objdir, "chain_split.timeline_%s.o" % which)
+        subprocess.check_call([nvcc] + g.NVCC_COMPILE + [define, "-I", os.path.join(ROOT, "include"), "-c",
+                                                       os.path.join(g.CSRC, "chain_split.cu"), "-o", obj])
+        subprocess.check_call([nvcc] + g.NVCC_LINK + ["-o", _lib_path(which)] + objs + [obj, "-lcuda"])
+        print("built", _lib_path(which))
 
 
-def run():
-    os.environ["AL3D_LIB"] = LIB
+def run(which="tail"):
+    os.environ["AL3D_LIB"] = _lib_path(which)
     import numpy as np
     import torch
     pkg = importlib.import_module("3dal_pytorch_b200")
@@ -59,7 +64,7 @@ def run():
         ids, clk = ids[:n], clk[:n]
         first = 0x100 if name == "issuer" else 0x200
         starts = [i for i in range(n) if ids[i] == first]
-        print("== %s: %d stamps, %d tiles" % (name, n, len(starts)))
+        print("== %s %s: %d stamps, %d tiles / units" % (which, name, n, len(starts)))
         rows = []
         for a_, b_ in zip(starts[2:-1], starts[3:]):           # skip the first two tiles (pipeline fill)
             seg_ids = ids[a_:b_ + 1]
@@ -76,4 +81,7 @@ def run():
 
 
 if __name__ == "__main__":
-    {"build": build, "run": run}[sys.argv[1]]()
+    if sys.argv[1] == "build":
+        build()
+    else:
+        run(sys.argv[2] if len(sys.argv) > 2 else "tail")
