@@ -12,14 +12,17 @@
 //   split_chain_kernel   first layer (tiny K, CUDA cores) -> 2-3 chained MMA layers, activations (hi | lo planes) in
 //                        shared memory, converted IN PLACE by the epilogue warps -> last layer computed transposed
 //                        (channels on TMEM lanes, points on columns) so the max over points is a per-thread reduction.
-//                        ins_seg conv1-5 + max (tools/static_model.py:279-284) runs it on tile PAIRS (N = 256 points
-//                        per streamed conv5 block); the static box-head trunk (:330-334), PointEmbedding and
-//                        BoxEmbedding trunks (tools/dynamic_model.py:241-245, 278-282) on single tiles.
+//                        Single tiles: the static box-head trunk (tools/static_model.py:330-334), PointEmbedding and
+//                        BoxEmbedding trunks (tools/dynamic_model.py:241-245, 278-282).
+//   split_chain_pair_kernel  the same chain on tile PAIRS for ins_seg conv1-5 + max (tools/static_model.py:279-284):
+//                        N = 256 points per streamed conv5 block, the two tiles' fronts interleaved, the next unit's
+//                        first layer computed under the streamed last layer.
 //   split_tail_kernel    conv1-2 recomputed, dconv1 (+ per-object global-feature bias) in four 128-channel chunks
 //                        pipelined into dconv2's accumulation, dconv3, dconv4, and the 128 -> 2 logits + mask in fp32
-//                        in the last epilogue (tools/static_model.py:286-295, :59).
+//                        (tools/static_model.py:286-295, :59); software-pipelined across tiles.
+//   split_tail_pair_kernel  cta_group::2 experiment of the tail (off by default).
 //
-// Both are persistent (one CTA per SM, 320 threads): warp 0 streams the packed weight blocks (hi block, lo block per
+// All are persistent (one CTA per SM, 320 threads): warp 0 streams the packed weight blocks (hi block, lo block per
 // 128 x 64 tile of W) with cp.async.bulk into a ring, one thread of warp 1 issues every MMA, warps 2-9 own the 128
 // TMEM lanes (two warps per lane quarter, splitting the columns) and run the epilogues.  Every mbarrier that guards
 // a buffer is private to that buffer and strictly ping-pongs with its counterpart, so no parity wait can be lapped.
@@ -207,7 +210,7 @@ struct ChainParams {
     const uint8_t *wstream;                              // 16 KB slots, (hi, lo) per block, consumption order
     float *out;                                          // (bs, last) fp32, zero-initialised; max-pooled with atomicMax
     int splits, n_items;
-    int pair;                                            // 1: the last layer runs on tile pairs (N = 256 points)
+    int pair;                                            // 1: tile pairs, split_chain_pair_kernel (last layer with N = 256 points)
     int act_bytes, pair_bytes, n_stages;                 // shared-memory carve-up chosen by the launcher
     int front_blocks, last_blocks;                       // 16 KB slots per tile (mid layers) / per unit (last layer)
     TcStatus wd;
@@ -232,12 +235,10 @@ split_chain_kernel(const ChainParams p)
     const TcStatus wd = p.wd;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t *const s_act = smem_raw;
-    uint8_t *const s_pair = smem_raw + p.act_bytes;
-    uint8_t *const s_ring = s_pair + p.pair_bytes;
+    uint8_t *const s_ring = smem_raw + p.act_bytes;
     ChainTail &s = *reinterpret_cast<ChainTail *>(s_ring + (size_t)p.n_stages * kStage);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t act_lo = (uint32_t)p.act_bytes / 2, pair_lo = (uint32_t)p.pair_bytes / 2;
-    const int nq = p.pair ? 2 : 1;
+    const uint32_t act_lo = (uint32_t)p.act_bytes / 2;
 
     for (int i = threadIdx.x; i < p.w0 * 8; i += kThreads) s.w0_w[i] = p.w0_w[i];
     for (int i = threadIdx.x; i < p.w0; i += kThreads) s.w0_b[i] = p.w0_b[i];
@@ -270,11 +271,8 @@ split_chain_kernel(const ChainParams p)
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int sp_i = item % p.splits;
                 const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
-                for (int t = t0; t < t1; t += nq) {
-                    const int total = nq * p.front_blocks + p.last_blocks;
-                    for (int i = 0; i < total; ++i) {
-                        // slots: the front blocks once per tile of the unit, then the last layer's blocks
-                        const int blk = i < nq * p.front_blocks ? i % p.front_blocks : p.front_blocks + (i - nq * p.front_blocks);
+                for (int t = t0; t < t1; ++t) {
+                    for (int blk = 0; blk < p.front_blocks + p.last_blocks; ++blk) {
                         SPLIT_STRESS(wd, 0x51);
                         if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x5100 + stage, wd)) goto done;
                         mbar_arrive_expect_tx(&s.w_full[stage], kStage);
@@ -289,29 +287,24 @@ split_chain_kernel(const ChainParams p)
         if (elect_one_sync()) {
             RingView ring{smem_u32(s_ring), s.w_full, s.w_empty, p.n_stages, 0, 0u};
             uint32_t act_phase = 0, le_phase[2] = {0, 0};
-            CH_STAMP_DECL(1024)
-            const uint32_t a_act = smem_u32(s_act), a_pair = smem_u32(s_pair);
+            const uint32_t a_act = smem_u32(s_act);
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const int sp_i = item % p.splits;
                 const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
-                for (int t = t0; t < t1; t += nq) {
-                    CH_STAMP(0x100);
-                    for (int q = 0; q < nq; ++q) {
-                        // mid layers: D[points x channels], input = the activation buffer (converted in place)
-                        for (int l = 0; l < p.n_mid; ++l) {
-                            const int K = chain_in_width(p, l), N = p.mid[l];
-                            const int rows = N < 128 ? N : 128;
-                            SPLIT_STRESS(wd, 0x52);
-                            if (!mbar_wait(&s.act_ready, act_phase, 0x5200 + l, wd)) goto done;
-                            act_phase ^= 1;
-                            tc_fence_after();
-                            CH_STAMP(0x110 + q * 4 + l);
-                            const uint32_t idesc = make_idesc_bf16(128, rows);
-                            for (int nc = 0; nc < N / rows; ++nc)
-                                for (int kb = 0; kb < K / 64; ++kb)
-                                    SPLIT_MMA_BLOCK(ring, tmem + nc * 128, a_act + kb * 8 * kPlane, act_lo, kPlane, 128, rows, idesc, kb == 0, 0x5300)
-                            mma_commit(&s.acc_ready);
-                        }
+                for (int t = t0; t < t1; ++t) {
+                    // mid layers: D[points x channels], input = the activation buffer (converted in place)
+                    for (int l = 0; l < p.n_mid; ++l) {
+                        const int K = chain_in_width(p, l), N = p.mid[l];
+                        const int rows = N < 128 ? N : 128;
+                        SPLIT_STRESS(wd, 0x52);
+                        if (!mbar_wait(&s.act_ready, act_phase, 0x5200 + l, wd)) goto done;
+                        act_phase ^= 1;
+                        tc_fence_after();
+                        const uint32_t idesc = make_idesc_bf16(128, rows);
+                        for (int nc = 0; nc < N / rows; ++nc)
+                            for (int kb = 0; kb < K / 64; ++kb)
+                                SPLIT_MMA_BLOCK(ring, tmem + nc * 128, a_act + kb * 8 * kPlane, act_lo, kPlane, 128, rows, idesc, kb == 0, 0x5300)
+                        mma_commit(&s.acc_ready);
                     }
                     // last layer, transposed: D^T[channels x points], double-buffered in TMEM
                     {
@@ -319,21 +312,17 @@ split_chain_kernel(const ChainParams p)
                         if (!mbar_wait(&s.act_ready, act_phase, 0x52F0, wd)) goto done;
                         act_phase ^= 1;
                         tc_fence_after();
-                        CH_STAMP(0x120);
-                        const uint32_t idesc = make_idesc_bf16(128, p.pair ? 256 : 128);
+                        const uint32_t idesc = make_idesc_bf16(128, 128);
                         for (int cc = 0; cc < n_last_chunks; ++cc) {
                             const int b = cc & 1;
                             SPLIT_STRESS(wd, 0x54);
                             if (!mbar_wait(&s.last_empty[b], le_phase[b] ^ 1, 0x5400 + b, wd)) goto done;
                             le_phase[b] ^= 1;
                             tc_fence_after();
-                            const uint32_t d = p.pair ? tmem + b * 256 : tmem + 256 + b * 128;
-                            for (int kb = 0; kb < k_last / 64; ++kb) {
-                                if (p.pair) SPLIT_MMA_BLOCK_T(ring, d, a_pair + kb * 8 * 2 * kPlane, pair_lo, 2 * kPlane, 256, idesc, kb == 0, 0x5500)
-                                else        SPLIT_MMA_BLOCK_T(ring, d, a_act + kb * 8 * kPlane, act_lo, kPlane, 128, idesc, kb == 0, 0x5500)
-                            }
+                            const uint32_t d = tmem + 256 + b * 128;
+                            for (int kb = 0; kb < k_last / 64; ++kb)
+                                SPLIT_MMA_BLOCK_T(ring, d, a_act + kb * 8 * kPlane, act_lo, kPlane, 128, idesc, kb == 0, 0x5500)
                             mma_commit(&s.last_full[b]);
-                            CH_STAMP(0x130 + cc);
                         }
                     }
                 }
@@ -344,53 +333,40 @@ split_chain_kernel(const ChainParams p)
         const int row = epi_row(), half = epi_half();
         const uint32_t lane_addr = (uint32_t)(row & ~31) << 16;
         uint32_t acc_phase = 0, lf_phase[2] = {0, 0};
-        const int etid = threadIdx.x - 64;
-        (void)etid;
-        CH_STAMP_DECL(8192)
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int b = item / p.splits, sp_i = item % p.splits;
             const int t0 = (int)((int64_t)tiles_per_obj * sp_i / p.splits), t1 = (int)((int64_t)tiles_per_obj * (sp_i + 1) / p.splits);
             float rmax[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) rmax[i] = -INFINITY;
-            for (int t = t0; t < t1; t += nq) {
-                CH_STAMP_E(0x200);
-                for (int q = 0; q < nq; ++q) {
-                    // ---- first layer (rows past the end of the object replicate its last point, an odd tail pair
-                    //      repeats its tile: the max-pool is idempotent under duplicates)
-                    {
-                        const int tq = (t + q < t1) ? t + q : t1 - 1;
-                        int pidx = tq * kTile + row;
-                        if (pidx > p.n - 1) pidx = p.n - 1;
-                        const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
-                        float xv[8];
+            for (int t = t0; t < t1; ++t) {
+                // ---- first layer (rows past the end of the object replicate its last point: the max-pool is
+                //      idempotent under duplicates)
+                {
+                    int pidx = t * kTile + row;
+                    if (pidx > p.n - 1) pidx = p.n - 1;
+                    const float *px = p.x + (int64_t)b * p.sb + (int64_t)pidx * p.sp;
+                    float xv[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
-                        first_layer_split(s_act, act_lo, row, xv, p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b);
-                        fence_proxy_async_smem();
-                        CH_ARRIVE(&s.act_ready);
-                        CH_STAMP_E(0x210 + q * 8);
-                    }
-                    // ---- mid layers: this thread converts columns [half*N/2, (half+1)*N/2) of its row, in place
-                    //      (the layer's MMAs are complete when acc_ready fires); in pair mode the last mid layer
-                    //      writes rows q*128.. of the pair buffer instead
-                    int boff = 0;
-                    for (int l = 0; l < p.n_mid; ++l) {
-                        const int N = p.mid[l];
-                        const bool to_pair = p.pair && l == p.n_mid - 1;
-                        SPLIT_STRESS_WARP(wd, 0x41);
-                        if (!mbar_wait(&s.acc_ready, acc_phase, 0x4100 + l, wd)) goto done;
-                        acc_phase ^= 1;
-                        tc_fence_after();
-                        CH_STAMP_E(0x211 + q * 8 + l * 2);
-                        if (to_pair) epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_pair, pair_lo, 2 * kPlane, q * kTile + row, s.mid_b + boff);
-                        else         epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_act, act_lo, kPlane, row, s.mid_b + boff);
-                        boff += N;
-                        tc_fence_before();
-                        fence_proxy_async_smem();
-                        if (!(to_pair && q == 0)) CH_ARRIVE(&s.act_ready);     // tile X of a pair: the issuer has nothing to wait for yet
-                        CH_STAMP_E(0x212 + q * 8 + l * 2);
-                    }
+                    for (int c = 0; c < 8; ++c) xv[c] = (c < p.c_in) ? __ldg(px + c * p.sc) : 0.f;
+                    first_layer_split(s_act, act_lo, row, xv, p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b);
+                    fence_proxy_async_smem();
+                    CH_ARRIVE(&s.act_ready);
+                }
+                // ---- mid layers: this thread converts columns [half*N/2, (half+1)*N/2) of its row, in place (the
+                //      layer's MMAs are complete when acc_ready fires)
+                int boff = 0;
+                for (int l = 0; l < p.n_mid; ++l) {
+                    const int N = p.mid[l];
+                    SPLIT_STRESS_WARP(wd, 0x41);
+                    if (!mbar_wait(&s.acc_ready, acc_phase, 0x4100 + l, wd)) goto done;
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                    epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_act, act_lo, kPlane, row, s.mid_b + boff);
+                    boff += N;
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    CH_ARRIVE(&s.act_ready);
                 }
                 // ---- last layer: this thread owns channel (cc*128 + row) and half of the unit's points
 #pragma unroll
@@ -401,16 +377,14 @@ split_chain_kernel(const ChainParams p)
                         if (!mbar_wait(&s.last_full[bsel], lf_phase[bsel], 0x4200 + cc, wd)) goto done;
                         lf_phase[bsel] ^= 1;
                         tc_fence_after();
-                        CH_STAMP_E(0x230 + cc * 2);
                         float m0 = rmax[cc], m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-                        const int ncol = p.pair ? 128 : 64;
-                        const uint32_t ta = tmem + lane_addr + (p.pair ? bsel * 256 : 256 + bsel * 128) + half * ncol;
-                        for (int c0 = 0; c0 < ncol; c0 += 64) {
+                        const uint32_t ta = tmem + lane_addr + 256 + bsel * 128 + half * 64;
+                        {
                             uint32_t v0[32], v1[32];
-                            tmem_ld32(ta + c0, v0);
-                            tmem_ld32(ta + c0 + 32, v1);
+                            tmem_ld32(ta, v0);
+                            tmem_ld32(ta + 32, v1);
                             tmem_ld_wait();
-                            if (c0 + 64 >= ncol) { tc_fence_before(); CH_ARRIVE(&s.last_empty[bsel]); }   // all values are in registers
+                            tc_fence_before(); CH_ARRIVE(&s.last_empty[bsel]);       // all values are in registers
 #pragma unroll
                             for (int i = 0; i < 32; i += 8) {
                                 m0 = fmax3(m0, __uint_as_float(v0[i]), __uint_as_float(v0[i + 1]));
@@ -424,7 +398,6 @@ split_chain_kernel(const ChainParams p)
                             }
                         }
                         rmax[cc] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                        CH_STAMP_E(0x231 + cc * 2);
                     }
                 }
             }

@@ -173,7 +173,7 @@ class _timed:
 WATCHDOG_ROLES = {
     0x0: "split_tail_pair_kernel epilogue warps", 0x1: "split_tail_pair_kernel producer / notifier / MMA issuer",
     0x2: "split_tail_kernel epilogue warps", 0x3: "split_tail_kernel producer / MMA issuer",
-    0x4: "split_chain_kernel epilogue warps", 0x5: "split_chain_kernel producer / MMA issuer",
+    0x4: "split_chain(_pair)_kernel epilogue warps", 0x5: "split_chain(_pair)_kernel producer / MMA issuer",
     0x6: "trunk_pair_kernel epilogue warps", 0x7: "trunk_pair_kernel producer / MMA issuer",
     0x8: "seg_pass1_kernel reducer / front warps", 0x9: "seg_pass1_kernel producer / MMA issuers",
     0xA: "seg_pass2_kernel loader / MMA issuers", 0xB: "seg_pass2_kernel epilogue warps",

@@ -106,6 +106,7 @@ class SplitChainPack:
             setattr(s, k, self.t[k].data_ptr())
         self.struct = s
         self.last = s.last
+        self.pair = bool(pair)
 
 
 class SplitSegPack:
@@ -147,7 +148,7 @@ def pack_trunk(fw):
     return SplitChainPack(fw, ["conv1", "conv2", "conv3", "conv4"], pair=False)
 
 
-def chain_maxpool(pack, x, name="split_chain_kernel"):
+def chain_maxpool(pack, x, name=None):
     """x (bs,C,n) any strides -> (bs,last) fp32 = relu(max over points of the chain)."""
     ops._need_cuda(x)
     bs, C, n = x.shape
@@ -155,6 +156,7 @@ def chain_maxpool(pack, x, name="split_chain_kernel"):
     out = torch.zeros((bs, pack.last), device=x.device, dtype=torch.float32)
     sb, sc, sp = x.stride()
     check_abort("chain_maxpool_bf16x3 launch", x.device)
+    name = name or ("split_chain_pair_kernel" if pack.pair else "split_chain_kernel")
     with _timed("%s[last=%d]" % (name, pack.last)):
         _lib.check(_lib.lib().al3d_chain_maxpool_bf16x3(ctypes.byref(pack.struct), x.data_ptr(), sb, sc, sp, bs, n,
                                                         out.data_ptr(), ops._stream()), "chain_maxpool_bf16x3")
