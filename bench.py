@@ -204,7 +204,7 @@ def run_reference(args, rank, world):
             "config": _config(args, world, None, sample=sample),
             "cpu_baseline": {"value": val, "unit": "objects/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def _config(args, world, t_local, **extra):
@@ -252,7 +252,27 @@ def bench_crop(dev, peaks, n_frames=200):
             "l2": "%.0f MB of points per sweep > 126 MB L2" % (plan.read_bytes / 1e6)}
 
 
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its version on rank 0), so the
+    real stdout is kept aside for the result line and file descriptor 1 is pointed at stderr for everything else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -488,7 +508,7 @@ def main():
             "kernel_ms": kernel_ms, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fast_mode": fast, "crop": crop_res,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
