@@ -53,7 +53,28 @@ def _drop(bs, n, seed=3):
     return (torch.rand((bs, 128, n), generator=g) >= 0.5).float() * 2.0
 
 
-def _check_grads(named_params, grads_of, grads32, grads64):
+# GEMM arithmetic of the training step: "f32" = every GEMM on the fp32 SIMT kernels (the default: gradients at the fp32
+# oracle's own noise level), "x3" = the split-precision tensor-core GEMMs (csrc/gemm_split.cu; opt-in, 1.75x faster step).
+# Train-mode BatchNorm subtracts the batch mean, so where |mean| >> std the ~1e-5 relative error of a bf16x3 product is
+# amplified by mean/std: measured on the B200 the logits agree to 3e-4 of max|logit| (fp32 mode 3e-5), the losses to
+# 1e-4, and the gradients to 2-3e-2 in the worst tensor / 1-5e-3 in the median (fp32 mode 4e-3 / 1e-3; the dynamic net has
+# one BatchNorm-bias gradient at 0.19 where the fp32 torch oracle itself is 1.5e-2 away from float64).  Far tighter than
+# bf16 autocast training, but not the reference's arithmetic -- hence opt-in.  Bounds for x3: worst tensor < 0.3 and within
+# 15x the fp32 oracle's worst (+1e-2); median < 1e-2.
+TOL = {"f32": {"logits": 1e-4, "loss": 1e-4, "stats_rtol": 1e-4, "grad_max": 1e-2, "grad_med": 2.5e-3, "grad_slack": 5e-4, "grad_mult": 3},
+       "x3": {"logits": 1e-3, "loss": 1e-3, "stats_rtol": 1e-3, "grad_max": 0.3, "grad_med": 1e-2, "grad_slack": 1e-2, "grad_mult": 15}}
+
+
+@pytest.fixture(params=["x3", "f32"])
+def gemm_mode(request):
+    old = tr.GEMM_X3
+    tr.GEMM_X3 = request.param == "x3"
+    yield request.param
+    tr.GEMM_X3 = old
+
+
+def _check_grads(named_params, grads_of, grads32, grads64, tol=None):
+    tol = tol or TOL["f32"]
     errs, floors, names = [], [], []
     for name, p in named_params:
         g, r32, r64 = grads_of(p).detach().cpu().double(), grads32[name].double(), grads64[name]
@@ -66,8 +87,8 @@ def _check_grads(named_params, grads_of, grads32, grads64):
         floors.append(float((r32 - r64).abs().max()) / scale)
         names.append(name)
     worst = int(np.argmax(errs))
-    assert max(errs) < 3 * max(floors) + 5e-4, (names[worst], errs[worst], max(floors))
-    assert max(errs) < 1e-2 and float(np.median(errs)) < 2.5e-3, (float(np.median(errs)), float(np.median(floors)))
+    assert max(errs) < tol["grad_mult"] * max(floors) + tol["grad_slack"], (names[worst], errs[worst], max(floors))
+    assert max(errs) < tol["grad_max"] and float(np.median(errs)) < tol["grad_med"], (max(errs), float(np.median(errs)), float(np.median(floors)))
     return {"worst": (names[worst], errs[worst]), "median": float(np.median(errs)), "oracle_fp32_worst": max(floors),
             "oracle_fp32_median": float(np.median(floors))}
 
@@ -142,7 +163,8 @@ def test_fused_adam_matches_torch_adam():
 
 
 @pytest.mark.parametrize("dropout", [False, True])
-def test_fused_training_step_matches_oracle(dropout):
+def test_fused_training_step_matches_oracle(dropout, gemm_mode):
+    tol = TOL[gemm_mode]
     sd, pts, init_box, gt, labels = _case("static_one")
     bs, _, n = pts.shape
     drop = _drop(bs, n) if dropout else None
@@ -155,23 +177,28 @@ def test_fused_training_step_matches_oracle(dropout):
     lab = tuple(t.to(DEV) for t in labels)
     out = step.forward_backward(pts.to(DEV), init_box.to(DEV), lab, drop_mask=drop.to(DEV) if dropout else None)
     torch.cuda.synchronize()
-    assert rel_err(out["logits"].cpu(), oout["logits"].detach()) < 1e-4
-    assert torch.equal(out["mask"].cpu(), oout["mask"])
+    ologits = oout["logits"].detach()
+    assert rel_err(out["logits"].cpu(), ologits) < tol["logits"]
+    flips = out["mask"].cpu() != oout["mask"]
+    margin = (ologits[..., 1] - ologits[..., 0]).abs()
+    assert int(flips.sum()) == 0 or float(margin[flips].max()) < 2 * tol["logits"] * float(ologits.abs().max())
+    if gemm_mode == "f32":
+        assert int(flips.sum()) == 0
     for k in ("total_loss", "mask_loss", "center_loss", "heading_class_loss", "size_class_loss",
               "heading_residuals_normalized_loss", "size_residuals_normalized_loss"):
-        assert abs(float(out[k]) - float(ols[k])) <= 1e-4 * max(abs(float(ols[k])), 1e-3), k
-    worst = _check_grads(model.named_parameters(), step.grads.view, ograds, ograds64)
-    print("worst relative gradient error vs the fp64 oracle (ours, fp32 oracle's own):", worst)
+        assert abs(float(out[k]) - float(ols[k])) <= tol["loss"] * max(abs(float(ols[k])), 1e-3), k
+    worst = _check_grads(model.named_parameters(), step.grads.view, ograds, ograds64, tol)
+    print(gemm_mode, "worst relative gradient error vs the fp64 oracle (ours, fp32 oracle's own):", worst)
     for name, b in model.named_buffers():
         if name.endswith("running_mean") or name.endswith("running_var"):
-            assert torch.allclose(b.cpu(), ostats[name], rtol=1e-4, atol=1e-6), name
-    # seg accuracy metric (tools/static_train.py:128-129)
+            assert torch.allclose(b.cpu(), ostats[name], rtol=tol["stats_rtol"], atol=1e-5 if gemm_mode == "x3" else 1e-6), name
+    # seg accuracy metric (tools/static_train.py:128-129): computed from OUR logits, so compare with torch on the same tensor
     cnt = int(tr.seg_accuracy_count(out["logits"], lab[0]))
-    assert cnt == int(torch.argmax(oout["logits"].detach(), 2).eq(labels[0].long()).sum())
+    assert cnt == int(torch.argmax(out["logits"].cpu(), 2).eq(labels[0].long()).sum())
 
 
 @pytest.mark.parametrize("kind", ["static_one", "static_two", "dynamic"])
-def test_reference_style_loop_through_autograd(kind):
+def test_reference_style_loop_through_autograd(kind, gemm_mode):
     """model.train(); out = model(...); criterion(out, ...)['total_loss'].backward() -- the reference's loop -- gives the
     oracle's loss and parameter gradients (dropout switched off on both sides: its RNG stream is torch's own)."""
     sd, pts, aux, gt, labels = _case(kind)
@@ -197,13 +224,13 @@ def test_reference_style_loop_through_autograd(kind):
     opt.zero_grad()
     ls["total_loss"].backward()
     torch.cuda.synchronize()
-    assert abs(float(ls["total_loss"]) - float(ols["total_loss"])) <= 1e-4 * abs(float(ols["total_loss"]))
-    worst = _check_grads(model.named_parameters(), lambda p: p.grad, ograds, ograds64)
-    print(kind, "worst relative gradient error vs the fp64 oracle (ours, fp32 oracle's own):", worst)
+    assert abs(float(ls["total_loss"]) - float(ols["total_loss"])) <= TOL[gemm_mode]["loss"] * abs(float(ols["total_loss"]))
+    worst = _check_grads(model.named_parameters(), lambda p: p.grad, ograds, ograds64, TOL[gemm_mode])
+    print(kind, gemm_mode, "worst relative gradient error vs the fp64 oracle (ours, fp32 oracle's own):", worst)
     opt.step()                                           # torch's optimiser consumes the gradients as usual
 
 
-def test_three_fused_steps_track_torch_adam_on_the_oracle():
+def test_three_fused_steps_track_torch_adam_on_the_oracle(gemm_mode):
     sd, pts, init_box, gt, labels = _case("static_one")
     model = sm.StaticModelOneBoxEst().to(DEV).train()
     model.load_state_dict(sd)
@@ -228,7 +255,8 @@ def test_three_fused_steps_track_torch_adam_on_the_oracle():
             P[k] = v
     # Adam's first steps are ~ lr * sign(g): components whose sign is rounding noise move differently on the two sides, so
     # the trajectories agree to a few percent, not to rounding
-    assert abs(gl[0] - ol[0]) <= 1e-4 * ol[0] and np.allclose(gl, ol, rtol=6e-2), (gl, ol)
+    # (x3: the noisier gradients flip more of those signs -- the third loss is within 25 %)
+    assert abs(gl[0] - ol[0]) <= TOL[gemm_mode]["loss"] * ol[0] and np.allclose(gl, ol, rtol=6e-2 if gemm_mode == "f32" else 0.25), (gl, ol)
     assert gl[-1] < gl[0]                                 # and it learns
 
 
@@ -248,3 +276,58 @@ def test_loss_modules_backward_through_autograd():
     ls["total_loss"].backward()
     for k in out:
         assert rel_err(dev_in[k].grad.cpu(), ref_in[k].grad) < 1e-4, k
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core GEMMs
+@pytest.mark.parametrize("M,N,K", [(4096, 64, 64), (5000, 128, 64), (2048, 256, 128), (3000, 512, 256), (1024, 1024, 128),
+                                   (1500, 128, 1024), (148 * 128 * 2 + 77, 256, 512)])
+def test_gemm_x3_nt_matches_fp64(M, N, K):
+    """C = A . B^T (+ bias) in split precision against torch float64: ~1e-5 of max|C| (bf16x3, fp32 accumulation)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((M, K + 8), generator=g).to(DEV)[:, :K]          # row stride > K
+    w = (torch.randn((N, K), generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn((N,), generator=g).to(DEV)
+    ref = (a.double() @ w.double().t() + bias.double())
+    got = tr.linear_x3(a, w, bias)
+    torch.cuda.synchronize()
+    err = float((got.double() - ref).abs().max() / ref.abs().max())
+    assert err < 3e-5, err
+    # dgrad form: the same product from the transposed weight, accumulated onto an existing tensor
+    wt = w.t().contiguous()
+    base = torch.randn((M, N), generator=g).to(DEV)
+    out = base.clone()
+    tr.linear_x3(a, wt, out=out, accumulate=True, transposed=True)
+    ref2 = base.double() + a.double() @ w.double().t()
+    err2 = float((out.double() - ref2).abs().max() / ref2.abs().max())
+    assert err2 < 3e-5, err2
+
+
+def test_gemm_x3_nt_rowbias_per_group():
+    M, N, K, rpg = 4096, 512, 64, 512
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn((M, K), generator=g).to(DEV)
+    w = (torch.randn((N, K), generator=g) / 8).to(DEV)
+    rb = torch.randn((M // rpg, N), generator=g).to(DEV)
+    got = tr.linear_x3(a, w, rowbias=rb, rows_per_group=rpg)
+    ref = a.double() @ w.double().t() + rb.double().repeat_interleave(rpg, 0)
+    assert float((got.double() - ref).abs().max() / ref.abs().max()) < 3e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 64, 64), (5000, 128, 64), (2048, 128, 256), (3001, 256, 512), (4096, 1024, 128),
+                                   (1500, 128, 1024), (64 * 4096, 512, 64)])
+def test_gemm_x3_tn_wgrad_matches_fp64(M, N, K):
+    """dW = dY^T X (reduction over the rows) in split precision against torch float64."""
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    dy = torch.randn((M, N), generator=g).to(DEV)
+    x = torch.randn((M, K + 4), generator=g).to(DEV)[:, :K]
+    dw = torch.full((N, K), 7.0, device=DEV)
+    tr.wgrad_x3(dy, x, dw)
+    torch.cuda.synchronize()
+    ref = dy.double().t() @ x.double()
+    err = float((dw.double() - ref).abs().max() / ref.abs().max())
+    assert err < 3e-5, err
+    again = torch.empty_like(dw)
+    tr.wgrad_x3(dy, x, again)
+    assert torch.equal(again, dw)                                  # fixed reduction order: bit-reproducible
+    tr.wgrad_x3(dy, x, dw, accumulate=True)
+    assert float((dw.double() - 2 * ref).abs().max() / ref.abs().max()) < 6e-5
