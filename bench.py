@@ -252,6 +252,83 @@ def bench_crop(dev, peaks, n_frames=200):
             "l2": "%.0f MB of points per sweep > 126 MB L2" % (plan.read_bytes / 1e6)}
 
 
+# ------------------------------------------------------------------------------------------------ the other BASELINE configs
+def _events_ms(fn, warmup, iters):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_dynamic(dev, precision):
+    """configs[1]: dynamic-object model forward, 64 tracks x (5 x 1024 points + 101-step box trajectory); and the same
+    model at 4096 tracks for its throughput."""
+    import numpy as np
+    synth = importlib.import_module("3dal_pytorch_b200.synth")
+    dm = importlib.import_module("3dal_pytorch_b200.dynamic_model")
+    spec = importlib.import_module("3dal_pytorch_b200.spec")
+    tr = synth.dynamic_tracks(64, seed=2)
+    sd = synth.random_state_dict("dynamic", seed=synth.REFERENCE_SEED)
+    m = dm.DynamicModel().to(dev).eval()
+    m.load_state_dict(sd)
+    m.precision = precision
+    out = {"workload": "dynamic model forward, 5-frame 1024-point windows + 101-step box trajectory (BASELINE.json configs[1])",
+           "precision": precision}
+    for bs in (64, 4096):
+        rep = -(-bs // 64)
+        pts = torch.from_numpy(np.tile(tr["pts_pm"], (rep, 1, 1))[:bs]).to(dev).transpose(2, 1)
+        box = torch.from_numpy(np.tile(tr["box_sm"], (rep, 1, 1))[:bs]).to(dev).transpose(2, 1)
+        with torch.no_grad():
+            ms = _events_ms(lambda: m(pts, box, None), 3, 10 if bs == 64 else 3)
+        out["tracks_%d" % bs] = {"ms": ms, "objects_per_s": bs / (ms * 1e-3),
+                                 "model_tflops": bs * spec.flops_per_object("dynamic", 5120) / (ms * 1e-3) / 1e12}
+    return out
+
+
+def bench_train_step(dev, rank, world, dist, steps=5):
+    """configs[4]: static one-box training step (train-mode BN, dropout, fused loss, backward, ONE flat-bucket all-reduce,
+    fused Adam), 64 tracks x 4096 points per GPU, in both GEMM modes (3dal_pytorch_b200/train.py)."""
+    synth = importlib.import_module("3dal_pytorch_b200.synth")
+    sm = importlib.import_module("3dal_pytorch_b200.static_model")
+    tr = importlib.import_module("3dal_pytorch_b200.train")
+    bs, n = 64, 4096
+    d = synth.static_tracks_device(bs, n=n, seed=100 + rank, device=dev)
+    pts, init_box = d["pts_pm"].transpose(2, 1), d["init_box"]
+    g = torch.Generator(device=dev); g.manual_seed(5 + rank)
+    labels = ((torch.rand((bs, n), device=dev, generator=g) < 0.3).float(), torch.randn((bs, 3), device=dev, generator=g) * 0.3,
+              torch.randint(0, 12, (bs,), device=dev, generator=g), torch.randn((bs,), device=dev, generator=g) * 0.1,
+              torch.randint(0, 3, (bs,), device=dev, generator=g), torch.randn((bs, 3), device=dev, generator=g) * 0.2)
+    out = {"workload": "static one-box training step, %d tracks x %d points per GPU, %d GPU(s) (BASELINE.json configs[4])" % (bs, n, world)}
+    old = tr.GEMM_X3
+    try:
+        for mode in ("f32", "x3"):
+            tr.set_gemm_mode(mode)
+            model = sm.StaticModelOneBoxEst().to(dev).train()
+            model.load_state_dict(synth.random_state_dict("static_one", seed=synth.REFERENCE_SEED))
+            step = tr.TrainStep(model, lr=1e-3, weight_decay=1e-4, dropout_p=0.5)
+            if world > 1:
+                dist.barrier()
+            ms = _events_ms(lambda: step.step(pts, init_box, labels), 2, steps)
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            out[mode] = {"ms_per_step": ms, "objects_per_s": world * bs / (ms * 1e-3),
+                         "gemm": "fp32 SIMT (gradients at the fp32 oracle's noise level; the default)" if mode == "f32"
+                         else "bf16x3 tensor cores (opt-in; see tests/test_gpu_train.py TOL)"}
+            del step, model
+    finally:
+        tr.GEMM_X3 = old
+    torch.cuda.empty_cache()
+    return out
+
+
 _RESULT_OUT = None
 
 
@@ -285,6 +362,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fast-mode", action="store_true")
     ap.add_argument("--no-crop", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-lines of BASELINE configs[1] (dynamic) and configs[4] (training step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -471,6 +549,13 @@ def main():
                 "tolerance": "logits within 3e-2 of max|ref| (measured 2.2e-2), ~1 % of the mask bits differ from the fp32 "
                              "reference (profiles/r2_parity_per_tensor.jsonl): does NOT meet the 1e-3 bar"}
 
+    # ---------------- BASELINE configs[4] (every rank: the step all-reduces its gradient bucket) and configs[1]
+    train_res = dyn_res = None
+    if not args.no_configs:
+        train_res = bench_train_step(dev, rank, world, dist if world > 1 else None)
+        if rank == 0 and world == 1:
+            dyn_res = bench_dynamic(dev, args.precision)
+
     if rank == 0:
         peaks = _peaks()
         roofline = roofline_of(kernel_ms, args.precision, peaks, clocks)
@@ -507,6 +592,7 @@ def main():
             "model_tflops": value * flop_obj / 1e12 / world, "flop_per_object": flop_obj,
             "kernel_ms": kernel_ms, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fast_mode": fast, "crop": crop_res,
+            "dynamic": dyn_res, "train_step": train_res,
         }
         _emit(line)
     if world > 1:
