@@ -54,8 +54,11 @@ col_reduce_kernel(const float *__restrict__ x, int64_t ldx, const float *__restr
     if (col < C) {
         float mean = 0.f, rstd = 0.f, gamma = 0.f, beta = 0.f;
         if (MODE == 1) { mean = ctx.mean[col]; rstd = ctx.rstd[col]; gamma = ctx.gamma[col]; beta = ctx.beta[col]; }
+        // MODE 0 sums (x - s) and (x - s)^2 with the shift s = row 0 of the matrix: a sample lies within a few standard
+        // deviations of the mean, so E[(x-s)^2] - E[x-s]^2 does not cancel the way E[x^2] - E[x]^2 does when |mean| >> std
+        const float shift = MODE == 0 ? __ldg(x + col) : 0.f;
         for (int64_t m = r0 + w; m < r1; m += kColWarps) {
-            const float v = __ldg(x + m * ldx + col);
+            const float v = __ldg(x + m * ldx + col) - shift;
             if (MODE == 0) { a += v; b = fmaf(v, v, b); }
             else if (MODE == 2) a += v;
             else {
@@ -80,16 +83,17 @@ col_reduce_kernel(const float *__restrict__ x, int64_t ldx, const float *__restr
 
 // BatchNorm statistics from the slab partials: mean, rstd = 1/sqrt(biased var + eps), running-stat update
 // (running = (1 - momentum) * running + momentum * batch, with the UNBIASED variance, nn.BatchNorm1d semantics).
-__global__ void bn_finalize_kernel(const float *__restrict__ part, int n_slabs, int C, int64_t M, float eps, float momentum,
-                                   float *__restrict__ mean, float *__restrict__ rstd, float *__restrict__ running_mean,
-                                   float *__restrict__ running_var)
+__global__ void bn_finalize_kernel(const float *__restrict__ part, int n_slabs, int C, int64_t M, const float *__restrict__ shift_row,
+                                   float eps, float momentum, float *__restrict__ mean, float *__restrict__ rstd,
+                                   float *__restrict__ running_mean, float *__restrict__ running_var)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    double s = 0.0, ss = 0.0;
+    double s = 0.0, ss = 0.0;                                  // sums of (x - shift) and (x - shift)^2
     for (int i = 0; i < n_slabs; ++i) { s += part[((int64_t)i * 2 + 0) * C + c]; ss += part[((int64_t)i * 2 + 1) * C + c]; }
-    const double mu = s / (double)M;
-    double var = ss / (double)M - mu * mu;
+    const double d = s / (double)M;
+    const double mu = (double)shift_row[c] + d;
+    double var = ss / (double)M - d * d;
     if (var < 0.0) var = 0.0;
     mean[c] = (float)mu;
     rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -143,6 +147,146 @@ bn_backward_apply_kernel(const float *dz, const float *__restrict__ y, int64_t M
         float g = dz[i] * bn_drop(ctx, m, c);
         if (ctx.relu && !(fmaf(ctx.gamma[c], xhat, ctx.beta[c]) > 0.f)) g = 0.f;
         dy[i] = ctx.gamma[c] * ctx.rstd[c] * (g - sum_g[c] * inv_m - xhat * sum_gx[c] * inv_m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// float4 forms of the three passes above for contiguous (M, C) matrices with C a multiple of 64 (every BatchNorm of the
+// nets at training batch sizes): 16-byte loads, four rows in flight per thread, per-thread channel constants in
+// registers (no per-element index division).  Same outputs, same fixed reduction order within a launch geometry.
+// ---------------------------------------------------------------------------------------------------------------
+// four consecutive per-channel constants; the vectors may be views of a flat parameter / gradient buffer (4-byte aligned)
+__device__ __forceinline__ float4 ld4(const float *p) { return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)); }
+
+__device__ __forceinline__ float bn_g_of(float dz, float y, float mean, float rstd, float gamma, float beta, float drop, int relu, float &xhat)
+{
+    xhat = (y - mean) * rstd;
+    float g = dz * drop;
+    if (relu && !(fmaf(gamma, xhat, beta) > 0.f)) g = 0.f;
+    return g;
+}
+
+// grid = (C / (4 * tile_cv), n_slabs), 256 threads; tile_cv = 32 (one row per warp step) or 16 (two rows per warp step)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+col_reduce_v4_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t M, int C, int tile_cv, int64_t rows_per_slab,
+                     BnCtx ctx, float *__restrict__ out)
+{
+    __shared__ float4 red[2][kColWarps][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int rows_w = 32 / tile_cv;                                  // rows per warp step
+    const int cvl = lane % tile_cv, rsub = lane / tile_cv;
+    const int col = (blockIdx.x * tile_cv + cvl) * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab, r1 = min(r0 + rows_per_slab, M);
+    const int64_t step = (int64_t)kColWarps * rows_w;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    float4 mean = a, rstd = a, gamma = a, beta = a;
+    if (MODE == 1) { mean = ld4(ctx.mean + col); rstd = ld4(ctx.rstd + col); gamma = ld4(ctx.gamma + col); beta = ld4(ctx.beta + col); }
+    const float4 shift = MODE == 0 ? ld4(x + col) : make_float4(0.f, 0.f, 0.f, 0.f);     // row 0, see col_reduce_kernel
+    for (int64_t m0 = r0 + (int64_t)w * rows_w + rsub; m0 < r1; m0 += 4 * step) {
+        float4 v[4], u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t m = m0 + k * step;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f); u[k] = v[k];
+            if (m < r1) {
+                v[k] = __ldg(reinterpret_cast<const float4 *>(x + m * C + col));
+                if (MODE == 1) u[k] = __ldg(reinterpret_cast<const float4 *>(y + m * C + col));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t m = m0 + k * step;
+            if (m >= r1) break;
+            if (MODE == 0) {
+                const float4 t = make_float4(v[k].x - shift.x, v[k].y - shift.y, v[k].z - shift.z, v[k].w - shift.w);
+                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                b.x = fmaf(t.x, t.x, b.x); b.y = fmaf(t.y, t.y, b.y); b.z = fmaf(t.z, t.z, b.z); b.w = fmaf(t.w, t.w, b.w);
+            } else if (MODE == 2) {
+                a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
+            } else {
+                float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;
+                if (ctx.drop) { d0 = bn_drop(ctx, m, col); d1 = bn_drop(ctx, m, col + 1); d2 = bn_drop(ctx, m, col + 2); d3 = bn_drop(ctx, m, col + 3); }
+                float xh, g;
+                g = bn_g_of(v[k].x, u[k].x, mean.x, rstd.x, gamma.x, beta.x, d0, ctx.relu, xh); a.x += g; b.x = fmaf(g, xh, b.x);
+                g = bn_g_of(v[k].y, u[k].y, mean.y, rstd.y, gamma.y, beta.y, d1, ctx.relu, xh); a.y += g; b.y = fmaf(g, xh, b.y);
+                g = bn_g_of(v[k].z, u[k].z, mean.z, rstd.z, gamma.z, beta.z, d2, ctx.relu, xh); a.z += g; b.z = fmaf(g, xh, b.z);
+                g = bn_g_of(v[k].w, u[k].w, mean.w, rstd.w, gamma.w, beta.w, d3, ctx.relu, xh); a.w += g; b.w = fmaf(g, xh, b.w);
+            }
+        }
+    }
+    if (rows_w == 2) {                                                // the two row phases of a warp: fixed order (low half + high half)
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, 16); a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, 16); a.w += __shfl_xor_sync(0xffffffffu, a.w, 16);
+        b.x += __shfl_xor_sync(0xffffffffu, b.x, 16); b.y += __shfl_xor_sync(0xffffffffu, b.y, 16);
+        b.z += __shfl_xor_sync(0xffffffffu, b.z, 16); b.w += __shfl_xor_sync(0xffffffffu, b.w, 16);
+    }
+    red[0][w][lane] = a; red[1][w][lane] = b;
+    __syncthreads();
+    if (w == 0 && lane < tile_cv) {
+        float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+#pragma unroll
+        for (int i = 0; i < kColWarps; ++i) {                         // fixed order
+            const float4 p = red[0][i][lane], q = red[1][i][lane];
+            sa.x += p.x; sa.y += p.y; sa.z += p.z; sa.w += p.w; sb.x += q.x; sb.y += q.y; sb.z += q.z; sb.w += q.w;
+        }
+        if (MODE == 2) *reinterpret_cast<float4 *>(out + (int64_t)blockIdx.y * C + col) = sa;
+        else {
+            *reinterpret_cast<float4 *>(out + ((int64_t)blockIdx.y * 2 + 0) * C + col) = sa;
+            *reinterpret_cast<float4 *>(out + ((int64_t)blockIdx.y * 2 + 1) * C + col) = sb;
+        }
+    }
+}
+
+// every thread keeps ONE group of four channels (its constants live in registers) and strides over the rows;
+// requires (gridDim.x * 256) % (C / 4) == 0.  BACKWARD: dy = gamma * rstd * (g - sum_g / M - xhat * sum_gx / M).
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256)
+bn_apply_v4_kernel(const float *dz, const float *__restrict__ y, int64_t M, int C, BnCtx ctx, const float *__restrict__ sum_g,
+                   const float *__restrict__ sum_gx, float *out)
+{
+    const int CV = C >> 2;
+    const int64_t gtid = (int64_t)blockIdx.x * 256 + threadIdx.x, nthr = (int64_t)gridDim.x * 256;
+    const int col = (int)(gtid % CV) * 4;
+    const int64_t row_step = nthr / CV;
+    const float4 mean = ld4(ctx.mean + col), rstd = ld4(ctx.rstd + col), gamma = ld4(ctx.gamma + col), beta = ld4(ctx.beta + col);
+    float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sgx = sg;
+    const float inv_m = 1.f / (float)M;
+    if (BACKWARD) {
+        sg = ld4(sum_g + col); sgx = ld4(sum_gx + col);
+        sg.x *= inv_m; sg.y *= inv_m; sg.z *= inv_m; sg.w *= inv_m; sgx.x *= inv_m; sgx.y *= inv_m; sgx.z *= inv_m; sgx.w *= inv_m;
+    }
+    for (int64_t m0 = gtid / CV; m0 < M; m0 += 4 * row_step) {
+        float4 v[4], u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t m = m0 + k * row_step;
+            if (m < M) {
+                v[k] = __ldg(reinterpret_cast<const float4 *>(y + m * C + col));
+                if (BACKWARD) u[k] = *reinterpret_cast<const float4 *>(dz + m * C + col);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t m = m0 + k * row_step;
+            if (m >= M) break;
+            float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;
+            if (ctx.drop) { d0 = bn_drop(ctx, m, col); d1 = bn_drop(ctx, m, col + 1); d2 = bn_drop(ctx, m, col + 2); d3 = bn_drop(ctx, m, col + 3); }
+            float4 o;
+            if (!BACKWARD) {
+                o.x = fmaf(gamma.x, (v[k].x - mean.x) * rstd.x, beta.x); o.y = fmaf(gamma.y, (v[k].y - mean.y) * rstd.y, beta.y);
+                o.z = fmaf(gamma.z, (v[k].z - mean.z) * rstd.z, beta.z); o.w = fmaf(gamma.w, (v[k].w - mean.w) * rstd.w, beta.w);
+                if (ctx.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                o.x *= d0; o.y *= d1; o.z *= d2; o.w *= d3;
+            } else {
+                float xh, g;
+                g = bn_g_of(u[k].x, v[k].x, mean.x, rstd.x, gamma.x, beta.x, d0, ctx.relu, xh); o.x = gamma.x * rstd.x * (g - sg.x - xh * sgx.x);
+                g = bn_g_of(u[k].y, v[k].y, mean.y, rstd.y, gamma.y, beta.y, d1, ctx.relu, xh); o.y = gamma.y * rstd.y * (g - sg.y - xh * sgx.y);
+                g = bn_g_of(u[k].z, v[k].z, mean.z, rstd.z, gamma.z, beta.z, d2, ctx.relu, xh); o.z = gamma.z * rstd.z * (g - sg.z - xh * sgx.z);
+                g = bn_g_of(u[k].w, v[k].w, mean.w, rstd.w, gamma.w, beta.w, d3, ctx.relu, xh); o.w = gamma.w * rstd.w * (g - sg.w - xh * sgx.w);
+            }
+            *reinterpret_cast<float4 *>(out + m * C + col) = o;
+        }
     }
 }
 
@@ -375,6 +519,25 @@ static int slabs_for(int64_t M, int64_t tiles, int64_t min_rows, int64_t *rows_p
 using namespace al3d;
 using namespace al3d::train;
 
+// geometry of the float4 kernels; 0 if (M, C) does not qualify
+static int v4_mask()
+{
+    const char *e = getenv("AL3D_BN_V4");        // debugging aid: bit mask of the float4 kernels to use (default: all)
+    return e ? atoi(e) : 63;
+}
+static int v4_tile_cv(int C, const void *a, const void *b, const void *c)
+{
+    if (C % 64 != 0 || C / 4 > 256 || 256 % (C / 4) != 0) return 0;       // the apply kernel needs (C / 4) | 256
+    if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) return 0;
+    return (C / 4) % 32 == 0 ? 32 : 16;
+}
+static int v4_slabs(int64_t M, int C, int tile_cv, int64_t *rps) { return slabs_for(M, (C / 4) / tile_cv, 512, rps); }
+static int v4_apply_grid(int64_t M, int C)
+{
+    const int64_t want = ceil_div(M * (int64_t)(C / 4), 256 * 4);        // ~4 float4 per thread
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, 148 * 8));
+}
+
 static BnCtx make_ctx(const float *mean, const float *rstd, const float *gamma, const float *beta, const float *drop, int64_t sg,
                       int64_t sc, int64_t sr, int64_t rows_per_group, int relu, int64_t M)
 {
@@ -389,7 +552,8 @@ extern "C" int al3d_train_ws_floats(int64_t M, int C)
 {
     // largest scratch any column reduction over (M, C) needs, in floats
     int64_t rps;
-    const int slabs = slabs_for(M, ceil_div(C, kColTile), 256, &rps);
+    int slabs = slabs_for(M, ceil_div(C, kColTile), 256, &rps);
+    if (C % 64 == 0 && C / 4 <= 256) slabs = std::max(slabs, v4_slabs(M, C, (C / 4) % 32 == 0 ? 32 : 16, &rps));
     return (int)std::min<int64_t>((int64_t)slabs * 2 * C, 0x7fffffff);
 }
 
@@ -402,13 +566,26 @@ extern "C" int al3d_bn_train_forward(const float *y, int64_t M, int C, const flo
     AL3D_CHECK_ARG(M >= 2 && C >= 1, "al3d_bn_train_forward: M=%lld C=%d (batch statistics need >= 2 rows)", (long long)M, C);
     cudaStream_t st = (cudaStream_t)stream;
     int64_t rps;
-    const int slabs = slabs_for(M, ceil_div(C, kColTile), 256, &rps);
     BnCtx none = make_ctx(nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, M);
-    col_reduce_kernel<0><<<dim3((unsigned)ceil_div(C, kColTile), slabs), kColTile * kColWarps, 0, st>>>(y, C, nullptr, 0, M, C, rps, none, ws);
-    AL3D_CHECK_LAUNCH("col_reduce_kernel<0>");
-    bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(ws, slabs, C, M, eps, momentum, mean, rstd, running_mean, running_var);
+    const int tcv = v4_tile_cv(C, y, z, ws);
+    int slabs;
+    if (tcv && (v4_mask() & 1)) {
+        slabs = v4_slabs(M, C, tcv, &rps);
+        col_reduce_v4_kernel<0><<<dim3((unsigned)((C / 4) / tcv), slabs), 256, 0, st>>>(y, nullptr, M, C, tcv, rps, none, ws);
+        AL3D_CHECK_LAUNCH("col_reduce_v4_kernel<0>");
+    } else {
+        slabs = slabs_for(M, ceil_div(C, kColTile), 256, &rps);
+        col_reduce_kernel<0><<<dim3((unsigned)ceil_div(C, kColTile), slabs), kColTile * kColWarps, 0, st>>>(y, C, nullptr, 0, M, C, rps, none, ws);
+        AL3D_CHECK_LAUNCH("col_reduce_kernel<0>");
+    }
+    bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(ws, slabs, C, M, y, eps, momentum, mean, rstd, running_mean, running_var);
     AL3D_CHECK_LAUNCH("bn_finalize_kernel");
     BnCtx ctx = make_ctx(mean, rstd, gamma, beta, drop, drop_sg, drop_sc, drop_sr, rows_per_group, relu, M);
+    if (tcv && (v4_mask() & 2)) {
+        bn_apply_v4_kernel<false><<<v4_apply_grid(M, C), 256, 0, st>>>(nullptr, y, M, C, ctx, nullptr, nullptr, z);
+        AL3D_CHECK_LAUNCH("bn_apply_v4_kernel");
+        return 0;
+    }
     const int grid = (int)std::min<int64_t>(ceil_div(M * C, 256), 148 * 16);
     bn_apply_kernel<<<grid, 256, 0, st>>>(y, M, C, ctx, z);
     AL3D_CHECK_LAUNCH("bn_apply_kernel");
@@ -424,13 +601,26 @@ extern "C" int al3d_bn_train_backward(const float *dz, const float *y, int64_t M
     AL3D_CHECK_ARG(M >= 2 && C >= 1, "al3d_bn_train_backward: M=%lld C=%d", (long long)M, C);
     cudaStream_t st = (cudaStream_t)stream;
     int64_t rps;
-    const int slabs = slabs_for(M, ceil_div(C, kColTile), 256, &rps);
     BnCtx ctx = make_ctx(mean, rstd, gamma, beta, drop, drop_sg, drop_sc, drop_sr, rows_per_group, relu, M);
-    col_reduce_kernel<1><<<dim3((unsigned)ceil_div(C, kColTile), slabs), kColTile * kColWarps, 0, st>>>(dz, C, y, C, M, C, rps, ctx, ws);
-    AL3D_CHECK_LAUNCH("col_reduce_kernel<1>");
+    const int tcv = (((uintptr_t)ws & 15) == 0) ? v4_tile_cv(C, dz, y, dy) : 0;
+    int slabs;
+    if (tcv && (v4_mask() & 4)) {
+        slabs = v4_slabs(M, C, tcv, &rps);
+        col_reduce_v4_kernel<1><<<dim3((unsigned)((C / 4) / tcv), slabs), 256, 0, st>>>(dz, y, M, C, tcv, rps, ctx, ws);
+        AL3D_CHECK_LAUNCH("col_reduce_v4_kernel<1>");
+    } else {
+        slabs = slabs_for(M, ceil_div(C, kColTile), 256, &rps);
+        col_reduce_kernel<1><<<dim3((unsigned)ceil_div(C, kColTile), slabs), kColTile * kColWarps, 0, st>>>(dz, C, y, C, M, C, rps, ctx, ws);
+        AL3D_CHECK_LAUNCH("col_reduce_kernel<1>");
+    }
     // dbeta = sum g, dgamma = sum g * xhat
     slab_sum_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(ws, slabs, 2, C, dbeta, dgamma);
     AL3D_CHECK_LAUNCH("slab_sum_kernel");
+    if (tcv && (v4_mask() & 8)) {
+        bn_apply_v4_kernel<true><<<v4_apply_grid(M, C), 256, 0, st>>>(dz, y, M, C, ctx, dbeta, dgamma, dy);
+        AL3D_CHECK_LAUNCH("bn_apply_v4_kernel");
+        return 0;
+    }
     const int grid = (int)std::min<int64_t>(ceil_div(M * C, 256), 148 * 16);
     bn_backward_apply_kernel<<<grid, 256, 0, st>>>(dz, y, M, C, ctx, dbeta, dgamma, dy);
     AL3D_CHECK_LAUNCH("bn_backward_apply_kernel");
@@ -448,6 +638,11 @@ extern "C" int al3d_group_colsum(const float *x, int64_t M, int C, int64_t rows_
         AL3D_CHECK_ARG(M % rows_per_group == 0, "al3d_group_colsum: M not a multiple of rows_per_group");
         const int64_t G = M / rows_per_group;
         AL3D_CHECK_ARG(G <= 65535, "al3d_group_colsum: too many groups");
+        if (const int tcv = (v4_mask() & 32) ? v4_tile_cv(C, x, out, nullptr) : 0) {
+            col_reduce_v4_kernel<2><<<dim3((unsigned)((C / 4) / tcv), (unsigned)G), 256, 0, st>>>(x, nullptr, M, C, tcv, rows_per_group, none, out);
+            AL3D_CHECK_LAUNCH("col_reduce_v4_kernel<2>");
+            return 0;
+        }
         col_reduce_kernel<2><<<dim3((unsigned)ceil_div(C, kColTile), (unsigned)G), kColTile * kColWarps, 0, st>>>(x, C, nullptr, 0, M, C,
                                                                                                                  rows_per_group, none, out);
         AL3D_CHECK_LAUNCH("col_reduce_kernel<2>");
@@ -455,9 +650,16 @@ extern "C" int al3d_group_colsum(const float *x, int64_t M, int C, int64_t rows_
     }
     AL3D_CHECK_ARG(ws, "al3d_group_colsum: workspace needed for the whole-matrix sum");
     int64_t rps;
-    const int slabs = slabs_for(M, ceil_div(C, kColTile), 256, &rps);
-    col_reduce_kernel<2><<<dim3((unsigned)ceil_div(C, kColTile), slabs), kColTile * kColWarps, 0, st>>>(x, C, nullptr, 0, M, C, rps, none, ws);
-    AL3D_CHECK_LAUNCH("col_reduce_kernel<2>");
+    int slabs;
+    if (const int tcv = (v4_mask() & 16) ? v4_tile_cv(C, x, ws, nullptr) : 0) {
+        slabs = v4_slabs(M, C, tcv, &rps);
+        col_reduce_v4_kernel<2><<<dim3((unsigned)((C / 4) / tcv), slabs), 256, 0, st>>>(x, nullptr, M, C, tcv, rps, none, ws);
+        AL3D_CHECK_LAUNCH("col_reduce_v4_kernel<2>");
+    } else {
+        slabs = slabs_for(M, ceil_div(C, kColTile), 256, &rps);
+        col_reduce_kernel<2><<<dim3((unsigned)ceil_div(C, kColTile), slabs), kColTile * kColWarps, 0, st>>>(x, C, nullptr, 0, M, C, rps, none, ws);
+        AL3D_CHECK_LAUNCH("col_reduce_kernel<2>");
+    }
     slab_sum_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(ws, slabs, 1, C, out, nullptr);
     AL3D_CHECK_LAUNCH("slab_sum_kernel");
     return 0;

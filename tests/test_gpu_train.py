@@ -93,9 +93,10 @@ def _check_grads(named_params, grads_of, grads32, grads64, tol=None):
             "oracle_fp32_median": float(np.median(floors))}
 
 
-def test_batchnorm_relu_dropout_forward_backward_against_torch():
+@pytest.mark.parametrize("bs,n,C", [(3, 700, 96), (5, 1024, 128), (4, 1280, 64), (2, 4096, 256), (3, 515, 1024), (64, 1, 512)])
+def test_batchnorm_relu_dropout_forward_backward_against_torch(bs, n, C):
+    """C = 96 runs the scalar kernels, the multiples of 64 the float4 kernels (csrc/train.cu)."""
     torch.manual_seed(0)
-    bs, n, C = 3, 700, 96
     M = bs * n
     y = torch.randn(M, C, device=DEV) * 2 + 0.5
     bn = torch.nn.BatchNorm1d(C).to(DEV)
