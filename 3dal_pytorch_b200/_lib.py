@@ -52,10 +52,10 @@ _SIGNATURES = {
     "al3d_group_max_forward": [_vp, _i64, _i64, _i, _vp, _vp, _vp],
     "al3d_group_max_backward": [_vp, _vp, _i64, _i64, _i, _vp, _vp],
     "al3d_wgrad_f32": [_vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _i64, _i, _vp],
-    "al3d_gemm_bf16x3_ws_bytes": [_i, _i],
-    "al3d_gemm_bf16x3_nt": [_vp, _i64, _i, _i, _vp, _i64, _i, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _vp],
-    "al3d_gemm_bf16x3_tn_ws_bytes": [_i64, _i, _i],
-    "al3d_gemm_bf16x3_tn": [_vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _i64, _i, _vp],
+    "al3d_gemm_split_ws_bytes": [_i, _i, _i],
+    "al3d_gemm_split_nt": [_vp, _i64, _i, _i, _vp, _i64, _i, _vp, _vp, _i, _i, _i, _vp, _i64, _i, _vp, _vp],
+    "al3d_gemm_split_tn_ws_bytes": [_i64, _i, _i, _i],
+    "al3d_gemm_split_tn": [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _i64, _i, _vp],
     "al3d_loss_backward": [_vp, _vp, _i64] + [_vp] * 10 + [_i, _vp, _vp, _vp, _vp],
     "al3d_seg_correct": [_vp, _vp, _i64, _vp, _vp],
     "al3d_adam_step": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp],
@@ -74,7 +74,7 @@ _SIGNATURES = {
     "al3d_tc_configure": [_i, _i],
     "al3d_set_debug_buffer": [_vp],
 }
-_RESTYPES = {"al3d_last_error": ctypes.c_char_p, "al3d_gemm_bf16x3_ws_bytes": ctypes.c_int64, "al3d_gemm_bf16x3_tn_ws_bytes": ctypes.c_int64}
+_RESTYPES = {"al3d_last_error": ctypes.c_char_p, "al3d_gemm_split_ws_bytes": ctypes.c_int64, "al3d_gemm_split_tn_ws_bytes": ctypes.c_int64}
 
 _lib = None
 
@@ -104,7 +104,7 @@ def lib():
 
 # kernels launched through this binding since import (bench.py reports it as gpu_launches)
 LAUNCHES = 0
-_NO_LAUNCH = ("train_ws_floats", "wgrad_ws_floats", "gemm_bf16x3_ws_bytes", "gemm_bf16x3_tn_ws_bytes", "tc_abort_code", "tc_status_word_host", "tc_configure", "set_debug_buffer", "crop_chunk_points", "crop_occ_words", "crop_hit_bytes")
+_NO_LAUNCH = ("train_ws_floats", "wgrad_ws_floats", "gemm_split_ws_bytes", "gemm_split_tn_ws_bytes", "tc_abort_code", "tc_status_word_host", "tc_configure", "set_debug_buffer", "crop_chunk_points", "crop_occ_words", "crop_hit_bytes")
 
 
 def check(rc, what=""):

@@ -1,13 +1,15 @@
 // Split-precision ("bf16x3") tensor-core GEMMs on fp32 operands in global memory: the layer GEMMs of the training step.
 //
-//   al3d_gemm_bf16x3_nt   C[M x N] (+)= A[M x K] . B[N x K]^T (+ bias[N] | per-group row bias)
+//   al3d_gemm_split_nt    C[M x N] (+)= A[M x K] . B[N x K]^T (+ bias[N] | per-group row bias)
 //                         forward  (A = activations, B = conv weight;      tools/static_model.py:279-295 in .train())
 //                         dgrad    (A = dY,          B = weight transposed; autograd of the same Conv1d / Linear)
-//   al3d_gemm_bf16x3_tn   C[N x K] (+)= A[M x N]^T . B[M x K]       (reduction over the M rows = points)
+//   al3d_gemm_split_tn    C[N x K] (+)= A[M x N]^T . B[M x K]       (reduction over the M rows = points)
 //                         wgrad    (A = dY, B = layer input)
 //
-// Arithmetic as in chain_split.cu: every fp32 value is carried as hi = bf16(x), lo = bf16(x - hi) and every product is
-// three tcgen05.mma (kind::f16, fp32 accumulation in TMEM); results agree with an fp32 GEMM to ~1e-5 relative.
+// Arithmetic, PARTS = 2 ("bf16x3", as in chain_split.cu): every fp32 value is carried as hi = bf16(x), lo = bf16(x - hi)
+// and every product is three tcgen05.mma (kind::f16, fp32 accumulation in TMEM): ~1e-5 relative to an fp32 GEMM.
+// PARTS = 3 ("bf16x6"): x = hi + mid + lo carries all 24 mantissa bits and a product is the six MMAs of combined order
+// <= 2 (hh, hm, mh, hl, lh, mm): ~1e-7 relative, i.e. fp32-grade -- the mode the training step uses by default.
 //
 // NT kernel.  Persistent, one CTA per SM, 320 threads.  An item is (128-row tile of A, pass of <= 256 output columns);
 // accumulators ping-pong between TMEM columns [0,256) and [256,512).  Warp 0 streams the packed weight blocks (hi, lo per
@@ -32,13 +34,15 @@ namespace al3d {
 namespace split {
 using namespace umma;
 
-constexpr int kSlabBytes = 32768;          // one A slab: 128 rows x 64 k, hi (16 KB) | lo (16 KB)
-constexpr int kGemmSlabs = 4;
-constexpr int kGemmStages = 5;
+constexpr int kPartBytes = 16384;          // one part (hi / mid / lo) of an A slab: 128 rows x 64 k bf16
+template <int PARTS> struct NtCfg;
+template <> struct NtCfg<2> { static constexpr int kSlabs = 4, kStages = 5; };
+template <> struct NtCfg<3> { static constexpr int kSlabs = 3, kStages = 4; };
 
 // ------------------------------------------------------------------------------------------------ weight packing
 // B fp32 (element (n, k) at b[n * ldb + k], or b[k * ldb + n] when `trans`) -> slots in consumption order:
-// pass p (np columns) > K slab s > column block nc (rows) > (hi slot, lo slot); a slot is a KP tile [rows x 64].
+// pass p (np columns) > K slab s > column block nc (rows) > PARTS slots (hi, [mid,] lo); a slot is a KP tile [rows x 64].
+template <int PARTS>
 __global__ void split_pack_kernel(const float *__restrict__ b, int64_t ldb, int trans, int N, int K, int np, int rows, uint8_t *__restrict__ img)
 {
     const int n_nc = np / rows, S = K / 64;
@@ -49,13 +53,39 @@ __global__ void split_pack_kernel(const float *__restrict__ b, int64_t ldb, int 
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = trans ? b[(int64_t)(k8 * 8 + j) * ldb + n] : b[(int64_t)n * ldb + k8 * 8 + j];
-        uint4 h, l;
-        split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y); split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
-        uint8_t *slot = img + ((((int64_t)p * S + s) * n_nc + nc) * 2) * kStage + (size_t)pl * rows * 16 + (size_t)r * 16;
-        *reinterpret_cast<uint4 *>(slot) = h;
-        *reinterpret_cast<uint4 *>(slot + kStage) = l;
+        uint8_t *slot = img + ((((int64_t)p * S + s) * n_nc + nc) * PARTS) * kStage + (size_t)pl * rows * 16 + (size_t)r * 16;
+        uint4 h, m, l;
+        if (PARTS == 2) {
+            split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y); split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
+            *reinterpret_cast<uint4 *>(slot) = h;
+            *reinterpret_cast<uint4 *>(slot + kStage) = l;
+        } else {
+            split3(v[0], v[1], h.x, m.x, l.x); split3(v[2], v[3], h.y, m.y, l.y); split3(v[4], v[5], h.z, m.z, l.z); split3(v[6], v[7], h.w, m.w, l.w);
+            *reinterpret_cast<uint4 *>(slot) = h;
+            *reinterpret_cast<uint4 *>(slot + kStage) = m;
+            *reinterpret_cast<uint4 *>(slot + 2 * kStage) = l;
+        }
     }
 }
+
+// One K = 64 block of D (+)= A . W^T with operands in PARTS bf16 parts (planes of A part q at a_hi + q * 16 KB):
+// weight slot j (part j of W) multiplies the A parts 0 .. PARTS-1-j, so every product of combined order < PARTS is taken.
+#define GEMM_MMA_BLOCK(PARTS_, r, d_tmem, a_hi, w_rows, idesc, first, code)                                          \
+    {                                                                                                                \
+        _Pragma("unroll")                                                                                            \
+        for (int j_ = 0; j_ < (PARTS_); ++j_) {                                                                      \
+            SPLIT_RING_NEXT(r, code)                                                                                 \
+            _Pragma("unroll")                                                                                        \
+            for (int k_ = 0; k_ < 4; ++k_) {                                                                         \
+                const uint64_t db_ = make_desc(wst_ + k_ * 2 * (w_rows) * 16, (w_rows));                             \
+                _Pragma("unroll")                                                                                    \
+                for (int q_ = 0; q_ < (PARTS_) - j_; ++q_)                                                           \
+                    mma_bf16((d_tmem), make_desc((a_hi) + q_ * kPartBytes + k_ * 2 * kPlane, 128), db_, (idesc),     \
+                             ((first) && j_ == 0 && k_ == 0 && q_ == 0) ? 0u : 1u);                                  \
+            }                                                                                                        \
+            SPLIT_RING_RELEASE(r)                                                                                    \
+        }                                                                                                            \
+    }
 
 // ------------------------------------------------------------------------------------------------ NT kernel
 struct GemmNtParams {
@@ -67,22 +97,26 @@ struct GemmNtParams {
     TcStatus wd;
 };
 
+template <int PARTS>
 struct GemmNtSmem {
-    uint8_t slab[kGemmSlabs][kSlabBytes];
-    uint8_t ring[kGemmStages][kStage];
-    uint64_t w_full[kGemmStages], w_empty[kGemmStages];
-    uint64_t a_full[kGemmSlabs], a_empty[kGemmSlabs];
+    static constexpr int kSlabs = NtCfg<PARTS>::kSlabs, kStages = NtCfg<PARTS>::kStages, kSlabBytes = PARTS * kPartBytes;
+    uint8_t slab[kSlabs][kSlabBytes];
+    uint8_t ring[kStages][kStage];
+    uint64_t w_full[kStages], w_empty[kStages];
+    uint64_t a_full[kSlabs], a_empty[kSlabs];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
-static_assert(sizeof(GemmNtSmem) + 128 <= 232448, "GemmNtSmem exceeds the 227 KB opt-in limit");
+static_assert(sizeof(GemmNtSmem<2>) + 128 <= 232448 && sizeof(GemmNtSmem<3>) + 128 <= 232448, "GemmNtSmem exceeds the 227 KB opt-in limit");
 
+template <int PARTS>
 __global__ void __launch_bounds__(kThreads, 1)
 split_gemm_nt_kernel(const GemmNtParams p)
 {
+    constexpr int kGemmSlabs = GemmNtSmem<PARTS>::kSlabs, kGemmStages = GemmNtSmem<PARTS>::kStages, kSlabBytes = GemmNtSmem<PARTS>::kSlabBytes;
     const TcStatus wd = p.wd;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    GemmNtSmem &s = *reinterpret_cast<GemmNtSmem *>(smem_raw);
+    GemmNtSmem<PARTS> &s = *reinterpret_cast<GemmNtSmem<PARTS> *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         constexpr int kW = kEpiThreads / 32;
@@ -107,8 +141,8 @@ split_gemm_nt_kernel(const GemmNtParams p)
             const uint32_t bytes = (uint32_t)p.rows * 128u;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int pass = item % p.n_pass;
-                const uint8_t *src = p.wimg + (size_t)pass * S * n_nc * 2 * kStage;
-                for (int blk = 0; blk < S * n_nc * 2; ++blk) {
+                const uint8_t *src = p.wimg + (size_t)pass * S * n_nc * PARTS * kStage;
+                for (int blk = 0; blk < S * n_nc * PARTS; ++blk) {
                     SPLIT_STRESS(wd, 0x71);
                     if (!mbar_wait(&s.w_empty[stage], phase ^ 1, 0x7100 + stage, wd)) goto done;
                     mbar_arrive_expect_tx(&s.w_full[stage], bytes);
@@ -137,7 +171,7 @@ split_gemm_nt_kernel(const GemmNtParams p)
                     tc_fence_after();
                     const uint32_t a_hi = slab0 + (uint32_t)ab * kSlabBytes;
                     for (int nc = 0; nc < n_nc; ++nc)
-                        SPLIT_MMA_BLOCK(ring, tmem + buf * 256 + nc * 128, a_hi, 16384u, kPlane, 128, p.rows, idesc, sl == 0, 0x7400)
+                        GEMM_MMA_BLOCK(PARTS, ring, tmem + buf * 256 + nc * 128, a_hi, p.rows, idesc, sl == 0, 0x7400)
                     mma_commit(&s.a_empty[ab]);
                     if (++ab == kGemmSlabs) { ab = 0; a_phase ^= 1; }
                 }
@@ -199,11 +233,19 @@ split_gemm_nt_kernel(const GemmNtParams p)
                 uint8_t *dst = s.slab[ab] + (size_t)(half * 4) * kPlane + (size_t)row * 16;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    uint4 h, l;
-                    split2(x[2 * j].x, x[2 * j].y, h.x, l.x); split2(x[2 * j].z, x[2 * j].w, h.y, l.y);
-                    split2(x[2 * j + 1].x, x[2 * j + 1].y, h.z, l.z); split2(x[2 * j + 1].z, x[2 * j + 1].w, h.w, l.w);
-                    *reinterpret_cast<uint4 *>(dst + (size_t)j * kPlane) = h;
-                    *reinterpret_cast<uint4 *>(dst + 16384 + (size_t)j * kPlane) = l;
+                    uint4 h, m, l;
+                    if (PARTS == 2) {
+                        split2(x[2 * j].x, x[2 * j].y, h.x, l.x); split2(x[2 * j].z, x[2 * j].w, h.y, l.y);
+                        split2(x[2 * j + 1].x, x[2 * j + 1].y, h.z, l.z); split2(x[2 * j + 1].z, x[2 * j + 1].w, h.w, l.w);
+                        *reinterpret_cast<uint4 *>(dst + (size_t)j * kPlane) = h;
+                        *reinterpret_cast<uint4 *>(dst + kPartBytes + (size_t)j * kPlane) = l;
+                    } else {
+                        split3(x[2 * j].x, x[2 * j].y, h.x, m.x, l.x); split3(x[2 * j].z, x[2 * j].w, h.y, m.y, l.y);
+                        split3(x[2 * j + 1].x, x[2 * j + 1].y, h.z, m.z, l.z); split3(x[2 * j + 1].z, x[2 * j + 1].w, h.w, m.w, l.w);
+                        *reinterpret_cast<uint4 *>(dst + (size_t)j * kPlane) = h;
+                        *reinterpret_cast<uint4 *>(dst + kPartBytes + (size_t)j * kPlane) = m;
+                        *reinterpret_cast<uint4 *>(dst + 2 * kPartBytes + (size_t)j * kPlane) = l;
+                    }
                 }
                 fence_proxy_async_smem();
                 GM_ARRIVE(&s.a_full[ab]);
@@ -227,8 +269,11 @@ done:
 // smem slab of 64 m: [m / 8][channel / 8][m % 8][channel % 8] bf16, i.e. 128-byte core matrices (8 channels contiguous,
 // 8 m at 16-byte steps), channel groups 128 B apart (SBO), m groups (channels / 8) * 128 B apart (LBO).
 constexpr int kTnStages = 2;
-constexpr int kTnA = 16384, kTnB = 32768;                  // one half (hi or lo) of an A / B slab
-constexpr int kTnStageBytes = 2 * kTnA + 2 * kTnB;         // A_hi | A_lo | B_hi | B_lo
+constexpr int kTnA = 16384;                                // one part of an A slab (64 m x 128 n bf16)
+constexpr int kTnStageBytes = 98304;                       // PARTS A parts | PARTS B parts: 2 x (16 + 32) KB or 3 x (16 + 16) KB
+template <int PARTS> struct TnCfg;
+template <> struct TnCfg<2> { static constexpr int kMaxKc = 256, kB = 32768; };
+template <> struct TnCfg<3> { static constexpr int kMaxKc = 128, kB = 16384; };
 
 struct GemmTnParams {
     const float *a; int64_t lda;          // (M, N)
@@ -253,7 +298,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) { return
 // 64 rows x (8 * groups) channels of fp32 -> hi / lo MN-major slab halves.  A warp instruction covers 8 rows x 4 channel
 // groups: a quarter-warp writes the 8 rows of one core matrix (128 contiguous bytes, conflict-free) and reads 32-byte
 // sectors of 8 consecutive rows.
-__device__ __forceinline__ void tn_stage_operand(uint8_t *hi, uint8_t *lo, const float *src, int64_t ld, int64_t m0, int64_t m_end,
+template <int PARTS>
+__device__ __forceinline__ void tn_stage_operand(uint8_t *part0, uint32_t part_stride, const float *src, int64_t ld, int64_t m0, int64_t m_end,
                                                  int c0, int c_end, int groups, int warp_e, int lane)
 {
     const int mr = lane & 7, gq = lane >> 3;
@@ -267,17 +313,26 @@ __device__ __forceinline__ void tn_stage_operand(uint8_t *hi, uint8_t *lo, const
             const float4 *q = reinterpret_cast<const float4 *>(src + m * ld + c);
             x0 = __ldg(q); x1 = __ldg(q + 1);
         }
-        uint4 h, l;
-        split2(x0.x, x0.y, h.x, l.x); split2(x0.z, x0.w, h.y, l.y); split2(x1.x, x1.y, h.z, l.z); split2(x1.z, x1.w, h.w, l.w);
         const uint32_t off = (uint32_t)m8 * lbo + (uint32_t)g * 128u + (uint32_t)mr * 16u;
-        *reinterpret_cast<uint4 *>(hi + off) = h;
-        *reinterpret_cast<uint4 *>(lo + off) = l;
+        uint4 h, md, l;
+        if (PARTS == 2) {
+            split2(x0.x, x0.y, h.x, l.x); split2(x0.z, x0.w, h.y, l.y); split2(x1.x, x1.y, h.z, l.z); split2(x1.z, x1.w, h.w, l.w);
+            *reinterpret_cast<uint4 *>(part0 + off) = h;
+            *reinterpret_cast<uint4 *>(part0 + part_stride + off) = l;
+        } else {
+            split3(x0.x, x0.y, h.x, md.x, l.x); split3(x0.z, x0.w, h.y, md.y, l.y); split3(x1.x, x1.y, h.z, md.z, l.z); split3(x1.z, x1.w, h.w, md.w, l.w);
+            *reinterpret_cast<uint4 *>(part0 + off) = h;
+            *reinterpret_cast<uint4 *>(part0 + part_stride + off) = md;
+            *reinterpret_cast<uint4 *>(part0 + 2 * part_stride + off) = l;
+        }
     }
 }
 
+template <int PARTS>
 __global__ void __launch_bounds__(kThreads, 1)
 split_gemm_tn_kernel(const GemmTnParams p)
 {
+    constexpr uint32_t kTnB = TnCfg<PARTS>::kB;
     const TcStatus wd = p.wd;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     GemmTnSmem &s = *reinterpret_cast<GemmTnSmem *>(smem_raw);
@@ -310,14 +365,17 @@ split_gemm_tn_kernel(const GemmTnParams p)
                 SPLIT_STRESS(wd, 0x75);
                 if (!mbar_wait(&s.full[st], phase, 0x7500 + st, wd)) goto done;
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(s.stage[st]), a_lo = a_hi + kTnA, b_hi = a_hi + 2 * kTnA, b_lo = b_hi + kTnB;
+                const uint32_t a0 = smem_u32(s.stage[st]), b0 = a0 + PARTS * kTnA;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t dah = make_desc_lbo(a_hi + ks * 2 * lbo_a, lbo_a), dal = make_desc_lbo(a_lo + ks * 2 * lbo_a, lbo_a);
-                    const uint64_t dbh = make_desc_lbo(b_hi + ks * 2 * lbo_b, lbo_b), dbl = make_desc_lbo(b_lo + ks * 2 * lbo_b, lbo_b);
-                    mma_bf16(tmem, dah, dbh, idesc, (sl == 0 && ks == 0) ? 0u : 1u);
-                    mma_bf16(tmem, dal, dbh, idesc, 1u);
-                    mma_bf16(tmem, dah, dbl, idesc, 1u);
+                    // B part j multiplies the A parts 0 .. PARTS-1-j: every product of combined order < PARTS
+#pragma unroll
+                    for (int j = 0; j < PARTS; ++j) {
+                        const uint64_t db = make_desc_lbo(b0 + j * kTnB + ks * 2 * lbo_b, lbo_b);
+#pragma unroll
+                        for (int q = 0; q < PARTS - j; ++q)
+                            mma_bf16(tmem, make_desc_lbo(a0 + q * kTnA + ks * 2 * lbo_a, lbo_a), db, idesc, (sl == 0 && ks == 0 && j == 0 && q == 0) ? 0u : 1u);
+                    }
                 }
                 mma_commit(&s.empty[st]);
                 if (++st == kTnStages) { st = 0; phase ^= 1; }
@@ -333,8 +391,8 @@ split_gemm_tn_kernel(const GemmTnParams p)
             if (!mbar_wait(&s.empty[st], phase ^ 1, 0x6500 + st, wd)) goto done;
             uint8_t *base = s.stage[st];
             const int64_t m0 = r0 + (int64_t)sl * 64;
-            tn_stage_operand(base, base + kTnA, p.a, p.lda, m0, r1, n0, p.N, 16, warp_e, lane);
-            tn_stage_operand(base + 2 * kTnA, base + 2 * kTnA + kTnB, p.b, p.ldb, m0, r1, k0, p.K, gb, warp_e, lane);
+            tn_stage_operand<PARTS>(base, kTnA, p.a, p.lda, m0, r1, n0, p.N, 16, warp_e, lane);
+            tn_stage_operand<PARTS>(base + PARTS * kTnA, kTnB, p.b, p.ldb, m0, r1, k0, p.K, gb, warp_e, lane);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.full[st]);
@@ -389,47 +447,55 @@ __global__ void split_gemm_tn_reduce_kernel(const float *__restrict__ part, int 
 
 using namespace al3d;
 
-extern "C" int64_t al3d_gemm_bf16x3_ws_bytes(int N, int K)
+extern "C" int64_t al3d_gemm_split_ws_bytes(int N, int K, int parts)
 {
-    // packed weight image: N/rows x K/64 blocks x (hi, lo) slots of 16 KB
+    // packed weight image: N/rows x K/64 blocks x `parts` slots of 16 KB
     const int rows = N < 128 ? N : 128;
-    return (int64_t)(N / rows) * (K / 64) * 2 * al3d::split::kStage;
+    return (int64_t)(N / rows) * (K / 64) * parts * al3d::split::kStage;
 }
 
-extern "C" int al3d_gemm_bf16x3_nt(const float *a, int64_t lda, int M, int K, const float *b, int64_t ldb, int b_transposed,
-                                   const float *bias, const float *rowbias, int rows_per_group, int N, int accumulate,
-                                   float *c, int64_t ldc, void *ws, void *stream)
+template <int PARTS>
+static int launch_nt(const al3d::split::GemmNtParams &p, const float *b, int64_t ldb, int b_transposed, void *ws, cudaStream_t st)
 {
     using namespace al3d::split;
-    AL3D_CHECK_ARG(a && b && c && ws, "al3d_gemm_bf16x3_nt: null pointer");
-    AL3D_CHECK_ARG(M >= 1 && K >= 64 && K % 64 == 0, "al3d_gemm_bf16x3_nt: M=%d K=%d (K must be a multiple of 64)", M, K);
-    AL3D_CHECK_ARG(N == 64 || N == 128 || (N % 256 == 0 && N <= 4096), "al3d_gemm_bf16x3_nt: N=%d must be 64, 128 or a multiple of 256", N);
-    AL3D_CHECK_ARG(lda % 4 == 0 && ldc % 4 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)c & 15) == 0, "al3d_gemm_bf16x3_nt: A / C rows must be 16-byte aligned");
-    AL3D_CHECK_ARG(!rowbias || rows_per_group >= 1, "al3d_gemm_bf16x3_nt: rowbias needs rows_per_group");
-    AL3D_CHECK_ARG(!(bias && rowbias), "al3d_gemm_bf16x3_nt: bias and rowbias are exclusive");
+    {
+        const int64_t total = (int64_t)p.N * (p.K / 8);
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, 4096);
+        split_pack_kernel<PARTS><<<blocks, 256, 0, st>>>(b, ldb, b_transposed ? 1 : 0, p.N, p.K, p.np, p.rows, (uint8_t *)ws);
+        AL3D_CHECK_LAUNCH("split_pack_kernel");
+    }
+    const int grid = std::min(p.n_mtiles * p.n_pass, tc_num_sms());
+    const size_t smem = sizeof(GemmNtSmem<PARTS>) + 128;
+    AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_gemm_nt_kernel<PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    split_gemm_nt_kernel<PARTS><<<grid, kThreads, smem, st>>>(p);
+    AL3D_CHECK_LAUNCH("split_gemm_nt_kernel");
+    return 0;
+}
+
+extern "C" int al3d_gemm_split_nt(const float *a, int64_t lda, int M, int K, const float *b, int64_t ldb, int b_transposed,
+                                  const float *bias, const float *rowbias, int rows_per_group, int N, int accumulate,
+                                  float *c, int64_t ldc, int parts, void *ws, void *stream)
+{
+    using namespace al3d::split;
+    AL3D_CHECK_ARG(a && b && c && ws, "al3d_gemm_split_nt: null pointer");
+    AL3D_CHECK_ARG(parts == 2 || parts == 3, "al3d_gemm_split_nt: parts=%d must be 2 (bf16x3) or 3 (bf16x6)", parts);
+    AL3D_CHECK_ARG(M >= 1 && K >= 64 && K % 64 == 0, "al3d_gemm_split_nt: M=%d K=%d (K must be a multiple of 64)", M, K);
+    AL3D_CHECK_ARG(N == 64 || N == 128 || (N % 256 == 0 && N <= 4096), "al3d_gemm_split_nt: N=%d must be 64, 128 or a multiple of 256", N);
+    AL3D_CHECK_ARG(lda % 4 == 0 && ldc % 4 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)c & 15) == 0, "al3d_gemm_split_nt: A / C rows must be 16-byte aligned");
+    AL3D_CHECK_ARG(!rowbias || rows_per_group >= 1, "al3d_gemm_split_nt: rowbias needs rows_per_group");
+    AL3D_CHECK_ARG(!(bias && rowbias), "al3d_gemm_split_nt: bias and rowbias are exclusive");
     GemmNtParams p;
     p.a = a; p.lda = lda; p.M = M; p.K = K; p.wimg = (const uint8_t *)ws;
     p.bias = bias; p.rowbias = rowbias; p.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
     p.c = c; p.ldc = ldc; p.N = N; p.accumulate = accumulate ? 1 : 0;
     p.np = std::min(N, 256); p.rows = std::min(N, 128); p.n_pass = N / p.np; p.n_mtiles = (M + kTile - 1) / kTile;
     if (tc_launch_status(&p.wd)) return 1;
-    {
-        const int64_t total = (int64_t)N * (K / 8);
-        const int blocks = (int)std::min<int64_t>((total + 255) / 256, 4096);
-        split_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b, ldb, b_transposed ? 1 : 0, N, K, p.np, p.rows, (uint8_t *)ws);
-        AL3D_CHECK_LAUNCH("split_pack_kernel");
-    }
-    const int grid = std::min(p.n_mtiles * p.n_pass, tc_num_sms());
-    const size_t smem = sizeof(GemmNtSmem) + 128;
-    AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    split_gemm_nt_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
-    AL3D_CHECK_LAUNCH("split_gemm_nt_kernel");
-    return 0;
+    return parts == 2 ? launch_nt<2>(p, b, ldb, b_transposed, ws, (cudaStream_t)stream) : launch_nt<3>(p, b, ldb, b_transposed, ws, (cudaStream_t)stream);
 }
 
-static void tn_plan(int64_t M, int N, int K, int sms, int &kc, int &n_ntiles, int &n_ktiles, int &splits, int64_t &rows_per_split)
+static void tn_plan(int64_t M, int N, int K, int parts, int sms, int &kc, int &n_ntiles, int &n_ktiles, int &splits, int64_t &rows_per_split)
 {
-    kc = std::min(K, 256);
+    kc = std::min(K, parts == 2 ? 256 : 128);
     n_ntiles = (N + 127) / 128; n_ktiles = K / kc;
     const int tiles = n_ntiles * n_ktiles;
     const int64_t slabs = (M + 63) / 64;
@@ -439,29 +505,36 @@ static void tn_plan(int64_t M, int N, int K, int sms, int &kc, int &n_ntiles, in
     splits = (int)((M + rows_per_split - 1) / rows_per_split);
 }
 
-extern "C" int64_t al3d_gemm_bf16x3_tn_ws_bytes(int64_t M, int N, int K)
+extern "C" int64_t al3d_gemm_split_tn_ws_bytes(int64_t M, int N, int K, int parts)
 {
     int kc, nn, nk, splits; int64_t rps;
-    tn_plan(M, N, K, tc_num_sms(), kc, nn, nk, splits, rps);
+    tn_plan(M, N, K, parts, tc_num_sms(), kc, nn, nk, splits, rps);
     return (int64_t)splits * N * K * 4;
 }
 
-extern "C" int al3d_gemm_bf16x3_tn(const float *a, int64_t lda, const float *b, int64_t ldb, int64_t M, int N, int K,
-                                   void *ws, float *c, int64_t ldc, int accumulate, void *stream)
+extern "C" int al3d_gemm_split_tn(const float *a, int64_t lda, const float *b, int64_t ldb, int64_t M, int N, int K, int parts,
+                                  void *ws, float *c, int64_t ldc, int accumulate, void *stream)
 {
     using namespace al3d::split;
-    AL3D_CHECK_ARG(a && b && c && ws, "al3d_gemm_bf16x3_tn: null pointer");
-    AL3D_CHECK_ARG(M >= 1 && N >= 8 && N % 8 == 0 && K >= 64 && (K <= 256 ? K % 32 == 0 : K % 256 == 0),
-                   "al3d_gemm_bf16x3_tn: M=%lld N=%d K=%d (N %% 8, K 64..256 in steps of 32 or a multiple of 256)", (long long)M, N, K);
-    AL3D_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0, "al3d_gemm_bf16x3_tn: operand rows must be 16-byte aligned");
+    AL3D_CHECK_ARG(a && b && c && ws, "al3d_gemm_split_tn: null pointer");
+    AL3D_CHECK_ARG(parts == 2 || parts == 3, "al3d_gemm_split_tn: parts=%d must be 2 (bf16x3) or 3 (bf16x6)", parts);
+    const int max_kc = parts == 2 ? 256 : 128;
+    AL3D_CHECK_ARG(M >= 1 && N >= 8 && N % 8 == 0 && K >= 64 && (K <= max_kc ? K % 32 == 0 : K % max_kc == 0),
+                   "al3d_gemm_split_tn: M=%lld N=%d K=%d (N %% 8; K 64..%d in steps of 32 or a multiple of %d)", (long long)M, N, K, max_kc, max_kc);
+    AL3D_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0, "al3d_gemm_split_tn: operand rows must be 16-byte aligned");
     GemmTnParams p;
     p.a = a; p.lda = lda; p.b = b; p.ldb = ldb; p.M = M; p.N = N; p.K = K; p.part = (float *)ws;
-    tn_plan(M, N, K, tc_num_sms(), p.kc, p.n_ntiles, p.n_ktiles, p.splits, p.rows_per_split);
+    tn_plan(M, N, K, parts, tc_num_sms(), p.kc, p.n_ntiles, p.n_ktiles, p.splits, p.rows_per_split);
     if (tc_launch_status(&p.wd)) return 1;
     const int grid = p.n_ntiles * p.n_ktiles * p.splits;
     const size_t smem = sizeof(GemmTnSmem) + 128;
-    AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    split_gemm_tn_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    if (parts == 2) {
+        AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_gemm_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        split_gemm_tn_kernel<2><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_gemm_tn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        split_gemm_tn_kernel<3><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    }
     AL3D_CHECK_LAUNCH("split_gemm_tn_kernel");
     const int64_t NK = (int64_t)N * K;
     split_gemm_tn_reduce_kernel<<<(unsigned)std::min<int64_t>((NK + 255) / 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(

@@ -42,6 +42,16 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
 }
 
+// Three-way split: x = hi + mid + lo, 24 significant bits (all of an fp32 mantissa).
+__device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t &mid, uint32_t &lo)
+{
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(rb), "f"(ra));
+    const float sa = ra - __uint_as_float(mid << 16), sb = rb - __uint_as_float(mid & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(sb), "f"(sa));
+}
+
 // 32 accumulator columns (channels c .. c+31 of this thread's row) -> + bias, ReLU, hi / lo split -> four 16-byte
 // plane rows in each half of the operand buffer.  dst: address of (plane c/8, row) in the hi half.
 __device__ __forceinline__ void store_split32(uint8_t *dst, uint32_t lo_off, uint32_t plane_stride, const uint32_t (&v)[32],

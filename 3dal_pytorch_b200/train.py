@@ -98,8 +98,8 @@ def wgrad(dy, x, dw, accumulate=False):
     M, N = dy.shape
     K = x.shape[1]
     assert dw.shape == (N, K) and dw.stride(1) == 1 and dy.stride(1) == 1 and x.stride(1) == 1
-    if wgrad_x3_fits(M, N, K) and dy.stride(0) % 4 == 0 and x.stride(0) % 4 == 0:
-        return wgrad_x3(dy, x, dw, accumulate=accumulate)
+    if wgrad_split_fits(M, N, K) and dy.stride(0) % 4 == 0 and x.stride(0) % 4 == 0:
+        return wgrad_split(dy, x, dw, accumulate=accumulate)
     ws = _ws(_lib.lib().al3d_wgrad_ws_floats(M, N, K), dy.device)
     _lib.check(_lib.lib().al3d_wgrad_f32(_p(dy), dy.stride(0), _p(x), x.stride(0), M, N, K, _p(ws), _p(dw), dw.stride(0),
                                          int(accumulate), ops._stream()), "wgrad_f32")
@@ -107,23 +107,29 @@ def wgrad(dy, x, dw, accumulate=False):
 
 def dgrad(dy, w, out=None, accumulate=False):
     """dx (M,K) = dy (M,N) . w (N,K): the NT GEMM on the transposed weight."""
-    if gemm_x3_fits(dy.shape[0], w.shape[1], w.shape[0]) and dy.stride(0) % 4 == 0:
-        return linear_x3(dy, w, out=out, accumulate=accumulate, transposed=True)
+    if gemm_split_fits(dy.shape[0], w.shape[1], w.shape[0]) and dy.stride(0) % 4 == 0:
+        return linear_split(dy, w, out=out, accumulate=accumulate, transposed=True)
     wt = w.t().contiguous()
     return ops.linear(dy, wt, None, act=ops.ACT_NONE, out=out, accumulate=accumulate)
 
 
 # ---- split-precision tensor-core GEMMs (csrc/gemm_split.cu) for the layers that are big enough to feed them
-# Off by default: the fp32 SIMT GEMMs reproduce the reference's gradients at the fp32 oracle's own noise level; the
-# split-precision tensor-core GEMMs make the step 1.75x faster with logits within 3e-4 and gradients within 1e-3..3e-2
-# of float64 (tests/test_gpu_train.py, TOL).  AL3D_TRAIN_GEMM=x3 or set_gemm_mode("x3") selects them.
-GEMM_X3 = os.environ.get("AL3D_TRAIN_GEMM", "f32") == "x3"
+# GEMM_MODE: "x6" (default) = bf16 hi + mid + lo, six MMAs per product: fp32-grade (~1e-7 relative), gradients at the fp32
+#                             oracle's own noise level;
+#            "x3"           = bf16 hi + lo, three MMAs: ~1e-5 relative; train-mode BatchNorm amplifies that where
+#                             |mean| >> std (logits 3e-4, gradients 1e-3..3e-2 of float64) -- faster, opt-in;
+#            "f32"          = every GEMM on the fp32 SIMT kernels.
+# AL3D_TRAIN_GEMM or set_gemm_mode() selects; tests/test_gpu_train.py runs every training test in all three.
+GEMM_MODE = os.environ.get("AL3D_TRAIN_GEMM", "x6")
+_PARTS = {"x3": 2, "x6": 3}
 
 
 def set_gemm_mode(mode):
-    global GEMM_X3
-    assert mode in ("f32", "x3"), mode
-    GEMM_X3 = mode == "x3"
+    global GEMM_MODE
+    assert mode in ("f32", "x3", "x6"), mode
+    GEMM_MODE = mode
+
+
 _gemm_ws_cache = {}
 
 
@@ -135,14 +141,15 @@ def _gemm_ws(nbytes, dev):
     return t
 
 
-def gemm_x3_fits(M, N, K):
-    return GEMM_X3 and M >= 1024 and K >= 64 and K % 64 == 0 and (N in (64, 128) or (N % 256 == 0 and N <= 4096))
+def gemm_split_fits(M, N, K):
+    return GEMM_MODE in _PARTS and M >= 1024 and K >= 64 and K % 64 == 0 and (N in (64, 128) or (N % 256 == 0 and N <= 4096))
 
 
-def linear_x3(a, w, bias=None, rowbias=None, rows_per_group=0, out=None, accumulate=False, transposed=False, K=None):
+def linear_split(a, w, bias=None, rowbias=None, rows_per_group=0, out=None, accumulate=False, transposed=False, K=None, parts=None):
     """(M,N) (+)= a[:, :K] . B^T (+ bias | per-group row bias) on the tensor cores in split precision.
     w is B (N, K) -- or, with transposed=True, the (K, N) matrix whose transpose is B (dgrad takes the weight as it is)."""
     ops._need_cuda(a, w, bias, rowbias)
+    parts = parts or _PARTS[GEMM_MODE]
     M = a.shape[0]
     if transposed:
         Kk, N = w.shape
@@ -152,25 +159,29 @@ def linear_x3(a, w, bias=None, rowbias=None, rows_per_group=0, out=None, accumul
     assert K == Kk and a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] >= K
     y = out if out is not None else torch.empty((M, N), device=a.device, dtype=torch.float32)
     assert y.shape == (M, N) and y.stride(1) == 1
-    ws = _gemm_ws(_lib.lib().al3d_gemm_bf16x3_ws_bytes(N, K), a.device)
-    _lib.check(_lib.lib().al3d_gemm_bf16x3_nt(_p(a), a.stride(0), M, K, _p(w), w.stride(0), int(transposed), _p(bias), _p(rowbias),
-                                              int(rows_per_group), N, int(accumulate), _p(y), y.stride(0), _p(ws), ops._stream()),
-               "gemm_bf16x3_nt")
+    ws = _gemm_ws(_lib.lib().al3d_gemm_split_ws_bytes(N, K, parts), a.device)
+    _lib.check(_lib.lib().al3d_gemm_split_nt(_p(a), a.stride(0), M, K, _p(w), w.stride(0), int(transposed), _p(bias), _p(rowbias),
+                                             int(rows_per_group), N, int(accumulate), _p(y), y.stride(0), parts, _p(ws), ops._stream()),
+               "gemm_split_nt")
     return y
 
 
-def wgrad_x3_fits(M, N, K):
-    return GEMM_X3 and M >= 1024 and N % 8 == 0 and N >= 64 and K >= 64 and (K % 32 == 0 if K <= 256 else K % 256 == 0)
+def wgrad_split_fits(M, N, K):
+    if GEMM_MODE not in _PARTS:
+        return False
+    kc = 256 if GEMM_MODE == "x3" else 128
+    return M >= 1024 and N % 8 == 0 and N >= 64 and K >= 64 and (K % 32 == 0 if K <= kc else K % kc == 0)
 
 
-def wgrad_x3(dy, x, dw, accumulate=False):
+def wgrad_split(dy, x, dw, accumulate=False, parts=None):
     """dw (N,K) view with unit column stride (+)= dy^T x on the tensor cores in split precision; dy (M,N), x (M,>=K)."""
+    parts = parts or _PARTS[GEMM_MODE]
     M, N = dy.shape
     K = dw.shape[1]
     assert dw.shape == (N, K) and dw.stride(1) == 1 and dy.stride(1) == 1 and x.stride(1) == 1 and x.shape[1] >= K
-    ws = _gemm_ws(_lib.lib().al3d_gemm_bf16x3_tn_ws_bytes(M, N, K), dy.device)
-    _lib.check(_lib.lib().al3d_gemm_bf16x3_tn(_p(dy), dy.stride(0), _p(x), x.stride(0), M, N, K, _p(ws), _p(dw), dw.stride(0),
-                                              int(accumulate), ops._stream()), "gemm_bf16x3_tn")
+    ws = _gemm_ws(_lib.lib().al3d_gemm_split_tn_ws_bytes(M, N, K, parts), dy.device)
+    _lib.check(_lib.lib().al3d_gemm_split_tn(_p(dy), dy.stride(0), _p(x), x.stride(0), M, N, K, parts, _p(ws), _p(dw), dw.stride(0),
+                                             int(accumulate), ops._stream()), "gemm_split_tn")
 
 
 def _w2(layer):
@@ -258,8 +269,8 @@ def _layer_fwd(x, lin, bn, tape, key, rowbias=None, rows_per_group=0, K=None, dr
     """Linear (+ per-group bias) -> BatchNorm(batch stats) -> ReLU (-> Dropout multiplier).  bn None: plain linear."""
     W = _w2(lin)
     Wk = W if K is None else W[:, :K]
-    if gemm_x3_fits(x.shape[0], Wk.shape[0], Wk.shape[1]) and x.stride(0) % 4 == 0:
-        y = linear_x3(x, Wk, lin.bias if rowbias is None else None, rowbias=rowbias, rows_per_group=rows_per_group, K=Wk.shape[1])
+    if gemm_split_fits(x.shape[0], Wk.shape[0], Wk.shape[1]) and x.stride(0) % 4 == 0:
+        y = linear_split(x, Wk, lin.bias if rowbias is None else None, rowbias=rowbias, rows_per_group=rows_per_group, K=Wk.shape[1])
     else:
         y = ops.linear(x, Wk, lin.bias if rowbias is None else None, rowbias=rowbias, rows_per_group=rows_per_group,
                        act=ops.ACT_NONE, K=Wk.shape[1])

@@ -293,7 +293,7 @@ def bench_dynamic(dev, precision):
 
 def bench_train_step(dev, rank, world, dist, steps=5):
     """configs[4]: static one-box training step (train-mode BN, dropout, fused loss, backward, ONE flat-bucket all-reduce,
-    fused Adam), 64 tracks x 4096 points per GPU, in both GEMM modes (3dal_pytorch_b200/train.py)."""
+    fused Adam), 64 tracks x 4096 points per GPU, in the three GEMM modes (3dal_pytorch_b200/train.py)."""
     synth = importlib.import_module("3dal_pytorch_b200.synth")
     sm = importlib.import_module("3dal_pytorch_b200.static_model")
     tr = importlib.import_module("3dal_pytorch_b200.train")
@@ -305,9 +305,9 @@ def bench_train_step(dev, rank, world, dist, steps=5):
               torch.randint(0, 12, (bs,), device=dev, generator=g), torch.randn((bs,), device=dev, generator=g) * 0.1,
               torch.randint(0, 3, (bs,), device=dev, generator=g), torch.randn((bs, 3), device=dev, generator=g) * 0.2)
     out = {"workload": "static one-box training step, %d tracks x %d points per GPU, %d GPU(s) (BASELINE.json configs[4])" % (bs, n, world)}
-    old = tr.GEMM_X3
+    old = tr.GEMM_MODE
     try:
-        for mode in ("f32", "x3"):
+        for mode in ("x6", "x3", "f32"):
             tr.set_gemm_mode(mode)
             model = sm.StaticModelOneBoxEst().to(dev).train()
             model.load_state_dict(synth.random_state_dict("static_one", seed=synth.REFERENCE_SEED))
@@ -320,11 +320,12 @@ def bench_train_step(dev, rank, world, dist, steps=5):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms = float(t.item())
             out[mode] = {"ms_per_step": ms, "objects_per_s": world * bs / (ms * 1e-3),
-                         "gemm": "fp32 SIMT (gradients at the fp32 oracle's noise level; the default)" if mode == "f32"
-                         else "bf16x3 tensor cores (opt-in; see tests/test_gpu_train.py TOL)"}
+                         "gemm": {"x6": "bf16x6 tensor cores (three-way split operands, fp32-grade; the default)",
+                                  "x3": "bf16x3 tensor cores (two-way split; opt-in, see tests/test_gpu_train.py TOL)",
+                                  "f32": "fp32 SIMT"}[mode]}
             del step, model
     finally:
-        tr.GEMM_X3 = old
+        tr.set_gemm_mode(old)
     torch.cuda.empty_cache()
     return out
 

@@ -289,24 +289,25 @@ int al3d_group_max_backward(const float *dg, const int32_t *arg, int64_t G, int6
 /* Weight gradient dW (N, K; row stride lddw) (+)= dY^T . X with dY (M, N; ldy), X (M, K; ldx). */
 int al3d_wgrad_f32(const float *dy, int64_t ldy, const float *x, int64_t ldx, int64_t M, int N, int K, float *ws,
                    float *dw, int64_t lddw, int accumulate, void *stream);
-/* Split-precision ("bf16x3") tensor-core GEMM on fp32 operands: the layer GEMMs of the training step (the Conv1d(k=1) /
- * Linear forward and input gradient of tools/static_model.py:241-339 under .train() / .backward()).
+/* Split-precision tensor-core GEMMs on fp32 operands: the layer GEMMs of the training step (the Conv1d(k=1) / Linear
+ * forward and input gradient of tools/static_model.py:241-339 under .train() / .backward()).
  *   C (M, N; ldc) (+)= A (M, K; lda) . B^T (+ bias[N] | rowbias[row / rows_per_group][N])
  * B is (N, K; ldb), or with b_transposed != 0 the (K, N; ldb) matrix whose transpose is meant (dgrad: the weight itself).
- * K % 64 == 0; N is 64, 128 or a multiple of 256; A and C rows 16-byte aligned.  ws: al3d_gemm_bf16x3_ws_bytes(N, K)
- * bytes of device scratch (the packed hi / lo weight image).  Every product is a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with
- * bf16 parts and fp32 accumulation: ~1e-5 relative to an fp32 GEMM. */
-int64_t al3d_gemm_bf16x3_ws_bytes(int N, int K);
-int al3d_gemm_bf16x3_nt(const float *a, int64_t lda, int M, int K, const float *b, int64_t ldb, int b_transposed,
-                        const float *bias, const float *rowbias, int rows_per_group, int N, int accumulate,
-                        float *c, int64_t ldc, void *ws, void *stream);
+ * K % 64 == 0; N is 64, 128 or a multiple of 256; A and C rows 16-byte aligned.  ws: al3d_gemm_split_ws_bytes(N, K, parts)
+ * bytes of device scratch (the packed weight image).  parts = 2 ("bf16x3"): every fp32 value is hi + lo in bf16 and a
+ * product is a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, ~1e-5 relative to an fp32 GEMM; parts = 3 ("bf16x6"): hi + mid + lo (all
+ * 24 mantissa bits) and the six products of combined order <= 2, ~1e-7 relative (fp32-grade).  fp32 accumulation. */
+int64_t al3d_gemm_split_ws_bytes(int N, int K, int parts);
+int al3d_gemm_split_nt(const float *a, int64_t lda, int M, int K, const float *b, int64_t ldb, int b_transposed,
+                       const float *bias, const float *rowbias, int rows_per_group, int N, int accumulate,
+                       float *c, int64_t ldc, int parts, void *ws, void *stream);
 /* The weight gradient on the tensor cores: C (N, K; ldc) (+)= A^T . B with A (M, N; lda) = dY and B (M, K; ldb) = the layer
- * input, reduced over the M rows in split precision (both operands staged MN-major, no transposition); per-CTA partial
- * tiles are summed in a fixed order (deterministic).  N % 8 == 0; K in 64..256 (steps of 32) or a multiple of 256;
- * ws: al3d_gemm_bf16x3_tn_ws_bytes(M, N, K) bytes of device scratch. */
-int64_t al3d_gemm_bf16x3_tn_ws_bytes(int64_t M, int N, int K);
-int al3d_gemm_bf16x3_tn(const float *a, int64_t lda, const float *b, int64_t ldb, int64_t M, int N, int K,
-                        void *ws, float *c, int64_t ldc, int accumulate, void *stream);
+ * input, reduced over the M rows (both operands staged MN-major, no transposition); per-CTA partial tiles are summed in a
+ * fixed order (deterministic).  N % 8 == 0; K in 64..Kc (steps of 32) or a multiple of Kc, Kc = 256 (parts 2) / 128
+ * (parts 3); ws: al3d_gemm_split_tn_ws_bytes(M, N, K, parts) bytes of device scratch. */
+int64_t al3d_gemm_split_tn_ws_bytes(int64_t M, int N, int K, int parts);
+int al3d_gemm_split_tn(const float *a, int64_t lda, const float *b, int64_t ldb, int64_t M, int N, int K, int parts,
+                       void *ws, float *c, int64_t ldc, int accumulate, void *stream);
 /* Gradient of sum_t w6[t] * term_t (terms of al3d_loss_forward, w6 six DEVICE floats) w.r.t. the logits -> dlogits
  * (M, 2) (skipped when logits == NULL) and w.r.t. the 39-wide head vector -> dbox (bs, 39) = [centre 3 | heading scores
  * 12 | normalised heading residuals 12 | size scores 3 | normalised size residuals 9] (tools/static_model.py:341-425). */

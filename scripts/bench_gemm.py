@@ -35,12 +35,15 @@ def main():
         dw = torch.empty((N, K), device=DEV)
         out = torch.empty((M, N), device=DEV)
         row = {"M": M, "N": N, "K": K, "gflop": 2.0 * M * N * K / 1e9}
-        row["nt_x3_ms"] = timed(lambda: tr.linear_x3(a, w, out=out))
+        row["nt_x3_ms"] = timed(lambda: tr.linear_split(a, w, out=out, parts=2))
+        row["nt_x6_ms"] = timed(lambda: tr.linear_split(a, w, out=out, parts=3))
         row["nt_f32_ms"] = timed(lambda: ops.linear(a, w, None, act=ops.ACT_NONE, out=out))
-        if hasattr(tr, "wgrad_x3"):
-            row["tn_x3_ms"] = timed(lambda: tr.wgrad_x3(dy, a, dw))
+        row["tn_x3_ms"] = timed(lambda: tr.wgrad_split(dy, a, dw, parts=2))
+        row["tn_x6_ms"] = timed(lambda: tr.wgrad_split(dy, a, dw, parts=3))
+        tr.set_gemm_mode("f32")
         row["tn_f32_ms"] = timed(lambda: tr.wgrad(dy, a, dw))
         row["nt_x3_tflops"] = row["gflop"] / row["nt_x3_ms"]
+        row["nt_x6_tflops"] = row["gflop"] / row["nt_x6_ms"]
         print(json.dumps(row))
 
 

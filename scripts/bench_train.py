@@ -28,8 +28,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--points", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--gemm", default="f32", choices=["f32", "x3"],
-                    help="layer GEMMs: fp32 SIMT kernels (parity-grade default) or split-precision tensor-core kernels")
+    ap.add_argument("--gemm", default="x6", choices=["x6", "x3", "f32"],
+                    help="layer GEMMs: bf16x6 tensor-core kernels (fp32-grade, default), bf16x3 tensor-core kernels, fp32 SIMT kernels")
     args = ap.parse_args()
     ge.build()
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
@@ -86,7 +86,8 @@ def main():
         line = {"bench": "train_step", "model": "static_one", "n_gpus": world, "batch_per_gpu": bs, "points": n,
                 "ms_per_step": ms, "objects_per_s": world * bs / (ms * 1e-3), "model_tflops_per_gpu": bs * flop / (ms * 1e-3) / 1e12,
                 "grad_bucket_floats": int(step.grads.flat.numel()), "allreduce_ms": ar_ms,
-                "loss_first_last": [float(losses[0]), float(losses[-1])], "dtype": "f32 (SIMT GEMMs)" if args.gemm == "f32" else "bf16x3 tensor-core GEMMs (fp32 in / out, fp32 accumulate)", "gemm": args.gemm,
+                "loss_first_last": [float(losses[0]), float(losses[-1])], "dtype": {"f32": "f32 (SIMT GEMMs)", "x3": "bf16x3 tensor-core GEMMs (fp32 in / out, fp32 accumulate)",
+                          "x6": "bf16x6 tensor-core GEMMs (fp32 in / out, fp32 accumulate)"}[args.gemm], "gemm": args.gemm,
                 "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
         if world == 1 and not args.no_cpu:
             from oracle import train as otrain

@@ -53,24 +53,26 @@ def _drop(bs, n, seed=3):
     return (torch.rand((bs, 128, n), generator=g) >= 0.5).float() * 2.0
 
 
-# GEMM arithmetic of the training step: "f32" = every GEMM on the fp32 SIMT kernels (the default: gradients at the fp32
-# oracle's own noise level), "x3" = the split-precision tensor-core GEMMs (csrc/gemm_split.cu; opt-in, 1.75x faster step).
+# GEMM arithmetic of the training step (train.GEMM_MODE): "x6" = tensor-core GEMMs with three-way split operands (the
+# default: fp32-grade, same bounds as "f32"), "f32" = every GEMM on the fp32 SIMT kernels, "x3" = tensor-core GEMMs with
+# two-way split operands (csrc/gemm_split.cu; opt-in, fastest).
 # Train-mode BatchNorm subtracts the batch mean, so where |mean| >> std the ~1e-5 relative error of a bf16x3 product is
 # amplified by mean/std: measured on the B200 the logits agree to 3e-4 of max|logit| (fp32 mode 3e-5), the losses to
 # 1e-4, and the gradients to 2-3e-2 in the worst tensor / 1-5e-3 in the median (fp32 mode 4e-3 / 1e-3; the dynamic net has
 # one BatchNorm-bias gradient at 0.19 where the fp32 torch oracle itself is 1.5e-2 away from float64).  Far tighter than
 # bf16 autocast training, but not the reference's arithmetic -- hence opt-in.  Bounds for x3: worst tensor < 0.3 and within
 # 15x the fp32 oracle's worst (+1e-2); median < 1e-2.
-TOL = {"f32": {"logits": 1e-4, "loss": 1e-4, "stats_rtol": 1e-4, "grad_max": 1e-2, "grad_med": 2.5e-3, "grad_slack": 5e-4, "grad_mult": 3},
+_TIGHT = {"logits": 1e-4, "loss": 1e-4, "stats_rtol": 1e-4, "grad_max": 1e-2, "grad_med": 2.5e-3, "grad_slack": 5e-4, "grad_mult": 3}
+TOL = {"x6": _TIGHT, "f32": {"logits": 1e-4, "loss": 1e-4, "stats_rtol": 1e-4, "grad_max": 1e-2, "grad_med": 2.5e-3, "grad_slack": 5e-4, "grad_mult": 3},
        "x3": {"logits": 1e-3, "loss": 1e-3, "stats_rtol": 1e-3, "grad_max": 0.3, "grad_med": 1e-2, "grad_slack": 1e-2, "grad_mult": 15}}
 
 
-@pytest.fixture(params=["x3", "f32"])
+@pytest.fixture(params=["x6", "x3", "f32"])
 def gemm_mode(request):
-    old = tr.GEMM_X3
-    tr.GEMM_X3 = request.param == "x3"
+    old = tr.GEMM_MODE
+    tr.set_gemm_mode(request.param)
     yield request.param
-    tr.GEMM_X3 = old
+    tr.set_gemm_mode(old)
 
 
 def _check_grads(named_params, grads_of, grads32, grads64, tol=None):
@@ -88,7 +90,8 @@ def _check_grads(named_params, grads_of, grads32, grads64, tol=None):
         names.append(name)
     worst = int(np.argmax(errs))
     assert max(errs) < tol["grad_mult"] * max(floors) + tol["grad_slack"], (names[worst], errs[worst], max(floors))
-    assert max(errs) < tol["grad_max"] and float(np.median(errs)) < tol["grad_med"], (max(errs), float(np.median(errs)), float(np.median(floors)))
+    # (absolute cap, unless the fp32 oracle's own worst tensor is already beyond it: the dynamic net's is 1.5e-2)
+    assert max(errs) < max(tol["grad_max"], 1.5 * max(floors)) and float(np.median(errs)) < tol["grad_med"], (max(errs), float(np.median(errs)), float(np.median(floors)))
     return {"worst": (names[worst], errs[worst]), "median": float(np.median(errs)), "oracle_fp32_worst": max(floors),
             "oracle_fp32_median": float(np.median(floors))}
 
@@ -183,7 +186,7 @@ def test_fused_training_step_matches_oracle(dropout, gemm_mode):
     flips = out["mask"].cpu() != oout["mask"]
     margin = (ologits[..., 1] - ologits[..., 0]).abs()
     assert int(flips.sum()) == 0 or float(margin[flips].max()) < 2 * tol["logits"] * float(ologits.abs().max())
-    if gemm_mode == "f32":
+    if gemm_mode != "x3":
         assert int(flips.sum()) == 0
     for k in ("total_loss", "mask_loss", "center_loss", "heading_class_loss", "size_class_loss",
               "heading_residuals_normalized_loss", "size_residuals_normalized_loss"):
@@ -256,7 +259,8 @@ def test_three_fused_steps_track_torch_adam_on_the_oracle(gemm_mode):
             P[k] = v
     # Adam's first steps are ~ lr * sign(g): components whose sign is rounding noise move differently on the two sides, so
     # the trajectories agree to a few percent, not to rounding
-    # (x3: the noisier gradients flip more of those signs -- the third loss is within 25 %)
+    # (tensor-core modes: a different summation order flips a different set of those signs -- measured: second loss within
+    # 6 %, third within 17 % -- so the bound there is 25 %)
     assert abs(gl[0] - ol[0]) <= TOL[gemm_mode]["loss"] * ol[0] and np.allclose(gl, ol, rtol=6e-2 if gemm_mode == "f32" else 0.25), (gl, ol)
     assert gl[-1] < gl[0]                                 # and it learns
 
@@ -282,53 +286,59 @@ def test_loss_modules_backward_through_autograd():
 # ------------------------------------------------------------------------------------------------ tensor-core GEMMs
 @pytest.mark.parametrize("M,N,K", [(4096, 64, 64), (5000, 128, 64), (2048, 256, 128), (3000, 512, 256), (1024, 1024, 128),
                                    (1500, 128, 1024), (148 * 128 * 2 + 77, 256, 512)])
-def test_gemm_x3_nt_matches_fp64(M, N, K):
-    """C = A . B^T (+ bias) in split precision against torch float64: ~1e-5 of max|C| (bf16x3, fp32 accumulation)."""
+@pytest.mark.parametrize("parts,tol", [(2, 3e-5), (3, 8e-6)])
+def test_gemm_split_nt_matches_fp64(M, N, K, parts, tol):
+    """C = A . B^T (+ bias) in split precision against torch float64: ~1e-5 of max|C| with bf16x3 (parts 2); with bf16x6
+    (parts 3) the level of an fp32 GEMM -- measured 6e-7 (K = 64) .. 5e-6 (K = 1024), the rounding of the fp32 accumulation
+    of K/16 x 6 partial products, not of the operands."""
     g = torch.Generator().manual_seed(M + N + K)
     a = torch.randn((M, K + 8), generator=g).to(DEV)[:, :K]          # row stride > K
     w = (torch.randn((N, K), generator=g) / K ** 0.5).to(DEV)
     bias = torch.randn((N,), generator=g).to(DEV)
     ref = (a.double() @ w.double().t() + bias.double())
-    got = tr.linear_x3(a, w, bias)
+    got = tr.linear_split(a, w, bias, parts=parts)
     torch.cuda.synchronize()
     err = float((got.double() - ref).abs().max() / ref.abs().max())
-    assert err < 3e-5, err
+    assert err < tol, err
     # dgrad form: the same product from the transposed weight, accumulated onto an existing tensor
     wt = w.t().contiguous()
     base = torch.randn((M, N), generator=g).to(DEV)
     out = base.clone()
-    tr.linear_x3(a, wt, out=out, accumulate=True, transposed=True)
+    tr.linear_split(a, wt, out=out, accumulate=True, transposed=True, parts=parts)
     ref2 = base.double() + a.double() @ w.double().t()
     err2 = float((out.double() - ref2).abs().max() / ref2.abs().max())
-    assert err2 < 3e-5, err2
+    assert err2 < tol, err2
 
 
-def test_gemm_x3_nt_rowbias_per_group():
+@pytest.mark.parametrize("parts,tol", [(2, 3e-5), (3, 8e-6)])
+def test_gemm_split_nt_rowbias_per_group(parts, tol):
     M, N, K, rpg = 4096, 512, 64, 512
     g = torch.Generator().manual_seed(9)
     a = torch.randn((M, K), generator=g).to(DEV)
     w = (torch.randn((N, K), generator=g) / 8).to(DEV)
     rb = torch.randn((M // rpg, N), generator=g).to(DEV)
-    got = tr.linear_x3(a, w, rowbias=rb, rows_per_group=rpg)
+    got = tr.linear_split(a, w, rowbias=rb, rows_per_group=rpg, parts=parts)
     ref = a.double() @ w.double().t() + rb.double().repeat_interleave(rpg, 0)
-    assert float((got.double() - ref).abs().max() / ref.abs().max()) < 3e-5
+    assert float((got.double() - ref).abs().max() / ref.abs().max()) < tol
 
 
 @pytest.mark.parametrize("M,N,K", [(4096, 64, 64), (5000, 128, 64), (2048, 128, 256), (3001, 256, 512), (4096, 1024, 128),
                                    (1500, 128, 1024), (64 * 4096, 512, 64)])
-def test_gemm_x3_tn_wgrad_matches_fp64(M, N, K):
+@pytest.mark.parametrize("parts,tol", [(2, 3e-5), (3, 8e-6)])
+def test_gemm_split_tn_wgrad_matches_fp64(M, N, K, parts, tol):
     """dW = dY^T X (reduction over the rows) in split precision against torch float64."""
     g = torch.Generator().manual_seed(M + 3 * N + K)
     dy = torch.randn((M, N), generator=g).to(DEV)
     x = torch.randn((M, K + 4), generator=g).to(DEV)[:, :K]
     dw = torch.full((N, K), 7.0, device=DEV)
-    tr.wgrad_x3(dy, x, dw)
+    tr.wgrad_split(dy, x, dw, parts=parts)
     torch.cuda.synchronize()
     ref = dy.double().t() @ x.double()
     err = float((dw.double() - ref).abs().max() / ref.abs().max())
-    assert err < 3e-5, err
+    tol = tol * max(1.0, (M / 4096) ** 0.5) if parts == 3 else tol       # fp32 accumulation over the M rows (bf16x6 shows it)
+    assert err < tol, err
     again = torch.empty_like(dw)
-    tr.wgrad_x3(dy, x, again)
+    tr.wgrad_split(dy, x, again, parts=parts)
     assert torch.equal(again, dw)                                  # fixed reduction order: bit-reproducible
-    tr.wgrad_x3(dy, x, dw, accumulate=True)
-    assert float((dw.double() - 2 * ref).abs().max() / ref.abs().max()) < 6e-5
+    tr.wgrad_split(dy, x, dw, accumulate=True, parts=parts)
+    assert float((dw.double() - 2 * ref).abs().max() / ref.abs().max()) < 2 * tol
