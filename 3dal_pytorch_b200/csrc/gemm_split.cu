@@ -295,36 +295,46 @@ static_assert(sizeof(GemmTnSmem) + 128 <= 232448, "GemmTnSmem exceeds the 227 KB
 
 __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) { return make_idesc_bf16(M, N) | (1u << 15) | (1u << 16); }
 
-// 64 rows x (8 * groups) channels of fp32 -> hi / lo MN-major slab halves.  A warp instruction covers 8 rows x 4 channel
-// groups: a quarter-warp writes the 8 rows of one core matrix (128 contiguous bytes, conflict-free) and reads 32-byte
-// sectors of 8 consecutive rows.
-template <int PARTS>
-__device__ __forceinline__ void tn_stage_operand(uint8_t *part0, uint32_t part_stride, const float *src, int64_t ld, int64_t m0, int64_t m_end,
-                                                 int c0, int c_end, int groups, int warp_e, int lane)
+// 64 rows x (8 * groups) channels of fp32 -> MN-major slab parts.  A warp task covers 8 rows x 4 channel groups: a
+// quarter-warp writes the 8 rows of one core matrix (128 contiguous bytes, conflict-free) and reads 32-byte sectors of 8
+// consecutive rows.  A thread owns tasks i = 0 .. groups/4 - 1 (warp task w = warp_e + 8 i) and keeps their fp32 values
+// in registers: tn_load issues the 32-byte loads of one task, tn_store converts and writes it -- the kernel reloads a
+// task for the NEXT slab right after storing it, so the global loads are in flight under the conversion of the other
+// tasks, the mbarrier wait and the MMAs (the first cut loaded and converted task by task: ~11 k cycles per slab, all
+// of it exposed load latency, against 1.5 k cycles of MMAs).  Measured with the MMAs / the staging switched off in turn
+// (256 x 512, M = 262 144): MMAs alone 0.13 ms (parts 2) / 0.22 ms (parts 3), staging alone 0.75 / 0.88 ms -- the kernel is
+// bound by re-reading and re-converting the operands (every dY chunk once per K tile, every X chunk once per N tile).
+struct TnTask { float4 x0, x1; };
+
+__device__ __forceinline__ void tn_load(TnTask &t, int i, const float *src, int64_t ld, int64_t m0, int64_t m_end, int c0, int c_end,
+                                        int warp_e, int lane)
 {
-    const int mr = lane & 7, gq = lane >> 3;
-    const uint32_t lbo = (uint32_t)groups * 128u;
-    for (int w = warp_e; w < 8 * (groups / 4); w += kEpiThreads / 32) {
-        const int m8 = w & 7, g = (w >> 3) * 4 + gq;
-        const int64_t m = m0 + m8 * 8 + mr;
-        const int c = c0 + g * 8;
-        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-        if (m < m_end && c < c_end) {
-            const float4 *q = reinterpret_cast<const float4 *>(src + m * ld + c);
-            x0 = __ldg(q); x1 = __ldg(q + 1);
-        }
-        const uint32_t off = (uint32_t)m8 * lbo + (uint32_t)g * 128u + (uint32_t)mr * 16u;
-        uint4 h, md, l;
-        if (PARTS == 2) {
-            split2(x0.x, x0.y, h.x, l.x); split2(x0.z, x0.w, h.y, l.y); split2(x1.x, x1.y, h.z, l.z); split2(x1.z, x1.w, h.w, l.w);
-            *reinterpret_cast<uint4 *>(part0 + off) = h;
-            *reinterpret_cast<uint4 *>(part0 + part_stride + off) = l;
-        } else {
-            split3(x0.x, x0.y, h.x, md.x, l.x); split3(x0.z, x0.w, h.y, md.y, l.y); split3(x1.x, x1.y, h.z, md.z, l.z); split3(x1.z, x1.w, h.w, md.w, l.w);
-            *reinterpret_cast<uint4 *>(part0 + off) = h;
-            *reinterpret_cast<uint4 *>(part0 + part_stride + off) = md;
-            *reinterpret_cast<uint4 *>(part0 + 2 * part_stride + off) = l;
-        }
+    const int w = warp_e + i * (kEpiThreads / 32);
+    const int64_t m = m0 + (w & 7) * 8 + (lane & 7);
+    const int c = c0 + ((w >> 3) * 4 + (lane >> 3)) * 8;
+    t.x0 = make_float4(0.f, 0.f, 0.f, 0.f); t.x1 = t.x0;
+    if (m < m_end && c < c_end) {
+        const float4 *q = reinterpret_cast<const float4 *>(src + m * ld + c);
+        t.x0 = __ldg(q); t.x1 = __ldg(q + 1);
+    }
+}
+
+template <int PARTS>
+__device__ __forceinline__ void tn_store(const TnTask &t, int i, uint8_t *part0, uint32_t part_stride, int groups, int warp_e, int lane)
+{
+    const int w = warp_e + i * (kEpiThreads / 32);
+    const uint32_t off = (uint32_t)(w & 7) * ((uint32_t)groups * 128u) + (uint32_t)((w >> 3) * 4 + (lane >> 3)) * 128u + (uint32_t)(lane & 7) * 16u;
+    uint4 h, md, l;
+    if (PARTS == 2) {
+        split2(t.x0.x, t.x0.y, h.x, l.x); split2(t.x0.z, t.x0.w, h.y, l.y); split2(t.x1.x, t.x1.y, h.z, l.z); split2(t.x1.z, t.x1.w, h.w, l.w);
+        *reinterpret_cast<uint4 *>(part0 + off) = h;
+        *reinterpret_cast<uint4 *>(part0 + part_stride + off) = l;
+    } else {
+        split3(t.x0.x, t.x0.y, h.x, md.x, l.x); split3(t.x0.z, t.x0.w, h.y, md.y, l.y);
+        split3(t.x1.x, t.x1.y, h.z, md.z, l.z); split3(t.x1.z, t.x1.w, h.w, md.w, l.w);
+        *reinterpret_cast<uint4 *>(part0 + off) = h;
+        *reinterpret_cast<uint4 *>(part0 + part_stride + off) = md;
+        *reinterpret_cast<uint4 *>(part0 + 2 * part_stride + off) = l;
     }
 }
 
@@ -385,14 +395,34 @@ split_gemm_tn_kernel(const GemmTnParams p)
     } else if (warp >= 2) {
         // ------------------------------------------------------------ stagers + epilogue (256 threads)
         const int warp_e = warp - 2;
+        constexpr int kNiB = TnCfg<PARTS>::kMaxKc / 32;           // tasks per thread: A 4 (16 channel groups), B kc / 32
+        const int ni_b = gb / 4;
+        TnTask ta[4], tb[kNiB];
+        if (n_slabs > 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tn_load(ta[i], i, p.a, p.lda, r0, r1, n0, p.N, warp_e, lane);
+#pragma unroll
+            for (int i = 0; i < kNiB; ++i) if (i < ni_b) tn_load(tb[i], i, p.b, p.ldb, r0, r1, k0, p.K, warp_e, lane);
+        }
         int st = 0; uint32_t phase = 0;
         for (int sl = 0; sl < n_slabs; ++sl) {
             SPLIT_STRESS_WARP(wd, 0x65);
             if (!mbar_wait(&s.empty[st], phase ^ 1, 0x6500 + st, wd)) goto done;
             uint8_t *base = s.stage[st];
-            const int64_t m0 = r0 + (int64_t)sl * 64;
-            tn_stage_operand<PARTS>(base, kTnA, p.a, p.lda, m0, r1, n0, p.N, 16, warp_e, lane);
-            tn_stage_operand<PARTS>(base + PARTS * kTnA, kTnB, p.b, p.ldb, m0, r1, k0, p.K, gb, warp_e, lane);
+            const int64_t m_next = r0 + (int64_t)(sl + 1) * 64;
+            const bool more = sl + 1 < n_slabs;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                tn_store<PARTS>(ta[i], i, base, kTnA, 16, warp_e, lane);
+                if (more) tn_load(ta[i], i, p.a, p.lda, m_next, r1, n0, p.N, warp_e, lane);
+            }
+#pragma unroll
+            for (int i = 0; i < kNiB; ++i) {
+                if (i < ni_b) {
+                    tn_store<PARTS>(tb[i], i, base + PARTS * kTnA, kTnB, gb, warp_e, lane);
+                    if (more) tn_load(tb[i], i, p.b, p.ldb, m_next, r1, k0, p.K, warp_e, lane);
+                }
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.full[st]);

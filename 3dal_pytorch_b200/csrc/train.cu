@@ -81,16 +81,29 @@ col_reduce_kernel(const float *__restrict__ x, int64_t ldx, const float *__restr
     }
 }
 
+// Sum of one channel's slab partials by a warp: lane l adds slabs l, l + 32, ... in order, then a fixed shuffle tree --
+// the same association for a given n_slabs on every run (fp64 accumulation).
+__device__ __forceinline__ double warp_slab_sum(const float *__restrict__ part, int n_slabs, int64_t stride, int lane)
+{
+    double s = 0.0;
+    for (int i = lane; i < n_slabs; i += 32) s += (double)part[(int64_t)i * stride];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
 // BatchNorm statistics from the slab partials: mean, rstd = 1/sqrt(biased var + eps), running-stat update
 // (running = (1 - momentum) * running + momentum * batch, with the UNBIASED variance, nn.BatchNorm1d semantics).
+// One warp per channel.
 __global__ void bn_finalize_kernel(const float *__restrict__ part, int n_slabs, int C, int64_t M, const float *__restrict__ shift_row,
                                    float eps, float momentum, float *__restrict__ mean, float *__restrict__ rstd,
                                    float *__restrict__ running_mean, float *__restrict__ running_var)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
-    double s = 0.0, ss = 0.0;                                  // sums of (x - shift) and (x - shift)^2
-    for (int i = 0; i < n_slabs; ++i) { s += part[((int64_t)i * 2 + 0) * C + c]; ss += part[((int64_t)i * 2 + 1) * C + c]; }
+    const double s = warp_slab_sum(part + c, n_slabs, 2 * (int64_t)C, lane);            // sums of (x - shift) and (x - shift)^2
+    const double ss = warp_slab_sum(part + C + c, n_slabs, 2 * (int64_t)C, lane);
+    if (lane != 0) return;
     const double d = s / (double)M;
     const double mu = (double)shift_row[c] + d;
     double var = ss / (double)M - d * d;
@@ -104,17 +117,16 @@ __global__ void bn_finalize_kernel(const float *__restrict__ part, int n_slabs, 
     }
 }
 
-// sums of slab partials -> out[c] (fp64 accumulation, fixed order); n_vec = 1 or 2 interleaved vectors per slab
+// sums of slab partials -> out[c] (fp64 accumulation, fixed order); n_vec = 1 or 2 interleaved vectors per slab.
+// One warp per channel.
 __global__ void slab_sum_kernel(const float *__restrict__ part, int n_slabs, int n_vec, int C, float *__restrict__ out0,
                                 float *__restrict__ out1)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
-    double s0 = 0.0, s1 = 0.0;
-    for (int i = 0; i < n_slabs; ++i) {
-        s0 += part[((int64_t)i * n_vec + 0) * C + c];
-        if (n_vec == 2) s1 += part[((int64_t)i * n_vec + 1) * C + c];
-    }
+    const double s0 = warp_slab_sum(part + c, n_slabs, (int64_t)n_vec * C, lane);
+    const double s1 = n_vec == 2 ? warp_slab_sum(part + C + c, n_slabs, (int64_t)n_vec * C, lane) : 0.0;
+    if (lane != 0) return;
     if (out0) out0[c] = (float)s0;
     if (n_vec == 2 && out1) out1[c] = (float)s1;
 }
@@ -578,7 +590,7 @@ extern "C" int al3d_bn_train_forward(const float *y, int64_t M, int C, const flo
         col_reduce_kernel<0><<<dim3((unsigned)ceil_div(C, kColTile), slabs), kColTile * kColWarps, 0, st>>>(y, C, nullptr, 0, M, C, rps, none, ws);
         AL3D_CHECK_LAUNCH("col_reduce_kernel<0>");
     }
-    bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(ws, slabs, C, M, y, eps, momentum, mean, rstd, running_mean, running_var);
+    bn_finalize_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>(ws, slabs, C, M, y, eps, momentum, mean, rstd, running_mean, running_var);
     AL3D_CHECK_LAUNCH("bn_finalize_kernel");
     BnCtx ctx = make_ctx(mean, rstd, gamma, beta, drop, drop_sg, drop_sc, drop_sr, rows_per_group, relu, M);
     if (tcv && (v4_mask() & 2)) {
@@ -614,7 +626,7 @@ extern "C" int al3d_bn_train_backward(const float *dz, const float *y, int64_t M
         AL3D_CHECK_LAUNCH("col_reduce_kernel<1>");
     }
     // dbeta = sum g, dgamma = sum g * xhat
-    slab_sum_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(ws, slabs, 2, C, dbeta, dgamma);
+    slab_sum_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>(ws, slabs, 2, C, dbeta, dgamma);
     AL3D_CHECK_LAUNCH("slab_sum_kernel");
     if (tcv && (v4_mask() & 8)) {
         bn_apply_v4_kernel<true><<<v4_apply_grid(M, C), 256, 0, st>>>(dz, y, M, C, ctx, dbeta, dgamma, dy);
@@ -660,7 +672,7 @@ extern "C" int al3d_group_colsum(const float *x, int64_t M, int C, int64_t rows_
         col_reduce_kernel<2><<<dim3((unsigned)ceil_div(C, kColTile), slabs), kColTile * kColWarps, 0, st>>>(x, C, nullptr, 0, M, C, rps, none, ws);
         AL3D_CHECK_LAUNCH("col_reduce_kernel<2>");
     }
-    slab_sum_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(ws, slabs, 1, C, out, nullptr);
+    slab_sum_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>(ws, slabs, 1, C, out, nullptr);
     AL3D_CHECK_LAUNCH("slab_sum_kernel");
     return 0;
 }
