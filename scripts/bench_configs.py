@@ -23,6 +23,7 @@ crop = importlib.import_module("3dal_pytorch_b200.crop")
 sm = importlib.import_module("3dal_pytorch_b200.static_model")
 dm = importlib.import_module("3dal_pytorch_b200.dynamic_model")
 spec = importlib.import_module("3dal_pytorch_b200.spec")
+graphs = importlib.import_module("3dal_pytorch_b200.graphs")
 PEAKS = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
 DEV = "cuda:0"
@@ -120,8 +121,12 @@ def bench_dynamic():
             m.precision = prec
             ms = timed(lambda: m(pts, box, None), iters=5)
             fl = spec.flops_per_object("dynamic", 5120)
-            print(json.dumps({"bench": "dynamic", "tracks": bs, "precision": prec, "ms": ms, "objects_per_s": bs / (ms * 1e-3),
-                              "model_tflops": bs * fl / (ms * 1e-3) / 1e12}))
+            row = {"bench": "dynamic", "tracks": bs, "precision": prec, "ms": ms, "objects_per_s": bs / (ms * 1e-3),
+                   "model_tflops": bs * fl / (ms * 1e-3) / 1e12}
+            if prec == "bf16x3" and bs == 64:
+                g = graphs.GraphedForward(m, pts, box, None)
+                row["ms_cuda_graph"] = timed(lambda: g(pts, box, None), iters=10)
+            print(json.dumps(row))
 
 
 def bench_static32():
@@ -133,8 +138,11 @@ def bench_static32():
         for prec in ("bf16x3", "bf16", "fp32"):
             m.precision = prec
             ms = timed(lambda: m(pts, ib, gt), iters=10)
-            print(json.dumps({"bench": "static32", "model": kind, "tracks": 32, "precision": prec, "ms": ms,
-                              "objects_per_s": 32 / (ms * 1e-3)}))
+            row = {"bench": "static32", "model": kind, "tracks": 32, "precision": prec, "ms": ms, "objects_per_s": 32 / (ms * 1e-3)}
+            if prec == "bf16x3":
+                g = graphs.GraphedForward(m, pts, ib, gt)
+                row["ms_cuda_graph"] = timed(lambda: g(pts, ib, gt), iters=10)
+            print(json.dumps(row))
 
 
 if __name__ == "__main__":
