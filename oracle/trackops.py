@@ -4,6 +4,13 @@
   motion_features  tools/motionState.py:36-49 (np.array of a list of (1,7) boxes is (L,1,7); [0, :3] keeps all 7 columns)
   labels           tools/static_model.py:549-566 + tools/utils.py:53-67
   transform_box / write-back   tools/static_eval.py:30-45, 84-92
+  iou3d            det3d/ops/iou3d_nms/iou3d_nms_utils.py:35-72 (rotated BEV overlap x height overlap / union volume)
+
+Pinning: iou3d is checked against the REAL reference's CPU rotated BEV IoU (det3d/ops/iou3d_nms/src/iou3d_cpu.cpp:232,
+compiled from its source by oracle/build_ref.py into oracle/_ref) -- live where that module is built, and through the
+golden file tests/golden/iou_bev_ref.npz everywhere (tests/test_oracle_iou_ref.py): < 6e-7 on all but the near-degenerate
+pairs, where the reference's float32 corner test carries a 1e-2 margin (worst 2.7e-4).  The other functions are pinned by
+the fixtures generated from the reference's Python (tests/golden/make_golden.py).
 """
 import numpy as np
 
