@@ -480,6 +480,32 @@ class TrainStep:
         return out
 
 
+class AutogradTrainStep:
+    """The same step for ANY of the three models, through their own ``forward`` in ``.train()`` mode -- the reference's
+    loop (tools/static_train.py:65-90, tools/dynamic_train.py:37-133): ``out = model(*inputs)``,
+    ``criterion(out, *labels)['total_loss'].backward()`` -- where the backward of the models' autograd Functions writes every
+    parameter gradient into the model's flat bucket; then ONE all-reduce of that bucket and the fused Adam step
+    (``p.grad`` is not used)."""
+
+    def __init__(self, model, criterion, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, group=None):
+        self.model, self.crit, self.group = model.train(), criterion, group
+        self.grads = GradBucket(model)
+        self.opt = FusedAdam(model, self.grads, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        # the optimiser re-homed the parameters in one flat buffer: make the Functions' backward write into THIS bucket
+        model._bucket, model._bucket_key = self.grads, tuple(p.data_ptr() for p in model.parameters())
+
+    def step(self, inputs, labels):
+        self.grads.zero_()
+        out = self.model(*inputs)
+        ls = self.crit(out, *labels)
+        ls["total_loss"].backward()
+        for p in self.model.parameters():
+            p.grad = None                                  # copies of the bucket's views handed to autograd: not needed
+        scale = allreduce_gradients(self.grads, self.group)
+        self.opt.step(grad_scale=scale)
+        return ls
+
+
 # ------------------------------------------------------------------------------------------------ autograd wrappers
 class _SegFn(torch.autograd.Function):
     """logits = ins_seg(pts) in training mode; backward fills a temporary bucket and returns its views."""
