@@ -167,7 +167,14 @@ def seg_forward(pack, fw, pts):
     """-> logits (bs,n,2) f32, mask (bs,n) bool."""
     bs, C, n = pts.shape
     g = chain_maxpool(pack.pass1, pts)
-    gbias = ops.linear(g, pack.w_glob, pack.b_d1, act=ops.ACT_NONE, K=1024)
+    # the 1024-wide half of dconv1 on the per-object global feature: a (bs x 1024) . (1024 x 512) GEMM.  From 1024 objects on
+    # it runs on the tensor cores in three-way split precision (fp32-grade, csrc/gemm_split.cu; 0.36 -> 0.07 ms at 8192
+    # objects), below that on the fp32 kernel.
+    if bs >= 1024:
+        from . import train
+        gbias = train.linear_split(g, pack.w_glob, pack.b_d1, parts=3)
+    else:
+        gbias = ops.linear(g, pack.w_glob, pack.b_d1, act=ops.ACT_NONE, K=1024)
     logits = torch.empty((bs, n, 2), device=pts.device, dtype=torch.float32)
     mask = torch.empty((bs, n), device=pts.device, dtype=torch.bool)
     sb, sc, sp = pts.stride()
