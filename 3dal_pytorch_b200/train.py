@@ -295,7 +295,12 @@ def _layer_bwd(dz, lin, bn, tape, key, grads, need_dx=True, K=None, dx_out=None,
     Kx = x.shape[1] if K is None else K
     wgrad(dy, x, gw if K is None else gw[:, :Kx])
     if bias_grad:
-        colsum(dy, grads.view(lin.bias))
+        if bn is not None:
+            # a bias in front of a BatchNorm: its gradient sum(dy) is exactly zero (the BatchNorm backward removes the batch
+            # mean of dy; the reference's autograd returns ~1e-10 rounding noise here) -- written as zero, not reduced
+            grads.view(lin.bias).zero_()
+        else:
+            colsum(dy, grads.view(lin.bias))
     dx = None
     if need_dx:
         dx = dgrad(dy, W if K is None else W[:, :Kx], out=dx_out, accumulate=dx_accumulate)
