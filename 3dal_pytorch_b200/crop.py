@@ -110,20 +110,23 @@ class CropPlan:
             self.d_sincos = torch.zeros((0, 2), device=dev, dtype=torch.float32)
         self.max_boxes = max(1, max(nb) if nb else 1)
         CH = lib.al3d_crop_chunk_points()
-        chunks, frame_chunk_off = [], [0]
-        for f in range(F):
-            for k, first in enumerate(range(0, n_pts[f], CH)):
-                chunks.append((f, first, min(CH, n_pts[f] - first), k))
-            frame_chunk_off.append(len(chunks))
-        self.n_chunks = len(chunks)
+        # chunk table (frame, first point, points, chunk index in frame), frame-major -- vectorised: a sweep has ~9000 chunks
+        n_arr = np.asarray(n_pts, dtype=np.int64).reshape(-1)
+        n_ch = (n_arr + CH - 1) // CH
+        frame_chunk_off = np.concatenate([[0], np.cumsum(n_ch)]).astype(np.int64)
+        self.n_chunks = int(frame_chunk_off[-1])
+        f_of = np.repeat(np.arange(F, dtype=np.int64), n_ch)
+        k_of = np.arange(self.n_chunks, dtype=np.int64) - frame_chunk_off[f_of]
+        first = k_of * CH
+        chunks = np.stack([f_of, first, np.minimum(CH, n_arr[f_of] - first), k_of], 1).astype(np.int32) if self.n_chunks else np.zeros((0, 4), np.int32)
         # hits per WARP segment (512 consecutive points) of a chunk; the synthetic Waymo-shaped frames average ~50
         self.hit_cap = int(hit_cap or 256)
         self.n_seg = 8                               # warps per chunk CTA (csrc/crop.cu kCropWarps)
         i32 = lambda *s: torch.empty(s, device=dev, dtype=torch.int32)
         self.d_pt_off = torch.from_numpy(pt_off).to(dev)
         self.d_box_off = torch.from_numpy(self.box_off).to(dev)
-        self.d_chunks = torch.tensor(chunks, dtype=torch.int32, device=dev).reshape(-1, 4)
-        self.d_fco = torch.tensor(frame_chunk_off, dtype=torch.int64, device=dev)
+        self.d_chunks = torch.from_numpy(np.ascontiguousarray(chunks)).to(dev)
+        self.d_fco = torch.from_numpy(frame_chunk_off).to(dev)
         self.meta = torch.empty((max(F, 1), 8), device=dev, dtype=torch.float32)
         self.occ = torch.zeros((max(F, 1), lib.al3d_crop_occ_words()), device=dev, dtype=torch.int32)
         self.cell_start = i32(max(F, 1), GRID * GRID + 1)

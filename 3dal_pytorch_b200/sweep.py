@@ -50,8 +50,10 @@ class StaticSweep:
         crop result, pts (T,npoints,3))."""
         dev = next(self.labeler.model.parameters()).device
         F = len(frames)
-        boxes_w = [crop.detector_to_waymo(f["det_boxes"]) for f in frames]
-        T = boxes_w[0].shape[0]
+        # one conversion for the whole sweep (every frame holds the same number of boxes: persistent tracking ids)
+        T = int(np.asarray(frames[0]["det_boxes"]).shape[0])
+        all_w = crop.detector_to_waymo(np.concatenate([np.asarray(f["det_boxes"]).reshape(-1, 7) for f in frames], 0)).reshape(F, -1, 7)
+        boxes_w = [all_w[f] for f in range(F)]
         plan = crop.CropPlan([f["points"] for f in frames], boxes_w, [f["pose"] for f in frames], device=dev)
         res = plan.run()
         seg_start, seg_len = track_segments(res["offsets"], res["box_off"], F, T)
@@ -64,7 +66,7 @@ class StaticSweep:
         poses = np.stack([np.asarray(f["pose"], dtype=np.float64) for f in frames])
         inv_pose = np.linalg.inv(poses[best])                                       # (T,4,4) global -> vehicle frame
         # the detector box of the best frame, in that frame's vehicle coordinates, is the initial box
-        init_box = np.stack([boxes_w[best[t]][t].astype(np.float64) for t in range(T)])
+        init_box = all_w[best, np.arange(T)].astype(np.float64)
         d_inv = torch.from_numpy(np.ascontiguousarray(inv_pose)).to(dev)
         d_init = torch.from_numpy(np.ascontiguousarray(init_box)).to(dev)
         pts = trackprep.prep_points(res["xyz_global"].contiguous(), rows.contiguous(), d_inv, d_init, heading_col=6, c_out=3)

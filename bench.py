@@ -220,7 +220,7 @@ def _config(args, world, t_local, **extra):
 
 
 # ------------------------------------------------------------------------------------------------ crop sub-metric
-def bench_crop(dev, peaks, n_frames=200):
+def bench_crop(dev, peaks, n_frames=200, model=None):
     """configs[3], crop stage: n_frames Waymo-shaped frames x ~180k points x 200 boxes -> achieved HBM GB/s on the
     algorithmic bytes of SURVEY.md 8d (12 B per point read, 96 B per box, 16 B per inside point written)."""
     synth = importlib.import_module("3dal_pytorch_b200.synth")
@@ -245,7 +245,26 @@ def bench_crop(dev, peaks, n_frames=200):
     ms = e0.elapsed_time(e1) / iters
     alg = plan.read_bytes + inside * 16
     gbs = alg / (ms * 1e-3) / 1e9
-    return {"workload": "%d frames x %d points x %d boxes/frame (BASELINE.json configs[3], crop stage)" % (
+    sweep_res = None
+    if model is not None:
+        # configs[3] end to end on the same frames: crop -> regroup by track -> merge / resample / canonicalise -> segmentation
+        # -> gather -> box head -> decoded boxes; wall clock of run() including its host-side plan construction
+        sweep = importlib.import_module("3dal_pytorch_b200.sweep")
+        for f, p_ in zip(frames, pts):
+            f["points"] = p_
+        sw = sweep.StaticSweep(model)
+        for _ in range(2):
+            out = sw.run(frames)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            out = sw.run(frames)
+        torch.cuda.synchronize()
+        sms = 1e3 * (time.perf_counter() - t0) / 5
+        sweep_res = {"workload": "%d frames: crop -> track regroup -> prep -> seg -> gather -> box head -> boxes (BASELINE.json configs[3])" % n_frames,
+                     "ms_wall": sms, "frames_per_s": n_frames / (sms * 1e-3), "tracks": int(out["boxes"].shape[0]),
+                     "boxes_cropped_per_s": n_frames * int(frames[0]["det_boxes"].shape[0]) / (sms * 1e-3), "crop_share": ms / sms}
+    return {"sweep": sweep_res, "workload": "%d frames x %d points x %d boxes/frame (BASELINE.json configs[3], crop stage)" % (
                 n_frames, int(frames[0]["points"].shape[0]), int(frames[0]["det_boxes"].shape[0])),
             "ms_per_sweep": ms, "frames_per_s": n_frames / (ms * 1e-3), "points_inside": inside, "algorithmic_bytes": alg,
             "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"],
@@ -580,7 +599,7 @@ def main():
                        "mask_flips": int((got["mask"].cpu() != ref_out["mask"]).sum()), "mask_points": int(rl.shape[0] * rl.shape[1])}}
         crop_res = None
         if world == 1 and not args.no_crop:
-            crop_res = bench_crop(dev, peaks)
+            crop_res = bench_crop(dev, peaks, model=model)
         flop_obj = spec.flops_per_object("static_one", N_POINTS)
         line = {
             "metric": "auto-labeled objects/sec", "value": value, "unit": "objects/s", "n_gpus": world,
@@ -593,6 +612,7 @@ def main():
             "model_tflops": value * flop_obj / 1e12 / world, "flop_per_object": flop_obj,
             "kernel_ms": kernel_ms, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fast_mode": fast, "crop": crop_res,
+            "sweep": crop_res.pop("sweep") if crop_res else None,
             "dynamic": dyn_res, "train_step": train_res,
         }
         _emit(line)
