@@ -108,6 +108,12 @@ class CropPlan:
             self.d_aabb = torch.zeros((0, 6), device=dev, dtype=torch.float32)
             self.d_boxes = torch.zeros((0, 7), device=dev, dtype=torch.float32)
             self.d_sincos = torch.zeros((0, 2), device=dev, dtype=torch.float32)
+        # the boxes in their own frames (conservative pair classification of the hits kernel)
+        self.d_local = torch.empty((max(TB, 1), 12), device=dev, dtype=torch.float32)
+        if TB:
+            with torch.cuda.device(dev):
+                _lib.check(lib.al3d_crop_box_local(self.d_boxes.data_ptr(), self.d_sincos.data_ptr(), TB, self.d_local.data_ptr(),
+                                                   ops._stream()), "crop_box_local")
         self.max_boxes = max(1, max(nb) if nb else 1)
         CH = lib.al3d_crop_chunk_points()
         # chunk table (frame, first point, points, chunk index in frame), frame-major -- vectorised: a sweep has ~9000 chunks
@@ -130,6 +136,7 @@ class CropPlan:
         self.meta = torch.empty((max(F, 1), 8), device=dev, dtype=torch.float32)
         self.occ = torch.zeros((max(F, 1), lib.al3d_crop_occ_words()), device=dev, dtype=torch.int32)
         self.cell_start = i32(max(F, 1), GRID * GRID + 1)
+        self.cell4 = i32(max(F, 1), GRID * GRID, 2)          # packed cell entries (up to three box ids in 8 bytes)
         self.overflow = torch.zeros((1,), device=dev, dtype=torch.int32)
         # Size the CSR cell lists from the data: a counting run of the grid kernel (cell_cap = 0 stores nothing) leaves
         # every frame's total in cell_start[f, -1].  Few large or heavily overlapping boxes can cover all 64 x 64 cells
@@ -167,13 +174,13 @@ class CropPlan:
     def grid(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
         _lib.check(lib.al3d_crop_build_grid(p(self.d_aabb), p(self.d_boxes), p(self.d_sincos), p(self.d_box_off), self.F, GRID,
-                                            p(self.meta), p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.occ),
-                                            p(self.overflow), st), "crop_build_grid")
+                                            p(self.meta), p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.cell4),
+                                            p(self.occ), p(self.overflow), st), "crop_build_grid")
 
     def hits_pass(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
-        _lib.check(lib.al3d_crop_hits(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_planes), p(self.d_aabb), p(self.d_box_off), GRID, p(self.meta),
-                                      p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.occ), p(self.d_chunks), self.n_chunks,
+        _lib.check(lib.al3d_crop_hits(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_planes), p(self.d_local), p(self.d_box_off), GRID, p(self.meta),
+                                      p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.cell4), p(self.occ), p(self.d_chunks), self.n_chunks,
                                       p(self.hits), self.hit_cap, p(self.n_hits), p(self.cbc), self.max_boxes, p(self.overflow), st),
                    "crop_hits")
 

@@ -48,7 +48,8 @@ __device__ __forceinline__ int crop_cell(float v, float v0, float inv, int G)
 __global__ void __launch_bounds__(kCropThreads)
 crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes, const float *__restrict__ sincos,
                  const int64_t *__restrict__ box_off, int G, CropGridMeta *__restrict__ meta, int32_t *__restrict__ cell_start,
-                 int32_t *__restrict__ cell_boxes, int cell_cap, uint32_t *__restrict__ occ, int32_t *__restrict__ overflow)
+                 int32_t *__restrict__ cell_boxes, int cell_cap, uint2 *__restrict__ cell4, uint32_t *__restrict__ occ,
+                 int32_t *__restrict__ overflow)
 {
     extern __shared__ int32_t s_cnt[];            // G*G counts -> exclusive offsets; then G*G fill cursors; then the occupancy bitmap
     __shared__ float red[6][kCropThreads / 32];
@@ -105,7 +106,8 @@ crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes
             const float *bx = boxes + (b0 + b) * 7;
             const float sn = sincos[(b0 + b) * 2], cs = sincos[(b0 + b) * 2 + 1];
             const float grow = hd + 0.5f * ((a[3] - a[0]) - (fabsf(bx[3] * cs) + fabsf(bx[4] * sn))) + 0.01f;   // half diagonal + rectangle pad + 1 cm
-            const float hl = 0.5f * bx[3] + fmaxf(grow, hd + 0.06f), hw = 0.5f * bx[4] + fmaxf(grow, hd + 0.06f);
+            // |l|, |w|: two negative dimensions mirror the box onto itself, and the reference then still finds points inside
+            const float hl = 0.5f * fabsf(bx[3]) + fmaxf(grow, hd + 0.06f), hw = 0.5f * fabsf(bx[4]) + fmaxf(grow, hd + 0.06f);
             int cx0 = max(crop_cell(a[0], m.x0, m.inv_fx, kOccRes), 0), cx1 = min(crop_cell(a[3], m.x0, m.inv_fx, kOccRes), kOccRes - 1);
             int cy0 = max(crop_cell(a[1], m.y0, m.inv_fy, kOccRes), 0), cy1 = min(crop_cell(a[4], m.y0, m.inv_fy, kOccRes), kOccRes - 1);
             for (int cy = cy0; cy <= cy1; ++cy)
@@ -171,6 +173,17 @@ crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes
             int j = i - 1;
             while (j >= 0 && l[j] > v) { l[j + 1] = l[j]; --j; }
             l[j + 1] = v;
+        }
+        // packed entry of the cell for the hits kernel: up to three box ids in one 8-byte word (id0 | id1 << 16,
+        // id2 | count << 16); count = 0xFFFF sends the reader to the CSR list (longer or truncated lists)
+        if (cell4 != nullptr) {
+            const int full = s_cur[c];
+            uint2 e = make_uint2(0u, 0xFFFFu << 16);
+            if (full <= 3 && full == n) {
+                const unsigned i0 = n > 0 ? (unsigned)l[0] : 0u, i1 = n > 1 ? (unsigned)l[1] : 0u, i2 = n > 2 ? (unsigned)l[2] : 0u;
+                e = make_uint2(i0 | (i1 << 16), i2 | ((unsigned)n << 16));
+            }
+            cell4[(int64_t)f * cells + c] = e;
         }
     }
 }
@@ -250,37 +263,89 @@ static_assert(sizeof(CropHit) == 8, "CropHit");
 constexpr int kCropWarps = kCropThreads / 32;
 constexpr int kCropWarpPts = kCropChunk / kCropWarps;     // consecutive points owned by one warp
 constexpr int kCropIter = 128;                            // points per warp iteration: 4 consecutive points per lane
-constexpr int kCropQueue = 256;                           // per-warp candidate queue (power of two, >= 31 left over + kCropIter new)
+constexpr int kCropCQ = kCropIter;                        // per-warp candidate queue: emptied every iteration
+constexpr int kCropPQ = 128;                              // per-warp (point, box) pair ring: < 32 left over + <= 96 new
+constexpr int kCellIds = 3;                               // box ids held by one packed coarse-cell entry
+static_assert(kCropChunk <= 4096, "a pair carries the chunk-relative point index in 12 bits");
+static_assert(31 + 32 * kCellIds <= kCropPQ, "pair ring");
+
+// Box in its own frame, for the conservative classification of a (point, box) pair (crop_box_local_kernel):
+//   a = (cx, cy, cz, cos)   b = (sin, l/2, w/2, h/2)   c.x = margin m (NaN: always run the exact predicate)
+// With (lx, ly) = R^T (p - c) and t = max(|lx| - l/2, |ly| - w/2, |dz| - h/2):  t < -m  =>  the reference predicate is
+// true, t > m  =>  it is false; only pairs with |t| <= m (a millimetre-thin shell around the faces, or an irregular box)
+// evaluate the six float32 plane equations.  m bounds the rounding of BOTH computations with a wide factor:
+//   reference sign / |n|: <= ~8 eps (|p| + R) k,  k = 1 + D / min(l, w, h)  (corner rounding eps R turned into an
+//   angular error of the normal eps R / min_dim, acting over the box extent D);  local coordinates: <= ~4 eps (t + D);
+//   m = 32 eps (R + D) k  with R = |cx| + |cy| + |cz| + D, D = l + w + h, eps = 2^-23.
+struct CropBoxLocal { float4 a, b, c; };
+static_assert(sizeof(CropBoxLocal) == 48, "CropBoxLocal");
+
+__global__ void crop_box_local_kernel(const float *__restrict__ boxes, const float *__restrict__ sincos, int64_t n_boxes,
+                                      CropBoxLocal *__restrict__ local)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_boxes) return;
+    const float *bx = boxes + b * 7;
+    const float l = bx[3], w = bx[4], h = bx[5];
+    const float D = l + w + h, mind = fminf(l, fminf(w, h));
+    const float R = fabsf(bx[0]) + fabsf(bx[1]) + fabsf(bx[2]) + D;
+    float m = 32.f * 1.1920929e-7f * (R + D) * (1.f + D / mind);
+    // irregular: a non-positive or non-finite dimension, or a margin that is not small against the box
+    if (!(l > 0.f) || !(w > 0.f) || !(h > 0.f) || !(m < 0.25f * mind) || !(R < 1e18f)) m = __int_as_float(0x7fc00000);
+    CropBoxLocal o;
+    o.a = make_float4(bx[0], bx[1], bx[2], sincos[b * 2 + 1]);
+    o.b = make_float4(sincos[b * 2], 0.5f * l, 0.5f * w, 0.5f * h);
+    o.c = make_float4(m, 0.f, 0.f, 0.f);
+    local[b] = o;
+}
 
 // streaming load (the points are read once: do not let them evict the hit lists / counters from L2)
 __device__ __forceinline__ float4 ldg_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
 
+// NaN / infinite (or absurdly large) coordinate: the reference's float32 arithmetic decides (a NaN sign never rejects, so
+// a NaN point is inside every box; inf * 0 products do the same for some boxes) -> exact predicate against EVERY box
+__device__ __forceinline__ bool crop_weird(float x, float y, float z) { return !(fabsf(x) + fabsf(y) + fabsf(z) < 1e18f); }
+
 #ifndef CROP_MINB
-#define CROP_MINB 4          // measured (profiles/r2_crop_variants.txt): 4 -> 0.419 ms, 3 -> 0.429, 2 -> 0.547, 1 -> 0.557 (occupancy)
+#define CROP_MINB 4
+#endif
+#ifdef CROP_STATS
+// diagnostic build only (scripts/gpu_r2_w.sh): [0] candidates, [1] pairs, [2] expand batches, [3] serial expand batches,
+// [4] test batches, [5] test batches that ran the exact predicate, [6] pairs inside the margin, [7] hits
+__device__ unsigned long long g_crop_stats[8];
+#define CROP_STAT(i, v) do { if (lane == 0) atomicAdd(&g_crop_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define CROP_STAT(i, v) do { } while (0)
 #endif
 __global__ void __launch_bounds__(kCropThreads, CROP_MINB)
 crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
-                 const float *__restrict__ planes, const float *__restrict__ aabb, const int64_t *__restrict__ box_off, int G,
+                 const float *__restrict__ planes, const CropBoxLocal *__restrict__ local, const int64_t *__restrict__ box_off, int G,
                  const CropGridMeta *__restrict__ meta, const int32_t *__restrict__ cell_start,
-                 const int32_t *__restrict__ cell_boxes, int cell_cap, const uint32_t *__restrict__ occ,
+                 const int32_t *__restrict__ cell_boxes, int cell_cap, const uint2 *__restrict__ cell4, const uint32_t *__restrict__ occ,
                  const CropChunk *__restrict__ chunks, CropHit *__restrict__ hits, int hit_cap, int32_t *__restrict__ n_hits,
                  int32_t *__restrict__ chunk_box_count, int max_boxes, int rank_boxes, int32_t *__restrict__ overflow)
 {
     // Each warp owns kCropWarpPts CONSECUTIVE points and streams them 128 at a time (four consecutive points per lane,
-    // three 16-byte loads).  Stage 1 is a cheap filter: z range of the frame's boxes, then one bit of the frame's fine
-    // occupancy bitmap (is there any box footprint near this BEV cell?).  ~85 % of the points end here.  The survivors
-    // are compacted, in point order, into a per-warp queue.  Stage 2 takes DENSE batches of 32 queued points -- every
-    // lane busy -- looks up the boxes registered in the point's coarse BEV cell, rejects by the padded rectangle and
-    // runs the exact six-plane predicate; the hits (point, box) go, in point order and ascending box order, to the
-    // warp's staging list.  No block barrier inside the point loop; no limit on the number of boxes a point is in.
-    // The hit list of a chunk is kept as eight per-warp segments of hit_cap entries in global memory (L2-resident while
-    // the chunk is processed): hits[(chunk * 8 + warp) * hit_cap + i], n_hits[chunk * 8 + warp].
-    extern __shared__ int32_t s_dyn[];
-    int32_t *s_box_cnt = s_dyn;                                        // per-box hit counters (max_boxes)
-    float4 *s_queue = reinterpret_cast<float4 *>(s_dyn + ((max_boxes + 3) & ~3));   // kCropWarps x kCropQueue
+    // three 16-byte loads).  Three stages, each run on DENSE batches (every lane busy), connected by per-warp queues in
+    // shared memory that keep point order:
+    //   1  filter: z range of the frame's boxes, then one bit of the frame's fine occupancy bitmap (staged in shared
+    //      memory).  ~85 % of the points end here; survivors go to the candidate queue.
+    //   2  expand: one 8-byte load gives the (up to three) boxes registered in the candidate's coarse BEV cell; every
+    //      (point, box) pair goes to the pair ring.  Cells with more boxes, and NaN / inf points (tested against every
+    //      box, like the reference does), take a serial path that walks the CSR list.
+    //   3  test: classification of the pair in the box's own frame with a rounding margin; only pairs inside the margin
+    //      evaluate the exact six-plane float32 predicate.  Hits are appended, in point order, to the warp's segment.
+    // No block barrier inside the point loop; no limit on the number of boxes a point is in.  The hit list of a chunk is
+    // kept as eight per-warp segments of hit_cap entries in global memory (L2-resident while the chunk is processed):
+    // hits[(chunk * 8 + warp) * hit_cap + i], n_hits[chunk * 8 + warp].
+    extern __shared__ float4 s_dyn4[];
+    float4 *s_cq = s_dyn4;                                             // kCropWarps x kCropCQ
+    float4 *s_pq = s_cq + kCropWarps * kCropCQ;                        // kCropWarps x kCropPQ
+    uint32_t *s_occ = reinterpret_cast<uint32_t *>(s_pq + kCropWarps * kCropPQ);   // kOccWords
+    int32_t *s_box_cnt = reinterpret_cast<int32_t *>(s_occ + kOccWords);           // per-box hit counters (max_boxes)
+    int32_t *s_wcnt = s_box_cnt + ((max_boxes + 3) & ~3);              // kCropWarps x rank_boxes per-warp box counts
     __shared__ int warp_total[kCropWarps];
     const int stage_cap = hit_cap;
-    int32_t *s_wcnt = reinterpret_cast<int32_t *>(s_queue + kCropWarps * kCropQueue);   // kCropWarps x rank_boxes per-warp box counts
     const CropChunk ck = chunks[blockIdx.x];
     const int f = ck.frame;
     const int64_t b0 = box_off[f];
@@ -289,84 +354,144 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     const int cells = G * G;
     const int32_t *cs = cell_start + (int64_t)f * (cells + 1);
     const int32_t *cb = cell_boxes + (int64_t)f * cell_cap;
-    const uint32_t *oc = occ + (int64_t)f * kOccWords;
+    const uint2 *c4 = cell4 + (int64_t)f * cells;
     const float *pts = points + (pt_off[f] + ck.first_pt) * pt_stride;
     const float4 *pl = reinterpret_cast<const float4 *>(planes) + b0 * 6;
-    const float2 *bb = reinterpret_cast<const float2 *>(aabb) + b0 * 3;
+    const CropBoxLocal *loc = local + b0;
+    {
+        const uint32_t *oc = occ + (int64_t)f * kOccWords;
+        for (int w = threadIdx.x; w < kOccWords; w += blockDim.x) s_occ[w] = __ldg(oc + w);
+    }
     for (int b = threadIdx.x; b < B; b += blockDim.x) s_box_cnt[b] = 0;
     const bool par_rank = B <= rank_boxes;                            // ranking by all warps in parallel (else one warp, serially)
     if (par_rank) for (int t = threadIdx.x; t < kCropWarps * rank_boxes; t += blockDim.x) s_wcnt[t] = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float4 *queue = s_queue + wid * kCropQueue;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float4 *cq = s_cq + wid * kCropCQ;
+    float4 *pq = s_pq + wid * kCropPQ;
     CropHit *stage = hits + ((int64_t)blockIdx.x * kCropWarps + wid) * hit_cap;
-    int wcount = 0, qhead = 0, qcount = 0;
+    int wcount = 0, phead = 0, pcount = 0;
     const bool vec = pt_stride == 3 && (reinterpret_cast<uintptr_t>(pts) & 15) == 0;
     const bool grid_ok = m.inv_fx > 0.f;
 
-    // stage 2 on up to 32 queued points (one per lane): exact tests, hits appended in (point, box) order
-    auto drain = [&](int n) {
+    // stage 3 on n <= 32 queued pairs (one per lane, in point order)
+    auto test = [&](int n) {
+        bool hit = false, unc = false;
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        int e0 = 0, len = 0, cnt = 0;
-        unsigned mask = 0;
-        bool all_boxes = false;
+        int pidx = 0, box = 0;
         if (lane < n) {
-            e = queue[(qhead + lane) & (kCropQueue - 1)];
-            if (e.x != e.x || e.y != e.y || e.z != e.z) {
-                // NaN never satisfies `sign >= 0`: the reference reports such a point inside every box it is tested against
-                all_boxes = true; len = B;
-            } else {
+            e = pq[(phead + lane) & (kCropPQ - 1)];
+            const int w = __float_as_int(e.w);
+            pidx = w & 4095; box = (w >> 12) & 0x3FFF;
+            const float4 *L = reinterpret_cast<const float4 *>(loc + box);
+            const float4 A = __ldg(L), Bq = __ldg(L + 1);
+            const float mm = __ldg(reinterpret_cast<const float *>(L + 2));
+            const float dx = e.x - A.x, dy = e.y - A.y, dz = e.z - A.z;
+            // world = [[c, s], [-s, c]] local  (rotation_3d_in_axis)  ->  local = [[c, -s], [s, c]] world
+            const float lx = dx * A.w - dy * Bq.x, ly = dx * Bq.x + dy * A.w;
+            const float t = fmaxf(fmaxf(fabsf(lx) - Bq.y, fabsf(ly) - Bq.z), fabsf(dz) - Bq.w);
+            hit = t < -mm;
+            unc = (w >> 30) != 0 || !(hit || t > mm);                  // weird point, irregular box (m = NaN), or inside the margin
+        }
+        CROP_STAT(4, 1);
+        const unsigned um = __ballot_sync(0xffffffffu, unc);
+        if (um) {
+            CROP_STAT(5, 1); CROP_STAT(6, __popc(um));
+            if (unc) hit = crop_inside(e.x, e.y, e.z, pl + box * 6);
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        const int total = __popc(hm);
+        CROP_STAT(7, total);
+        if (total) {
+            // a batch that does not fit is dropped as a whole (warp-uniform decision): the segment never has holes
+            const bool fits = wcount + total <= stage_cap;
+            if (!fits) { if (lane == 0) atomicExch(overflow, 3); }
+            else {
+                if (hit) stage[wcount + __popc(hm & lt_mask)] = CropHit{ck.first_pt + pidx, box};
+                wcount += total;
+            }
+        }
+        phead = (phead + n) & (kCropPQ - 1);
+        pcount -= n;
+        __syncwarp();
+    };
+
+    // stage 2, serial form: candidates cq[base .. base + n) one after the other, lanes over the boxes of the list
+    auto expand_slow = [&](int base, int n) {
+        CROP_STAT(3, 1);
+        for (int c = 0; c < n; ++c) {
+            const float4 e = cq[base + c];                               // same address in every lane: broadcast
+            const bool weird = crop_weird(e.x, e.y, e.z);
+            int e0 = 0, len = 0;
+            if (weird) len = B;
+            else {
                 const int cx = crop_cell(e.x, m.x0, m.inv_x, G), cy = crop_cell(e.y, m.y0, m.inv_y, G);
                 if (cx >= 0 && cx < G && cy >= 0 && cy < G) {
                     e0 = __ldg(cs + cy * G + cx);
                     len = min(__ldg(cs + cy * G + cx + 1), cell_cap) - e0;
                 }
             }
-            // pass 1: count (and, for lists of up to 32 entries, remember which entries hit)
-            for (int k = 0; k < len; ++k) {
-                const int b = all_boxes ? k : __ldg(cb + e0 + k);
-                bool hit;
-                if (all_boxes) hit = crop_inside(e.x, e.y, e.z, pl + b * 6);
-                else {
-                    const float2 lo = __ldg(bb + b * 3), mid = __ldg(bb + b * 3 + 1), hi = __ldg(bb + b * 3 + 2);
-                    // aabb = [xmin ymin | zmin xmax | ymax zmax], padded: never rejects a point the exact test accepts
-                    hit = e.x >= lo.x && e.y >= lo.y && e.z >= mid.x && e.x <= mid.y && e.y <= hi.x && e.z <= hi.y &&
-                          crop_inside(e.x, e.y, e.z, pl + b * 6);
+            const int tag = __float_as_int(e.w) | (weird ? (1 << 30) : 0);
+            for (int k0 = 0; k0 < len; k0 += 32) {
+                const int k = k0 + lane;
+                if (k < len) {
+                    const int b = weird ? k : __ldg(cb + e0 + k);
+                    pq[(phead + pcount + lane) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (b << 12)));
                 }
-                if (hit) { ++cnt; if (k < 32) mask |= 1u << k; }
+                pcount += min(32, len - k0);
+                CROP_STAT(1, min(32, len - k0));
+                __syncwarp();
+                while (pcount >= 32) test(32);
+            }
+        }
+    };
+
+    // stage 2 on n <= 32 candidates cq[base .. base + n) (one per lane)
+    auto expand = [&](int base, int n) {
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint2 ce = make_uint2(0u, 0u);
+        int cnt = 0, e0 = -1;
+        bool weird = false;
+        CROP_STAT(0, n); CROP_STAT(2, 1);
+        if (lane < n) {
+            e = cq[base + lane];
+            weird = crop_weird(e.x, e.y, e.z);
+            if (!weird) {
+                const int cx = crop_cell(e.x, m.x0, m.inv_x, G), cy = crop_cell(e.y, m.y0, m.inv_y, G);
+                if (cx >= 0 && cx < G && cy >= 0 && cy < G) {
+                    ce = __ldg(c4 + cy * G + cx);                      // id0 | id1 << 16,  id2 | count << 16
+                    cnt = (int)(ce.y >> 16);
+                    if (cnt > kCellIds) {                              // a longer list: this lane reads it from the CSR arrays
+                        e0 = __ldg(cs + cy * G + cx);
+                        cnt = min(__ldg(cs + cy * G + cx + 1), cell_cap) - e0;
+                    }
+                }
             }
         }
         int incl = cnt;
+#pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
-        // a batch that does not fit is dropped as a whole (warp-uniform decision): the segment never has holes
-        const bool fits = wcount + total <= stage_cap;
-        if (!fits && lane == 0) atomicExch(overflow, 3);
-        if (cnt > 0 && fits) {
-            int at = wcount + incl - cnt;
-            const int pidx = ck.first_pt + __float_as_int(e.w);
-            if (len <= 32) {
-                while (mask) {
-                    const int k = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    stage[at++] = CropHit{pidx, all_boxes ? k : __ldg(cb + e0 + k)};
-                }
-            } else {
-                // long list (heavily overlapping boxes, or a NaN point in a frame with many boxes): walk it again
-                for (int k = 0; k < len; ++k) {
-                    const int b = all_boxes ? k : __ldg(cb + e0 + k);
-                    if (crop_inside(e.x, e.y, e.z, pl + b * 6)) stage[at++] = CropHit{pidx, b};
-                }
-            }
+        // weird points (every box) and batches that would not fit the ring go through the serial form
+        if (__any_sync(0xffffffffu, weird) || total > kCropPQ - 32) { expand_slow(base, n); return; }
+        if (total == 0) return;
+        const int at = phead + pcount + incl - cnt;
+        const int tag = __float_as_int(e.w);
+        if (e0 < 0) {
+            if (cnt > 0) pq[at & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (int)((ce.x & 0xFFFFu) << 12)));
+            if (cnt > 1) pq[(at + 1) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (int)((ce.x >> 16) << 12)));
+            if (cnt > 2) pq[(at + 2) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (int)((ce.y & 0xFFFFu) << 12)));
+        } else {
+            for (int k = 0; k < cnt; ++k) pq[(at + k) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (__ldg(cb + e0 + k) << 12)));
         }
-        if (fits) wcount += total;
-        qhead = (qhead + n) & (kCropQueue - 1);
-        qcount -= n;
+        pcount += total;
+        CROP_STAT(1, total);
         __syncwarp();
+        while (pcount >= 32) test(32);
     };
 
     const int w_lo = wid * kCropWarpPts, w_hi = min(w_lo + kCropWarpPts, ck.n_pts);
-    // (Issuing the next iteration's loads before filtering this one was measured: slower -- the extra registers cost an
-    // occupancy step, and with four CTAs per SM other warps already cover the load latency.)
     for (int base = w_lo; base < w_hi; base += kCropIter) {
         const int i0 = base + lane * 4;
         float px[4], py[4], pz[4];
@@ -389,12 +514,12 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
         for (int j = 0; j < 4; ++j) {
             bool ok = false;
             if (i0 + j < w_hi) {
-                if (px[j] != px[j] || py[j] != py[j] || pz[j] != pz[j]) ok = B > 0;            // NaN: inside every box
+                if (crop_weird(px[j], py[j], pz[j])) ok = B > 0;
                 else if (grid_ok && pz[j] >= m.zmin && pz[j] <= m.zmax) {
                     const int cx = crop_cell(px[j], m.x0, m.inv_fx, kOccRes), cy = crop_cell(py[j], m.y0, m.inv_fy, kOccRes);
                     if (cx >= 0 && cx < kOccRes && cy >= 0 && cy < kOccRes) {
                         const int bit = cy * kOccRes + cx;
-                        ok = (__ldg(oc + (bit >> 5)) >> (bit & 31)) & 1u;
+                        ok = (s_occ[bit >> 5] >> (bit & 31)) & 1u;
                     }
                 }
             }
@@ -402,19 +527,19 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
         }
         const int cnt = __popc(pass);
         int incl = cnt;
+#pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         if (total == 0) continue;
-        int at = qhead + qcount + incl - cnt;
+        int at = incl - cnt;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (pass & (1u << j)) queue[(at++) & (kCropQueue - 1)] = make_float4(px[j], py[j], pz[j], __int_as_float(i0 + j));
-        qcount += total;
+            if (pass & (1u << j)) cq[at++] = make_float4(px[j], py[j], pz[j], __int_as_float(i0 + j));
         __syncwarp();
-        while (qcount >= 32) drain(32);
+        for (int q = 0; q < total; q += 32) expand(q, min(32, total - q));
+        __syncwarp();
     }
-    __syncwarp();
-    while (qcount > 0) drain(min(qcount, 32));
+    while (pcount > 0) test(min(pcount, 32));
     if (lane == 0) { warp_total[wid] = wcount; n_hits[(int64_t)blockIdx.x * kCropWarps + wid] = wcount; }
     __syncwarp();
     // ---- rank of every hit among the hits of the same box in this chunk (point order).
@@ -610,11 +735,32 @@ extern "C" int al3d_crop_box_setup(const float *boxes, const float *sincos, int6
     return 0;
 }
 
+extern "C" int al3d_crop_box_local(const float *boxes, const float *sincos, int64_t n_boxes, float *local, void *stream)
+{
+    AL3D_CHECK_ARG(n_boxes >= 0, "al3d_crop_box_local: negative size");
+    if (n_boxes == 0) return 0;
+    AL3D_CHECK_ARG(boxes && sincos && local, "al3d_crop_box_local: null pointer");
+    AL3D_CHECK_ARG((reinterpret_cast<uintptr_t>(local) & 15) == 0, "al3d_crop_box_local: local must be 16-byte aligned");
+    crop_box_local_kernel<<<(unsigned)ceil_div(n_boxes, 128), 128, 0, (cudaStream_t)stream>>>(boxes, sincos, n_boxes,
+                                                                                              reinterpret_cast<CropBoxLocal *>(local));
+    AL3D_CHECK_LAUNCH("crop_box_local_kernel");
+    return 0;
+}
+
 extern "C" int al3d_crop_occ_words(void) { return kOccWords; }
+#ifdef CROP_STATS
+extern "C" int al3d_crop_stats(unsigned long long *out8, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_crop_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_crop_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 extern "C" int al3d_crop_build_grid(const float *aabb, const float *boxes, const float *sincos, const int64_t *box_off, int n_frames, int G,
-                                    float *grid_meta, int32_t *cell_start, int32_t *cell_boxes, int cell_cap, uint32_t *occ,
-                                    int32_t *overflow, void *stream)
+                                    float *grid_meta, int32_t *cell_start, int32_t *cell_boxes, int cell_cap, uint32_t *cell4,
+                                    uint32_t *occ, int32_t *overflow, void *stream)
 {
     AL3D_CHECK_ARG(aabb && box_off && grid_meta && cell_start && cell_boxes && overflow, "al3d_crop_build_grid: null pointer");
     AL3D_CHECK_ARG(!occ || (boxes && sincos), "al3d_crop_build_grid: the occupancy bitmap needs boxes and sincos");
@@ -622,31 +768,36 @@ extern "C" int al3d_crop_build_grid(const float *aabb, const float *boxes, const
     if (n_frames <= 0) return 0;
     const size_t smem = (size_t)(2 * G * G + kOccWords) * sizeof(int32_t);
     crop_grid_kernel<<<n_frames, kCropThreads, smem, (cudaStream_t)stream>>>(
-        aabb, boxes, sincos, box_off, G, reinterpret_cast<CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap, occ, overflow);
+        aabb, boxes, sincos, box_off, G, reinterpret_cast<CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap,
+        reinterpret_cast<uint2 *>(cell4), occ, overflow);
     AL3D_CHECK_LAUNCH("crop_grid_kernel");
     return 0;
 }
 
 extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
-                              const float *aabb, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
-                              const int32_t *cell_boxes, int cell_cap, const uint32_t *occ, const int32_t *chunks, int n_chunks, void *hits,
-                              int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes, int32_t *overflow, void *stream)
+                              const float *local, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
+                              const int32_t *cell_boxes, int cell_cap, const uint32_t *cell4, const uint32_t *occ, const int32_t *chunks,
+                              int n_chunks, void *hits, int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes,
+                              int32_t *overflow, void *stream)
 {
-    AL3D_CHECK_ARG(points && pt_off && planes && aabb && box_off && grid_meta && cell_start && cell_boxes && occ && chunks && hits && n_hits &&
-                   chunk_box_count && overflow, "al3d_crop_hits: null pointer");
+    AL3D_CHECK_ARG(points && pt_off && planes && local && box_off && grid_meta && cell_start && cell_boxes && cell4 && occ && chunks && hits &&
+                   n_hits && chunk_box_count && overflow, "al3d_crop_hits: null pointer");
     AL3D_CHECK_ARG(pt_stride >= 3, "al3d_crop_hits: pt_stride=%lld", (long long)pt_stride);
     AL3D_CHECK_ARG(max_boxes >= 1 && max_boxes <= 12288, "al3d_crop_hits: max_boxes=%d not in [1,12288]", max_boxes);
     AL3D_CHECK_ARG(hit_cap >= 1 && hit_cap <= (1 << 20), "al3d_crop_hits: hit_cap=%d not in [1, 2^20]", hit_cap);
+    AL3D_CHECK_ARG((reinterpret_cast<uintptr_t>(local) & 15) == 0 && (reinterpret_cast<uintptr_t>(cell4) & 7) == 0,
+                   "al3d_crop_hits: local / cell4 misaligned");
     if (n_chunks <= 0) return 0;
     const int rank_boxes = max_boxes <= 512 ? max_boxes : 0;          // per-warp box counters for the parallel ranking, if modest
-    const size_t smem = (size_t)((max_boxes + 3) & ~3) * sizeof(int32_t) + (size_t)kCropWarps * kCropQueue * sizeof(float4) +
-                        (size_t)kCropWarps * rank_boxes * sizeof(int32_t);
-    AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_crop_hits: hit_cap=%d x max_boxes=%d needs too much shared memory", hit_cap, max_boxes);
+    const size_t smem = (size_t)kCropWarps * (kCropCQ + kCropPQ) * sizeof(float4) + (size_t)kOccWords * sizeof(uint32_t) +
+                        (size_t)((max_boxes + 3) & ~3) * sizeof(int32_t) + (size_t)kCropWarps * rank_boxes * sizeof(int32_t);
+    AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_crop_hits: max_boxes=%d needs too much shared memory", max_boxes);
     if (smem > 48 * 1024) AL3D_CHECK_CUDA(cudaFuncSetAttribute(crop_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     crop_hits_kernel<<<n_chunks, kCropThreads, smem, (cudaStream_t)stream>>>(
-        points, pt_stride, pt_off, planes, aabb, box_off, G, reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes,
-        cell_cap, occ, reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<CropHit *>(hits), hit_cap, n_hits, chunk_box_count,
-        max_boxes, rank_boxes, overflow);
+        points, pt_stride, pt_off, planes, reinterpret_cast<const CropBoxLocal *>(local), box_off, G,
+        reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap, reinterpret_cast<const uint2 *>(cell4), occ,
+        reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<CropHit *>(hits), hit_cap, n_hits, chunk_box_count, max_boxes,
+        rank_boxes, overflow);
     AL3D_CHECK_LAUNCH("crop_hits_kernel");
     return 0;
 }

@@ -135,7 +135,7 @@ int al3d_fc_chain(const al3d_fc_chain_desc *d, int bs, void *stream);
  * (det3d/datasets/waymo/waymo_common.py:167-171).  Frames are concatenated: points (sum N_f, stride)
  * f32 with pt_off (F+1) i64; boxes as inward plane equations planes (sum B_f, 6, 4) f32 and padded
  * axis-aligned rectangles aabb (sum B_f, 6) f32 [xmin ymin zmin xmax ymax zmax] with box_off (F+1) i64
- * (both from al3d_crop_box_setup).
+ * (both from al3d_crop_box_setup).  Every point ends up in exactly the lists the reference predicate puts it in.
  * `overflow` is a device int32 the kernels set non-zero when a caller-provided capacity is too small.
  * Order of calls: build_grid -> hits -> scan -> (read offsets[n_boxes] = total, allocate) -> fill.
  * ---------------------------------------------------------------------------------------------- */
@@ -144,24 +144,31 @@ int al3d_fc_chain(const al3d_fc_chain_desc *d, int bs, void *stream);
  * to the reference's numpy arithmetic (box_np_ops.py:55-85,146-179,241-262,650-670; geometry.py:351-377). */
 int al3d_crop_box_setup(const float *boxes, const float *sincos, int64_t n_boxes, float pad_abs, float pad_rel, float *planes,
                         float *aabb, void *stream);
+/* boxes + sincos as above -> local (n,12) f32, 16-byte aligned: the box in its own frame [cx cy cz cos | sin l/2 w/2 h/2 |
+ * margin - - -] for the conservative pair classification of al3d_crop_hits (only pairs within the rounding margin of a
+ * face evaluate the exact plane predicate; margin = NaN marks a box that always does). */
+int al3d_crop_box_local(const float *boxes, const float *sincos, int64_t n_boxes, float *local, void *stream);
 int al3d_crop_chunk_points(void);      /* points per work chunk (the caller builds the chunk table) */
 int al3d_crop_occ_words(void);         /* 32-bit words of one frame's fine occupancy bitmap */
 int al3d_crop_hit_bytes(void);         /* bytes of one hit record of al3d_crop_hits / al3d_crop_fill */
 /* Per frame: grid_meta (n_frames, 8) f32, the coarse G x G cell -> box lists (CSR: cell_start (n_frames, G*G+1),
  * cell_boxes (n_frames, cell_cap); with cell_cap = 0 nothing is stored and cell_start[f, G*G] receives the capacity
- * the frame needs) and, when occ != NULL, the fine occupancy bitmap occ (n_frames, al3d_crop_occ_words()) u32 rasterised
- * from the rotated box footprints (boxes (n,7) + sincos (n,2) as for al3d_crop_box_setup). */
+ * the frame needs), when cell4 != NULL the packed cell entries cell4 (n_frames, G*G, 2) u32 [id0 | id1 << 16,
+ * id2 | count << 16; count 0xFFFF = use the CSR list] and, when occ != NULL, the fine occupancy bitmap occ (n_frames,
+ * al3d_crop_occ_words()) u32 rasterised from the rotated box footprints (boxes (n,7) + sincos (n,2) as for
+ * al3d_crop_box_setup). */
 int al3d_crop_build_grid(const float *aabb, const float *boxes, const float *sincos, const int64_t *box_off, int n_frames, int G,
-                         float *grid_meta, int32_t *cell_start, int32_t *cell_boxes, int cell_cap, uint32_t *occ,
+                         float *grid_meta, int32_t *cell_start, int32_t *cell_boxes, int cell_cap, uint32_t *cell4, uint32_t *occ,
                          int32_t *overflow, void *stream);
 /* chunks: (n_chunks, 4) i32 rows [frame, first point in frame, n points, chunk index in frame];
  * hits: (n_chunks, 8, hit_cap) records of al3d_crop_hit_bytes() bytes, scratch (one ordered segment per warp of the
  * chunk's CTA: point index, box | rank << 16), n_hits (n_chunks, 8) i32;
  * chunk_box_count: (n_chunks, max_boxes) i32 scratch. */
 int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
-                   const float *aabb, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
-                   const int32_t *cell_boxes, int cell_cap, const uint32_t *occ, const int32_t *chunks, int n_chunks, void *hits,
-                   int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes, int32_t *overflow, void *stream);
+                   const float *local, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
+                   const int32_t *cell_boxes, int cell_cap, const uint32_t *cell4, const uint32_t *occ, const int32_t *chunks,
+                   int n_chunks, void *hits, int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes,
+                   int32_t *overflow, void *stream);
 /* frame_chunk_off (F+1) i64; writes box_total (n_boxes) i32 and offsets (n_boxes+1) i64 (exclusive). */
 int al3d_crop_scan(const int64_t *box_off, const int64_t *frame_chunk_off, int n_frames, int64_t n_boxes,
                    int32_t *chunk_box_count, int max_boxes, int32_t *box_total, int64_t *offsets, void *stream);

@@ -152,3 +152,61 @@ def test_crop_many_candidate_rectangles_but_few_hits():
     res = crop.crop_frames([pts], [boxes], [np.eye(4)], hit_cap=16384)
     assert int(res["overflow"].item()) == 0
     _check_against_oracle([pts], [boxes], [np.eye(4)], res)
+
+
+@pytest.mark.gpu
+def test_crop_points_within_the_rounding_margin_of_faces():
+    """The hits kernel classifies a (point, box) pair in the box's own frame and only evaluates the float32 plane
+    equations inside a rounding margin around the faces.  Points placed at 1e-7 .. 1e-1 m on both sides of the faces of
+    rotated boxes far from the origin (where float32 rounding is largest) must land exactly where the reference puts them."""
+    rng = np.random.default_rng(12)
+    nb = 120
+    boxes = np.concatenate([rng.uniform(-300, 300, (nb, 2)), rng.normal(0.5, 0.5, (nb, 1)),
+                            rng.uniform(0.3, 12, (nb, 3)), rng.uniform(-7, 7, (nb, 1))], 1).astype(np.float32)
+    boxes[:6, 3:6] = [[8.0, 0.2, 1.0], [0.2, 8.0, 1.0], [20.0, 2.5, 0.3], [0.5, 0.5, 0.5], [30.0, 0.15, 4.0], [1.0, 1.0, 1.0]]
+    pts = []
+    for b in boxes.astype(np.float64):
+        n = 400
+        u = rng.uniform(-0.5, 0.5, (n, 3)) * b[3:6]
+        ax = rng.integers(0, 3, n)
+        side = rng.choice([-1.0, 1.0], n)
+        eps = side * 10.0 ** rng.uniform(-7, -1, n) * rng.choice([-1.0, 1.0], n)
+        u[np.arange(n), ax] = side * 0.5 * b[3 + ax] + eps
+        c, s = np.cos(b[6]), np.sin(b[6])
+        w = np.stack([u[:, 0] * c + u[:, 1] * s, -u[:, 0] * s + u[:, 1] * c, u[:, 2]], 1) + b[:3]
+        pts.append(w)
+    pts = np.concatenate(pts, 0)[rng.permutation(nb * 400)].astype(np.float32)
+    res = crop.crop_frames([pts], [boxes], [np.eye(4)], hit_cap=16384)
+    assert int(res["overflow"].item()) == 0
+    _check_against_oracle([pts], [boxes], [np.eye(4)], res)
+    ref = ocrop.points_in_boxes(pts, boxes)
+    assert 0.2 < ref.any(1).mean() < 0.8                                   # the sample really straddles the faces
+
+
+@pytest.mark.gpu
+def test_crop_infinite_points_and_irregular_boxes():
+    """inf / NaN / huge coordinates and boxes with zero or negative dimensions take the exact predicate -- whatever the reference's float32 arithmetic says (inf * 0 = NaN never rejects) is the answer."""
+    rng = np.random.default_rng(13)
+    pts = rng.uniform(-6, 6, (9000, 3)).astype(np.float32)
+    pts[:, 2] = rng.uniform(-1.5, 1.5, 9000)
+    inf = np.float32(np.inf)
+    pts[5] = [inf, inf, 0.0]
+    pts[6] = [inf, 0.0, 0.0]
+    pts[7] = [0.0, -inf, 0.2]
+    pts[8] = [np.nan, 0.0, 0.0]
+    pts[9] = [1e30, 1e30, 0.0]
+    pts[10] = [0.0, 0.0, inf]
+    pts[4000] = [-inf, inf, -inf]
+    boxes = np.array([[0, 0, 0, 4, 2, 2, 0.0],            # axis aligned: inf * 0 products
+                      [1, 1, 0, 3, 3, 2, np.pi / 2],
+                      [0.5, -1, 0, 4, 2, 2, 0.7],
+                      [2, 2, 0, 0.0, 2, 2, 0.3],          # zero length
+                      [-2, 1, 0, -3, 2, 2, 0.1],          # negative length
+                      [-2, -2, 0, -3, -2, 2, 0.4],        # two negative dimensions
+                      [0, 3, 0, 1e-4, 1e-4, 1e-4, 0.2],   # margin not small against the box
+                      [3, -3, 0, 2, 2, 2, 0.0]], np.float32)
+    res = crop.crop_frames([pts], [boxes], [np.eye(4)], hit_cap=16384)
+    assert int(res["overflow"].item()) == 0
+    _check_against_oracle([pts], [boxes], [np.eye(4)], res)
+    m = crop.points_in_rbbox(pts, boxes)
+    assert np.array_equal(m, ocrop.points_in_boxes(pts, boxes))
