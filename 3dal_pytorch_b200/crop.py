@@ -88,7 +88,7 @@ class CropPlan:
     """Device-resident state of a batch crop: inputs uploaded, scratch allocated.  ``run()`` only launches the
     kernels (grid build -> hits -> scan -> fill), so it can be timed / replayed without host work."""
 
-    def __init__(self, points, boxes, poses=None, device="cuda", want_xyz=True, hit_cap=None):
+    def __init__(self, points, boxes, poses=None, device="cuda", want_xyz=True, hit_cap=None, chunk=None):
         lib = _lib.lib()
         dev = torch.device(device)
         self.dev, self.want_xyz = dev, want_xyz
@@ -115,7 +115,9 @@ class CropPlan:
                 _lib.check(lib.al3d_crop_box_local(self.d_boxes.data_ptr(), self.d_sincos.data_ptr(), TB, self.d_local.data_ptr(),
                                                    ops._stream()), "crop_box_local")
         self.max_boxes = max(1, max(nb) if nb else 1)
-        CH = lib.al3d_crop_chunk_points()
+        CH = self.chunk_pts = int(chunk) if chunk else self.chunk_points(sum(n_pts))
+        if not 1 <= CH <= lib.al3d_crop_chunk_points():
+            raise ValueError("chunk=%d not in [1, %d]" % (CH, lib.al3d_crop_chunk_points()))
         # chunk table (frame, first point, points, chunk index in frame), frame-major -- vectorised: a sweep has ~9000 chunks
         n_arr = np.asarray(n_pts, dtype=np.int64).reshape(-1)
         n_ch = (n_arr + CH - 1) // CH
@@ -125,8 +127,9 @@ class CropPlan:
         k_of = np.arange(self.n_chunks, dtype=np.int64) - frame_chunk_off[f_of]
         first = k_of * CH
         chunks = np.stack([f_of, first, np.minimum(CH, n_arr[f_of] - first), k_of], 1).astype(np.int32) if self.n_chunks else np.zeros((0, 4), np.int32)
-        # hits per WARP segment (512 consecutive points) of a chunk; the synthetic Waymo-shaped frames average ~50
-        self.hit_cap = int(hit_cap or 256)
+        # hits per WARP segment (an eighth of a chunk, consecutive points): half of its points unless told otherwise (the
+        # synthetic Waymo-shaped frames put ~10 % of the points inside a box)
+        self.hit_cap = int(hit_cap or max(256, CH // 16))
         self.n_seg = 8                               # warps per chunk CTA (csrc/crop.cu kCropWarps)
         i32 = lambda *s: torch.empty(s, device=dev, dtype=torch.int32)
         self.d_pt_off = torch.from_numpy(pt_off).to(dev)
@@ -163,6 +166,14 @@ class CropPlan:
         # algorithmic bytes: every point read once (12 B) + plane equations; the writes are added per run
         self.read_bytes = int(self.pts_all.shape[0]) * 12 + TB * 96
 
+    @staticmethod
+    def chunk_points(total_points):
+        """Points per work chunk (one CTA of the hits kernel): as large as the kernel takes (the per-CTA set-up and the
+        ranking of its hits are amortised over the chunk) while the job still fills every SM several times over."""
+        most = _lib.lib().al3d_crop_chunk_points()
+        want = int(total_points) // 1184                     # 148 SMs x 4 resident CTAs x 2
+        return int(min(most, max(2048, want // 1024 * 1024)))
+
     def _alloc_outputs(self, capacity):
         dev = self.dev
         self.capacity = int(capacity)
@@ -175,7 +186,7 @@ class CropPlan:
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
         _lib.check(lib.al3d_crop_build_grid(p(self.d_aabb), p(self.d_boxes), p(self.d_sincos), p(self.d_box_off), self.F, GRID,
                                             p(self.meta), p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.cell4),
-                                            p(self.occ), p(self.overflow), st), "crop_build_grid")
+                                            self.max_boxes, p(self.occ), p(self.overflow), st), "crop_build_grid")
 
     def hits_pass(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
@@ -219,7 +230,7 @@ class CropPlan:
                 "xyz_global": self.out_glob, "overflow": self.overflow, "read_bytes": self.read_bytes}
 
 
-def crop_frames(points, boxes, poses=None, device="cuda", want_xyz=True, hit_cap=None, capacity=None):
+def crop_frames(points, boxes, poses=None, device="cuda", want_xyz=True, hit_cap=None, capacity=None, chunk=None):
     """points: list of (N_f, >=3) f32 arrays / CUDA tensors; boxes: list of (B_f, 7) f32 Waymo-convention
     arrays; poses: optional list of 4x4 f64 vehicle->global matrices.
 
@@ -228,7 +239,7 @@ def crop_frames(points, boxes, poses=None, device="cuda", want_xyz=True, hit_cap
                  box_off (F+1,) i64 host; xyz (T,3) f32; xyz_global (T,3) f64 when poses are given).
     With ``capacity`` set no host synchronisation happens (the output is over-allocated); otherwise the total
     count is read back once to size the outputs exactly."""
-    return CropPlan(points, boxes, poses, device=device, want_xyz=want_xyz, hit_cap=hit_cap).run(capacity)
+    return CropPlan(points, boxes, poses, device=device, want_xyz=want_xyz, hit_cap=hit_cap, chunk=chunk).run(capacity)
 
 
 def points_in_rbbox(points, rbbox, z_axis=2, origin=(0.5, 0.5, 0.5), device="cuda"):
@@ -245,7 +256,7 @@ def points_in_rbbox(points, rbbox, z_axis=2, origin=(0.5, 0.5, 0.5), device="cud
     try:
         res = crop_frames([pts], [rb], device=device, want_xyz=False)
     except OverflowError:
-        res = crop_frames([pts], [rb], device=device, want_xyz=False, hit_cap=512 * B)
+        res = crop_frames([pts], [rb], device=device, want_xyz=False, hit_cap=CropPlan.chunk_points(N) // 8 * B)
     _check_overflow(res["overflow"], "fill")
     mask = torch.zeros((N, B), device=res["indices"].device, dtype=torch.uint8)
     _lib.check(_lib.lib().al3d_crop_dense_mask(res["indices"].data_ptr(), res["offsets"].data_ptr(), B, mask.data_ptr(),

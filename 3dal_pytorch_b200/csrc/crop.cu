@@ -23,7 +23,7 @@
 
 namespace al3d {
 
-constexpr int kCropChunk = 4096;       // points per CTA of the hits kernel
+constexpr int kCropChunk = 16384;      // most points one CTA of the hits kernel takes (the caller may cut smaller chunks)
 constexpr int kCropThreads = 256;
 constexpr int kOccRes = 256;           // fine occupancy bitmap per frame: kOccRes x kOccRes bits (8 KB)
 constexpr int kOccWords = kOccRes * kOccRes / 32;
@@ -48,7 +48,7 @@ __device__ __forceinline__ int crop_cell(float v, float v0, float inv, int G)
 __global__ void __launch_bounds__(kCropThreads)
 crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes, const float *__restrict__ sincos,
                  const int64_t *__restrict__ box_off, int G, CropGridMeta *__restrict__ meta, int32_t *__restrict__ cell_start,
-                 int32_t *__restrict__ cell_boxes, int cell_cap, uint2 *__restrict__ cell4, uint32_t *__restrict__ occ,
+                 int32_t *__restrict__ cell_boxes, int cell_cap, uint2 *__restrict__ cell4, int packed32, uint32_t *__restrict__ occ,
                  int32_t *__restrict__ overflow)
 {
     extern __shared__ int32_t s_cnt[];            // G*G counts -> exclusive offsets; then G*G fill cursors; then the occupancy bitmap
@@ -176,14 +176,16 @@ crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes
         }
         // packed entry of the cell for the hits kernel: up to three box ids in one 8-byte word (id0 | id1 << 16,
         // id2 | count << 16); count = 0xFFFF sends the reader to the CSR list (longer or truncated lists)
+        // (packed32, for frames of at most 1023 boxes: one 4-byte word id0 | id1 << 10 | id2 << 20 | count << 30, all ones =
+        // use the CSR list -- small enough for the hits kernel to keep a frame's table in shared memory)
         if (cell4 != nullptr) {
             const int full = s_cur[c];
-            uint2 e = make_uint2(0u, 0xFFFFu << 16);
-            if (full <= 3 && full == n) {
-                const unsigned i0 = n > 0 ? (unsigned)l[0] : 0u, i1 = n > 1 ? (unsigned)l[1] : 0u, i2 = n > 2 ? (unsigned)l[2] : 0u;
-                e = make_uint2(i0 | (i1 << 16), i2 | ((unsigned)n << 16));
-            }
-            cell4[(int64_t)f * cells + c] = e;
+            const bool ok = full <= 3 && full == n;
+            const unsigned i0 = ok && n > 0 ? (unsigned)l[0] : 0u, i1 = ok && n > 1 ? (unsigned)l[1] : 0u, i2 = ok && n > 2 ? (unsigned)l[2] : 0u;
+            if (packed32)
+                reinterpret_cast<uint32_t *>(cell4)[(int64_t)f * cells + c] = ok ? (i0 | (i1 << 10) | (i2 << 20) | ((unsigned)n << 30)) : 0xFFFFFFFFu;
+            else
+                cell4[(int64_t)f * cells + c] = ok ? make_uint2(i0 | (i1 << 16), i2 | ((unsigned)n << 16)) : make_uint2(0u, 0xFFFFu << 16);
         }
     }
 }
@@ -261,12 +263,20 @@ struct CropChunk { int32_t frame; int32_t first_pt; int32_t n_pts; int32_t chunk
 struct __align__(8) CropHit { int32_t idx, box_rank; };          // one 8-byte store per hit
 static_assert(sizeof(CropHit) == 8, "CropHit");
 constexpr int kCropWarps = kCropThreads / 32;
-constexpr int kCropWarpPts = kCropChunk / kCropWarps;     // consecutive points owned by one warp
-constexpr int kCropIter = 128;                            // points per warp iteration: 4 consecutive points per lane
-constexpr int kCropCQ = kCropIter;                        // per-warp candidate queue: emptied every iteration
+constexpr int kCropIter = 128;                            // points per warp iteration: point base + j * 32 + lane, j < 4
+constexpr int kCropCQ = 96;                               // per-warp candidate queue: < 32 carried over + <= 64 new (half an iteration)
+constexpr int kLocSmemBoxes = 256;                        // frames with at most this many boxes keep their box records in shared memory
+// The packed 4-byte cell table of such frames can be staged in shared memory too.  Measured on the 200-frame sweep
+// (profiles/r2_crop_v3_ablation.txt): it takes 0.026 ms off the expand stage, but the 16 KB cost the fourth resident
+// CTA per SM and the streaming filter then loses 0.04 ms -- off.
+#ifndef CROP_C4_SMEM
+#define CROP_C4_SMEM 0
+#endif
+constexpr bool kC4Smem = CROP_C4_SMEM != 0;
 constexpr int kCropPQ = 128;                              // per-warp (point, box) pair ring: < 32 left over + <= 96 new
 constexpr int kCellIds = 3;                               // box ids held by one packed coarse-cell entry
-static_assert(kCropChunk <= 4096, "a pair carries the chunk-relative point index in 12 bits");
+constexpr int kIdxBits = 14;                              // a pair's tag: chunk-relative point index | box << 14 | weird << 30
+static_assert(kCropChunk <= (1 << kIdxBits), "a pair carries the chunk-relative point index in kIdxBits bits");
 static_assert(31 + 32 * kCellIds <= kCropPQ, "pair ring");
 
 // Box in its own frame, for the conservative classification of a (point, box) pair (crop_box_local_kernel):
@@ -299,15 +309,15 @@ __global__ void crop_box_local_kernel(const float *__restrict__ boxes, const flo
     local[b] = o;
 }
 
-// streaming load (the points are read once: do not let them evict the hit lists / counters from L2)
-__device__ __forceinline__ float4 ldg_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
-
 // NaN / infinite (or absurdly large) coordinate: the reference's float32 arithmetic decides (a NaN sign never rejects, so
 // a NaN point is inside every box; inf * 0 products do the same for some boxes) -> exact predicate against EVERY box
 __device__ __forceinline__ bool crop_weird(float x, float y, float z) { return !(fabsf(x) + fabsf(y) + fabsf(z) < 1e18f); }
 
 #ifndef CROP_MINB
-#define CROP_MINB 4
+#define CROP_MINB 3
+#endif
+#ifndef CROP_PREFETCH
+#define CROP_PREFETCH 0
 #endif
 #ifdef CROP_STATS
 // diagnostic build only (scripts/gpu_r2_w.sh): [0] candidates, [1] pairs, [2] expand batches, [3] serial expand batches,
@@ -317,6 +327,7 @@ __device__ unsigned long long g_crop_stats[8];
 #else
 #define CROP_STAT(i, v) do { } while (0)
 #endif
+template <bool kSmemTables>
 __global__ void __launch_bounds__(kCropThreads, CROP_MINB)
 crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
                  const float *__restrict__ planes, const CropBoxLocal *__restrict__ local, const int64_t *__restrict__ box_off, int G,
@@ -325,14 +336,14 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                  const CropChunk *__restrict__ chunks, CropHit *__restrict__ hits, int hit_cap, int32_t *__restrict__ n_hits,
                  int32_t *__restrict__ chunk_box_count, int max_boxes, int rank_boxes, int32_t *__restrict__ overflow)
 {
-    // Each warp owns kCropWarpPts CONSECUTIVE points and streams them 128 at a time (four consecutive points per lane,
-    // three 16-byte loads).  Three stages, each run on DENSE batches (every lane busy), connected by per-warp queues in
-    // shared memory that keep point order:
+    // Each warp owns a run of CONSECUTIVE points of the chunk and streams it 128 points at a time (point = base + j * 32 +
+    // lane: lane order is point order, so a ballot compacts in order).  Three stages, each run on DENSE batches (every
+    // lane busy), connected by per-warp queues in shared memory that keep point order:
     //   1  filter: z range of the frame's boxes, then one bit of the frame's fine occupancy bitmap (staged in shared
-    //      memory).  ~85 % of the points end here; survivors go to the candidate queue.
+    //      memory).  ~80 % of the points end here; survivors go to the candidate queue.
     //   2  expand: one 8-byte load gives the (up to three) boxes registered in the candidate's coarse BEV cell; every
-    //      (point, box) pair goes to the pair ring.  Cells with more boxes, and NaN / inf points (tested against every
-    //      box, like the reference does), take a serial path that walks the CSR list.
+    //      (point, box) pair goes to the pair ring.  A lane whose cell holds more boxes reads the CSR list; NaN / inf points
+    //      (tested against every box, like the reference does) take a serial form.
     //   3  test: classification of the pair in the box's own frame with a rounding margin; only pairs inside the margin
     //      evaluate the exact six-plane float32 predicate.  Hits are appended, in point order, to the warp's segment.
     // No block barrier inside the point loop; no limit on the number of boxes a point is in.  The hit list of a chunk is
@@ -341,7 +352,9 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     extern __shared__ float4 s_dyn4[];
     float4 *s_cq = s_dyn4;                                             // kCropWarps x kCropCQ
     float4 *s_pq = s_cq + kCropWarps * kCropCQ;                        // kCropWarps x kCropPQ
-    uint32_t *s_occ = reinterpret_cast<uint32_t *>(s_pq + kCropWarps * kCropPQ);   // kOccWords
+    float4 *s_loc = s_pq + kCropWarps * kCropPQ;                       // kSmemTables: the frame's box records (3 x 16 B each)
+    uint32_t *s_c4 = reinterpret_cast<uint32_t *>(s_loc + (kSmemTables ? 3 * max_boxes : 0));   // kSmemTables && kC4Smem: packed cell entries (G x G)
+    uint32_t *s_occ = s_c4 + (kSmemTables && kC4Smem ? G * G : 0);    // kOccWords
     int32_t *s_box_cnt = reinterpret_cast<int32_t *>(s_occ + kOccWords);           // per-box hit counters (max_boxes)
     int32_t *s_wcnt = s_box_cnt + ((max_boxes + 3) & ~3);              // kCropWarps x rank_boxes per-warp box counts
     __shared__ int warp_total[kCropWarps];
@@ -362,6 +375,16 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
         const uint32_t *oc = occ + (int64_t)f * kOccWords;
         for (int w = threadIdx.x; w < kOccWords; w += blockDim.x) s_occ[w] = __ldg(oc + w);
     }
+    if (kSmemTables) {
+        // the expand stage gathers one cell entry per lane and the pair test a 48-byte box record per lane: scattered, so
+        // from L2 they cost a full round trip per batch (measured: 0.085 ms of a 0.27 ms sweep for the cell entries alone)
+        const float4 *g = reinterpret_cast<const float4 *>(loc);
+        for (int t = threadIdx.x; t < 3 * B; t += blockDim.x) s_loc[t] = __ldg(g + t);
+        if (kC4Smem) {
+            const uint32_t *g4 = reinterpret_cast<const uint32_t *>(cell4) + (int64_t)f * cells;
+            for (int t = threadIdx.x; t < cells; t += blockDim.x) s_c4[t] = __ldg(g4 + t);
+        }
+    }
     for (int b = threadIdx.x; b < B; b += blockDim.x) s_box_cnt[b] = 0;
     const bool par_rank = B <= rank_boxes;                            // ranking by all warps in parallel (else one warp, serially)
     if (par_rank) for (int t = threadIdx.x; t < kCropWarps * rank_boxes; t += blockDim.x) s_wcnt[t] = 0;
@@ -371,9 +394,10 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     float4 *cq = s_cq + wid * kCropCQ;
     float4 *pq = s_pq + wid * kCropPQ;
     CropHit *stage = hits + ((int64_t)blockIdx.x * kCropWarps + wid) * hit_cap;
-    int wcount = 0, phead = 0, pcount = 0;
-    const bool vec = pt_stride == 3 && (reinterpret_cast<uintptr_t>(pts) & 15) == 0;
-    const bool grid_ok = m.inv_fx > 0.f;
+    int wcount = 0, phead = 0, pcount = 0, cqn = 0;
+#ifdef CROP_ABLATE       // timing experiments only (scripts/gpu_r2_abl.sh): 1 prologue, 2 + filter, 3 + expand, 4 + test (no ranking)
+    if (CROP_ABLATE == 1) return;
+#endif
 
     // stage 3 on n <= 32 queued pairs (one per lane, in point order)
     auto test = [&](int n) {
@@ -383,10 +407,14 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
         if (lane < n) {
             e = pq[(phead + lane) & (kCropPQ - 1)];
             const int w = __float_as_int(e.w);
-            pidx = w & 4095; box = (w >> 12) & 0x3FFF;
-            const float4 *L = reinterpret_cast<const float4 *>(loc + box);
-            const float4 A = __ldg(L), Bq = __ldg(L + 1);
-            const float mm = __ldg(reinterpret_cast<const float *>(L + 2));
+            pidx = w & ((1 << kIdxBits) - 1); box = (w >> kIdxBits) & 0x3FFF;
+            float4 A, Bq;
+            float mm;
+            if (kSmemTables) { A = s_loc[box * 3]; Bq = s_loc[box * 3 + 1]; mm = s_loc[box * 3 + 2].x; }
+            else {
+                const float4 *L = reinterpret_cast<const float4 *>(loc + box);
+                A = __ldg(L); Bq = __ldg(L + 1); mm = __ldg(reinterpret_cast<const float *>(L + 2));
+            }
             const float dx = e.x - A.x, dy = e.y - A.y, dz = e.z - A.z;
             // world = [[c, s], [-s, c]] local  (rotation_3d_in_axis)  ->  local = [[c, -s], [s, c]] world
             const float lx = dx * A.w - dy * Bq.x, ly = dx * Bq.x + dy * A.w;
@@ -437,7 +465,7 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                 const int k = k0 + lane;
                 if (k < len) {
                     const int b = weird ? k : __ldg(cb + e0 + k);
-                    pq[(phead + pcount + lane) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (b << 12)));
+                    pq[(phead + pcount + lane) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (b << kIdxBits)));
                 }
                 pcount += min(32, len - k0);
                 CROP_STAT(1, min(32, len - k0));
@@ -457,89 +485,131 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
         if (lane < n) {
             e = cq[base + lane];
             weird = crop_weird(e.x, e.y, e.z);
-            if (!weird) {
-                const int cx = crop_cell(e.x, m.x0, m.inv_x, G), cy = crop_cell(e.y, m.y0, m.inv_y, G);
-                if (cx >= 0 && cx < G && cy >= 0 && cy < G) {
-                    ce = __ldg(c4 + cy * G + cx);                      // id0 | id1 << 16,  id2 | count << 16
-                    cnt = (int)(ce.y >> 16);
-                    if (cnt > kCellIds) {                              // a longer list: this lane reads it from the CSR arrays
-                        e0 = __ldg(cs + cy * G + cx);
-                        cnt = min(__ldg(cs + cy * G + cx + 1), cell_cap) - e0;
-                    }
+            // the same cell function the grid kernel registered the rectangles with (crop_cell, unclamped: the unsigned
+            // comparison rejects everything outside [0, G))
+            const int cx = __float2int_rd((e.x - m.x0) * m.inv_x), cy = __float2int_rd((e.y - m.y0) * m.inv_y);
+            if (!weird && (unsigned)cx < (unsigned)G && (unsigned)cy < (unsigned)G) {
+                if (kSmemTables && kC4Smem) {
+                    const uint32_t w = s_c4[cy * G + cx];              // id0 | id1 << 10 | id2 << 20 | count << 30, all ones = long list
+                    ce = make_uint2((w & 1023u) | (((w >> 10) & 1023u) << 16), ((w >> 20) & 1023u) | ((w == 0xFFFFFFFFu ? 0xFFFFu : (w >> 30)) << 16));
+                } else ce = __ldg(c4 + cy * G + cx);                   // id0 | id1 << 16,  id2 | count << 16
+                cnt = (int)(ce.y >> 16);
+                if (cnt > kCellIds) {                                  // a longer list: this lane reads it from the CSR arrays
+                    e0 = __ldg(cs + cy * G + cx);
+                    cnt = min(__ldg(cs + cy * G + cx + 1), cell_cap) - e0;
                 }
             }
         }
-        int incl = cnt;
+        // exclusive prefix of the pair counts over the lanes: counts of 0..3 (all but a few per cent of the batches) from two
+        // ballots of the count's bits, anything longer from a shuffle scan
+        int excl, total;
+        if (!__any_sync(0xffffffffu, cnt > 3)) {
+            const unsigned b0m = __ballot_sync(0xffffffffu, cnt & 1), b1m = __ballot_sync(0xffffffffu, cnt & 2);
+            excl = __popc(b0m & lt_mask) + 2 * __popc(b1m & lt_mask);
+            total = __popc(b0m) + 2 * __popc(b1m);
+        } else {
+            int incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            total = __shfl_sync(0xffffffffu, incl, 31);
+            excl = incl - cnt;
+        }
         // weird points (every box) and batches that would not fit the ring go through the serial form
         if (__any_sync(0xffffffffu, weird) || total > kCropPQ - 32) { expand_slow(base, n); return; }
         if (total == 0) return;
-        const int at = phead + pcount + incl - cnt;
+        const int at = phead + pcount + excl;
         const int tag = __float_as_int(e.w);
         if (e0 < 0) {
-            if (cnt > 0) pq[at & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (int)((ce.x & 0xFFFFu) << 12)));
-            if (cnt > 1) pq[(at + 1) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (int)((ce.x >> 16) << 12)));
-            if (cnt > 2) pq[(at + 2) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (int)((ce.y & 0xFFFFu) << 12)));
+            if (cnt > 0) pq[at & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (int)((ce.x & 0xFFFFu) << kIdxBits)));
+            if (cnt > 1) pq[(at + 1) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (int)((ce.x >> 16) << kIdxBits)));
+            if (cnt > 2) pq[(at + 2) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (int)((ce.y & 0xFFFFu) << kIdxBits)));
         } else {
-            for (int k = 0; k < cnt; ++k) pq[(at + k) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (__ldg(cb + e0 + k) << 12)));
+            for (int k = 0; k < cnt; ++k)
+                pq[(at + k) & (kCropPQ - 1)] = make_float4(e.x, e.y, e.z, __int_as_float(tag | (__ldg(cb + e0 + k) << kIdxBits)));
         }
         pcount += total;
         CROP_STAT(1, total);
         __syncwarp();
+#ifdef CROP_ABLATE
+        if (CROP_ABLATE == 3) { phead = (phead + pcount) & (kCropPQ - 1); pcount = 0; }
+#endif
         while (pcount >= 32) test(32);
     };
 
-    const int w_lo = wid * kCropWarpPts, w_hi = min(w_lo + kCropWarpPts, ck.n_pts);
-    for (int base = w_lo; base < w_hi; base += kCropIter) {
-        const int i0 = base + lane * 4;
-        float px[4], py[4], pz[4];
-        if (vec && i0 + 3 < w_hi) {
-            const float4 a = ldg_stream4(pts + (int64_t)i0 * 3), b = ldg_stream4(pts + (int64_t)i0 * 3 + 4), c = ldg_stream4(pts + (int64_t)i0 * 3 + 8);
-            px[0] = a.x; py[0] = a.y; pz[0] = a.z; px[1] = a.w; py[1] = b.x; pz[1] = b.y;
-            px[2] = b.z; py[2] = b.w; pz[2] = c.x; px[3] = c.y; py[3] = c.z; pz[3] = c.w;
+    // the warps split the chunk into runs of whole iterations
+    const int wp = ((ck.n_pts + kCropWarps * kCropIter - 1) / (kCropWarps * kCropIter)) * kCropIter;
+    const int w_lo = min(wid * wp, ck.n_pts), w_hi = min(w_lo + wp, ck.n_pts);
+    const int ps = (int)pt_stride;
+    const float ofx = -m.x0 * m.inv_fx, ofy = -m.y0 * m.inv_fy;      // fine cell = floor(x * inv + of): the bitmap is conservative
+    const bool any_box = B > 0;                                       // by centimetres, so this need not be crop_cell's rounding
+    auto load = [&](int base, float (&px)[4], float (&py)[4], float (&pz)[4]) {
+        if (base + kCropIter <= w_hi && ps == 3) {
+            const float *q = pts + (base + lane) * 3;                  // 12-byte stride: immediate offsets, any alignment
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { px[j] = __ldg(q + j * 96); py[j] = __ldg(q + j * 96 + 1); pz[j] = __ldg(q + j * 96 + 2); }
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                px[j] = py[j] = pz[j] = 0.f;
-                if (i0 + j < w_hi) {
-                    const float *q = pts + (int64_t)(i0 + j) * pt_stride;
-                    px[j] = __ldg(q); py[j] = __ldg(q + 1); pz[j] = __ldg(q + 2);
-                }
+                const float *q = pts + (int64_t)min(base + j * 32 + lane, w_hi - 1) * ps;
+                px[j] = __ldg(q); py[j] = __ldg(q + 1); pz[j] = __ldg(q + 2);
             }
         }
-        unsigned pass = 0;
+    };
+    float px[4], py[4], pz[4];
+    if (w_lo < w_hi) load(w_lo, px, py, pz);
+    for (int base = w_lo; base < w_hi; base += kCropIter) {
+        const bool full = base + kCropIter <= w_hi;
+#if CROP_PREFETCH
+        // the next iteration's points are requested before this iteration's are looked at (registers are there: shared
+        // memory, not the register file, limits the CTAs per SM)
+        float nx[4], ny[4], nz[4];
+        if (base + kCropIter < w_hi) load(base + kCropIter, nx, ny, nz);
+#endif
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            bool ok = false;
-            if (i0 + j < w_hi) {
-                if (crop_weird(px[j], py[j], pz[j])) ok = B > 0;
-                else if (grid_ok && pz[j] >= m.zmin && pz[j] <= m.zmax) {
-                    const int cx = crop_cell(px[j], m.x0, m.inv_fx, kOccRes), cy = crop_cell(py[j], m.y0, m.inv_fy, kOccRes);
-                    if (cx >= 0 && cx < kOccRes && cy >= 0 && cy < kOccRes) {
-                        const int bit = cy * kOccRes + cx;
-                        ok = (s_occ[bit >> 5] >> (bit & 31)) & 1u;
-                    }
-                }
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = half * 2 + jj;
+                const float x = px[j], y = py[j], z = pz[j];
+                const int ix = __float2int_rd(fmaf(x, m.inv_fx, ofx)), iy = __float2int_rd(fmaf(y, m.inv_fy, ofy));
+                const int bit = iy * kOccRes + ix;
+                const uint32_t word = s_occ[(bit >> 5) & (kOccWords - 1)];
+                const bool near_box = (unsigned)(ix | iy) < (unsigned)kOccRes && z >= m.zmin && z <= m.zmax && ((word >> (bit & 31)) & 1u);
+                bool ok = crop_weird(x, y, z) ? any_box : near_box;    // empty frame: zmin = +inf, nothing passes
+                if (!full) ok = ok && base + j * 32 + lane < w_hi;
+                const unsigned bm = __ballot_sync(0xffffffffu, ok);
+                if (ok) cq[cqn + __popc(bm & lt_mask)] = make_float4(x, y, z, __int_as_float(base + j * 32 + lane));
+                cqn += __popc(bm);
             }
-            pass |= ok ? (1u << j) : 0u;
+            __syncwarp();
+#ifdef CROP_ABLATE
+            if (CROP_ABLATE == 2) cqn = 0;
+#endif
+            if (cqn >= 32) {
+                int q = 0;
+                for (; q + 32 <= cqn; q += 32) expand(q, 32);
+                // carry the remainder (< 32 candidates) to the front of the queue
+                const int rem = cqn - q;
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < rem) e = cq[q + lane];
+                __syncwarp();
+                if (lane < rem) cq[lane] = e;
+                cqn = rem;
+                __syncwarp();
+            }
         }
-        const int cnt = __popc(pass);
-        int incl = cnt;
+#if CROP_PREFETCH
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) continue;
-        int at = incl - cnt;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (pass & (1u << j)) cq[at++] = make_float4(px[j], py[j], pz[j], __int_as_float(i0 + j));
-        __syncwarp();
-        for (int q = 0; q < total; q += 32) expand(q, min(32, total - q));
-        __syncwarp();
+        for (int j = 0; j < 4; ++j) { px[j] = nx[j]; py[j] = ny[j]; pz[j] = nz[j]; }
+#else
+        if (base + kCropIter < w_hi) load(base + kCropIter, px, py, pz);
+#endif
     }
+    if (cqn > 0) expand(0, cqn);
     while (pcount > 0) test(min(pcount, 32));
+#ifdef CROP_ABLATE
+    if (CROP_ABLATE >= 2) return;
+#endif
     if (lane == 0) { warp_total[wid] = wcount; n_hits[(int64_t)blockIdx.x * kCropWarps + wid] = wcount; }
     __syncwarp();
     // ---- rank of every hit among the hits of the same box in this chunk (point order).
@@ -760,7 +830,7 @@ extern "C" int al3d_crop_stats(unsigned long long *out8, int reset)
 
 extern "C" int al3d_crop_build_grid(const float *aabb, const float *boxes, const float *sincos, const int64_t *box_off, int n_frames, int G,
                                     float *grid_meta, int32_t *cell_start, int32_t *cell_boxes, int cell_cap, uint32_t *cell4,
-                                    uint32_t *occ, int32_t *overflow, void *stream)
+                                    int max_boxes, uint32_t *occ, int32_t *overflow, void *stream)
 {
     AL3D_CHECK_ARG(aabb && box_off && grid_meta && cell_start && cell_boxes && overflow, "al3d_crop_build_grid: null pointer");
     AL3D_CHECK_ARG(!occ || (boxes && sincos), "al3d_crop_build_grid: the occupancy bitmap needs boxes and sincos");
@@ -769,7 +839,7 @@ extern "C" int al3d_crop_build_grid(const float *aabb, const float *boxes, const
     const size_t smem = (size_t)(2 * G * G + kOccWords) * sizeof(int32_t);
     crop_grid_kernel<<<n_frames, kCropThreads, smem, (cudaStream_t)stream>>>(
         aabb, boxes, sincos, box_off, G, reinterpret_cast<CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap,
-        reinterpret_cast<uint2 *>(cell4), occ, overflow);
+        reinterpret_cast<uint2 *>(cell4), kC4Smem && max_boxes <= kLocSmemBoxes, occ, overflow);
     AL3D_CHECK_LAUNCH("crop_grid_kernel");
     return 0;
 }
@@ -789,11 +859,15 @@ extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int6
                    "al3d_crop_hits: local / cell4 misaligned");
     if (n_chunks <= 0) return 0;
     const int rank_boxes = max_boxes <= 512 ? max_boxes : 0;          // per-warp box counters for the parallel ranking, if modest
-    const size_t smem = (size_t)kCropWarps * (kCropCQ + kCropPQ) * sizeof(float4) + (size_t)kOccWords * sizeof(uint32_t) +
-                        (size_t)((max_boxes + 3) & ~3) * sizeof(int32_t) + (size_t)kCropWarps * rank_boxes * sizeof(int32_t);
+    const bool loc_smem = max_boxes <= kLocSmemBoxes;                 // must agree with the format al3d_crop_build_grid chose
+    const size_t smem = (size_t)kCropWarps * (kCropCQ + kCropPQ) * sizeof(float4) +
+                        (loc_smem ? (size_t)max_boxes * sizeof(CropBoxLocal) + (kC4Smem ? (size_t)G * G * sizeof(uint32_t) : 0) : 0) +
+                        (size_t)kOccWords * sizeof(uint32_t) + (size_t)((max_boxes + 3) & ~3) * sizeof(int32_t) +
+                        (size_t)kCropWarps * rank_boxes * sizeof(int32_t);
     AL3D_CHECK_ARG(smem <= 200 * 1024, "al3d_crop_hits: max_boxes=%d needs too much shared memory", max_boxes);
-    if (smem > 48 * 1024) AL3D_CHECK_CUDA(cudaFuncSetAttribute(crop_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    crop_hits_kernel<<<n_chunks, kCropThreads, smem, (cudaStream_t)stream>>>(
+    auto kern = loc_smem ? crop_hits_kernel<true> : crop_hits_kernel<false>;
+    if (smem > 48 * 1024) AL3D_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_chunks, kCropThreads, smem, (cudaStream_t)stream>>>(
         points, pt_stride, pt_off, planes, reinterpret_cast<const CropBoxLocal *>(local), box_off, G,
         reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap, reinterpret_cast<const uint2 *>(cell4), occ,
         reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<CropHit *>(hits), hit_cap, n_hits, chunk_box_count, max_boxes,

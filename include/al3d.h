@@ -154,12 +154,13 @@ int al3d_crop_hit_bytes(void);         /* bytes of one hit record of al3d_crop_h
 /* Per frame: grid_meta (n_frames, 8) f32, the coarse G x G cell -> box lists (CSR: cell_start (n_frames, G*G+1),
  * cell_boxes (n_frames, cell_cap); with cell_cap = 0 nothing is stored and cell_start[f, G*G] receives the capacity
  * the frame needs), when cell4 != NULL the packed cell entries cell4 (n_frames, G*G, 2) u32 [id0 | id1 << 16,
- * id2 | count << 16; count 0xFFFF = use the CSR list] and, when occ != NULL, the fine occupancy bitmap occ (n_frames,
+ * id2 | count << 16; count 0xFFFF = use the CSR list; max_boxes must be the value al3d_crop_hits gets: a build with
+ * CROP_C4_SMEM stores (n_frames, G*G) 4-byte words id0 | id1 << 10 | id2 << 20 | count << 30 instead when it is <= 256] and, when occ != NULL, the fine occupancy bitmap occ (n_frames,
  * al3d_crop_occ_words()) u32 rasterised from the rotated box footprints (boxes (n,7) + sincos (n,2) as for
  * al3d_crop_box_setup). */
 int al3d_crop_build_grid(const float *aabb, const float *boxes, const float *sincos, const int64_t *box_off, int n_frames, int G,
-                         float *grid_meta, int32_t *cell_start, int32_t *cell_boxes, int cell_cap, uint32_t *cell4, uint32_t *occ,
-                         int32_t *overflow, void *stream);
+                         float *grid_meta, int32_t *cell_start, int32_t *cell_boxes, int cell_cap, uint32_t *cell4, int max_boxes,
+                         uint32_t *occ, int32_t *overflow, void *stream);
 /* chunks: (n_chunks, 4) i32 rows [frame, first point in frame, n points, chunk index in frame];
  * hits: (n_chunks, 8, hit_cap) records of al3d_crop_hit_bytes() bytes, scratch (one ordered segment per warp of the
  * chunk's CTA: point index, box | rank << 16), n_hits (n_chunks, 8) i32;

@@ -78,6 +78,13 @@ def test_crop_ragged_batch_and_edge_cases():
     res = crop.crop_frames(points, boxes, poses, hit_cap=16384)
     assert int(res["overflow"].item()) == 0
     _check_against_oracle(points, boxes, poses, res)
+    # the chunk size is a scheduling choice: the largest chunks (what a 200-frame sweep runs with), odd ones and tiny ones
+    # give the same lists
+    for ch in (16384, 5000, 130):
+        alt = crop.crop_frames(points, boxes, poses, hit_cap=16384, chunk=ch)
+        assert int(alt["overflow"].item()) == 0
+        for k in ("indices", "offsets", "xyz", "xyz_global"):
+            assert np.array_equal(alt[k].cpu().numpy(), res[k].cpu().numpy(), equal_nan=k.startswith("xyz")), (ch, k)
     # NaN point is "inside" every box, exactly like the reference predicate
     off = res["offsets"].cpu().numpy(); idx = res["indices"].cpu().numpy()
     k = res["box_off"][5] + 3
@@ -90,7 +97,7 @@ def test_crop_overflow_is_reported():
     pts = rng.uniform(-0.5, 0.5, (4096, 3)).astype(np.float32)
     boxes = np.tile(np.array([[0, 0, 0, 4, 4, 4, 0.0]], np.float32), (10, 1))     # every point inside 10 boxes
     with pytest.raises(OverflowError):
-        crop.crop_frames([pts], [boxes], hit_cap=1024)                           # 512 points x 10 boxes per warp segment
+        crop.crop_frames([pts], [boxes], hit_cap=1024)                           # 256 points x 10 boxes per warp segment
     res = crop.crop_frames([pts], [boxes], [np.eye(4)], hit_cap=8192)             # enough room: no limit on boxes per point
     _check_against_oracle([pts], [boxes], [np.eye(4)], res)
 
@@ -210,3 +217,18 @@ def test_crop_infinite_points_and_irregular_boxes():
     _check_against_oracle([pts], [boxes], [np.eye(4)], res)
     m = crop.points_in_rbbox(pts, boxes)
     assert np.array_equal(m, ocrop.points_in_boxes(pts, boxes))
+
+
+@pytest.mark.gpu
+def test_crop_frames_with_many_boxes_use_the_global_tables():
+    """Up to 256 boxes per frame the hits kernel keeps the frame's box records and packed cell table in shared memory;
+    beyond that it reads them from global memory (8-byte cell entries).  Both must give the reference's lists -- also
+    in one batch, where the largest frame decides."""
+    rng = np.random.default_rng(21)
+    frames = synth.lidar_frames(2, n_points=40000, n_boxes=600, seed=6)
+    points = [f["points"] for f in frames] + [rng.normal(0, 8, (5000, 3)).astype(np.float32)]
+    boxes = [crop.detector_to_waymo(f["det_boxes"]) for f in frames] + [_random_boxes(rng, 7, spread=6.0)]
+    poses = [f["pose"] for f in frames] + [np.eye(4)]
+    res = crop.crop_frames(points, boxes, poses, hit_cap=16384)
+    assert int(res["overflow"].item()) == 0
+    _check_against_oracle(points, boxes, poses, res)
