@@ -258,10 +258,11 @@ __device__ __forceinline__ bool crop_inside(float px, float py, float pz, const 
 
 struct CropChunk { int32_t frame; int32_t first_pt; int32_t n_pts; int32_t chunk_in_frame; };
 
-// one hit: point index in its frame, box | rank << 16 (rank among the chunk's hits of that box).  (Carrying the point's
-// xyz in the record as well was measured: +60 us in the hits pass for the wider stores, nothing gained in the fill.)
-struct __align__(8) CropHit { int32_t idx, box_rank; };          // one 8-byte store per hit
-static_assert(sizeof(CropHit) == 8, "CropHit");
+// one hit = a 16-byte record (x, y, z, point index in its frame) + a 4-byte word box | rank << 16 (rank among the chunk's
+// hits of that box), kept in two arrays over the same slots: the ranking only touches the 4-byte words, and the
+// materialise pass reads the coordinates from the records (60 MB, written moments earlier) instead of gathering them
+// from the point cloud again -- a gather of 10 % of the points touches nearly every DRAM line of it (measured: 450 MB).
+constexpr int kCropHitBytes = 20;
 constexpr int kCropWarps = kCropThreads / 32;
 constexpr int kCropIter = 128;                            // points per warp iteration: point base + j * 32 + lane, j < 4
 constexpr int kCropCQ = 96;                               // per-warp candidate queue: < 32 carried over + <= 64 new (half an iteration)
@@ -333,7 +334,8 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                  const float *__restrict__ planes, const CropBoxLocal *__restrict__ local, const int64_t *__restrict__ box_off, int G,
                  const CropGridMeta *__restrict__ meta, const int32_t *__restrict__ cell_start,
                  const int32_t *__restrict__ cell_boxes, int cell_cap, const uint2 *__restrict__ cell4, const uint32_t *__restrict__ occ,
-                 const CropChunk *__restrict__ chunks, CropHit *__restrict__ hits, int hit_cap, int32_t *__restrict__ n_hits,
+                 const CropChunk *__restrict__ chunks, float4 *__restrict__ hits_xyz, int32_t *__restrict__ hits_br, int hit_cap,
+                 int32_t *__restrict__ n_hits,
                  int32_t *__restrict__ chunk_box_count, int max_boxes, int rank_boxes, int32_t *__restrict__ overflow)
 {
     // Each warp owns a run of CONSECUTIVE points of the chunk and streams it 128 points at a time (point = base + j * 32 +
@@ -393,7 +395,8 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     const unsigned lt_mask = (1u << lane) - 1u;
     float4 *cq = s_cq + wid * kCropCQ;
     float4 *pq = s_pq + wid * kCropPQ;
-    CropHit *stage = hits + ((int64_t)blockIdx.x * kCropWarps + wid) * hit_cap;
+    float4 *stage_xyz = hits_xyz + ((int64_t)blockIdx.x * kCropWarps + wid) * hit_cap;
+    int32_t *stage = hits_br + ((int64_t)blockIdx.x * kCropWarps + wid) * hit_cap;
     int wcount = 0, phead = 0, pcount = 0, cqn = 0;
 #ifdef CROP_ABLATE       // timing experiments only (scripts/gpu_r2_abl.sh): 1 prologue, 2 + filter, 3 + expand, 4 + test (no ranking)
     if (CROP_ABLATE == 1) return;
@@ -436,7 +439,11 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
             const bool fits = wcount + total <= stage_cap;
             if (!fits) { if (lane == 0) atomicExch(overflow, 3); }
             else {
-                if (hit) stage[wcount + __popc(hm & lt_mask)] = CropHit{ck.first_pt + pidx, box};
+                if (hit) {
+                    const int at = wcount + __popc(hm & lt_mask);
+                    stage_xyz[at] = make_float4(e.x, e.y, e.z, __int_as_float(ck.first_pt + pidx));
+                    stage[at] = box;
+                }
                 wcount += total;
             }
         }
@@ -620,9 +627,9 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
         for (int h0 = 0; h0 < wcount; h0 += 32) {
             const int h = h0 + lane;
             const bool act = h < wcount;
-            const int box = act ? stage[h].box_rank : -1 - lane;
+            const int box = act ? stage[h] : -1 - lane;
             const unsigned same = __match_any_sync(0xffffffffu, box);
-            if (act) stage[h].box_rank = box | ((mine[box] + __popc(same & ((1u << lane) - 1u))) << 16);
+            if (act) stage[h] = box | ((mine[box] + __popc(same & ((1u << lane) - 1u))) << 16);
             __syncwarp();
             if (act && (same >> lane) == 1u) mine[box] += __popc(same);          // highest lane of each group updates
             __syncwarp();
@@ -630,11 +637,11 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
         __syncthreads();
         if (wid > 0)
             for (int h = lane; h < wcount; h += 32) {
-                const int br = stage[h].box_rank;
+                const int br = stage[h];
                 const int box = br & 0xFFFF;
                 int prefix = 0;
                 for (int w = 0; w < wid; ++w) prefix += s_wcnt[w * rank_boxes + box];
-                if (prefix) stage[h].box_rank = br + (prefix << 16);
+                if (prefix) stage[h] = br + (prefix << 16);
             }
         for (int b = threadIdx.x; b < B; b += blockDim.x) {
             int sum = 0;
@@ -650,13 +657,13 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     if (wid == 0) {
         for (int w = 0; w < kCropWarps; ++w) {
             const int cnt = warp_total[w];
-            CropHit *l = hits + ((int64_t)blockIdx.x * kCropWarps + w) * hit_cap;
+            int32_t *l = hits_br + ((int64_t)blockIdx.x * kCropWarps + w) * hit_cap;
             for (int h0 = 0; h0 < cnt; h0 += 32) {
                 const int h = h0 + lane;
                 const bool act = h < cnt;
-                const int box = act ? l[h].box_rank : -1 - lane;
+                const int box = act ? l[h] : -1 - lane;
                 const unsigned same = __match_any_sync(0xffffffffu, box);
-                if (act) l[h].box_rank = box | ((s_box_cnt[box] + __popc(same & ((1u << lane) - 1u))) << 16);
+                if (act) l[h] = box | ((s_box_cnt[box] + __popc(same & ((1u << lane) - 1u))) << 16);
                 __syncwarp();
                 if (act && (same >> lane) == 1u) s_box_cnt[box] += __popc(same);  // highest lane of each group updates
                 __syncwarp();
@@ -723,39 +730,40 @@ crop_offsets_kernel(const int32_t *__restrict__ box_total, int64_t n_boxes, int6
 }
 
 __global__ void __launch_bounds__(kCropThreads)
-crop_fill_kernel(const int64_t *__restrict__ box_off, const CropChunk *__restrict__ chunks, const CropHit *__restrict__ hits,
-                 int hit_cap, const int32_t *__restrict__ n_hits, const int32_t *__restrict__ chunk_box_count, int max_boxes,
-                 const int64_t *__restrict__ offsets, int64_t capacity, int32_t *__restrict__ out_idx, int32_t *__restrict__ overflow)
+crop_fill_kernel(const int64_t *__restrict__ box_off, const CropChunk *__restrict__ chunks, const float4 *__restrict__ hits_xyz,
+                 const int32_t *__restrict__ hits_br, int hit_cap, const int32_t *__restrict__ n_hits,
+                 const int32_t *__restrict__ chunk_box_count, int max_boxes, const int64_t *__restrict__ offsets, int64_t capacity,
+                 int write_slots, int32_t *__restrict__ out_idx, int32_t *__restrict__ overflow)
 {
     // destination of a hit = global offset of its box + hits of that box in earlier chunks of the frame + rank in this chunk.
-    // Only the 4-byte point index is scattered here; the coordinates are gathered by crop_materialise_kernel, which writes
-    // every box's list front to back (seven scattered stores per hit in this kernel were what bounded it).
+    // Only four bytes are scattered here: the hit's SLOT when crop_materialise_kernel follows (it writes every box's list
+    // front to back from the hit records; seven scattered stores per hit in this kernel were what bounded it), the point
+    // index itself when only the index lists are wanted.
     const CropChunk ck = chunks[blockIdx.x];
     const int64_t b0 = box_off[ck.frame];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = min(n_hits[(int64_t)blockIdx.x * kCropWarps + wid], hit_cap);          // this warp's segment
-    const CropHit *my_hits = hits + ((int64_t)blockIdx.x * kCropWarps + wid) * hit_cap;
+    const int64_t seg = ((int64_t)blockIdx.x * kCropWarps + wid) * hit_cap;
     for (int h = lane; h < total; h += 32) {
-        const CropHit hr = my_hits[h];
-        const int box = hr.box_rank & 0xFFFF;
-        const int64_t dst = offsets[b0 + box] + chunk_box_count[(int64_t)blockIdx.x * max_boxes + box] + (hr.box_rank >> 16);
+        const int br = hits_br[seg + h];
+        const int box = br & 0xFFFF;
+        const int64_t dst = offsets[b0 + box] + chunk_box_count[(int64_t)blockIdx.x * max_boxes + box] + (br >> 16);
         if (dst >= capacity) { atomicExch(overflow, 4); continue; }
-        out_idx[dst] = hr.idx;
+        out_idx[dst] = write_slots ? (int32_t)(seg + h) : __float_as_int(hits_xyz[seg + h].w);
     }
 }
 
-// one warp per (frame, box): out_xyz[k] = points[idx[k]] and out_xyz_global[k] = pose_f [x y z 1] for the box's index list,
-// written front to back (coalesced); waymo_common.py:169-171.
+// one warp per (frame, box), front to back (coalesced stores): idx[k] holds the slot of the k-th hit; its record gives
+// idx[k] = point index, out_xyz[k] = the point and out_xyz_global[k] = pose_f [x y z 1]; waymo_common.py:169-171.
 __global__ void __launch_bounds__(256)
-crop_materialise_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
-                        const int64_t *__restrict__ box_off, const int64_t *__restrict__ offsets, const double *__restrict__ poses,
-                        int64_t capacity, const int32_t *__restrict__ idx, float *__restrict__ out_xyz, double *__restrict__ out_xyz_global)
+crop_materialise_kernel(const float4 *__restrict__ hits_xyz, const int64_t *__restrict__ box_off, const int64_t *__restrict__ offsets,
+                        const double *__restrict__ poses, int64_t capacity, int32_t *__restrict__ idx, float *__restrict__ out_xyz,
+                        double *__restrict__ out_xyz_global)
 {
     const int f = blockIdx.x;
     const int64_t b0 = box_off[f];
     const int B = (int)(box_off[f + 1] - b0);
     const int lane = threadIdx.x & 31;
-    const float *fpts = points + pt_off[f] * pt_stride;
     const double *P = poses ? poses + (int64_t)f * 16 : nullptr;
     double Pm[12];
     if (P) {
@@ -765,14 +773,14 @@ crop_materialise_kernel(const float *__restrict__ points, int64_t pt_stride, con
     for (int b = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += gridDim.y * (blockDim.x >> 5)) {
         const int64_t lo = offsets[b0 + b], hi = min(offsets[b0 + b + 1], capacity);
         for (int64_t k = lo + lane; k < hi; k += 32) {
-            const float *q = fpts + (int64_t)idx[k] * pt_stride;
-            const float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
-            if (out_xyz) { out_xyz[k * 3] = x; out_xyz[k * 3 + 1] = y; out_xyz[k * 3 + 2] = z; }
+            const float4 r = __ldg(hits_xyz + idx[k]);
+            idx[k] = __float_as_int(r.w);
+            if (out_xyz) { out_xyz[k * 3] = r.x; out_xyz[k * 3 + 1] = r.y; out_xyz[k * 3 + 2] = r.z; }
             if (out_xyz_global && P) {
-                const double dx = x, dy = y, dz = z;
+                const double dx = r.x, dy = r.y, dz = r.z;
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
-                    out_xyz_global[k * 3 + r] = ((Pm[r * 4] * dx + Pm[r * 4 + 1] * dy) + Pm[r * 4 + 2] * dz) + Pm[r * 4 + 3];
+                for (int q = 0; q < 3; ++q)
+                    out_xyz_global[k * 3 + q] = ((Pm[q * 4] * dx + Pm[q * 4 + 1] * dy) + Pm[q * 4 + 2] * dz) + Pm[q * 4 + 3];
             }
         }
     }
@@ -855,8 +863,9 @@ extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int6
     AL3D_CHECK_ARG(pt_stride >= 3, "al3d_crop_hits: pt_stride=%lld", (long long)pt_stride);
     AL3D_CHECK_ARG(max_boxes >= 1 && max_boxes <= 12288, "al3d_crop_hits: max_boxes=%d not in [1,12288]", max_boxes);
     AL3D_CHECK_ARG(hit_cap >= 1 && hit_cap <= (1 << 20), "al3d_crop_hits: hit_cap=%d not in [1, 2^20]", hit_cap);
-    AL3D_CHECK_ARG((reinterpret_cast<uintptr_t>(local) & 15) == 0 && (reinterpret_cast<uintptr_t>(cell4) & 7) == 0,
-                   "al3d_crop_hits: local / cell4 misaligned");
+    AL3D_CHECK_ARG((reinterpret_cast<uintptr_t>(local) & 15) == 0 && (reinterpret_cast<uintptr_t>(cell4) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(hits) & 15) == 0, "al3d_crop_hits: local / cell4 / hits misaligned");
+    AL3D_CHECK_ARG((int64_t)n_chunks * kCropWarps * hit_cap < (int64_t)1 << 31, "al3d_crop_hits: more than 2^31 hit slots");
     if (n_chunks <= 0) return 0;
     const int rank_boxes = max_boxes <= 512 ? max_boxes : 0;          // per-warp box counters for the parallel ranking, if modest
     const bool loc_smem = max_boxes <= kLocSmemBoxes;                 // must agree with the format al3d_crop_build_grid chose
@@ -870,7 +879,8 @@ extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int6
     kern<<<n_chunks, kCropThreads, smem, (cudaStream_t)stream>>>(
         points, pt_stride, pt_off, planes, reinterpret_cast<const CropBoxLocal *>(local), box_off, G,
         reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap, reinterpret_cast<const uint2 *>(cell4), occ,
-        reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<CropHit *>(hits), hit_cap, n_hits, chunk_box_count, max_boxes,
+        reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<float4 *>(hits),
+        reinterpret_cast<int32_t *>(reinterpret_cast<float4 *>(hits) + (int64_t)n_chunks * kCropWarps * hit_cap), hit_cap, n_hits, chunk_box_count, max_boxes,
         rank_boxes, overflow);
     AL3D_CHECK_LAUNCH("crop_hits_kernel");
     return 0;
@@ -889,7 +899,7 @@ extern "C" int al3d_crop_scan(const int64_t *box_off, const int64_t *frame_chunk
     return 0;
 }
 
-extern "C" int al3d_crop_hit_bytes(void) { return (int)sizeof(CropHit); }
+extern "C" int al3d_crop_hit_bytes(void) { return kCropHitBytes; }
 
 extern "C" int al3d_crop_fill(const float *points, int64_t pt_stride, const int64_t *pt_off, const int64_t *box_off, int n_frames,
                               const int32_t *chunks, int n_chunks, const void *hits, int hit_cap, const int32_t *n_hits,
@@ -901,13 +911,17 @@ extern "C" int al3d_crop_fill(const float *points, int64_t pt_stride, const int6
                    "al3d_crop_fill: null pointer");
     if (n_chunks <= 0 || n_frames <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    crop_fill_kernel<<<n_chunks, kCropThreads, 0, st>>>(box_off, reinterpret_cast<const CropChunk *>(chunks),
-                                                        reinterpret_cast<const CropHit *>(hits), hit_cap, n_hits, chunk_box_count, max_boxes,
-                                                        offsets, capacity, out_idx, overflow);
+    AL3D_CHECK_ARG((reinterpret_cast<uintptr_t>(hits) & 15) == 0, "al3d_crop_fill: hits must be 16-byte aligned");
+    AL3D_CHECK_ARG((int64_t)n_chunks * kCropWarps * hit_cap < (int64_t)1 << 31, "al3d_crop_fill: more than 2^31 hit slots");
+    const float4 *hx = reinterpret_cast<const float4 *>(hits);
+    const int32_t *hb = reinterpret_cast<const int32_t *>(hx + (int64_t)n_chunks * kCropWarps * hit_cap);
+    const bool materialise = out_xyz || (out_xyz_global && poses);
+    crop_fill_kernel<<<n_chunks, kCropThreads, 0, st>>>(box_off, reinterpret_cast<const CropChunk *>(chunks), hx, hb, hit_cap, n_hits,
+                                                        chunk_box_count, max_boxes, offsets, capacity, materialise ? 1 : 0, out_idx, overflow);
     AL3D_CHECK_LAUNCH("crop_fill_kernel");
-    if (out_xyz || (out_xyz_global && poses)) {
+    if (materialise) {
         crop_materialise_kernel<<<dim3(n_frames, (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(max_boxes, 8), 16))), 256, 0, st>>>(
-            points, pt_stride, pt_off, box_off, offsets, poses, capacity, out_idx, out_xyz, out_xyz_global);
+            hx, box_off, offsets, poses, capacity, out_idx, out_xyz, out_xyz_global);
         AL3D_CHECK_LAUNCH("crop_materialise_kernel");
     }
     return 0;

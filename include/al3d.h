@@ -162,8 +162,9 @@ int al3d_crop_build_grid(const float *aabb, const float *boxes, const float *sin
                          float *grid_meta, int32_t *cell_start, int32_t *cell_boxes, int cell_cap, uint32_t *cell4, int max_boxes,
                          uint32_t *occ, int32_t *overflow, void *stream);
 /* chunks: (n_chunks, 4) i32 rows [frame, first point in frame, n points, chunk index in frame];
- * hits: (n_chunks, 8, hit_cap) records of al3d_crop_hit_bytes() bytes, scratch (one ordered segment per warp of the
- * chunk's CTA: point index, box | rank << 16), n_hits (n_chunks, 8) i32;
+ * hits: scratch of n_chunks * 8 * hit_cap slots of al3d_crop_hit_bytes() bytes, 16-byte aligned (one ordered segment per
+ * warp of the chunk's CTA; stored as an array of 16-byte records x y z | point index followed by an array of 4-byte
+ * words box | rank << 16), n_hits (n_chunks, 8) i32;
  * chunk_box_count: (n_chunks, max_boxes) i32 scratch. */
 int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
                    const float *local, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
