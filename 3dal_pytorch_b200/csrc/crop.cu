@@ -25,7 +25,15 @@ namespace al3d {
 
 constexpr int kCropChunk = 16384;      // most points one CTA of the hits kernel takes (the caller may cut smaller chunks)
 constexpr int kCropThreads = 256;
-constexpr int kGridThreads = 1024;    // crop_grid_kernel: one CTA per frame
+// measured on the 200-frame sweep (bands x threads): 1 x 256 0.067 ms, 1 x 1024 0.050, 4 x 256 0.067, 2 x 512 0.044, 8 x 128 0.145
+#ifndef CROP_GRID_THREADS
+#define CROP_GRID_THREADS 512
+#endif
+#ifndef CROP_GRID_BANDS
+#define CROP_GRID_BANDS 2
+#endif
+constexpr int kGridThreads = CROP_GRID_THREADS;
+constexpr int kGridBands = CROP_GRID_BANDS;          // crop_grid_kernel: CTAs per frame, each owns a band of rows of both grids
 constexpr int kOccRes = 256;           // fine occupancy bitmap per frame: kOccRes x kOccRes bits (8 KB)
 constexpr int kOccWords = kOccRes * kOccRes / 32;
 
@@ -52,7 +60,16 @@ crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes
                  int32_t *__restrict__ cell_boxes, int cell_cap, uint2 *__restrict__ cell4, int packed32, uint32_t *__restrict__ occ,
                  int32_t *__restrict__ overflow)
 {
-    extern __shared__ int32_t s_cnt[];            // G*G counts -> exclusive offsets; then G*G fill cursors; then the occupancy bitmap
+    // A frame is built by kGridBands CTAs.  Each of them repeats the cheap, global parts (extent of the boxes, per-cell counts,
+    // exclusive scan: ~12 shared-memory atomics per box and 4096 cells) and does the other parts -- rasterising the fine
+    // bitmap, filling / sorting / packing the cell lists -- only for its own band of rows, so that 200 frames make 400 CTAs
+    // that are all resident at once instead of 200 long ones on 148 SMs (two waves).
+    extern __shared__ int32_t s_cnt[];            // G*G counts -> exclusive offsets; then G*G fill cursors; then the band of the occupancy bitmap
+    const int band = blockIdx.y;
+    const int fr0 = band * (kOccRes / kGridBands), fr1 = fr0 + kOccRes / kGridBands - 1;          // fine rows of this band
+    const int gpb = (G + kGridBands - 1) / kGridBands;
+    const int gr0 = band * gpb, gr1 = min(G, gr0 + gpb) - 1;                                      // coarse rows of this band
+    constexpr int kBandWords = kOccWords / kGridBands;
     __shared__ float red[6][kGridThreads / 32];
     __shared__ int32_t s_warp[kGridThreads / 32];
     const int f = blockIdx.x;
@@ -75,7 +92,7 @@ crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) { red[0][wid] = xmin; red[1][wid] = ymin; red[2][wid] = xmax; red[3][wid] = ymax; red[4][wid] = zmin; red[5][wid] = zmax; }
     uint32_t *s_occ = reinterpret_cast<uint32_t *>(s_cnt + 2 * cells);
-    for (int c = threadIdx.x; c < 2 * cells + kOccWords; c += blockDim.x) s_cnt[c] = 0;
+    for (int c = threadIdx.x; c < 2 * cells + kBandWords; c += blockDim.x) s_cnt[c] = 0;
     __syncthreads();
     for (int w = 0; w < kGridThreads / 32; ++w) {
         xmin = fminf(xmin, red[0][w]); ymin = fminf(ymin, red[1][w]);
@@ -96,7 +113,7 @@ crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes
         m.zmin = zmin; m.zmax = zmax;
         fsx = 1.f / m.inv_fx; fsy = 1.f / m.inv_fy;
     }
-    if (threadIdx.x == 0) meta[f] = m;
+    if (threadIdx.x == 0 && band == 0) meta[f] = m;
     // ---- fine occupancy bitmap: a bit is set if the cell can contain a point of some box.  Conservative: the cell
     //      centre lies inside the box footprint grown by the cell's half diagonal plus the rectangle padding (which
     //      already exceeds the rounding slack of the exact test by orders of magnitude) plus 1 cm.
@@ -111,14 +128,14 @@ crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes
             // |l|, |w|: two negative dimensions mirror the box onto itself, and the reference then still finds points inside
             const float hl = 0.5f * fabsf(bx[3]) + fmaxf(grow, hd + 0.06f), hw = 0.5f * fabsf(bx[4]) + fmaxf(grow, hd + 0.06f);
             const int cx0 = max(crop_cell(a[0], m.x0, m.inv_fx, kOccRes), 0), cx1 = min(crop_cell(a[3], m.x0, m.inv_fx, kOccRes), kOccRes - 1);
-            const int cy0 = max(crop_cell(a[1], m.y0, m.inv_fy, kOccRes), 0), cy1 = min(crop_cell(a[4], m.y0, m.inv_fy, kOccRes), kOccRes - 1);
+            const int cy0 = max(crop_cell(a[1], m.y0, m.inv_fy, kOccRes), fr0), cy1 = min(crop_cell(a[4], m.y0, m.inv_fy, kOccRes), fr1);
             const int ncx = cx1 - cx0 + 1, n = ncx > 0 && cy1 >= cy0 ? ncx * (cy1 - cy0 + 1) : 0;
             for (int t = lane; t < n; t += 32) {
                 const int cy = cy0 + t / ncx, cx = cx0 + t % ncx;
                 const float dx = m.x0 + ((float)cx + 0.5f) * fsx - bx[0], dy = m.y0 + ((float)cy + 0.5f) * fsy - bx[1];
                 // world = [[c, s], [-s, c]] local  (rotation_3d_in_axis)  ->  local = [[c, -s], [s, c]] world
                 const float lx = dx * cs - dy * sn, ly = dx * sn + dy * cs;
-                if (fabsf(lx) <= hl && fabsf(ly) <= hw) atomicOr(&s_occ[(cy * kOccRes + cx) >> 5], 1u << ((cy * kOccRes + cx) & 31));
+                if (fabsf(lx) <= hl && fabsf(ly) <= hw) atomicOr(&s_occ[((cy - fr0) * kOccRes + cx) >> 5], 1u << (cx & 31));
             }
         }
     }
@@ -131,6 +148,7 @@ crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes
             int x0c = crop_cell(a[0], m.x0, m.inv_x, G), x1c = crop_cell(a[3], m.x0, m.inv_x, G);
             int y0c = crop_cell(a[1], m.y0, m.inv_y, G), y1c = crop_cell(a[4], m.y0, m.inv_y, G);
             x0c = max(x0c, 0); y0c = max(y0c, 0); x1c = min(x1c, G - 1); y1c = min(y1c, G - 1);
+            if (pass == 1) { y0c = max(y0c, gr0); y1c = min(y1c, gr1); }      // lists: only the rows of this band
             for (int cy = y0c; cy <= y1c; ++cy)
                 for (int cx = x0c; cx <= x1c; ++cx) {
                     const int c = cy * G + cx;
@@ -158,24 +176,42 @@ crop_grid_kernel(const float *__restrict__ aabb, const float *__restrict__ boxes
             __syncthreads();
             int total = 0;
             for (int w = 0; w < kGridThreads / 32; ++w) total += s_warp[w];
-            if (threadIdx.x == 0) {
+            if (threadIdx.x == 0 && band == 0) {
                 cell_start[(int64_t)f * (cells + 1) + cells] = total;
                 if (total > cell_cap) atomicExch(overflow, 1);
             }
-            for (int c = threadIdx.x; c < cells; c += blockDim.x) cell_start[(int64_t)f * (cells + 1) + c] = s_cnt[c];
+            if (gr0 <= gr1)
+                for (int c = gr0 * G + threadIdx.x; c < (gr1 + 1) * G; c += blockDim.x) cell_start[(int64_t)f * (cells + 1) + c] = s_cnt[c];
         }
     }
-    if (occ != nullptr) for (int w = threadIdx.x; w < kOccWords; w += blockDim.x) occ[(int64_t)f * kOccWords + w] = s_occ[w];
+    if (occ != nullptr) for (int w = threadIdx.x; w < kBandWords; w += blockDim.x) occ[(int64_t)f * kOccWords + band * kBandWords + w] = s_occ[w];
     // ---- sort every cell's list (a handful of entries): insertion sort by one thread per cell
     __threadfence_block();
-    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+    for (int c = gr0 * G + threadIdx.x; c < (gr1 + 1) * G; c += blockDim.x) {
         const int lo = s_cnt[c], n = min(s_cur[c], max(cell_cap - lo, 0));
         int32_t *l = cell_boxes + (int64_t)f * cell_cap + lo;
-        for (int i = 1; i < n; ++i) {
-            const int v = l[i];
-            int j = i - 1;
-            while (j >= 0 && l[j] > v) { l[j + 1] = l[j]; --j; }
-            l[j + 1] = v;
+        if (n <= 8) {
+            // the usual case, in registers: one round trip to read the list and one to write it (sorting it in place in
+            // global memory is a chain of dependent L2 accesses -- it was most of this kernel's time)
+            int v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = k < n ? l[k] : 0x7fffffff;
+#pragma unroll
+            for (int i = 1; i < 8; ++i)
+#pragma unroll
+                for (int j = i; j > 0; --j) {
+                    const int a = min(v[j - 1], v[j]), b = max(v[j - 1], v[j]);
+                    v[j - 1] = a; v[j] = b;
+                }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (k < n) l[k] = v[k];
+        } else {
+            for (int i = 1; i < n; ++i) {
+                const int v = l[i];
+                int j = i - 1;
+                while (j >= 0 && l[j] > v) { l[j + 1] = l[j]; --j; }
+                l[j + 1] = v;
+            }
         }
         // packed entry of the cell for the hits kernel: up to three box ids in one 8-byte word (id0 | id1 << 16,
         // id2 | count << 16); count = 0xFFFF sends the reader to the CSR list (longer or truncated lists)
@@ -847,8 +883,8 @@ extern "C" int al3d_crop_build_grid(const float *aabb, const float *boxes, const
     AL3D_CHECK_ARG(!occ || (boxes && sincos), "al3d_crop_build_grid: the occupancy bitmap needs boxes and sincos");
     AL3D_CHECK_ARG(G >= 1 && G <= 64, "al3d_crop_build_grid: G=%d not in [1,64]", G);
     if (n_frames <= 0) return 0;
-    const size_t smem = (size_t)(2 * G * G + kOccWords) * sizeof(int32_t);
-    crop_grid_kernel<<<n_frames, kGridThreads, smem, (cudaStream_t)stream>>>(
+    const size_t smem = (size_t)(2 * G * G + kOccWords / kGridBands) * sizeof(int32_t);
+    crop_grid_kernel<<<dim3(n_frames, kGridBands), kGridThreads, smem, (cudaStream_t)stream>>>(
         aabb, boxes, sincos, box_off, G, reinterpret_cast<CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap,
         reinterpret_cast<uint2 *>(cell4), kC4Smem && max_boxes <= kLocSmemBoxes, occ, overflow);
     AL3D_CHECK_LAUNCH("crop_grid_kernel");
