@@ -349,15 +349,35 @@ __global__ void crop_box_local_kernel(const float *__restrict__ boxes, const flo
     local[b] = o;
 }
 
+// TMA staging of the points (one 1536-byte bulk copy per warp iteration, completion on an mbarrier of the warp's own)
+__device__ __forceinline__ uint32_t crop_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void crop_mbar_init(uint64_t *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(crop_smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void crop_bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the generic-proxy reads of the buffer come before the copy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(crop_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(crop_smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(crop_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void crop_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(crop_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 // NaN / infinite (or absurdly large) coordinate: the reference's float32 arithmetic decides (a NaN sign never rejects, so
 // a NaN point is inside every box; inf * 0 products do the same for some boxes) -> exact predicate against EVERY box
 __device__ __forceinline__ bool crop_weird(float x, float y, float z) { return !(fabsf(x) + fabsf(y) + fabsf(z) < 1e18f); }
 
 #ifndef CROP_MINB
 #define CROP_MINB 3
-#endif
-#ifndef CROP_PREFETCH
-#define CROP_PREFETCH 0
 #endif
 #ifdef CROP_STATS
 // diagnostic build only (scripts/gpu_r2_w.sh): [0] candidates, [1] pairs, [2] expand batches, [3] serial expand batches,
@@ -393,7 +413,9 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     extern __shared__ float4 s_dyn4[];
     float4 *s_cq = s_dyn4;                                             // kCropWarps x kCropCQ
     float4 *s_pq = s_cq + kCropWarps * kCropCQ;                        // kCropWarps x kCropPQ
-    float4 *s_loc = s_pq + kCropWarps * kCropPQ;                       // kSmemTables: the frame's box records (3 x 16 B each)
+    float *s_pt = reinterpret_cast<float *>(s_pq + kCropWarps * kCropPQ);    // kCropWarps x 384 floats: the points of one warp iteration (TMA)
+    float4 *s_loc = reinterpret_cast<float4 *>(s_pt + kCropWarps * kCropIter * 3);   // kSmemTables: the frame's box records (3 x 16 B each)
+    __shared__ __align__(8) uint64_t s_bar[kCropWarps];
     uint32_t *s_c4 = reinterpret_cast<uint32_t *>(s_loc + (kSmemTables ? 3 * max_boxes : 0));   // kSmemTables && kC4Smem: packed cell entries (G x G)
     uint32_t *s_occ = s_c4 + (kSmemTables && kC4Smem ? G * G : 0);    // kOccWords
     int32_t *s_box_cnt = reinterpret_cast<int32_t *>(s_occ + kOccWords);           // per-box hit counters (max_boxes)
@@ -591,8 +613,30 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     const int ps = (int)pt_stride;
     const float ofx = -m.x0 * m.inv_fx, ofy = -m.y0 * m.inv_fy;      // fine cell = floor(x * inv + of): the bitmap is conservative
     const bool any_box = B > 0;                                       // by centimetres, so this need not be crop_cell's rounding
-    auto load = [&](int base, float (&px)[4], float (&py)[4], float (&pz)[4]) {
-        if (base + kCropIter <= w_hi && ps == 3) {
+    // Full iterations of contiguous xyz points whose run starts on a 16-byte boundary arrive by TMA: lane 0 requests the
+    // next 1536 bytes as soon as the warp has copied the current ones to registers, so the copy is in flight during the
+    // whole iteration, costs no load instructions and no L1 wavefronts, and the twelve shared-memory reads at a stride of
+    // three words are conflict-free.  Anything else (strided points, odd alignment, the tail of a run) uses plain loads.
+    float *buf = s_pt + wid * (kCropIter * 3);
+    uint64_t *bar = s_bar + wid;
+    const bool tma_ok = ps == 3 && (reinterpret_cast<uintptr_t>(pts + (int64_t)w_lo * 3) & 15) == 0;
+    uint32_t tma_phase = 0;
+    if (lane == 0) {
+        crop_mbar_init(bar);
+        if (tma_ok && w_lo + kCropIter <= w_hi) crop_bulk_load(buf, pts + (int64_t)w_lo * 3, kCropIter * 12, bar);
+    }
+    __syncwarp();
+    for (int base = w_lo; base < w_hi; base += kCropIter) {
+        const bool full = base + kCropIter <= w_hi;
+        float px[4], py[4], pz[4];
+        if (full && tma_ok) {
+            crop_mbar_wait(bar, tma_phase);
+            tma_phase ^= 1u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { px[j] = buf[(j * 32 + lane) * 3]; py[j] = buf[(j * 32 + lane) * 3 + 1]; pz[j] = buf[(j * 32 + lane) * 3 + 2]; }
+            __syncwarp();
+            if (lane == 0 && base + 2 * kCropIter <= w_hi) crop_bulk_load(buf, pts + (int64_t)(base + kCropIter) * 3, kCropIter * 12, bar);
+        } else if (full && ps == 3) {
             const float *q = pts + (base + lane) * 3;                  // 12-byte stride: immediate offsets, any alignment
 #pragma unroll
             for (int j = 0; j < 4; ++j) { px[j] = __ldg(q + j * 96); py[j] = __ldg(q + j * 96 + 1); pz[j] = __ldg(q + j * 96 + 2); }
@@ -603,17 +647,6 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                 px[j] = __ldg(q); py[j] = __ldg(q + 1); pz[j] = __ldg(q + 2);
             }
         }
-    };
-    float px[4], py[4], pz[4];
-    if (w_lo < w_hi) load(w_lo, px, py, pz);
-    for (int base = w_lo; base < w_hi; base += kCropIter) {
-        const bool full = base + kCropIter <= w_hi;
-#if CROP_PREFETCH
-        // the next iteration's points are requested before this iteration's are looked at (registers are there: shared
-        // memory, not the register file, limits the CTAs per SM)
-        float nx[4], ny[4], nz[4];
-        if (base + kCropIter < w_hi) load(base + kCropIter, nx, ny, nz);
-#endif
         // (Requesting a survivor's coarse cell entry here, right after its filter, and queueing it behind the four filters was
         // measured: four sparse L2 round trips per iteration instead of 0.7 dense ones, hits pass 0.25 -> 0.30 ms.)
 #pragma unroll
@@ -649,12 +682,6 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
                 __syncwarp();
             }
         }
-#if CROP_PREFETCH
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { px[j] = nx[j]; py[j] = ny[j]; pz[j] = nz[j]; }
-#else
-        if (base + kCropIter < w_hi) load(base + kCropIter, px, py, pz);
-#endif
     }
     if (cqn > 0) expand(0, cqn);
     while (pcount > 0) test(min(pcount, 32));
@@ -908,7 +935,7 @@ extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int6
     if (n_chunks <= 0) return 0;
     const int rank_boxes = max_boxes <= 512 ? max_boxes : 0;          // per-warp box counters for the parallel ranking, if modest
     const bool loc_smem = max_boxes <= kLocSmemBoxes;                 // must agree with the format al3d_crop_build_grid chose
-    const size_t smem = (size_t)kCropWarps * (kCropCQ + kCropPQ) * sizeof(float4) +
+    const size_t smem = (size_t)kCropWarps * (kCropCQ + kCropPQ) * sizeof(float4) + (size_t)kCropWarps * kCropIter * 12 +
                         (loc_smem ? (size_t)max_boxes * sizeof(CropBoxLocal) + (kC4Smem ? (size_t)G * G * sizeof(uint32_t) : 0) : 0) +
                         (size_t)kOccWords * sizeof(uint32_t) + (size_t)((max_boxes + 3) & ~3) * sizeof(int32_t) +
                         (size_t)kCropWarps * rank_boxes * sizeof(int32_t);
