@@ -9,6 +9,8 @@ geometry.py:351-377): it is 6x4 floats per box, and it keeps numpy's float32 sin
 device predicate sees bit-identical plane equations.  The N x B point tests, the ordered compaction,
 the gather and the float64 pose transform run in libal3d.so.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -171,8 +173,12 @@ class CropPlan:
         """Points per work chunk (one CTA of the hits kernel): as large as the kernel takes (the per-CTA set-up and the
         ranking of its hits are amortised over the chunk) while the job still fills every SM several times over."""
         most = _lib.lib().al3d_crop_chunk_points()
+        if os.environ.get("AL3D_CROP_CHUNK"):                # tuning experiments (scripts/gpu_r2_v2.sh)
+            return int(min(most, max(1, int(os.environ["AL3D_CROP_CHUNK"]))))
         want = int(total_points) // 1184                     # 148 SMs x 4 resident CTAs x 2
-        return int(min(most, max(2048, want // 1024 * 1024)))
+        # measured on the 200-frame sweep (ms per sweep): 4096 0.483, 8192 0.421, 12288 0.403, 16384 0.389, 20480 0.391,
+        # 24576 0.396, 32768 0.403 (fewer, longer CTAs: the last wave is emptier)
+        return int(min(most, 16384, max(2048, want // 1024 * 1024)))
 
     def _alloc_outputs(self, capacity):
         dev = self.dev
