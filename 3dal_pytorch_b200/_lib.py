@@ -32,9 +32,9 @@ _SIGNATURES = {
     "al3d_crop_occ_words": [],
     "al3d_crop_box_local": [_vp, _vp, _i64, _vp, _vp],
     "al3d_crop_build_grid": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp],
-    "al3d_crop_hits": [_vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp],
+    "al3d_crop_hits": [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp],
     "al3d_crop_scan": [_vp, _vp, _i, _i64, _vp, _i, _vp, _vp, _vp],
-    "al3d_crop_fill": [_vp, _i64, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "al3d_crop_fill": [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "al3d_crop_hit_bytes": [],
     "al3d_crop_dense_mask": [_vp, _vp, _i, _vp, _vp],
     "al3d_track_points_prep": [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],

@@ -86,6 +86,56 @@ def _check_overflow(flag, what):
         raise OverflowError("crop %s: %s (code %d)" % (what, names.get(code, "?"), code))
 
 
+_TORCH_OF = {np.dtype(np.int64): torch.int64, np.dtype(np.int32): torch.int32, np.dtype(np.float32): torch.float32,
+             np.dtype(np.float64): torch.float64}
+
+
+def _upload(dev, arrays):
+    """One host -> device copy for a set of small numpy tables: dict name -> array (or None) in, dict name -> device tensor
+    (a view of one buffer, every table 16-byte aligned) out."""
+    off, total = {}, 0
+    for k, a in arrays.items():
+        if a is None:
+            continue
+        arrays[k] = a = np.ascontiguousarray(a)
+        off[k] = total
+        total += (a.nbytes + 15) // 16 * 16
+    buf = np.zeros((max(total, 16),), np.uint8)
+    for k, o in off.items():
+        buf[o:o + arrays[k].nbytes] = arrays[k].reshape(-1).view(np.uint8)
+    d = torch.from_numpy(buf).to(dev)
+    out = {}
+    for k, a in arrays.items():
+        out[k] = None if a is None else d[off[k]:off[k] + a.nbytes].view(_TORCH_OF[a.dtype]).view(a.shape)
+    return out
+
+
+def cell_cap_bound(boxes, box_off, G):
+    """Upper bound on the entries of one frame's coarse cell -> box lists (crop_grid_kernel), from the boxes alone.
+    A box whose padded rectangle is at most 2 r wide spans at most floor(2 r / cell) + 2 cells per axis, at most G; the
+    frame's cell size is its extent / G and the extent is at least the spread of the box centres.  r is taken per FRAME
+    (its largest box): a few reductions over the boxes, loose by the ratio of the largest to the typical box."""
+    boxes = np.asarray(boxes, dtype=np.float32).reshape(-1, 7)
+    nb = np.diff(np.asarray(box_off))
+    if boxes.shape[0] == 0:
+        return 1
+    with np.errstate(all="ignore"):
+        start = np.asarray(box_off)[:-1][nb > 0]             # strictly increasing: reduceat is exact
+        x, y = boxes[:, 0], boxes[:, 1]
+        xmin, xmax = np.minimum.reduceat(x, start), np.maximum.reduceat(x, start)
+        ymin, ymax = np.minimum.reduceat(y, start), np.maximum.reduceat(y, start)
+        # half diagonal <= (|l| + |w|) / 2; padding = AABB_PAD + 1e-5 max|corner| in the kernel, taken generously here
+        r = 0.5 * np.maximum.reduceat(np.abs(boxes[:, 3]) + np.abs(boxes[:, 4]), start).astype(np.float64)
+        r = r + 2 * AABB_PAD + 1e-4 * (np.maximum(np.abs(xmin), np.abs(xmax)) + np.maximum(np.abs(ymin), np.abs(ymax)) + r)
+        ex = np.maximum((xmax - xmin).astype(np.float64), 1e-3)
+        ey = np.maximum((ymax - ymin).astype(np.float64), 1e-3)
+        nx, ny = np.floor(2 * r * G / ex) + 2, np.floor(2 * r * G / ey) + 2
+        nx = np.where(nx >= 1, np.minimum(nx, G), G)         # NaN / inf / negative: the whole axis
+        ny = np.where(ny >= 1, np.minimum(ny, G), G)
+        per_frame = nb[nb > 0] * nx * ny
+    return int(max(per_frame.max(), 1))
+
+
 class CropPlan:
     """Device-resident state of a batch crop: inputs uploaded, scratch allocated.  ``run()`` only launches the
     kernels (grid build -> hits -> scan -> fill), so it can be timed / replayed without host work."""
@@ -93,34 +143,46 @@ class CropPlan:
     def __init__(self, points, boxes, poses=None, device="cuda", want_xyz=True, hit_cap=None, chunk=None):
         lib = _lib.lib()
         dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.dev, self.want_xyz = dev, want_xyz
         F = self.F = len(points)
-        pts_t = [torch.as_tensor(p, dtype=torch.float32).to(dev) for p in points]
-        self.pts_all = torch.cat([p[:, :3].contiguous() for p in pts_t], 0) if F else torch.zeros((0, 3), device=dev)
-        n_pts = [int(p.shape[0]) for p in pts_t]
+        # ---- points.  Frames that already live on the device as contiguous (N, >=3) float32 tensors of one row width are
+        #      used where they lie (the kernels take a table of frame pointers); anything else is packed into (sum N, 3) on
+        #      the host and uploaded in one copy.
+        in_place = F > 0 and all(isinstance(p, torch.Tensor) and p.is_cuda and p.device.index == dev.index and p.dtype == torch.float32
+                                 and p.dim() == 2 and p.shape[1] >= 3 and p.is_contiguous() for p in points) \
+            and len({int(p.shape[1]) for p in points}) == 1
+        n_pts = [int(p.shape[0]) for p in points]
         pt_off = np.concatenate([[0], np.cumsum(n_pts)]).astype(np.int64)
-        nb = [int(np.asarray(b).reshape(-1, 7).shape[0]) for b in boxes]
+        self.n_points = int(pt_off[-1])
+        if in_place:
+            self._frames = list(points)                      # keeps the memory alive
+            self.pt_stride = int(points[0].shape[1])
+            ptrs = np.array([p.data_ptr() for p in points], dtype=np.int64)
+            self.pts_all = None
+        else:
+            host = [np.asarray(p.detach().cpu() if isinstance(p, torch.Tensor) else p, dtype=np.float32) for p in points]
+            host = [h.reshape(h.shape[0], -1)[:, :3] if h.shape[0] else np.zeros((0, 3), np.float32) for h in host]
+            self.pts_all = torch.from_numpy(np.ascontiguousarray(np.concatenate(host, 0)) if F else np.zeros((0, 3), np.float32)).to(dev)
+            self.pt_stride = 3
+            ptrs = self.pts_all.data_ptr() + pt_off[:-1] * 12
+        # ---- boxes
+        if isinstance(boxes, np.ndarray) and boxes.ndim == 3:        # (F, B, 7): the same number of boxes in every frame, one array
+            nb = [int(boxes.shape[1])] * F
+            all_boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 7)
+        else:
+            nb = [int(np.asarray(b).reshape(-1, 7).shape[0]) for b in boxes]
+            all_boxes = np.ascontiguousarray(np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 7) for b in boxes], 0)) if sum(nb) \
+                else np.zeros((0, 7), np.float32)
         self.box_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
         TB = self.TB = int(self.box_off[-1])
-        if TB:
-            self.d_planes, self.d_aabb, self.d_boxes, self.d_sincos = box_planes_device(
-                np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 7) for b in boxes], 0), dev, return_inputs=True)
-        else:
-            self.d_planes = torch.zeros((0, 6, 4), device=dev, dtype=torch.float32)
-            self.d_aabb = torch.zeros((0, 6), device=dev, dtype=torch.float32)
-            self.d_boxes = torch.zeros((0, 7), device=dev, dtype=torch.float32)
-            self.d_sincos = torch.zeros((0, 2), device=dev, dtype=torch.float32)
-        # the boxes in their own frames (conservative pair classification of the hits kernel)
-        self.d_local = torch.empty((max(TB, 1), 12), device=dev, dtype=torch.float32)
-        if TB:
-            with torch.cuda.device(dev):
-                _lib.check(lib.al3d_crop_box_local(self.d_boxes.data_ptr(), self.d_sincos.data_ptr(), TB, self.d_local.data_ptr(),
-                                                   ops._stream()), "crop_box_local")
+        sincos = np.stack([np.sin(all_boxes[:, 6]), np.cos(all_boxes[:, 6])], 1).astype(np.float32)    # numpy float32, like the reference
         self.max_boxes = max(1, max(nb) if nb else 1)
-        CH = self.chunk_pts = int(chunk) if chunk else self.chunk_points(sum(n_pts))
+        CH = self.chunk_pts = int(chunk) if chunk else self.chunk_points(self.n_points)
         if not 1 <= CH <= lib.al3d_crop_chunk_points():
             raise ValueError("chunk=%d not in [1, %d]" % (CH, lib.al3d_crop_chunk_points()))
-        # chunk table (frame, first point, points, chunk index in frame), frame-major -- vectorised: a sweep has ~9000 chunks
+        # chunk table (frame, first point, points, chunk index in frame), frame-major -- vectorised: a sweep has thousands of chunks
         n_arr = np.asarray(n_pts, dtype=np.int64).reshape(-1)
         n_ch = (n_arr + CH - 1) // CH
         frame_chunk_off = np.concatenate([[0], np.cumsum(n_ch)]).astype(np.int64)
@@ -133,40 +195,45 @@ class CropPlan:
         # synthetic Waymo-shaped frames put ~10 % of the points inside a box)
         self.hit_cap = int(hit_cap or max(256, CH // 16))
         self.n_seg = 8                               # warps per chunk CTA (csrc/crop.cu kCropWarps)
-        i32 = lambda *s: torch.empty(s, device=dev, dtype=torch.int32)
-        self.d_pt_off = torch.from_numpy(pt_off).to(dev)
-        self.d_box_off = torch.from_numpy(self.box_off).to(dev)
-        self.d_chunks = torch.from_numpy(np.ascontiguousarray(chunks)).to(dev)
-        self.d_fco = torch.from_numpy(frame_chunk_off).to(dev)
-        self.meta = torch.empty((max(F, 1), 8), device=dev, dtype=torch.float32)
-        self.occ = torch.zeros((max(F, 1), lib.al3d_crop_occ_words()), device=dev, dtype=torch.int32)
+        # ---- every small host table in ONE upload
+        host_poses = None
+        if poses is not None:
+            if isinstance(poses, np.ndarray):
+                host_poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(F, 4, 4)
+            else:
+                host_poses = np.stack([np.asarray(P, dtype=np.float64).reshape(4, 4) for P in poses]) if F else np.zeros((0, 4, 4))
+        d = _upload(dev, {"ptrs": ptrs, "box_off": self.box_off, "fco": frame_chunk_off, "poses": host_poses, "chunks": chunks,
+                          "boxes": all_boxes, "sincos": sincos})
+        self.d_frame_ptrs, self.d_box_off, self.d_fco, self.d_chunks = d["ptrs"], d["box_off"], d["fco"], d["chunks"]
+        self.d_boxes, self.d_sincos, self.d_poses = d["boxes"], d["sincos"], d["poses"]
+        # ---- plane equations, padded rectangles and box-frame records on the device
+        f32 = lambda *sh: torch.empty(sh, device=dev, dtype=torch.float32)
+        i32 = lambda *sh: torch.empty(sh, device=dev, dtype=torch.int32)
+        self.d_planes, self.d_aabb, self.d_local = f32(max(TB, 1), 6, 4)[:TB], f32(max(TB, 1), 6)[:TB], f32(max(TB, 1), 12)
+        if TB:
+            with torch.cuda.device(dev):
+                _lib.check(lib.al3d_crop_box_setup(self.d_boxes.data_ptr(), self.d_sincos.data_ptr(), TB, AABB_PAD, 1e-5, self.d_planes.data_ptr(),
+                                                   self.d_aabb.data_ptr(), ops._stream()), "crop_box_setup")
+                _lib.check(lib.al3d_crop_box_local(self.d_boxes.data_ptr(), self.d_sincos.data_ptr(), TB, self.d_local.data_ptr(),
+                                                   ops._stream()), "crop_box_local")
+        self.meta = f32(max(F, 1), 8)
+        self.occ = i32(max(F, 1), lib.al3d_crop_occ_words())
         self.cell_start = i32(max(F, 1), GRID * GRID + 1)
         self.cell4 = i32(max(F, 1), GRID * GRID, 2)          # packed cell entries (up to three box ids in 8 bytes)
         self.overflow = torch.zeros((1,), device=dev, dtype=torch.int32)
-        # Size the CSR cell lists from the data: a counting run of the grid kernel (cell_cap = 0 stores nothing) leaves
-        # every frame's total in cell_start[f, -1].  Few large or heavily overlapping boxes can cover all 64 x 64 cells
-        # each -- a fixed 64 * B + 4096 guess overflowed on two near-duplicate detections.
-        self.cell_cap = 0
-        self.cell_boxes = i32(1)
-        if F and TB:
-            self.grid()
-            self.cell_cap = max(int(self.cell_start[:, GRID * GRID].max().item()), 1)
-            self.overflow.zero_()
-        self.cell_cap = max(self.cell_cap, 1)
+        # CSR cell lists: sized by an upper bound computed from the boxes on the host (no counting run, no read-back); the
+        # overflow flag of the grid kernel stays as the safety net
+        self.cell_cap = cell_cap_bound(all_boxes, self.box_off, GRID)
         self.cell_boxes = i32(max(F, 1), self.cell_cap)
         self.hits = torch.empty((max(self.n_chunks, 1), self.n_seg, self.hit_cap, lib.al3d_crop_hit_bytes() // 4), device=dev, dtype=torch.int32)
         self.n_hits = i32(max(self.n_chunks, 1), self.n_seg)
         self.cbc = i32(max(self.n_chunks, 1), self.max_boxes)
         self.box_total = i32(max(TB, 1))
         self.offsets = torch.zeros((TB + 1,), device=dev, dtype=torch.int64)
-        self.d_poses = None
-        if poses is not None:
-            self.d_poses = torch.from_numpy(np.ascontiguousarray(
-                np.stack([np.asarray(P, dtype=np.float64).reshape(4, 4) for P in poses]) if F else np.zeros((0, 4, 4)))).to(dev)
         self.capacity = None
         self.out_idx = self.out_xyz = self.out_glob = None
         # algorithmic bytes: every point read once (12 B) + plane equations; the writes are added per run
-        self.read_bytes = int(self.pts_all.shape[0]) * 12 + TB * 96
+        self.read_bytes = self.n_points * 12 + TB * 96
 
     @staticmethod
     def chunk_points(total_points):
@@ -196,7 +263,7 @@ class CropPlan:
 
     def hits_pass(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr())
-        _lib.check(lib.al3d_crop_hits(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_planes), p(self.d_local), p(self.d_box_off), GRID, p(self.meta),
+        _lib.check(lib.al3d_crop_hits(p(self.d_frame_ptrs), self.pt_stride, p(self.d_planes), p(self.d_local), p(self.d_box_off), GRID, p(self.meta),
                                       p(self.cell_start), p(self.cell_boxes), self.cell_cap, p(self.cell4), p(self.occ), p(self.d_chunks), self.n_chunks,
                                       p(self.hits), self.hit_cap, p(self.n_hits), p(self.cbc), self.max_boxes, p(self.overflow), st),
                    "crop_hits")
@@ -214,7 +281,7 @@ class CropPlan:
 
     def fill(self):
         lib, st, p = _lib.lib(), ops._stream(), (lambda t: t.data_ptr() if t is not None else None)
-        _lib.check(lib.al3d_crop_fill(p(self.pts_all), 3, p(self.d_pt_off), p(self.d_box_off), self.F, p(self.d_chunks), self.n_chunks,
+        _lib.check(lib.al3d_crop_fill(p(self.d_box_off), self.F, p(self.d_chunks), self.n_chunks,
                                       p(self.hits), self.hit_cap, p(self.n_hits), p(self.cbc), self.max_boxes, p(self.offsets),
                                       p(self.d_poses), self.capacity, p(self.out_idx), p(self.out_xyz), p(self.out_glob),
                                       p(self.overflow), st), "crop_fill")
@@ -226,6 +293,11 @@ class CropPlan:
         if capacity is not None and self.capacity != capacity:
             self._alloc_outputs(capacity)
         if self.capacity is None:
+            if int(self.overflow.item()) == 1:               # cell lists larger than the host bound (never seen): size them exactly
+                self.cell_cap = max(int(self.cell_start[:, GRID * GRID].max().item()), 1)
+                self.cell_boxes = torch.empty((max(self.F, 1), self.cell_cap), device=self.dev, dtype=torch.int32)
+                self.overflow.zero_()
+                self.count()
             _check_overflow(self.overflow, "hits")
             self._alloc_outputs(int(self.offsets[-1].item()))
         self.fill()

@@ -389,7 +389,7 @@ __device__ unsigned long long g_crop_stats[8];
 #endif
 template <bool kSmemTables>
 __global__ void __launch_bounds__(kCropThreads, CROP_MINB)
-crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int64_t *__restrict__ pt_off,
+crop_hits_kernel(const float *const *__restrict__ frame_points, int64_t pt_stride,
                  const float *__restrict__ planes, const CropBoxLocal *__restrict__ local, const int64_t *__restrict__ box_off, int G,
                  const CropGridMeta *__restrict__ meta, const int32_t *__restrict__ cell_start,
                  const int32_t *__restrict__ cell_boxes, int cell_cap, const uint2 *__restrict__ cell4, const uint32_t *__restrict__ occ,
@@ -431,7 +431,7 @@ crop_hits_kernel(const float *__restrict__ points, int64_t pt_stride, const int6
     const int32_t *cs = cell_start + (int64_t)f * (cells + 1);
     const int32_t *cb = cell_boxes + (int64_t)f * cell_cap;
     const uint2 *c4 = cell4 + (int64_t)f * cells;
-    const float *pts = points + (pt_off[f] + ck.first_pt) * pt_stride;
+    const float *pts = frame_points[f] + (int64_t)ck.first_pt * pt_stride;
     const float4 *pl = reinterpret_cast<const float4 *>(planes) + b0 * 6;
     const CropBoxLocal *loc = local + b0;
     {
@@ -917,13 +917,13 @@ extern "C" int al3d_crop_build_grid(const float *aabb, const float *boxes, const
     return 0;
 }
 
-extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
+extern "C" int al3d_crop_hits(const float *const *frame_points, int64_t pt_stride, const float *planes,
                               const float *local, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
                               const int32_t *cell_boxes, int cell_cap, const uint32_t *cell4, const uint32_t *occ, const int32_t *chunks,
                               int n_chunks, void *hits, int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes,
                               int32_t *overflow, void *stream)
 {
-    AL3D_CHECK_ARG(points && pt_off && planes && local && box_off && grid_meta && cell_start && cell_boxes && cell4 && occ && chunks && hits &&
+    AL3D_CHECK_ARG(frame_points && planes && local && box_off && grid_meta && cell_start && cell_boxes && cell4 && occ && chunks && hits &&
                    n_hits && chunk_box_count && overflow, "al3d_crop_hits: null pointer");
     AL3D_CHECK_ARG(pt_stride >= 3, "al3d_crop_hits: pt_stride=%lld", (long long)pt_stride);
     AL3D_CHECK_ARG(max_boxes >= 1 && max_boxes <= 12288, "al3d_crop_hits: max_boxes=%d not in [1,12288]", max_boxes);
@@ -942,7 +942,7 @@ extern "C" int al3d_crop_hits(const float *points, int64_t pt_stride, const int6
     auto kern = loc_smem ? crop_hits_kernel<true> : crop_hits_kernel<false>;
     if (smem > 48 * 1024) AL3D_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_chunks, kCropThreads, smem, (cudaStream_t)stream>>>(
-        points, pt_stride, pt_off, planes, reinterpret_cast<const CropBoxLocal *>(local), box_off, G,
+        frame_points, pt_stride, planes, reinterpret_cast<const CropBoxLocal *>(local), box_off, G,
         reinterpret_cast<const CropGridMeta *>(grid_meta), cell_start, cell_boxes, cell_cap, reinterpret_cast<const uint2 *>(cell4), occ,
         reinterpret_cast<const CropChunk *>(chunks), reinterpret_cast<float4 *>(hits),
         reinterpret_cast<int32_t *>(reinterpret_cast<float4 *>(hits) + (int64_t)n_chunks * kCropWarps * hit_cap), hit_cap, n_hits, chunk_box_count, max_boxes,
@@ -966,14 +966,13 @@ extern "C" int al3d_crop_scan(const int64_t *box_off, const int64_t *frame_chunk
 
 extern "C" int al3d_crop_hit_bytes(void) { return kCropHitBytes; }
 
-extern "C" int al3d_crop_fill(const float *points, int64_t pt_stride, const int64_t *pt_off, const int64_t *box_off, int n_frames,
+extern "C" int al3d_crop_fill(const int64_t *box_off, int n_frames,
                               const int32_t *chunks, int n_chunks, const void *hits, int hit_cap, const int32_t *n_hits,
                               const int32_t *chunk_box_count, int max_boxes, const int64_t *offsets, const double *poses,
                               int64_t capacity, int32_t *out_idx, float *out_xyz, double *out_xyz_global, int32_t *overflow,
                               void *stream)
 {
-    AL3D_CHECK_ARG(points && pt_off && box_off && chunks && hits && n_hits && chunk_box_count && offsets && out_idx && overflow,
-                   "al3d_crop_fill: null pointer");
+    AL3D_CHECK_ARG(box_off && chunks && hits && n_hits && chunk_box_count && offsets && out_idx && overflow, "al3d_crop_fill: null pointer");
     if (n_chunks <= 0 || n_frames <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     AL3D_CHECK_ARG((reinterpret_cast<uintptr_t>(hits) & 15) == 0, "al3d_crop_fill: hits must be 16-byte aligned");

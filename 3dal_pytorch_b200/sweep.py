@@ -53,8 +53,8 @@ class StaticSweep:
         # one conversion for the whole sweep (every frame holds the same number of boxes: persistent tracking ids)
         T = int(np.asarray(frames[0]["det_boxes"]).shape[0])
         all_w = crop.detector_to_waymo(np.concatenate([np.asarray(f["det_boxes"]).reshape(-1, 7) for f in frames], 0)).reshape(F, -1, 7)
-        boxes_w = [all_w[f] for f in range(F)]
-        plan = crop.CropPlan([f["points"] for f in frames], boxes_w, [f["pose"] for f in frames], device=dev)
+        poses = np.stack([np.asarray(f["pose"], dtype=np.float64) for f in frames])
+        plan = crop.CropPlan([f["points"] for f in frames], all_w, poses, device=dev)
         res = plan.run()
         seg_start, seg_len = track_segments(res["offsets"], res["box_off"], F, T)
         rows = resample_rows(seg_start, seg_len, self.npoints, self.policy)
@@ -63,7 +63,6 @@ class StaticSweep:
             best = seg_len.argmax(1).cpu().numpy()
         else:
             best = np.asarray(det_scores).argmax(0)
-        poses = np.stack([np.asarray(f["pose"], dtype=np.float64) for f in frames])
         inv_pose = np.linalg.inv(poses[best])                                       # (T,4,4) global -> vehicle frame
         # the detector box of the best frame, in that frame's vehicle coordinates, is the initial box
         init_box = all_w[best, np.arange(T)].astype(np.float64)

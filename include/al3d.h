@@ -132,8 +132,9 @@ int al3d_fc_chain(const al3d_fc_chain_desc *d, int bs, void *stream);
  * Points-in-rotated-box crop over a batch of lidar frames (integer / indexing work, bit-exact).
  * Replaces box_np_ops.points_in_rbbox (det3d/core/bbox/box_np_ops.py:641-647 ->
  * det3d/core/bbox/geometry.py:241-276) and the per-box crop loop of _create_pd_detection
- * (det3d/datasets/waymo/waymo_common.py:167-171).  Frames are concatenated: points (sum N_f, stride)
- * f32 with pt_off (F+1) i64; boxes as inward plane equations planes (sum B_f, 6, 4) f32 and padded
+ * (det3d/datasets/waymo/waymo_common.py:167-171).  The points of frame f are the (N_f, pt_stride) f32 rows at
+ * frame_points[f] (a device array of F device pointers: frames are used where they lie, nothing is concatenated; x y z
+ * are the first three columns); the boxes of all frames are concatenated: inward plane equations planes (sum B_f, 6, 4) f32 and padded
  * axis-aligned rectangles aabb (sum B_f, 6) f32 [xmin ymin zmin xmax ymax zmax] with box_off (F+1) i64
  * (both from al3d_crop_box_setup).  Every point ends up in exactly the lists the reference predicate puts it in.
  * `overflow` is a device int32 the kernels set non-zero when a caller-provided capacity is too small.
@@ -166,7 +167,7 @@ int al3d_crop_build_grid(const float *aabb, const float *boxes, const float *sin
  * warp of the chunk's CTA; stored as an array of 16-byte records x y z | point index followed by an array of 4-byte
  * words box | rank << 16), n_hits (n_chunks, 8) i32;
  * chunk_box_count: (n_chunks, max_boxes) i32 scratch. */
-int al3d_crop_hits(const float *points, int64_t pt_stride, const int64_t *pt_off, const float *planes,
+int al3d_crop_hits(const float *const *frame_points, int64_t pt_stride, const float *planes,
                    const float *local, const int64_t *box_off, int G, const float *grid_meta, const int32_t *cell_start,
                    const int32_t *cell_boxes, int cell_cap, const uint32_t *cell4, const uint32_t *occ, const int32_t *chunks,
                    int n_chunks, void *hits, int hit_cap, int32_t *n_hits, int32_t *chunk_box_count, int max_boxes,
@@ -177,7 +178,7 @@ int al3d_crop_scan(const int64_t *box_off, const int64_t *frame_chunk_off, int n
 /* out_idx (capacity) i32 point index within its frame, ascending per box; out_xyz (capacity,3) f32 copy
  * (may be NULL); out_xyz_global (capacity,3) f64 = poses[f] (4x4 row-major f64) applied to [x y z 1]
  * (may be NULL, needs poses). */
-int al3d_crop_fill(const float *points, int64_t pt_stride, const int64_t *pt_off, const int64_t *box_off, int n_frames,
+int al3d_crop_fill(const int64_t *box_off, int n_frames,
                    const int32_t *chunks, int n_chunks, const void *hits, int hit_cap, const int32_t *n_hits,
                    const int32_t *chunk_box_count, int max_boxes, const int64_t *offsets, const double *poses,
                    int64_t capacity, int32_t *out_idx, float *out_xyz, double *out_xyz_global, int32_t *overflow,

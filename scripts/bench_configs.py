@@ -57,7 +57,7 @@ def bench_crop(n_frames):
     seqs = [("grid",), ("grid", "hits_pass"), ("grid", "hits_pass", "scan"), ("grid", "hits_pass", "scan", "fill")]
     cum = [timed(lambda q=q: [getattr(plan, k)() for k in q]) for q in seqs]
     stage_ms = {"grid": cum[0], "hits": cum[1] - cum[0], "scan": cum[2] - cum[1], "fill": cum[3] - cum[2]}
-    n_points = int(plan.pts_all.shape[0])
+    n_points = int(plan.n_points)
     alg_bytes = plan.read_bytes + total * (4 + 12)                  # + 4 B index + 12 B xyz per inside point
     moved = alg_bytes + total * 24                                  # the f64 global xyz is extra output
     # CPU reference for the same job: oracle (C restatement of the numba loop), one thread, on a 2-frame sample

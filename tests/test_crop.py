@@ -27,6 +27,31 @@ def test_host_planes_bitwise_equal_to_oracle():
     assert np.array_equal(crop.detector_to_waymo(boxes), ocrop.detector_to_waymo(boxes))
 
 
+def test_cell_list_bound_covers_the_grid_kernel_count():
+    """crop.cell_cap_bound sizes the coarse cell -> box lists without a counting run on the device: it must never be below
+    what crop_grid_kernel registers (replayed here in numpy float32: padded rectangles -> frame extent -> cell ranges)."""
+    rng = np.random.default_rng(5)
+    G = crop.GRID
+    frames = [_random_boxes(rng, 200, spread=40.0), _random_boxes(rng, 3, spread=0.3), _random_boxes(rng, 1),
+              np.tile(_random_boxes(rng, 1), (10, 1)), _random_boxes(rng, 60, spread=2000.0), np.zeros((0, 7), np.float32),
+              crop.detector_to_waymo(synth.lidar_frames(1, n_points=10, seed=2)[0]["det_boxes"])]
+    box_off = np.concatenate([[0], np.cumsum([len(b) for b in frames])])
+    bound = crop.cell_cap_bound(np.concatenate(frames, 0), box_off, G)
+    worst = 0
+    for b in frames:
+        if len(b) == 0:
+            continue
+        _, aabb = crop.box_planes_host(b)
+        x0, y0 = aabb[:, 0].min(), aabb[:, 1].min()
+        ex = max(np.float32(aabb[:, 3].max() - x0), np.float32(1e-3)); ey = max(np.float32(aabb[:, 4].max() - y0), np.float32(1e-3))
+        ix, iy = np.float32(G) / ex * np.float32(0.999), np.float32(G) / ey * np.float32(0.999)
+        cell = lambda v, v0, inv: np.clip(np.floor((v - v0) * inv), 0, G - 1)
+        nx = cell(aabb[:, 3], x0, ix) - cell(aabb[:, 0], x0, ix) + 1
+        ny = cell(aabb[:, 4], y0, iy) - cell(aabb[:, 1], y0, iy) + 1
+        worst = max(worst, int((nx * ny).sum()))
+    assert bound >= worst, (bound, worst)
+
+
 def _check_against_oracle(points, boxes, poses, res):
     off = res["offsets"].cpu().numpy()
     idx = res["indices"].cpu().numpy()
@@ -232,3 +257,10 @@ def test_crop_frames_with_many_boxes_use_the_global_tables():
     res = crop.crop_frames(points, boxes, poses, hit_cap=16384)
     assert int(res["overflow"].item()) == 0
     _check_against_oracle(points, boxes, poses, res)
+    # frames that already live on the device are used where they lie, whatever their row width (x y z intensity elongation)
+    wide = [torch.from_numpy(np.concatenate([p, rng.random((len(p), 2)).astype(np.float32)], 1)).cuda() for p in points]
+    res5 = crop.crop_frames(wide, boxes, poses, hit_cap=16384)
+    plain = [torch.from_numpy(p).cuda() for p in points]
+    res3 = crop.crop_frames(plain, boxes, poses, hit_cap=16384)
+    for k in ("indices", "offsets", "xyz", "xyz_global"):
+        assert torch.equal(res5[k], res[k]) and torch.equal(res3[k], res[k]), k
