@@ -14,54 +14,96 @@ __constant__ float  c_mean_size_f32[9] = {4.8f, 1.8f, 1.5f, 10.0f, 2.6f, 3.2f, 2
 __constant__ double c_mean_size_f64[9] = {4.8, 1.8, 1.5, 10.0, 2.6, 3.2, 2.0, 1.0, 1.6};
 
 // ---------------------------------------------------------------------------------------------
-// mask + ordered compaction: one CTA per object, 256 points per sweep.
+// mask + ordered compaction: one CTA of 128 threads per object, 4096 points per sweep -- 32 consecutive points per thread
+// (vector loads, all issued before the first is used; a 32-bit foreground word), one block-wide exclusive scan of the
+// per-thread counts, then every thread writes its own foreground indices.  Two barriers per sweep (the first cut swept
+// 256 points at a time with three barriers each: 0.65 TB/s on 8192 x 4096 points).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kCompactThreads = 128;
+constexpr int kCompactPer = 32;                        // points per thread and sweep
+
+__global__ void __launch_bounds__(kCompactThreads)
 mask_compact_kernel(const float *__restrict__ logits, uint8_t *__restrict__ mask, int n,
                     int32_t *__restrict__ pos, int32_t *__restrict__ count)
 {
-    __shared__ int warp_cnt[8];
-    __shared__ int base_s;
+    __shared__ int warp_cnt[kCompactThreads / 32];
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) base_s = 0;
-    __syncthreads();
     const float2 *lg = logits ? reinterpret_cast<const float2 *>(logits) + (int64_t)b * n : nullptr;
     uint8_t *mk = mask + (int64_t)b * n;
     int32_t *ps = pos + (int64_t)b * n;
-    for (int p0 = 0; p0 < n; p0 += 256) {
-        const int p = p0 + threadIdx.x;
-        bool fg = false;
-        if (p < n) {
+    const bool vec = (n & 15) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
+    int base = 0;                                     // foreground points of the sweeps done (the same in every thread)
+    for (int p0 = 0; p0 < n; p0 += kCompactThreads * kCompactPer) {
+        const int t0 = p0 + threadIdx.x * kCompactPer;
+        unsigned bits = 0;
+        if (vec && t0 + kCompactPer <= n) {
             if (lg) {
-                const float2 l = __ldg(lg + p);
-                fg = l.x < l.y;                       // strict; false when either is NaN
-                mk[p] = fg ? 1 : 0;
+                const float4 *q = reinterpret_cast<const float4 *>(lg + t0);
+                float4 v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = __ldg(q + k);
+#pragma unroll
+                for (int k = 0; k < 16; ++k)          // strict; false when either logit is NaN
+                    bits |= (v[k].x < v[k].y ? 1u << (2 * k) : 0u) | (v[k].z < v[k].w ? 2u << (2 * k) : 0u);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned x = (bits >> (16 * h + 4 * j)) & 0xFu;
+                        w[j] = (x & 1u) | ((x & 2u) << 7) | ((x & 4u) << 14) | ((x & 8u) << 21);
+                    }
+                    *reinterpret_cast<uint4 *>(mk + t0 + 16 * h) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
             } else {
-                fg = mk[p] != 0;
+                const uint4 m0 = *reinterpret_cast<const uint4 *>(mk + t0), m1 = *reinterpret_cast<const uint4 *>(mk + t0 + 16);
+                const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) bits |= ((w[j] >> (8 * k)) & 0xFFu) ? 1u << (4 * j + k) : 0u;
+            }
+        } else {
+            for (int k = 0; k < kCompactPer; ++k) {
+                const int p = t0 + k;
+                if (p >= n) break;
+                bool fg;
+                if (lg) {
+                    const float2 l = __ldg(lg + p);
+                    fg = l.x < l.y;
+                    mk[p] = fg ? 1 : 0;
+                } else fg = mk[p] != 0;
+                bits |= fg ? 1u << k : 0u;
             }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, fg);
-        if (lane == 0) warp_cnt[wid] = __popc(bal);
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_cnt[wid] = incl;
         __syncthreads();
-        int before = base_s;
-        for (int w = 0; w < wid; ++w) before += warp_cnt[w];
-        if (fg) ps[before + __popc(bal & ((1u << lane) - 1u))] = p;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int w = 0; w < 8; ++w) t += warp_cnt[w];
-            base_s += t;
+        int before = base + incl - cnt, total = 0;
+#pragma unroll
+        for (int w = 0; w < kCompactThreads / 32; ++w) { const int c = warp_cnt[w]; before += w < wid ? c : 0; total += c; }
+        while (bits) {                                 // ascending: lowest set bit first
+            const int k = __ffs(bits) - 1;
+            bits &= bits - 1;
+            ps[before++] = t0 + k;
         }
+        base += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) count[b] = base_s;
+    if (threadIdx.x == 0) count[b] = base;
 }
 
 // ---------------------------------------------------------------------------------------------
-// gather: one CTA per object.
+// gather: one CTA of 128 threads per object, four output slots per thread and round -- the four index loads, then the
+// twelve coordinate loads are all in flight together.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kGatherThreads = 128;
+
+__global__ void __launch_bounds__(kGatherThreads)
 gather_fg_kernel(const float *__restrict__ x, int64_t sb, int64_t sc, int64_t sp, int C, int n,
                  const int32_t *__restrict__ pos, const int32_t *__restrict__ count, int policy,
                  const int32_t *__restrict__ choice, int n_pts, float *__restrict__ out, int64_t *__restrict__ indices)
@@ -69,18 +111,47 @@ gather_fg_kernel(const float *__restrict__ x, int64_t sb, int64_t sc, int64_t sp
     const int b = blockIdx.x;
     const int L = count[b];
     const int32_t *ps = pos + (int64_t)b * n;
-    for (int j = threadIdx.x; j < n_pts; j += blockDim.x) {
-        int64_t src = 0;
-        if (L > 0) {
-            int sel;
-            if (policy == AL3D_GATHER_TABLE) sel = choice[(int64_t)b * n_pts + j];
-            else sel = (L >= n_pts) ? (int)(((uint64_t)j * (uint64_t)L) / (uint64_t)n_pts) : (j % L);
-            src = ps[sel];
+    const float *xb = x + b * sb;
+    const bool small = (uint64_t)n_pts * (uint64_t)max(L, 1) < (1ull << 32);      // j * L fits 32 bits: no 64-bit division
+    for (int j0 = threadIdx.x; j0 < n_pts; j0 += 4 * kGatherThreads) {
+        int64_t src[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * kGatherThreads;
+            src[u] = 0;
+            if (L > 0 && j < n_pts) {
+                int sel;
+                if (policy == AL3D_GATHER_TABLE) sel = choice[(int64_t)b * n_pts + j];
+                else if (L < n_pts) sel = j % L;
+                else sel = small ? (int)(((unsigned)j * (unsigned)L) / (unsigned)n_pts) : (int)(((uint64_t)j * (uint64_t)L) / (uint64_t)n_pts);
+                src[u] = ps[sel];
+            }
         }
-        if (indices) indices[(int64_t)b * n_pts + j] = src;
-        for (int c = 0; c < C; ++c) {
-            const float v = (L > 0) ? __ldg(x + b * sb + c * sc + src * sp) : 0.f;
-            out[((int64_t)b * C + c) * n_pts + j] = v;
+        if (C == 3) {
+            float v[4][3];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float *q = xb + src[u] * sp;
+                const bool ok = L > 0 && j0 + u * kGatherThreads < n_pts;
+                v[u][0] = ok ? __ldg(q) : 0.f; v[u][1] = ok ? __ldg(q + sc) : 0.f; v[u][2] = ok ? __ldg(q + 2 * sc) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * kGatherThreads;
+                if (j >= n_pts) continue;
+                if (indices) indices[(int64_t)b * n_pts + j] = src[u];
+                float *o = out + (int64_t)b * 3 * n_pts + j;
+                o[0] = v[u][0]; o[n_pts] = v[u][1]; o[2 * (int64_t)n_pts] = v[u][2];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * kGatherThreads;
+                if (j >= n_pts) continue;
+                if (indices) indices[(int64_t)b * n_pts + j] = src[u];
+                for (int c = 0; c < C; ++c)
+                    out[((int64_t)b * C + c) * n_pts + j] = (L > 0) ? __ldg(xb + c * sc + src[u] * sp) : 0.f;
+            }
         }
     }
 }
@@ -196,7 +267,7 @@ extern "C" int al3d_mask_compact(const float *logits, uint8_t *mask, int bs, int
     AL3D_CHECK_ARG(mask && pos && count, "al3d_mask_compact: null pointer");
     AL3D_CHECK_ARG(bs >= 0 && n >= 0, "al3d_mask_compact: negative size");
     if (bs == 0) return 0;
-    mask_compact_kernel<<<bs, 256, 0, (cudaStream_t)stream>>>(logits, mask, n, pos, count);
+    mask_compact_kernel<<<bs, kCompactThreads, 0, (cudaStream_t)stream>>>(logits, mask, n, pos, count);
     AL3D_CHECK_LAUNCH("mask_compact_kernel");
     return 0;
 }
@@ -210,7 +281,7 @@ extern "C" int al3d_gather_fg(const float *x, int64_t sb, int64_t sc, int64_t sp
                    "al3d_gather_fg: bad policy %d (or missing choice table)", policy);
     AL3D_CHECK_ARG(bs >= 0 && C > 0 && n >= 0 && n_pts > 0, "al3d_gather_fg: bad shape");
     if (bs == 0) return 0;
-    gather_fg_kernel<<<bs, 256, 0, (cudaStream_t)stream>>>(x, sb, sc, sp, C, n, pos, count, policy, choice, n_pts, out, indices);
+    gather_fg_kernel<<<bs, kGatherThreads, 0, (cudaStream_t)stream>>>(x, sb, sc, sp, C, n, pos, count, policy, choice, n_pts, out, indices);
     AL3D_CHECK_LAUNCH("gather_fg_kernel");
     return 0;
 }

@@ -144,21 +144,23 @@ def choice_table_numpy_legacy(counts_host, n_pts):
 def mask_and_gather(pts, logits, n_pts, policy, want_indices=False, mask=None):
     """mask: the (bs,n) bool mask already produced by the segmentation epilogue (bf16 mode), or None
     to derive it from the logits here."""
+    from . import engine_bf16
     from_tc = mask is not None
-    if mask is None:
-        mask, pos, count = ops.mask_compact(logits=logits)
-    else:
-        mask, pos, count = ops.mask_compact(mask=mask)
+    with engine_bf16._timed("mask_compact_kernel"):
+        if mask is None:
+            mask, pos, count = ops.mask_compact(logits=logits)
+        else:
+            mask, pos, count = ops.mask_compact(mask=mask)
     choice = None
     if policy == "numpy_legacy":
         # the one documented host round-trip: bs counts down, a (bs,n_pts) table up
         counts_host = count.cpu().numpy()
         if from_tc:                           # the mask came from a tensor-core kernel: this D2H is a sync point
-            from . import engine_bf16
             engine_bf16.check_abort("gather (numpy_legacy count copy)", pts.device)
         table = choice_table_numpy_legacy(counts_host, n_pts)
         choice = torch.from_numpy(table).to(pts.device, non_blocking=True)
     elif policy != "strided":
         raise ValueError("gather_policy must be 'strided' or 'numpy_legacy'")
-    out = ops.gather_fg(pts, pos, count, n_pts, choice=choice, want_indices=want_indices)
+    with engine_bf16._timed("gather_fg_kernel"):
+        out = ops.gather_fg(pts, pos, count, n_pts, choice=choice, want_indices=want_indices)
     return out, mask, count

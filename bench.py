@@ -601,6 +601,16 @@ def main():
         if world == 1 and not args.no_crop:
             crop_res = bench_crop(dev, peaks, model=model)
         flop_obj = spec.flops_per_object("static_one", N_POINTS)
+        # the foreground compaction and gather kernels of the step against the HBM roofline (algorithmic bytes: 1 B of mask
+        # read per point + 4 B per foreground index written; per gathered point 4 B of index + 12 B of xyz read, 12 B written)
+        gather = {}
+        fg_mean = float(fg.mean().item())
+        for name, nbytes in (("mask_compact_kernel", T * (N_POINTS + 4.0 * fg_mean + 4)),
+                             ("gather_fg_kernel", T * spec.NUM_OBJECT_POINT * (4 + 12 + 12.0))):
+            if name in kernel_ms and kernel_ms[name] > 0:
+                gbs = nbytes / (kernel_ms[name] * 1e-3) / 1e9
+                gather[name] = {"ms": kernel_ms[name], "algorithmic_bytes": nbytes, "achieved": gbs, "unit": "GB/s",
+                                "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"]}
         line = {
             "metric": "auto-labeled objects/sec", "value": value, "unit": "objects/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -611,7 +621,7 @@ def main():
                               fg_points_per_object_median=float(fg.median().item())),
             "model_tflops": value * flop_obj / 1e12 / world, "flop_per_object": flop_obj,
             "kernel_ms": kernel_ms, "gpu_launches": launches, "clocks": clocks,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fast_mode": fast, "crop": crop_res,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fast_mode": fast, "crop": crop_res, "gather": gather,
             "sweep": crop_res.pop("sweep") if crop_res else None,
             "dynamic": dyn_res, "train_step": train_res,
         }

@@ -1,9 +1,10 @@
 #!/bin/bash
-# round 2, GPU call G (2 GPUs): remaining tests, training bench N=1/2, strong-scaling bench N=2
+# gather kernels: parity tests + the bench line (gather object)
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.build()" > gpurun_out/g_build.log 2>&1
-timeout 900 python -m pytest tests/test_gpu_train.py tests/test_crop.py tests/test_trackops.py -m gpu -q > gpurun_out/g_tests.log 2>&1; echo "tests rc=$?"
-timeout 600 python scripts/bench_train.py --steps 10 > gpurun_out/g_train1.json 2> gpurun_out/g_train1.err; echo "train1 rc=$?"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/bench_train.py --steps 10 > gpurun_out/g_train2.json 2> gpurun_out/g_train2.err; echo "train2 rc=$?"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/g_bench2.json 2> gpurun_out/g_bench2.err; echo "bench2 rc=$?"
-tail -4 gpurun_out/g_tests.log; tail -c 700 gpurun_out/g_train1.json; tail -c 500 gpurun_out/g_train2.json; tail -c 300 gpurun_out/g_train1.err
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_pipeline.py tests/test_gpu_graphs.py -x -q -m gpu > gpurun_out/g_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/g_tests.log
+tail -4 gpurun_out/g_tests.log
+timeout 900 python bench.py --no-crop > gpurun_out/g_bench.json 2> gpurun_out/g_bench.err; echo "bench rc=$?"
+python -c "
+import json; d=json.loads(open('gpurun_out/g_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['kernel_ms']); print(json.dumps(d['gather'], indent=1)); print(d['e2e'])"
