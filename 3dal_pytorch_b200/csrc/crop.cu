@@ -8,16 +8,20 @@
 // pose(4x4 f64) @ [x y z 1]).  The plane equations are computed on the device (crop_box_setup_kernel) in numpy's own
 // float32 operation order; only sin / cos of the headings come from the host.
 //
-// The reference tests every point against every box (N*B*6 plane evaluations per frame).  Here a BEV grid
-// per frame maps a point to the few boxes whose (padded) bounding rectangle covers its cell, so each
-// point does O(1) exact tests and the kernels are bound by reading the points once from HBM.
+// The reference tests every point against every box (N*B*6 plane evaluations per frame).  Here a fine BEV occupancy
+// bitmap per frame discards the points that are near no box, a coarse BEV grid maps a survivor to the few boxes whose
+// (padded) bounding rectangle covers its cell, and a (point, box) pair evaluates the six plane equations only when a
+// classification in the box's own frame cannot decide it with a rounding margin to spare -- same result, bit for bit.
 //
-// Pipeline (all launches cover the whole batch of frames):
-//   crop_grid_kernel   one CTA per frame: grid extent from the box AABBs, CSR cell -> box lists
-//   crop_hits_kernel   one CTA per chunk of 2048 points: exact tests, ordered (point, box, rank) hit list
-//                      per chunk and per-(chunk, box) counts
+// Pipeline (all launches cover the whole batch of frames; frames are read where they lie, through a table of pointers):
+//   crop_box_setup / crop_box_local   per box: plane equations + padded rectangle, box-frame record
+//   crop_grid_kernel   kGridBands CTAs per frame: grid extent from the rectangles, CSR cell -> box lists + packed cell
+//                      entries, fine occupancy bitmap
+//   crop_hits_kernel   one CTA per chunk of <= 16384 points: filter -> expand -> test in dense warp batches, ordered
+//                      (x y z index | box, rank) hit records per chunk and per-(chunk, box) counts
 //   crop_scan_kernel   per frame: exclusive scan over chunks for every box; crop_offsets_kernel: global offsets
-//   crop_fill_kernel   scatter indices / xyz / global xyz to their final, ascending positions
+//   crop_fill_kernel   scatters each hit's slot to its final, ascending position; crop_materialise_kernel turns the slots
+//                      into point indices, coordinates and float64 global coordinates, front to back
 #include "common.cuh"
 #include "../../include/al3d.h"
 
