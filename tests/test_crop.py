@@ -216,6 +216,34 @@ def test_crop_points_within_the_rounding_margin_of_faces():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("offset", [1.0, 60.0, 800.0, 20000.0])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_crop_margin_classification_fuzz(offset, seed):
+    """Same property over box sizes from 5 cm to 40 m, aspect ratios up to 800 : 1 and scene offsets up to 20 km (where the
+    float32 grid of the coordinates is ~2 mm and most pairs fall inside the margin or the box is declared irregular):
+    whatever path a pair takes -- classified in the box frame, or evaluated exactly -- the lists equal the oracle's."""
+    rng = np.random.default_rng(100 + seed)
+    nb = 64
+    dims = 10.0 ** rng.uniform(np.log10(0.05), np.log10(40.0), (nb, 3))
+    boxes = np.concatenate([rng.uniform(-1, 1, (nb, 2)) * offset + offset, rng.normal(0.5, 0.5, (nb, 1)), dims,
+                            rng.uniform(-7, 7, (nb, 1))], 1).astype(np.float32)
+    pts = []
+    for b in boxes.astype(np.float64):
+        n = 300
+        u = rng.uniform(-0.6, 0.6, (n, 3)) * b[3:6]                          # some inside, some outside
+        k = rng.random(n) < 0.6                                              # most of them pushed next to a face
+        ax = rng.integers(0, 3, n)
+        eps = rng.choice([-1.0, 1.0], n) * 10.0 ** rng.uniform(-8, 0, n)
+        u[np.arange(n)[k], ax[k]] = (rng.choice([-1.0, 1.0], n) * 0.5 * b[3 + ax] + eps)[k]
+        c, s_ = np.cos(b[6]), np.sin(b[6])
+        pts.append(np.stack([u[:, 0] * c + u[:, 1] * s_, -u[:, 0] * s_ + u[:, 1] * c, u[:, 2]], 1) + b[:3])
+    pts = np.concatenate(pts, 0)[rng.permutation(nb * 300)].astype(np.float32)
+    res = crop.crop_frames([pts], [boxes], [np.eye(4)], hit_cap=32768)
+    assert int(res["overflow"].item()) == 0
+    _check_against_oracle([pts], [boxes], [np.eye(4)], res)
+
+
+@pytest.mark.gpu
 def test_crop_infinite_points_and_irregular_boxes():
     """inf / NaN / huge coordinates and boxes with zero or negative dimensions take the exact predicate -- whatever the reference's float32 arithmetic says (inf * 0 = NaN never rejects) is the answer."""
     rng = np.random.default_rng(13)
