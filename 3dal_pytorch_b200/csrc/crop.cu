@@ -308,7 +308,11 @@ struct CropChunk { int32_t frame; int32_t first_pt; int32_t n_pts; int32_t chunk
 constexpr int kCropHitBytes = 20;
 constexpr int kCropWarps = kCropThreads / 32;
 constexpr int kCropIter = 128;                            // points per warp iteration: point base + j * 32 + lane, j < 4
-constexpr int kCropCQ = 96;                               // per-warp candidate queue: < 32 carried over + <= 64 new (half an iteration)
+#ifndef CROP_PER_CHECK
+#define CROP_PER_CHECK 2                                  // measured (hits pass): a look at the queue every 32 points 0.306 ms, 64: 0.231, 128: 0.229
+#endif
+constexpr int kPerCheck = CROP_PER_CHECK;                 // filters (of 32 points) between two looks at the candidate queue
+constexpr int kCropCQ = 32 + 32 * kPerCheck;              // per-warp candidate queue: < 32 carried over + <= 32 kPerCheck new
 constexpr int kLocSmemBoxes = 256;                        // frames with at most this many boxes keep their box records in shared memory
 // The packed 4-byte cell table of such frames can be staged in shared memory too.  Measured on the 200-frame sweep
 // (profiles/r2_crop_v3_ablation.txt): it takes 0.026 ms off the expand stage, but the 16 KB cost the fourth resident
@@ -655,10 +659,10 @@ crop_hits_kernel(const float *const *__restrict__ frame_points, int64_t pt_strid
         // measured: four sparse L2 round trips per iteration instead of 0.7 dense ones, hits pass 0.25 -> 0.30 ms.  So was
         // expanding two batches of 32 at a time with both batches' cell entries in flight together: 0.23 -> 0.29 ms.)
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < 4 / kPerCheck; ++half) {
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int j = half * 2 + jj;
+            for (int jj = 0; jj < kPerCheck; ++jj) {
+                const int j = half * kPerCheck + jj;
                 const float x = px[j], y = py[j], z = pz[j];
                 const int ix = __float2int_rd(fmaf(x, m.inv_fx, ofx)), iy = __float2int_rd(fmaf(y, m.inv_fy, ofy));
                 const int bit = iy * kOccRes + ix;
