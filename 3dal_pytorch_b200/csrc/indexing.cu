@@ -60,9 +60,11 @@ mask_compact_kernel(const float *__restrict__ logits, uint8_t *__restrict__ mask
                 const uint4 m0 = *reinterpret_cast<const uint4 *>(mk + t0), m1 = *reinterpret_cast<const uint4 *>(mk + t0 + 16);
                 const uint32_t w[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) bits |= ((w[j] >> (8 * k)) & 0xFFu) ? 1u << (4 * j + k) : 0u;
+                for (int j = 0; j < 8; ++j) {
+                    // four mask bytes -> four bits: non-zero bytes to 0x01 each, then one multiply gathers them in bits 24..27
+                    const uint32_t nz = __vcmpne4(w[j], 0u) & 0x01010101u;
+                    bits |= ((nz * 0x01020408u) >> 24) << (4 * j);
+                }
             }
         } else {
             for (int k = 0; k < kCompactPer; ++k) {
