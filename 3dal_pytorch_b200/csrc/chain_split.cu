@@ -73,6 +73,7 @@ struct ChainParams {
     int pair;                                            // 1: tile pairs, split_chain_pair_kernel (last layer with N = 256 points)
     int act_bytes, pair_bytes, n_stages;                 // shared-memory carve-up chosen by the launcher
     int front_blocks, last_blocks;                       // 16 KB slots per tile (mid layers) / per unit (last layer)
+    int last_f16;                                        // pair kernel: the streamed last layer as ONE fp16 MMA per product
     TcStatus wd;
 };
 
@@ -431,15 +432,20 @@ split_chain_pair_kernel(const ChainParams p)
                 pair_phase ^= 1;
                 tc_fence_after();
                 CH_STAMP(0x120);
-                const uint32_t idesc = make_idesc_bf16(128, 256);
+                const uint32_t idesc = p.last_f16 ? make_idesc_f16(128, 256) : make_idesc_bf16(128, 256);
                 for (int cc = 0; cc < n_last_chunks; ++cc) {
                     const int b = cc & 1;
                     SPLIT_STRESS(wd, 0x54);
                     if (!mbar_wait(&s.last_empty[b], le_phase[b] ^ 1, 0x5400 + b, wd)) goto done;
                     le_phase[b] ^= 1;
                     tc_fence_after();
-                    for (int kb = 0; kb < k_last / 64; ++kb)
-                        SPLIT_MMA_BLOCK_T(ring, tmem + b * 256, a_pair + kb * 8 * 2 * kPlane, pair_lo, 2 * kPlane, 256, idesc, kb == 0, 0x5500)
+                    if (p.last_f16) {
+                        for (int kb = 0; kb < k_last / 64; ++kb)
+                            SPLIT_MMA_BLOCK_T_F16(ring, tmem + b * 256, a_pair + kb * 8 * 2 * kPlane, 2 * kPlane, 256, idesc, kb == 0, 0x5500)
+                    } else {
+                        for (int kb = 0; kb < k_last / 64; ++kb)
+                            SPLIT_MMA_BLOCK_T(ring, tmem + b * 256, a_pair + kb * 8 * 2 * kPlane, pair_lo, 2 * kPlane, 256, idesc, kb == 0, 0x5500)
+                    }
                     mma_commit(&s.last_full[b]);
                     CH_STAMP(0x130 + cc);
                 }
@@ -508,7 +514,8 @@ split_chain_pair_kernel(const ChainParams p)
                     acc_phase[q] ^= 1;
                     tc_fence_after();
                     CH_STAMP_E(0x210 + l * 4 + q * 2);
-                    if (q == 1 || last_mid) epilogue_split(tmem + lane_addr + q * 128, half * (N >> 1), N >> 1, s_pair, pair_lo, 2 * kPlane, q * kTile + row, s.mid_b + boff);
+                    if (last_mid && p.last_f16) epilogue_split<kFmtF16>(tmem + lane_addr + q * 128, half * (N >> 1), N >> 1, s_pair, pair_lo, 2 * kPlane, q * kTile + row, s.mid_b + boff);
+                    else if (q == 1 || last_mid) epilogue_split(tmem + lane_addr + q * 128, half * (N >> 1), N >> 1, s_pair, pair_lo, 2 * kPlane, q * kTile + row, s.mid_b + boff);
                     else                    epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_act, act_lo, kPlane, row, s.mid_b + boff);
                     tc_fence_before();
                     fence_proxy_async_smem();
@@ -612,11 +619,13 @@ struct TailParams {
     const uint8_t *wstream;
     float *logits; uint8_t *mask;
     int tiles_per_obj, n_items;
+    int d2_mode;                       // dconv2 operands: 0 bf16 hi+lo x hi+lo (3 MMAs), 1 fp16 x fp16 (1), 2 fp16 hi+lo x fp16 (2)
     TcStatus wd;
 };
 constexpr int kTailStages = 3;
 constexpr int kTailBlocks = 2 + 4 * 2 + 4 * 8 + 8 + 4;       // 54 slots per tile
 constexpr int kBlkConv2 = 0, kBlkD1a = 2, kBlkSteady = 6, kBlkD4 = 50;   // conv2 (2) | d1(0), d1(1) (4) | d1(2) .. dconv3 (44) | dconv4 (4)
+constexpr int kBlkD4F16 = 34;      // d2_mode != 0: the sixteen dconv2 blocks are single fp16 slots, the steady section has 28
 struct TailSmem {
     uint8_t a2[32768];
     uint8_t big[131072];
@@ -632,6 +641,14 @@ struct TailSmem {
 static_assert(sizeof(TailSmem) + 128 <= 232448, "TailSmem exceeds the 227 KB opt-in limit");
 constexpr uint32_t kTD2 = 0, kTDA = 256, kTDB = 384, kTD4 = 0, kTC2 = 128;
 
+// dconv1 chunk (64 accumulator columns of this thread's row) -> dconv2's operand in chunk buffer `cb`, in the format
+// dconv2 multiplies in.
+__device__ __forceinline__ void chunk_epilogue(int d2_mode, uint32_t taddr, int c0, uint8_t *cb, int row, const float *bias)
+{
+    if (d2_mode == 0)      epilogue_split<kFmtBf16x2>(taddr, c0, 64, cb, 32768u, kPlane, row, bias);
+    else if (d2_mode == 1) epilogue_split<kFmtF16>(taddr, c0, 64, cb, 32768u, kPlane, row, bias);
+    else                   epilogue_split<kFmtF16x2>(taddr, c0, 64, cb, 32768u, kPlane, row, bias);
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 split_tail_kernel(const TailParams p)
@@ -679,13 +696,14 @@ split_tail_kernel(const TailParams p)
                 bulk_g2s(s.ring[stage], p.wstream + (size_t)blk * kStage, bytes_, &s.w_full[stage]);  \
                 if (++stage == kTailStages) { stage = 0; phase ^= 1; }                                \
             }
+            const int blk_d4 = p.d2_mode ? kBlkD4F16 : kBlkD4;
             TL_PUSH(kBlkConv2, 2)
             TL_PUSH(kBlkD1a, 4)
             for (int item = item0; item < p.n_items; item += stride) {
                 const bool has_next = item + stride < p.n_items;
-                TL_PUSH(kBlkSteady, kBlkD4 - kBlkSteady)
+                TL_PUSH(kBlkSteady, blk_d4 - kBlkSteady)
                 if (has_next) { TL_PUSH(kBlkConv2, 2) }
-                TL_PUSH(kBlkD4, 4)
+                TL_PUSH(blk_d4, 4)
                 if (has_next) { TL_PUSH(kBlkD1a, 4) }
             }
 #undef TL_PUSH
@@ -695,7 +713,7 @@ split_tail_kernel(const TailParams p)
         if (elect_one_sync()) {
             RingView ring{smem_u32(s.ring[0]), s.w_full, s.w_empty, kTailStages, 0, 0u};
             uint32_t d1a_phase[2] = {0, 0};
-            const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128);
+            const uint32_t id64 = make_idesc_bf16(128, 64), id128 = make_idesc_bf16(128, 128), id128h = make_idesc_f16(128, 128);
             const uint32_t a2 = smem_u32(s.a2), big = smem_u32(s.big);
             TL_STAMP_DECL(1024)
 #define TL_WAIT(bar, par, code)                                                  \
@@ -733,9 +751,16 @@ split_tail_kernel(const TailParams p)
                     if (c + 2 < 4) TL_ISSUE_D1(c + 2)
                     // dconv2 partial sum over input channels c*128..+128: D2[:, nc*128..] += CB[j] x Wd2[nc*128.., c*128..]
                     const uint32_t cb = big + j * 65536;
-                    for (int nc = 0; nc < 2; ++nc)
-                        for (int kb = 0; kb < 2; ++kb)
-                            SPLIT_MMA_BLOCK(ring, tmem + kTD2 + nc * 128, cb + kb * 8 * kPlane, 32768u, kPlane, 128, 128, id128, c == 0 && kb == 0, 0x3320)
+                    if (p.d2_mode) {
+                        const bool two = p.d2_mode == 2;
+                        for (int nc = 0; nc < 2; ++nc)
+                            for (int kb = 0; kb < 2; ++kb)
+                                SPLIT_MMA_BLOCK_F16(ring, tmem + kTD2 + nc * 128, cb + kb * 8 * kPlane, 32768u, kPlane, 128, 128, id128h, c == 0 && kb == 0, two, 0x3320)
+                    } else {
+                        for (int nc = 0; nc < 2; ++nc)
+                            for (int kb = 0; kb < 2; ++kb)
+                                SPLIT_MMA_BLOCK(ring, tmem + kTD2 + nc * 128, cb + kb * 8 * kPlane, 32768u, kPlane, 128, 128, id128, c == 0 && kb == 0, 0x3320)
+                    }
                     if (c + 2 < 4) mma_commit(&s.cb_free[j]);          // chunk c + 2 may overwrite CB[j] once these have run
                     TL_STAMP(0x120 + c);
                 }
@@ -818,7 +843,7 @@ split_tail_kernel(const TailParams p)
                 if (!mbar_wait(&s.cb_free[j_], cbf_phase[j_], 0x2210 + (c), wd)) goto done;   /* dconv2 partial c - 2 has read CB[j] */ \
                 cbf_phase[j_] ^= 1;                                                                           \
             }                                                                                                 \
-            epilogue_split(tl + (j_ ? kTDB : kTDA), half * 64, 64, s.big + j_ * 65536, 32768u, kPlane, row, s.gb + (c) * 128); \
+            chunk_epilogue(p.d2_mode, tl + (j_ ? kTDB : kTDA), half * 64, s.big + j_ * 65536, row, s.gb + (c) * 128); \
             TL_PUBLISH(&s.d1_act[j_]);                                                                        \
         }
         int b, pidx; bool valid;
@@ -1200,8 +1225,10 @@ extern "C" int al3d_chain_maxpool_bf16x3(const al3d_split_chain_weights *w, cons
     p.w0_w = w->w0_w; p.w0_b = w->w0_b; p.mid_b = w->mid_b; p.last_b = w->last_b;
     p.wstream = (const uint8_t *)w->wstream; p.out = out;
     p.pair = w->pair ? 1 : 0;
+    p.last_f16 = w->last_f16 ? 1 : 0;
+    AL3D_CHECK_ARG(!p.last_f16 || p.pair, "al3d_chain_maxpool_bf16x3: last_f16 needs pair mode");
     p.front_blocks = front_blocks;
-    p.last_blocks = 2 * (w->last / 128) * (prev / 64);
+    p.last_blocks = (p.last_f16 ? 1 : 2) * (w->last / 128) * (prev / 64);
     AL3D_CHECK_ARG(w->n_blocks == p.front_blocks + p.last_blocks, "al3d_chain_maxpool_bf16x3: n_blocks=%d, expected %d", w->n_blocks,
                    p.front_blocks + p.last_blocks);
     if (tc_launch_status(&p.wd)) return 1;
@@ -1251,6 +1278,9 @@ extern "C" int al3d_seg_pass2_bf16x3(const al3d_split_tail_weights *w, const flo
     p.w1_w = w->w1_w; p.w1_b = w->w1_b; p.b2 = w->b2; p.gbias = gbias;
     p.bd2 = w->bd2; p.bd3 = w->bd3; p.bd4 = w->bd4; p.w5 = w->w5; p.b5 = w->b5;
     p.wstream = (const uint8_t *)w->wstream; p.logits = logits; p.mask = mask;
+    AL3D_CHECK_ARG(w->d2_mode >= 0 && w->d2_mode <= 2, "al3d_seg_pass2_bf16x3: d2_mode=%d", w->d2_mode);
+    AL3D_CHECK_ARG(w->d2_mode == 0 || w->wstream_pair == nullptr, "al3d_seg_pass2_bf16x3: the CTA-pair kernel has no fp16 dconv2");
+    p.d2_mode = w->d2_mode;
     if (tc_launch_status(&p.wd)) return 1;
     p.tiles_per_obj = (n + kTile - 1) / kTile;
     const int64_t items = (int64_t)bs * p.tiles_per_obj;

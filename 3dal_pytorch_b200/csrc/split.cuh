@@ -2,6 +2,7 @@
 // the epilogue that converts an accumulator row into split operand planes, the weight ring as the MMA issuer sees it,
 // and the three-MMA block.  See chain_split.cu for the arithmetic.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -52,8 +53,33 @@ __device__ __forceinline__ void split3(float a, float b, uint32_t &hi, uint32_t 
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(sb), "f"(sa));
 }
 
+// IEEE fp16 operands for the layers of the "mixed" mode (see chain_split.cu): 11 significant bits per number instead
+// of 8.  (a, b) fp32 >= 0 -> {f16(a), f16(b)}, a in the low half; values above the fp16 range saturate to 65504.
+__device__ __forceinline__ uint32_t pack_f16(float a, float b)
+{
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(fminf(b, 65504.f)), "f"(fminf(a, 65504.f)));
+    return r;
+}
+__device__ __forceinline__ float f16_lo_f32(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)(h & 0xFFFFu))); }
+__device__ __forceinline__ float f16_hi_f32(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)(h >> 16))); }
+// hi = f16(x), lo = f16(x - hi): 22 significant bits together (less below 2^-14, where lo is subnormal: the absolute
+// error stays under 3e-8).
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    hi = pack_f16(a, b);
+    const float ra = fminf(a, 65504.f) - f16_lo_f32(hi), rb = fminf(b, 65504.f) - f16_hi_f32(hi);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
+// Operand formats an epilogue can write.
+constexpr int kFmtBf16x2 = 0;      // hi | lo planes of bf16 (the bf16x3 layers)
+constexpr int kFmtF16 = 1;         // one plane set of fp16 (hi half of the buffer; the lo half is not touched)
+constexpr int kFmtF16x2 = 2;       // hi | lo planes of fp16
+
 // 32 accumulator columns (channels c .. c+31 of this thread's row) -> + bias, ReLU, hi / lo split -> four 16-byte
 // plane rows in each half of the operand buffer.  dst: address of (plane c/8, row) in the hi half.
+template <int kFmt = kFmtBf16x2>
 __device__ __forceinline__ void store_split32(uint8_t *dst, uint32_t lo_off, uint32_t plane_stride, const uint32_t (&v)[32],
                                               const float *bias)
 {
@@ -61,17 +87,28 @@ __device__ __forceinline__ void store_split32(uint8_t *dst, uint32_t lo_off, uin
     for (int j = 0; j < 4; ++j) {
         const float4 b0 = *reinterpret_cast<const float4 *>(bias + j * 8);
         const float4 b1 = *reinterpret_cast<const float4 *>(bias + j * 8 + 4);
+        const float y0 = fmaxf(__uint_as_float(v[j * 8 + 0]) + b0.x, 0.f), y1 = fmaxf(__uint_as_float(v[j * 8 + 1]) + b0.y, 0.f);
+        const float y2 = fmaxf(__uint_as_float(v[j * 8 + 2]) + b0.z, 0.f), y3 = fmaxf(__uint_as_float(v[j * 8 + 3]) + b0.w, 0.f);
+        const float y4 = fmaxf(__uint_as_float(v[j * 8 + 4]) + b1.x, 0.f), y5 = fmaxf(__uint_as_float(v[j * 8 + 5]) + b1.y, 0.f);
+        const float y6 = fmaxf(__uint_as_float(v[j * 8 + 6]) + b1.z, 0.f), y7 = fmaxf(__uint_as_float(v[j * 8 + 7]) + b1.w, 0.f);
         uint4 h, l;
-        split2(fmaxf(__uint_as_float(v[j * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[j * 8 + 1]) + b0.y, 0.f), h.x, l.x);
-        split2(fmaxf(__uint_as_float(v[j * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[j * 8 + 3]) + b0.w, 0.f), h.y, l.y);
-        split2(fmaxf(__uint_as_float(v[j * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[j * 8 + 5]) + b1.y, 0.f), h.z, l.z);
-        split2(fmaxf(__uint_as_float(v[j * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[j * 8 + 7]) + b1.w, 0.f), h.w, l.w);
-        *reinterpret_cast<uint4 *>(dst + (size_t)j * plane_stride) = h;
-        *reinterpret_cast<uint4 *>(dst + lo_off + (size_t)j * plane_stride) = l;
+        if (kFmt == kFmtF16) {
+            h.x = pack_f16(y0, y1); h.y = pack_f16(y2, y3); h.z = pack_f16(y4, y5); h.w = pack_f16(y6, y7);
+            *reinterpret_cast<uint4 *>(dst + (size_t)j * plane_stride) = h;
+        } else {
+            if (kFmt == kFmtF16x2) {
+                split2_f16(y0, y1, h.x, l.x); split2_f16(y2, y3, h.y, l.y); split2_f16(y4, y5, h.z, l.z); split2_f16(y6, y7, h.w, l.w);
+            } else {
+                split2(y0, y1, h.x, l.x); split2(y2, y3, h.y, l.y); split2(y4, y5, h.z, l.z); split2(y6, y7, h.w, l.w);
+            }
+            *reinterpret_cast<uint4 *>(dst + (size_t)j * plane_stride) = h;
+            *reinterpret_cast<uint4 *>(dst + lo_off + (size_t)j * plane_stride) = l;
+        }
     }
 }
 
 // Accumulator columns [c0, c0 + ncols) of this thread's TMEM lane -> split operand planes (ncols multiple of 32).
+template <int kFmt = kFmtBf16x2>
 __device__ __forceinline__ void epilogue_split(uint32_t taddr, int c0, int ncols, uint8_t *buf, uint32_t lo_off, uint32_t plane_stride,
                                                int buf_row, const float *bias)
 {
@@ -79,7 +116,7 @@ __device__ __forceinline__ void epilogue_split(uint32_t taddr, int c0, int ncols
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
-        store_split32(buf + (size_t)(c >> 3) * plane_stride + (size_t)buf_row * 16, lo_off, plane_stride, v, bias + c);
+        store_split32<kFmt>(buf + (size_t)(c >> 3) * plane_stride + (size_t)buf_row * 16, lo_off, plane_stride, v, bias + c);
     }
 }
 
@@ -160,6 +197,28 @@ struct RingView {
           SPLIT_RING_RELEASE(r) }                                                                                    \
     }
 
+// fp16 forms (one weight slot per block, fp16 idesc).  kTerms = 1: D (+)= A_hi * W; kTerms = 2: D (+)= (A_hi + A_lo) * W.
+#define SPLIT_MMA_BLOCK_F16(r, d_tmem, a_hi, a_lo_off, a_plane, a_rows, w_rows, idesc, first, two_terms, code)       \
+    {                                                                                                                \
+        SPLIT_RING_NEXT(r, code)                                                                                     \
+        _Pragma("unroll")                                                                                            \
+        for (int k_ = 0; k_ < 4; ++k_) {                                                                             \
+            const uint64_t db_ = make_desc(wst_ + k_ * 2 * (w_rows) * 16, (w_rows));                                 \
+            mma_bf16((d_tmem), make_desc((a_hi) + k_ * 2 * (a_plane), (a_rows)), db_, (idesc), ((first) && k_ == 0) ? 0u : 1u); \
+            if (two_terms) mma_bf16((d_tmem), make_desc((a_hi) + (a_lo_off) + k_ * 2 * (a_plane), (a_rows)), db_, (idesc), 1u); \
+        }                                                                                                            \
+        SPLIT_RING_RELEASE(r)                                                                                        \
+    }
+// Transposed, one term: D^T[128 channels x n_pts] (+)= W[128 x 64] * Act_hi[n_pts x 64]^T.
+#define SPLIT_MMA_BLOCK_T_F16(r, d_tmem, b_hi, b_plane, b_rows, idesc, first, code)                                  \
+    {                                                                                                                \
+        SPLIT_RING_NEXT(r, code)                                                                                     \
+        _Pragma("unroll")                                                                                            \
+        for (int k_ = 0; k_ < 4; ++k_)                                                                               \
+            mma_bf16((d_tmem), make_desc(wst_ + k_ * 4096, 128), make_desc((b_hi) + k_ * 2 * (b_plane), (b_rows)), (idesc), \
+                     ((first) && k_ == 0) ? 0u : 1u);                                                                \
+        SPLIT_RING_RELEASE(r)                                                                                        \
+    }
 
 }  // namespace split
 }  // namespace al3d

@@ -7,7 +7,7 @@ reference's static_eval.py / static_train.py can import them unchanged (INTEGRAT
 forward runs entirely in libal3d.so (sm_100a CUDA); the nn.Conv1d / nn.BatchNorm1d / nn.Linear
 children only hold parameters (identical default initialisation and key names) and are never called.
 
-Extra, non-reference attributes: ``precision`` ("fp32" SIMT | "bf16x3" split-precision tensor cores | "bf16" fast tensor cores) and ``gather_policy``
+Extra, non-reference attributes: ``precision`` ("fp32" SIMT | "bf16x3" split-precision tensor cores | "mixed" bf16x3 with conv5 / dconv2 in fp16 | "bf16" fast tensor cores) and ``gather_policy``
 ("strided" device rule | "numpy_legacy" reference RNG replay).
 """
 import numpy as np
@@ -106,7 +106,10 @@ class _AutoLabelBase(nn.Module):
         if self.precision == "bf16x3":
             from . import engine_split
             return engine_split
-        raise ValueError("precision must be 'fp32', 'bf16x3' or 'bf16', got %r" % (self.precision,))
+        if self.precision == "mixed":
+            from . import engine_split
+            return engine_split.mixed
+        raise ValueError("precision must be 'fp32', 'bf16x3', 'mixed' or 'bf16', got %r" % (self.precision,))
 
     def _seg(self, pts):
         fw = self._packs.get("seg_f32", self.ins_seg, lambda: engine.fold_block(self.ins_seg, self.ins_seg._table))

@@ -401,6 +401,11 @@ int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, int64_t sb,
  * a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (three tcgen05.mma per K step, fp32 accumulation): 16 significant bits per
  * operand, logits within ~5e-5 of the fp32 reference (bf16: ~2e-2, fp16 / tf32 operands: ~3e-3).
  * Weights: 16 KB slots, KP layout, a hi slot followed by a lo slot per (<=128 rows x 64 K) block, in consumption order.
+ * "mixed" mode (last_f16 / d2_mode below): the two widest layers of PointNetInstanceSeg -- conv5 128 -> 1024
+ * (tools/static_model.py:283) and dconv2 512 -> 256 (:290), 73 % of the network's MACs -- multiply IEEE fp16 operands
+ * (11 significant bits, fp32 accumulation) with one / two MMAs per product instead of three; every other layer stays
+ * bf16x3.  Logits within ~4e-4 of the fp32 reference (profiles/r2_precision_study_mixed.txt).  Activations above the
+ * fp16 range (65504) saturate in those two layers.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct al3d_split_chain_weights {
     int32_t c_in;            /* input channels (1..8)                                                          */
@@ -410,7 +415,8 @@ typedef struct al3d_split_chain_weights {
     int32_t last;            /* width of the max-pooled last layer (multiple of 128, <= 1024)                   */
     int32_t n_blocks;        /* number of 16 KB slots in wstream                                                */
     int32_t pair;            /* 1: the last layer runs on pairs of 128-point tiles (its input must fit 128 KB)  */
-    int32_t reserved;
+    int32_t last_f16;        /* pair = 1 only.  1: the last layer multiplies IEEE fp16 operands, ONE MMA per product
+                                (its blocks are single fp16 slots, no lo slot): the "mixed" mode, see below          */
     const float *w0_w;       /* (8, w0) fp32, transposed, zero rows for c >= c_in                               */
     const float *w0_b;       /* (w0)                                                                            */
     const float *mid_b;      /* concatenated fp32 biases of the mid layers                                      */
@@ -423,7 +429,9 @@ int al3d_chain_maxpool_bf16x3(const al3d_split_chain_weights *w, const float *x,
 
 typedef struct al3d_split_tail_weights {
     int32_t c_in;
-    int32_t reserved;
+    int32_t d2_mode;               /* dconv2 (512 -> 256, 61 % of this kernel's MACs): 0 = bf16x3 like every other layer (54 slots);
+                                      1 = fp16 activations x fp16 weights, one MMA per product; 2 = fp16 hi + lo activations x fp16
+                                      weights, two MMAs.  1 / 2: the sixteen p(c) blocks are single fp16 slots (38 slots in all)   */
     const float *w1_w, *w1_b;      /* ins_seg.conv1 folded fp32: (8,64) transposed + padded, (64)  */
     const float *b2;               /* conv2 bias (64)                                               */
     const float *bd2, *bd3, *bd4;  /* dconv2-4 biases (256),(128),(128)                             */

@@ -117,7 +117,7 @@ def bench_dynamic():
         pts = torch.from_numpy(np.tile(tr["pts_pm"], (rep, 1, 1))[:bs]).to(DEV).transpose(2, 1)
         box = torch.from_numpy(np.tile(tr["box_sm"], (rep, 1, 1))[:bs]).to(DEV).transpose(2, 1)
         m = _calibrated("dynamic", dm.DynamicModel, pts, box)
-        for prec in ("bf16x3", "bf16", "fp32") if bs == 64 else ("bf16x3", "bf16"):
+        for prec in ("mixed", "bf16x3", "bf16", "fp32") if bs == 64 else ("mixed", "bf16x3", "bf16"):
             m.precision = prec
             ms = timed(lambda: m(pts, box, None), iters=5)
             fl = spec.flops_per_object("dynamic", 5120)
@@ -135,7 +135,7 @@ def bench_static32():
     ib, gt = torch.from_numpy(tr["init_box"]).to(DEV), torch.from_numpy(tr["bbox_gt"]).to(DEV)
     for kind, cls in (("static_one", sm.StaticModelOneBoxEst), ("static_two", sm.StaticModelTwoBoxEst)):
         m = _calibrated(kind, cls, pts, ib)
-        for prec in ("bf16x3", "bf16", "fp32"):
+        for prec in ("mixed", "bf16x3", "bf16", "fp32"):
             m.precision = prec
             ms = timed(lambda: m(pts, ib, gt), iters=10)
             row = {"bench": "static32", "model": kind, "tracks": 32, "precision": prec, "ms": ms, "objects_per_s": 32 / (ms * 1e-3)}

@@ -27,7 +27,7 @@ def rel(a, b):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
-    ap.add_argument("--precisions", default="fp32,bf16x3,bf16")
+    ap.add_argument("--precisions", default="fp32,bf16x3,mixed,bf16")
     ap.add_argument("--fg", type=float, default=0.3)
     args = ap.parse_args()
     ge.build()

@@ -113,3 +113,52 @@ def emulate_seg_bf16(fw, x):
     d = bf16_round(torch.relu(d @ bf16_round(fw["dconv3"][0]).t() + fw["dconv3"][1]))
     d = torch.relu(d @ bf16_round(fw["dconv4"][0]).t() + fw["dconv4"][1])     # stays fp32
     return d @ fw["dconv5"][0].t() + fw["dconv5"][1]
+
+
+def _round_mantissa(t, bits):
+    """Round-to-nearest-even to `bits` explicit mantissa bits (fp32 in, fp32 out)."""
+    i = t.contiguous().view(torch.int32)
+    drop = 23 - bits
+    bias = ((i >> drop) & 1) + (1 << (drop - 1)) - 1
+    return (((i + bias) >> drop) << drop).view(torch.float32)
+
+
+def bf16x2_round(t):
+    """hi + lo of the bf16x3 kernels: bf16(x) + bf16(x - bf16(x))."""
+    hi = bf16_round(t)
+    return hi + bf16_round(t - hi)
+
+
+def f16_round(t):
+    return t.clamp(max=65504.0).half().float()
+
+
+def f16x2_round(t):
+    hi = f16_round(t)
+    return hi + (t.clamp(max=65504.0) - hi).half().float()
+
+
+def emulate_seg_mixed(fw, x, conv5_f16=True, d2_mode=2):
+    """Numerics model of the split-precision segmentation kernels (csrc/chain_split.cu) evaluated in float64 on rounded
+    operands: every layer bf16 hi+lo x hi+lo, except conv5 (fp16 x fp16 when conv5_f16) and dconv2 (d2_mode 1: fp16 x
+    fp16, 2: fp16 hi+lo x fp16).  -> logits (bs,n,2) float64, global feature (bs,1024) float64."""
+    A, W = bf16x2_round, bf16x2_round
+
+    def lin(a, w, ra=A, rw=W):
+        return ra(a).double() @ rw(w).double().t()
+
+    h = x.transpose(2, 1).float()
+    o1 = torch.relu(h @ fw["conv1"][0].t() + fw["conv1"][1])
+    o2 = torch.relu(lin(o1, fw["conv2"][0]) + fw["conv2"][1]).float()
+    o3 = torch.relu(lin(o2, fw["conv3"][0]) + fw["conv3"][1]).float()
+    o4 = torch.relu(lin(o3, fw["conv4"][0]) + fw["conv4"][1]).float()
+    r5 = (f16_round, f16_round) if conv5_f16 else (A, W)
+    g = torch.relu(lin(o4, fw["conv5"][0], *r5).max(dim=1)[0] + fw["conv5"][1])
+    wd1, bd1 = fw["dconv1"]
+    gb = g @ wd1[:, 64:].double().t() + bd1
+    d = torch.relu(lin(o2, wd1[:, :64]) + gb[:, None, :]).float()
+    r2 = {0: (A, W), 1: (f16_round, f16_round), 2: (f16x2_round, f16_round)}[d2_mode]
+    d = torch.relu(lin(d, fw["dconv2"][0], *r2) + fw["dconv2"][1]).float()
+    d = torch.relu(lin(d, fw["dconv3"][0]) + fw["dconv3"][1]).float()
+    d = torch.relu(lin(d, fw["dconv4"][0]) + fw["dconv4"][1])
+    return d @ fw["dconv5"][0].double().t() + fw["dconv5"][1], g

@@ -24,7 +24,7 @@ def _inputs(kind, bs, seed):
 
 @pytest.mark.parametrize("kind,cls,bs", [("static_one", sm.StaticModelOneBoxEst, 32), ("static_two", sm.StaticModelTwoBoxEst, 32),
                                          ("dynamic", dm.DynamicModel, 16)])
-@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("precision", ["mixed", "bf16x3", "fp32"])
 def test_graph_replay_equals_eager(kind, cls, bs, precision):
     model = cls().to(DEV).eval()
     model.load_state_dict(synth.random_state_dict(kind, seed=11))

@@ -21,10 +21,12 @@ MODEL = {"static_one": sm.StaticModelOneBoxEst, "static_two": sm.StaticModelTwoB
 # Float tolerance of BASELINE.json's north_star: 1e-3 relative (per tensor, to max|ref|).  The fp32 SIMT mode is held
 # to 1e-4 and the split-precision tensor-core mode (bf16x3) to the 1e-3 bar itself (measured ~5e-5,
 # profiles/r2_parity_per_tensor.jsonl); plain bf16 (8-bit mantissa) states its own, looser tolerance.
-TOL = {"fp32": 1e-4, "bf16x3": 1e-3, "bf16": 3e-2}
+# "mixed" (bf16x3 with conv5 / dconv2 of the segmentation net in fp16) is held to the same 1e-3 bar (emulated 4e-5 .. 1.1e-4
+# on these cases, profiles/r2_precision_study_mixed.txt).
+TOL = {"fp32": 1e-4, "bf16x3": 1e-3, "mixed": 1e-3, "bf16": 3e-2}
 # A mask bit is `l0 < l1` of OUR logits; against the fp32 reference it may differ only where the reference margin
 # |l1 - l0| is inside the logit tolerance (2 * TOL * max|logit|: both logits can move).
-PRECISIONS = ["fp32", "bf16x3", "bf16"]
+PRECISIONS = ["fp32", "bf16x3", "mixed", "bf16"]
 
 
 def _check_outputs(out, z, policy, prec, sd, pts, aux, gt):

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import emulate_chain_bf16, emulate_seg_bf16, fold_state_dict, rel_err, spec, synth  # noqa: E402
+from helpers import emulate_chain_bf16, emulate_seg_bf16, emulate_seg_mixed, fold_state_dict, rel_err, spec, synth  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -160,6 +160,65 @@ def test_split_seg_matches_fp64(C, n, bs):
     ref = d @ fw["dconv5"][0].double().t() + fw["dconv5"][1].double()
     assert rel_err(logits.cpu(), ref.cpu()) < 3e-4, rel_err(logits.cpu(), ref.cpu())
     assert torch.equal(mask, logits[..., 0] < logits[..., 1])
+
+
+@pytest.mark.parametrize("conv5_f16,d2_mode", [(True, 2), (True, 1), (False, 2), (True, 0)])
+@pytest.mark.parametrize("C,n,bs", [(3, 4096, 2), (4, 5120, 2), (3, 1000, 3), (3, 300, 310), (3, 129, 1)])
+def test_mixed_seg_matches_its_numerics_model(C, n, bs, conv5_f16, d2_mode):
+    """"mixed" mode: conv5 as one fp16 MMA per product, dconv2 with fp16 (hi + lo) activations x fp16 weights, the other
+    layers bf16x3.  Against the float64 evaluation on operands rounded the same way (tests/helpers.emulate_seg_mixed) the
+    kernels agree to ~1e-4 of the largest logit (a wrong block, format or descriptor shows up as >= 1e-1); against plain
+    float64 they stay inside the 1e-3 bar."""
+    kind = "dynamic" if C == 4 else "static_one"
+    sd = synth.random_state_dict(kind, seed=6)
+    fw = fold_state_dict(sd, "ins_seg", spec.seg_layers(C))
+    torch.manual_seed(1)
+    x = (torch.randn(bs, n, C) * torch.tensor([2.0, 2.0, 0.7, 0.2][:C])).transpose(2, 1)
+    emu, emu_g = emulate_seg_mixed(fw, x, conv5_f16=conv5_f16, d2_mode=d2_mode)
+    exact, exact_g = _fp64_seg(fw, x)
+    fwd = _dev(fw)
+    pack = es.SplitSegPack(fwd, C, conv5_f16=conv5_f16, d2_mode=d2_mode)
+    assert pack.pass1.struct.n_blocks == 6 + (16 if conv5_f16 else 32)       # conv2-4: one (hi, lo) block each; conv5: 8 chunks x 2 k blocks
+    xd = x.to(DEV)
+    g = es.chain_maxpool(pack.pass1, xd)
+    # (an activation that sits on an fp16 rounding boundary may round the other way than in the model: one fp16 ulp, 5e-4 of
+    # that value; measured 1.6e-4 on the pooled feature)
+    assert rel_err(g.cpu(), emu_g) < 5e-4, rel_err(g.cpu(), emu_g)
+    logits, mask = es.seg_forward(pack, fwd, xd)
+    torch.cuda.synchronize()
+    assert rel_err(logits.cpu(), emu) < 3e-4, rel_err(logits.cpu(), emu)
+    assert rel_err(logits.cpu(), exact) < 1e-3, rel_err(logits.cpu(), exact)
+    assert torch.equal(mask, logits[..., 0] < logits[..., 1])
+    # strided and contiguous inputs give the same bits
+    l2, m2 = es.seg_forward(pack, fwd, xd.contiguous())
+    assert torch.equal(l2, logits) and torch.equal(m2, mask)
+
+
+def _fp64_seg(fw, x):
+    h = x.transpose(2, 1).double()
+    o1 = torch.relu(h @ fw["conv1"][0].double().t() + fw["conv1"][1].double())
+    o2 = torch.relu(o1 @ fw["conv2"][0].double().t() + fw["conv2"][1].double())
+    o = o2
+    for nm in ("conv3", "conv4"):
+        o = torch.relu(o @ fw[nm][0].double().t() + fw[nm][1].double())
+    g = torch.relu((o @ fw["conv5"][0].double().t()).max(dim=1)[0] + fw["conv5"][1].double())
+    wd1, bd1 = fw["dconv1"]
+    gb = g @ wd1[:, 64:].double().t() + bd1.double()
+    d = torch.relu(o2 @ wd1[:, :64].double().t() + gb[:, None, :])
+    for nm in ("dconv2", "dconv3", "dconv4"):
+        d = torch.relu(d @ fw[nm][0].double().t() + fw[nm][1].double())
+    return d @ fw["dconv5"][0].double().t() + fw["dconv5"][1].double(), g
+
+
+def test_mixed_mode_saturates_above_the_fp16_range():
+    """Activations above 65504 saturate in the two fp16 layers (documented); finite inputs never produce inf / NaN logits."""
+    sd = synth.random_state_dict("static_one", seed=6)
+    fw = _dev(fold_state_dict(sd, "ins_seg", spec.seg_layers(3)))
+    x = (torch.randn(2, 512, 3, device=DEV) * 1e6).transpose(2, 1)
+    pack = es.SplitSegPack(fw, 3, conv5_f16=True, d2_mode=2)
+    logits, mask = es.seg_forward(pack, fw, x)
+    torch.cuda.synchronize()
+    assert torch.isfinite(logits).all()
 
 
 def test_split_tail_pair_kernel_equals_single_cta_kernel():

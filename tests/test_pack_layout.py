@@ -93,3 +93,56 @@ def test_pass2_stream_order_matches_kernel_schedule():
             assert torch.equal(got, w[r * rows:(r + 1) * rows]), (name, r)
             off += rows * 64
     assert pack.struct.c_in == 4 and pack.w_glob.shape == (512, 1024)
+
+
+def test_mixed_mode_streams_single_fp16_slots_for_conv5_and_dconv2():
+    """"mixed" mode: conv5 (pass 1) and the sixteen dconv2 partial-sum blocks (tail) are ONE slot of IEEE fp16 each, in the
+    consumption order of csrc/chain_split.cu; every other block keeps its (hi, lo) bf16 slots."""
+    es = importlib.import_module("3dal_pytorch_b200.engine_split")
+    sd = synth.random_state_dict("static_one", seed=4)
+    fw = fold_state_dict(sd, "ins_seg", spec.seg_layers(3))
+    ref = es.SplitSegPack(fw, 3)
+    mix = es.mixed.pack_seg(fw, 3)
+    assert (ref.pass1.struct.last_f16, ref.struct.d2_mode) == (0, 0)
+    assert (mix.pass1.struct.last_f16, mix.struct.d2_mode) == (1, es.D2_F16X2)
+    # pass 1: conv2-4 as before (one block x (hi, lo) each), then conv5's 8 row chunks x 2 k blocks, single slots
+    a, b = _blocks(ref.pass1.t["wstream"]), _blocks(mix.pass1.t["wstream"])
+    assert (a.shape[0], b.shape[0]) == (6 + 32, 6 + 16) and mix.pass1.struct.n_blocks == 22
+    assert torch.equal(a[:6], b[:6])
+    w5 = fw["conv5"][0]
+    for cc in range(8):
+        for kb in range(2):
+            got = kp_unpack(b[6 + cc * 2 + kb].view(torch.float16).float(), 128, 64)
+            assert torch.equal(got, w5[cc * 128:(cc + 1) * 128, kb * 64:(kb + 1) * 64].half().float()), (cc, kb)
+    # tail: conv2 | d1(0) d1(1) d1(2) | p(0) | d1(3) | p(1) p(2) p(3) | dconv3 | dconv4 with p(c) = 4 single fp16 slots
+    a, b = _blocks(ref.t["wstream"]), _blocks(mix.t["wstream"])
+    assert (a.shape[0], b.shape[0]) == (54, 38)
+    wd2 = fw["dconv2"][0]
+    ia = ib = 0
+    for kind, c in [("x", 0)] * 4 + [("p", 0), ("x", 0), ("p", 1), ("p", 2), ("p", 3)] + [("x", 0)] * 6:
+        if kind == "x":
+            assert torch.equal(a[ia:ia + 2], b[ib:ib + 2])
+            ia, ib = ia + 2, ib + 2
+        else:
+            for nc in range(2):
+                for kb in range(2):
+                    got = kp_unpack(b[ib].view(torch.float16).float(), 128, 64)
+                    assert torch.equal(got, wd2[nc * 128:(nc + 1) * 128, c * 128 + kb * 64:c * 128 + (kb + 1) * 64].half().float()), (c, nc, kb)
+                    ia, ib = ia + 2, ib + 1
+    assert (ia, ib) == (54, 38)
+
+
+def test_mixed_mode_keeps_a_layer_bf16x3_when_its_weights_exceed_the_fp16_range():
+    es = importlib.import_module("3dal_pytorch_b200.engine_split")
+    sd = synth.random_state_dict("static_one", seed=4)
+    fw = fold_state_dict(sd, "ins_seg", spec.seg_layers(3))
+    w, b = fw["conv5"]
+    w = w.clone()
+    w[3, 5] = 7.0e4
+    fw["conv5"] = (w, b)
+    pk = es.mixed.pack_seg(fw, 3)
+    assert (pk.pass1.struct.last_f16, pk.pass1.struct.n_blocks, pk.struct.d2_mode) == (0, 6 + 32, es.D2_F16X2)
+    w2, b2 = fw["dconv2"]
+    fw["dconv2"] = (w2 * 1e6, b2)
+    pk = es.mixed.pack_seg(fw, 3)
+    assert (pk.pass1.struct.last_f16, pk.struct.d2_mode, pk.t["wstream"].numel()) == (0, es.D2_BF16X3, 54 * eb.BLOCK_ELEMS)
