@@ -74,12 +74,14 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def _traffic(kernel):
+def _traffic(kernel, precision=None):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json names the
-    .csv it was read from); None when that kernel has not been captured."""
+    .csv it was read from; the mixed mode's kernels are stored under "mixed:<kernel>"); None when that kernel has not
+    been captured."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
-        return json.load(open(path)).get(kernel)
+        d = json.load(open(path))
+        return d.get("%s:%s" % (precision, kernel), d.get(kernel))
     return None
 
 
@@ -528,7 +530,7 @@ def main():
         capped = bool(clocks) and clocks.get("sm_mhz") and clocks["sm_mhz"] < 0.97 * clocks.get("sm_max_mhz", 1e9)
         peak = peaks["bf16_tflops_sustained"] if capped else peaks["bf16_tflops"]
         r = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-             "frac": ach / peak, "traffic": _traffic(dom),
+             "frac": ach / peak, "traffic": _traffic(dom, precision),
              "peak_source": peaks["source"] + (" bf16_tflops_sustained (the timed region ran power-capped below the maximum SM "
                                                "clock, see clocks)" if capped else
                                                " bf16_tflops (burst figure: the run held the maximum SM clock, see clocks)"),
