@@ -9,6 +9,14 @@
 // i.e. three tcgen05.mma (kind::f16, fp32 accumulation in TMEM) per K = 16 step instead of one.  The result matches the
 // fp32 reference to ~5e-5 of max|ref| on the logits; a mask bit can only differ where |l1 - l0| is within that error.
 //
+// "mixed" mode (ChainParams::last_f16, TailParams::d2_mode; the default of the Python side): the two widest layers of the
+// segmentation net -- conv5 128 -> 1024 and dconv2 512 -> 256, 73 % of its MACs and the two the logits are LEAST
+// sensitive to (profiles/r2_precision_study.txt) -- multiply IEEE fp16 operands (11 significant bits) instead: conv5
+// as f16(a) * f16(w), ONE MMA per product; dconv2 as (f16 hi + f16 lo of a) * f16(w), two.  Their weight blocks are
+// single fp16 slots, the epilogue in front of them writes fp16 planes (saturating at 65504), the instruction descriptor
+// names fp16 operands; nothing else changes.  63 % of the MMAs of bf16x3; logits within 4e-5 .. 4.4e-4 of the fp32
+// reference (profiles/r2_precision_study_mixed.txt, profiles/r2_parity_per_tensor.jsonl).
+//
 //   split_chain_kernel   first layer (tiny K, CUDA cores) -> 2-3 chained MMA layers, activations (hi | lo planes) in
 //                        shared memory, converted IN PLACE by the epilogue warps -> last layer computed transposed
 //                        (channels on TMEM lanes, points on columns) so the max over points is a per-thread reduction.

@@ -1,3 +1,3 @@
 cd /root/repo
-AL3D_CUDA_PROFILER_RANGE=1 timeout 300 ncu --profile-from-start off --set full --clock-control none -k regex:"split_(chain_pair|tail|chain)_kernel" -c 3 --csv --page raw --log-file gpurun_out/f3_ncu_full.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-fast-mode --no-crop --no-configs > gpurun_out/f3_ncu_full.log 2>&1; echo "ncu full rc=$?"
-tail -3 gpurun_out/f3_ncu_full.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/f4_bench_n2.json 2> gpurun_out/f4_bench_n2.err; echo "bench n2 rc=$?"
+tail -c 1500 gpurun_out/f4_bench_n2.json | head -c 1500; tail -3 gpurun_out/f4_bench_n2.err
