@@ -35,6 +35,7 @@
 // TMEM lanes (two warps per lane quarter, splitting the columns) and run the epilogues.  Every mbarrier that guards
 // a buffer is private to that buffer and strictly ping-pongs with its counterpart, so no parity wait can be lapped.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "umma.cuh"
 #include "split.cuh"
@@ -81,7 +82,8 @@ struct ChainParams {
     int pair;                                            // 1: tile pairs, split_chain_pair_kernel (last layer with N = 256 points)
     int act_bytes, pair_bytes, n_stages;                 // shared-memory carve-up chosen by the launcher
     int front_blocks, last_blocks;                       // 16 KB slots per tile (mid layers) / per unit (last layer)
-    int last_f16;                                        // pair kernel: the streamed last layer as ONE fp16 MMA per product
+    int last_f16;                                        // the streamed last layer as ONE fp16 MMA per product
+    int y_front_lo;                                      // pair kernel, last_f16 only: tile Y's front lives in the (then idle) lo half of the pair buffer
     TcStatus wd;
 };
 
@@ -181,7 +183,7 @@ split_chain_kernel(const ChainParams p)
                         if (!mbar_wait(&s.act_ready, act_phase, 0x52F0, wd)) goto done;
                         act_phase ^= 1;
                         tc_fence_after();
-                        const uint32_t idesc = make_idesc_bf16(128, 128);
+                        const uint32_t idesc = p.last_f16 ? make_idesc_f16(128, 128) : make_idesc_bf16(128, 128);
                         for (int cc = 0; cc < n_last_chunks; ++cc) {
                             const int b = cc & 1;
                             SPLIT_STRESS(wd, 0x54);
@@ -189,8 +191,13 @@ split_chain_kernel(const ChainParams p)
                             le_phase[b] ^= 1;
                             tc_fence_after();
                             const uint32_t d = tmem + 256 + b * 128;
-                            for (int kb = 0; kb < k_last / 64; ++kb)
-                                SPLIT_MMA_BLOCK_T(ring, d, a_act + kb * 8 * kPlane, act_lo, kPlane, 128, idesc, kb == 0, 0x5500)
+                            if (p.last_f16) {
+                                for (int kb = 0; kb < k_last / 64; ++kb)
+                                    SPLIT_MMA_BLOCK_T_F16(ring, d, a_act + kb * 8 * kPlane, kPlane, 128, idesc, kb == 0, 0x5500)
+                            } else {
+                                for (int kb = 0; kb < k_last / 64; ++kb)
+                                    SPLIT_MMA_BLOCK_T(ring, d, a_act + kb * 8 * kPlane, act_lo, kPlane, 128, idesc, kb == 0, 0x5500)
+                            }
                             mma_commit(&s.last_full[b]);
                         }
                     }
@@ -231,7 +238,8 @@ split_chain_kernel(const ChainParams p)
                     if (!mbar_wait(&s.acc_ready, acc_phase, 0x4100 + l, wd)) goto done;
                     acc_phase ^= 1;
                     tc_fence_after();
-                    epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_act, act_lo, kPlane, row, s.mid_b + boff);
+                    if (p.last_f16 && l == p.n_mid - 1) epilogue_split<kFmtF16>(tmem + lane_addr, half * (N >> 1), N >> 1, s_act, act_lo, kPlane, row, s.mid_b + boff);
+                    else epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_act, act_lo, kPlane, row, s.mid_b + boff);
                     boff += N;
                     tc_fence_before();
                     fence_proxy_async_smem();
@@ -427,8 +435,10 @@ split_chain_pair_kernel(const ChainParams p)
                         act_phase[q] ^= 1;
                         tc_fence_after();
                         CH_STAMP(0x110 + l * 2 + q);
-                        const uint32_t a_hi = q ? a_pair + kTile * 16 : a_act, a_lo = q ? pair_lo : act_lo;
-                        const uint32_t a_pl = q ? 2 * kPlane : kPlane, a_rows = q ? 2 * kTile : kTile;
+                        // tile Y's front: the Y rows of the pair buffer, or (y_front_lo) a buffer of X's shape in its lo half
+                        const bool yrows = q && !p.y_front_lo;
+                        const uint32_t a_hi = yrows ? a_pair + kTile * 16 : (q ? a_pair + pair_lo : a_act), a_lo = yrows ? pair_lo : act_lo;
+                        const uint32_t a_pl = yrows ? 2 * kPlane : kPlane, a_rows = yrows ? 2 * kTile : kTile;
                         for (int kb = 0; kb < K / 64; ++kb)
                             SPLIT_MMA_BLOCK(ring, tmem + q * 128, a_hi + kb * 8 * a_pl, a_lo, a_pl, a_rows, N, idesc, kb == 0, 0x5300)
                         mma_commit(&s.acc_ready[q]);
@@ -490,11 +500,20 @@ split_chain_pair_kernel(const ChainParams p)
             fence_proxy_async_smem();                                                                         \
             CH_ARRIVE(&s.act_ready[0]);                                                                       \
         }
+        // first layer of tile Y -> its front buffer in the lo half of the pair buffer (y_front_lo: nothing reads that half
+        // while the fp16 last layer streams, so this runs under it like X's)
+#define CP_FIRST_Y_LO()                                                                                       \
+        {                                                                                                     \
+            first_layer_split(s_pair + pair_lo, act_lo, row, xv[1], p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b); \
+            fence_proxy_async_smem();                                                                         \
+            CH_ARRIVE(&s.act_ready[1]);                                                                       \
+        }
         UnitIter u, nx;
         bool ok = unit_first(p, tiles_per_obj, u);
         if (ok) {
             CP_LOAD(u)
             CP_FIRST_X()
+            if (p.y_front_lo) CP_FIRST_Y_LO()
         }
         float rmax[8];
 #pragma unroll
@@ -504,9 +523,11 @@ split_chain_pair_kernel(const ChainParams p)
             CH_STAMP_E(0x200);
             // ---- first layer of tile Y -> the Y rows of the pair buffer (the previous unit's last layer has read it:
             //      this thread has seen its final accumulator)
-            first_layer_split(s_pair, pair_lo, kTile + row, xv[1], p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b, 2 * kPlane);
-            fence_proxy_async_smem();
-            CH_ARRIVE(&s.act_ready[1]);
+            if (!p.y_front_lo) {
+                first_layer_split(s_pair, pair_lo, kTile + row, xv[1], p.c_in, p.w0, half * (p.w0 >> 1), p.w0 >> 1, s.w0_w, s.w0_b, 2 * kPlane);
+                fence_proxy_async_smem();
+                CH_ARRIVE(&s.act_ready[1]);
+            }
             CH_STAMP_E(0x201);
             // ---- mid layers, X and Y alternating: this thread converts columns [half*N/2, (half+1)*N/2) of its row,
             //      in place (the layer's MMAs are complete when acc_ready fires); the last mid layer of both tiles
@@ -523,6 +544,7 @@ split_chain_pair_kernel(const ChainParams p)
                     tc_fence_after();
                     CH_STAMP_E(0x210 + l * 4 + q * 2);
                     if (last_mid && p.last_f16) epilogue_split<kFmtF16>(tmem + lane_addr + q * 128, half * (N >> 1), N >> 1, s_pair, pair_lo, 2 * kPlane, q * kTile + row, s.mid_b + boff);
+                    else if (q == 1 && p.y_front_lo) epilogue_split(tmem + lane_addr + 128, half * (N >> 1), N >> 1, s_pair + pair_lo, act_lo, kPlane, row, s.mid_b + boff);
                     else if (q == 1 || last_mid) epilogue_split(tmem + lane_addr + q * 128, half * (N >> 1), N >> 1, s_pair, pair_lo, 2 * kPlane, q * kTile + row, s.mid_b + boff);
                     else                    epilogue_split(tmem + lane_addr, half * (N >> 1), N >> 1, s_act, act_lo, kPlane, row, s.mid_b + boff);
                     tc_fence_before();
@@ -569,6 +591,7 @@ split_chain_pair_kernel(const ChainParams p)
                     CH_STAMP_E(0x231 + cc * 2);
                     if (has_next && cc == 0) CP_LOAD(nx)
                     if (has_next && cc == (n_last_chunks > 2 ? 2 : n_last_chunks - 1)) CP_FIRST_X()
+                    if (has_next && p.y_front_lo && cc == (n_last_chunks > 4 ? 4 : n_last_chunks - 1)) CP_FIRST_Y_LO()
                 }
             }
             // ---- end of the object's share: publish relu(max + bias) >= 0, so integer atomicMax on the bit pattern is exact
@@ -586,6 +609,7 @@ split_chain_pair_kernel(const ChainParams p)
             }
             u = nx; ok = has_next;
         }
+#undef CP_FIRST_Y_LO
 #undef CP_FIRST_X
 #undef CP_LOAD
     }
@@ -1234,7 +1258,7 @@ extern "C" int al3d_chain_maxpool_bf16x3(const al3d_split_chain_weights *w, cons
     p.wstream = (const uint8_t *)w->wstream; p.out = out;
     p.pair = w->pair ? 1 : 0;
     p.last_f16 = w->last_f16 ? 1 : 0;
-    AL3D_CHECK_ARG(!p.last_f16 || p.pair, "al3d_chain_maxpool_bf16x3: last_f16 needs pair mode");
+    p.y_front_lo = 0;
     p.front_blocks = front_blocks;
     p.last_blocks = (p.last_f16 ? 1 : 2) * (w->last / 128) * (prev / 64);
     AL3D_CHECK_ARG(w->n_blocks == p.front_blocks + p.last_blocks, "al3d_chain_maxpool_bf16x3: n_blocks=%d, expected %d", w->n_blocks,
@@ -1261,6 +1285,13 @@ extern "C" int al3d_chain_maxpool_bf16x3(const al3d_split_chain_weights *w, cons
         static_assert(sizeof(PairTail) <= sizeof(ChainTail) + 64, "PairTail must fit the ChainTail budget");
         AL3D_CHECK_ARG(act_w <= prev && prev <= 128, "al3d_chain_maxpool_bf16x3: pair mode needs mid widths <= 128 (got %d, %d)", act_w, prev);
         for (int l = 0; l < w->n_mid; ++l) AL3D_CHECK_ARG(w->mid[l] <= 128, "al3d_chain_maxpool_bf16x3: pair mode, mid width %d", w->mid[l]);
+        // fp16 last layer: the lo half of the pair buffer is idle while it streams; tile Y's front (a buffer of X's shape)
+        // moves there so that its first layer is computed under the previous unit's last layer (12.2 -> 11.8 ms per
+        // 8192 x 4096 launch).  AL3D_PAIR_Y_FRONT_LO=0 keeps it in the Y rows.
+        {
+            static const int ylo_env = [] { const char *e = getenv("AL3D_PAIR_Y_FRONT_LO"); return e ? atoi(e) : 1; }();
+            p.y_front_lo = (p.last_f16 && ylo_env && p.act_bytes <= p.pair_bytes / 2) ? 1 : 0;
+        }
         const size_t smem_pair = smem - sizeof(ChainTail) + sizeof(PairTail);
         AL3D_CHECK_CUDA(cudaFuncSetAttribute(split_chain_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair));
         split_chain_pair_kernel<<<grid, kThreads, smem_pair, (cudaStream_t)stream>>>(p);

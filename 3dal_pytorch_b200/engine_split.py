@@ -113,7 +113,6 @@ class SplitChainPack:
         self.c_in = w0.shape[1]
         self.t = {"w0_w": _pad8(w0), "w0_b": b0.contiguous(),
                   "mid_b": torch.cat([fw[m][1] for m in mids]).contiguous(), "last_b": fw[last][1].contiguous()}
-        assert pair or not last_f16
         slots = []
         for m in mids:
             slots += _layer_slots(fw[m][0])
@@ -169,13 +168,13 @@ def pack_seg(fw, c_in):
     return SplitSegPack(fw, c_in)
 
 
-def pack_trunk(fw):
-    return SplitChainPack(fw, ["conv1", "conv2", "conv3", "conv4"], pair=False)
+def pack_trunk(fw, last_f16=False):
+    return SplitChainPack(fw, ["conv1", "conv2", "conv3", "conv4"], pair=False, last_f16=last_f16)
 
 
 class _MixedEngine:
-    """precision = "mixed": the engine interface of this module with conv5 / dconv2 of the segmentation net in fp16 (the box-head
-    and embedding trunks are small and stay bf16x3)."""
+    """precision = "mixed": the engine interface of this module with conv5 / dconv2 of the segmentation net and the max-pooled
+    last layer of the box-head / embedding trunks in fp16."""
     CONV5_F16 = os.environ.get("AL3D_MIXED_CONV5", "1") == "1"
     D2_MODE = int(os.environ.get("AL3D_MIXED_D2", str(D2_F16X2)))
 
@@ -184,8 +183,11 @@ class _MixedEngine:
         fits = lambda name: float(fw[name][0].abs().max()) <= F16_MAX
         return SplitSegPack(fw, c_in, conv5_f16=self.CONV5_F16 and fits("conv5"), d2_mode=self.D2_MODE if fits("dconv2") else D2_BF16X3)
 
+    # the max-pooled last layer of the box-head / embedding trunks (72-76 % of their MACs) as one fp16 MMA per product
+    TRUNK_F16 = os.environ.get("AL3D_MIXED_TRUNK", "1") == "1"
+
     def pack_trunk(self, fw):
-        return pack_trunk(fw)
+        return pack_trunk(fw, last_f16=self.TRUNK_F16 and float(fw["conv4"][0].abs().max()) <= F16_MAX)
 
     def seg_forward(self, pack, fw, pts):
         return seg_forward(pack, fw, pts)

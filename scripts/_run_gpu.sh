@@ -1,3 +1,3 @@
 cd /root/repo
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/f4_bench_n2.json 2> gpurun_out/f4_bench_n2.err; echo "bench n2 rc=$?"
-tail -c 1500 gpurun_out/f4_bench_n2.json | head -c 1500; tail -3 gpurun_out/f4_bench_n2.err
+timeout 60 python -m pytest tests/test_pipeline.py tests/test_gpu_graphs.py -q -m gpu -k "mixed or pipeline" > gpurun_out/f6_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/f6_tests.log
+timeout 40 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/f6_smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/f6_smoke.log

@@ -28,7 +28,7 @@ def test_stress_suite_against_the_hooked_library():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu"], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
-    assert "5 passed" in r.stdout, r.stdout[-2000:]
+    assert "7 passed" in r.stdout, r.stdout[-2000:]
 
 DEV = "cuda:0"
 eb = importlib.import_module("3dal_pytorch_b200.engine_bf16")
@@ -57,6 +57,28 @@ def test_static_forward_is_bitwise_stable_under_injected_delays(stress_ns):
     try:
         eb.configure_watchdog(trap=False, stress_ns=stress_ns)
         for it in range(6):
+            out = m(pts, box, None)
+            torch.cuda.synchronize()
+            eb.check_abort("stress iteration %d" % it)
+            for k in ref:
+                assert torch.equal(out[k], ref[k]), (it, k)
+    finally:
+        eb.configure_watchdog(trap=True, stress_ns=0)
+
+
+@in_stress_process
+@pytest.mark.parametrize("stress_ns", [2000, 20000])
+def test_mixed_mode_forward_is_bitwise_stable_under_injected_delays(stress_ns):
+    """The split-precision kernels (csrc/chain_split.cu) in the default mixed mode: same requirement."""
+    m = _static_model("mixed")
+    d = synth.static_tracks_device(600, n=4096, seed=11, device=DEV)
+    pts, box = d["pts_pm"].transpose(2, 1), d["init_box"]
+    eb.configure_watchdog(trap=False, stress_ns=0)
+    ref = m(pts, box, None)
+    torch.cuda.synchronize()
+    try:
+        eb.configure_watchdog(trap=False, stress_ns=stress_ns)
+        for it in range(4):
             out = m(pts, box, None)
             torch.cuda.synchronize()
             eb.check_abort("stress iteration %d" % it)

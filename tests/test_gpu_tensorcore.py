@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import emulate_chain_bf16, emulate_seg_bf16, emulate_seg_mixed, fold_state_dict, rel_err, spec, synth  # noqa: E402
+from helpers import (bf16x2_round, emulate_chain_bf16, emulate_seg_bf16, emulate_seg_mixed, f16_round, fold_state_dict, rel_err, spec,
+                     synth)  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -208,6 +209,34 @@ def _fp64_seg(fw, x):
     for nm in ("dconv2", "dconv3", "dconv4"):
         d = torch.relu(d @ fw[nm][0].double().t() + fw[nm][1].double())
     return d @ fw["dconv5"][0].double().t() + fw["dconv5"][1].double(), g
+
+
+@pytest.mark.parametrize("kind,block,table,C,n,bs", [
+    ("static_one", "box_est", "static_est_layers", 3, 512, 5),
+    ("dynamic", "point_emb", "point_emb_layers", 4, 2560, 3),
+    ("dynamic", "box_emb", "box_emb_layers", 8, 101, 7),
+    ("static_one", "box_est", "static_est_layers", 3, 130, 300),
+])
+def test_split_chain_trunk_with_fp16_last_layer(kind, block, table, C, n, bs):
+    """The single-tile trunk kernel with its max-pooled last layer as one fp16 MMA per product (last_f16): against a float64
+    evaluation with that layer's operands rounded to fp16 and against plain float64."""
+    sd = synth.random_state_dict(kind, seed=5)
+    fw = fold_state_dict(sd, block, getattr(spec, table)())
+    torch.manual_seed(0)
+    x = torch.randn(bs, n, C).transpose(2, 1)
+    h = x.transpose(2, 1).float()
+    o = torch.relu(h @ fw["conv1"][0].t() + fw["conv1"][1])
+    for nm in ("conv2", "conv3"):
+        o = torch.relu(bf16x2_round(o).double() @ bf16x2_round(fw[nm][0]).double().t() + fw[nm][1]).float()
+    emu = torch.relu((f16_round(o).double() @ f16_round(fw["conv4"][0]).double().t()).max(dim=1)[0] + fw["conv4"][1])
+    fwd = _dev(fw)
+    pack = es.pack_trunk(fwd, last_f16=True)
+    assert pack.struct.last_f16 == 1
+    got = es.chain_maxpool(pack, x.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_err(got.cpu(), emu) < 5e-4, rel_err(got.cpu(), emu)
+    assert rel_err(got.cpu(), _fp32_chain(fw, ["conv1", "conv2", "conv3", "conv4"], x)) < 1e-3
+    assert torch.equal(got, es.chain_maxpool(pack, x.to(DEV).contiguous()))
 
 
 def test_mixed_mode_saturates_above_the_fp16_range():

@@ -21,7 +21,7 @@ def test_chunk_schedule_covers_all_tracks_once(T, chunk, first):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "mixed", "bf16"])
 def test_label_host_equals_label_device(prec):
     dev = "cuda:0"
     T = 150                                                                  # not a multiple of the chunk sizes
