@@ -1,3 +1,10 @@
 cd /root/repo
-timeout 60 python -m pytest tests/test_pipeline.py tests/test_gpu_graphs.py -q -m gpu -k "mixed or pipeline" > gpurun_out/f6_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/f6_tests.log
-timeout 40 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/f6_smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/f6_smoke.log
+timeout 38 python bench.py --steps 10 --no-configs --no-crop --no-cpu-baseline > gpurun_out/f7_bench.json 2> gpurun_out/f7_bench.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+try:
+    d=json.loads(open("gpurun_out/f7_bench.json").read().strip().splitlines()[-1])
+    print(d["value"], d["ms_per_step"], d["kernel_ms"], d["clocks"], d["e2e"])
+    print({k:(v["value"],v["ms_per_step"]) for k,v in d.items() if k in ("bf16x3_mode","fast_mode") and v})
+except Exception as e: print("ERR", e)
+PY
