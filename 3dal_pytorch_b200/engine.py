@@ -11,8 +11,9 @@ Precision modes (attribute ``precision`` of the models; default "mixed", environ
             BASELINE.json); a mask bit can differ only where |l1 - l0| is inside that error.  The tightest tensor-core mode.
   "mixed"   bf16x3, except that the two widest layers of the segmentation net (conv5 128->1024 and dconv2 512->256, 73 % of
             its MACs) multiply IEEE fp16 operands: conv5 with one MMA per product, dconv2 with fp16 hi+lo activations x fp16
-            weights (two).  63 % of the MMAs of bf16x3; logits within ~4e-4 of max|ref| (inside the 1e-3 bar with less
-            margin), activations above 65504 saturate in those two layers (csrc/chain_split.cu, engine_split.mixed).  The default:
+            weights (two); the max-pooled last layer of the box-head / embedding trunks with one fp16 MMA as well.  63 % of
+            the MMAs of bf16x3; logits within ~4e-4 of max|ref|, head outputs within ~1e-4 (inside the 1e-3 bar with less
+            margin), activations above 65504 saturate in those layers (csrc/chain_split.cu, engine_split.mixed).  The default:
             1.4x the throughput of bf16x3 inside the same tolerance.
   "bf16"    one bf16 MMA per product (csrc/chain_bf16.cu): 2.9x faster, logits within ~2e-2, ~1 % of the mask bits
             differ from the fp32 reference -- a throughput mode that does NOT meet the 1e-3 bar.

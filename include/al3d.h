@@ -404,8 +404,9 @@ int al3d_seg_pass2_bf16(const al3d_pass2_weights *w, const float *x, int64_t sb,
  * "mixed" mode (last_f16 / d2_mode below): the two widest layers of PointNetInstanceSeg -- conv5 128 -> 1024
  * (tools/static_model.py:283) and dconv2 512 -> 256 (:290), 73 % of the network's MACs -- multiply IEEE fp16 operands
  * (11 significant bits, fp32 accumulation) with one / two MMAs per product instead of three; every other layer stays
- * bf16x3.  Logits within ~4e-4 of the fp32 reference (profiles/r2_precision_study_mixed.txt).  Activations above the
- * fp16 range (65504) saturate in those two layers.
+ * bf16x3; the box-head / embedding trunks may run their max-pooled last layer the same way (last_f16 with pair = 0).
+ * Logits within ~4e-4 of the fp32 reference (profiles/r2_precision_study_mixed.txt).  Activations above the fp16 range
+ * (65504) saturate in those layers.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct al3d_split_chain_weights {
     int32_t c_in;            /* input channels (1..8)                                                          */
@@ -415,8 +416,8 @@ typedef struct al3d_split_chain_weights {
     int32_t last;            /* width of the max-pooled last layer (multiple of 128, <= 1024)                   */
     int32_t n_blocks;        /* number of 16 KB slots in wstream                                                */
     int32_t pair;            /* 1: the last layer runs on pairs of 128-point tiles (its input must fit 128 KB)  */
-    int32_t last_f16;        /* pair = 1 only.  1: the last layer multiplies IEEE fp16 operands, ONE MMA per product
-                                (its blocks are single fp16 slots, no lo slot): the "mixed" mode, see below          */
+    int32_t last_f16;        /* 1: the max-pooled last layer multiplies IEEE fp16 operands, ONE MMA per product (its
+                                blocks are single fp16 slots, no lo slot): the "mixed" mode, see above               */
     const float *w0_w;       /* (8, w0) fp32, transposed, zero rows for c >= c_in                               */
     const float *w0_b;       /* (w0)                                                                            */
     const float *mid_b;      /* concatenated fp32 biases of the mid layers                                      */
