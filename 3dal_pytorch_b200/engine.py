@@ -15,7 +15,7 @@ Precision modes (attribute ``precision`` of the models; default "mixed", environ
             the MMAs of bf16x3; logits within ~4e-4 of max|ref|, head outputs within ~1e-4 (inside the 1e-3 bar with less
             margin), activations above 65504 saturate in those layers (csrc/chain_split.cu, engine_split.mixed).  The default:
             1.4x the throughput of bf16x3 inside the same tolerance.
-  "bf16"    one bf16 MMA per product (csrc/chain_bf16.cu): 2.9x faster, logits within ~2e-2, ~1 % of the mask bits
+  "bf16"    one bf16 MMA per product (csrc/chain_bf16.cu): 1.8x the throughput of "mixed", logits within ~2e-2, ~1 % of the mask bits
             differ from the fp32 reference -- a throughput mode that does NOT meet the 1e-3 bar.
   "fp32"    every MLP layer in the fp32 SIMT kernels (csrc/linear_f32.cu): ~5e-6, the slowest.
 In all modes the FC heads, the global-feature GEMV and the last 128->2 segmentation layer are fp32.
